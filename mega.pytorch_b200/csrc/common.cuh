@@ -1,0 +1,235 @@
+// Common device/host helpers for the sm_100a kernels of the MEGA hot path.
+// Everything here is inline PTX for Blackwell (tcgen05 / TMEM / TMA / mbarrier);
+// there is no dependency on CUTLASS or torch.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MEGA_OK 0
+#define MEGA_ERR_ARG 1
+#define MEGA_ERR_CUDA 2
+#define MEGA_ERR_UNSUPPORTED 3
+
+#define MEGA_CUDA_CHECK(expr)                                                      \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      mega_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                 \
+                     cudaGetErrorString(_e));                                      \
+      return MEGA_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+#define MEGA_ARG_CHECK(cond, ...)                                                  \
+  do {                                                                             \
+    if (!(cond)) {                                                                 \
+      mega_set_error(__VA_ARGS__);                                                 \
+      return MEGA_ERR_ARG;                                                         \
+    }                                                                              \
+  } while (0)
+
+// error string shared by every translation unit (defined in api.cu)
+void mega_set_error(const char* fmt, ...);
+
+static inline int mega_ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+namespace mega {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---------------------------------------------------------------- mbarrier --
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded wait: a pipeline bug traps after ~2 s instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+#ifndef MEGA_NO_WATCHDOG
+  uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+#endif
+  while (!mbar_try_wait(bar, parity)) {
+#ifndef MEGA_NO_WATCHDOG
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
+      printf("mega: mbarrier wait timeout block(%d,%d,%d) thread %d parity %u\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, parity);
+      __trap();
+    }
+#endif
+  }
+}
+
+// --------------------------------------------------------------------- TMA --
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// ----------------------------------------------------------------- tcgen05 --
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; operands described by 64-bit smem descriptors.
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrive once every MMA issued so far by this thread has completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+          smem_u32(bar))
+      : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread t of the warp receives lane (base+t), columns c..c+31.
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile stored as rows of exactly 128 bytes with the 128B swizzle
+// (what TMA writes for a box whose inner extent is 128 B): 8-row groups are 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);  // start address, 16 B units
+  d |= static_cast<uint64_t>(1) << 16;                  // leading byte offset (unused for SW128 K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;          // stride byte offset: 8 rows * 128 B
+  d |= static_cast<uint64_t>(1) << 46;                  // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                  // layout: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: fp32 accumulate, K-major A and B, M x N tile
+template <int kFormat /*0=f16 1=bf16 2=tf32*/>
+__device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                          // D format = F32
+  d |= static_cast<uint32_t>(kFormat) << 7;   // A format
+  d |= static_cast<uint32_t>(kFormat) << 10;  // B format
+  d |= static_cast<uint32_t>(n >> 3) << 17;
+  d |= static_cast<uint32_t>(m >> 4) << 24;
+  return d;
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+}  // namespace mega
+#endif  // __CUDACC__

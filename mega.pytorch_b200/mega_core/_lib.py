@@ -1,0 +1,87 @@
+"""ctypes binding of libmega_b200.so (the C ABI declared in include/mega_b200.h).
+
+The library is the product: if it is missing or does not load, importing this module raises --
+there is no CPU or PyTorch fallback anywhere in the package.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.environ.get("MEGA_B200_LIB", os.path.join(_PKG_ROOT, "lib", "libmega_b200.so"))
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libmega_b200.so not found at %s -- run `python mega.pytorch_b200/build.py` "
+        "(or __graft_entry__.build()) first; there is no fallback path" % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+c_f32p = ctypes.c_void_p
+c_ll = ctypes.c_longlong
+c_int = ctypes.c_int
+
+
+class ConvGemmDesc(ctypes.Structure):
+    """mirror of `mega_conv_gemm_desc` (include/mega_b200.h)"""
+    _fields_ = [
+        ("a", c_f32p),
+        ("a_n", c_int), ("a_h", c_int), ("a_w", c_int), ("a_c", c_int),
+        ("a_stride_w", c_ll), ("a_stride_h", c_ll), ("a_stride_n", c_ll),
+        ("b", c_f32p),
+        ("b_n", c_int), ("b_k", c_int),
+        ("b_stride_n", c_ll), ("b_stride_tap", c_ll),
+        ("taps_r", c_int), ("taps_s", c_int), ("dil", c_int), ("pad", c_int),
+        ("k_per_tap", c_int),
+        ("out", c_f32p),
+        ("out_ld", c_ll),
+        ("n_img", c_int), ("out_h", c_int), ("out_w", c_int), ("cout", c_int),
+        ("scale", c_f32p), ("bias", c_f32p), ("residual", c_f32p),
+        ("res_ld", c_ll),
+        ("relu", c_int),
+        ("tile_h", c_int), ("tile_w", c_int), ("block_n", c_int),
+        ("batch", c_int),
+        ("a_c_off", c_int), ("a_n_off", c_int), ("b_k_off", c_int), ("b_n_off", c_int),
+        ("out_z_off", c_ll), ("res_z_off", c_ll),
+        ("splits", c_int),
+        ("partial", c_f32p),
+    ]
+
+
+lib.mega_last_error.restype = ctypes.c_char_p
+lib.mega_abi_version.restype = c_int
+lib.mega_device_ok.restype = c_int
+lib.mega_conv_gemm_tf32.argtypes = [ctypes.POINTER(ConvGemmDesc), ctypes.c_void_p]
+lib.mega_conv_gemm_tf32.restype = c_int
+lib.mega_set_tf32_rounding.argtypes = [c_int]
+lib.mega_set_tf32_rounding.restype = c_int
+
+
+class MegaError(RuntimeError):
+    pass
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib.mega_last_error().decode("utf-8", "replace")
+        raise MegaError("%s failed (status %d): %s" % (what or "libmega_b200 call", status, msg))
+
+
+def stream_ptr():
+    """cudaStream_t of torch's current stream, as an integer for ctypes."""
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise MegaError("libmega_b200 ops take CUDA tensors only (got a %s tensor); "
+                            "the B200 path has no CPU fallback" % t.device)
