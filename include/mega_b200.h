@@ -64,6 +64,7 @@ typedef struct mega_conv_gemm_desc {
   int a_c_off, a_n_off; /* added to A's channel / image coordinate, times batch index */
   int b_k_off, b_n_off; /* added to B's k / row coordinate, times batch index */
   long long out_z_off, res_z_off;
+  int bias_z_off; /* added to the scale/bias index, times batch index */
   /* split-K (batch must be 1): partial is [splits][n_img*out_h*out_w][cout] floats */
   int splits;
   float* partial;
@@ -72,6 +73,85 @@ typedef struct mega_conv_gemm_desc {
 int mega_conv_gemm_tf32(const mega_conv_gemm_desc* desc, void* stream);
 /* TMA fp32->tf32 conversion on load (round-to-nearest) on/off; returns the previous value. */
 int mega_set_tf32_rounding(int enable);
+
+/* ------------------------------------------------------------------- NMS
+ * Greedy NMS, "+1" pixel convention, suppress when IoU > thresh; keep_out receives the kept
+ * ORIGINAL indices in ascending order, *count_out their number (both device memory).
+ * Replaces `_C.nms` -> nms_cuda (csrc/nms.h:10-28, csrc/cuda/nms.cu:70-131). n <= 8192.
+ * Equal scores are ordered by ascending index (the reference leaves ties unspecified). */
+long long mega_nms_workspace_bytes(int n);
+int mega_nms(const float* boxes /*[n,4]*/, const float* scores /*[n]*/, int n, float thresh, void* workspace,
+             long long workspace_bytes, long long* keep_out /*[n]*/, int* count_out, void* stream);
+
+/* ------------------------------------------------------- RPN proposal selection
+ * sigmoid -> top-k (sorted) -> decode -> clip -> remove-small -> NMS -> first post_nms, per image.
+ * Replaces RPNPostProcessor.forward_for_single_feature_map (modeling/rpn/inference.py:76-123),
+ * BoxCoder.decode (modeling/box_coder.py:52-95), AnchorGenerator.grid_anchors
+ * (modeling/rpn/anchor_generator.py:73-95; anchors are generated in-kernel from base_anchors).
+ * head: NHWC rows of `ld` floats per cell: [0,A) objectness logits, [A,5A) deltas (a*4+c).
+ * Outputs (per image, padded with zeros): out_boxes [n_img,post,4], out_scores [n_img,post],
+ * out_anchor [n_img,post] (anchor index of each proposal, may be NULL), out_count [n_img]. */
+long long mega_rpn_select_workspace_bytes(int n_img, int h, int w, int num_anchors, int pre_nms);
+int mega_rpn_select(const float* head, long long head_img_stride, int ld, int n_img, int h, int w, int num_anchors,
+                    int stride, const float* base_anchors, float im_w, float im_h, int pre_nms, int post_nms,
+                    float nms_thresh, float min_size, void* workspace, long long workspace_bytes, float* out_boxes,
+                    float* out_scores, int* out_anchor, int* out_count, void* stream);
+
+/* ------------------------------------------------------------------- ROIAlign
+ * Replaces `_C.roi_align_forward` (csrc/ROIAlign.h:11-25, csrc/cuda/ROIAlign_cuda.cu:257-299).
+ * _nchw: reference layout (NCHW in, rois [K,5]=(batch,x1,y1,x2,y2), out [K,C,ph,pw]).
+ * _nhwc: engine layout (NHWC in, out [K, ph*pw, C]); rois rows of roi_ld floats with the box at
+ *        roi_box_off (roi_box_off < 0: packed [K,5] like the reference), batch index from
+ *        roi_batch (int32, may be NULL = image 0). */
+int mega_roi_align_forward_nchw(const float* input, int batch, int channels, int height, int width,
+                                const float* rois, int num_rois, float spatial_scale, int pooled_h, int pooled_w,
+                                int sampling_ratio, float* output, void* stream);
+int mega_roi_align_forward_nhwc(const float* input, int channels, int height, int width, long long in_img_stride,
+                                const float* rois, int roi_ld, int roi_box_off, const int* roi_batch, int num_rois,
+                                float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, float* output,
+                                long long out_roi_stride, void* stream);
+
+/* --------------------------------------------------------- backbone helpers
+ * stem_im2col: NCHW image [N,3,H,W] -> [N, Ho*Wo, kpad] rows (k = c*49 + r*7 + s, zero padded) for
+ * BaseStem.conv1 (7x7/2, pad 3; modeling/backbone/resnet.py:347-366); maxpool: F.max_pool2d(3,2,1)
+ * in NHWC (resnet.py:365). */
+int mega_stem_im2col(const float* input, int n_img, int height, int width, int kpad, float* out, void* stream);
+int mega_maxpool3x3s2_nhwc(const float* input, int n_img, int height, int width, int channels, float* out,
+                           void* stream);
+/* dst[i,:] = src[idx[i],:] (idx[i] < 0 -> zeros): replaces the per-frame torch.cat of the window /
+ * memory deques (detector/generalized_rcnn_mega.py:213-216, roi_box_feature_extractors.py:674-688). */
+int mega_gather_rows(const float* src, long long src_ld, const int* idx, int n_rows, int row_len, float* dst,
+                     long long dst_ld, void* stream);
+/* general form: dst[dst_idx ? dst_idx[i] : i, :] = src[src_idx ? src_idx[i] : i, :] (negative source index ->
+ * zeros, negative destination index -> skipped): ring-buffer pushes of the window and the long-range memory. */
+int mega_copy_rows(const float* src, long long src_ld, const int* src_idx, float* dst, long long dst_ld,
+                   const int* dst_idx, int n_rows, int row_len, void* stream);
+/* per image [rows, cols] -> [cols, rows] (NCHW <-> NHWC at the module boundary). */
+int mega_transpose_2d(const float* input, int n_img, int rows, int cols, float* out, void* stream);
+
+/* ------------------------------------------------------ relation-module soft-max
+ * In place over logits [16][n_rows][ldm] (raw q.k, incl. the `u` term folded into q):
+ *   p = softmax_m( log(relu(Wg.emb(box_q[n], box_k[m]) + bg) + 1e-6) + scale * logits )
+ * with emb the 64-d sin/cos position embedding; boxes_q == NULL drops the position term.
+ * Replaces extract_position_matrix / extract_position_embedding / the Wg conv / softmax of
+ * roi_heads/box_head/roi_box_feature_extractors.py:125-176, :593-597, :624-633.
+ * Keys m >= *m_valid_ptr (or m_host) get probability 0; query rows n with
+ * *n_valid_ptr <= n < n_valid_off are padding and are skipped. dim_mat = 1000^(k/8), k=0..7. */
+int mega_relation_softmax(float* logits, int n_rows, int ldm, const float* boxes_q, const float* boxes_k,
+                          const float* wg, const float* bg, const float* dim_mat, const int* m_valid_ptr, int m_host,
+                          const int* n_valid_ptr, int n_valid_off, float scale, void* stream);
+
+/* ------------------------------------------------------ box-head post-processing
+ * softmax -> decode (weights wx..wh) -> clip -> per-class score threshold + NMS -> top max_det.
+ * Replaces PostProcessor.forward / filter_results (roi_heads/box_head/inference.py:45-149).
+ * Outputs in the reference's order (class by class, proposal index ascending):
+ * out_boxes [out_cap,4], out_scores [out_cap], out_labels [out_cap] (int64), *out_count. */
+long long mega_box_postprocess_workspace_bytes(int r_max, int num_classes);
+int mega_box_postprocess(const float* logits, int ld_logits, const float* deltas, int ld_deltas,
+                         const float* proposals, const int* count_ptr, int r_max, int num_classes, float im_w,
+                         float im_h, float score_thresh, float nms_thresh, int max_det, float wx, float wy, float ww,
+                         float wh, void* workspace, long long workspace_bytes, float* out_boxes, float* out_scores,
+                         long long* out_labels, int out_cap, int* out_count, void* stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,7 @@ struct ConvGemmParams {
   int a_c_off, a_n_off, b_k_off, b_n_off;
   long long out_z_off;
   long long res_z_off;
+  int bias_z_off;
   int splits;
   float* partial;  // [splits][M_total][cout] when splits > 1
 };
@@ -181,7 +182,9 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       out_row = p.out + batch * p.out_z_off + pix * p.out_ld;
       if (p.residual) res_row = p.residual + batch * p.res_z_off + pix * p.res_ld;
     }
-    const bool vec_ok = ((p.cout & 3) == 0) && ((reinterpret_cast<uintptr_t>(out_row) & 15) == 0) &&
+    const float* scale_p = p.scale ? p.scale + batch * p.bias_z_off : nullptr;
+    const float* bias_p = p.bias ? p.bias + batch * p.bias_z_off : nullptr;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_row) & 15) == 0) &&
                         (res_row == nullptr || (reinterpret_cast<uintptr_t>(res_row) & 15) == 0);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
@@ -216,12 +219,12 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (n + 3 < p.cout && vec_ok) {
           float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
                                  __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
-          if (p.scale) {
-            const float4 sc = ldg_f4(p.scale + n);
+          if (scale_p) {
+            const float4 sc = ldg_f4(scale_p + n);
             v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
           }
-          if (p.bias) {
-            const float4 bi = ldg_f4(p.bias + n);
+          if (bias_p) {
+            const float4 bi = ldg_f4(bias_p + n);
             v.x += bi.x; v.y += bi.y; v.z += bi.z; v.w += bi.w;
           }
           if (res_row) {
@@ -236,8 +239,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int t = 0; t < 4; ++t) {
             if (n + t < p.cout) {
               float v = __uint_as_float(acc[j + t]);
-              if (p.scale) v *= __ldg(p.scale + n + t);
-              if (p.bias) v += __ldg(p.bias + n + t);
+              if (scale_p) v *= __ldg(scale_p + n + t);
+              if (bias_p) v += __ldg(bias_p + n + t);
               if (res_row) v += __ldg(res_row + n + t);
               if (p.relu) v = fmaxf(v, 0.f);
               out_row[n + t] = v;
@@ -410,6 +413,7 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
   p.b_n_off = d->b_n_off;
   p.out_z_off = d->out_z_off;
   p.res_z_off = d->res_z_off;
+  p.bias_z_off = d->bias_z_off;
   p.splits = d->splits;
   p.partial = d->partial;
 

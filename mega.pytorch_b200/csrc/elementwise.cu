@@ -1,0 +1,196 @@
+// Memory-bound helpers of the backbone and the window/memory plumbing:
+//   * stem im2col (7x7 / stride 2 / pad 3 over the NCHW input image -> K-major GEMM operand),
+//     feeding the tcgen05 GEMM for BaseStem.conv1 (modeling/backbone/resnet.py:347-366);
+//   * 3x3 / stride 2 / pad 1 max-pool in NHWC (resnet.py:365);
+//   * row gather (replaces the torch.cat of 25-deep deques every frame,
+//     detector/generalized_rcnn_mega.py:213-216 and roi_box_feature_extractors.py:674-688);
+//   * NCHW <-> NHWC converters for the module-API boundary.
+// All are pure bandwidth kernels: 128-bit accesses, grid-stride, one pass.
+#include "common.cuh"
+#include "mega_b200.h"
+
+namespace mega {
+
+// out[n][oh*Wo+ow][k], k = c*49 + r*7 + s for k < 147 (matches weight.view(64,147)), zero for k >= 147
+__global__ void stem_im2col_kernel(const float* __restrict__ in, int n_img, int height, int width, int ho, int wo,
+                                   int kpad, float* __restrict__ out) {
+  const int groups = kpad / 4;
+  const long long total = static_cast<long long>(n_img) * ho * wo * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int grp = static_cast<int>(i % groups);
+    const long long pix = i / groups;
+    const int ow = static_cast<int>(pix % wo);
+    const int oh = static_cast<int>((pix / wo) % ho);
+    const int n = static_cast<int>(pix / (static_cast<long long>(wo) * ho));
+    float v[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int k = grp * 4 + t;
+      float val = 0.f;
+      if (k < 147) {
+        const int c = k / 49, rs = k - c * 49, r = rs / 7, s = rs - r * 7;
+        const int ih = oh * 2 - 3 + r, iw = ow * 2 - 3 + s;
+        if (ih >= 0 && ih < height && iw >= 0 && iw < width)
+          val = __ldg(in + ((static_cast<long long>(n) * 3 + c) * height + ih) * width + iw);
+      }
+      v[t] = val;
+    }
+    *reinterpret_cast<float4*>(out + pix * kpad + grp * 4) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+__global__ void maxpool3x3s2_nhwc_kernel(const float* __restrict__ in, int n_img, int height, int width, int channels,
+                                         int ho, int wo, float* __restrict__ out) {
+  const int cg = channels / 4;
+  const long long total = static_cast<long long>(n_img) * ho * wo * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % cg);
+    const long long pix = i / cg;
+    const int ow = static_cast<int>(pix % wo);
+    const int oh = static_cast<int>((pix / wo) % ho);
+    const int n = static_cast<int>(pix / (static_cast<long long>(wo) * ho));
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= height) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= width) continue;
+        const float4 v = ldg_f4(in + ((static_cast<long long>(n) * height + ih) * width + iw) * channels + c4 * 4);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    *reinterpret_cast<float4*>(out + pix * channels + c4 * 4) = m;
+  }
+}
+
+// dst[didx ? didx[i] : i, :] = src[idx ? idx[i] : i, :] (source index < 0 -> zeros, destination
+// index < 0 -> row skipped); row_len multiple of 4
+__global__ void gather_rows_kernel(const float* __restrict__ src, long long src_ld, const int* __restrict__ idx,
+                                   int n_rows, int row_len, float* __restrict__ dst, long long dst_ld,
+                                   const int* __restrict__ didx) {
+  const int vec = row_len / 4;
+  const long long total = static_cast<long long>(n_rows) * vec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / vec), c = static_cast<int>(i - static_cast<long long>(r) * vec);
+    const int s = idx ? idx[r] : r;
+    const int d = didx ? didx[r] : r;
+    if (d < 0) continue;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s >= 0) v = ldg_f4(src + static_cast<long long>(s) * src_ld + c * 4);
+    *reinterpret_cast<float4*>(dst + static_cast<long long>(d) * dst_ld + c * 4) = v;
+  }
+}
+
+// same, element-wise, for rows that are not a multiple of 4 floats (e.g. per-frame counters)
+__global__ void gather_rows_scalar_kernel(const float* __restrict__ src, long long src_ld, const int* __restrict__ idx,
+                                          int n_rows, int row_len, float* __restrict__ dst, long long dst_ld,
+                                          const int* __restrict__ didx) {
+  const long long total = static_cast<long long>(n_rows) * row_len;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / row_len), c = static_cast<int>(i - static_cast<long long>(r) * row_len);
+    const int s = idx ? idx[r] : r;
+    const int d = didx ? didx[r] : r;
+    if (d < 0) continue;
+    dst[static_cast<long long>(d) * dst_ld + c] = (s >= 0) ? src[static_cast<long long>(s) * src_ld + c] : 0.f;
+  }
+}
+
+// tiled transpose of a [rows, cols] matrix per image (rows*cols floats per image)
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const long long img_off = static_cast<long long>(blockIdx.z) * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = in[img_off + static_cast<long long>(r) * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[img_off + static_cast<long long>(c) * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+static int grid_for(long long total, int block) {
+  long long b = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace mega
+
+using namespace mega;
+
+extern "C" int mega_stem_im2col(const float* input, int n_img, int height, int width, int kpad, float* out,
+                                void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(kpad >= 148 && (kpad & 3) == 0, "stem_im2col: kpad must be a multiple of 4 >= 148");
+  const int ho = (height - 1) / 2 + 1, wo = (width - 1) / 2 + 1;
+  const long long total = static_cast<long long>(n_img) * ho * wo * (kpad / 4);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(input, n_img, height, width, ho, wo, kpad, out);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_maxpool3x3s2_nhwc(const float* input, int n_img, int height, int width, int channels, float* out,
+                                      void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK((channels & 3) == 0, "maxpool: channels must be a multiple of 4");
+  const int ho = (height - 1) / 2 + 1, wo = (width - 1) / 2 + 1;
+  const long long total = static_cast<long long>(n_img) * ho * wo * (channels / 4);
+  maxpool3x3s2_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(input, n_img, height, width, channels, ho, wo,
+                                                                     out);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_gather_rows(const float* src, long long src_ld, const int* idx, int n_rows, int row_len,
+                                float* dst, long long dst_ld, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (n_rows == 0) return MEGA_OK;
+  if ((row_len & 3) || (src_ld & 3) || (dst_ld & 3) || (reinterpret_cast<uintptr_t>(src) & 15) ||
+      (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    gather_rows_scalar_kernel<<<grid_for(static_cast<long long>(n_rows) * row_len, 256), 256, 0, stream>>>(
+        src, src_ld, idx, n_rows, row_len, dst, dst_ld, nullptr);
+    MEGA_CUDA_CHECK(cudaGetLastError());
+    return MEGA_OK;
+  }
+  const long long total = static_cast<long long>(n_rows) * (row_len / 4);
+  gather_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, src_ld, idx, n_rows, row_len, dst, dst_ld,
+                                                               nullptr);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_copy_rows(const float* src, long long src_ld, const int* src_idx, float* dst, long long dst_ld,
+                              const int* dst_idx, int n_rows, int row_len, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (n_rows == 0) return MEGA_OK;
+  if ((row_len & 3) || (src_ld & 3) || (dst_ld & 3) || (reinterpret_cast<uintptr_t>(src) & 15) ||
+      (reinterpret_cast<uintptr_t>(dst) & 15)) {
+    gather_rows_scalar_kernel<<<grid_for(static_cast<long long>(n_rows) * row_len, 256), 256, 0, stream>>>(
+        src, src_ld, src_idx, n_rows, row_len, dst, dst_ld, dst_idx);
+    MEGA_CUDA_CHECK(cudaGetLastError());
+    return MEGA_OK;
+  }
+  const long long total = static_cast<long long>(n_rows) * (row_len / 4);
+  gather_rows_kernel<<<grid_for(total, 256), 256, 0, stream>>>(src, src_ld, src_idx, n_rows, row_len, dst, dst_ld,
+                                                               dst_idx);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+// per image: in [rows, cols] -> out [cols, rows]; NCHW->NHWC is rows=C, cols=H*W
+extern "C" int mega_transpose_2d(const float* input, int n_img, int rows, int cols, float* out, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (n_img == 0 || rows == 0 || cols == 0) return MEGA_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, n_img), block(32, 8);
+  transpose_kernel<<<grid, block, 0, stream>>>(input, rows, cols, out);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}

@@ -1,0 +1,213 @@
+// Relation-module softmax with the geometric position bias generated on the fly.
+//
+// Reference (mega_core/modeling/roi_heads/box_head/roi_box_feature_extractors.py):
+//   extract_position_matrix :146-176, extract_position_embedding :125-144 (materialises a
+//   [1,64,N,M] fp32 tensor -- 648 MB at N=675, M=3750), Wg 1x1 conv + ReLU :593-597,
+//   weighted_aff = log(aff_weight + 1e-6) + aff/sqrt(64) :624-632, softmax over M :633.
+// Here nothing of that is materialised: for every (query n, key m) pair the four log-ratios,
+// the 64 sin/cos features, the 64->16 projection, ReLU, log and the scaled logit are computed in
+// registers and the soft-max is taken in place over the [G,N,M] logits produced by the
+// tcgen05 Q.K^T GEMM. One CTA per query row; three light passes over its [16,M] slice (L2-resident):
+// logits + max, exp + sum, normalise.
+#include "common.cuh"
+#include "mega_b200.h"
+
+namespace mega {
+
+constexpr int kGroups = 16;
+constexpr int kEmb = 64;
+constexpr int kRelThreads = 256;
+
+struct RelParams {
+  float* s;                 // [G][N][ldm] logits in, probabilities out
+  long long head_stride;    // N * ldm
+  int ldm;
+  const float* boxes_q;     // [N,4] or NULL (no position term)
+  const float* boxes_k;     // [M,4]
+  const float* wg;          // [16,64] (Wgs[i].weight) or NULL
+  const float* bg;          // [16]
+  const float* inv_dim;     // [8]: 1 / 1000^(k/8)  (divisors, passed as the reference's dim_mat)
+  const int* m_valid_ptr;   // device scalar: number of valid keys (<= ldm), or NULL -> m_host
+  int m_host;
+  const int* n_valid_ptr;   // rows >= *n_valid_ptr are skipped (padding rows of the key frame), or NULL
+  int n_valid_off;          // rows in [n_valid, n_valid_off) are padding; rows >= n_valid_off are live
+  float scale;
+};
+
+__global__ void __launch_bounds__(kRelThreads)
+relation_softmax_kernel(const RelParams p) {
+  __shared__ float wg_s[kEmb][kGroups];  // e-major so the 16 group weights of one feature are contiguous
+  __shared__ float bg_s[kGroups];
+  __shared__ float dim_s[8];
+  __shared__ float red_max[kRelThreads / 32][kGroups];
+  __shared__ float red_sum[kRelThreads / 32][kGroups];
+  __shared__ float fin_max[kGroups], fin_inv[kGroups];
+
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int m_valid = p.m_valid_ptr ? min(*p.m_valid_ptr, p.ldm) : p.m_host;
+  if (p.n_valid_ptr) {
+    const int nv = *p.n_valid_ptr;
+    if (n >= nv && n < p.n_valid_off) return;  // padding query row: nothing downstream reads it
+  }
+  const bool has_pe = (p.boxes_q != nullptr);
+  if (has_pe) {
+    for (int i = tid; i < kEmb * kGroups; i += blockDim.x) {
+      const int g = i / kEmb, e = i - g * kEmb;
+      wg_s[e][g] = p.wg[i];
+    }
+    if (tid < kGroups) bg_s[tid] = p.bg[tid];
+    if (tid < 8) dim_s[tid] = p.inv_dim[tid];
+  }
+  __syncthreads();
+
+  float qw = 1.f, qh = 1.f, qcx = 0.f, qcy = 0.f;
+  if (has_pe) {
+    const float4 q = *reinterpret_cast<const float4*>(p.boxes_q + static_cast<long long>(n) * 4);
+    qw = __fadd_rn(__fsub_rn(q.z, q.x), 1.f);
+    qh = __fadd_rn(__fsub_rn(q.w, q.y), 1.f);
+    qcx = __fmul_rn(0.5f, __fadd_rn(q.x, q.z));
+    qcy = __fmul_rn(0.5f, __fadd_rn(q.y, q.w));
+  }
+  float* srow = p.s + static_cast<long long>(n) * p.ldm;
+
+  float mx[kGroups];
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) mx[g] = -INFINITY;
+
+  // ---- pass 1: logits (+ position bias), running max per head
+  for (int m = tid; m < m_valid; m += blockDim.x) {
+    float bias[kGroups];
+    if (has_pe) {
+      const float4 k = *reinterpret_cast<const float4*>(p.boxes_k + static_cast<long long>(m) * 4);
+      const float kw = __fadd_rn(__fsub_rn(k.z, k.x), 1.f);
+      const float kh = __fadd_rn(__fsub_rn(k.w, k.y), 1.f);
+      const float kcx = __fmul_rn(0.5f, __fadd_rn(k.x, k.z));
+      const float kcy = __fmul_rn(0.5f, __fadd_rn(k.y, k.w));
+      float delta[4];
+      delta[0] = logf(__fadd_rn(fabsf(__fdiv_rn(__fsub_rn(qcx, kcx), qw)), 1e-3f));
+      delta[1] = logf(__fadd_rn(fabsf(__fdiv_rn(__fsub_rn(qcy, kcy), qh)), 1e-3f));
+      delta[2] = logf(__fdiv_rn(qw, kw));
+      delta[3] = logf(__fdiv_rn(qh, kh));
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) bias[g] = bg_s[g];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float d100 = __fmul_rn(delta[c], 100.0f);
+#pragma unroll
+        for (int kf = 0; kf < 8; ++kf) {
+          const float arg = __fdiv_rn(d100, dim_s[kf]);
+          float sv, cv;
+          sincosf(arg, &sv, &cv);
+          const float4* ws = reinterpret_cast<const float4*>(&wg_s[c * 16 + kf][0]);
+          const float4* wc = reinterpret_cast<const float4*>(&wg_s[c * 16 + 8 + kf][0]);
+#pragma unroll
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 a = ws[g4], b = wc[g4];
+            bias[g4 * 4 + 0] = fmaf(a.x, sv, fmaf(b.x, cv, bias[g4 * 4 + 0]));
+            bias[g4 * 4 + 1] = fmaf(a.y, sv, fmaf(b.y, cv, bias[g4 * 4 + 1]));
+            bias[g4 * 4 + 2] = fmaf(a.z, sv, fmaf(b.z, cv, bias[g4 * 4 + 2]));
+            bias[g4 * 4 + 3] = fmaf(a.w, sv, fmaf(b.w, cv, bias[g4 * 4 + 3]));
+          }
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) bias[g] = logf(__fadd_rn(fmaxf(bias[g], 0.f), 1e-6f));
+    } else {
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) bias[g] = 0.f;
+    }
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      float* sp = srow + g * p.head_stride + m;
+      const float l = __fadd_rn(bias[g], __fmul_rn(p.scale, *sp));
+      *sp = l;
+      mx[g] = fmaxf(mx[g], l);
+    }
+  }
+
+  // ---- block reduction of the max per head
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {
+    float m_ = mx[g];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m_ = fmaxf(m_, __shfl_xor_sync(0xffffffffu, m_, off));
+    if (lane == 0) red_max[warp][g] = m_;
+  }
+  __syncthreads();
+  if (tid < kGroups) {
+    float m_ = -INFINITY;
+    for (int w = 0; w < kRelThreads / 32; ++w) m_ = fmaxf(m_, red_max[w][tid]);
+    fin_max[tid] = m_;
+  }
+  __syncthreads();
+
+  // ---- pass 2: exact two-pass soft-max (sum of exp(l - max) recomputed, like torch softmax)
+  float part[kGroups];
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) part[g] = 0.f;
+  for (int m = tid; m < m_valid; m += blockDim.x) {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      float* sp = srow + g * p.head_stride + m;
+      const float e = expf(__fsub_rn(*sp, fin_max[g]));
+      *sp = e;
+      part[g] += e;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {
+    float s_ = part[g];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s_ += __shfl_xor_sync(0xffffffffu, s_, off);
+    if (lane == 0) red_sum[warp][g] = s_;
+  }
+  __syncthreads();
+  if (tid < kGroups) {
+    float s_ = 0.f;
+    for (int w = 0; w < kRelThreads / 32; ++w) s_ += red_sum[w][tid];
+    fin_inv[tid] = s_;
+  }
+  __syncthreads();
+  for (int m = tid; m < p.ldm; m += blockDim.x) {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      float* sp = srow + g * p.head_stride + m;
+      *sp = (m < m_valid) ? __fdiv_rn(*sp, fin_inv[g]) : 0.f;
+    }
+  }
+}
+
+}  // namespace mega
+
+using namespace mega;
+
+extern "C" int mega_relation_softmax(float* logits, int n_rows, int ldm, const float* boxes_q, const float* boxes_k,
+                                     const float* wg, const float* bg, const float* dim_mat, const int* m_valid_ptr,
+                                     int m_host, const int* n_valid_ptr, int n_valid_off, float scale,
+                                     void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(logits != nullptr && n_rows >= 0 && ldm > 0, "relation_softmax: bad arguments");
+  MEGA_ARG_CHECK((boxes_q == nullptr) || (boxes_k && wg && bg && dim_mat),
+                 "relation_softmax: position term needs boxes_k, wg, bg and dim_mat");
+  MEGA_ARG_CHECK(m_valid_ptr != nullptr || (m_host >= 0 && m_host <= ldm), "relation_softmax: m out of range");
+  if (n_rows == 0) return MEGA_OK;
+  RelParams p;
+  p.s = logits;
+  p.head_stride = static_cast<long long>(n_rows) * ldm;
+  p.ldm = ldm;
+  p.boxes_q = boxes_q;
+  p.boxes_k = boxes_k;
+  p.wg = wg;
+  p.bg = bg;
+  p.inv_dim = dim_mat;
+  p.m_valid_ptr = m_valid_ptr;
+  p.m_host = m_host;
+  p.n_valid_ptr = n_valid_ptr;
+  p.n_valid_off = n_valid_off;
+  p.scale = scale;
+  relation_softmax_kernel<<<n_rows, kRelThreads, 0, stream>>>(p);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}

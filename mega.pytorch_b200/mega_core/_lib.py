@@ -45,6 +45,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("batch", c_int),
         ("a_c_off", c_int), ("a_n_off", c_int), ("b_k_off", c_int), ("b_n_off", c_int),
         ("out_z_off", c_ll), ("res_z_off", c_ll),
+        ("bias_z_off", c_int),
         ("splits", c_int),
         ("partial", c_f32p),
     ]
@@ -85,3 +86,45 @@ def require_cuda(*tensors):
         if t is not None and not t.is_cuda:
             raise MegaError("libmega_b200 ops take CUDA tensors only (got a %s tensor); "
                             "the B200 path has no CPU fallback" % t.device)
+
+
+# ---- argtypes of the remaining entry points (include/mega_b200.h)
+_vp, _i, _f, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+lib.mega_nms_workspace_bytes.argtypes = [_i]
+lib.mega_nms_workspace_bytes.restype = _ll
+lib.mega_nms.argtypes = [_vp, _vp, _i, _f, _vp, _ll, _vp, _vp, _vp]
+lib.mega_nms.restype = _i
+lib.mega_rpn_select_workspace_bytes.argtypes = [_i, _i, _i, _i, _i]
+lib.mega_rpn_select_workspace_bytes.restype = _ll
+lib.mega_rpn_select.argtypes = [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _f, _f, _i, _i, _f, _f, _vp, _ll, _vp, _vp,
+                                _vp, _vp, _vp]
+lib.mega_rpn_select.restype = _i
+lib.mega_roi_align_forward_nchw.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _vp]
+lib.mega_roi_align_forward_nchw.restype = _i
+lib.mega_roi_align_forward_nhwc.argtypes = [_vp, _i, _i, _i, _ll, _vp, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _ll, _vp]
+lib.mega_roi_align_forward_nhwc.restype = _i
+lib.mega_stem_im2col.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
+lib.mega_stem_im2col.restype = _i
+lib.mega_maxpool3x3s2_nhwc.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
+lib.mega_maxpool3x3s2_nhwc.restype = _i
+lib.mega_gather_rows.argtypes = [_vp, _ll, _vp, _i, _i, _vp, _ll, _vp]
+lib.mega_gather_rows.restype = _i
+lib.mega_copy_rows.argtypes = [_vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _vp]
+lib.mega_copy_rows.restype = _i
+lib.mega_transpose_2d.argtypes = [_vp, _i, _i, _i, _vp, _vp]
+lib.mega_transpose_2d.restype = _i
+lib.mega_relation_softmax.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp]
+lib.mega_relation_softmax.restype = _i
+lib.mega_box_postprocess_workspace_bytes.argtypes = [_i, _i]
+lib.mega_box_postprocess_workspace_bytes.restype = _ll
+lib.mega_box_postprocess.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _f, _f, _f, _f, _i, _f, _f, _f, _f, _vp, _ll,
+                                     _vp, _vp, _vp, _i, _vp, _vp]
+lib.mega_box_postprocess.restype = _i
+
+EXPORTS = [
+    "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm_tf32", "mega_set_tf32_rounding",
+    "mega_nms_workspace_bytes", "mega_nms", "mega_rpn_select_workspace_bytes", "mega_rpn_select",
+    "mega_roi_align_forward_nchw", "mega_roi_align_forward_nhwc", "mega_stem_im2col", "mega_maxpool3x3s2_nhwc",
+    "mega_gather_rows", "mega_copy_rows", "mega_transpose_2d", "mega_relation_softmax", "mega_box_postprocess_workspace_bytes",
+    "mega_box_postprocess",
+]

@@ -32,8 +32,8 @@ def pick_block_n(cout, m_tiles, batch=1):
 
 def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, residual=None,
               relu=False, tile=None, block_n=None, cout=None, k=None, batch=1, a_c_off=0,
-              a_n_off=0, b_k_off=0, b_n_off=0, out_z_off=0, res_z_off=0, splits=1, partial=None,
-              out_hw=None):
+              a_n_off=0, b_k_off=0, b_n_off=0, out_z_off=0, res_z_off=0, bias_z_off=0, splits=1,
+              partial=None, out_hw=None):
     """out[n,h,w,:] = act(scale * conv(a, w) + bias + residual)   (TF32 tensor cores)
 
     a   : [N,H,W,C] fp32 view (innermost stride 1; other strides multiples of 4 floats)
@@ -75,6 +75,7 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.batch = batch
     d.a_c_off, d.a_n_off, d.b_k_off, d.b_n_off = a_c_off, a_n_off, b_k_off, b_n_off
     d.out_z_off, d.res_z_off = out_z_off, res_z_off
+    d.bias_z_off = bias_z_off
     d.splits = splits
     d.partial = ptr(partial)
     check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
@@ -94,3 +95,150 @@ def linear(x, w, out, *, bias=None, relu=False, residual=None, splits=1, partial
     w3 = w.as_strided((1, nrows, kdim), (w.stride(0) * nrows, w.stride(0), 1))
     return conv_gemm(a4, w3, o4, bias=bias, relu=relu, residual=r4, tile=(1, 128), cout=nrows,
                      splits=splits, partial=partial, block_n=block_n)
+
+
+# --------------------------------------------------------------------------- non-GEMM kernels
+_ws_cache = {}
+
+
+def _workspace(key, nbytes, device):
+    """persistent byte workspace per (kind, device): kernels never allocate device memory."""
+    ws = _ws_cache.get((key, device))
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _ws_cache[(key, device)] = ws
+    return ws
+
+
+def nms_device(boxes, scores, thresh, keep=None, count=None):
+    """-> (keep int64 [n] buffer, count int32 [1]) on the device; no synchronisation."""
+    require_cuda(boxes, scores)
+    n = boxes.shape[0]
+    boxes = boxes.contiguous().float()
+    scores = scores.contiguous().float()
+    if keep is None:
+        keep = torch.empty(max(n, 1), dtype=torch.int64, device=boxes.device)
+    if count is None:
+        count = torch.zeros(1, dtype=torch.int32, device=boxes.device)
+    nbytes = lib.mega_nms_workspace_bytes(n)
+    if nbytes < 0:
+        raise _lib.MegaError("nms: n=%d exceeds the single-pass capacity (8192 boxes)" % n)
+    ws = _workspace("nms", max(nbytes, 256), boxes.device)
+    check(lib.mega_nms(ptr(boxes), ptr(scores), n, float(thresh), ptr(ws), ws.numel(), ptr(keep), ptr(count),
+                       stream_ptr()), "mega_nms")
+    return keep, count
+
+
+def rpn_select(head, n_img, h, w, base_anchors, im_w, im_h, pre_nms, post_nms, nms_thresh, min_size=0.0,
+               stride=16, out=None, want_anchor=False):
+    """head: [n_img, h, w, ld] fp32 (ld >= 5A). Returns (boxes [n_img,post,4], scores, anchor_idx|None, count)."""
+    require_cuda(head, base_anchors)
+    a = base_anchors.shape[0]
+    ld = head.shape[-1]
+    dev = head.device
+    if out is None:
+        boxes = torch.empty(n_img, post_nms, 4, device=dev)
+        scores = torch.empty(n_img, post_nms, device=dev)
+        count = torch.empty(n_img, dtype=torch.int32, device=dev)
+        anchor = torch.empty(n_img, post_nms, dtype=torch.int32, device=dev) if want_anchor else None
+    else:
+        boxes, scores, anchor, count = out
+    nbytes = lib.mega_rpn_select_workspace_bytes(n_img, h, w, a, pre_nms)
+    if nbytes < 0:
+        raise _lib.MegaError("rpn_select: pre_nms_top_n=%d exceeds 8192" % pre_nms)
+    ws = _workspace("rpn%d" % n_img, nbytes, dev)
+    check(lib.mega_rpn_select(ptr(head), head.stride(0), ld, n_img, h, w, a, stride, ptr(base_anchors), float(im_w),
+                              float(im_h), pre_nms, post_nms, float(nms_thresh), float(min_size), ptr(ws), ws.numel(),
+                              ptr(boxes), ptr(scores), ptr(anchor), ptr(count), stream_ptr()), "mega_rpn_select")
+    return boxes, scores, anchor, count
+
+
+def roi_align_nchw(inp, rois, scale, ph, pw, sampling_ratio, out=None):
+    require_cuda(inp, rois)
+    inp = inp.contiguous().float()
+    rois = rois.contiguous().float()
+    n, c, h, w = inp.shape
+    k = rois.shape[0]
+    if out is None:
+        out = torch.empty(k, c, ph, pw, device=inp.device)
+    check(lib.mega_roi_align_forward_nchw(ptr(inp), n, c, h, w, ptr(rois), k, float(scale), ph, pw, sampling_ratio,
+                                          ptr(out), stream_ptr()), "mega_roi_align_forward_nchw")
+    return out
+
+
+def roi_align_nhwc(feat, boxes, roi_batch, scale, ph, pw, sampling_ratio, out):
+    """feat [N,H,W,C]; boxes [K,4]; roi_batch int32 [K] or None; out [K, ph*pw*C]."""
+    require_cuda(feat, boxes, roi_batch, out)
+    n, h, w, c = feat.shape
+    k = boxes.shape[0]
+    check(lib.mega_roi_align_forward_nhwc(ptr(feat), c, h, w, feat.stride(0), ptr(boxes), boxes.stride(0), 0,
+                                          ptr(roi_batch), k, float(scale), ph, pw, sampling_ratio, ptr(out),
+                                          out.stride(0), stream_ptr()), "mega_roi_align_forward_nhwc")
+    return out
+
+
+def stem_im2col(img, out, kpad=160):
+    require_cuda(img, out)
+    n, c, h, w = img.shape
+    assert c == 3 and img.is_contiguous()
+    check(lib.mega_stem_im2col(ptr(img), n, h, w, kpad, ptr(out), stream_ptr()), "mega_stem_im2col")
+    return out
+
+
+def maxpool3x3s2(x, out):
+    require_cuda(x, out)
+    n, h, w, c = x.shape
+    check(lib.mega_maxpool3x3s2_nhwc(ptr(x), n, h, w, c, ptr(out), stream_ptr()), "mega_maxpool3x3s2_nhwc")
+    return out
+
+
+def gather_rows(src, idx, dst, n_rows=None, row_len=None):
+    require_cuda(src, idx, dst)
+    assert idx.dtype == torch.int32
+    n_rows = idx.numel() if n_rows is None else n_rows
+    row_len = src.shape[-1] if row_len is None else row_len
+    check(lib.mega_gather_rows(ptr(src), src.stride(-2), ptr(idx), n_rows, row_len, ptr(dst), dst.stride(-2),
+                               stream_ptr()), "mega_gather_rows")
+    return dst
+
+
+def copy_rows(src, dst, n_rows, row_len=None, src_idx=None, dst_idx=None):
+    """dst[dst_idx[i]] = src[src_idx[i]] for i < n_rows (either index optional); 2-D row views."""
+    require_cuda(src, dst, src_idx, dst_idx)
+    row_len = src.shape[-1] if row_len is None else row_len
+    check(lib.mega_copy_rows(ptr(src), src.stride(-2), ptr(src_idx), ptr(dst), dst.stride(-2), ptr(dst_idx), n_rows,
+                             row_len, stream_ptr()), "mega_copy_rows")
+    return dst
+
+
+def transpose_2d(x, out, n_img, rows, cols):
+    require_cuda(x, out)
+    check(lib.mega_transpose_2d(ptr(x), n_img, rows, cols, ptr(out), stream_ptr()), "mega_transpose_2d")
+    return out
+
+
+def relation_softmax(logits, n_rows, ldm, scale, boxes_q=None, boxes_k=None, wg=None, bg=None, dim_mat=None,
+                     m_valid=None, m_host=0, n_valid=None, n_valid_off=0):
+    require_cuda(logits, boxes_q, boxes_k, wg, bg, dim_mat, m_valid, n_valid)
+    check(lib.mega_relation_softmax(ptr(logits), n_rows, ldm, ptr(boxes_q), ptr(boxes_k), ptr(wg), ptr(bg),
+                                    ptr(dim_mat), ptr(m_valid), m_host, ptr(n_valid), n_valid_off, float(scale),
+                                    stream_ptr()), "mega_relation_softmax")
+    return logits
+
+
+def box_postprocess(logits, deltas, proposals, count, num_classes, im_w, im_h, score_thresh, nms_thresh, max_det,
+                    weights, out):
+    """logits [R, ld] / deltas [R, ld] views (may alias one buffer); out = (boxes, scores, labels int64, count)."""
+    require_cuda(logits, deltas, proposals, count)
+    r = proposals.shape[0]
+    nbytes = lib.mega_box_postprocess_workspace_bytes(r, num_classes)
+    if nbytes < 0:
+        raise _lib.MegaError("box_postprocess: at most 512 proposals per image")
+    ws = _workspace("post", nbytes, logits.device)
+    ob, os_, ol, oc = out
+    check(lib.mega_box_postprocess(ptr(logits), logits.stride(0), ptr(deltas), deltas.stride(0), ptr(proposals),
+                                   ptr(count), r, num_classes, float(im_w), float(im_h), float(score_thresh),
+                                   float(nms_thresh), max_det, *[float(x) for x in weights], ptr(ws), ws.numel(),
+                                   ptr(ob), ptr(os_), ptr(ol), ob.shape[0], ptr(oc), stream_ptr()),
+          "mega_box_postprocess")
+    return out
