@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of MEGA R-101 inference (1000x600) on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one steady-state key frame of MEGA R-101 at 600x1000 (configs[1] of BASELINE.json):
+one new look-ahead local frame and one new global frame go through backbone -> RPN -> res5 ->
+ROIAlign -> l_fcs[0], then the key frame (position 12 of the 25-frame local window) is aggregated
+against 25 local / 10 global / 25 memory frames and post-processed. Weights are the seeded
+synthetic initialisation of mega_core.b200.synth (no checkpoints offline); frames are synthetic.
+
+Output: ONE JSON line (see the driver contract): `value` = frames/s with inputs resident in HBM,
+`e2e` = frames/s through the public model(images) call with pinned-host inputs and a host read of
+the detections, `roofline` for the tcgen05 conv/GEMM kernel, `cpu_baseline` = the oracle port timed
+on this box's host cores on a bounded sample.
+
+N > 1 (torchrun): every rank runs an independent video stream (the reference's own multi-GPU
+strategy: VIDTestDistributedSampler shards by whole video, data/samplers/distributed.py:69-115;
+no data-path collective) -> weak scaling; value = total frames of all ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "mega.pytorch_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "frames/sec MEGA R-101 inference (1000x600)"
+ALGO_GFLOP_PER_FRAME = 734.0      # SURVEY.md section 8(d) / BASELINE.md section 2 (minimal exact form)
+H, W = 600, 1000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--arch", default="mega_r101")
+    ap.add_argument("--height", type=int, default=H)
+    ap.add_argument("--width", type=int, default=W)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
+    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "MEASURED_PEAKS.json (bf16 dense sustained)"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def frame_pool(n, h, w):
+    from mega_core.b200 import synth
+    return [synth.synthetic_frame(i, h, w) for i in range(n)]
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args, rank, world):
+    import torch.distributed as dist
+    from mega_core.b200 import engine, ops, synth
+    from mega_core.modeling.detector import build_detection_model_from_state_dict
+    from mega_core.structures.image_list import to_image_list
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    h, w = args.height, args.width
+    sd = synth.make_state_dict(args.arch, seed=0)
+    model = build_detection_model_from_state_dict(sd, method="mega", device=dev)
+    eng = model.engine
+    eng.use_graph = not args.no_graph
+    pool = frame_pool(16, h, w)
+    pool_pinned = [f.pin_memory() for f in pool]
+    pool_dev = [f.to(dev) for f in pool]
+    pair_shape = (2, 3, h, w)
+
+    def infos_first():
+        return {"cur": pool_pinned[0], "ref_l": [], "ref_g": [pool_pinned[(3 * j + 1) % 16] for j in range(10)],
+                "frame_category": 0, "seg_len": 10 ** 6, "pattern": "%06d", "img_dir": "%s",
+                "lookahead": [pool_pinned[(j + 1) % 16] for j in range(12)]}
+
+    def infos_next(t):
+        return {"cur": pool_pinned[t % 16], "ref_l": [pool_pinned[(t + 12) % 16]], "ref_g": [pool_pinned[(5 * t + 3) % 16]],
+                "frame_category": 1, "seg_len": 10 ** 6, "pattern": "%06d", "img_dir": "%s"}
+
+    # ---- prime: first frame of the video, then fill the long-range memory (25 key frames)
+    with torch.no_grad():
+        model(infos_first())
+        t = 1
+        for _ in range(eng.MEMF + 2 if args.prime < 0 else args.prime):
+            model(infos_next(t))
+            t += 1
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- timed region A: device-resident inputs, engine-level step (no host transfers)
+    static_in = eng.static_input(pair_shape)
+    pairs_dev = [torch.cat([pool_dev[(i + 12) % 16], pool_dev[(5 * i + 3) % 16]], 0) for i in range(16)]
+    launches0 = ops.LAUNCHES[0]
+    for i in range(args.warmup):
+        eng.step_batched(pairs_dev[i % 16], w, h)
+    launches_per_step = (ops.LAUNCHES[0] - launches0) / max(args.warmup, 1)
+    if eng._graphs:
+        launches_per_step = eng.launches_per_frame
+    barrier()
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        eng.step_batched(pairs_dev[i % 16], w, h)
+    e1.record()
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+
+    # ---- timed region B: end to end through model(images): pinned host inputs -> detections on the host
+    for i in range(max(args.warmup, 3)):
+        model(infos_next(t))
+        t += 1
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    ndet = 0
+    for i in range(args.steps):
+        out = model(infos_next(t))
+        ndet += len(out[0])
+        t += 1
+    e3.record()
+    barrier()
+    e2e_ms = e2.elapsed_time(e3)
+    h2d = 2 * 3 * h * w * 4 + eng.tab_h.numel() * 4
+    d2h = model.d2h_bytes_per_frame
+
+    # ---- roofline of the dominant kernel (tcgen05 conv/GEMM): eager frames with an event pair per launch
+    roof = roofline_pass(eng, pairs_dev, w, h)
+
+    times = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = times.tolist()
+    if rank != 0:
+        return None
+    pk = peaks()
+    line = {
+        "metric": METRIC, "value": world * args.steps / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+        "config": {"workload": "MEGA R-101 C4 steady-state key frame, %dx%d, 25 local / 10 global / 25 memory frames, "
+                               "1 new local + 1 new global frame per step" % (w, h),
+                   "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
+                   "parallelism": "1 video stream per GPU (shard by video)" if world > 1 else "single GPU",
+                   "cuda_graph": bool(eng._graphs),
+                   "l2": "per-step working set (0.7 GB fp32 weights + >0.5 GB activations) exceeds the 126 MB L2; no flush"},
+        "clocks": clocks,
+        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "detections_per_frame": ndet / args.steps},
+        "gpu_launches": int(round(launches_per_step * args.steps)),
+        "roofline": {"bound": "tensor", "achieved": roof["algo_tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": roof["algo_tflops"] / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                     "kernel": "conv_gemm_tf32_kernel (tcgen05 kind::tf32; TF32 dense peak is half the bf16 figure)",
+                     "algorithmic_gflop_per_frame": ALGO_GFLOP_PER_FRAME, "executed_gflop_per_frame": roof["exec_gflop"],
+                     "kernel_ms_per_frame": roof["kernel_ms"], "launches_per_frame": roof["launches"],
+                     "executed_tflops": roof["exec_tflops"], "kernel_share_of_step": roof["kernel_ms"] / (dev_ms / args.steps)},
+    }
+    return line
+
+
+def roofline_pass(eng, pairs_dev, w, h, reps=3):
+    """sum of conv_gemm kernel durations per frame (CUDA events on the launching stream)"""
+    from mega_core.b200 import ops
+    saved_graphs, eng._graphs = eng._graphs, {}
+    saved_flag, eng.use_graph = eng.use_graph, False
+    rec = []
+    orig = ops._launch_conv_gemm
+
+    def timed(d):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        orig(d)
+        b.record()
+        m = d.n_img * d.out_h * d.out_w * d.batch
+        rec.append((a, b, 2.0 * m * d.cout * d.k_per_tap * d.taps_r * d.taps_s))
+
+    ops._launch_conv_gemm = timed
+    try:
+        eng.step_batched(pairs_dev[0], w, h)   # warm
+        rec.clear()
+        for i in range(reps):
+            eng.step_batched(pairs_dev[(i + 1) % 16], w, h)
+        torch.cuda.synchronize()
+    finally:
+        ops._launch_conv_gemm = orig
+        eng._graphs, eng.use_graph = saved_graphs, saved_flag
+    ms = sum(a.elapsed_time(b) for a, b, _ in rec) / reps
+    fl = sum(f for _, _, f in rec) / reps
+    return {"kernel_ms": ms, "exec_gflop": fl / 1e9, "exec_tflops": fl / (ms * 1e-3) / 1e12,
+            "algo_tflops": ALGO_GFLOP_PER_FRAME * 1e9 / (ms * 1e-3) / 1e12, "launches": len(rec) / reps}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(args, frames_to_time):
+    """the oracle port (oracle/mega_oracle.py) on this box's host cores: steady-state MEGA R-101
+    frames at full size. The 25-frame window, the global pool and the long-range memory are
+    pre-filled with synthetic rows (bounded sample: building them for real costs 23 backbone
+    passes); each timed frame then runs 2 backbone/RPN/res5/ROIAlign/FC passes + the full
+    aggregation, exactly like a steady-state frame of the reference."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mega_oracle as mo
+    from collections import deque
+    from mega_core.b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h, w = args.height, args.width
+    sd = synth.make_state_dict(args.arch, seed=0)
+    orc = mo.MegaOracle(sd)
+    c = orc.cfg
+    g = torch.Generator().manual_seed(1)
+    L, R, A = c.all_frame_interval, c.ref_post_nms_top_n, c.advanced_num
+
+    def boxes(n):
+        xy = torch.rand(n, 2, generator=g) * torch.tensor([w * 0.8, h * 0.8])
+        return torch.cat([xy, xy + torch.rand(n, 2, generator=g) * 150 + 8], 1)
+
+    fh, fw = (h - 1) // 16 + 1, (w - 1) // 16 + 1
+    orc.q_feats = deque([torch.randn(1, 1024, fh, fw, generator=g).relu() for _ in range(L)], maxlen=L)
+    orc.q_boxes = deque([boxes(R) for _ in range(L)], maxlen=L)
+    orc.q_boxes_dis = deque([b[:A] for b in orc.q_boxes], maxlen=L)
+    orc.q_pfeat = deque([torch.randn(R, 1024, generator=g).relu() * 0.3 for _ in range(L)], maxlen=L)
+    orc.q_pfeat_dis = deque([p[:A] for p in orc.q_pfeat], maxlen=L)
+    orc.mem_q = []
+    for i in range(c.stage):
+        n = R if i == 0 else A
+        orc.mem_q.append({"rois": deque([boxes(n) for _ in range(L)], maxlen=L),
+                          "feats": deque([torch.randn(n, 1024, generator=g).relu() * 0.3 for _ in range(L)], maxlen=L)})
+    orc.mem = [{"rois": torch.cat(list(q["rois"])), "feats": torch.cat(list(q["feats"]))} for q in orc.mem_q]
+    orc.global_q = deque([torch.randn(R, 1024, generator=g).relu() * 0.3 for _ in range(c.global_size)], maxlen=c.global_size)
+    pool = frame_pool(4, h, w)
+    with torch.no_grad():
+        t0 = time.time()
+        for i in range(frames_to_time):
+            orc.forward(pool[i % 4], {"frame_category": 1, "ref_l": [pool[(i + 1) % 4]], "ref_g": [pool[(i + 2) % 4]]})
+        dt = time.time() - t0
+    return {"value": frames_to_time / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "%d steady-state MEGA R-101 frames at %dx%d (2 backbone passes + full 25/10/25 aggregation each); "
+                      "window/global/memory pre-filled with synthetic rows; oracle/mega_oracle.py, torch fp32, %d threads"
+                      % (frames_to_time, w, h, cores), "seconds": dt}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return None
+    per_step = []
+    total = args.warmup + args.steps
+    base = None
+    # each "step" is one bounded sample (1 steady-state frame); keep the whole run within minutes
+    n = max(1, min(total, 6))
+    base = cpu_sample(args, n)
+    v = base["value"]
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MEGA R-101 C4 steady-state key frame, %dx%d, CPU oracle port, %d timed frames"
+                                   % (args.width, args.height, n), "arch": args.arch},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+        if line is not None:
+            print(json.dumps(line))
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+        dist.init_process_group("nccl")
+    line = run_b200(args, rank, world)
+    if rank == 0:
+        if not args.skip_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_sample(args, args.cpu_sample_frames)
+        elif world == 1:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -363,8 +363,10 @@ class MegaEngine(HeadCommon):
         self.Qb = z(nq_g0, D)
         self.Kb = z(max(self.nl0 + self.mem_cap0, GF * R), D)
         self.Vt = {ld: z(D, ld) for ld in {self.ld_g, self.ld_0, self.ld_12}}
-        self.S = {self.ld_g: z(16 * nq_g0 * self.ld_g), self.ld_0: z(16 * self.nq * self.ld_0),
-                  self.ld_12: z(16 * self.nq * self.ld_12)}
+        s_need = {}
+        for ld, rows in ((self.ld_g, nq_g0), (self.ld_0, self.nq), (self.ld_12, self.nq)):
+            s_need[ld] = max(s_need.get(ld, 0), 16 * rows * ld)
+        self.S = {ld: z(n) for ld, n in s_need.items()}
         self.pooled = z(KP + R + KP, res * res * ch)            # up to (local 300 + global 75 [+ spare]) rois
         self.fc_partial = z(16, KP + R + KP, D)
         self.fc0_out = z(KP + R + KP, D)
@@ -378,12 +380,18 @@ class MegaEngine(HeadCommon):
             o[name] = (off, n)
             off += _round_up(n, 4)
         self._tab_off = o
-        self.tab_h = torch.zeros(off, dtype=torch.int32).pin_memory() if dev.type == "cuda" else torch.zeros(off, dtype=torch.int32)
+        # host mirrors are multi-buffered: the H2D copy of frame t may still be queued when the host
+        # prepares frame t+1 (each buffer is reused only after the event recorded behind its copy)
+        self._tab_ring = [torch.zeros(off, dtype=torch.int32).pin_memory() for _ in range(4)]
+        self._tab_ev = [None] * 4
+        self.tab_h = self._tab_ring[0]
         self.tab_d = z(off, dtype=torch.int32)
         # static tables
         q_idx = list(range(KP)) + [KP + f * R + j for f in range(L) for j in range(A)]
         self.idx_qin0 = torch.tensor(q_idx, dtype=torch.int32, device=dev)
         self._roi_tabs = {}
+        self._graphs, self._static_in, self._eager_done = {}, {}, {}
+        self.use_graph = False
         self.reset()
 
     # ------------------------------------------------------------------ host-side state machine
@@ -493,13 +501,52 @@ class MegaEngine(HeadCommon):
         gslot = self.glob_pushed % self.GF
         self.glob_pushed += 1
         self._fill_tables(slot_new=slot_new, gslot=gslot)
+        key = (tuple(imgs.shape), im_w, im_h)
+        if self.use_graph and key not in self._graphs and self._eager_done.get(key, 0) >= 1:
+            self._capture(key, imgs)
+        g = self._graphs.get(key)
+        if g is not None:
+            graph, static_in, det = g
+            if imgs.data_ptr() != static_in.data_ptr():
+                static_in.copy_(imgs, non_blocking=True)
+            graph.replay()
+            return det
+        self._eager_done[key] = self._eager_done.get(key, 0) + 1
         return self._steady_frame(imgs, im_w, im_h)
+
+    def static_input(self, shape):
+        """device buffer [2,3,H,W] the captured graph reads its (local, global) frame pair from;
+        writing the next pair straight into it saves the device-to-device copy"""
+        t = self._static_in.get(tuple(shape))
+        if t is None:
+            t = torch.zeros(*shape, device=self.dev)
+            self._static_in[tuple(shape)] = t
+        return t
+
+    def _capture(self, key, imgs):
+        """Capture the steady-state frame (a fixed sequence of ~200 kernel launches whose
+        frame-dependent addresses all come from the device-side index tables) into one CUDA graph.
+        Capturing does not execute anything: the first steady frame of a video runs eagerly (which
+        also warms every buffer / kernel attribute), the second one is captured and replayed."""
+        shape, im_w, im_h = key
+        static_in = self.static_input(shape)
+        torch.cuda.synchronize(self.dev)
+        graph = torch.cuda.CUDAGraph()
+        l0 = ops.LAUNCHES[0]
+        with torch.cuda.graph(graph):
+            det = self._steady_frame(static_in, im_w, im_h)
+        self.launches_per_frame = ops.LAUNCHES[0] - l0
+        self._graphs[key] = (graph, static_in, det)
 
     def _fill_tables(self, slot_new=None, gslot=None):
         KP, R, A, L = self.KP, self.R, self.A, self.L
         slots = list(self.win_slots)
         assert len(slots) == L
         kslot = slots[self.cfg.key_frame_location]
+        ring = self.frames % len(self._tab_ring)
+        if self._tab_ev[ring] is not None:
+            self._tab_ev[ring].synchronize()
+        self.tab_h = self._tab_ring[ring]
         th = self._tab_h
         mem_frames = min(self.mem_pushed, self.MEMF)
         mv = th("mvalid")
@@ -524,6 +571,9 @@ class MegaEngine(HeadCommon):
         th("dst_memb12").copy_(torch.arange(self.nl12 + mslot * A, self.nl12 + (mslot + 1) * A, dtype=torch.int32))
         th("slot_key")[0] = kslot
         self.tab_d.copy_(self.tab_h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._tab_ev[ring] = ev
         self.mem_pushed += 1
         self.frames += 1
 

@@ -7,6 +7,16 @@ from .. import _lib
 from .._lib import ConvGemmDesc, check, lib, ptr, require_cuda, stream_ptr
 
 
+# kernel launches issued through this module (bench.py reports it as `gpu_launches`)
+LAUNCHES = [0]
+
+
+def _launch_conv_gemm(d):
+    """single choke point of the tcgen05 kernel (bench.py wraps it with CUDA events for the roofline)"""
+    check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
+    LAUNCHES[0] += 2 if d.splits > 1 else 1
+
+
 def pick_tile(h, w):
     """128-pixel output tile (tile_h, tile_w) wasting the fewest pixels for an h x w map."""
     best = None
@@ -78,7 +88,7 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.bias_z_off = bias_z_off
     d.splits = splits
     d.partial = ptr(partial)
-    check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
+    _launch_conv_gemm(d)
     return out
 
 
@@ -126,6 +136,7 @@ def nms_device(boxes, scores, thresh, keep=None, count=None):
     ws = _workspace("nms", max(nbytes, 256), boxes.device)
     check(lib.mega_nms(ptr(boxes), ptr(scores), n, float(thresh), ptr(ws), ws.numel(), ptr(keep), ptr(count),
                        stream_ptr()), "mega_nms")
+    LAUNCHES[0] += 4
     return keep, count
 
 
@@ -150,6 +161,7 @@ def rpn_select(head, n_img, h, w, base_anchors, im_w, im_h, pre_nms, post_nms, n
     check(lib.mega_rpn_select(ptr(head), head.stride(0), ld, n_img, h, w, a, stride, ptr(base_anchors), float(im_w),
                               float(im_h), pre_nms, post_nms, float(nms_thresh), float(min_size), ptr(ws), ws.numel(),
                               ptr(boxes), ptr(scores), ptr(anchor), ptr(count), stream_ptr()), "mega_rpn_select")
+    LAUNCHES[0] += 4
     return boxes, scores, anchor, count
 
 
@@ -163,6 +175,7 @@ def roi_align_nchw(inp, rois, scale, ph, pw, sampling_ratio, out=None):
         out = torch.empty(k, c, ph, pw, device=inp.device)
     check(lib.mega_roi_align_forward_nchw(ptr(inp), n, c, h, w, ptr(rois), k, float(scale), ph, pw, sampling_ratio,
                                           ptr(out), stream_ptr()), "mega_roi_align_forward_nchw")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -174,6 +187,7 @@ def roi_align_nhwc(feat, boxes, roi_batch, scale, ph, pw, sampling_ratio, out):
     check(lib.mega_roi_align_forward_nhwc(ptr(feat), c, h, w, feat.stride(0), ptr(boxes), boxes.stride(0), 0,
                                           ptr(roi_batch), k, float(scale), ph, pw, sampling_ratio, ptr(out),
                                           out.stride(0), stream_ptr()), "mega_roi_align_forward_nhwc")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -182,6 +196,7 @@ def stem_im2col(img, out, kpad=160):
     n, c, h, w = img.shape
     assert c == 3 and img.is_contiguous()
     check(lib.mega_stem_im2col(ptr(img), n, h, w, kpad, ptr(out), stream_ptr()), "mega_stem_im2col")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -189,6 +204,7 @@ def maxpool3x3s2(x, out):
     require_cuda(x, out)
     n, h, w, c = x.shape
     check(lib.mega_maxpool3x3s2_nhwc(ptr(x), n, h, w, c, ptr(out), stream_ptr()), "mega_maxpool3x3s2_nhwc")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -199,6 +215,7 @@ def gather_rows(src, idx, dst, n_rows=None, row_len=None):
     row_len = src.shape[-1] if row_len is None else row_len
     check(lib.mega_gather_rows(ptr(src), src.stride(-2), ptr(idx), n_rows, row_len, ptr(dst), dst.stride(-2),
                                stream_ptr()), "mega_gather_rows")
+    LAUNCHES[0] += 1
     return dst
 
 
@@ -208,12 +225,14 @@ def copy_rows(src, dst, n_rows, row_len=None, src_idx=None, dst_idx=None):
     row_len = src.shape[-1] if row_len is None else row_len
     check(lib.mega_copy_rows(ptr(src), src.stride(-2), ptr(src_idx), ptr(dst), dst.stride(-2), ptr(dst_idx), n_rows,
                              row_len, stream_ptr()), "mega_copy_rows")
+    LAUNCHES[0] += 1
     return dst
 
 
 def transpose_2d(x, out, n_img, rows, cols):
     require_cuda(x, out)
     check(lib.mega_transpose_2d(ptr(x), n_img, rows, cols, ptr(out), stream_ptr()), "mega_transpose_2d")
+    LAUNCHES[0] += 1
     return out
 
 
@@ -223,6 +242,7 @@ def relation_softmax(logits, n_rows, ldm, scale, boxes_q=None, boxes_k=None, wg=
     check(lib.mega_relation_softmax(ptr(logits), n_rows, ldm, ptr(boxes_q), ptr(boxes_k), ptr(wg), ptr(bg),
                                     ptr(dim_mat), ptr(m_valid), m_host, ptr(n_valid), n_valid_off, float(scale),
                                     stream_ptr()), "mega_relation_softmax")
+    LAUNCHES[0] += 1
     return logits
 
 
@@ -241,4 +261,5 @@ def box_postprocess(logits, deltas, proposals, count, num_classes, im_w, im_h, s
                                    float(nms_thresh), max_det, *[float(x) for x in weights], ptr(ws), ws.numel(),
                                    ptr(ob), ptr(os_), ptr(ol), ob.shape[0], ptr(oc), stream_ptr()),
           "mega_box_postprocess")
+    LAUNCHES[0] += 2
     return out

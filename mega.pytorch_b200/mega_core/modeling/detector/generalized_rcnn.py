@@ -1,0 +1,130 @@
+"""Meta-architectures with the reference's forward() contracts.
+
+GeneralizedRCNN       -- detector/generalized_rcnn.py:16-65 (single frame)
+GeneralizedRCNNMEGA   -- detector/generalized_rcnn_mega.py:21-225 (per-video state machine)
+
+`forward(images)` returns `list[BoxList]` (fields `scores`, `labels`) exactly like the reference in
+eval mode; the arithmetic runs in the B200 engine built lazily from this module's own state_dict
+(so weights loaded with load_state_dict / DetectronCheckpointer are what the kernels use).
+"""
+import torch
+from torch import nn
+
+from ..nets import build_backbone, build_roi_heads, build_rpn, engine_config_from
+from ...b200 import engine as _engine
+from ...structures.bounding_box import BoxList
+from ...structures.image_list import to_image_list
+
+
+class _EngineBacked(nn.Module):
+    engine_cls = None
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg.clone()
+        self.device = torch.device(cfg.MODEL.DEVICE)
+        self.backbone = build_backbone(cfg)
+        self.rpn = build_rpn(cfg, self.backbone.out_channels)
+        self.roi_heads = build_roi_heads(cfg, self.backbone.out_channels)
+        self._engine = None
+        self._sd_override = None
+        self.d2h_bytes_per_frame = 0
+
+    def adopt_state_dict(self, sd):
+        self._sd_override = {k: v for k, v in sd.items()}
+        self._engine = None
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("mega_core (B200 build) runs on CUDA only; MODEL.DEVICE=%s" % self.device)
+            sd = self._sd_override if self._sd_override is not None else self.state_dict()
+            self._engine = self.engine_cls(sd, engine_config_from(self.cfg), self.device)
+        return self._engine
+
+    def _to_boxlist(self, det, im_w, im_h):
+        n = int(det.count.item())
+        out = BoxList(det.boxes[:n].clone(), (int(im_w), int(im_h)), mode="xyxy")
+        out.add_field("scores", det.scores[:n].clone())
+        out.add_field("labels", det.labels[:n].clone())
+        self.d2h_bytes_per_frame = 4 + n * (16 + 4 + 8)
+        return out
+
+    def _dev(self, t):
+        t = t.tensors if hasattr(t, "tensors") else t
+        if t.dim() == 3:
+            t = t[None]
+        return t.to(self.device, non_blocking=True).float().contiguous()
+
+
+class GeneralizedRCNN(_EngineBacked):
+    engine_cls = _engine.BaseEngine
+
+    def forward(self, images, targets=None):
+        if self.training:
+            raise NotImplementedError("the B200 build covers inference (eval mode) only")
+        images = to_image_list(images)
+        out = []
+        with torch.no_grad():
+            for i, (h, w) in enumerate(images.image_sizes):
+                det = self.engine.forward(self._dev(images.tensors[i][:, :h, :w]), w, h)
+                out.append(self._to_boxlist(det, w, h))
+        return out
+
+
+class GeneralizedRCNNMEGA(_EngineBacked):
+    engine_cls = _engine.MegaEngine
+
+    def forward(self, images, targets=None):
+        """images: the dict VIDMEGADataset._get_test builds (data/datasets/vid_mega.py:132-140):
+        cur, ref_l, ref_g, frame_category, seg_len, pattern, img_dir, transforms. Optional extra key
+        `lookahead` (list of 12 pre-staged frames) replaces the disk reads of frame 0
+        (generalized_rcnn_mega.py:183-193) for synthetic / benchmark streams."""
+        if self.training:
+            raise NotImplementedError("the B200 build covers inference (eval mode) only")
+        if targets is not None:
+            raise ValueError("In testing mode, targets should be None")
+        cur = to_image_list(images["cur"])
+        im_h, im_w = cur.image_sizes[0]
+        eng = self.engine
+        with torch.no_grad():
+            if images["frame_category"] == 0:
+                self.seg_len, self.end_id = images["seg_len"], 0
+                look = images.get("lookahead")
+                if look is None:
+                    look = self._read_lookahead(images, eng.L - eng.cfg.key_frame_location - 1)
+                det = eng.start_video(self._dev(cur), [self._dev(x) for x in look],
+                                      [self._dev(g) for g in images["ref_g"]], im_w, im_h)
+            else:
+                self.end_id = min(getattr(self, "end_id", 0) + 1, getattr(self, "seg_len", 1) - 1)
+                assert len(images["ref_l"]) == 1 and len(images["ref_g"]) == 1, \
+                    "steady-state frames carry one look-ahead local frame and one global frame"
+                pair = eng.static_input((2,) + tuple(cur.tensors.shape[1:]))
+                pair[0].copy_(self._host(images["ref_l"][0]), non_blocking=True)
+                pair[1].copy_(self._host(images["ref_g"][0]), non_blocking=True)
+                det = eng.step_batched(pair, im_w, im_h)
+        return [self._to_boxlist(det, im_w, im_h)]
+
+    @staticmethod
+    def _host(t):
+        t = t.tensors if hasattr(t, "tensors") else t
+        return t[0] if t.dim() == 4 else t
+
+    def _read_lookahead(self, infos, n):
+        """frame 0 of a video: the reference opens the next frames from disk inside the model"""
+        from PIL import Image
+        frames = []
+        for _ in range(n):
+            self.end_id = min(self.end_id + 1, self.seg_len - 1)
+            name = infos["pattern"] % self.end_id
+            img = Image.open(infos["img_dir"] % name).convert("RGB")
+            img = infos["transforms"](img)
+            if isinstance(img, tuple):
+                img = img[0]
+            frames.append(img.view(1, *img.shape))
+        return frames

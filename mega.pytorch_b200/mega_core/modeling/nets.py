@@ -1,0 +1,217 @@
+"""Parameter-holding module tree with the reference's attribute / state_dict names.
+
+The reference's checkpoints (e.g. MEGA_R_101.pth) load through `load_state_dict` because every
+parameter and buffer keeps its name and shape: backbone.body.{stem,layer1..3}, rpn.head.*,
+rpn.anchor_generator.cell_anchors.0, roi_heads.box.feature_extractor.{head.layer4, l_fcs, l_Wgs,
+l_Wqs, l_Wks, l_Wvs, l_us, g_Wqs, g_Wks, g_Wvs, g_us}, roi_heads.box.predictor.{cls_score,bbox_pred}
+(reference: modeling/backbone/resnet.py, rpn/rpn.py, roi_heads/box_head/*). The torch modules below
+only HOLD the tensors; all arithmetic runs in the B200 engine (mega_core/b200/engine.py).
+"""
+import torch
+from torch import nn
+
+from . import registry
+from ..layers import Conv2d, FrozenBatchNorm2d
+from ..b200 import engine as _engine
+
+BLOCKS = {"R-50-C4": (3, 4, 6), "R-101-C4": (3, 4, 23)}
+
+
+class Bottleneck(nn.Module):
+    def __init__(self, cin, mid, cout, stride, dilation):
+        super().__init__()
+        if cin != cout:
+            self.downsample = nn.Sequential(Conv2d(cin, cout, 1, stride=(stride if dilation == 1 else 1), bias=False),
+                                            FrozenBatchNorm2d(cout))
+        self.conv1 = Conv2d(cin, mid, 1, stride=(1 if dilation > 1 else stride), bias=False)
+        self.bn1 = FrozenBatchNorm2d(mid)
+        self.conv2 = Conv2d(mid, mid, 3, padding=dilation, dilation=dilation, bias=False)
+        self.bn2 = FrozenBatchNorm2d(mid)
+        self.conv3 = Conv2d(mid, cout, 1, bias=False)
+        self.bn3 = FrozenBatchNorm2d(cout)
+
+
+def _stage(cin, mid, cout, n, stride, dilation=1):
+    blocks = []
+    for i in range(n):
+        blocks.append(Bottleneck(cin if i == 0 else cout, mid, cout, stride if i == 0 else 1, dilation))
+    return nn.Sequential(*blocks)
+
+
+class Stem(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = FrozenBatchNorm2d(64)
+
+
+class ResNetBody(nn.Module):
+    """`backbone.body` (modeling/backbone/resnet.py:81-152)"""
+
+    def __init__(self, conv_body):
+        super().__init__()
+        b = BLOCKS[conv_body]
+        self.stem = Stem()
+        self.layer1 = _stage(64, 64, 256, b[0], 1)
+        self.layer2 = _stage(256, 128, 512, b[1], 2)
+        self.layer3 = _stage(512, 256, 1024, b[2], 2)
+        self.out_channels = 1024
+
+
+class ResNetHead(nn.Module):
+    """res5 as `feature_extractor.head` (resnet.py:155-204; stride_init=1)"""
+
+    def __init__(self, dilation):
+        super().__init__()
+        self.layer4 = _stage(1024, 512, 2048, 3, 1, dilation)
+        self.out_channels = 2048
+
+
+@registry.BACKBONES.register("R-50-C4")
+@registry.BACKBONES.register("R-101-C4")
+def build_resnet_backbone(cfg):
+    model = nn.Sequential()
+    model.add_module("body", ResNetBody(cfg.MODEL.BACKBONE.CONV_BODY))
+    model.out_channels = cfg.MODEL.RESNETS.BACKBONE_OUT_CHANNELS
+    return model
+
+
+class BufferList(nn.Module):
+    def __init__(self, buffers):
+        super().__init__()
+        for i, b in enumerate(buffers):
+            self.register_buffer(str(i), b)
+
+
+class AnchorGenerator(nn.Module):
+    def __init__(self, sizes, ratios, stride):
+        super().__init__()
+        self.strides = (stride,)
+        self.cell_anchors = BufferList([_engine.cell_anchors(stride, sizes, ratios)])
+
+    def num_anchors_per_location(self):
+        return [self.cell_anchors._buffers["0"].shape[0]]
+
+
+@registry.RPN_HEADS.register("SingleConvRPNHead")
+class RPNHead(nn.Module):
+    def __init__(self, cfg, in_channels, num_anchors):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, in_channels, 3, padding=1)
+        self.cls_logits = nn.Conv2d(in_channels, num_anchors, 1)
+        self.bbox_pred = nn.Conv2d(in_channels, num_anchors * 4, 1)
+
+
+class RPNModule(nn.Module):
+    """`model.rpn` (rpn/rpn.py:109-243): holds head + anchors; forward() is served by the detector's engine"""
+
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        r = cfg.MODEL.RPN
+        self.anchor_generator = AnchorGenerator(r.ANCHOR_SIZES, r.ASPECT_RATIOS, r.ANCHOR_STRIDE[0])
+        self.head = registry.RPN_HEADS[r.RPN_HEAD](cfg, in_channels, self.anchor_generator.num_anchors_per_location()[0])
+
+
+def _fc(i, o):
+    return nn.Linear(i, o)
+
+
+@registry.ROI_BOX_FEATURE_EXTRACTORS.register("ResNetConv52MLPFeatureExtractor")
+class ResNetConv52MLPFeatureExtractor(nn.Module):
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        self.head = ResNetHead(cfg.MODEL.RESNETS.RES5_DILATION)
+        ch = 2048
+        if cfg.MODEL.VID.ROI_BOX_HEAD.REDUCE_CHANNEL:
+            self.conv = nn.Conv2d(2048, 256, 1)
+            ch = 256
+        else:
+            self.conv = None
+        res = cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION
+        dim = cfg.MODEL.ROI_BOX_HEAD.MLP_HEAD_DIM
+        self.fc6 = _fc(ch * res * res, dim)
+        self.fc7 = _fc(dim, dim)
+        self.out_channels = dim
+
+
+@registry.ROI_BOX_FEATURE_EXTRACTORS.register("MEGAFeatureExtractor")
+class MEGAFeatureExtractor(nn.Module):
+    """parameters of roi_box_feature_extractors.py:457-565"""
+
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        self.head = ResNetHead(cfg.MODEL.RESNETS.RES5_DILATION)
+        self.conv = None
+        res = cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION
+        dim = cfg.MODEL.ROI_BOX_HEAD.MLP_HEAD_DIM
+        att = cfg.MODEL.VID.ROI_BOX_HEAD.ATTENTION
+        emb, grp, stages = att.EMBED_DIM, att.GROUP, att.STAGE
+        self.l_fcs = nn.ModuleList([_fc(2048 * res * res if i == 0 else dim, dim) for i in range(stages)])
+        self.l_Wgs = nn.ModuleList([nn.Conv2d(emb, grp, 1) for _ in range(stages)])
+        self.l_Wqs = nn.ModuleList([_fc(dim, dim) for _ in range(stages)])
+        self.l_Wks = nn.ModuleList([_fc(dim, dim) for _ in range(stages)])
+        self.l_Wvs = nn.ModuleList([nn.Conv2d(dim * grp, dim, 1, groups=grp) for _ in range(stages)])
+        self.l_us = nn.ParameterList([nn.Parameter(torch.zeros(grp, 1, emb)) for _ in range(stages)])
+        g = cfg.MODEL.VID.MEGA.GLOBAL.RES_STAGE + 1
+        self.g_Wqs = nn.ModuleList([_fc(dim, dim) for _ in range(g)])
+        self.g_Wks = nn.ModuleList([_fc(dim, dim) for _ in range(g)])
+        self.g_Wvs = nn.ModuleList([nn.Conv2d(dim * grp, dim, 1, groups=grp) for _ in range(g)])
+        self.g_us = nn.ParameterList([nn.Parameter(torch.zeros(grp, 1, emb)) for _ in range(g)])
+        self.out_channels = dim
+
+
+@registry.ROI_BOX_PREDICTOR.register("FPNPredictor")
+class FPNPredictor(nn.Module):
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        n = cfg.MODEL.ROI_BOX_HEAD.NUM_CLASSES
+        self.cls_score = nn.Linear(in_channels, n)
+        self.bbox_pred = nn.Linear(in_channels, (2 if cfg.MODEL.CLS_AGNOSTIC_BBOX_REG else n) * 4)
+
+
+class ROIBoxHead(nn.Module):
+    """`model.roi_heads.box` (box_head/box_head.py:11-124): feature_extractor + predictor"""
+
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        fe = registry.ROI_BOX_FEATURE_EXTRACTORS[cfg.MODEL.ROI_BOX_HEAD.FEATURE_EXTRACTOR]
+        self.feature_extractor = fe(cfg, in_channels)
+        pr = registry.ROI_BOX_PREDICTOR[cfg.MODEL.ROI_BOX_HEAD.PREDICTOR]
+        self.predictor = pr(cfg, self.feature_extractor.out_channels)
+
+
+class CombinedROIHeads(nn.ModuleDict):
+    """`model.roi_heads` (roi_heads/roi_heads.py:9-76), box head only (MASK_ON / KEYPOINT_ON are False)"""
+
+    def __init__(self, cfg, heads):
+        super().__init__(heads)
+        self.cfg = cfg.clone()
+
+
+def build_backbone(cfg):
+    return registry.BACKBONES[cfg.MODEL.BACKBONE.CONV_BODY](cfg)
+
+
+def build_rpn(cfg, in_channels):
+    return RPNModule(cfg, in_channels)
+
+
+def build_roi_heads(cfg, in_channels):
+    return CombinedROIHeads(cfg, [("box", ROIBoxHead(cfg, in_channels))])
+
+
+def engine_config_from(cfg):
+    m = cfg.MODEL
+    v = m.VID
+    return _engine.EngineConfig(
+        pre_nms_top_n=m.RPN.PRE_NMS_TOP_N_TEST, post_nms_top_n=m.RPN.POST_NMS_TOP_N_TEST,
+        ref_post_nms_top_n=v.RPN.REF_POST_NMS_TOP_N, rpn_nms_thresh=m.RPN.NMS_THRESH, rpn_min_size=m.RPN.MIN_SIZE,
+        ratio=v.MEGA.RATIO, all_frame_interval=v.MEGA.ALL_FRAME_INTERVAL, key_frame_location=v.MEGA.KEY_FRAME_LOCATION,
+        memory_size=v.MEGA.MEMORY.SIZE, global_size=v.MEGA.GLOBAL.SIZE, global_res_stage=v.MEGA.GLOBAL.RES_STAGE,
+        stage=v.ROI_BOX_HEAD.ATTENTION.STAGE, groups=v.ROI_BOX_HEAD.ATTENTION.GROUP,
+        pooler_resolution=m.ROI_BOX_HEAD.POOLER_RESOLUTION, pooler_scale=m.ROI_BOX_HEAD.POOLER_SCALES[0],
+        sampling_ratio=m.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO, res5_dilation=m.RESNETS.RES5_DILATION,
+        score_thresh=m.ROI_HEADS.SCORE_THRESH, nms_thresh=m.ROI_HEADS.NMS, detections_per_img=m.ROI_HEADS.DETECTIONS_PER_IMG,
+        bbox_reg_weights=tuple(m.ROI_HEADS.BBOX_REG_WEIGHTS), anchor_sizes=tuple(m.RPN.ANCHOR_SIZES),
+        aspect_ratios=tuple(m.RPN.ASPECT_RATIOS), anchor_stride=m.RPN.ANCHOR_STRIDE[0],
+        num_classes=m.ROI_BOX_HEAD.NUM_CLASSES)

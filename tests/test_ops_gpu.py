@@ -215,5 +215,5 @@ def test_box_postprocess_matches_oracle(cuda_dev):
                                         cuda_semantics=True)
         assert n == rb.shape[0], (n, rb.shape)
         assert torch.equal(out[2][:n].cpu(), rl)
-        assert torch.allclose(out[1][:n].cpu(), rs, rtol=0, atol=2e-7)
+        assert torch.allclose(out[1][:n].cpu(), rs, rtol=0, atol=1e-6)    # 31-way softmax: exp + sum order
         assert torch.allclose(out[0][:n].cpu(), rb, rtol=0, atol=2e-3)
