@@ -65,12 +65,17 @@ typedef struct mega_conv_gemm_desc {
   int b_k_off, b_n_off; /* added to B's k / row coordinate, times batch index */
   long long out_z_off, res_z_off;
   int bias_z_off; /* added to the scale/bias index, times batch index */
-  /* split-K (batch must be 1): partial is [splits][n_img*out_h*out_w][cout] floats */
-  int splits;
-  float* partial;
+  /* persistent stream-K scheduling: at most max_ctas CTAs (0 = one per SM). `workspace` (device,
+   * >= mega_conv_gemm_workspace_bytes(), 256-byte aligned, ZERO-INITIALISED once; the kernel leaves
+   * its counter region zero) holds the tile counters and the partial accumulators of tiles whose
+   * K range is shared by several CTAs. Launches that may run concurrently need distinct workspaces. */
+  int max_ctas;
+  void* workspace;
+  long long workspace_bytes;
 } mega_conv_gemm_desc;
 
 int mega_conv_gemm_tf32(const mega_conv_gemm_desc* desc, void* stream);
+long long mega_conv_gemm_workspace_bytes(void);
 /* TMA fp32->tf32 conversion on load (round-to-nearest) on/off; returns the previous value. */
 int mega_set_tf32_rounding(int enable);
 

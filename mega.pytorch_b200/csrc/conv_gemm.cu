@@ -24,6 +24,7 @@ constexpr int kBM = 128;        // UMMA M (one CTA)
 constexpr int kBK = 32;         // floats per K slab = 128 bytes
 constexpr int kUmmaK = 8;       // tf32
 constexpr int kThreads = 192;   // 6 warps
+constexpr int kMaxCtas = 148;   // persistent grid: one CTA per SM
 
 struct ConvGemmParams {
   int tiles_w, tiles_h, tile_w, tile_h;
@@ -42,8 +43,12 @@ struct ConvGemmParams {
   long long out_z_off;
   long long res_z_off;
   int bias_z_off;
-  int splits;
-  float* partial;  // [splits][M_total][cout] when splits > 1
+  // stream-K decomposition
+  int m_tiles, n_tiles;      // per batch entry
+  int kb_per_tile;           // taps * k_chunks
+  long long total_units;     // batch * m_tiles * n_tiles * kb_per_tile
+  float* part_ws;            // [grid][2][128][BN] partial accumulators
+  int* counters;             // [tiles], zero between launches
 };
 
 template <int BN, int STAGES>
@@ -52,9 +57,49 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16 + 1024;  // + align slack
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 32 + 1024;  // + align slack
 };
 
+struct TileCoord {
+  int img, h0, w0, n0, batch;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, long long t, int bn) {
+  TileCoord c;
+  const int m_tile = static_cast<int>(t % p.m_tiles);
+  const long long rest = t / p.m_tiles;
+  const int n_tile = static_cast<int>(rest % p.n_tiles);
+  c.batch = static_cast<int>(rest / p.n_tiles);
+  const int tw_i = m_tile % p.tiles_w;
+  const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+  c.img = m_tile / (p.tiles_w * p.tiles_h);
+  c.h0 = th_i * p.tile_h;
+  c.w0 = tw_i * p.tile_w;
+  c.n0 = n_tile * bn;
+  return c;
+}
+
+__device__ __forceinline__ long long cta_first_unit(long long total, int grid, int c) {
+  return (total * c) / grid;
+}
+
+// the CTA whose unit range [first(c), first(c+1)) contains unit u
+__device__ __forceinline__ int unit_owner(long long total, int grid, long long u) {
+  int c = static_cast<int>((u * grid) / total);
+  if (c >= grid) c = grid - 1;
+  while (c + 1 < grid && cta_first_unit(total, grid, c + 1) <= u) ++c;
+  while (c > 0 && cta_first_unit(total, grid, c) > u) --c;
+  return c;
+}
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Persistent stream-K kernel. The work is the list of (tile, k-block) units, tiles ordered
+// (batch, n-tile, m-tile) with m fastest; CTA c owns the contiguous unit range
+// [c*U/G, (c+1)*U/G). A tile whose k-blocks straddle CTAs is finished by the last CTA to
+// arrive, which sums the partial accumulators (in CTA order -> deterministic) and runs the
+// epilogue. Accumulators are double-buffered in TMEM so the epilogue of item i overlaps the
+// MMAs of item i+1.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -66,25 +111,19 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  const int tile = blockIdx.x;
-  const int tw_i = tile % p.tiles_w;
-  const int th_i = (tile / p.tiles_w) % p.tiles_h;
-  const int img = tile / (p.tiles_w * p.tiles_h);
-  const int h0 = th_i * p.tile_h;
-  const int w0 = tw_i * p.tile_w;
-  const int n0 = blockIdx.y * BN;
-  const int batch = blockIdx.z / p.splits;
-  const int split = blockIdx.z % p.splits;
-  const int total_kb = p.taps_r * p.taps_s * p.k_chunks;
-  const int kb_begin = static_cast<int>((static_cast<long long>(total_kb) * split) / p.splits);
-  const int kb_end = static_cast<int>((static_cast<long long>(total_kb) * (split + 1)) / p.splits);
+  const int grid = gridDim.x;
+  const int cta = blockIdx.x;
+  const long long U = p.total_units;
+  const int KB = p.kb_per_tile;
+  const long long u_begin = cta_first_unit(U, grid, cta);
+  const long long u_end = cta_first_unit(U, grid, cta + 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -95,11 +134,14 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
   }
   tc_fence_before();
   __syncthreads();
@@ -111,23 +153,30 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        const int tap = kb / p.k_chunks;
-        const int kc = kb - tap * p.k_chunks;
-        const int r = tap / p.taps_s;
-        const int s = tap - r * p.taps_s;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* a_dst = smem + stage * L::kStageBytes;
-        uint8_t* b_dst = a_dst + L::kABytes;
-        mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-        tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + batch * p.a_c_off,
-                    w0 + s * p.dil - p.pad, h0 + r * p.dil - p.pad, img + batch * p.a_n_off);
-        tma_load_3d(b_dst, &tmB, &full_bar[stage], kc * kBK + batch * p.b_k_off,
-                    n0 + batch * p.b_n_off, tap);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+      for (long long u = u_begin; u < u_end;) {
+        const long long t = u / KB;
+        const int kb0 = static_cast<int>(u - t * KB);
+        const int kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
+        const TileCoord tc = decode_tile(p, t, BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int tap = kb / p.k_chunks;
+          const int kc = kb - tap * p.k_chunks;
+          const int r = tap / p.taps_s;
+          const int s = tap - r * p.taps_s;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * L::kStageBytes;
+          uint8_t* b_dst = a_dst + L::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + tc.batch * p.a_c_off,
+                      tc.w0 + s * p.dil - p.pad, tc.h0 + r * p.dil - p.pad, tc.img + tc.batch * p.a_n_off);
+          tma_load_3d(b_dst, &tmB, &full_bar[stage], kc * kBK + tc.batch * p.b_k_off,
+                      tc.n0 + tc.batch * p.b_n_off, tap);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
+        u += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
@@ -136,118 +185,173 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint32_t idesc = umma_idesc<2>(kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      int item = 0;
+      for (long long u = u_begin; u < u_end; ++item) {
+        const long long t = u / KB;
+        const int kb0 = static_cast<int>(u - t * KB);
+        const int kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
+        const int buf = item & 1;
+        const uint32_t use = static_cast<uint32_t>(item >> 1);
+        mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes;
-        const uint64_t adesc = umma_desc_sw128(a_addr);
-        const uint64_t bdesc = umma_desc_sw128(b_addr);
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+          const uint64_t adesc = umma_desc_sw128(a_addr);
+          const uint64_t bdesc = umma_desc_sw128(b_addr);
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          // advance 8 floats = 32 B inside the swizzle row: +2 in 16-byte units
-          umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc,
-                    (kb > kb_begin || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 8 floats = 32 B inside the swizzle row: +2 in 16-byte units
+            umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
+        umma_commit(&tmem_full_bar[buf]);
+        u += kb1 - kb0;
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
+    const int epi_tid = (warp - 2) * 32 + lane;
     const int hl = row / p.tile_w;
     const int wl = row - hl * p.tile_w;
-    const int h = h0 + hl;
-    const int w = w0 + wl;
-    const bool row_ok = (h < p.out_h) && (w < p.out_w);
-    const long long pix = (static_cast<long long>(img) * p.out_h + h) * p.out_w + w;
-
-    if (kb_end > kb_begin) {
-      mbar_wait(tmem_full_bar, 0);
+    int item = 0;
+    for (long long u = u_begin; u < u_end; ++item) {
+      const long long t = u / KB;
+      const int kb0 = static_cast<int>(u - t * KB);
+      const int kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
+      u += kb1 - kb0;
+      const TileCoord tc = decode_tile(p, t, BN);
+      const int buf = item & 1;
+      const uint32_t use = static_cast<uint32_t>(item >> 1);
+      mbar_wait(&tmem_full_bar[buf], use & 1);
       tc_fence_after();
-    }
-    const bool have_acc = kb_end > kb_begin;
-    float* out_row;
-    const float* res_row = nullptr;
-    if (p.splits > 1) {
-      const long long m_total = static_cast<long long>(p.n_img) * p.out_h * p.out_w;
-      out_row = p.partial + ((static_cast<long long>(blockIdx.z) * m_total) + pix) * p.cout;
-    } else {
-      out_row = p.out + batch * p.out_z_off + pix * p.out_ld;
-      if (p.residual) res_row = p.residual + batch * p.res_z_off + pix * p.res_ld;
-    }
-    const float* scale_p = p.scale ? p.scale + batch * p.bias_z_off : nullptr;
-    const float* bias_p = p.bias ? p.bias + batch * p.bias_z_off : nullptr;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_row) & 15) == 0) &&
-                        (res_row == nullptr || (reinterpret_cast<uintptr_t>(res_row) & 15) == 0);
+      const uint32_t tmem_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const bool complete = (kb0 == 0 && kb1 == KB);
+      bool finalize = complete;
+      int c_first = cta, c_last = cta;
+      if (!complete) {
+        // ---- publish this CTA's partial accumulator, then find out whether it arrived last
+        float* my_ws = p.part_ws + ((static_cast<long long>(cta) * 2 + (item == 0 ? 0 : 1)) * kBM + row) * BN;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t acc[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores
-      if (have_acc) {
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, acc);
-        tmem_ld_wait();
-      } else {
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t acc[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_row + c * 32, acc);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = 0u;
-      }
-      const int nb = n0 + c * 32;
-      if (!row_ok || nb >= p.cout) continue;
-      if (p.splits > 1) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (nb + j + 3 < p.cout && vec_ok) {
+          for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
                                    __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
-            *reinterpret_cast<float4*>(out_row + nb + j) = v;
-          } else {
-            for (int t = 0; t < 4; ++t)
-              if (nb + j + t < p.cout) out_row[nb + j + t] = __uint_as_float(acc[j + t]);
+            __stcg(reinterpret_cast<float4*>(my_ws + c * 32 + j), v);
           }
         }
-        continue;
+        __threadfence();
+        epi_bar_sync();
+        c_first = unit_owner(U, grid, t * KB);
+        c_last = unit_owner(U, grid, t * KB + KB - 1);
+        if (epi_tid == 0) {
+          const int parts = c_last - c_first + 1;
+          const int old = atomicAdd(&p.counters[t], 1);
+          const int last = (old == parts - 1);
+          if (last) p.counters[t] = 0;   // every part has arrived: leave the counter clean for the next launch
+          *epi_flag = last;
+        }
+        epi_bar_sync();
+        finalize = (*epi_flag != 0);
+        if (finalize) __threadfence();
       }
+      if (finalize) {
+        const int h = tc.h0 + hl;
+        const int w = tc.w0 + wl;
+        const bool row_ok = (h < p.out_h) && (w < p.out_w);
+        const long long pix = (static_cast<long long>(tc.img) * p.out_h + h) * p.out_w + w;
+        float* out_row = p.out + tc.batch * p.out_z_off + pix * p.out_ld;
+        const float* res_row = p.residual ? p.residual + tc.batch * p.res_z_off + pix * p.res_ld : nullptr;
+        const float* scale_p = p.scale ? p.scale + tc.batch * p.bias_z_off : nullptr;
+        const float* bias_p = p.bias ? p.bias + tc.batch * p.bias_z_off : nullptr;
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_row) & 15) == 0) &&
+                            (res_row == nullptr || (reinterpret_cast<uintptr_t>(res_row) & 15) == 0);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t acc[32];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores
+          tmem_ld_32x32(tmem_row + c * 32, acc);
+          tmem_ld_wait();
+          const int nb = tc.n0 + c * 32;
+          if (!row_ok || nb >= p.cout) continue;
+          if (!complete) {
+            // deterministic reduction: parts summed in CTA order, own part from TMEM
+            float sum[32];
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int n = nb + j;
-        if (n + 3 < p.cout && vec_ok) {
-          float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
-                                 __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
-          if (scale_p) {
-            const float4 sc = ldg_f4(scale_p + n);
-            v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+            for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+            for (int oc = c_first; oc <= c_last; ++oc) {
+              if (oc == cta) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(acc[j]);
+              } else {
+                const int slot = (cta_first_unit(U, grid, oc) >= t * KB) ? 0 : 1;
+                const float* ws = p.part_ws + ((static_cast<long long>(oc) * 2 + slot) * kBM + row) * BN + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + j));
+                  sum[j] += v.x; sum[j + 1] += v.y; sum[j + 2] += v.z; sum[j + 3] += v.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[j]);
           }
-          if (bias_p) {
-            const float4 bi = ldg_f4(bias_p + n);
-            v.x += bi.x; v.y += bi.y; v.z += bi.z; v.w += bi.w;
-          }
-          if (res_row) {
-            const float4 rr = ldg_f4(res_row + n);
-            v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-          }
-          if (p.relu) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-          }
-          *reinterpret_cast<float4*>(out_row + n) = v;
-        } else {
-          for (int t = 0; t < 4; ++t) {
-            if (n + t < p.cout) {
-              float v = __uint_as_float(acc[j + t]);
-              if (scale_p) v *= __ldg(scale_p + n + t);
-              if (bias_p) v += __ldg(bias_p + n + t);
-              if (res_row) v += __ldg(res_row + n + t);
-              if (p.relu) v = fmaxf(v, 0.f);
-              out_row[n + t] = v;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = nb + j;
+            if (n + 3 < p.cout && vec_ok) {
+              float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                                     __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+              if (scale_p) {
+                const float4 sc = ldg_f4(scale_p + n);
+                v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+              }
+              if (bias_p) {
+                const float4 bi = ldg_f4(bias_p + n);
+                v.x += bi.x; v.y += bi.y; v.z += bi.z; v.w += bi.w;
+              }
+              if (res_row) {
+                const float4 rr = ldg_f4(res_row + n);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              if (p.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(out_row + n) = v;
+            } else {
+              for (int tt = 0; tt < 4; ++tt) {
+                if (n + tt < p.cout) {
+                  float v = __uint_as_float(acc[j + tt]);
+                  if (scale_p) v *= __ldg(scale_p + n + tt);
+                  if (bias_p) v += __ldg(bias_p + n + tt);
+                  if (res_row) v += __ldg(res_row + n + tt);
+                  if (p.relu) v = fmaxf(v, 0.f);
+                  out_row[n + tt] = v;
+                }
+              }
             }
           }
         }
       }
+      // release the accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
   }
 
@@ -255,27 +359,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
-  }
-}
-
-// sums split-K partials and applies the epilogue
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long m_total,
-                                     int cout, float* __restrict__ out, long long out_ld,
-                                     const float* __restrict__ scale, const float* __restrict__ bias,
-                                     const float* __restrict__ residual, long long res_ld, int relu) {
-  const long long total = m_total * cout;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long m = i / cout;
-    const int n = static_cast<int>(i - m * cout);
-    float v = 0.f;
-    for (int s = 0; s < splits; ++s) v += partial[(static_cast<long long>(s) * m_total + m) * cout + n];
-    if (scale) v *= scale[n];
-    if (bias) v += bias[n];
-    if (residual) v += residual[m * res_ld + n];
-    if (relu) v = fmaxf(v, 0.f);
-    out[m * out_ld + n] = v;
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -300,6 +384,10 @@ static EncodeTiledFn get_encode_fn() {
 
 static int g_tf32_round = 1;  // TMA converts fp32 -> tf32 (round to nearest) while loading
 
+static int g_num_sms = 0;
+constexpr int kCounterSlots = 65536;   // ints at the head of the workspace
+constexpr int kMinUnits = 4;
+
 template <int BN, int STAGES>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid,
                       cudaStream_t stream) {
@@ -318,6 +406,11 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 }  // namespace mega
 
 using namespace mega;
+
+extern "C" long long mega_conv_gemm_workspace_bytes(void) {
+  return static_cast<long long>(kCounterSlots) * sizeof(int) +
+         static_cast<long long>(kMaxCtas) * 2 * kBM * 256 * sizeof(float);
+}
 
 extern "C" int mega_set_tf32_rounding(int enable) {
   int old = g_tf32_round;
@@ -339,9 +432,10 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
                  "conv_gemm: activation strides must be multiples of 4 floats");
   MEGA_ARG_CHECK((d->b_stride_n % 4) == 0 && (d->b_stride_tap % 4) == 0,
                  "conv_gemm: weight strides must be multiples of 4 floats");
-  MEGA_ARG_CHECK(d->batch >= 1 && d->splits >= 1, "conv_gemm: batch/splits must be >= 1");
-  MEGA_ARG_CHECK(d->splits == 1 || (d->batch == 1 && d->partial != nullptr),
-                 "conv_gemm: split-K needs batch==1 and a partial workspace");
+  MEGA_ARG_CHECK(d->batch >= 1, "conv_gemm: batch must be >= 1");
+  MEGA_ARG_CHECK(d->workspace != nullptr && d->workspace_bytes >= mega_conv_gemm_workspace_bytes(),
+                 "conv_gemm: workspace missing or smaller than mega_conv_gemm_workspace_bytes()");
+  MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(d->workspace) & 255) == 0, "conv_gemm: workspace must be 256-byte aligned");
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     mega_set_error("conv_gemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -414,10 +508,27 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
   p.out_z_off = d->out_z_off;
   p.res_z_off = d->res_z_off;
   p.bias_z_off = d->bias_z_off;
-  p.splits = d->splits;
-  p.partial = d->partial;
-
-  dim3 grid(p.tiles_w * p.tiles_h * p.n_img, mega_ceil_div(d->cout, d->block_n), d->batch * d->splits);
+  p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
+  p.n_tiles = mega_ceil_div(d->cout, d->block_n);
+  p.kb_per_tile = d->taps_r * d->taps_s * p.k_chunks;
+  const long long tiles = static_cast<long long>(d->batch) * p.m_tiles * p.n_tiles;
+  p.total_units = tiles * p.kb_per_tile;
+  MEGA_ARG_CHECK(tiles <= kCounterSlots, "conv_gemm: %lld output tiles exceed the %d counter slots", tiles, kCounterSlots);
+  MEGA_ARG_CHECK(p.total_units > 0, "conv_gemm: empty problem");
+  p.counters = static_cast<int*>(d->workspace);
+  p.part_ws = reinterpret_cast<float*>(static_cast<char*>(d->workspace) + kCounterSlots * sizeof(int));
+  if (g_num_sms == 0) {
+    int dev = 0;
+    MEGA_CUDA_CHECK(cudaGetDevice(&dev));
+    MEGA_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    if (g_num_sms > kMaxCtas) g_num_sms = kMaxCtas;
+  }
+  // persistent grid: one CTA per SM, but never fewer than kMinUnits k-blocks of work per CTA
+  long long ctas = p.total_units / kMinUnits;
+  if (ctas < 1) ctas = 1;
+  if (ctas > g_num_sms) ctas = g_num_sms;
+  if (d->max_ctas > 0 && ctas > d->max_ctas) ctas = d->max_ctas;
+  dim3 grid(static_cast<unsigned>(ctas), 1, 1);
   int rc;
   switch (d->block_n) {
     case 32: rc = launch_cfg<32, 8>(tmA, tmB, p, grid, stream); break;
@@ -425,15 +536,6 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
     case 128: rc = launch_cfg<128, 6>(tmA, tmB, p, grid, stream); break;
     default: rc = launch_cfg<256, 4>(tmA, tmB, p, grid, stream); break;
   }
-  if (rc != MEGA_OK) return rc;
-  if (d->splits > 1) {
-    const long long m_total = static_cast<long long>(d->n_img) * d->out_h * d->out_w;
-    const long long total = m_total * d->cout;
-    int blocks = static_cast<int>((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(d->partial, d->splits, m_total, d->cout, d->out, d->out_ld,
-                                                      d->scale, d->bias, d->residual, d->res_ld, d->relu);
-    MEGA_CUDA_CHECK(cudaGetLastError());
-  }
-  return MEGA_OK;
+  return rc;
 }
+

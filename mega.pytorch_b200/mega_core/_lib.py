@@ -46,8 +46,9 @@ class ConvGemmDesc(ctypes.Structure):
         ("a_c_off", c_int), ("a_n_off", c_int), ("b_k_off", c_int), ("b_n_off", c_int),
         ("out_z_off", c_ll), ("res_z_off", c_ll),
         ("bias_z_off", c_int),
-        ("splits", c_int),
-        ("partial", c_f32p),
+        ("max_ctas", c_int),
+        ("workspace", ctypes.c_void_p),
+        ("workspace_bytes", c_ll),
     ]
 
 
@@ -56,6 +57,7 @@ lib.mega_abi_version.restype = c_int
 lib.mega_device_ok.restype = c_int
 lib.mega_conv_gemm_tf32.argtypes = [ctypes.POINTER(ConvGemmDesc), ctypes.c_void_p]
 lib.mega_conv_gemm_tf32.restype = c_int
+lib.mega_conv_gemm_workspace_bytes.restype = c_ll
 lib.mega_set_tf32_rounding.argtypes = [c_int]
 lib.mega_set_tf32_rounding.restype = c_int
 
@@ -122,7 +124,7 @@ lib.mega_box_postprocess.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _f, _f,
 lib.mega_box_postprocess.restype = _i
 
 EXPORTS = [
-    "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm_tf32", "mega_set_tf32_rounding",
+    "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm_tf32", "mega_conv_gemm_workspace_bytes", "mega_set_tf32_rounding",
     "mega_nms_workspace_bytes", "mega_nms", "mega_rpn_select_workspace_bytes", "mega_rpn_select",
     "mega_roi_align_forward_nchw", "mega_roi_align_forward_nhwc", "mega_stem_im2col", "mega_maxpool3x3s2_nhwc",
     "mega_gather_rows", "mega_copy_rows", "mega_transpose_2d", "mega_relation_softmax", "mega_box_postprocess_workspace_bytes",

@@ -368,7 +368,6 @@ class MegaEngine(HeadCommon):
             s_need[ld] = max(s_need.get(ld, 0), 16 * rows * ld)
         self.S = {ld: z(n) for ld, n in s_need.items()}
         self.pooled = z(KP + R + KP, res * res * ch)            # up to (local 300 + global 75 [+ spare]) rois
-        self.fc_partial = z(16, KP + R + KP, D)
         self.fc0_out = z(KP + R + KP, D)
         self.roi_boxes, self.roi_batch = z(KP + R + KP, 4), z(KP + R + KP, dtype=torch.int32)
         # ---- per-frame index tables: pinned host mirror + device copy
@@ -442,9 +441,7 @@ class MegaEngine(HeadCommon):
         ops.roi_align_nhwc(r5, self.roi_boxes[:rows], bidx, c.pooler_scale, c.pooler_resolution,
                            c.pooler_resolution, c.sampling_ratio, pooled)
         x = self.fc0_out[:rows]
-        splits = 16 if rows <= 384 else 8
-        part = self.fc_partial.view(-1)[:splits * rows * self.feat_dim].view(splits, rows, self.feat_dim)
-        ops.linear(pooled, self.fc0_w, x, bias=self.fc0_b, relu=True, splits=splits, partial=part, block_n=128)
+        ops.linear(pooled, self.fc0_w, x, bias=self.fc0_b, relu=True)
         return x, boxes, cnt, spans
 
     def _push_local_rows(self, x_rows, boxes300, cnt_row, slot):
@@ -697,8 +694,7 @@ class BaseEngine(HeadCommon):
         pooled = self._buf("pooled", (KP, res * res * self.ch))
         ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)
         f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]))
-        part = self._buf("fc6_part", (4, KP, self.fc6_w.shape[0]))
-        ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True, splits=4, partial=part)
+        ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True)
         f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]))
         ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
         self.last_feats, self.last_props, self.last_cnt, self.last_pooled = feats, boxes[0], cnt, pooled

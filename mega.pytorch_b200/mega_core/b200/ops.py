@@ -14,7 +14,23 @@ LAUNCHES = [0]
 def _launch_conv_gemm(d):
     """single choke point of the tcgen05 kernel (bench.py wraps it with CUDA events for the roofline)"""
     check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
-    LAUNCHES[0] += 2 if d.splits > 1 else 1
+    LAUNCHES[0] += 1
+
+
+_gemm_ws = {}
+WS_LANE = [0]   # launches that may overlap on different streams must use different lanes
+
+
+def gemm_workspace(device):
+    """zero-initialised stream-K workspace, one per (device, lane): kernels on one stream are
+    ordered; kernels issued on concurrent streams must select distinct lanes (WS_LANE) so they do
+    not share tile counters"""
+    key = (device, WS_LANE[0])
+    ws = _gemm_ws.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.mega_conv_gemm_workspace_bytes()), dtype=torch.uint8, device=device)
+        _gemm_ws[key] = ws
+    return ws
 
 
 def pick_tile(h, w):
@@ -29,28 +45,26 @@ def pick_tile(h, w):
     return best[1], best[2]
 
 
-def pick_block_n(cout, m_tiles, batch=1):
-    """Largest N tile that still gives every SM a CTA (148 SMs); small layers favour more CTAs."""
-    for bn in (256, 128, 64):
-        if cout >= bn and m_tiles * -(-cout // bn) * batch >= 148:
-            return bn
-    for bn in (32, 64, 128, 256):
+def pick_block_n(cout, m_tiles=0, batch=1):
+    """N tile of the stream-K kernel: work is balanced over the SMs at k-block granularity whatever the
+    tile count, so the widest tile that does not over-pad `cout` wins (higher FLOP per byte staged)."""
+    for bn in (32, 64, 128):
         if cout <= bn:
             return bn
-    return 64
+    return 256
 
 
 def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, residual=None,
               relu=False, tile=None, block_n=None, cout=None, k=None, batch=1, a_c_off=0,
-              a_n_off=0, b_k_off=0, b_n_off=0, out_z_off=0, res_z_off=0, bias_z_off=0, splits=1,
-              partial=None, out_hw=None):
+              a_n_off=0, b_k_off=0, b_n_off=0, out_z_off=0, res_z_off=0, bias_z_off=0, max_ctas=0,
+              out_hw=None):
     """out[n,h,w,:] = act(scale * conv(a, w) + bias + residual)   (TF32 tensor cores)
 
     a   : [N,H,W,C] fp32 view (innermost stride 1; other strides multiples of 4 floats)
     w   : [taps, rows, K] fp32 (K contiguous)
     out : [N,Ho,Wo,>=cout] fp32 view (innermost stride 1)
     """
-    require_cuda(a, w, out, scale, bias, residual, partial)
+    require_cuda(a, w, out, scale, bias, residual)
     assert a.dtype == torch.float32 and w.dtype == torch.float32 and out.dtype == torch.float32
     assert a.dim() == 4 and w.dim() == 3 and out.dim() == 4
     assert a.stride(3) == 1 and w.stride(2) == 1 and out.stride(3) == 1
@@ -86,13 +100,15 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.a_c_off, d.a_n_off, d.b_k_off, d.b_n_off = a_c_off, a_n_off, b_k_off, b_n_off
     d.out_z_off, d.res_z_off = out_z_off, res_z_off
     d.bias_z_off = bias_z_off
-    d.splits = splits
-    d.partial = ptr(partial)
+    d.max_ctas = max_ctas
+    ws = gemm_workspace(a.device)
+    d.workspace = ptr(ws)
+    d.workspace_bytes = ws.numel()
     _launch_conv_gemm(d)
     return out
 
 
-def linear(x, w, out, *, bias=None, relu=False, residual=None, splits=1, partial=None, block_n=None):
+def linear(x, w, out, *, bias=None, relu=False, residual=None, block_n=None, max_ctas=0):
     """out[m,:] = act(x[m,:] @ w.T + bias + residual[m,:]); x [M,K], w [N,K], out [M,N]."""
     m, kdim = x.shape
     nrows = w.shape[0]
@@ -103,8 +119,8 @@ def linear(x, w, out, *, bias=None, relu=False, residual=None, splits=1, partial
         r4 = residual.as_strided((1, 1, m, residual.shape[1]),
                                  (residual.stride(0) * m, residual.stride(0) * m, residual.stride(0), 1))
     w3 = w.as_strided((1, nrows, kdim), (w.stride(0) * nrows, w.stride(0), 1))
-    return conv_gemm(a4, w3, o4, bias=bias, relu=relu, residual=r4, tile=(1, 128), cout=nrows,
-                     splits=splits, partial=partial, block_n=block_n)
+    return conv_gemm(a4, w3, o4, bias=bias, relu=relu, residual=r4, tile=(1, 128), cout=nrows, block_n=block_n,
+                     max_ctas=max_ctas)
 
 
 # --------------------------------------------------------------------------- non-GEMM kernels

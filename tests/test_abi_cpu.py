@@ -45,7 +45,7 @@ def test_argument_validation_without_device():
     assert lib.mega_box_postprocess_workspace_bytes(300, 31) > 0
     assert lib.mega_box_postprocess_workspace_bytes(600, 31) == -1
     d = _lib.ConvGemmDesc()
-    d.tile_h, d.tile_w, d.block_n, d.batch, d.splits = 3, 40, 64, 1, 1
+    d.tile_h, d.tile_w, d.block_n, d.batch = 3, 40, 64, 1
     assert lib.mega_conv_gemm_tf32(ctypes.byref(d), None) != 0
     assert b"tile_h*tile_w" in lib.mega_last_error()
 
@@ -55,8 +55,7 @@ def test_tile_and_block_heuristics():
     for h, w in ((38, 63), (150, 250), (75, 125), (1, 375), (12, 20)):
         th, tw = ops.pick_tile(h, w)
         assert th * tw == 128
-    assert ops.pick_block_n(60, 40) == 64
-    assert ops.pick_block_n(1024, 38) in (128, 256)
+    assert ops.pick_block_n(60) == 64 and ops.pick_block_n(1024) == 256 and ops.pick_block_n(31) == 32
 
 
 def test_engine_tables_host_logic():

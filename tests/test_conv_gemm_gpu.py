@@ -70,9 +70,8 @@ def test_linear_matches_fp32(cuda_dev, m, k, n, splits):
     b = torch.randn(n, generator=g)
     ref = (x.double() @ w.double().t() + b.double()).relu().float()
     out = torch.full((m, n), float("nan"), device=cuda_dev)
-    partial = torch.empty(splits, m, n, device=cuda_dev) if splits > 1 else None
-    ops.linear(x.to(cuda_dev), w.to(cuda_dev), out, bias=b.to(cuda_dev), relu=True, splits=splits,
-               partial=partial)
+    ops.linear(x.to(cuda_dev), w.to(cuda_dev), out, bias=b.to(cuda_dev), relu=True,
+               max_ctas=(0 if splits > 1 else 3))
     torch.cuda.synchronize()
     assert torch.isfinite(out).all()
     assert _rel_err(out, ref) < TOL

@@ -98,12 +98,9 @@ x = torch.randn(m, k, device=dev)
 w = torch.randn(n, k, device=dev) / k ** 0.5
 out = torch.empty(m, n, device=dev)
 fc = {}
-for splits in (8, 16, 32):
-    partial = torch.empty(splits, m, n, device=dev)
-    for bn in (64, 128):
-        t = timeit(lambda: ops.linear(x, w, out, splits=splits, partial=partial, block_n=bn), iters=10)
-        fc["splits%d_bn%d" % (splits, bn)] = {"us": t * 1e6, "weight_GBps": k * n * 4 / t / 1e9,
-                                              "tflops": 2.0 * m * k * n / t / 1e12}
+for bn in (128, 256):
+    t = timeit(lambda: ops.linear(x, w, out, block_n=bn), iters=10)
+    fc["bn%d" % bn] = {"us": t * 1e6, "weight_GBps": k * n * 4 / t / 1e9, "tflops": 2.0 * m * k * n / t / 1e12}
 t = timeit(lambda: torch.mm(x, w.t()), iters=10)
 fc["cublas_fp32"] = {"us": t * 1e6}
 res["fc0"] = fc
