@@ -57,7 +57,7 @@ typedef struct mega_conv_gemm_desc {
   const float* residual; /* same indexing as out with res_ld, or NULL */
   long long res_ld;
   int relu;
-  /* tiling: tile_h*tile_w == 128 output pixels per CTA, block_n in {32,64,128,256} */
+  /* tiling: tile_h*tile_w == 128 output pixels per CTA, block_n in {32,64,96,128,160,192,256} */
   int tile_h, tile_w, block_n;
   /* batched mode (grid.z = batch): per-batch coordinate offsets */
   int batch;
@@ -70,6 +70,8 @@ typedef struct mega_conv_gemm_desc {
    * its counter region zero) holds the tile counters and the partial accumulators of tiles whose
    * K range is shared by several CTAs. Launches that may run concurrently need distinct workspaces. */
   int max_ctas;
+  int stream_k; /* 1: split tiles across CTAs at k-block granularity (balances any tile count over the
+                   SMs; partial tiles are reduced by the last CTA to arrive, in CTA order); 0: whole tiles */
   void* workspace;
   long long workspace_bytes;
 } mega_conv_gemm_desc;

@@ -47,6 +47,8 @@ struct ConvGemmParams {
   int m_tiles, n_tiles;      // per batch entry
   int kb_per_tile;           // taps * k_chunks
   long long total_units;     // batch * m_tiles * n_tiles * kb_per_tile
+  long long total_tiles;     // batch * m_tiles * n_tiles
+  int stream_k;              // 1: k-block granular split across CTAs, 0: whole tiles round-robin
   float* part_ws;            // [grid][2][128][BN] partial accumulators
   int* counters;             // [tiles], zero between launches
 };
@@ -92,6 +94,34 @@ __device__ __forceinline__ int unit_owner(long long total, int grid, long long u
   return c;
 }
 
+// the (tile, k-block range) items of one CTA, identical for the three warp roles
+struct WorkIter {
+  long long u, u_end, tile, tiles;
+  int KB, grid;
+  bool sk;
+  __device__ __forceinline__ WorkIter(const ConvGemmParams& p, int cta, int grid_)
+      : tile(cta), tiles(p.total_tiles), KB(p.kb_per_tile), grid(grid_), sk(p.stream_k != 0) {
+    u = cta_first_unit(p.total_units, grid_, cta);
+    u_end = cta_first_unit(p.total_units, grid_, cta + 1);
+  }
+  __device__ __forceinline__ bool next(long long& t, int& kb0, int& kb1) {
+    if (sk) {
+      if (u >= u_end) return false;
+      t = u / KB;
+      kb0 = static_cast<int>(u - t * KB);
+      kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
+      u += kb1 - kb0;
+      return true;
+    }
+    if (tile >= tiles) return false;
+    t = tile;
+    kb0 = 0;
+    kb1 = KB;
+    tile += grid;
+    return true;
+  }
+};
+
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // Persistent stream-K kernel. The work is the list of (tile, k-block) units, tiles ordered
@@ -105,6 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const ConvGemmParams p) {
   using L = SmemLayout<BN, STAGES>;
+  constexpr uint32_t kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   // the 128B swizzle pattern is a function of the absolute smem address: align to 1024 B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -122,8 +153,6 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int cta = blockIdx.x;
   const long long U = p.total_units;
   const int KB = p.kb_per_tile;
-  const long long u_begin = cta_first_unit(U, grid, cta);
-  const long long u_end = cta_first_unit(U, grid, cta + 1);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -141,7 +170,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, kTmemCols);
   }
   tc_fence_before();
   __syncthreads();
@@ -153,10 +182,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long u = u_begin; u < u_end;) {
-        const long long t = u / KB;
-        const int kb0 = static_cast<int>(u - t * KB);
-        const int kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
+      WorkIter it(p, cta, grid);
+      long long t;
+      int kb0, kb1;
+      while (it.next(t, kb0, kb1)) {
         const TileCoord tc = decode_tile(p, t, BN);
         for (int kb = kb0; kb < kb1; ++kb) {
           const int tap = kb / p.k_chunks;
@@ -176,7 +205,6 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             phase ^= 1;
           }
         }
-        u += kb1 - kb0;
       }
     }
   } else if (warp == 1) {
@@ -185,16 +213,15 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint32_t idesc = umma_idesc<2>(kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      int item = 0;
-      for (long long u = u_begin; u < u_end; ++item) {
-        const long long t = u / KB;
-        const int kb0 = static_cast<int>(u - t * KB);
-        const int kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
+      WorkIter it(p, cta, grid);
+      long long t;
+      int kb0, kb1;
+      for (int item = 0; it.next(t, kb0, kb1); ++item) {
         const int buf = item & 1;
         const uint32_t use = static_cast<uint32_t>(item >> 1);
         mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * BN;
+        const uint32_t tmem_d = tmem_base + buf * (kTmemCols / 2);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -214,7 +241,6 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
         umma_commit(&tmem_full_bar[buf]);
-        u += kb1 - kb0;
       }
     }
   } else {
@@ -224,18 +250,16 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int epi_tid = (warp - 2) * 32 + lane;
     const int hl = row / p.tile_w;
     const int wl = row - hl * p.tile_w;
-    int item = 0;
-    for (long long u = u_begin; u < u_end; ++item) {
-      const long long t = u / KB;
-      const int kb0 = static_cast<int>(u - t * KB);
-      const int kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
-      u += kb1 - kb0;
+    WorkIter it(p, cta, grid);
+    long long t;
+    int kb0, kb1;
+    for (int item = 0; it.next(t, kb0, kb1); ++item) {
       const TileCoord tc = decode_tile(p, t, BN);
       const int buf = item & 1;
       const uint32_t use = static_cast<uint32_t>(item >> 1);
       mbar_wait(&tmem_full_bar[buf], use & 1);
       tc_fence_after();
-      const uint32_t tmem_row = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t tmem_row = tmem_base + buf * (kTmemCols / 2) + (static_cast<uint32_t>(q * 32) << 16);
       const bool complete = (kb0 == 0 && kb1 == KB);
       bool finalize = complete;
       int c_first = cta, c_last = cta;
@@ -359,7 +383,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -424,8 +448,9 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
   MEGA_ARG_CHECK(d->tile_h > 0 && d->tile_w > 0 && d->tile_h * d->tile_w == kBM,
                  "conv_gemm: tile_h*tile_w must be 128 (got %dx%d)", d->tile_h, d->tile_w);
   MEGA_ARG_CHECK(d->tile_w <= 256 && d->tile_h <= 256, "conv_gemm: tile too large for a TMA box");
-  MEGA_ARG_CHECK(d->block_n == 32 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256,
-                 "conv_gemm: block_n must be 32/64/128/256");
+  MEGA_ARG_CHECK(d->block_n == 32 || d->block_n == 64 || d->block_n == 96 || d->block_n == 128 ||
+                     d->block_n == 160 || d->block_n == 192 || d->block_n == 256,
+                 "conv_gemm: block_n must be one of 32/64/96/128/160/192/256");
   MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(d->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->b) & 15) == 0,
                  "conv_gemm: operand base pointers must be 16-byte aligned");
   MEGA_ARG_CHECK((d->a_stride_w % 4) == 0 && (d->a_stride_h % 4) == 0 && (d->a_stride_n % 4) == 0,
@@ -513,6 +538,8 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
   p.kb_per_tile = d->taps_r * d->taps_s * p.k_chunks;
   const long long tiles = static_cast<long long>(d->batch) * p.m_tiles * p.n_tiles;
   p.total_units = tiles * p.kb_per_tile;
+  p.total_tiles = tiles;
+  p.stream_k = d->stream_k ? 1 : 0;
   MEGA_ARG_CHECK(tiles <= kCounterSlots, "conv_gemm: %lld output tiles exceed the %d counter slots", tiles, kCounterSlots);
   MEGA_ARG_CHECK(p.total_units > 0, "conv_gemm: empty problem");
   p.counters = static_cast<int*>(d->workspace);
@@ -524,7 +551,7 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
     if (g_num_sms > kMaxCtas) g_num_sms = kMaxCtas;
   }
   // persistent grid: one CTA per SM, but never fewer than kMinUnits k-blocks of work per CTA
-  long long ctas = p.total_units / kMinUnits;
+  long long ctas = p.stream_k ? p.total_units / kMinUnits : tiles;
   if (ctas < 1) ctas = 1;
   if (ctas > g_num_sms) ctas = g_num_sms;
   if (d->max_ctas > 0 && ctas > d->max_ctas) ctas = d->max_ctas;
@@ -533,7 +560,10 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
   switch (d->block_n) {
     case 32: rc = launch_cfg<32, 8>(tmA, tmB, p, grid, stream); break;
     case 64: rc = launch_cfg<64, 8>(tmA, tmB, p, grid, stream); break;
+    case 96: rc = launch_cfg<96, 6>(tmA, tmB, p, grid, stream); break;
     case 128: rc = launch_cfg<128, 6>(tmA, tmB, p, grid, stream); break;
+    case 160: rc = launch_cfg<160, 5>(tmA, tmB, p, grid, stream); break;
+    case 192: rc = launch_cfg<192, 4>(tmA, tmB, p, grid, stream); break;
     default: rc = launch_cfg<256, 4>(tmA, tmB, p, grid, stream); break;
   }
   return rc;

@@ -7,8 +7,8 @@
 // Here nothing of that is materialised: for every (query n, key m) pair the four log-ratios,
 // the 64 sin/cos features, the 64->16 projection, ReLU, log and the scaled logit are computed in
 // registers and the soft-max is taken in place over the [G,N,M] logits produced by the
-// tcgen05 Q.K^T GEMM. One CTA per query row; three light passes over its [16,M] slice (L2-resident):
-// logits + max, exp + sum, normalise.
+// tcgen05 Q.K^T GEMM. One CTA per query row; two passes over its [16,M] slice (L2-resident):
+// logits + online (max, sum), then normalise.
 #include "common.cuh"
 #include "mega_b200.h"
 
@@ -71,11 +71,15 @@ relation_softmax_kernel(const RelParams p) {
   }
   float* srow = p.s + static_cast<long long>(n) * p.ldm;
 
-  float mx[kGroups];
+  // running (max, sum) per head: one read+write pass produces the logits and the statistics,
+  // a second read+write pass normalises (online soft-max; same value as exp(l - max) / sum)
+  float mx[kGroups], sm[kGroups];
 #pragma unroll
-  for (int g = 0; g < kGroups; ++g) mx[g] = -INFINITY;
+  for (int g = 0; g < kGroups; ++g) {
+    mx[g] = -INFINITY;
+    sm[g] = 0.f;
+  }
 
-  // ---- pass 1: logits (+ position bias), running max per head
   for (int m = tid; m < m_valid; m += blockDim.x) {
     float bias[kGroups];
     if (has_pe) {
@@ -94,11 +98,15 @@ relation_softmax_kernel(const RelParams p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         const float d100 = __fmul_rn(delta[c], 100.0f);
-#pragma unroll
+#pragma unroll 1
         for (int kf = 0; kf < 8; ++kf) {
           const float arg = __fdiv_rn(d100, dim_s[kf]);
-          float sv, cv;
-          sincosf(arg, &sv, &cv);
+          // Cody-Waite reduction to [-pi, pi] (|arg| < ~1e3 here), then the SFU sin/cos
+          // (abs error ~5e-7, far below the 1e-5 tolerance on the soft-max output)
+          const float kq = rintf(arg * 0.15915494309189535f);
+          float r = fmaf(-kq, 6.28125f, arg);
+          r = fmaf(-kq, 1.9353071795864769e-3f, r);
+          const float sv = __sinf(r), cv = __cosf(r);
           const float4* ws = reinterpret_cast<const float4*>(&wg_s[c * 16 + kf][0]);
           const float4* wc = reinterpret_cast<const float4*>(&wg_s[c * 16 + 8 + kf][0]);
 #pragma unroll
@@ -112,7 +120,7 @@ relation_softmax_kernel(const RelParams p) {
         }
       }
 #pragma unroll
-      for (int g = 0; g < kGroups; ++g) bias[g] = logf(__fadd_rn(fmaxf(bias[g], 0.f), 1e-6f));
+      for (int g = 0; g < kGroups; ++g) bias[g] = __logf(__fadd_rn(fmaxf(bias[g], 0.f), 1e-6f));
     } else {
 #pragma unroll
       for (int g = 0; g < kGroups; ++g) bias[g] = 0.f;
@@ -122,59 +130,50 @@ relation_softmax_kernel(const RelParams p) {
       float* sp = srow + g * p.head_stride + m;
       const float l = __fadd_rn(bias[g], __fmul_rn(p.scale, *sp));
       *sp = l;
-      mx[g] = fmaxf(mx[g], l);
+      const float nm = fmaxf(mx[g], l);
+      sm[g] = sm[g] * __expf(mx[g] - nm) + __expf(l - nm);
+      mx[g] = nm;
     }
   }
 
-  // ---- block reduction of the max per head
+  // ---- block reduction of (max, sum) per head
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int g = 0; g < kGroups; ++g) {
-    float m_ = mx[g];
+    float m_ = mx[g], s_ = sm[g];
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) m_ = fmaxf(m_, __shfl_xor_sync(0xffffffffu, m_, off));
-    if (lane == 0) red_max[warp][g] = m_;
+    for (int off = 16; off > 0; off >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m_, off);
+      const float os = __shfl_xor_sync(0xffffffffu, s_, off);
+      const float nm = fmaxf(m_, om);
+      const float a = (m_ == -INFINITY) ? 0.f : s_ * __expf(m_ - nm);
+      const float b = (om == -INFINITY) ? 0.f : os * __expf(om - nm);
+      s_ = a + b;
+      m_ = nm;
+    }
+    if (lane == 0) {
+      red_max[warp][g] = m_;
+      red_sum[warp][g] = s_;
+    }
   }
   __syncthreads();
   if (tid < kGroups) {
     float m_ = -INFINITY;
     for (int w = 0; w < kRelThreads / 32; ++w) m_ = fmaxf(m_, red_max[w][tid]);
+    float s_ = 0.f;
+    for (int w = 0; w < kRelThreads / 32; ++w)
+      if (red_max[w][tid] != -INFINITY) s_ += red_sum[w][tid] * __expf(red_max[w][tid] - m_);
     fin_max[tid] = m_;
+    fin_inv[tid] = 1.0f / s_;
   }
   __syncthreads();
 
-  // ---- pass 2: exact two-pass soft-max (sum of exp(l - max) recomputed, like torch softmax)
-  float part[kGroups];
-#pragma unroll
-  for (int g = 0; g < kGroups; ++g) part[g] = 0.f;
-  for (int m = tid; m < m_valid; m += blockDim.x) {
-#pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-      float* sp = srow + g * p.head_stride + m;
-      const float e = expf(__fsub_rn(*sp, fin_max[g]));
-      *sp = e;
-      part[g] += e;
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < kGroups; ++g) {
-    float s_ = part[g];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s_ += __shfl_xor_sync(0xffffffffu, s_, off);
-    if (lane == 0) red_sum[warp][g] = s_;
-  }
-  __syncthreads();
-  if (tid < kGroups) {
-    float s_ = 0.f;
-    for (int w = 0; w < kRelThreads / 32; ++w) s_ += red_sum[w][tid];
-    fin_inv[tid] = s_;
-  }
-  __syncthreads();
+  // ---- pass 2: normalise in place; padded key columns get probability 0
   for (int m = tid; m < p.ldm; m += blockDim.x) {
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
       float* sp = srow + g * p.head_stride + m;
-      *sp = (m < m_valid) ? __fdiv_rn(*sp, fin_inv[g]) : 0.f;
+      *sp = (m < m_valid) ? __expf(*sp - fin_max[g]) * fin_inv[g] : 0.f;
     }
   }
 }

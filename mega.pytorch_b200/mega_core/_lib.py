@@ -47,6 +47,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("out_z_off", c_ll), ("res_z_off", c_ll),
         ("bias_z_off", c_int),
         ("max_ctas", c_int),
+        ("stream_k", c_int),
         ("workspace", ctypes.c_void_p),
         ("workspace_bytes", c_ll),
     ]

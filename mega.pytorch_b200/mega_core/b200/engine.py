@@ -16,6 +16,7 @@ same arithmetic):
     so a steady-state frame is a fixed launch sequence (CUDA-graph capturable).
 """
 import math
+import os
 from collections import deque
 
 import numpy as np
@@ -253,6 +254,8 @@ class HeadCommon:
 
     def __init__(self, sd, cfg, dev):
         self.cfg, self.dev = cfg, dev
+        # per-shape (tile width, scheduling) selection by on-device timing the first time a shape is seen
+        ops.AUTOTUNE[0] = os.environ.get("MEGA_B200_AUTOTUNE", "1") != "0"
         self.backbone = Backbone(sd, dev)
         self.rpn_w = pack_conv(sd["rpn.head.conv.weight"], dev)
         self.rpn_b = sd["rpn.head.conv.bias"].float().contiguous().to(dev)

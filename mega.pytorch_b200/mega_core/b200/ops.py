@@ -45,19 +45,78 @@ def pick_tile(h, w):
     return best[1], best[2]
 
 
+# ---- per-shape kernel configuration (block_n, stream_k, max_ctas), filled by autotune()
+TUNED = {}
+AUTOTUNE = [False]
+BLOCK_NS = (32, 64, 96, 128, 160, 192, 256)
+
+
+def _shape_key(d):
+    return (d.a_n, d.a_h, d.a_w, d.a_c, d.a_stride_w, d.b_n, d.b_k, d.taps_r, d.taps_s, d.dil, d.k_per_tap, d.n_img,
+            d.out_h, d.out_w, d.cout, d.tile_h, d.tile_w, d.batch, bool(d.residual), d.out_ld)
+
+
+def _candidates(cout):
+    cands = []
+    for bn in BLOCK_NS:
+        if bn >= 2 * cout and bn > 32:
+            continue
+        for sk in (0, 1):
+            cands.append((bn, sk))
+    return cands
+
+
+def _autotune(d):
+    """time every (block_n, stream_k) candidate for this exact problem on the device (CUDA events,
+    3 warm + 5 timed launches each) and remember the fastest; outputs are overwritten identically"""
+    best = None
+    for bn, sk in _candidates(d.cout):
+        d.block_n, d.stream_k = bn, sk
+        try:
+            for _ in range(2):
+                check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(8):
+                check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
+            e1.record()
+            e1.synchronize()
+            t = e0.elapsed_time(e1) / 8
+        except _lib.MegaError:
+            continue
+        if best is None or t < best[0]:
+            best = (t, bn, sk)
+    return best
+
+
+def pick_config(cout, m_tiles, batch, kb_per_tile):
+    """(block_n, stream_k) when no autotuned entry exists. Deep reductions balance best at k-block
+    granularity (stream-K, widest tile); shallow ones run whole tiles, with the tile width chosen to
+    minimise waves x bytes staged per k-block on 148 SMs."""
+    if kb_per_tile >= 48:
+        for bn in (32, 64, 128):
+            if cout <= bn:
+                return bn, 1
+        return 256, 1
+    best = None
+    for bn in BLOCK_NS:
+        if bn >= 2 * cout and bn > 32:
+            continue
+        tiles = m_tiles * (-(-cout // bn)) * batch
+        cost = (-(-tiles // 148)) * (128 + bn)
+        if best is None or cost < best[0] or (cost == best[0] and bn > best[1]):
+            best = (cost, bn)
+    return best[1], 0
+
+
 def pick_block_n(cout, m_tiles=0, batch=1):
-    """N tile of the stream-K kernel: work is balanced over the SMs at k-block granularity whatever the
-    tile count, so the widest tile that does not over-pad `cout` wins (higher FLOP per byte staged)."""
-    for bn in (32, 64, 128):
-        if cout <= bn:
-            return bn
-    return 256
+    return pick_config(cout, max(m_tiles, 1), batch, 1)[0]
 
 
 def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, residual=None,
               relu=False, tile=None, block_n=None, cout=None, k=None, batch=1, a_c_off=0,
               a_n_off=0, b_k_off=0, b_n_off=0, out_z_off=0, res_z_off=0, bias_z_off=0, max_ctas=0,
-              out_hw=None):
+              stream_k=None, out_hw=None):
     """out[n,h,w,:] = act(scale * conv(a, w) + bias + residual)   (TF32 tensor cores)
 
     a   : [N,H,W,C] fp32 view (innermost stride 1; other strides multiples of 4 floats)
@@ -95,8 +154,11 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     th, tw = tile if tile is not None else pick_tile(oh, ow)
     d.tile_h, d.tile_w = th, tw
     m_tiles = on * (-(-oh // th)) * (-(-ow // tw))
-    d.block_n = block_n if block_n is not None else pick_block_n(d.cout, m_tiles, batch)
     d.batch = batch
+    kb_per_tile = taps[0] * taps[1] * (-(-d.k_per_tap // 32))
+    auto_bn, auto_sk = pick_config(d.cout, m_tiles, batch, kb_per_tile)
+    d.block_n = block_n if block_n is not None else auto_bn
+    d.stream_k = auto_sk if stream_k is None else int(stream_k)
     d.a_c_off, d.a_n_off, d.b_k_off, d.b_n_off = a_c_off, a_n_off, b_k_off, b_n_off
     d.out_z_off, d.res_z_off = out_z_off, res_z_off
     d.bias_z_off = bias_z_off
@@ -104,11 +166,21 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     ws = gemm_workspace(a.device)
     d.workspace = ptr(ws)
     d.workspace_bytes = ws.numel()
+    if block_n is None and stream_k is None:
+        key = _shape_key(d)
+        cfg = TUNED.get(key)
+        aliased = residual is not None and residual.data_ptr() == out.data_ptr()   # in-place: not idempotent
+        if cfg is None and AUTOTUNE[0] and not aliased and not torch.cuda.is_current_stream_capturing():
+            best = _autotune(d)
+            if best is not None:
+                cfg = TUNED[key] = (best[1], best[2], best[0])
+        if cfg is not None:
+            d.block_n, d.stream_k = cfg[0], cfg[1]
     _launch_conv_gemm(d)
     return out
 
 
-def linear(x, w, out, *, bias=None, relu=False, residual=None, block_n=None, max_ctas=0):
+def linear(x, w, out, *, bias=None, relu=False, residual=None, block_n=None, max_ctas=0, stream_k=None):
     """out[m,:] = act(x[m,:] @ w.T + bias + residual[m,:]); x [M,K], w [N,K], out [M,N]."""
     m, kdim = x.shape
     nrows = w.shape[0]
@@ -120,7 +192,7 @@ def linear(x, w, out, *, bias=None, relu=False, residual=None, block_n=None, max
                                  (residual.stride(0) * m, residual.stride(0) * m, residual.stride(0), 1))
     w3 = w.as_strided((1, nrows, kdim), (w.stride(0) * nrows, w.stride(0), 1))
     return conv_gemm(a4, w3, o4, bias=bias, relu=relu, residual=r4, tile=(1, 128), cout=nrows, block_n=block_n,
-                     max_ctas=max_ctas)
+                     max_ctas=max_ctas, stream_k=stream_k)
 
 
 # --------------------------------------------------------------------------- non-GEMM kernels

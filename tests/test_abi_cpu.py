@@ -55,7 +55,8 @@ def test_tile_and_block_heuristics():
     for h, w in ((38, 63), (150, 250), (75, 125), (1, 375), (12, 20)):
         th, tw = ops.pick_tile(h, w)
         assert th * tw == 128
-    assert ops.pick_block_n(60) == 64 and ops.pick_block_n(1024) == 256 and ops.pick_block_n(31) == 32
+    assert ops.pick_config(60, 38, 1, 32)[0] in (32, 64) and ops.pick_config(1024, 38, 1, 288) == (256, 1)
+    assert ops.pick_config(256, 38, 1, 32) == (96, 0)
 
 
 def test_engine_tables_host_logic():

@@ -96,3 +96,21 @@ def test_batched_heads(cuda_dev):
     torch.cuda.synchronize()
     assert _rel_err(out[:, :, :mk], ref) < TOL
     assert (out[:, :, mk:] == 0).all()
+
+
+@pytest.mark.parametrize("bn,sk", [(96, 0), (96, 1), (160, 0), (160, 1), (192, 1), (256, 0), (64, 1), (32, 1)])
+def test_stream_k_and_wide_tiles(cuda_dev, bn, sk):
+    """every N-tile width in both scheduling modes on a 3x3 conv whose tile count (57) does not divide the SMs"""
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(bn + sk)
+    n, h, w, cin, cout = 1, 38, 63, 160, 320
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    ref = F.conv2d(x, wt, None, 1, 1).relu()
+    a = x.permute(0, 2, 3, 1).contiguous().to(cuda_dev)
+    wp = wt.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().to(cuda_dev)
+    out = torch.full((n, h, w, cout), float("nan"), device=cuda_dev)
+    for _ in range(2):          # twice: the tile counters must come back to zero
+        ops.conv_gemm(a, wp, out, taps=(3, 3), pad=1, relu=True, block_n=bn, stream_k=sk)
+    torch.cuda.synchronize()
+    assert _rel_err(out.permute(0, 3, 1, 2), ref) < TOL

@@ -74,15 +74,16 @@ for name, n, h, wd, cin, cout, ks, dil in shapes:
     bi = torch.zeros(cout, device=dev)
     flops = 2.0 * n * h * wd * cin * cout * ks * ks
     entry = {}
-    for bn in (64, 128, 256):
-        if bn > cout:
+    for bn in ops.BLOCK_NS:
+        if bn >= 2 * cout and bn > 32:
             continue
-        try:
-            t = timeit(lambda: ops.conv_gemm(a, wp, out, taps=(ks, ks), dil=dil, pad=dil * (ks - 1) // 2,
-                                             scale=sc, bias=bi, relu=True, block_n=bn))
-            entry["bn%d" % bn] = {"us": t * 1e6, "tflops": flops / t / 1e12}
-        except Exception as e:  # noqa
-            entry["bn%d" % bn] = {"error": str(e)}
+        for sk in (0, 1):
+            try:
+                t = timeit(lambda: ops.conv_gemm(a, wp, out, taps=(ks, ks), dil=dil, pad=dil * (ks - 1) // 2,
+                                                 scale=sc, bias=bi, relu=True, block_n=bn, stream_k=sk))
+                entry["bn%d_sk%d" % (bn, sk)] = {"us": t * 1e6, "tflops": flops / t / 1e12}
+            except Exception as e:  # noqa
+                entry["bn%d_sk%d" % (bn, sk)] = {"error": str(e)}
     # cuDNN/cuBLAS reference speed (tf32 allowed) for orientation only
     torch.backends.cudnn.allow_tf32 = True
     xn = a.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
@@ -99,7 +100,7 @@ w = torch.randn(n, k, device=dev) / k ** 0.5
 out = torch.empty(m, n, device=dev)
 fc = {}
 for bn in (128, 256):
-    t = timeit(lambda: ops.linear(x, w, out, block_n=bn), iters=10)
+    t = timeit(lambda: ops.linear(x, w, out, block_n=bn, stream_k=1), iters=10)
     fc["bn%d" % bn] = {"us": t * 1e6, "weight_GBps": k * n * 4 / t / 1e9, "tflops": 2.0 * m * k * n / t / 1e12}
 t = timeit(lambda: torch.mm(x, w.t()), iters=10)
 fc["cublas_fp32"] = {"us": t * 1e6}
