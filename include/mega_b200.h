@@ -48,7 +48,8 @@ typedef struct mega_conv_gemm_desc {
   long long b_stride_n, b_stride_tap;
   int taps_r, taps_s, dil, pad;
   int k_per_tap; /* reduction length per tap (Cin) */
-  /* output NHWC (out_ld floats between pixels); out_h/out_w = output spatial size */
+  /* output NHWC, dense in (w, h, n) with out_ld floats between pixels (written by TMA: 16-byte aligned
+   * base, out_ld % 4 == 0; the residual likewise); out_h/out_w = output spatial size */
   float* out;
   long long out_ld;
   int n_img, out_h, out_w, cout;
@@ -63,7 +64,8 @@ typedef struct mega_conv_gemm_desc {
   int batch;
   int a_c_off, a_n_off; /* added to A's channel / image coordinate, times batch index */
   int b_k_off, b_n_off; /* added to B's k / row coordinate, times batch index */
-  long long out_z_off, res_z_off;
+  int out_c_off, out_n_off; /* added to the output's channel / image coordinate, times batch index */
+  int res_c_off, res_n_off; /* same for the residual */
   int bias_z_off; /* added to the scale/bias index, times batch index */
   /* persistent stream-K scheduling: at most max_ctas CTAs (0 = one per SM). `workspace` (device,
    * >= mega_conv_gemm_workspace_bytes(), 256-byte aligned, ZERO-INITIALISED once; the kernel leaves

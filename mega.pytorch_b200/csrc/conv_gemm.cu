@@ -32,17 +32,15 @@ struct ConvGemmParams {
   int taps_r, taps_s, dil, pad;
   int k_chunks;  // ceil(Cin / 32)
   int cout;
-  float* out;
-  long long out_ld;
   const float* scale;
   const float* bias;
-  const float* residual;
-  long long res_ld;
+  int has_residual;
   int relu;
   int a_c_off, a_n_off, b_k_off, b_n_off;
-  long long out_z_off;
-  long long res_z_off;
+  int out_c_off, out_n_off;   // per-batch coordinate offsets of the output / residual tensors
+  int res_c_off, res_n_off;
   int bias_z_off;
+  int box_w, box_h;           // per-warp store box: 32 output pixels = box_h x box_w
   // stream-K decomposition
   int m_tiles, n_tiles;      // per batch entry
   int kb_per_tile;           // taps * k_chunks
@@ -58,8 +56,10 @@ struct SmemLayout {
   static constexpr int kABytes = kBM * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kBarOffset = STAGES * kStageBytes;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 32 + 1024;  // + align slack
+  static constexpr int kEpiOffset = STAGES * kStageBytes;       // 4 warps x (2 out + 2 residual) x 4 KB
+  static constexpr int kEpiBytes = 4 * 4 * 4096;
+  static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
+  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4 + 8) * 8 + 32 + 1024;  // + align slack
 };
 
 struct TileCoord {
@@ -133,6 +133,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                       const ConvGemmParams p) {
   using L = SmemLayout<BN, STAGES>;
   constexpr uint32_t kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
@@ -144,7 +145,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;         // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
   int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -157,6 +159,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmOut);
+    if (p.has_residual) prefetch_tmap(&tmRes);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -167,6 +171,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 4);
     }
+    for (int b = 0; b < 8; ++b) mbar_init(&res_bar[b], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -248,8 +253,10 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int epi_tid = (warp - 2) * 32 + lane;
-    const int hl = row / p.tile_w;
-    const int wl = row - hl * p.tile_w;
+    uint8_t* epi_out = smem + L::kEpiOffset + (warp - 2) * 16384;   // 2 x 4 KB store staging
+    uint8_t* epi_res = epi_out + 8192;                              // 2 x 4 KB residual staging
+    uint64_t* rbar = res_bar + (warp - 2) * 2;
+    uint32_t rphase = 0;
     WorkIter it(p, cta, grid);
     long long t;
     int kb0, kb1;
@@ -295,24 +302,29 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (finalize) __threadfence();
       }
       if (finalize) {
-        const int h = tc.h0 + hl;
-        const int w = tc.w0 + wl;
-        const bool row_ok = (h < p.out_h) && (w < p.out_w);
-        const long long pix = (static_cast<long long>(tc.img) * p.out_h + h) * p.out_w + w;
-        float* out_row = p.out + tc.batch * p.out_z_off + pix * p.out_ld;
-        const float* res_row = p.residual ? p.residual + tc.batch * p.res_z_off + pix * p.res_ld : nullptr;
+        // Output pixels of this warp: tile rows [32q, 32q+32) = a box_h x box_w rectangle. Results go
+        // registers -> 128B-swizzled smem -> one TMA store per 32-column chunk (full-line writes,
+        // image-edge and channel-edge clipping by the TMA unit); the residual arrives the same way.
+        const int r0 = q * 32;
+        const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
+        const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
+        const int out_n = tc.img + tc.batch * p.out_n_off;
+        const int res_n = tc.img + tc.batch * p.res_n_off;
         const float* scale_p = p.scale ? p.scale + tc.batch * p.bias_z_off : nullptr;
         const float* bias_p = p.bias ? p.bias + tc.batch * p.bias_z_off : nullptr;
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(out_row) & 15) == 0) &&
-                            (res_row == nullptr || (reinterpret_cast<uintptr_t>(res_row) & 15) == 0);
+        const int nchunks = min(BN / 32, (p.cout - tc.n0 + 31) / 32);
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        if (p.has_residual && lane == 0 && nchunks > 0) {
+          mbar_arrive_expect_tx(&rbar[0], 4096);
+          tma_load_4d(epi_res, &tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
+        }
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; c < nchunks; ++c) {
           uint32_t acc[32];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the divergent stores
+          __syncwarp();  // tcgen05.ld is .sync.aligned
           tmem_ld_32x32(tmem_row + c * 32, acc);
           tmem_ld_wait();
           const int nb = tc.n0 + c * 32;
-          if (!row_ok || nb >= p.cout) continue;
           if (!complete) {
             // deterministic reduction: parts summed in CTA order, own part from TMEM
             float sum[32];
@@ -335,12 +347,28 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sum[j]);
           }
+          const uint8_t* rsrc = nullptr;
+          if (p.has_residual) {
+            const int rb = c & 1;
+            if (c + 1 < nchunks && lane == 0) {   // prefetch the next residual chunk into the other buffer
+              mbar_arrive_expect_tx(&rbar[rb ^ 1], 4096);
+              tma_load_4d(epi_res + (rb ^ 1) * 4096, &tmRes, &rbar[rb ^ 1], nb + 32 + tc.batch * p.res_c_off, st_w,
+                          st_h, res_n);
+            }
+            mbar_wait(&rbar[rb], (rphase >> rb) & 1u);
+            rphase ^= (1u << rb);
+            rsrc = epi_res + rb * 4096 + lane * 128;
+          }
+          // the out staging buffer (c & 1) was handed to a TMA store two chunks ago: wait until read
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* dst = epi_out + (c & 1) * 4096 + lane * 128;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const int n = nb + j;
-            if (n + 3 < p.cout && vec_ok) {
-              float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
-                                     __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+            float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                                   __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+            if (n < p.cout) {   // cout is padded to 4 by the host wrapper's buffers; tail lanes are clipped by TMA
               if (scale_p) {
                 const float4 sc = ldg_f4(scale_p + n);
                 v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
@@ -349,26 +377,22 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 const float4 bi = ldg_f4(bias_p + n);
                 v.x += bi.x; v.y += bi.y; v.z += bi.z; v.w += bi.w;
               }
-              if (res_row) {
-                const float4 rr = ldg_f4(res_row + n);
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-              }
-              if (p.relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              }
-              *reinterpret_cast<float4*>(out_row + n) = v;
-            } else {
-              for (int tt = 0; tt < 4; ++tt) {
-                if (n + tt < p.cout) {
-                  float v = __uint_as_float(acc[j + tt]);
-                  if (scale_p) v *= __ldg(scale_p + n + tt);
-                  if (bias_p) v += __ldg(bias_p + n + tt);
-                  if (res_row) v += __ldg(res_row + n + tt);
-                  if (p.relu) v = fmaxf(v, 0.f);
-                  out_row[n + tt] = v;
-                }
-              }
             }
+            const uint32_t chunk = (static_cast<uint32_t>(j >> 2) ^ sw) << 4;
+            if (rsrc) {
+              const float4 rr = *reinterpret_cast<const float4*>(rsrc + chunk);
+              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            }
+            if (p.relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(dst + chunk) = v;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmOut, epi_out + (c & 1) * 4096, nb + tc.batch * p.out_c_off, st_w, st_h, out_n);
+            tma_store_commit();
           }
         }
       }
@@ -377,6 +401,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
+    if (lane == 0) tma_store_wait<0>();   // global writes complete before the CTA retires
   }
 
   tc_fence_before();
@@ -413,8 +438,8 @@ constexpr int kCounterSlots = 65536;   // ints at the head of the workspace
 constexpr int kMinUnits = 4;
 
 template <int BN, int STAGES>
-static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, dim3 grid,
-                      cudaStream_t stream) {
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                      const CUtensorMap& tmRes, const ConvGemmParams& p, dim3 grid, cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
@@ -422,7 +447,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  conv_gemm_tf32_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, p);
+  conv_gemm_tf32_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, tmOut, tmRes, p);
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }
@@ -455,6 +480,13 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
                  "conv_gemm: operand base pointers must be 16-byte aligned");
   MEGA_ARG_CHECK((d->a_stride_w % 4) == 0 && (d->a_stride_h % 4) == 0 && (d->a_stride_n % 4) == 0,
                  "conv_gemm: activation strides must be multiples of 4 floats");
+  MEGA_ARG_CHECK(d->out != nullptr && (reinterpret_cast<uintptr_t>(d->out) & 15) == 0 && (d->out_ld % 4) == 0,
+                 "conv_gemm: output must be 16-byte aligned with a row pitch multiple of 4 floats");
+  MEGA_ARG_CHECK(d->residual == nullptr ||
+                     ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0 && (d->res_ld % 4) == 0),
+                 "conv_gemm: residual must be 16-byte aligned with a row pitch multiple of 4 floats");
+  MEGA_ARG_CHECK(d->out_c_off == 0 || d->cout == d->block_n,
+                 "conv_gemm: channel-offset batching needs cout == block_n (got %d vs %d)", d->cout, d->block_n);
   MEGA_ARG_CHECK((d->b_stride_n % 4) == 0 && (d->b_stride_tap % 4) == 0,
                  "conv_gemm: weight strides must be multiples of 4 floats");
   MEGA_ARG_CHECK(d->batch >= 1, "conv_gemm: batch must be >= 1");
@@ -505,6 +537,40 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
     }
   }
 
+  // per-warp store / residual boxes: 32 channels x (box_h x box_w = 32 output pixels), 128B swizzle
+  CUtensorMap tmOut, tmRes;
+  {
+    const int box_w = d->tile_w < 32 ? d->tile_w : 32;
+    const int box_h = 32 / box_w;
+    for (int which = 0; which < 2; ++which) {
+      const float* base = which == 0 ? d->out : d->residual;
+      CUtensorMap* tm = which == 0 ? &tmOut : &tmRes;
+      if (base == nullptr) {
+        *tm = tmOut;
+        continue;
+      }
+      const long long ld = which == 0 ? d->out_ld : d->res_ld;
+      const int c_off = which == 0 ? d->out_c_off : d->res_c_off;
+      const int n_off = which == 0 ? d->out_n_off : d->res_n_off;
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->cout + (d->batch - 1) * c_off), static_cast<cuuint64_t>(d->out_w),
+                            static_cast<cuuint64_t>(d->out_h),
+                            static_cast<cuuint64_t>(d->n_img + (d->batch - 1) * n_off)};
+      cuuint64_t gstr[3] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(ld) * d->out_w * 4,
+                            static_cast<cuuint64_t>(ld) * d->out_w * d->out_h * 4};
+      cuuint32_t box[4] = {32, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        mega_set_error("conv_gemm: encode %s tensor map failed (CUresult %d): C %d W %d H %d N %d ld %lld",
+                       which == 0 ? "output" : "residual", static_cast<int>(r), static_cast<int>(gdim[0]), d->out_w,
+                       d->out_h, static_cast<int>(gdim[3]), ld);
+        return MEGA_ERR_CUDA;
+      }
+    }
+  }
+
   ConvGemmParams p;
   p.tile_w = d->tile_w;
   p.tile_h = d->tile_h;
@@ -519,20 +585,21 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
   p.pad = d->pad;
   p.k_chunks = mega_ceil_div(d->k_per_tap, kBK);
   p.cout = d->cout;
-  p.out = d->out;
-  p.out_ld = d->out_ld;
   p.scale = d->scale;
   p.bias = d->bias;
-  p.residual = d->residual;
-  p.res_ld = d->res_ld;
+  p.has_residual = d->residual != nullptr;
   p.relu = d->relu;
   p.a_c_off = d->a_c_off;
   p.a_n_off = d->a_n_off;
   p.b_k_off = d->b_k_off;
   p.b_n_off = d->b_n_off;
-  p.out_z_off = d->out_z_off;
-  p.res_z_off = d->res_z_off;
+  p.out_c_off = d->out_c_off;
+  p.out_n_off = d->out_n_off;
+  p.res_c_off = d->res_c_off;
+  p.res_n_off = d->res_n_off;
   p.bias_z_off = d->bias_z_off;
+  p.box_w = d->tile_w < 32 ? d->tile_w : 32;
+  p.box_h = 32 / p.box_w;
   p.m_tiles = p.tiles_w * p.tiles_h * p.n_img;
   p.n_tiles = mega_ceil_div(d->cout, d->block_n);
   p.kb_per_tile = d->taps_r * d->taps_s * p.k_chunks;
@@ -558,13 +625,13 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
   dim3 grid(static_cast<unsigned>(ctas), 1, 1);
   int rc;
   switch (d->block_n) {
-    case 32: rc = launch_cfg<32, 8>(tmA, tmB, p, grid, stream); break;
-    case 64: rc = launch_cfg<64, 8>(tmA, tmB, p, grid, stream); break;
-    case 96: rc = launch_cfg<96, 6>(tmA, tmB, p, grid, stream); break;
-    case 128: rc = launch_cfg<128, 6>(tmA, tmB, p, grid, stream); break;
-    case 160: rc = launch_cfg<160, 5>(tmA, tmB, p, grid, stream); break;
-    case 192: rc = launch_cfg<192, 4>(tmA, tmB, p, grid, stream); break;
-    default: rc = launch_cfg<256, 4>(tmA, tmB, p, grid, stream); break;
+    case 32: rc = launch_cfg<32, 6>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;
+    case 64: rc = launch_cfg<64, 6>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;
+    case 96: rc = launch_cfg<96, 5>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;
+    case 128: rc = launch_cfg<128, 4>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;
+    case 160: rc = launch_cfg<160, 4>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;
+    case 192: rc = launch_cfg<192, 3>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;
+    default: rc = launch_cfg<256, 3>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;
   }
   return rc;
 }

@@ -44,7 +44,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("tile_h", c_int), ("tile_w", c_int), ("block_n", c_int),
         ("batch", c_int),
         ("a_c_off", c_int), ("a_n_off", c_int), ("b_k_off", c_int), ("b_n_off", c_int),
-        ("out_z_off", c_ll), ("res_z_off", c_ll),
+        ("out_c_off", c_int), ("out_n_off", c_int), ("res_c_off", c_int), ("res_n_off", c_int),
         ("bias_z_off", c_int),
         ("max_ctas", c_int),
         ("stream_k", c_int),

@@ -274,10 +274,12 @@ class HeadCommon:
         pw = torch.cat([sd["roi_heads.box.predictor.cls_score.weight"].float(),
                         sd["roi_heads.box.predictor.bbox_pred.weight"].float()], 0)
         self.num_classes = sd["roi_heads.box.predictor.cls_score.weight"].shape[0]
-        self.pred_w = pw.contiguous().to(dev)
-        self.pred_b = torch.cat([sd["roi_heads.box.predictor.cls_score.bias"].float(),
-                                 sd["roi_heads.box.predictor.bbox_pred.bias"].float()]).contiguous().to(dev)
         self.pred_ld = _round_up(5 * self.num_classes, 4)
+        self.pred_w = pw.contiguous().to(dev)
+        pb = torch.zeros(self.pred_ld)                       # bias padded: the epilogue loads it in float4 groups
+        pb[:5 * self.num_classes] = torch.cat([sd["roi_heads.box.predictor.cls_score.bias"].float(),
+                                               sd["roi_heads.box.predictor.bbox_pred.bias"].float()])
+        self.pred_b = pb.contiguous().to(dev)
         self._bufs = {}
 
     def _buf(self, tag, shape, dtype=torch.float32):
@@ -604,14 +606,14 @@ class MegaEngine(HeadCommon):
         ops.linear(xq, att.wq, q, bias=att.bq)
         ops.linear(refs, att.wk, k, bias=att.bk)
         ops.linear(att.wv, refs, vt)                                    # V'^T = Wv . refs^T  -> [1024, nref]
-        ops.conv_gemm(q.view(1, 1, nq, D), k.view(1, nref, D), s[0].view(1, 1, nq, ld), tile=(1, 128), cout=nref,
-                      k=64, batch=16, a_c_off=64, b_k_off=64, out_z_off=nq * ld)
+        ops.conv_gemm(q.view(1, 1, nq, D), k.view(1, nref, D), s.view(16, 1, nq, ld), tile=(1, 128), cout=nref,
+                      k=64, batch=16, a_c_off=64, b_k_off=64, out_n_off=1, n_img=1)
         ops.relation_softmax(s, nq, ld, 1.0 / math.sqrt(64.0), boxes_q=boxes_q, boxes_k=boxes_k,
                              wg=att.wg if boxes_q is not None else None, bg=att.bg if boxes_q is not None else None,
                              dim_mat=self.dim_mat if boxes_q is not None else None, m_valid=m_valid,
                              m_host=nref, n_valid=n_valid, n_valid_off=n_valid_off)
         ops.conv_gemm(s.view(16, 1, nq, ld), vt.view(1, D, ld), out.view(1, 1, nq, D), tile=(1, 128), cout=64, k=ld,
-                      batch=16, a_n_off=1, b_n_off=64, out_z_off=64, res_z_off=64, bias_z_off=64, bias=att.bv,
+                      batch=16, a_n_off=1, b_n_off=64, out_c_off=64, res_c_off=64, bias_z_off=64, bias=att.bv,
                       residual=xq.view(1, 1, nq, D), block_n=64)
         return out
 

@@ -53,7 +53,7 @@ BLOCK_NS = (32, 64, 96, 128, 160, 192, 256)
 
 def _shape_key(d):
     return (d.a_n, d.a_h, d.a_w, d.a_c, d.a_stride_w, d.b_n, d.b_k, d.taps_r, d.taps_s, d.dil, d.k_per_tap, d.n_img,
-            d.out_h, d.out_w, d.cout, d.tile_h, d.tile_w, d.batch, bool(d.residual), d.out_ld)
+            d.out_h, d.out_w, d.cout, d.tile_h, d.tile_w, d.batch, bool(d.residual), d.out_ld, d.out_c_off)
 
 
 def _candidates(cout):
@@ -115,8 +115,8 @@ def pick_block_n(cout, m_tiles=0, batch=1):
 
 def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, residual=None,
               relu=False, tile=None, block_n=None, cout=None, k=None, batch=1, a_c_off=0,
-              a_n_off=0, b_k_off=0, b_n_off=0, out_z_off=0, res_z_off=0, bias_z_off=0, max_ctas=0,
-              stream_k=None, out_hw=None):
+              a_n_off=0, b_k_off=0, b_n_off=0, out_c_off=0, out_n_off=0, res_c_off=0, res_n_off=0, bias_z_off=0,
+              max_ctas=0, stream_k=None, out_hw=None, n_img=None):
     """out[n,h,w,:] = act(scale * conv(a, w) + bias + residual)   (TF32 tensor cores)
 
     a   : [N,H,W,C] fp32 view (innermost stride 1; other strides multiples of 4 floats)
@@ -146,21 +146,21 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.k_per_tap = k if k is not None else kk
     d.out = ptr(out)
     d.out_ld = out.stride(2)
-    d.n_img, d.out_h, d.out_w = on, oh, ow
+    d.n_img, d.out_h, d.out_w = (on if n_img is None else n_img), oh, ow
     d.cout = cout if cout is not None else rows
     d.scale, d.bias, d.residual = ptr(scale), ptr(bias), ptr(residual)
     d.res_ld = residual.stride(-2) if residual is not None else 0
     d.relu = 1 if relu else 0
     th, tw = tile if tile is not None else pick_tile(oh, ow)
     d.tile_h, d.tile_w = th, tw
-    m_tiles = on * (-(-oh // th)) * (-(-ow // tw))
+    m_tiles = d.n_img * (-(-oh // th)) * (-(-ow // tw))
     d.batch = batch
     kb_per_tile = taps[0] * taps[1] * (-(-d.k_per_tap // 32))
     auto_bn, auto_sk = pick_config(d.cout, m_tiles, batch, kb_per_tile)
     d.block_n = block_n if block_n is not None else auto_bn
     d.stream_k = auto_sk if stream_k is None else int(stream_k)
     d.a_c_off, d.a_n_off, d.b_k_off, d.b_n_off = a_c_off, a_n_off, b_k_off, b_n_off
-    d.out_z_off, d.res_z_off = out_z_off, res_z_off
+    d.out_c_off, d.out_n_off, d.res_c_off, d.res_n_off = out_c_off, out_n_off, res_c_off, res_n_off
     d.bias_z_off = bias_z_off
     d.max_ctas = max_ctas
     ws = gemm_workspace(a.device)

@@ -11,12 +11,17 @@ import torch.nn.functional as F
 
 def _shadow_conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, residual=None, relu=False,
                       tile=None, block_n=None, cout=None, k=None, batch=1, a_c_off=0, a_n_off=0, b_k_off=0, b_n_off=0,
-                      out_z_off=0, res_z_off=0, bias_z_off=0, max_ctas=0, out_hw=None):
+                      out_c_off=0, out_n_off=0, res_c_off=0, res_n_off=0, bias_z_off=0, max_ctas=0, stream_k=None,
+                      out_hw=None, n_img=None):
     t, rows, kk = w.shape
     cout = rows if cout is None else cout
     k = kk if k is None else k
     on, oh, ow, oc = out.shape
+    if n_img is not None:
+        on = n_img
     ld = out.stride(2)
+    out_z_off = out_c_off + out_n_off * out.stride(0)
+    res_z_off = res_c_off + (res_n_off * residual.stride(0) if residual is not None else 0)
     for z in range(batch):
         az = a[z * a_n_off: z * a_n_off + on] if a_n_off else a
         az = az[..., z * a_c_off: z * a_c_off + k]                       # [n,h,w,k]

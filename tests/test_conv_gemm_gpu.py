@@ -90,9 +90,9 @@ def test_batched_heads(cuda_dev):
     qd, kd = q.to(cuda_dev), k.to(cuda_dev)
     a4 = qd.view(1, 1, nq, heads * dh)
     w3 = kd.view(1, mk, heads * dh)
-    o4 = out[0].view(1, 1, nq, mk_pad)
+    o4 = out.view(heads, 1, nq, mk_pad)
     ops.conv_gemm(a4, w3, o4, tile=(1, 128), cout=mk, k=dh, batch=heads, a_c_off=dh, b_k_off=dh,
-                  out_z_off=nq * mk_pad, block_n=128)
+                  out_n_off=1, n_img=1, block_n=128)
     torch.cuda.synchronize()
     assert _rel_err(out[:, :, :mk], ref) < TOL
     assert (out[:, :, mk:] == 0).all()
