@@ -14,9 +14,12 @@ Output: ONE JSON line (see the driver contract): `value` = frames/s with inputs 
 the detections, `roofline` for the tcgen05 conv/GEMM kernel, `cpu_baseline` = the oracle port timed
 on this box's host cores on a bounded sample.
 
-N > 1 (torchrun): every rank runs an independent video stream (the reference's own multi-GPU
-strategy: VIDTestDistributedSampler shards by whole video, data/samplers/distributed.py:69-115;
-no data-path collective) -> weak scaling; value = total frames of all ranks / max-over-ranks time.
+N > 1 (torchrun): ONE video stream, frame-parallel (SURVEY.md section 8e option i): per step every rank
+runs the per-frame branch (backbone/RPN/res5/ROIAlign/l_fcs[0]) of its own (local, global) frame pair,
+one NCCL all-gather exchanges the fixed-size ROI-feature payloads (1.54 MB per rank) in frame order, and
+every rank ingests all N frames so the window / global pool / long-range memory stay replicated (results
+do not depend on N). A step therefore produces N key frames: value = N * steps / max-over-ranks time.
+Per-GPU work per step is fixed -> "weak".
 """
 import argparse
 import json
@@ -50,7 +53,7 @@ def parse():
     ap.add_argument("--width", type=int, default=W)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
-    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -139,9 +142,15 @@ def run_b200(args, rank, world):
     with torch.no_grad():
         model(infos_first())
         t = 1
-        for _ in range(eng.MEMF + 2 if args.prime < 0 else args.prime):
-            model(infos_next(t))
-            t += 1
+        n_prime = eng.MEMF + 2 if args.prime < 0 else args.prime
+        if world == 1:
+            for _ in range(n_prime):
+                model(infos_next(t))
+                t += 1
+        else:
+            pd = [torch.cat([pool_dev[(i + 12) % 16], pool_dev[(5 * i + 3) % 16]], 0) for i in range(16)]
+            for i in range(-(-n_prime // world)):
+                eng.dist_step(pd[(i * world + rank) % 16], w, h)
     torch.cuda.synchronize(dev)
 
     def barrier():
@@ -152,45 +161,63 @@ def run_b200(args, rank, world):
     # ---- timed region A: device-resident inputs, engine-level step (no host transfers)
     static_in = eng.static_input(pair_shape)
     pairs_dev = [torch.cat([pool_dev[(i + 12) % 16], pool_dev[(5 * i + 3) % 16]], 0) for i in range(16)]
+    pairs_pinned = [torch.cat([pool[(i + 12) % 16], pool[(5 * i + 3) % 16]], 0).pin_memory() for i in range(16)]
+
+    def step_dev(i):
+        if world > 1:
+            return eng.dist_step(pairs_dev[(i * world + rank) % 16], w, h)[rank]
+        return eng.step_batched(pairs_dev[i % 16], w, h)
+
+    def step_e2e(i):
+        """pinned host frames -> device, one step, detections of this rank's key frame back on the host"""
+        if world == 1:
+            return model(infos_next(i))[0]
+        static_in.copy_(pairs_pinned[(i * world + rank) % 16], non_blocking=True)
+        det = eng.dist_step(static_in, w, h)[rank]
+        return det.to_host()[0]
+
     launches0 = ops.LAUNCHES[0]
     for i in range(args.warmup):
-        eng.step_batched(pairs_dev[i % 16], w, h)
+        step_dev(i)
     launches_per_step = (ops.LAUNCHES[0] - launches0) / max(args.warmup, 1)
     if eng._graphs:
-        launches_per_step = eng.launches_per_frame
+        launches_per_step = eng.launches_per_frame * (1 if world == 1 else 1)
     barrier()
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        eng.step_batched(pairs_dev[i % 16], w, h)
+        step_dev(i)
     e1.record()
     barrier()
     dev_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
 
-    # ---- timed region B: end to end through model(images): pinned host inputs -> detections on the host
+    # ---- timed region B: end to end: pinned host inputs -> detections on the host (model(images) at N=1)
     for i in range(max(args.warmup, 3)):
-        model(infos_next(t))
+        step_e2e(t)
         t += 1
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     ndet = 0
     for i in range(args.steps):
-        out = model(infos_next(t))
-        ndet += len(out[0])
+        out = step_e2e(t)
+        ndet += len(out)
         t += 1
     e3.record()
     barrier()
     e2e_ms = e2.elapsed_time(e3)
-    h2d = 2 * 3 * h * w * 4 + eng.tab_h.numel() * 4
-    d2h = model.d2h_bytes_per_frame
+    h2d = 2 * 3 * h * w * 4 + eng.tab_h.numel() * 4 * world
+    d2h = model.d2h_bytes_per_frame if world == 1 else 4 + 300 * 28
 
     # ---- roofline of the dominant kernel (tcgen05 conv/GEMM): eager frames with an event pair per launch
     roof = roofline_pass(eng, pairs_dev, w, h)
 
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        ops.save_tuned(os.path.join(ROOT, "gpurun_out", "tuned_b200.json"))
     times = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -205,13 +232,14 @@ def run_b200(args, rank, world):
         "config": {"workload": "MEGA R-101 C4 steady-state key frame, %dx%d, 25 local / 10 global / 25 memory frames, "
                                "1 new local + 1 new global frame per step" % (w, h),
                    "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
-                   "parallelism": "1 video stream per GPU (shard by video)" if world > 1 else "single GPU",
+                   "parallelism": ("frame-parallel over %d GPUs, NCCL all-gather of ROI-feature payloads, replicated "
+                                   "aggregation" % world) if world > 1 else "single GPU",
                    "cuda_graph": bool(eng._graphs),
                    "l2": "per-step working set (0.7 GB fp32 weights + >0.5 GB activations) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "detections_per_frame": ndet / args.steps},
-        "gpu_launches": int(round(launches_per_step * args.steps)),
+        "gpu_launches": int(round(launches_per_step * args.steps * (1 if world == 1 else 1))),
         "roofline": {"bound": "tensor", "achieved": roof["algo_tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": roof["algo_tflops"] / pk["tflops"], "traffic": None, "peak_source": pk["src"],
                      "kernel": "conv_gemm_tf32_kernel (tcgen05 kind::tf32; TF32 dense peak is half the bf16 figure)",
@@ -266,10 +294,25 @@ def cpu_sample(args, frames_to_time):
     from collections import deque
     from mega_core.b200 import synth
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     h, w = args.height, args.width
     sd = synth.make_state_dict(args.arch, seed=0)
     orc = mo.MegaOracle(sd)
+    # all the host threads it can USE: time one backbone stage at a few thread counts, keep the fastest
+    probe = frame_pool(1, h, w)[0]
+    best = None
+    for nt in sorted({cores, max(cores // 2, 1), min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
+        torch.set_num_threads(nt)
+        with torch.no_grad():
+            t0 = time.time()
+            torch.nn.functional.conv2d(probe, sd["backbone.body.stem.conv1.weight"], None, 2, 3)
+            x = torch.randn(1, 256, (h + 15) // 16, (w + 15) // 16)
+            for _ in range(6):
+                torch.nn.functional.conv2d(x, sd["backbone.body.layer3.1.conv2.weight"], None, 1, 1)
+            dt = time.time() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    cores_used = best[1]
+    torch.set_num_threads(cores_used)
     c = orc.cfg
     g = torch.Generator().manual_seed(1)
     L, R, A = c.all_frame_interval, c.ref_post_nms_top_n, c.advanced_num
@@ -297,10 +340,11 @@ def cpu_sample(args, frames_to_time):
         for i in range(frames_to_time):
             orc.forward(pool[i % 4], {"frame_category": 1, "ref_l": [pool[(i + 1) % 4]], "ref_g": [pool[(i + 2) % 4]]})
         dt = time.time() - t0
-    return {"value": frames_to_time / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+    return {"value": frames_to_time / dt, "unit": "frames/s", "cores": cores_used, "host_cores": cores, "kind": "port",
             "sample": "%d steady-state MEGA R-101 frames at %dx%d (2 backbone passes + full 25/10/25 aggregation each); "
-                      "window/global/memory pre-filled with synthetic rows; oracle/mega_oracle.py, torch fp32, %d threads"
-                      % (frames_to_time, w, h, cores), "seconds": dt}
+                      "window/global/memory pre-filled with synthetic rows; oracle/mega_oracle.py, torch fp32, %d threads "
+                      "(fastest of several thread counts on a conv probe; box has %d logical cores)"
+                      % (frames_to_time, w, h, cores_used, cores), "seconds": dt}
 
 
 def run_reference(args, rank, world):

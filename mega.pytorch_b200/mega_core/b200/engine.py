@@ -256,6 +256,7 @@ class HeadCommon:
         self.cfg, self.dev = cfg, dev
         # per-shape (tile width, scheduling) selection by on-device timing the first time a shape is seen
         ops.AUTOTUNE[0] = os.environ.get("MEGA_B200_AUTOTUNE", "1") != "0"
+        ops.load_tuned(os.environ.get("MEGA_B200_TUNED", os.path.join(os.path.dirname(__file__), "tuned_b200.json")))
         self.backbone = Backbone(sd, dev)
         self.rpn_w = pack_conv(sd["rpn.head.conv.weight"], dev)
         self.rpn_b = sd["rpn.head.conv.bias"].float().contiguous().to(dev)
@@ -360,6 +361,8 @@ class MegaEngine(HeadCommon):
         self.B1, self.B2 = z(self.nl12 + self.mem_cap12, 4), z(self.nl12 + self.mem_cap12, 4)
         self.X1, self.X2, self.X3, self.X4 = z(self.nq, D), z(self.nq, D), z(KP, D), z(KP, D)
         self.cur_cnt = z(1, 1, dtype=torch.int32)
+        self.payload_in = z(KP * D + KP * 4 + 4 + R * D)
+        self.payload_all = None
         # ---- attention scratch, one set per key-count geometry
         self.ld_g = _round_up(GF * R, 32)
         self.ld_0 = _round_up(self.nl0 + self.mem_cap0, 32)
@@ -499,22 +502,45 @@ class MegaEngine(HeadCommon):
 
     def step_batched(self, imgs, im_w, im_h):
         """imgs [2,3,H,W] = (look-ahead local frame, global frame), already on the device."""
+        self._run_ref(imgs, im_w, im_h)
+        return self._ingest_next(im_w, im_h)
+
+    # ---- the steady frame is two fixed launch sequences, each captured in its own CUDA graph:
+    #      "ref"    images -> payload (x300 | boxes300 | count | x75 of the global frame)
+    #      "ingest" payload -> ring buffers -> aggregation -> detections
+    #      (frame-parallel multi-GPU runs all-gather the payloads between the two)
+    def _graph_run(self, key, fn):
+        if self.use_graph and key not in self._graphs and self._eager_done.get(key, 0) >= 1:
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            l0 = ops.LAUNCHES[0]
+            with torch.cuda.graph(graph):
+                out = fn()
+            self._graphs[key] = (graph, out, ops.LAUNCHES[0] - l0)
+        g = self._graphs.get(key)
+        if g is not None:
+            g[0].replay()
+            return g[1]
+        self._eager_done[key] = self._eager_done.get(key, 0) + 1
+        return fn()
+
+    @property
+    def launches_per_frame(self):
+        return sum(g[2] for g in self._graphs.values())
+
+    def _run_ref(self, imgs, im_w, im_h):
+        static_in = self.static_input(tuple(imgs.shape))
+        if imgs.data_ptr() != static_in.data_ptr():
+            static_in.copy_(imgs, non_blocking=True)
+        self._graph_run(("ref", tuple(imgs.shape), im_w, im_h),
+                        lambda: self._ref_to_payload(static_in, im_w, im_h, self.payload_in))
+
+    def _ingest_next(self, im_w, im_h):
         slot_new = self._claim_slot()
         gslot = self.glob_pushed % self.GF
         self.glob_pushed += 1
         self._fill_tables(slot_new=slot_new, gslot=gslot)
-        key = (tuple(imgs.shape), im_w, im_h)
-        if self.use_graph and key not in self._graphs and self._eager_done.get(key, 0) >= 1:
-            self._capture(key, imgs)
-        g = self._graphs.get(key)
-        if g is not None:
-            graph, static_in, det = g
-            if imgs.data_ptr() != static_in.data_ptr():
-                static_in.copy_(imgs, non_blocking=True)
-            graph.replay()
-            return det
-        self._eager_done[key] = self._eager_done.get(key, 0) + 1
-        return self._steady_frame(imgs, im_w, im_h)
+        return self._graph_run(("ingest", im_w, im_h), lambda: self._ingest(im_w, im_h))
 
     def static_input(self, shape):
         """device buffer [2,3,H,W] the captured graph reads its (local, global) frame pair from;
@@ -525,20 +551,24 @@ class MegaEngine(HeadCommon):
             self._static_in[tuple(shape)] = t
         return t
 
-    def _capture(self, key, imgs):
-        """Capture the steady-state frame (a fixed sequence of ~200 kernel launches whose
-        frame-dependent addresses all come from the device-side index tables) into one CUDA graph.
-        Capturing does not execute anything: the first steady frame of a video runs eagerly (which
-        also warms every buffer / kernel attribute), the second one is captured and replayed."""
-        shape, im_w, im_h = key
-        static_in = self.static_input(shape)
-        torch.cuda.synchronize(self.dev)
-        graph = torch.cuda.CUDAGraph()
-        l0 = ops.LAUNCHES[0]
-        with torch.cuda.graph(graph):
-            det = self._steady_frame(static_in, im_w, im_h)
-        self.launches_per_frame = ops.LAUNCHES[0] - l0
-        self._graphs[key] = (graph, static_in, det)
+    # ---- frame-parallel multi-GPU (option i): rank r runs the per-frame branch of
+    #      frame pair r of every group of `world` key frames; one NCCL all-gather of the fixed-size payloads
+    #      (1.54 MB per rank) in frame order; every rank then ingests all `world` frames so the window /
+    #      global pool / long-range memory stay replicated and results do not depend on `world`.
+    def dist_step(self, imgs, im_w, im_h, group=None):
+        import torch.distributed as dist
+        from . import parallel
+        world = dist.get_world_size(group)
+        self._run_ref(imgs, im_w, im_h)
+        if self.payload_all is None or self.payload_all.shape[0] != world:
+            self.payload_all = torch.zeros(world, self.payload_in.numel(), device=self.dev)
+        parallel.gather_payloads(self.payload_in, self.payload_all, group)
+        dets = []
+        for g in range(world):
+            self.payload_in.copy_(self.payload_all[g], non_blocking=True)
+            det = self._ingest_next(im_w, im_h)
+            dets.append(Detections(det.boxes.clone(), det.scores.clone(), det.labels.clone(), det.count.clone()))
+        return dets
 
     def _fill_tables(self, slot_new=None, gslot=None):
         KP, R, A, L = self.KP, self.R, self.A, self.L
@@ -579,22 +609,44 @@ class MegaEngine(HeadCommon):
         self.mem_pushed += 1
         self.frames += 1
 
-    def _steady_frame(self, imgs, im_w, im_h):
-        """the fixed launch sequence of one steady-state frame (graph-capturable: every
-        frame-dependent address comes from `tab_d`)."""
+    def _payload_views(self, payload):
+        KP, R, D = self.KP, self.R, self.feat_dim
+        o = 0
+        x = payload[o:o + KP * D].view(KP, D)
+        o += KP * D
+        boxes = payload[o:o + KP * 4].view(KP, 4)
+        o += KP * 4
+        cnt = payload[o:o + 4].view(1, 4)
+        o += 4
+        xg = payload[o:o + R * D].view(R, D)
+        return x, boxes, cnt, xg
+
+    def _ref_to_payload(self, imgs, im_w, im_h, payload):
+        """per-frame branch of one (local, global) pair, packed into `payload`"""
         KP, R = self.KP, self.R
         x, boxes, cnt, spans = self.ref_branch(imgs, ["L", "G"], im_w, im_h)
         (ol, rl), (og, rg) = spans
-        ops.copy_rows(x[ol:ol + rl], self.win_x, KP, dst_idx=self._tab("dst_local"))
-        ops.copy_rows(boxes[0], self.win_boxes, KP, dst_idx=self._tab("dst_local"))
-        self._store_count(cnt, self._tab("slot_new"))
-        ops.copy_rows(x[og:og + rg], self.glob_x, R, dst_idx=self._tab("dst_glob"))
+        px, pb, pc, pg = self._payload_views(payload)
+        ops.copy_rows(x[ol:ol + rl], px, KP)
+        ops.copy_rows(boxes[0], pb, KP)
+        ops.copy_rows(cnt[0:1].view(torch.float32).view(1, 1), pc, 1, row_len=1)   # raw 32-bit count
+        ops.copy_rows(x[og:og + rg], pg, R)
+        return payload
+
+    def _ingest(self, im_w, im_h):
+        """payload_in -> ring slots named by the index tables -> aggregation (graph-capturable: every
+        frame-dependent address comes from `tab_d`)"""
+        KP, R = self.KP, self.R
+        px, pb, pc, pg = self._payload_views(self.payload_in)
+        ops.copy_rows(px, self.win_x, KP, dst_idx=self._tab("dst_local"))
+        ops.copy_rows(pb, self.win_boxes, KP, dst_idx=self._tab("dst_local"))
+        ops.copy_rows(pc[:, :1], self.win_cnt.view(torch.float32), 1, row_len=1, dst_idx=self._tab("slot_new")[:1])
+        ops.copy_rows(pg, self.glob_x, R, dst_idx=self._tab("dst_glob"))
         return self.aggregate(im_w, im_h, new_local=True)
 
-    def _store_count(self, cnt, slot_tab):
-        """win_cnt[slot] = cnt[0] through the row-copy kernel (raw 32-bit words)"""
-        ops.copy_rows(cnt[0:1].view(torch.float32).view(1, 1), self.win_cnt.view(torch.float32), 1, row_len=1,
-                      dst_idx=slot_tab[:1])
+    def _steady_frame(self, imgs, im_w, im_h):
+        self._ref_to_payload(imgs, im_w, im_h, self.payload_in)
+        return self._ingest(im_w, im_h)
 
     # ------------------------------------------------------------------ relation module
     def _attention(self, att, xq, nq, refs, nref, ld, out, boxes_q=None, boxes_k=None, m_valid=None, n_valid=None,

@@ -51,6 +51,27 @@ AUTOTUNE = [False]
 BLOCK_NS = (32, 64, 96, 128, 160, 192, 256)
 
 
+def save_tuned(path):
+    """persist the autotuned (block_n, stream_k) table (keyed by problem signature)"""
+    import json
+    with open(path, "w") as fh:
+        json.dump({"device": torch.cuda.get_device_name(0), "entries": [[list(k), list(v)] for k, v in TUNED.items()]}, fh)
+
+
+def load_tuned(path):
+    import json
+    import os
+    if not os.path.exists(path):
+        return 0
+    with open(path) as fh:
+        data = json.load(fh)
+    if torch.cuda.is_available() and data.get("device") != torch.cuda.get_device_name(0):
+        return 0
+    for k, v in data["entries"]:
+        TUNED.setdefault(tuple(bool(x) if isinstance(x, bool) else x for x in k), tuple(v))
+    return len(data["entries"])
+
+
 def _shape_key(d):
     return (d.a_n, d.a_h, d.a_w, d.a_c, d.a_stride_w, d.b_n, d.b_k, d.taps_r, d.taps_s, d.dil, d.k_per_tap, d.n_img,
             d.out_h, d.out_w, d.cout, d.tile_h, d.tile_w, d.batch, bool(d.residual), d.out_ld, d.out_c_off)
