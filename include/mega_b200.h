@@ -71,6 +71,8 @@ typedef struct mega_conv_gemm_desc {
    * >= mega_conv_gemm_workspace_bytes(), 256-byte aligned, ZERO-INITIALISED once; the kernel leaves
    * its counter region zero) holds the tile counters and the partial accumulators of tiles whose
    * K range is shared by several CTAs. Launches that may run concurrently need distinct workspaces. */
+  int precision; /* 0: TF32 operands (round-to-nearest on load); 1: "3xTF32" split (hi*hi + hi*lo + lo*hi),
+                    ~2^-19 relative error, block_n 64 or 128 */
   int max_ctas;
   int stream_k; /* 1: split tiles across CTAs at k-block granularity (balances any tile count over the
                    SMs; partial tiles are reduced by the last CTA to arrive, in CTA order); 0: whole tiles */

@@ -51,15 +51,16 @@ struct ConvGemmParams {
   int* counters;             // [tiles], zero between launches
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT3 = false>
 struct SmemLayout {
   static constexpr int kABytes = kBM * 128;
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kHalf = kABytes + kBBytes;                 // 3xTF32: the low-part tiles follow at +kHalf
+  static constexpr int kStageBytes = SPLIT3 ? 2 * kHalf : kHalf;
   static constexpr int kEpiOffset = STAGES * kStageBytes;       // 4 warps x (2 out + 2 residual) x 4 KB
   static constexpr int kEpiBytes = 4 * 4 * 4096;
   static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
-  static constexpr int kTotal = kBarOffset + (2 * STAGES + 4 + 8) * 8 + 32 + 1024;  // + align slack
+  static constexpr int kTotal = kBarOffset + (3 * STAGES + 4 + 8) * 8 + 32 + 1024;  // + align slack
 };
 
 struct TileCoord {
@@ -130,12 +131,15 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // arrive, which sums the partial accumulators (in CTA order -> deterministic) and runs the
 // epilogue. Accumulators are double-buffered in TMEM so the epilogue of item i overlaps the
 // MMAs of item i+1.
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+// SPLIT3 ("3xTF32"): operands stay full fp32 in shared memory; four extra warps split every staged tile into
+// hi = fp32 truncated to TF32 and lo = x - hi (exact), and each k-step issues hi*hi + hi*lo + lo*hi into the same
+// accumulator: ~2^-19 relative error instead of 2^-11, for the strict-parity mode.
+template <int BN, int STAGES, bool SPLIT3>
+__global__ void __launch_bounds__(kThreads + (SPLIT3 ? 128 : 0), 1)
 conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                       const ConvGemmParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, SPLIT3>;
   constexpr uint32_t kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   // the 128B swizzle pattern is a function of the absolute smem address: align to 1024 B
@@ -143,7 +147,8 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* split_bar = empty_bar + STAGES;       // [STAGES] (3xTF32 only)
+  uint64_t* tmem_full_bar = split_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint64_t* res_bar = tmem_empty_bar + 2;         // [4 warps][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
@@ -166,6 +171,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 4);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
@@ -228,7 +234,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + buf * (kTmemCols / 2);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(SPLIT3 ? &split_bar[stage] : &full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t b_addr = a_addr + L::kABytes;
@@ -238,6 +244,11 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance 8 floats = 32 B inside the swizzle row: +2 in 16-byte units
             umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (SPLIT3) {
+              const uint64_t alo = umma_desc_sw128(a_addr + L::kHalf), blo = umma_desc_sw128(b_addr + L::kHalf);
+              umma_tf32(tmem_d, adesc + 2 * k, blo + 2 * k, idesc, 1u);
+              umma_tf32(tmem_d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
@@ -246,6 +257,41 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           }
         }
         umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== operand splitter (3xTF32 only, warps 6..9) =====================
+    if (SPLIT3) {
+      const int stid = threadIdx.x - kThreads;
+      int stage = 0;
+      uint32_t phase = 0;
+      WorkIter it(p, cta, grid);
+      long long t;
+      int kb0, kb1;
+      while (it.next(t, kb0, kb1)) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          uint8_t* base = smem + stage * L::kStageBytes;
+          constexpr int kVecs = L::kHalf / 16;
+#pragma unroll 4
+          for (int v = stid; v < kVecs; v += 128) {
+            const float4 x = *reinterpret_cast<const float4*>(base + v * 16);
+            float4 hi, lo;
+            hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
+            hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
+            hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
+            hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
+            *reinterpret_cast<float4*>(base + v * 16) = hi;
+            *reinterpret_cast<float4*>(base + L::kHalf + v * 16) = lo;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
       }
     }
   } else {
@@ -437,17 +483,18 @@ static int g_num_sms = 0;
 constexpr int kCounterSlots = 65536;   // ints at the head of the workspace
 constexpr int kMinUnits = 4;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SPLIT3 = false>
 static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
                       const CUtensorMap& tmRes, const ConvGemmParams& p, dim3 grid, cudaStream_t stream) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, SPLIT3>;
   static bool configured = false;
   if (!configured) {
-    MEGA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, STAGES>,
+    MEGA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_tf32_kernel<BN, STAGES, SPLIT3>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  conv_gemm_tf32_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, stream>>>(tmA, tmB, tmOut, tmRes, p);
+  conv_gemm_tf32_kernel<BN, STAGES, SPLIT3><<<grid, kThreads + (SPLIT3 ? 128 : 0), L::kTotal, stream>>>(tmA, tmB, tmOut,
+                                                                                                      tmRes, p);
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }
@@ -498,7 +545,11 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
     mega_set_error("conv_gemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     return MEGA_ERR_CUDA;
   }
-  const CUtensorMapDataType dt = g_tf32_round ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const bool strict = d->precision == 1;
+  MEGA_ARG_CHECK(d->precision == 0 || d->precision == 1, "conv_gemm: precision must be 0 (tf32) or 1 (3xtf32)");
+  MEGA_ARG_CHECK(!strict || d->block_n == 64 || d->block_n == 128, "conv_gemm: 3xtf32 supports block_n 64 / 128");
+  const CUtensorMapDataType dt =
+      (g_tf32_round && !strict) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
   CUtensorMap tmA, tmB;
   {
@@ -624,6 +675,11 @@ extern "C" int mega_conv_gemm_tf32(const mega_conv_gemm_desc* d, void* stream_v)
   if (d->max_ctas > 0 && ctas > d->max_ctas) ctas = d->max_ctas;
   dim3 grid(static_cast<unsigned>(ctas), 1, 1);
   int rc;
+  if (strict) {
+    rc = d->block_n == 64 ? launch_cfg<64, 3, true>(tmA, tmB, tmOut, tmRes, p, grid, stream)
+                          : launch_cfg<128, 2, true>(tmA, tmB, tmOut, tmRes, p, grid, stream);
+    return rc;
+  }
   switch (d->block_n) {
     case 32: rc = launch_cfg<32, 6>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;
     case 64: rc = launch_cfg<64, 6>(tmA, tmB, tmOut, tmRes, p, grid, stream); break;

@@ -46,6 +46,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("a_c_off", c_int), ("a_n_off", c_int), ("b_k_off", c_int), ("b_n_off", c_int),
         ("out_c_off", c_int), ("out_n_off", c_int), ("res_c_off", c_int), ("res_n_off", c_int),
         ("bias_z_off", c_int),
+        ("precision", c_int),
         ("max_ctas", c_int),
         ("stream_k", c_int),
         ("workspace", ctypes.c_void_p),

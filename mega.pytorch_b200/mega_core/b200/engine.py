@@ -58,6 +58,7 @@ class EngineConfig:
     aspect_ratios = (0.5, 1.0, 2.0)
     anchor_stride = 16
     num_classes = 31
+    precision = "tf32"           # "tf32" | "fp32x3" (3xTF32 split: near-fp32 contractions, strict parity mode)
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -236,6 +237,17 @@ class _Att:
             self.bg = sd[pfx + "Wgs.%d.bias" % i].float().contiguous().to(dev)
         else:
             self.wg = self.bg = None
+
+
+def _with_precision(fn):
+    """run an engine entry point under the engine's contraction arithmetic (cfg.precision)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with ops.precision(self.cfg.precision):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 class Detections:
@@ -467,6 +479,7 @@ class MegaEngine(HeadCommon):
         self.win_slots.append(slot)
         return slot
 
+    @_with_precision
     def start_video(self, cur, lookahead, globals_, im_w, im_h):
         """frame_category == 0 (generalized_rcnn_mega.py:163-193): the current frame fills window
         positions 0..12, then the look-ahead frames; the global pool takes `globals_`."""
@@ -500,6 +513,7 @@ class MegaEngine(HeadCommon):
         imgs = torch.cat([new_local, new_global], 0)
         return self.step_batched(imgs, im_w, im_h)
 
+    @_with_precision
     def step_batched(self, imgs, im_w, im_h):
         """imgs [2,3,H,W] = (look-ahead local frame, global frame), already on the device."""
         self._run_ref(imgs, im_w, im_h)
@@ -555,6 +569,7 @@ class MegaEngine(HeadCommon):
     #      frame pair r of every group of `world` key frames; one NCCL all-gather of the fixed-size payloads
     #      (1.54 MB per rank) in frame order; every rank then ingests all `world` frames so the window /
     #      global pool / long-range memory stay replicated and results do not depend on `world`.
+    @_with_precision
     def dist_step(self, imgs, im_w, im_h, group=None):
         import torch.distributed as dist
         from . import parallel
@@ -736,6 +751,7 @@ class BaseEngine(HeadCommon):
         self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev)
         self.fc7_b = sd[FE + "fc7.bias"].float().contiguous().to(dev)
 
+    @_with_precision
     def forward(self, img, im_w, im_h):
         c = self.cfg
         KP = c.post_nms_top_n

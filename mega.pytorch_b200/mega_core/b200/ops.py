@@ -45,6 +45,26 @@ def pick_tile(h, w):
     return best[1], best[2]
 
 
+# ---- arithmetic of the dense contractions: 0 = TF32 operands, 1 = "3xTF32" split (near-fp32, strict parity)
+PRECISION = [0]
+PRECISION_NAMES = {"tf32": 0, "fp32x3": 1}
+
+
+class precision(object):
+    """context manager selecting the contraction arithmetic of every conv_gemm launched inside it"""
+
+    def __init__(self, name):
+        self.value = PRECISION_NAMES[name] if isinstance(name, str) else int(name)
+
+    def __enter__(self):
+        self.saved = PRECISION[0]
+        PRECISION[0] = self.value
+
+    def __exit__(self, *a):
+        PRECISION[0] = self.saved
+        return False
+
+
 # ---- per-shape kernel configuration (block_n, stream_k, max_ctas), filled by autotune()
 TUNED = {}
 AUTOTUNE = [False]
@@ -74,12 +94,13 @@ def load_tuned(path):
 
 def _shape_key(d):
     return (d.a_n, d.a_h, d.a_w, d.a_c, d.a_stride_w, d.b_n, d.b_k, d.taps_r, d.taps_s, d.dil, d.k_per_tap, d.n_img,
-            d.out_h, d.out_w, d.cout, d.tile_h, d.tile_w, d.batch, bool(d.residual), d.out_ld, d.out_c_off)
+            d.out_h, d.out_w, d.cout, d.tile_h, d.tile_w, d.batch, bool(d.residual), d.out_ld, d.out_c_off,
+            d.precision)
 
 
-def _candidates(cout):
+def _candidates(cout, prec=0):
     cands = []
-    for bn in BLOCK_NS:
+    for bn in ((64, 128) if prec == 1 else BLOCK_NS):
         if bn >= 2 * cout and bn > 32:
             continue
         for sk in (0, 1):
@@ -91,7 +112,7 @@ def _autotune(d):
     """time every (block_n, stream_k) candidate for this exact problem on the device (CUDA events,
     3 warm + 5 timed launches each) and remember the fastest; outputs are overwritten identically"""
     best = None
-    for bn, sk in _candidates(d.cout):
+    for bn, sk in _candidates(d.cout, d.precision):
         d.block_n, d.stream_k = bn, sk
         try:
             for _ in range(2):
@@ -177,7 +198,12 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     m_tiles = d.n_img * (-(-oh // th)) * (-(-ow // tw))
     d.batch = batch
     kb_per_tile = taps[0] * taps[1] * (-(-d.k_per_tap // 32))
+    d.precision = PRECISION[0]
     auto_bn, auto_sk = pick_config(d.cout, m_tiles, batch, kb_per_tile)
+    if d.precision == 1:
+        auto_bn = 64 if d.cout <= 64 else 128
+        if block_n not in (None, 64, 128):
+            block_n = auto_bn
     d.block_n = block_n if block_n is not None else auto_bn
     d.stream_k = auto_sk if stream_k is None else int(stream_k)
     d.a_c_off, d.a_n_off, d.b_k_off, d.b_n_off = a_c_off, a_n_off, b_k_off, b_n_off

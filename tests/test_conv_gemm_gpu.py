@@ -117,3 +117,27 @@ def test_stream_k_and_wide_tiles(cuda_dev, bn, sk):
         ops.conv_gemm(a, wp, out, taps=(3, 3), pad=1, relu=True, block_n=bn, stream_k=sk)
     torch.cuda.synchronize()
     assert _rel_err(out.permute(0, 3, 1, 2), ref) < TOL
+
+
+@pytest.mark.parametrize("bn,sk", [(64, 0), (128, 0), (128, 1)])
+def test_fp32x3_split_precision(cuda_dev, bn, sk):
+    """strict mode: hi*hi + hi*lo + lo*hi with TF32 MMAs -> near-fp32 (bound asserted: 2e-5 x RMS;
+    plain TF32 gives ~1.5e-3 on the same problem)"""
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(17)
+    n, h, w, cin, cout = 1, 38, 63, 256, 200
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g)
+    res = torch.randn(n, cout, h, w, generator=g)
+    ref = (F.conv2d(x.double(), wt.double(), bias.double(), 1, 2, 2) + res.double()).relu().float()
+    a = x.permute(0, 2, 3, 1).contiguous().to(cuda_dev)
+    wp = wt.permute(2, 3, 0, 1).reshape(9, cout, cin).contiguous().to(cuda_dev)
+    out = torch.full((n, h, w, cout), float("nan"), device=cuda_dev)
+    r = res.permute(0, 2, 3, 1).contiguous().to(cuda_dev)
+    with ops.precision("fp32x3"):
+        ops.conv_gemm(a, wp, out, taps=(3, 3), dil=2, pad=2, bias=bias.to(cuda_dev), residual=r, relu=True,
+                      block_n=bn, stream_k=sk)
+    torch.cuda.synchronize()
+    err = _rel_err(out.permute(0, 3, 1, 2), ref)
+    assert err < 2e-5, err

@@ -75,13 +75,13 @@ def test_base_r50_matches_reference_fixture(cuda_dev):
     assert dl < 5e-3, dl
 
 
-def _run_mega_against_fixture(cuda_dev, label):
+def _run_mega_against_fixture(cuda_dev, label, precision="tf32"):
     from mega_core.b200 import engine, synth
     gold = torch.load(os.path.join(ROOT, "tests", "golden", "mega_r101_192x320.pt"))
     h, w, total = gold["h"], gold["w"], gold["total"]
     sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
     frames = [synth.synthetic_frame(i, h, w).to(cuda_dev) for i in range(total)]
-    eng = engine.MegaEngine(sd, device=cuda_dev)
+    eng = engine.MegaEngine(sd, engine.EngineConfig(precision=precision), device=cuda_dev)
     gpf = gold["globals_per_frame"]
     per_frame = []
     for t, ref in enumerate(gold["frames"]):
@@ -139,3 +139,15 @@ def test_mega_r101_tf32_matches_reference_fixture(cuda_dev):
         assert f["matched_frac"] >= 0.97, f
         assert f["logits_maxabs"] < 8e-2, f
         assert f["proposals"] == f["ref_proposals"], f
+
+
+def test_mega_r101_fp32x3_product_path_matches_reference_fixture(cuda_dev):
+    """The PRODUCT path in its strict-parity arithmetic (EngineConfig(precision="fp32x3"): every dense
+    contraction on the tcgen05 tensor cores as a 3xTF32 split, ~2^-19 relative error) against the
+    reference's outputs: the north-star bar -- all proposals reproduced, class logits within 1e-3."""
+    frames = _run_mega_against_fixture(cuda_dev, "mega_r101_fp32x3", precision="fp32x3")
+    for f in frames:
+        assert f["matched_frac"] == 1.0, f
+        assert f["logits_maxabs"] < 1e-3, f
+        assert f["deltas_maxabs"] < 1e-3, f
+        assert f["dets"] == f["ref_dets"], f
