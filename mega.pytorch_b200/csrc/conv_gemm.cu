@@ -206,7 +206,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * L::kStageBytes;
           uint8_t* b_dst = a_dst + L::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          mbar_arrive_expect_tx(&full_bar[stage], L::kHalf);   // bytes delivered by the two TMA loads
           tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + tc.batch * p.a_c_off,
                       tc.w0 + s * p.dil - p.pad, tc.h0 + r * p.dil - p.pad, tc.img + tc.batch * p.a_n_off);
           tma_load_3d(b_dst, &tmB, &full_bar[stage], kc * kBK + tc.batch * p.b_k_off,

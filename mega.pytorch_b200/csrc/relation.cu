@@ -34,8 +34,12 @@ struct RelParams {
   float scale;
 };
 
+// SMEM_STAGE: the row's [16, ldm] logits live in shared memory between the passes (ldm <= 1024), so the
+// global logits are read once and the probabilities written once.
+template <bool SMEM_STAGE>
 __global__ void __launch_bounds__(kRelThreads)
 relation_softmax_kernel(const RelParams p) {
+  extern __shared__ float stage_s[];   // [16][ldm] when SMEM_STAGE
   __shared__ float wg_s[kEmb][kGroups];  // e-major so the 16 group weights of one feature are contiguous
   __shared__ float bg_s[kGroups];
   __shared__ float dim_s[8];
@@ -129,7 +133,7 @@ relation_softmax_kernel(const RelParams p) {
     for (int g = 0; g < kGroups; ++g) {
       float* sp = srow + g * p.head_stride + m;
       const float l = __fadd_rn(bias[g], __fmul_rn(p.scale, *sp));
-      *sp = l;
+      if (SMEM_STAGE) stage_s[g * p.ldm + m] = l; else *sp = l;
       const float nm = fmaxf(mx[g], l);
       sm[g] = sm[g] * __expf(mx[g] - nm) + __expf(l - nm);
       mx[g] = nm;
@@ -173,8 +177,50 @@ relation_softmax_kernel(const RelParams p) {
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
       float* sp = srow + g * p.head_stride + m;
-      *sp = (m < m_valid) ? __expf(*sp - fin_max[g]) * fin_inv[g] : 0.f;
+      const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
+      *sp = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
     }
+  }
+}
+
+// No position term: one warp per (head, query row); the row (<= 1024 keys) stays in registers, so the
+// logits are read once and the probabilities written once.
+__global__ void __launch_bounds__(256)
+plain_softmax_kernel(float* __restrict__ s, int n_rows, int ldm, long long head_stride, const int* m_valid_ptr, int m_host,
+                     const int* n_valid_ptr, int n_valid_off, float scale) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wid >= n_rows * kGroups) return;
+  const int g = wid / n_rows, n = wid - g * n_rows;
+  if (n_valid_ptr) {
+    const int nv = *n_valid_ptr;
+    if (n >= nv && n < n_valid_off) return;
+  }
+  const int m_valid = m_valid_ptr ? min(*m_valid_ptr, ldm) : m_host;
+  float* row = s + g * head_stride + static_cast<long long>(n) * ldm;
+  float v[32];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int m = j * 32 + lane;
+    v[j] = (m < m_valid) ? scale * row[m] : -INFINITY;
+    mx = fmaxf(mx, v[j]);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = (j * 32 + lane < m_valid) ? expf(v[j] - mx) : 0.f;
+    sum += v[j];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int m = j * 32 + lane;
+    if (m < ldm) row[m] = v[j] * inv;
   }
 }
 
@@ -206,7 +252,22 @@ extern "C" int mega_relation_softmax(float* logits, int n_rows, int ldm, const f
   p.n_valid_ptr = n_valid_ptr;
   p.n_valid_off = n_valid_off;
   p.scale = scale;
-  relation_softmax_kernel<<<n_rows, kRelThreads, 0, stream>>>(p);
+  if (boxes_q == nullptr && ldm <= 1024) {
+    const long long warps = static_cast<long long>(n_rows) * kGroups;
+    plain_softmax_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream>>>(
+        logits, n_rows, ldm, p.head_stride, m_valid_ptr, m_host, n_valid_ptr, n_valid_off, scale);
+  } else if (ldm <= 1024) {
+    const int smem = kGroups * ldm * static_cast<int>(sizeof(float));
+    static bool configured = false;
+    if (!configured) {
+      MEGA_CUDA_CHECK(cudaFuncSetAttribute(relation_softmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kGroups * 1024 * static_cast<int>(sizeof(float))));
+      configured = true;
+    }
+    relation_softmax_kernel<true><<<n_rows, kRelThreads, smem, stream>>>(p);
+  } else {
+    relation_softmax_kernel<false><<<n_rows, kRelThreads, 0, stream>>>(p);
+  }
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }

@@ -154,8 +154,8 @@ class ResNetStages:
             self._bufs[key] = t
         return t
 
-    def forward(self, x, out=None):
-        """x [N,H,W,C] NHWC -> [N,H',W',C']"""
+    def forward(self, x, out=None, max_ctas=0):
+        """x [N,H,W,C] NHWC -> [N,H',W',C'] (max_ctas > 0: leave SMs free for a concurrent stream)"""
         n_blocks = sum(len(s) for s in self.stages)
         done = 0
         for si, blocks in enumerate(self.stages):
@@ -165,12 +165,12 @@ class ResNetStages:
                 ho, wo = xs.shape[1], xs.shape[2]
                 t1 = self._buf("t1", (n, ho, wo, blk.mid))
                 t2 = self._buf("t2", (n, ho, wo, blk.mid))
-                ops.conv_gemm(xs, blk.w1, t1, scale=blk.s1, bias=blk.b1, relu=True)
+                ops.conv_gemm(xs, blk.w1, t1, scale=blk.s1, bias=blk.b1, relu=True, max_ctas=max_ctas)
                 ops.conv_gemm(t1, blk.w2, t2, taps=(3, 3), dil=blk.dil, pad=blk.dil, scale=blk.s2, bias=blk.b2,
-                              relu=True)
+                              relu=True, max_ctas=max_ctas)
                 if blk.wd is not None:
                     idn = self._buf("idn", (n, ho, wo, blk.cout))
-                    ops.conv_gemm(xs, blk.wd, idn, scale=blk.sd, bias=blk.bd, relu=False)
+                    ops.conv_gemm(xs, blk.wd, idn, scale=blk.sd, bias=blk.bd, relu=False, max_ctas=max_ctas)
                 else:
                     idn = x
                 done += 1
@@ -178,7 +178,7 @@ class ResNetStages:
                     y = out
                 else:
                     y = self._buf("y%d" % (done & 1), (n, ho, wo, blk.cout))
-                ops.conv_gemm(t2, blk.w3, y, scale=blk.s3, bias=blk.b3, residual=idn, relu=True)
+                ops.conv_gemm(t2, blk.w3, y, scale=blk.s3, bias=blk.b3, residual=idn, relu=True, max_ctas=max_ctas)
                 x = y
         return x
 
@@ -410,6 +410,7 @@ class MegaEngine(HeadCommon):
         self.idx_qin0 = torch.tensor(q_idx, dtype=torch.int32, device=dev)
         self._roi_tabs = {}
         self._graphs, self._static_in, self._eager_done = {}, {}, {}
+        self._side = None
         self.use_graph = False
         self.reset()
 
@@ -452,8 +453,20 @@ class MegaEngine(HeadCommon):
         c = self.cfg
         n = imgs.shape[0]
         feats = self.backbone.forward(imgs)
-        boxes, _, cnt = self.rpn(feats, im_w, im_h, self.KP)
-        r5 = self.res5.forward(feats)
+        # fork: proposal selection (few, latency-bound CTAs) on a side stream, overlapped with the res5 convolutions
+        # of the same frames (which need only `feats`); the GEMMs of the main branch leave 4 SMs free meanwhile
+        main = torch.cuda.current_stream(self.dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.dev)
+        self._side.wait_stream(main)
+        with torch.cuda.stream(self._side):
+            ops.WS_LANE[0] = 1
+            try:
+                boxes, _, cnt = self.rpn(feats, im_w, im_h, self.KP)
+            finally:
+                ops.WS_LANE[0] = 0
+        r5 = self.res5.forward(feats, max_ctas=144)
+        main.wait_stream(self._side)
         src, bidx, spans = self._roi_table(kinds)
         rows = src.numel()
         ops.gather_rows(boxes.view(n * self.KP, 4), src, self.roi_boxes[:rows])
