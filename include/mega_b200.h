@@ -164,6 +164,28 @@ int mega_box_postprocess(const float* logits, int ld_logits, const float* deltas
                          float wh, void* workspace, long long workspace_bytes, float* out_boxes, float* out_scores,
                          long long* out_labels, int out_cap, int* out_count, void* stream);
 
+/* -------------------------------------------- RetinaNet focal loss (csrc/SigmoidFocalLoss.h:10-32)
+ * logits [N,C] fp32, targets [N] int32 in {-1 (ignore), 0 (background), 1..C}. */
+int mega_sigmoid_focalloss_forward(const float* logits, const int* targets, int num_samples, int num_classes,
+                                   float gamma, float alpha, float* losses, void* stream);
+int mega_sigmoid_focalloss_backward(const float* logits, const int* targets, const float* d_losses, int num_samples,
+                                    int num_classes, float gamma, float alpha, float* d_logits, void* stream);
+
+/* --------------------------------------- deformable convolution v1 / v2 (csrc/deform_conv.h:11-28, :115)
+ * Bilinear im2col of an NCHW input with per-tap offsets [B, dg*2*kh*kw, Ho, Wo] and (v2) masks
+ * [B, dg*kh*kw, Ho, Wo] (mask == NULL: v1) into cols [B, Ho*Wo, kpad], k = c*kh*kw + i*kw + j; the
+ * contraction with weight.view(Cout, C*kh*kw) then runs on mega_conv_gemm_tf32. */
+int mega_deform_im2col(const float* input, const float* offset, const float* mask, int batch, int channels, int height,
+                       int width, int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w, int dil_h, int dil_w,
+                       int deformable_group, int kpad, float* cols, void* stream);
+
+/* ------------------- deformable position-sensitive ROI pooling forward (csrc/deform_pool.h:11-37) */
+int mega_deform_psroi_pooling_forward(const float* input, const float* rois, const float* trans, int num_rois,
+                                      int channels, int height, int width, int no_trans, float spatial_scale,
+                                      int output_dim, int group_size, int pooled_size, int part_size,
+                                      int sample_per_part, float trans_std, int num_classes, float* out,
+                                      float* top_count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

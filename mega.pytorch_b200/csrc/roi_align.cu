@@ -157,6 +157,86 @@ roi_align_nhwc_kernel(const float* __restrict__ in, int channels, int height, in
   }
 }
 
+// Same arithmetic, less L2 traffic: one CTA per (roi, 64-channel slice) first copies the cells the roi can touch
+// (rows r0..r1 x cols c0..c1 of the map, 256 B per cell) into shared memory, then all 49 bins sample from there;
+// neighbouring samples share corners, so each cell is fetched once per slice instead of up to ~8 times. ROIs whose
+// footprint exceeds the shared-memory budget (whole-image boxes) read global memory directly.
+constexpr int kRoiSlice = 64;            // channels per CTA
+constexpr int kRoiMaxCells = 192;        // 192 cells x 256 B = 48 KB per CTA (4 CTAs per SM)
+
+__global__ void __launch_bounds__(256)
+roi_align_nhwc_cached_kernel(const float* __restrict__ in, int channels, int height, int width, long long in_img_stride,
+                             const float* __restrict__ rois, int roi_ld, int roi_box_off,
+                             const int* __restrict__ roi_batch, float scale, int ph, int pw, int sampling_ratio,
+                             float* __restrict__ out, long long out_roi_stride) {
+  extern __shared__ float4 cell_s[];   // [cells][16] float4
+  const int slice = blockIdx.x;
+  const int n = blockIdx.y;
+  float roi5[5];
+  roi5[0] = roi_batch ? static_cast<float>(roi_batch[n]) : 0.f;
+  const float* rb = rois + static_cast<long long>(n) * roi_ld + roi_box_off;
+  if (roi_box_off < 0) {
+    rb = rois + static_cast<long long>(n) * roi_ld;
+    roi5[0] = rb[0];
+    rb += 1;
+  }
+  roi5[1] = rb[0]; roi5[2] = rb[1]; roi5[3] = rb[2]; roi5[4] = rb[3];
+  const RoiGeom g = roi_geom(roi5, scale, ph, pw, sampling_ratio);
+  const float* img = in + static_cast<long long>(g.batch) * in_img_stride + slice * kRoiSlice;
+  // footprint of every sample this roi can take (after the reference's clamping of y, x to the map)
+  const float end_h = __fadd_rn(g.start_h, __fmul_rn(g.bin_h, static_cast<float>(ph)));
+  const float end_w = __fadd_rn(g.start_w, __fmul_rn(g.bin_w, static_cast<float>(pw)));
+  int r0 = static_cast<int>(floorf(fmaxf(g.start_h, 0.f))), r1 = static_cast<int>(floorf(fmaxf(end_h, 0.f))) + 1;
+  int c0 = static_cast<int>(floorf(fmaxf(g.start_w, 0.f))), c1 = static_cast<int>(floorf(fmaxf(end_w, 0.f))) + 1;
+  r0 = min(max(r0, 0), height - 1); r1 = min(max(r1, 0), height - 1);
+  c0 = min(max(c0, 0), width - 1); c1 = min(max(c1, 0), width - 1);
+  const int rh = r1 - r0 + 1, rw = c1 - c0 + 1;
+  const bool cached = (rh * rw <= kRoiMaxCells);
+  if (cached) {
+    for (int i = threadIdx.x; i < rh * rw * 16; i += blockDim.x) {
+      const int cell = i >> 4, q = i & 15;
+      const int rr = cell / rw, cc = cell - rr * rw;
+      cell_s[i] = ldg_f4(img + (static_cast<long long>(r0 + rr) * width + (c0 + cc)) * channels + q * 4);
+    }
+  }
+  __syncthreads();
+  const int q = threadIdx.x & 15;
+  const float count = static_cast<float>(g.grid_h * g.grid_w);
+  float* obase = out + static_cast<long long>(n) * out_roi_stride + slice * kRoiSlice + q * 4;
+  for (int bin = threadIdx.x >> 4; bin < ph * pw; bin += blockDim.x >> 4) {
+    const int phi = bin / pw, pwi = bin - phi * pw;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const float y = sample_coord(g.start_h, phi, g.bin_h, iy, g.grid_h);
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const float x = sample_coord(g.start_w, pwi, g.bin_w, ix, g.grid_w);
+        const Bilinear b = bilinear_setup(height, width, y, x);
+        if (b.empty) continue;
+        float4 v1, v2, v3, v4;
+        const bool inside = cached && b.y_low >= r0 && b.y_high <= r1 && b.x_low >= c0 && b.x_high <= c1;
+        if (inside) {
+          v1 = cell_s[((b.y_low - r0) * rw + (b.x_low - c0)) * 16 + q];
+          v2 = cell_s[((b.y_low - r0) * rw + (b.x_high - c0)) * 16 + q];
+          v3 = cell_s[((b.y_high - r0) * rw + (b.x_low - c0)) * 16 + q];
+          v4 = cell_s[((b.y_high - r0) * rw + (b.x_high - c0)) * 16 + q];
+        } else {
+          v1 = ldg_f4(img + (static_cast<long long>(b.y_low) * width + b.x_low) * channels + q * 4);
+          v2 = ldg_f4(img + (static_cast<long long>(b.y_low) * width + b.x_high) * channels + q * 4);
+          v3 = ldg_f4(img + (static_cast<long long>(b.y_high) * width + b.x_low) * channels + q * 4);
+          v4 = ldg_f4(img + (static_cast<long long>(b.y_high) * width + b.x_high) * channels + q * 4);
+        }
+        acc.x = __fadd_rn(acc.x, blend(b, v1.x, v2.x, v3.x, v4.x));
+        acc.y = __fadd_rn(acc.y, blend(b, v1.y, v2.y, v3.y, v4.y));
+        acc.z = __fadd_rn(acc.z, blend(b, v1.z, v2.z, v3.z, v4.z));
+        acc.w = __fadd_rn(acc.w, blend(b, v1.w, v2.w, v3.w, v4.w));
+      }
+    }
+    acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
+    acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+    *reinterpret_cast<float4*>(obase + static_cast<long long>(bin) * channels) = acc;
+  }
+}
+
 }  // namespace mega
 
 using namespace mega;
@@ -189,6 +269,20 @@ extern "C" int mega_roi_align_forward_nhwc(const float* input, int channels, int
                      (out_roi_stride & 3) == 0,
                  "roi_align_nhwc: 16-byte alignment required");
   if (num_rois == 0) return MEGA_OK;
+  if ((channels % kRoiSlice) == 0) {
+    static bool configured = false;
+    if (!configured) {
+      MEGA_CUDA_CHECK(cudaFuncSetAttribute(roi_align_nhwc_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kRoiMaxCells * 256));
+      configured = true;
+    }
+    dim3 cgrid(channels / kRoiSlice, num_rois);
+    roi_align_nhwc_cached_kernel<<<cgrid, 256, kRoiMaxCells * 256, stream>>>(
+        input, channels, height, width, in_img_stride, rois, roi_ld, roi_box_off, roi_batch, spatial_scale, pooled_h,
+        pooled_w, sampling_ratio, output, out_roi_stride);
+    MEGA_CUDA_CHECK(cudaGetLastError());
+    return MEGA_OK;
+  }
   dim3 grid(pooled_h * pooled_w, num_rois);
   roi_align_nhwc_kernel<<<grid, 256, 0, stream>>>(input, channels, height, width, in_img_stride, rois, roi_ld,
                                                   roi_box_off, roi_batch, spatial_scale, pooled_h, pooled_w,

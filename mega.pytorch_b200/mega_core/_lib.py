@@ -125,10 +125,21 @@ lib.mega_box_postprocess.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _f, _f,
                                      _vp, _vp, _vp, _i, _vp, _vp]
 lib.mega_box_postprocess.restype = _i
 
+lib.mega_sigmoid_focalloss_forward.argtypes = [_vp, _vp, _i, _i, _f, _f, _vp, _vp]
+lib.mega_sigmoid_focalloss_forward.restype = _i
+lib.mega_sigmoid_focalloss_backward.argtypes = [_vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp]
+lib.mega_sigmoid_focalloss_backward.restype = _i
+lib.mega_deform_im2col.argtypes = [_vp, _vp, _vp] + [_i] * 14 + [_vp, _vp]
+lib.mega_deform_im2col.restype = _i
+lib.mega_deform_psroi_pooling_forward.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _i, _f, _i, _vp,
+                                                  _vp, _vp]
+lib.mega_deform_psroi_pooling_forward.restype = _i
+
 EXPORTS = [
     "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm_tf32", "mega_conv_gemm_workspace_bytes", "mega_set_tf32_rounding",
     "mega_nms_workspace_bytes", "mega_nms", "mega_rpn_select_workspace_bytes", "mega_rpn_select",
     "mega_roi_align_forward_nchw", "mega_roi_align_forward_nhwc", "mega_stem_im2col", "mega_maxpool3x3s2_nhwc",
     "mega_gather_rows", "mega_copy_rows", "mega_transpose_2d", "mega_relation_softmax", "mega_box_postprocess_workspace_bytes",
-    "mega_box_postprocess",
+    "mega_box_postprocess", "mega_sigmoid_focalloss_forward", "mega_sigmoid_focalloss_backward",
+    "mega_deform_im2col", "mega_deform_psroi_pooling_forward",
 ]

@@ -546,3 +546,70 @@ class BaseOracle:
                           "class_logits": logits.clone(), "box_regression": bdelta.clone(), "feats": feats}
         return box_postprocess(logits, bdelta, prop, im_w, im_h, c.score_thresh, c.nms_thresh,
                                c.detections_per_img, cuda_semantics=c.cuda_nms_semantics)
+
+
+# --------------------------------------------------------------------------- ops outside the VID configs
+def sigmoid_focal_loss(logits, targets, gamma, alpha):
+    """layers/sigmoid_focal_loss.py:40-50 (the reference's own CPU formula for RetinaNet's focal loss)."""
+    num_classes = logits.shape[1]
+    class_range = torch.arange(1, num_classes + 1, dtype=targets.dtype).unsqueeze(0)
+    t = targets.unsqueeze(1)
+    p = torch.sigmoid(logits)
+    term1 = (1 - p) ** gamma * torch.log(p)
+    term2 = p ** gamma * torch.log(1 - p)
+    return -(t == class_range).float() * term1 * alpha - ((t != class_range) * (t >= 0)).float() * term2 * (1 - alpha)
+
+
+def deform_psroi_pool(data, rois, trans, no_trans, spatial_scale, output_dim, group_size, pooled_size, part_size,
+                      sample_per_part, trans_std):
+    """plain-Python restatement of DeformablePSROIPoolForwardKernel (csrc/cuda/deform_pool_kernel_cuda.cu:53-141);
+    small inputs only. PARITY UNPINNED by any reference test or CPU implementation (deform_pool.h:37 has none)."""
+    n_rois = rois.shape[0]
+    _, channels, height, width = data.shape
+    num_classes = 1 if no_trans else trans.shape[1] // 2
+    cec = output_dim if no_trans else output_dim // num_classes
+    out = torch.zeros(n_rois, output_dim, pooled_size, pooled_size)
+    cnt = torch.zeros_like(out)
+    f = np.float32
+    for n in range(n_rois):
+        b = int(rois[n, 0])
+        sw = f(round(float(rois[n, 1]))) * f(spatial_scale) - f(0.5)
+        sh = f(round(float(rois[n, 2]))) * f(spatial_scale) - f(0.5)
+        ew = f(round(float(rois[n, 3])) + 1.0) * f(spatial_scale) - f(0.5)
+        eh = f(round(float(rois[n, 4])) + 1.0) * f(spatial_scale) - f(0.5)
+        rw, rh = max(f(ew - sw), f(0.1)), max(f(eh - sh), f(0.1))
+        bh, bw = f(rh / f(pooled_size)), f(rw / f(pooled_size))
+        sbh, sbw = f(bh / f(sample_per_part)), f(bw / f(sample_per_part))
+        for ctop in range(output_dim):
+            cls = ctop // cec
+            for ph in range(pooled_size):
+                for pw in range(pooled_size):
+                    part_h = int(math.floor(f(ph) / pooled_size * part_size))
+                    part_w = int(math.floor(f(pw) / pooled_size * part_size))
+                    tx = f(0) if no_trans else f(trans[n, cls * 2, part_h, part_w]) * f(trans_std)
+                    ty = f(0) if no_trans else f(trans[n, cls * 2 + 1, part_h, part_w]) * f(trans_std)
+                    wstart = f(f(pw) * bw + sw) + f(tx * rw)
+                    hstart = f(f(ph) * bh + sh) + f(ty * rh)
+                    gw = min(max(int(math.floor(f(pw) * group_size / pooled_size)), 0), group_size - 1)
+                    gh = min(max(int(math.floor(f(ph) * group_size / pooled_size)), 0), group_size - 1)
+                    c = (ctop * group_size + gh) * group_size + gw
+                    s, k = f(0), 0
+                    for ih in range(sample_per_part):
+                        for iw in range(sample_per_part):
+                            w_ = f(wstart + f(iw) * sbw)
+                            h_ = f(hstart + f(ih) * sbh)
+                            if w_ < -0.5 or w_ > width - 0.5 or h_ < -0.5 or h_ > height - 0.5:
+                                continue
+                            w_ = min(max(w_, f(0)), f(width - 1))
+                            h_ = min(max(h_, f(0)), f(height - 1))
+                            x1, x2 = int(math.floor(w_)), int(math.ceil(w_))
+                            y1, y2 = int(math.floor(h_)), int(math.ceil(h_))
+                            dx, dy = f(w_ - x1), f(h_ - y1)
+                            pl = data[b, c]
+                            v = (1 - dx) * (1 - dy) * f(pl[y1, x1]) + (1 - dx) * dy * f(pl[y2, x1]) + \
+                                dx * (1 - dy) * f(pl[y1, x2]) + dx * dy * f(pl[y2, x2])
+                            s = f(s + f(v))
+                            k += 1
+                    out[n, ctop, ph, pw] = 0.0 if k == 0 else float(s / f(k))
+                    cnt[n, ctop, ph, pw] = k
+    return out, cnt

@@ -36,10 +36,10 @@ def match(a, b, tol=0.75):
     return idx
 
 
-def run(label, ctx):
+def run(label, ctx, precision="tf32"):
     out = []
     with ctx:
-        eng = engine.MegaEngine(sd, device=dev)
+        eng = engine.MegaEngine(sd, engine.EngineConfig(precision=precision), device=dev)
         for t in range(3):
             if t == 0:
                 eng.start_video(dframes[0], dframes[1:13], [dframes[j] for j in gpf[0]], w, h)
@@ -69,6 +69,54 @@ def run(label, ctx):
 
 
 import contextlib  # noqa: E402
-res = {"tf32": run("tf32", contextlib.nullcontext()), "fp32_shadow": run("fp32", fp32_shadow())}
+from mega_core.b200 import ops  # noqa: E402
+import fp32_shadow as _fs  # noqa: E402
+
+
+def per_gemm_audit():
+    """strict mode: run every conv_gemm of two frames twice -- tcgen05 3xTF32 and the fp64 shadow on the SAME
+    inputs -- and report the worst relative error with the call's signature"""
+    worst = []
+    real = ops.conv_gemm
+
+    def audited(a, w, out, **kw):
+        res = kw.get("residual")
+        res_copy = res.clone() if res is not None else None
+        real(a, w, out, **kw)
+        got = out.clone()
+        if res is not None and res.data_ptr() == out.data_ptr():
+            kw = dict(kw)
+            kw["residual"] = res_copy
+        ref = torch.zeros_like(out)
+        ref.copy_(got)
+        _fs._shadow_conv_gemm(a, w, ref, **kw)
+        cout = kw.get("cout") or w.shape[1]
+        if kw.get("out_c_off"):
+            width = cout + (kw.get("batch", 1) - 1) * kw["out_c_off"]
+        else:
+            width = cout
+        d = (got[..., :width] - ref[..., :width]).abs().max().item()
+        r = ref[..., :width].pow(2).mean().sqrt().item()
+        worst.append((d / max(r, 1e-20), tuple(a.shape), tuple(w.shape), {k: v for k, v in kw.items()
+                                                                            if k in ("taps", "dil", "batch", "k", "cout", "block_n")}))
+        out.copy_(got)
+        return out
+
+    ops.conv_gemm = audited
+    try:
+        eng = engine.MegaEngine(sd, engine.EngineConfig(precision="fp32x3"), device=dev)
+        eng.start_video(dframes[0], dframes[1:13], [dframes[j] for j in gpf[0]], w, h)
+        eng.step(dframes[13], dframes[gpf[1][0]], w, h)
+        torch.cuda.synchronize()
+    finally:
+        ops.conv_gemm = real
+    worst.sort(key=lambda t: -t[0])
+    for t in worst[:12]:
+        print("AUDIT", "%.3e" % t[0], t[1], t[2], t[3])
+    return [[t[0], str(t[1]), str(t[2]), str(t[3])] for t in worst[:12]]
+
+audit = per_gemm_audit()
+res = {"gemm_audit_fp32x3": audit, "fp32x3": run("fp32x3", contextlib.nullcontext(), "fp32x3"), "tf32": run("tf32", contextlib.nullcontext()),
+       "fp32_shadow": run("fp32", fp32_shadow())}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "diag_parity.json"), "w"), indent=1)
