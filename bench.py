@@ -106,6 +106,11 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def workload(args):
+    return ("MEGA R-101 C4 steady-state key frame, %dx%d, 25 local / 10 global / 25 memory frames, "
+            "1 new local + 1 new global frame per step" % (args.width, args.height))
+
+
 def frame_pool(n, h, w):
     from mega_core.b200 import synth
     return [synth.synthetic_frame(i, h, w) for i in range(n)]
@@ -229,9 +234,7 @@ def run_b200(args, rank, world):
         "metric": METRIC, "value": world * args.steps / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-        "config": {"workload": "MEGA R-101 C4 steady-state key frame, %dx%d, 25 local / 10 global / 25 memory frames, "
-                               "1 new local + 1 new global frame per step" % (w, h),
-                   "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
+        "config": {"workload": workload(args), "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
                    "parallelism": ("frame-parallel over %d GPUs, NCCL all-gather of ROI-feature payloads, replicated "
                                    "aggregation" % world) if world > 1 else "single GPU",
                    "cuda_graph": bool(eng._graphs),
@@ -363,8 +366,9 @@ def run_reference(args, rank, world):
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MEGA R-101 C4 steady-state key frame, %dx%d, CPU oracle port, %d timed frames"
-                                   % (args.width, args.height, n), "arch": args.arch},
+            "config": {"workload": workload(args), "arch": args.arch,
+                       "weights": "seeded synthetic init (mega_core.b200.synth)",
+                       "implementation": "CPU port of the reference path (oracle/mega_oracle.py), %d timed frames" % n},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

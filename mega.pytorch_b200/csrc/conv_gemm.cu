@@ -140,7 +140,15 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                       const ConvGemmParams p) {
   using L = SmemLayout<BN, STAGES, SPLIT3>;
-  constexpr uint32_t kTmemCols = (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  // accumulators: two ping-pong buffers (+ a master accumulator in 3xTF32 mode, see kSegLen)
+  constexpr uint32_t kAccBufs = SPLIT3 ? 3 : 2;
+  constexpr uint32_t kTmemCols = (kAccBufs * BN <= 64) ? 64 : (kAccBufs * BN <= 128) ? 128 : (kAccBufs * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kAccStride = SPLIT3 ? BN : kTmemCols / 2;
+  // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
+  // accumulation chain (measured ~1e-3 relative after 3000 k-blocks). The strict mode therefore restarts the
+  // TMEM accumulator every kSegLen k-blocks and folds the segments into a master accumulator (also in TMEM)
+  // with round-to-nearest fp32 adds done by the epilogue warps.
+  constexpr int kSegLen = SPLIT3 ? 32 : 0x7fffffff;
   extern __shared__ uint8_t smem_raw[];
   // the 128B swizzle pattern is a function of the absolute smem address: align to 1024 B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -227,36 +235,40 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       WorkIter it(p, cta, grid);
       long long t;
       int kb0, kb1;
-      for (int item = 0; it.next(t, kb0, kb1); ++item) {
-        const int buf = item & 1;
-        const uint32_t use = static_cast<uint32_t>(item >> 1);
-        mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * (kTmemCols / 2);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(SPLIT3 ? &split_bar[stage] : &full_bar[stage], phase);
+      int item = 0;
+      while (it.next(t, kb0, kb1)) {
+        for (int s0 = kb0, s1 = 0; s0 < kb1; s0 = s1, ++item) {
+          s1 = (kb1 - s0 > kSegLen) ? s0 + kSegLen : kb1;
+          const int buf = item & 1;
+          const uint32_t use = static_cast<uint32_t>(item >> 1);
+          mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-          const uint32_t b_addr = a_addr + L::kABytes;
-          const uint64_t adesc = umma_desc_sw128(a_addr);
-          const uint64_t bdesc = umma_desc_sw128(b_addr);
+          const uint32_t tmem_d = tmem_base + buf * kAccStride;
+          for (int kb = s0; kb < s1; ++kb) {
+            mbar_wait(SPLIT3 ? &split_bar[stage] : &full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t b_addr = a_addr + L::kABytes;
+            const uint64_t adesc = umma_desc_sw128(a_addr);
+            const uint64_t bdesc = umma_desc_sw128(b_addr);
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advance 8 floats = 32 B inside the swizzle row: +2 in 16-byte units
-            umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (SPLIT3) {
-              const uint64_t alo = umma_desc_sw128(a_addr + L::kHalf), blo = umma_desc_sw128(b_addr + L::kHalf);
-              umma_tf32(tmem_d, adesc + 2 * k, blo + 2 * k, idesc, 1u);
-              umma_tf32(tmem_d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              // advance 8 floats = 32 B inside the swizzle row: +2 in 16-byte units
+              umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+              if (SPLIT3) {
+                const uint64_t alo = umma_desc_sw128(a_addr + L::kHalf), blo = umma_desc_sw128(b_addr + L::kHalf);
+                umma_tf32(tmem_d, adesc + 2 * k, blo + 2 * k, idesc, 1u);
+                umma_tf32(tmem_d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          umma_commit(&tmem_full_bar[buf]);
         }
-        umma_commit(&tmem_full_bar[buf]);
       }
     }
   } else if (warp >= 6) {
@@ -306,25 +318,69 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     WorkIter it(p, cta, grid);
     long long t;
     int kb0, kb1;
-    for (int item = 0; it.next(t, kb0, kb1); ++item) {
+    int item = 0;   // accumulator-segment counter (ping-pong bookkeeping shared with the MMA warp)
+    const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t master_row = tmem_base + 2 * kAccStride + lane_bits;
+    for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
       const TileCoord tc = decode_tile(p, t, BN);
+      // ---- 3xTF32 only: fold every segment but the last into the master accumulator (RN fp32 adds)
+      bool has_master = false;
+      int s0 = kb0;
+      for (; SPLIT3 && s0 + kSegLen < kb1; s0 += kSegLen, ++item) {
+        const int fb = item & 1;
+        mbar_wait(&tmem_full_bar[fb], static_cast<uint32_t>(item >> 1) & 1);
+        tc_fence_after();
+        const uint32_t seg_row = tmem_base + fb * kAccStride + lane_bits;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t a[32];
+          __syncwarp();
+          tmem_ld_32x32(seg_row + c * 32, a);
+          tmem_ld_wait();
+          if (has_master) {
+            uint32_t m[32];
+            tmem_ld_32x32(master_row + c * 32, m);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(__fadd_rn(__uint_as_float(a[j]), __uint_as_float(m[j])));
+          }
+          tmem_st_32x32(master_row + c * 32, a);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[fb]);
+        has_master = true;
+      }
       const int buf = item & 1;
       const uint32_t use = static_cast<uint32_t>(item >> 1);
+      ++item;
       mbar_wait(&tmem_full_bar[buf], use & 1);
       tc_fence_after();
-      const uint32_t tmem_row = tmem_base + buf * (kTmemCols / 2) + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t tmem_row = tmem_base + buf * kAccStride + lane_bits;
+      // accumulator chunk c (32 columns of this thread's row): last segment (+ master)
+      auto load_acc = [&](int c, uint32_t (&acc)[32]) {
+        __syncwarp();  // tcgen05.ld is .sync.aligned
+        tmem_ld_32x32(tmem_row + c * 32, acc);
+        tmem_ld_wait();
+        if (SPLIT3 && has_master) {
+          uint32_t m[32];
+          tmem_ld_32x32(master_row + c * 32, m);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__fadd_rn(__uint_as_float(acc[j]), __uint_as_float(m[j])));
+        }
+      };
       const bool complete = (kb0 == 0 && kb1 == KB);
       bool finalize = complete;
       int c_first = cta, c_last = cta;
       if (!complete) {
         // ---- publish this CTA's partial accumulator, then find out whether it arrived last
-        float* my_ws = p.part_ws + ((static_cast<long long>(cta) * 2 + (item == 0 ? 0 : 1)) * kBM + row) * BN;
+        float* my_ws = p.part_ws + ((static_cast<long long>(cta) * 2 + (tile_item == 0 ? 0 : 1)) * kBM + row) * BN;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t acc[32];
-          __syncwarp();
-          tmem_ld_32x32(tmem_row + c * 32, acc);
-          tmem_ld_wait();
+          load_acc(c, acc);
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
@@ -367,9 +423,7 @@ conv_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
           uint32_t acc[32];
-          __syncwarp();  // tcgen05.ld is .sync.aligned
-          tmem_ld_32x32(tmem_row + c * 32, acc);
-          tmem_ld_wait();
+          load_acc(c, acc);
           const int nb = tc.n0 + c * 32;
           if (!complete) {
             // deterministic reduction: parts summed in CTA order, own part from TMEM
