@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--arch", default="mega_r101")
     ap.add_argument("--height", type=int, default=H)
     ap.add_argument("--width", type=int, default=W)
+    ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32x3"],
+                    help="contraction arithmetic of the timed engine (EngineConfig.precision)")
+    ap.add_argument("--no-strict", action="store_true", help="skip the extra fp32x3 (strict-parity mode) timing")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
@@ -126,7 +129,7 @@ def run_b200(args, rank, world):
     torch.cuda.set_device(dev)
     h, w = args.height, args.width
     sd = synth.make_state_dict(args.arch, seed=0)
-    model = build_detection_model_from_state_dict(sd, method="mega", device=dev)
+    model = build_detection_model_from_state_dict(sd, method="mega", device=dev, precision=args.precision)
     eng = model.engine
     eng.use_graph = not args.no_graph
     pool = frame_pool(16, h, w)
@@ -220,6 +223,11 @@ def run_b200(args, rank, world):
     # ---- roofline of the dominant kernel (tcgen05 conv/GEMM): eager frames with an event pair per launch
     roof = roofline_pass(eng, pairs_dev, w, h)
 
+    # ---- the strict-parity arithmetic (3xTF32, logits within 1e-3 of the fp32 reference) timed on the same workload
+    strict = None
+    if world == 1 and not args.no_strict and args.precision != "fp32x3":
+        strict = strict_pass(args, sd, dev, pool_pinned, pairs_dev, w, h)
+
     if rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         ops.save_tuned(os.path.join(ROOT, "gpurun_out", "tuned_b200.json"))
@@ -233,11 +241,11 @@ def run_b200(args, rank, world):
     line = {
         "metric": METRIC, "value": world * args.steps / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": PRECISION_DTYPE[args.precision], "data": "synthetic",
         "config": {"workload": workload(args), "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
                    "parallelism": ("frame-parallel over %d GPUs, NCCL all-gather of ROI-feature payloads, replicated "
                                    "aggregation" % world) if world > 1 else "single GPU",
-                   "cuda_graph": bool(eng._graphs),
+                   "cuda_graph": bool(eng._graphs), "precision": args.precision,
                    "l2": "per-step working set (0.7 GB fp32 weights + >0.5 GB activations) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,
         "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
@@ -245,12 +253,45 @@ def run_b200(args, rank, world):
         "gpu_launches": int(round(launches_per_step * args.steps * (1 if world == 1 else 1))),
         "roofline": {"bound": "tensor", "achieved": roof["algo_tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": roof["algo_tflops"] / pk["tflops"], "traffic": None, "peak_source": pk["src"],
-                     "kernel": "conv_gemm_tf32_kernel (tcgen05 kind::tf32; TF32 dense peak is half the bf16 figure)",
+                     "kernel": KERNEL_NOTE[args.precision],
                      "algorithmic_gflop_per_frame": ALGO_GFLOP_PER_FRAME, "executed_gflop_per_frame": roof["exec_gflop"],
                      "kernel_ms_per_frame": roof["kernel_ms"], "launches_per_frame": roof["launches"],
                      "executed_tflops": roof["exec_tflops"], "kernel_share_of_step": roof["kernel_ms"] / (dev_ms / args.steps)},
     }
+    if strict is not None:
+        line["strict_parity_mode"] = strict
     return line
+
+
+PRECISION_DTYPE = {"f16": "f16 operands / f32 accumulate", "tf32": "tf32 operands / f32 accumulate",
+                   "fp32x3": "3xtf32 split (near-f32) / f32 accumulate"}
+KERNEL_NOTE = {"f16": "conv_gemm_kernel<.., kModeF16> (tcgen05 kind::f16, fp16 operands; same dense peak as bf16)",
+               "tf32": "conv_gemm_kernel<.., kModeTf32> (tcgen05 kind::tf32; TF32 dense peak is half the bf16 figure)",
+               "fp32x3": "conv_gemm_kernel<.., kModeSplit3> (3 tcgen05 kind::tf32 MMAs per product)"}
+
+
+def strict_pass(args, sd, dev, pool_pinned, pairs_dev, w, h, steps=8):
+    """same steady-state step with every contraction in the 3xTF32 strict-parity arithmetic"""
+    from mega_core.modeling.detector import build_detection_model_from_state_dict
+    model = build_detection_model_from_state_dict(sd, method="mega", device=dev, precision="fp32x3")
+    eng = model.engine
+    eng.use_graph = not args.no_graph
+    with torch.no_grad():
+        model({"cur": pool_pinned[0], "ref_l": [], "ref_g": [pool_pinned[(3 * j + 1) % 16] for j in range(10)],
+               "frame_category": 0, "seg_len": 10 ** 6, "pattern": "%06d", "img_dir": "%s",
+               "lookahead": [pool_pinned[(j + 1) % 16] for j in range(12)]})
+        for i in range(eng.MEMF + 2):
+            eng.step_batched(pairs_dev[i % 16], w, h)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            eng.step_batched(pairs_dev[i % 16], w, h)
+        e1.record()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"precision": "fp32x3", "value": 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "steps": steps,
+            "note": "3xTF32 contractions: class logits within 1e-3 of the fp32 reference (tests/test_engine_gpu.py)"}
 
 
 def roofline_pass(eng, pairs_dev, w, h, reps=3):

@@ -30,7 +30,10 @@ int mega_abi_version(void);
 int mega_device_ok(void);
 
 /* ------------------------------------------------- dense contractions (tcgen05)
- * Implicit-GEMM convolution / GEMM, TF32 operands, FP32 accumulation:
+ * Implicit-GEMM convolution / GEMM on the tensor cores, FP32 accumulation in TMEM. Operand arithmetic is selected
+ * by `precision`: 0 = fp32 tensors rounded to TF32 on load, 1 = fp32 tensors, 3xTF32 split (near-fp32), 2 = fp16
+ * tensors (same 10-bit mantissa as TF32, half the bytes, twice the tensor-pipe rate); the output / residual are
+ * fp32, or fp16 when out_f16 != 0 (precision 2 only).
  *   out[n,h,w,co] = act( scale[co] * sum_{r,s,ci} a[n, h + r*dil - pad, w + s*dil - pad, ci]
  *                                          * b[r*S+s, co, ci]  + bias[co] + residual[n,h,w,co] )
  * Replaces: ATen/cuDNN conv2d + FrozenBatchNorm2d + add + relu_ of
@@ -38,24 +41,24 @@ int mega_device_ok(void);
  * make_layers.py:80-92 (as an H=1 image, taps 1x1), torch.bmm / torch.matmul of
  * roi_heads/box_head/roi_box_feature_extractors.py:616-638 (batch>1 with the *_off fields). */
 typedef struct mega_conv_gemm_desc {
-  /* A: activations, NHWC fp32 (strides in floats, innermost stride 1) */
-  const float* a;
+  /* A: activations, NHWC, fp32 or fp16 by `precision` (strides in ELEMENTS, innermost stride 1) */
+  const void* a;
   int a_n, a_h, a_w, a_c;
   long long a_stride_w, a_stride_h, a_stride_n;
-  /* B: weights [taps][cout rows][k] fp32, k contiguous */
-  const float* b;
+  /* B: weights [taps][cout rows][k], same element type as A, k contiguous */
+  const void* b;
   int b_n, b_k;
   long long b_stride_n, b_stride_tap;
   int taps_r, taps_s, dil, pad;
   int k_per_tap; /* reduction length per tap (Cin) */
-  /* output NHWC, dense in (w, h, n) with out_ld floats between pixels (written by TMA: 16-byte aligned
-   * base, out_ld % 4 == 0; the residual likewise); out_h/out_w = output spatial size */
-  float* out;
+  /* output NHWC, dense in (w, h, n) with out_ld elements between pixels (written by TMA: 16-byte aligned
+   * base and pitch; the residual likewise, same element type as the output); out_h/out_w = output spatial size */
+  void* out;
   long long out_ld;
   int n_img, out_h, out_w, cout;
   const float* scale;    /* [cout] or NULL */
   const float* bias;     /* [cout] or NULL */
-  const float* residual; /* same indexing as out with res_ld, or NULL */
+  const void* residual;  /* same indexing and element type as out, with res_ld, or NULL */
   long long res_ld;
   int relu;
   /* tiling: tile_h*tile_w == 128 output pixels per CTA, block_n in {32,64,96,128,160,192,256} */
@@ -72,14 +75,19 @@ typedef struct mega_conv_gemm_desc {
    * its counter region zero) holds the tile counters and the partial accumulators of tiles whose
    * K range is shared by several CTAs. Launches that may run concurrently need distinct workspaces. */
   int precision; /* 0: TF32 operands (round-to-nearest on load); 1: "3xTF32" split (hi*hi + hi*lo + lo*hi),
-                    ~2^-19 relative error, block_n 64 or 128 */
+                    ~2^-19 relative error, block_n 64 or 128; 2: fp16 operands (A and B are __half arrays) */
   int max_ctas;
   int stream_k; /* 1: split tiles across CTAs at k-block granularity (balances any tile count over the
                    SMs; partial tiles are reduced by the last CTA to arrive, in CTA order); 0: whole tiles */
   void* workspace;
   long long workspace_bytes;
+  int out_f16; /* 1: out / residual are __half (precision 2, block_n % 64 == 0); 0: fp32 */
+  int pdl;     /* 1: programmatic dependent launch -- the kernel's prologue overlaps the tail of the previous kernel
+                  on the stream (it orders its own memory accesses behind that kernel with griddepcontrol.wait) */
 } mega_conv_gemm_desc;
 
+int mega_conv_gemm(const mega_conv_gemm_desc* desc, void* stream);
+/* ABI v1 name of mega_conv_gemm (kept for existing callers) */
 int mega_conv_gemm_tf32(const mega_conv_gemm_desc* desc, void* stream);
 long long mega_conv_gemm_workspace_bytes(void);
 /* TMA fp32->tf32 conversion on load (round-to-nearest) on/off; returns the previous value. */
@@ -122,6 +130,13 @@ int mega_roi_align_forward_nhwc(const float* input, int channels, int height, in
                                 float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, float* output,
                                 long long out_roi_stride, void* stream);
 
+/* fp16 feature map in, fp16 [K, ph*pw, C] out (the fp16-operand engine); interpolation arithmetic in fp32 as above,
+ * one rounding to fp16 at the store. in_img_stride / out_roi_stride in halves. */
+int mega_roi_align_forward_nhwc_f16(const void* input, int channels, int height, int width, long long in_img_stride,
+                                    const float* rois, int roi_ld, int roi_box_off, const int* roi_batch,
+                                    int num_rois, float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                                    void* output, long long out_roi_stride, void* stream);
+
 /* --------------------------------------------------------- backbone helpers
  * stem_im2col: NCHW image [N,3,H,W] -> [N, Ho*Wo, kpad] rows (k = c*49 + r*7 + s, zero padded) for
  * BaseStem.conv1 (7x7/2, pad 3; modeling/backbone/resnet.py:347-366); maxpool: F.max_pool2d(3,2,1)
@@ -129,6 +144,10 @@ int mega_roi_align_forward_nhwc(const float* input, int channels, int height, in
 int mega_stem_im2col(const float* input, int n_img, int height, int width, int kpad, float* out, void* stream);
 int mega_maxpool3x3s2_nhwc(const float* input, int n_img, int height, int width, int channels, float* out,
                            void* stream);
+/* fp16 variants: im2col rows / pooled map as __half (kpad % 8 == 0, channels % 8 == 0) */
+int mega_stem_im2col_f16(const float* input, int n_img, int height, int width, int kpad, void* out, void* stream);
+int mega_maxpool3x3s2_nhwc_f16(const void* input, int n_img, int height, int width, int channels, void* out,
+                               void* stream);
 /* dst[i,:] = src[idx[i],:] (idx[i] < 0 -> zeros): replaces the per-frame torch.cat of the window /
  * memory deques (detector/generalized_rcnn_mega.py:213-216, roi_box_feature_extractors.py:674-688). */
 int mega_gather_rows(const float* src, long long src_ld, const int* idx, int n_rows, int row_len, float* dst,
@@ -151,6 +170,13 @@ int mega_transpose_2d(const float* input, int n_img, int rows, int cols, float* 
 int mega_relation_softmax(float* logits, int n_rows, int ldm, const float* boxes_q, const float* boxes_k,
                           const float* wg, const float* bg, const float* dim_mat, const int* m_valid_ptr, int m_host,
                           const int* n_valid_ptr, int n_valid_off, float scale, void* stream);
+
+/* same, but the probabilities are written as __half into probs_f16 [16][n_rows][ldm] (the A operand of the fp16
+ * P.V' GEMM); `logits` is used as scratch. */
+int mega_relation_softmax_f16(float* logits, void* probs_f16, int n_rows, int ldm, const float* boxes_q,
+                              const float* boxes_k, const float* wg, const float* bg, const float* dim_mat,
+                              const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off, float scale,
+                              void* stream);
 
 /* ------------------------------------------------------ box-head post-processing
  * softmax -> decode (weights wx..wh) -> clip -> per-class score threshold + NMS -> top max_det.

@@ -185,7 +185,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -255,6 +255,25 @@ __device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
   d |= static_cast<uint32_t>(n >> 3) << 17;
   d |= static_cast<uint32_t>(m >> 4) << 24;
   return d;
+}
+
+// ------------------------------------------------- programmatic dependent launch --
+// wait: blocks until every kernel this launch depends on has completed and flushed its writes (no-op for a
+// launch without the programmatic-serialization attribute); launch_dependents: the next kernel on the stream
+// may begin its prologue once every CTA of this grid has executed it (or exited).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ------------------------------------------------------------------- fp16 packing --
+__device__ __forceinline__ uint32_t f2_to_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 h2_to_f2(uint32_t h) {
+  float2 f;
+  asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}" : "=f"(f.x), "=f"(f.y) : "r"(h));
+  return f;
 }
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {

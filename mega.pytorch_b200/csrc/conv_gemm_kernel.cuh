@@ -1,0 +1,603 @@
+// Implicit-GEMM convolution / GEMM on the 5th-gen tensor cores (tcgen05, TF32 operands,
+// FP32 accumulate in TMEM), fed by TMA with the 128-byte shared-memory swizzle.
+//
+// One kernel serves every dense contraction of the MEGA hot path:
+//   * backbone / res5 / RPN-head convolutions (1x1, 3x3, 3x3 dilated) over NHWC maps
+//     (reference: mega_core/modeling/backbone/resnet.py:324-344, rpn/rpn.py:99-106),
+//     with FrozenBatchNorm scale/bias (layers/batch_norm.py:26-31), residual add and ReLU
+//     folded into the epilogue;
+//   * Linear layers (make_layers.py:80-92) as a 1x1 "convolution" over an H=1 image;
+//   * the per-head Q.K^T and P.V' products of the relation module
+//     (roi_box_feature_extractors.py:602-646) through the batch (grid.z) offsets.
+//
+// Tiling: the M tile is a th x tw rectangle of 128 output pixels, so the A operand of filter
+// tap (r,s) is the same rectangle shifted by (r,s)*dilation - pad: a plain 4-D tiled TMA load
+// with out-of-bounds zero fill supplies the padding. K is consumed in slabs of 32 floats
+// (= one 128 B swizzle row) per tap. Warp roles: warp 0 TMA producer, warp 1 MMA issuer,
+// warps 2-5 epilogue (TMEM -> registers -> global).
+#include "common.cuh"
+#pragma once
+#include "mega_b200.h"
+
+namespace mega {
+
+constexpr int kBM = 128;        // UMMA M (one CTA)
+// operand arithmetic of a launch
+constexpr int kModeTf32 = 0;    // fp32 operands in HBM, rounded to TF32 by the TMA load; K slab = 32 floats
+constexpr int kModeSplit3 = 1;  // "3xTF32": fp32 operands split hi/lo in shared memory
+constexpr int kModeF16 = 2;     // fp16 operands in HBM (10-bit mantissa like TF32, half the bytes, twice the
+                                // tensor-pipe rate); K slab = 64 halves
+// every mode stages K slabs of 128 bytes per row (one swizzle row) and issues 4 MMAs of 32 bytes of K each
+__host__ __device__ constexpr int mode_bk(int mode) { return mode == kModeF16 ? 64 : 32; }
+constexpr int kThreads = 192;   // 6 warps
+constexpr int kMaxCtas = 148;   // persistent grid: one CTA per SM
+
+struct ConvGemmParams {
+  int tiles_w, tiles_h, tile_w, tile_h;
+  int out_h, out_w, n_img;
+  int taps_r, taps_s, dil, pad;
+  int k_chunks;  // ceil(Cin / BK)
+  int cout;
+  const float* scale;
+  const float* bias;
+  int has_residual;
+  int relu;
+  int a_c_off, a_n_off, b_k_off, b_n_off;
+  int out_c_off, out_n_off;   // per-batch coordinate offsets of the output / residual tensors
+  int res_c_off, res_n_off;
+  int bias_z_off;
+  int box_w, box_h;           // per-warp store box: 32 output pixels = box_h x box_w
+  // stream-K decomposition
+  int m_tiles, n_tiles;      // per batch entry
+  int kb_per_tile;           // taps * k_chunks
+  long long total_units;     // batch * m_tiles * n_tiles * kb_per_tile
+  long long total_tiles;     // batch * m_tiles * n_tiles
+  int stream_k;              // 1: k-block granular split across CTAs, 0: whole tiles round-robin
+  float* part_ws;            // [grid][2][128][BN] partial accumulators
+  int* counters;             // [tiles], zero between launches
+};
+
+template <int BN, int STAGES, int MODE = kModeTf32>
+struct SmemLayout {
+  static constexpr bool SPLIT3 = MODE == kModeSplit3;
+  static constexpr int kABytes = kBM * 128;
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kHalf = kABytes + kBBytes;                 // 3xTF32: the low-part tiles follow at +kHalf
+  static constexpr int kStageBytes = SPLIT3 ? 2 * kHalf : kHalf;
+  static constexpr int kEpiOffset = STAGES * kStageBytes;       // 4 warps x (2 out + 2 residual) x 4 KB
+  static constexpr int kEpiBytes = 4 * 4 * 4096;
+  static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
+  static constexpr int kTotal = kBarOffset + (3 * STAGES + 4 + 8) * 8 + 32 + 1024;  // + align slack
+};
+
+struct TileCoord {
+  int img, h0, w0, n0, batch;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, long long t, int bn) {
+  TileCoord c;
+  const int m_tile = static_cast<int>(t % p.m_tiles);
+  const long long rest = t / p.m_tiles;
+  const int n_tile = static_cast<int>(rest % p.n_tiles);
+  c.batch = static_cast<int>(rest / p.n_tiles);
+  const int tw_i = m_tile % p.tiles_w;
+  const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
+  c.img = m_tile / (p.tiles_w * p.tiles_h);
+  c.h0 = th_i * p.tile_h;
+  c.w0 = tw_i * p.tile_w;
+  c.n0 = n_tile * bn;
+  return c;
+}
+
+__device__ __forceinline__ long long cta_first_unit(long long total, int grid, int c) {
+  return (total * c) / grid;
+}
+
+// the CTA whose unit range [first(c), first(c+1)) contains unit u
+__device__ __forceinline__ int unit_owner(long long total, int grid, long long u) {
+  int c = static_cast<int>((u * grid) / total);
+  if (c >= grid) c = grid - 1;
+  while (c + 1 < grid && cta_first_unit(total, grid, c + 1) <= u) ++c;
+  while (c > 0 && cta_first_unit(total, grid, c) > u) --c;
+  return c;
+}
+
+// the (tile, k-block range) items of one CTA, identical for the three warp roles
+struct WorkIter {
+  long long u, u_end, tile, tiles;
+  int KB, grid;
+  bool sk;
+  __device__ __forceinline__ WorkIter(const ConvGemmParams& p, int cta, int grid_)
+      : tile(cta), tiles(p.total_tiles), KB(p.kb_per_tile), grid(grid_), sk(p.stream_k != 0) {
+    u = cta_first_unit(p.total_units, grid_, cta);
+    u_end = cta_first_unit(p.total_units, grid_, cta + 1);
+  }
+  __device__ __forceinline__ bool next(long long& t, int& kb0, int& kb1) {
+    if (sk) {
+      if (u >= u_end) return false;
+      t = u / KB;
+      kb0 = static_cast<int>(u - t * KB);
+      kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
+      u += kb1 - kb0;
+      return true;
+    }
+    if (tile >= tiles) return false;
+    t = tile;
+    kb0 = 0;
+    kb1 = KB;
+    tile += grid;
+    return true;
+  }
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Persistent stream-K kernel. The work is the list of (tile, k-block) units, tiles ordered
+// (batch, n-tile, m-tile) with m fastest; CTA c owns the contiguous unit range
+// [c*U/G, (c+1)*U/G). A tile whose k-blocks straddle CTAs is finished by the last CTA to
+// arrive, which sums the partial accumulators (in CTA order -> deterministic) and runs the
+// epilogue. Accumulators are double-buffered in TMEM so the epilogue of item i overlaps the
+// MMAs of item i+1.
+// SPLIT3 ("3xTF32"): operands stay full fp32 in shared memory; four extra warps split every staged tile into
+// hi = fp32 truncated to TF32 and lo = x - hi (exact), and each k-step issues hi*hi + hi*lo + lo*hi into the same
+// accumulator: ~2^-19 relative error instead of 2^-11, for the strict-parity mode.
+// OUT16: output (and residual) tensors are fp16; the epilogue then works in chunks of 64 columns (= one 128-byte
+// swizzle row of halves) instead of 32.
+// Programmatic dependent launch: the prologue (barrier init, TMEM allocation, descriptor prefetch) runs before
+// griddepcontrol.wait, i.e. overlapped with the tail of the previous kernel on the stream; nothing before the wait
+// touches global memory.
+template <int BN, int STAGES, int MODE, bool OUT16>
+__global__ void __launch_bounds__(kThreads + (MODE == kModeSplit3 ? 128 : 0), 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                      const ConvGemmParams p) {
+  constexpr bool SPLIT3 = MODE == kModeSplit3;
+  constexpr int kBK = mode_bk(MODE);
+  constexpr int CW = OUT16 ? 64 : 32;   // epilogue chunk: columns per 128-byte output row segment
+  static_assert(!OUT16 || BN % 64 == 0, "fp16 output needs block_n % 64 == 0");
+  using L = SmemLayout<BN, STAGES, MODE>;
+  // accumulators: two ping-pong buffers (+ a master accumulator in 3xTF32 mode, see kSegLen)
+  constexpr uint32_t kAccBufs = SPLIT3 ? 3 : 2;
+  constexpr uint32_t kTmemCols = (kAccBufs * BN <= 64) ? 64 : (kAccBufs * BN <= 128) ? 128 : (kAccBufs * BN <= 256) ? 256 : 512;
+  constexpr uint32_t kAccStride = SPLIT3 ? BN : kTmemCols / 2;
+  // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
+  // accumulation chain (measured ~1e-3 relative after 3000 k-blocks). The strict mode therefore restarts the
+  // TMEM accumulator every kSegLen k-blocks and folds the segments into a master accumulator (also in TMEM)
+  // with round-to-nearest fp32 adds done by the epilogue warps.
+  constexpr int kSegLen = SPLIT3 ? 32 : 0x7fffffff;
+  extern __shared__ uint8_t smem_raw[];
+  // the 128B swizzle pattern is a function of the absolute smem address: align to 1024 B
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* split_bar = empty_bar + STAGES;       // [STAGES] (3xTF32 only)
+  uint64_t* tmem_full_bar = split_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint64_t* res_bar = tmem_empty_bar + 2;         // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+  int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int grid = gridDim.x;
+  const int cta = blockIdx.x;
+  const long long U = p.total_units;
+  const int KB = p.kb_per_tile;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmOut);
+    if (p.has_residual) prefetch_tmap(&tmRes);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 4);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);
+    }
+    for (int b = 0; b < 8; ++b) mbar_init(&res_bar[b], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();               // the previous kernel's results (and its reads of our outputs) are complete
+  griddep_launch_dependents();  // let the next kernel's prologue overlap this kernel
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      WorkIter it(p, cta, grid);
+      long long t;
+      int kb0, kb1;
+      while (it.next(t, kb0, kb1)) {
+        const TileCoord tc = decode_tile(p, t, BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int tap = kb / p.k_chunks;
+          const int kc = kb - tap * p.k_chunks;
+          const int r = tap / p.taps_s;
+          const int s = tap - r * p.taps_s;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * L::kStageBytes;
+          uint8_t* b_dst = a_dst + L::kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kHalf);   // bytes delivered by the two TMA loads
+          tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + tc.batch * p.a_c_off,
+                      tc.w0 + s * p.dil - p.pad, tc.h0 + r * p.dil - p.pad, tc.img + tc.batch * p.a_n_off);
+          tma_load_3d(b_dst, &tmB, &full_bar[stage], kc * kBK + tc.batch * p.b_k_off,
+                      tc.n0 + tc.batch * p.b_n_off, tap);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = MODE == kModeF16 ? umma_idesc<0>(kBM, BN) : umma_idesc<2>(kBM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      WorkIter it(p, cta, grid);
+      long long t;
+      int kb0, kb1;
+      int item = 0;
+      while (it.next(t, kb0, kb1)) {
+        for (int s0 = kb0, s1 = 0; s0 < kb1; s0 = s1, ++item) {
+          s1 = (kb1 - s0 > kSegLen) ? s0 + kSegLen : kb1;
+          const int buf = item & 1;
+          const uint32_t use = static_cast<uint32_t>(item >> 1);
+          mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * kAccStride;
+          for (int kb = s0; kb < s1; ++kb) {
+            mbar_wait(SPLIT3 ? &split_bar[stage] : &full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+            const uint32_t b_addr = a_addr + L::kABytes;
+            const uint64_t adesc = umma_desc_sw128(a_addr);
+            const uint64_t bdesc = umma_desc_sw128(b_addr);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              // advance 32 B (8 floats / 16 halves) inside the swizzle row: +2 in 16-byte units
+              if (MODE == kModeF16) {
+                umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+              } else {
+                umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+              }
+              if (SPLIT3) {
+                const uint64_t alo = umma_desc_sw128(a_addr + L::kHalf), blo = umma_desc_sw128(b_addr + L::kHalf);
+                umma_tf32(tmem_d, adesc + 2 * k, blo + 2 * k, idesc, 1u);
+                umma_tf32(tmem_d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&tmem_full_bar[buf]);
+        }
+      }
+    }
+  } else if (warp >= 6) {
+    // ===================== operand splitter (3xTF32 only, warps 6..9) =====================
+    if (SPLIT3) {
+      const int stid = threadIdx.x - kThreads;
+      int stage = 0;
+      uint32_t phase = 0;
+      WorkIter it(p, cta, grid);
+      long long t;
+      int kb0, kb1;
+      while (it.next(t, kb0, kb1)) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          uint8_t* base = smem + stage * L::kStageBytes;
+          constexpr int kVecs = L::kHalf / 16;
+#pragma unroll 4
+          for (int v = stid; v < kVecs; v += 128) {
+            const float4 x = *reinterpret_cast<const float4*>(base + v * 16);
+            float4 hi, lo;
+            hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
+            hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
+            hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
+            hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
+            *reinterpret_cast<float4*>(base + v * 16) = hi;
+            *reinterpret_cast<float4*>(base + L::kHalf + v * 16) = lo;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&split_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int epi_tid = (warp - 2) * 32 + lane;
+    uint8_t* epi_out = smem + L::kEpiOffset + (warp - 2) * 16384;   // 2 x 4 KB store staging
+    uint8_t* epi_res = epi_out + 8192;                              // 2 x 4 KB residual staging
+    uint64_t* rbar = res_bar + (warp - 2) * 2;
+    uint32_t rphase = 0;
+    WorkIter it(p, cta, grid);
+    long long t;
+    int kb0, kb1;
+    int item = 0;   // accumulator-segment counter (ping-pong bookkeeping shared with the MMA warp)
+    const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t master_row = tmem_base + 2 * kAccStride + lane_bits;
+    for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
+      const TileCoord tc = decode_tile(p, t, BN);
+      // ---- 3xTF32 only: fold every segment but the last into the master accumulator (RN fp32 adds)
+      bool has_master = false;
+      int s0 = kb0;
+      for (; SPLIT3 && s0 + kSegLen < kb1; s0 += kSegLen, ++item) {
+        const int fb = item & 1;
+        mbar_wait(&tmem_full_bar[fb], static_cast<uint32_t>(item >> 1) & 1);
+        tc_fence_after();
+        const uint32_t seg_row = tmem_base + fb * kAccStride + lane_bits;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t a[32];
+          __syncwarp();
+          tmem_ld_32x32(seg_row + c * 32, a);
+          tmem_ld_wait();
+          if (has_master) {
+            uint32_t m[32];
+            tmem_ld_32x32(master_row + c * 32, m);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = __float_as_uint(__fadd_rn(__uint_as_float(a[j]), __uint_as_float(m[j])));
+          }
+          tmem_st_32x32(master_row + c * 32, a);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[fb]);
+        has_master = true;
+      }
+      const int buf = item & 1;
+      const uint32_t use = static_cast<uint32_t>(item >> 1);
+      ++item;
+      mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + buf * kAccStride + lane_bits;
+      // accumulator chunk c (32 columns of this thread's row): last segment (+ master)
+      auto load_acc = [&](int c, uint32_t (&acc)[32]) {
+        __syncwarp();  // tcgen05.ld is .sync.aligned
+        tmem_ld_32x32(tmem_row + c * 32, acc);
+        tmem_ld_wait();
+        if (SPLIT3 && has_master) {
+          uint32_t m[32];
+          tmem_ld_32x32(master_row + c * 32, m);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__fadd_rn(__uint_as_float(acc[j]), __uint_as_float(m[j])));
+        }
+      };
+      const bool complete = (kb0 == 0 && kb1 == KB);
+      bool finalize = complete;
+      int c_first = cta, c_last = cta;
+      if (!complete) {
+        // ---- publish this CTA's partial accumulator, then find out whether it arrived last
+        float* my_ws = p.part_ws + ((static_cast<long long>(cta) * 2 + (tile_item == 0 ? 0 : 1)) * kBM + row) * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t acc[32];
+          load_acc(c, acc);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]),
+                                   __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
+            __stcg(reinterpret_cast<float4*>(my_ws + c * 32 + j), v);
+          }
+        }
+        __threadfence();
+        epi_bar_sync();
+        c_first = unit_owner(U, grid, t * KB);
+        c_last = unit_owner(U, grid, t * KB + KB - 1);
+        if (epi_tid == 0) {
+          const int parts = c_last - c_first + 1;
+          const int old = atomicAdd(&p.counters[t], 1);
+          const int last = (old == parts - 1);
+          if (last) p.counters[t] = 0;   // every part has arrived: leave the counter clean for the next launch
+          *epi_flag = last;
+        }
+        epi_bar_sync();
+        finalize = (*epi_flag != 0);
+        if (finalize) __threadfence();
+      }
+      if (finalize) {
+        // Output pixels of this warp: tile rows [32q, 32q+32) = a box_h x box_w rectangle. Results go
+        // registers -> 128B-swizzled smem -> one TMA store per 32-column chunk (full-line writes,
+        // image-edge and channel-edge clipping by the TMA unit); the residual arrives the same way.
+        const int r0 = q * 32;
+        const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
+        const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
+        const int out_n = tc.img + tc.batch * p.out_n_off;
+        const int res_n = tc.img + tc.batch * p.res_n_off;
+        const float* scale_p = p.scale ? p.scale + tc.batch * p.bias_z_off : nullptr;
+        const float* bias_p = p.bias ? p.bias + tc.batch * p.bias_z_off : nullptr;
+        const int nchunks = min(BN / CW, (p.cout - tc.n0 + CW - 1) / CW);
+        const uint32_t sw = static_cast<uint32_t>(lane & 7);
+        if (p.has_residual && lane == 0 && nchunks > 0) {
+          mbar_arrive_expect_tx(&rbar[0], 4096);
+          tma_load_4d(epi_res, &tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
+        }
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+          float acc[CW];
+#pragma unroll
+          for (int h = 0; h < CW / 32; ++h) {
+            uint32_t raw[32];
+            load_acc(c * (CW / 32) + h, raw);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[h * 32 + j] = __uint_as_float(raw[j]);
+          }
+          const int nb = tc.n0 + c * CW;
+          if (!complete) {
+            // deterministic reduction: parts summed in CTA order, own part from TMEM
+            float sum[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) sum[j] = 0.f;
+            for (int oc = c_first; oc <= c_last; ++oc) {
+              if (oc == cta) {
+#pragma unroll
+                for (int j = 0; j < CW; ++j) sum[j] += acc[j];
+              } else {
+                const int slot = (cta_first_unit(U, grid, oc) >= t * KB) ? 0 : 1;
+                const float* ws = p.part_ws + ((static_cast<long long>(oc) * 2 + slot) * kBM + row) * BN + c * CW;
+#pragma unroll
+                for (int j = 0; j < CW; j += 4) {
+                  const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + j));
+                  sum[j] += v.x; sum[j + 1] += v.y; sum[j + 2] += v.z; sum[j + 3] += v.w;
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < CW; ++j) acc[j] = sum[j];
+          }
+          const uint8_t* rsrc = nullptr;
+          if (p.has_residual) {
+            const int rb = c & 1;
+            if (c + 1 < nchunks && lane == 0) {   // prefetch the next residual chunk into the other buffer
+              mbar_arrive_expect_tx(&rbar[rb ^ 1], 4096);
+              tma_load_4d(epi_res + (rb ^ 1) * 4096, &tmRes, &rbar[rb ^ 1], nb + CW + tc.batch * p.res_c_off, st_w,
+                          st_h, res_n);
+            }
+            mbar_wait(&rbar[rb], (rphase >> rb) & 1u);
+            rphase ^= (1u << rb);
+            rsrc = epi_res + rb * 4096 + lane * 128;
+          }
+          // the out staging buffer (c & 1) was handed to a TMA store two chunks ago: wait until read
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* dst = epi_out + (c & 1) * 4096 + lane * 128;
+          // scale / bias (cout is padded to 4 by the host wrapper's buffers; tail columns are clipped by TMA)
+#pragma unroll
+          for (int j = 0; j < CW; j += 4) {
+            const int n = nb + j;
+            if (n < p.cout) {
+              if (scale_p) {
+                const float4 sc = ldg_f4(scale_p + n);
+                acc[j] *= sc.x; acc[j + 1] *= sc.y; acc[j + 2] *= sc.z; acc[j + 3] *= sc.w;
+              }
+              if (bias_p) {
+                const float4 bi = ldg_f4(bias_p + n);
+                acc[j] += bi.x; acc[j + 1] += bi.y; acc[j + 2] += bi.z; acc[j + 3] += bi.w;
+              }
+            }
+          }
+          if (OUT16) {
+            // 64 halves per row: 16-byte groups of 8 halves, swizzled like the TMA box
+#pragma unroll
+            for (int j = 0; j < CW; j += 8) {
+              const uint32_t chunk = (static_cast<uint32_t>(j >> 3) ^ sw) << 4;
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = acc[j + e];
+              if (rsrc) {
+                const uint4 rr = *reinterpret_cast<const uint4*>(rsrc + chunk);
+                const float2 r0 = h2_to_f2(rr.x), r1 = h2_to_f2(rr.y), r2 = h2_to_f2(rr.z), r3 = h2_to_f2(rr.w);
+                v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
+                v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+              }
+              uint4 o;
+              o.x = f2_to_h2(v[0], v[1]); o.y = f2_to_h2(v[2], v[3]);
+              o.z = f2_to_h2(v[4], v[5]); o.w = f2_to_h2(v[6], v[7]);
+              *reinterpret_cast<uint4*>(dst + chunk) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+              float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+              const uint32_t chunk = (static_cast<uint32_t>(j >> 2) ^ sw) << 4;
+              if (rsrc) {
+                const float4 rr = *reinterpret_cast<const float4*>(rsrc + chunk);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              if (p.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              *reinterpret_cast<float4*>(dst + chunk) = v;
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&tmOut, epi_out + (c & 1) * 4096, nb + tc.batch * p.out_c_off, st_w, st_h, out_n);
+            tma_store_commit();
+          }
+        }
+      }
+      // release the accumulator buffer to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    }
+    if (lane == 0) tma_store_wait<0>();   // global writes complete before the CTA retires
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ launch
+// pdl != 0: launched with programmatic stream serialization, i.e. this kernel's prologue may start while the
+// previous kernel on the stream drains (the kernel itself orders its memory accesses with griddepcontrol.wait).
+template <int BN, int STAGES, int MODE, bool OUT16>
+static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                      const CUtensorMap& tmRes, const ConvGemmParams& p, dim3 grid, cudaStream_t stream, int pdl) {
+  using L = SmemLayout<BN, STAGES, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    MEGA_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES, MODE, OUT16>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads + (MODE == kModeSplit3 ? 128 : 0), 1, 1);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  MEGA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN, STAGES, MODE, OUT16>, tmA, tmB, tmOut, tmRes, p));
+  return MEGA_OK;
+}
+
+// fp16-operand instantiations live in their own translation unit (conv_gemm_f16.cu)
+int launch_conv_gemm_f16(int block_n, int out_f16, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const CUtensorMap& tmOut, const CUtensorMap& tmRes, const ConvGemmParams& p, dim3 grid,
+                         cudaStream_t stream, int pdl);
+
+}  // namespace mega

@@ -6,6 +6,7 @@
 //     detector/generalized_rcnn_mega.py:213-216 and roi_box_feature_extractors.py:674-688);
 //   * NCHW <-> NHWC converters for the module-API boundary.
 // All are pure bandwidth kernels: 128-bit accesses, grid-stride, one pass.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "mega_b200.h"
 
@@ -116,6 +117,70 @@ __global__ void transpose_kernel(const float* __restrict__ in, int rows, int col
   }
 }
 
+// fp16 variants of the two backbone helpers (the fp16-operand engine keeps activations in fp16)
+__global__ void stem_im2col_f16_kernel(const float* __restrict__ in, int n_img, int height, int width, int ho, int wo,
+                                       int kpad, __half* __restrict__ out) {
+  const int groups = kpad / 8;
+  const long long total = static_cast<long long>(n_img) * ho * wo * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int grp = static_cast<int>(i % groups);
+    const long long pix = i / groups;
+    const int ow = static_cast<int>(pix % wo);
+    const int oh = static_cast<int>((pix / wo) % ho);
+    const int n = static_cast<int>(pix / (static_cast<long long>(wo) * ho));
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int k = grp * 8 + t;
+      float val = 0.f;
+      if (k < 147) {
+        const int c = k / 49, rs = k - c * 49, r = rs / 7, s = rs - r * 7;
+        const int ih = oh * 2 - 3 + r, iw = ow * 2 - 3 + s;
+        if (ih >= 0 && ih < height && iw >= 0 && iw < width)
+          val = __ldg(in + ((static_cast<long long>(n) * 3 + c) * height + ih) * width + iw);
+      }
+      v[t] = val;
+    }
+    *reinterpret_cast<uint4*>(out + pix * kpad + grp * 8) =
+        make_uint4(f2_to_h2(v[0], v[1]), f2_to_h2(v[2], v[3]), f2_to_h2(v[4], v[5]), f2_to_h2(v[6], v[7]));
+  }
+}
+
+__global__ void maxpool3x3s2_nhwc_f16_kernel(const __half* __restrict__ in, int n_img, int height, int width,
+                                             int channels, int ho, int wo, __half* __restrict__ out) {
+  const int cg = channels / 8;
+  const long long total = static_cast<long long>(n_img) * ho * wo * cg;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % cg);
+    const long long pix = i / cg;
+    const int ow = static_cast<int>(pix % wo);
+    const int oh = static_cast<int>((pix / wo) % ho);
+    const int n = static_cast<int>(pix / (static_cast<long long>(wo) * ho));
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+    __half2 m0 = ninf, m1 = ninf, m2 = ninf, m3 = ninf;
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= height) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= width) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+            in + ((static_cast<long long>(n) * height + ih) * width + iw) * channels + c8 * 8));
+        m0 = __hmax2(m0, *reinterpret_cast<const __half2*>(&v.x));
+        m1 = __hmax2(m1, *reinterpret_cast<const __half2*>(&v.y));
+        m2 = __hmax2(m2, *reinterpret_cast<const __half2*>(&v.z));
+        m3 = __hmax2(m3, *reinterpret_cast<const __half2*>(&v.w));
+      }
+    }
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&m0); o.y = *reinterpret_cast<uint32_t*>(&m1);
+    o.z = *reinterpret_cast<uint32_t*>(&m2); o.w = *reinterpret_cast<uint32_t*>(&m3);
+    *reinterpret_cast<uint4*>(out + pix * channels + c8 * 8) = o;
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long b = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -133,6 +198,30 @@ extern "C" int mega_stem_im2col(const float* input, int n_img, int height, int w
   const int ho = (height - 1) / 2 + 1, wo = (width - 1) / 2 + 1;
   const long long total = static_cast<long long>(n_img) * ho * wo * (kpad / 4);
   stem_im2col_kernel<<<grid_for(total, 256), 256, 0, stream>>>(input, n_img, height, width, ho, wo, kpad, out);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_stem_im2col_f16(const float* input, int n_img, int height, int width, int kpad, void* out,
+                                    void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(kpad >= 152 && (kpad & 7) == 0, "stem_im2col_f16: kpad must be a multiple of 8 >= 152");
+  const int ho = (height - 1) / 2 + 1, wo = (width - 1) / 2 + 1;
+  const long long total = static_cast<long long>(n_img) * ho * wo * (kpad / 8);
+  stem_im2col_f16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(input, n_img, height, width, ho, wo, kpad,
+                                                                   static_cast<__half*>(out));
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_maxpool3x3s2_nhwc_f16(const void* input, int n_img, int height, int width, int channels, void* out,
+                                          void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK((channels & 7) == 0, "maxpool_f16: channels must be a multiple of 8");
+  const int ho = (height - 1) / 2 + 1, wo = (width - 1) / 2 + 1;
+  const long long total = static_cast<long long>(n_img) * ho * wo * (channels / 8);
+  maxpool3x3s2_nhwc_f16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      static_cast<const __half*>(input), n_img, height, width, channels, ho, wo, static_cast<__half*>(out));
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }

@@ -9,6 +9,7 @@
 // registers and the soft-max is taken in place over the [G,N,M] logits produced by the
 // tcgen05 Q.K^T GEMM. One CTA per query row; two passes over its [16,M] slice (L2-resident):
 // logits + online (max, sum), then normalise.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "mega_b200.h"
 
@@ -20,6 +21,8 @@ constexpr int kRelThreads = 256;
 
 struct RelParams {
   float* s;                 // [G][N][ldm] logits in, probabilities out
+  __half* p16;              // optional: probabilities are written here as fp16 [G][N][ldm] (A operand of the fp16
+                            // P.V' GEMM) instead of in place
   long long head_stride;    // N * ldm
   int ldm;
   const float* boxes_q;     // [N,4] or NULL (no position term)
@@ -178,7 +181,9 @@ relation_softmax_kernel(const RelParams p) {
     for (int g = 0; g < kGroups; ++g) {
       float* sp = srow + g * p.head_stride + m;
       const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
-      *sp = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
+      const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
+      if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + g * p.head_stride + m] = __float2half_rn(pr);
+      else *sp = pr;
     }
   }
 }
@@ -186,8 +191,8 @@ relation_softmax_kernel(const RelParams p) {
 // No position term: one warp per (head, query row); the row (<= 1024 keys) stays in registers, so the
 // logits are read once and the probabilities written once.
 __global__ void __launch_bounds__(256)
-plain_softmax_kernel(float* __restrict__ s, int n_rows, int ldm, long long head_stride, const int* m_valid_ptr, int m_host,
-                     const int* n_valid_ptr, int n_valid_off, float scale) {
+plain_softmax_kernel(float* __restrict__ s, __half* __restrict__ p16, int n_rows, int ldm, long long head_stride,
+                     const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off, float scale) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (wid >= n_rows * kGroups) return;
@@ -220,7 +225,10 @@ plain_softmax_kernel(float* __restrict__ s, int n_rows, int ldm, long long head_
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int m = j * 32 + lane;
-    if (m < ldm) row[m] = v[j] * inv;
+    if (m < ldm) {
+      if (p16) p16[g * head_stride + static_cast<long long>(n) * ldm + m] = __float2half_rn(v[j] * inv);
+      else row[m] = v[j] * inv;
+    }
   }
 }
 
@@ -228,10 +236,10 @@ plain_softmax_kernel(float* __restrict__ s, int n_rows, int ldm, long long head_
 
 using namespace mega;
 
-extern "C" int mega_relation_softmax(float* logits, int n_rows, int ldm, const float* boxes_q, const float* boxes_k,
-                                     const float* wg, const float* bg, const float* dim_mat, const int* m_valid_ptr,
-                                     int m_host, const int* n_valid_ptr, int n_valid_off, float scale,
-                                     void* stream_v) {
+static int relation_softmax_impl(float* logits, void* probs_f16, int n_rows, int ldm, const float* boxes_q,
+                                 const float* boxes_k, const float* wg, const float* bg, const float* dim_mat,
+                                 const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off,
+                                 float scale, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   MEGA_ARG_CHECK(logits != nullptr && n_rows >= 0 && ldm > 0, "relation_softmax: bad arguments");
   MEGA_ARG_CHECK((boxes_q == nullptr) || (boxes_k && wg && bg && dim_mat),
@@ -240,6 +248,7 @@ extern "C" int mega_relation_softmax(float* logits, int n_rows, int ldm, const f
   if (n_rows == 0) return MEGA_OK;
   RelParams p;
   p.s = logits;
+  p.p16 = static_cast<__half*>(probs_f16);
   p.head_stride = static_cast<long long>(n_rows) * ldm;
   p.ldm = ldm;
   p.boxes_q = boxes_q;
@@ -255,7 +264,7 @@ extern "C" int mega_relation_softmax(float* logits, int n_rows, int ldm, const f
   if (boxes_q == nullptr && ldm <= 1024) {
     const long long warps = static_cast<long long>(n_rows) * kGroups;
     plain_softmax_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream>>>(
-        logits, n_rows, ldm, p.head_stride, m_valid_ptr, m_host, n_valid_ptr, n_valid_off, scale);
+        logits, p.p16, n_rows, ldm, p.head_stride, m_valid_ptr, m_host, n_valid_ptr, n_valid_off, scale);
   } else if (ldm <= 1024) {
     const int smem = kGroups * ldm * static_cast<int>(sizeof(float));
     static bool configured = false;
@@ -270,4 +279,21 @@ extern "C" int mega_relation_softmax(float* logits, int n_rows, int ldm, const f
   }
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
+}
+
+extern "C" int mega_relation_softmax(float* logits, int n_rows, int ldm, const float* boxes_q, const float* boxes_k,
+                                     const float* wg, const float* bg, const float* dim_mat, const int* m_valid_ptr,
+                                     int m_host, const int* n_valid_ptr, int n_valid_off, float scale,
+                                     void* stream_v) {
+  return relation_softmax_impl(logits, nullptr, n_rows, ldm, boxes_q, boxes_k, wg, bg, dim_mat, m_valid_ptr, m_host,
+                               n_valid_ptr, n_valid_off, scale, stream_v);
+}
+
+extern "C" int mega_relation_softmax_f16(float* logits, void* probs_f16, int n_rows, int ldm, const float* boxes_q,
+                                         const float* boxes_k, const float* wg, const float* bg, const float* dim_mat,
+                                         const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off,
+                                         float scale, void* stream_v) {
+  MEGA_ARG_CHECK(probs_f16 != nullptr, "relation_softmax_f16: probs_f16 is NULL");
+  return relation_softmax_impl(logits, probs_f16, n_rows, ldm, boxes_q, boxes_k, wg, bg, dim_mat, m_valid_ptr, m_host,
+                               n_valid_ptr, n_valid_off, scale, stream_v);
 }

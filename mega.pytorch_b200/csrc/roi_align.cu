@@ -9,6 +9,7 @@
 //     the l_fcs[0] GEMM as its K-major A operand without a transpose.
 // Arithmetic is written with explicit round-to-nearest ops (no FMA contraction) in the
 // reference's association order, so results are bit-identical to the C oracle.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "mega_b200.h"
 
@@ -111,12 +112,37 @@ __global__ void roi_align_nchw_kernel(const float* __restrict__ in, int channels
   }
 }
 
-// grid = (ph*pw, K); block = 256 threads, each thread owns float4 channel groups.
+// ---- 16-byte channel vectors of the NHWC kernels: 4 floats or 8 halves; arithmetic always in fp32
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&v)[4]) {
+    return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+  }
+};
+template <> struct Vec16<__half> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void unpack(const uint4& r, float (&v)[8]) {
+    const float2 a = h2_to_f2(r.x), b = h2_to_f2(r.y), c = h2_to_f2(r.z), d = h2_to_f2(r.w);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+  static __device__ __forceinline__ uint4 pack(const float (&v)[8]) {
+    return make_uint4(f2_to_h2(v[0], v[1]), f2_to_h2(v[2], v[3]), f2_to_h2(v[4], v[5]), f2_to_h2(v[6], v[7]));
+  }
+};
+__device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// grid = (ph*pw, K); block = 256 threads, each thread owns 16-byte channel groups.
+template <typename T>
 __global__ void __launch_bounds__(256)
-roi_align_nhwc_kernel(const float* __restrict__ in, int channels, int height, int width, long long in_img_stride,
+roi_align_nhwc_kernel(const T* __restrict__ in, int channels, int height, int width, long long in_img_stride,
                       const float* __restrict__ rois, int roi_ld, int roi_box_off, const int* __restrict__ roi_batch,
-                      float scale, int ph, int pw, int sampling_ratio, float* __restrict__ out,
+                      float scale, int ph, int pw, int sampling_ratio, T* __restrict__ out,
                       long long out_roi_stride) {
+  constexpr int V = Vec16<T>::N;
   const int bin = blockIdx.x;
   const int n = blockIdx.y;
   const int phi = bin / pw, pwi = bin - phi * pw;
@@ -130,46 +156,50 @@ roi_align_nhwc_kernel(const float* __restrict__ in, int channels, int height, in
   }
   roi5[1] = rb[0]; roi5[2] = rb[1]; roi5[3] = rb[2]; roi5[4] = rb[3];
   const RoiGeom g = roi_geom(roi5, scale, ph, pw, sampling_ratio);
-  const float* img = in + static_cast<long long>(g.batch) * in_img_stride;
+  const T* img = in + static_cast<long long>(g.batch) * in_img_stride;
   const float count = static_cast<float>(g.grid_h * g.grid_w);
-  float* orow = out + static_cast<long long>(n) * out_roi_stride + static_cast<long long>(bin) * channels;
-  for (int c = threadIdx.x * 4; c < channels; c += blockDim.x * 4) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  T* orow = out + static_cast<long long>(n) * out_roi_stride + static_cast<long long>(bin) * channels;
+  for (int c = threadIdx.x * V; c < channels; c += blockDim.x * V) {
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
     for (int iy = 0; iy < g.grid_h; ++iy) {
       const float y = sample_coord(g.start_h, phi, g.bin_h, iy, g.grid_h);
       for (int ix = 0; ix < g.grid_w; ++ix) {
         const float x = sample_coord(g.start_w, pwi, g.bin_w, ix, g.grid_w);
         const Bilinear b = bilinear_setup(height, width, y, x);
         if (b.empty) continue;  // adds exactly 0 in the reference
-        const float4 v1 = ldg_f4(img + (static_cast<long long>(b.y_low) * width + b.x_low) * channels + c);
-        const float4 v2 = ldg_f4(img + (static_cast<long long>(b.y_low) * width + b.x_high) * channels + c);
-        const float4 v3 = ldg_f4(img + (static_cast<long long>(b.y_high) * width + b.x_low) * channels + c);
-        const float4 v4 = ldg_f4(img + (static_cast<long long>(b.y_high) * width + b.x_high) * channels + c);
-        acc.x = __fadd_rn(acc.x, blend(b, v1.x, v2.x, v3.x, v4.x));
-        acc.y = __fadd_rn(acc.y, blend(b, v1.y, v2.y, v3.y, v4.y));
-        acc.z = __fadd_rn(acc.z, blend(b, v1.z, v2.z, v3.z, v4.z));
-        acc.w = __fadd_rn(acc.w, blend(b, v1.w, v2.w, v3.w, v4.w));
+        float v1[V], v2[V], v3[V], v4[V];
+        Vec16<T>::unpack(ldg_u4(img + (static_cast<long long>(b.y_low) * width + b.x_low) * channels + c), v1);
+        Vec16<T>::unpack(ldg_u4(img + (static_cast<long long>(b.y_low) * width + b.x_high) * channels + c), v2);
+        Vec16<T>::unpack(ldg_u4(img + (static_cast<long long>(b.y_high) * width + b.x_low) * channels + c), v3);
+        Vec16<T>::unpack(ldg_u4(img + (static_cast<long long>(b.y_high) * width + b.x_high) * channels + c), v4);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = __fadd_rn(acc[e], blend(b, v1[e], v2[e], v3[e], v4[e]));
       }
     }
-    acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
-    acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
-    *reinterpret_cast<float4*>(orow + c) = acc;
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = __fdiv_rn(acc[e], count);
+    *reinterpret_cast<uint4*>(orow + c) = Vec16<T>::pack(acc);
   }
 }
 
-// Same arithmetic, less L2 traffic: one CTA per (roi, 64-channel slice) first copies the cells the roi can touch
-// (rows r0..r1 x cols c0..c1 of the map, 256 B per cell) into shared memory, then all 49 bins sample from there;
-// neighbouring samples share corners, so each cell is fetched once per slice instead of up to ~8 times. ROIs whose
-// footprint exceeds the shared-memory budget (whole-image boxes) read global memory directly.
-constexpr int kRoiSlice = 64;            // channels per CTA
+// Same arithmetic, less L2 traffic: one CTA per (roi, 256-byte channel slice) first copies the cells the roi can
+// touch (rows r0..r1 x cols c0..c1 of the map, 256 B per cell) into shared memory, then all 49 bins sample from
+// there; neighbouring samples share corners, so each cell is fetched once per slice instead of up to ~8 times. ROIs
+// whose footprint exceeds the shared-memory budget (whole-image boxes) read global memory directly.
+constexpr int kRoiSliceBytes = 256;      // channel bytes per CTA: 64 floats / 128 halves
 constexpr int kRoiMaxCells = 192;        // 192 cells x 256 B = 48 KB per CTA (4 CTAs per SM)
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-roi_align_nhwc_cached_kernel(const float* __restrict__ in, int channels, int height, int width, long long in_img_stride,
+roi_align_nhwc_cached_kernel(const T* __restrict__ in, int channels, int height, int width, long long in_img_stride,
                              const float* __restrict__ rois, int roi_ld, int roi_box_off,
                              const int* __restrict__ roi_batch, float scale, int ph, int pw, int sampling_ratio,
-                             float* __restrict__ out, long long out_roi_stride) {
-  extern __shared__ float4 cell_s[];   // [cells][16] float4
+                             T* __restrict__ out, long long out_roi_stride) {
+  constexpr int V = Vec16<T>::N;
+  constexpr int kSlice = kRoiSliceBytes / static_cast<int>(sizeof(T));
+  extern __shared__ uint4 cell_s[];   // [cells][16] 16-byte vectors
   const int slice = blockIdx.x;
   const int n = blockIdx.y;
   float roi5[5];
@@ -182,7 +212,7 @@ roi_align_nhwc_cached_kernel(const float* __restrict__ in, int channels, int hei
   }
   roi5[1] = rb[0]; roi5[2] = rb[1]; roi5[3] = rb[2]; roi5[4] = rb[3];
   const RoiGeom g = roi_geom(roi5, scale, ph, pw, sampling_ratio);
-  const float* img = in + static_cast<long long>(g.batch) * in_img_stride + slice * kRoiSlice;
+  const T* img = in + static_cast<long long>(g.batch) * in_img_stride + slice * kSlice;
   // footprint of every sample this roi can take (after the reference's clamping of y, x to the map)
   const float end_h = __fadd_rn(g.start_h, __fmul_rn(g.bin_h, static_cast<float>(ph)));
   const float end_w = __fadd_rn(g.start_w, __fmul_rn(g.bin_w, static_cast<float>(pw)));
@@ -196,45 +226,81 @@ roi_align_nhwc_cached_kernel(const float* __restrict__ in, int channels, int hei
     for (int i = threadIdx.x; i < rh * rw * 16; i += blockDim.x) {
       const int cell = i >> 4, q = i & 15;
       const int rr = cell / rw, cc = cell - rr * rw;
-      cell_s[i] = ldg_f4(img + (static_cast<long long>(r0 + rr) * width + (c0 + cc)) * channels + q * 4);
+      cell_s[i] = ldg_u4(img + (static_cast<long long>(r0 + rr) * width + (c0 + cc)) * channels + q * V);
     }
   }
   __syncthreads();
   const int q = threadIdx.x & 15;
   const float count = static_cast<float>(g.grid_h * g.grid_w);
-  float* obase = out + static_cast<long long>(n) * out_roi_stride + slice * kRoiSlice + q * 4;
+  T* obase = out + static_cast<long long>(n) * out_roi_stride + slice * kSlice + q * V;
   for (int bin = threadIdx.x >> 4; bin < ph * pw; bin += blockDim.x >> 4) {
     const int phi = bin / pw, pwi = bin - phi * pw;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = 0.f;
     for (int iy = 0; iy < g.grid_h; ++iy) {
       const float y = sample_coord(g.start_h, phi, g.bin_h, iy, g.grid_h);
       for (int ix = 0; ix < g.grid_w; ++ix) {
         const float x = sample_coord(g.start_w, pwi, g.bin_w, ix, g.grid_w);
         const Bilinear b = bilinear_setup(height, width, y, x);
         if (b.empty) continue;
-        float4 v1, v2, v3, v4;
+        uint4 r1v, r2v, r3v, r4v;
         const bool inside = cached && b.y_low >= r0 && b.y_high <= r1 && b.x_low >= c0 && b.x_high <= c1;
         if (inside) {
-          v1 = cell_s[((b.y_low - r0) * rw + (b.x_low - c0)) * 16 + q];
-          v2 = cell_s[((b.y_low - r0) * rw + (b.x_high - c0)) * 16 + q];
-          v3 = cell_s[((b.y_high - r0) * rw + (b.x_low - c0)) * 16 + q];
-          v4 = cell_s[((b.y_high - r0) * rw + (b.x_high - c0)) * 16 + q];
+          r1v = cell_s[((b.y_low - r0) * rw + (b.x_low - c0)) * 16 + q];
+          r2v = cell_s[((b.y_low - r0) * rw + (b.x_high - c0)) * 16 + q];
+          r3v = cell_s[((b.y_high - r0) * rw + (b.x_low - c0)) * 16 + q];
+          r4v = cell_s[((b.y_high - r0) * rw + (b.x_high - c0)) * 16 + q];
         } else {
-          v1 = ldg_f4(img + (static_cast<long long>(b.y_low) * width + b.x_low) * channels + q * 4);
-          v2 = ldg_f4(img + (static_cast<long long>(b.y_low) * width + b.x_high) * channels + q * 4);
-          v3 = ldg_f4(img + (static_cast<long long>(b.y_high) * width + b.x_low) * channels + q * 4);
-          v4 = ldg_f4(img + (static_cast<long long>(b.y_high) * width + b.x_high) * channels + q * 4);
+          r1v = ldg_u4(img + (static_cast<long long>(b.y_low) * width + b.x_low) * channels + q * V);
+          r2v = ldg_u4(img + (static_cast<long long>(b.y_low) * width + b.x_high) * channels + q * V);
+          r3v = ldg_u4(img + (static_cast<long long>(b.y_high) * width + b.x_low) * channels + q * V);
+          r4v = ldg_u4(img + (static_cast<long long>(b.y_high) * width + b.x_high) * channels + q * V);
         }
-        acc.x = __fadd_rn(acc.x, blend(b, v1.x, v2.x, v3.x, v4.x));
-        acc.y = __fadd_rn(acc.y, blend(b, v1.y, v2.y, v3.y, v4.y));
-        acc.z = __fadd_rn(acc.z, blend(b, v1.z, v2.z, v3.z, v4.z));
-        acc.w = __fadd_rn(acc.w, blend(b, v1.w, v2.w, v3.w, v4.w));
+        float v1[V], v2[V], v3[V], v4[V];
+        Vec16<T>::unpack(r1v, v1); Vec16<T>::unpack(r2v, v2); Vec16<T>::unpack(r3v, v3); Vec16<T>::unpack(r4v, v4);
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc[e] = __fadd_rn(acc[e], blend(b, v1[e], v2[e], v3[e], v4[e]));
       }
     }
-    acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
-    acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
-    *reinterpret_cast<float4*>(obase + static_cast<long long>(bin) * channels) = acc;
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[e] = __fdiv_rn(acc[e], count);
+    *reinterpret_cast<uint4*>(obase + static_cast<long long>(bin) * channels) = Vec16<T>::pack(acc);
   }
+}
+
+template <typename T>
+static int roi_align_nhwc_launch(const T* input, int channels, int height, int width, long long in_img_stride,
+                                 const float* rois, int roi_ld, int roi_box_off, const int* roi_batch, int num_rois,
+                                 float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio, T* output,
+                                 long long out_roi_stride, cudaStream_t stream) {
+  constexpr int V = Vec16<T>::N;
+  constexpr int kSlice = kRoiSliceBytes / static_cast<int>(sizeof(T));
+  MEGA_ARG_CHECK((channels % V) == 0, "roi_align_nhwc: channels must be a multiple of 16 bytes");
+  MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(input) & 15) == 0 && (reinterpret_cast<uintptr_t>(output) & 15) == 0 &&
+                     (out_roi_stride % V) == 0 && (in_img_stride % V) == 0,
+                 "roi_align_nhwc: 16-byte alignment required");
+  if (num_rois == 0) return MEGA_OK;
+  if ((channels % kSlice) == 0) {
+    static bool configured = false;
+    if (!configured) {
+      MEGA_CUDA_CHECK(cudaFuncSetAttribute(roi_align_nhwc_cached_kernel<T>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kRoiMaxCells * 256));
+      configured = true;
+    }
+    dim3 cgrid(channels / kSlice, num_rois);
+    roi_align_nhwc_cached_kernel<T><<<cgrid, 256, kRoiMaxCells * 256, stream>>>(
+        input, channels, height, width, in_img_stride, rois, roi_ld, roi_box_off, roi_batch, spatial_scale, pooled_h,
+        pooled_w, sampling_ratio, output, out_roi_stride);
+    MEGA_CUDA_CHECK(cudaGetLastError());
+    return MEGA_OK;
+  }
+  dim3 grid(pooled_h * pooled_w, num_rois);
+  roi_align_nhwc_kernel<T><<<grid, 256, 0, stream>>>(input, channels, height, width, in_img_stride, rois, roi_ld,
+                                                     roi_box_off, roi_batch, spatial_scale, pooled_h, pooled_w,
+                                                     sampling_ratio, output, out_roi_stride);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
 }
 
 }  // namespace mega
@@ -263,30 +329,18 @@ extern "C" int mega_roi_align_forward_nhwc(const float* input, int channels, int
                                            const int* roi_batch, int num_rois, float spatial_scale, int pooled_h,
                                            int pooled_w, int sampling_ratio, float* output, long long out_roi_stride,
                                            void* stream_v) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  MEGA_ARG_CHECK((channels & 3) == 0, "roi_align_nhwc: channels must be a multiple of 4");
-  MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(input) & 15) == 0 && (reinterpret_cast<uintptr_t>(output) & 15) == 0 &&
-                     (out_roi_stride & 3) == 0,
-                 "roi_align_nhwc: 16-byte alignment required");
-  if (num_rois == 0) return MEGA_OK;
-  if ((channels % kRoiSlice) == 0) {
-    static bool configured = false;
-    if (!configured) {
-      MEGA_CUDA_CHECK(cudaFuncSetAttribute(roi_align_nhwc_cached_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kRoiMaxCells * 256));
-      configured = true;
-    }
-    dim3 cgrid(channels / kRoiSlice, num_rois);
-    roi_align_nhwc_cached_kernel<<<cgrid, 256, kRoiMaxCells * 256, stream>>>(
-        input, channels, height, width, in_img_stride, rois, roi_ld, roi_box_off, roi_batch, spatial_scale, pooled_h,
-        pooled_w, sampling_ratio, output, out_roi_stride);
-    MEGA_CUDA_CHECK(cudaGetLastError());
-    return MEGA_OK;
-  }
-  dim3 grid(pooled_h * pooled_w, num_rois);
-  roi_align_nhwc_kernel<<<grid, 256, 0, stream>>>(input, channels, height, width, in_img_stride, rois, roi_ld,
-                                                  roi_box_off, roi_batch, spatial_scale, pooled_h, pooled_w,
-                                                  sampling_ratio, output, out_roi_stride);
-  MEGA_CUDA_CHECK(cudaGetLastError());
-  return MEGA_OK;
+  return roi_align_nhwc_launch<float>(input, channels, height, width, in_img_stride, rois, roi_ld, roi_box_off,
+                                      roi_batch, num_rois, spatial_scale, pooled_h, pooled_w, sampling_ratio, output,
+                                      out_roi_stride, static_cast<cudaStream_t>(stream_v));
+}
+
+extern "C" int mega_roi_align_forward_nhwc_f16(const void* input, int channels, int height, int width,
+                                               long long in_img_stride, const float* rois, int roi_ld, int roi_box_off,
+                                               const int* roi_batch, int num_rois, float spatial_scale, int pooled_h,
+                                               int pooled_w, int sampling_ratio, void* output,
+                                               long long out_roi_stride, void* stream_v) {
+  return roi_align_nhwc_launch<__half>(static_cast<const __half*>(input), channels, height, width, in_img_stride, rois,
+                                       roi_ld, roi_box_off, roi_batch, num_rois, spatial_scale, pooled_h, pooled_w,
+                                       sampling_ratio, static_cast<__half*>(output), out_roi_stride,
+                                       static_cast<cudaStream_t>(stream_v));
 }

@@ -51,12 +51,16 @@ class ConvGemmDesc(ctypes.Structure):
         ("stream_k", c_int),
         ("workspace", ctypes.c_void_p),
         ("workspace_bytes", c_ll),
+        ("out_f16", c_int),
+        ("pdl", c_int),
     ]
 
 
 lib.mega_last_error.restype = ctypes.c_char_p
 lib.mega_abi_version.restype = c_int
 lib.mega_device_ok.restype = c_int
+lib.mega_conv_gemm.argtypes = [ctypes.POINTER(ConvGemmDesc), ctypes.c_void_p]
+lib.mega_conv_gemm.restype = c_int
 lib.mega_conv_gemm_tf32.argtypes = [ctypes.POINTER(ConvGemmDesc), ctypes.c_void_p]
 lib.mega_conv_gemm_tf32.restype = c_int
 lib.mega_conv_gemm_workspace_bytes.restype = c_ll
@@ -107,6 +111,14 @@ lib.mega_roi_align_forward_nchw.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _f, _i
 lib.mega_roi_align_forward_nchw.restype = _i
 lib.mega_roi_align_forward_nhwc.argtypes = [_vp, _i, _i, _i, _ll, _vp, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _ll, _vp]
 lib.mega_roi_align_forward_nhwc.restype = _i
+lib.mega_roi_align_forward_nhwc_f16.argtypes = [_vp, _i, _i, _i, _ll, _vp, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _ll, _vp]
+lib.mega_roi_align_forward_nhwc_f16.restype = _i
+lib.mega_stem_im2col_f16.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
+lib.mega_stem_im2col_f16.restype = _i
+lib.mega_maxpool3x3s2_nhwc_f16.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
+lib.mega_maxpool3x3s2_nhwc_f16.restype = _i
+lib.mega_relation_softmax_f16.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp]
+lib.mega_relation_softmax_f16.restype = _i
 lib.mega_stem_im2col.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
 lib.mega_stem_im2col.restype = _i
 lib.mega_maxpool3x3s2_nhwc.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
@@ -136,10 +148,11 @@ lib.mega_deform_psroi_pooling_forward.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i,
 lib.mega_deform_psroi_pooling_forward.restype = _i
 
 EXPORTS = [
-    "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm_tf32", "mega_conv_gemm_workspace_bytes", "mega_set_tf32_rounding",
+    "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm", "mega_conv_gemm_tf32", "mega_conv_gemm_workspace_bytes", "mega_set_tf32_rounding",
     "mega_nms_workspace_bytes", "mega_nms", "mega_rpn_select_workspace_bytes", "mega_rpn_select",
     "mega_roi_align_forward_nchw", "mega_roi_align_forward_nhwc", "mega_stem_im2col", "mega_maxpool3x3s2_nhwc",
     "mega_gather_rows", "mega_copy_rows", "mega_transpose_2d", "mega_relation_softmax", "mega_box_postprocess_workspace_bytes",
     "mega_box_postprocess", "mega_sigmoid_focalloss_forward", "mega_sigmoid_focalloss_backward",
     "mega_deform_im2col", "mega_deform_psroi_pooling_forward",
+    "mega_roi_align_forward_nhwc_f16", "mega_stem_im2col_f16", "mega_maxpool3x3s2_nhwc_f16", "mega_relation_softmax_f16",
 ]

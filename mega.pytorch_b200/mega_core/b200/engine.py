@@ -45,6 +45,7 @@ class EngineConfig:
     global_size = 10
     global_res_stage = 1
     stage = 3
+    advanced_stage = 0           # RDN: MODEL.VID.ROI_BOX_HEAD.ATTENTION.ADVANCED_STAGE
     groups = 16
     pooler_resolution = 7
     pooler_scale = 1.0 / 16
@@ -58,7 +59,12 @@ class EngineConfig:
     aspect_ratios = (0.5, 1.0, 2.0)
     anchor_stride = 16
     num_classes = 31
-    precision = "tf32"           # "tf32" | "fp32x3" (3xTF32 split: near-fp32 contractions, strict parity mode)
+    # arithmetic of the dense contractions (all accumulate in fp32 on the tensor cores):
+    #   "f16"    fp16 operands: activations / weights of the GEMM chain are STORED in fp16 (10-bit mantissa, the
+    #            same operand rounding as TF32; half the bytes, twice the tensor-pipe rate) -- the throughput mode
+    #   "tf32"   fp32 tensors, operands rounded to TF32 by the TMA load
+    #   "fp32x3" fp32 tensors, 3xTF32 split: near-fp32 contractions, the strict-parity mode
+    precision = "tf32"
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -69,6 +75,11 @@ class EngineConfig:
     @property
     def advanced_num(self):
         return int(self.ref_post_nms_top_n * self.ratio)
+
+    @property
+    def act_dtype(self):
+        """storage type of the activations / weights that feed tensor-core contractions"""
+        return torch.float16 if self.precision == "f16" else torch.float32
 
 
 def cell_anchors(stride, sizes, ratios):
@@ -104,10 +115,10 @@ def fold_bn(sd, p, dev):
     return scale.contiguous().to(dev), bias.contiguous().to(dev)
 
 
-def pack_conv(w, dev):
+def pack_conv(w, dev, dtype=torch.float32):
     """[Cout,Cin,kh,kw] -> [kh*kw, Cout, Cin] (K-major rows per tap)"""
     co, ci, kh, kw = w.shape
-    return w.float().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous().to(dev)
+    return w.float().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous().to(dev).to(dtype)
 
 
 class _Block:
@@ -117,8 +128,8 @@ class _Block:
 class ResNetStages:
     """a sequence of bottleneck stages over NHWC activations (resnet.py:239-344)."""
 
-    def __init__(self, sd, prefix, layer_ids, dev, dilation=1, first_stride_of=None):
-        self.dev = dev
+    def __init__(self, sd, prefix, layer_ids, dev, dilation=1, first_stride_of=None, dtype=torch.float32):
+        self.dev, self.dtype = dev, dtype
         self.stages = []
         for li in layer_ids:
             blocks = []
@@ -126,15 +137,15 @@ class ResNetStages:
             while (prefix + "layer%d.%d.conv1.weight" % (li, b)) in sd:
                 p = prefix + "layer%d.%d." % (li, b)
                 blk = _Block()
-                blk.w1 = pack_conv(sd[p + "conv1.weight"], dev)
+                blk.w1 = pack_conv(sd[p + "conv1.weight"], dev, dtype)
                 blk.s1, blk.b1 = fold_bn(sd, p + "bn1.", dev)
-                blk.w2 = pack_conv(sd[p + "conv2.weight"], dev)
+                blk.w2 = pack_conv(sd[p + "conv2.weight"], dev, dtype)
                 blk.s2, blk.b2 = fold_bn(sd, p + "bn2.", dev)
-                blk.w3 = pack_conv(sd[p + "conv3.weight"], dev)
+                blk.w3 = pack_conv(sd[p + "conv3.weight"], dev, dtype)
                 blk.s3, blk.b3 = fold_bn(sd, p + "bn3.", dev)
                 blk.wd = None
                 if (p + "downsample.0.weight") in sd:
-                    blk.wd = pack_conv(sd[p + "downsample.0.weight"], dev)
+                    blk.wd = pack_conv(sd[p + "downsample.0.weight"], dev, dtype)
                     blk.sd, blk.bd = fold_bn(sd, p + "downsample.1.", dev)
                 stride = first_stride_of(li) if (b == 0 and first_stride_of) else 1
                 blk.stride = 1 if dilation > 1 else stride
@@ -150,7 +161,7 @@ class ResNetStages:
         key = (tag, tuple(shape))
         t = self._bufs.get(key)
         if t is None:
-            t = torch.zeros(*shape, device=self.dev)
+            t = torch.zeros(*shape, device=self.dev, dtype=self.dtype)
             self._bufs[key] = t
         return t
 
@@ -186,14 +197,15 @@ class ResNetStages:
 class Backbone:
     """ResNet C4 body: stem + res2..res4 (modeling/backbone/resnet.py:145-152, :347-366)."""
 
-    def __init__(self, sd, dev, prefix="backbone.body."):
-        self.dev = dev
+    def __init__(self, sd, dev, prefix="backbone.body.", dtype=torch.float32):
+        self.dev, self.dtype = dev, dtype
         w = sd[prefix + "stem.conv1.weight"].float().reshape(64, 147)
         wp = torch.zeros(1, 64, 160)
         wp[0, :, :147] = w
-        self.stem_w = wp.contiguous().to(dev)
+        self.stem_w = wp.contiguous().to(dev).to(dtype)
         self.stem_s, self.stem_b = fold_bn(sd, prefix + "stem.bn1.", dev)
-        self.stages = ResNetStages(sd, prefix, (1, 2, 3), dev, first_stride_of=lambda li: 2 if li > 1 else 1)
+        self.stages = ResNetStages(sd, prefix, (1, 2, 3), dev, first_stride_of=lambda li: 2 if li > 1 else 1,
+                                   dtype=dtype)
         self._bufs = {}
         self.out_channels = self.stages.stages[-1][-1].cout
 
@@ -201,7 +213,7 @@ class Backbone:
         key = (tag, tuple(shape))
         t = self._bufs.get(key)
         if t is None:
-            t = torch.zeros(*shape, device=self.dev)
+            t = torch.zeros(*shape, device=self.dev, dtype=self.dtype)
             self._bufs[key] = t
         return t
 
@@ -223,14 +235,17 @@ class Backbone:
 class _Att:
     """packed weights of one attention_module_multi_head instance"""
 
-    def __init__(self, sd, pfx, i, dev, with_g):
-        self.wq = sd[pfx + "Wqs.%d.weight" % i].float().contiguous().to(dev)
+    def __init__(self, sd, pfx, i, dev, with_g, dtype=torch.float32):
+        self.wq = sd[pfx + "Wqs.%d.weight" % i].float().contiguous().to(dev).to(dtype)
         # (q + u).k == q.k + u.k : the `u` term (extractors :619-622) becomes part of the query bias
-        self.bq = (sd[pfx + "Wqs.%d.bias" % i].float() + sd[pfx + "us.%d" % i].float().reshape(-1)).contiguous().to(dev)
-        self.wk = sd[pfx + "Wks.%d.weight" % i].float().contiguous().to(dev)
+        bq = sd[pfx + "Wqs.%d.bias" % i].float()
+        if (pfx + "us.%d" % i) in sd:        # MEGA only; the base / RDN module (extractors :178-238) has no `u`
+            bq = bq + sd[pfx + "us.%d" % i].float().reshape(-1)
+        self.bq = bq.contiguous().to(dev)
+        self.wk = sd[pfx + "Wks.%d.weight" % i].float().contiguous().to(dev).to(dtype)
         self.bk = sd[pfx + "Wks.%d.bias" % i].float().contiguous().to(dev)
         # grouped 1x1 conv Wv (16 groups of 1024->64, extractors :642) == one 1024x1024 matrix
-        self.wv = sd[pfx + "Wvs.%d.weight" % i].float().reshape(1024, 1024).contiguous().to(dev)
+        self.wv = sd[pfx + "Wvs.%d.weight" % i].float().reshape(1024, 1024).contiguous().to(dev).to(dtype)
         self.bv = sd[pfx + "Wvs.%d.bias" % i].float().contiguous().to(dev)
         if with_g:
             self.wg = sd[pfx + "Wgs.%d.weight" % i].float().reshape(16, 64).contiguous().to(dev)
@@ -269,26 +284,27 @@ class HeadCommon:
         # per-shape (tile width, scheduling) selection by on-device timing the first time a shape is seen
         ops.AUTOTUNE[0] = os.environ.get("MEGA_B200_AUTOTUNE", "1") != "0"
         ops.load_tuned(os.environ.get("MEGA_B200_TUNED", os.path.join(os.path.dirname(__file__), "tuned_b200.json")))
-        self.backbone = Backbone(sd, dev)
-        self.rpn_w = pack_conv(sd["rpn.head.conv.weight"], dev)
+        self.act = act = cfg.act_dtype
+        self.backbone = Backbone(sd, dev, dtype=act)
+        self.rpn_w = pack_conv(sd["rpn.head.conv.weight"], dev, act)
         self.rpn_b = sd["rpn.head.conv.bias"].float().contiguous().to(dev)
         a = sd["rpn.head.cls_logits.weight"].shape[0]
         self.num_anchors = a
         hw = torch.cat([sd["rpn.head.cls_logits.weight"].float().reshape(a, -1),
                         sd["rpn.head.bbox_pred.weight"].float().reshape(4 * a, -1)], 0)
-        self.rpn_hw = hw.reshape(1, 5 * a, -1).contiguous().to(dev)
+        self.rpn_hw = hw.reshape(1, 5 * a, -1).contiguous().to(dev).to(act)
         self.rpn_hb = torch.cat([sd["rpn.head.cls_logits.bias"].float(),
                                  sd["rpn.head.bbox_pred.bias"].float()]).contiguous().to(dev)
         self.rpn_ld = _round_up(5 * a, 4)
         self.base_anchors = cell_anchors(cfg.anchor_stride, cfg.anchor_sizes, cfg.aspect_ratios).to(dev)
         assert self.base_anchors.shape[0] == a
         self.res5 = ResNetStages(sd, FE + "head.", (4,), dev, dilation=cfg.res5_dilation,
-                                 first_stride_of=lambda li: 1)
+                                 first_stride_of=lambda li: 1, dtype=act)
         pw = torch.cat([sd["roi_heads.box.predictor.cls_score.weight"].float(),
                         sd["roi_heads.box.predictor.bbox_pred.weight"].float()], 0)
         self.num_classes = sd["roi_heads.box.predictor.cls_score.weight"].shape[0]
         self.pred_ld = _round_up(5 * self.num_classes, 4)
-        self.pred_w = pw.contiguous().to(dev)
+        self.pred_w = pw.contiguous().to(dev).to(act)
         pb = torch.zeros(self.pred_ld)                       # bias padded: the epilogue loads it in float4 groups
         pb[:5 * self.num_classes] = torch.cat([sd["roi_heads.box.predictor.cls_score.bias"].float(),
                                                sd["roi_heads.box.predictor.bbox_pred.bias"].float()])
@@ -307,7 +323,7 @@ class HeadCommon:
         """feats [n,h,w,1024] -> proposals (boxes [n,post,4], scores, count[n])"""
         c = self.cfg
         n, h, w, _ = feats.shape
-        t = self._buf("rpn_t", (n, h, w, feats.shape[3]))
+        t = self._buf("rpn_t", (n, h, w, feats.shape[3]), self.act)
         ops.conv_gemm(feats, self.rpn_w, t, taps=(3, 3), dil=1, pad=1, bias=self.rpn_b, relu=True)
         head = self._buf("rpn_head", (n, h, w, self.rpn_ld))
         ops.conv_gemm(t, self.rpn_hw, head, bias=self.rpn_hb, cout=5 * self.num_anchors, block_n=64)
@@ -316,6 +332,45 @@ class HeadCommon:
         ops.rpn_select(head, n, h, w, self.base_anchors, im_w, im_h, c.pre_nms_top_n, post, c.rpn_nms_thresh,
                        c.rpn_min_size, c.anchor_stride, out=out)
         return out[0], out[1], out[3]
+
+    # ------------------------------------------------------------------ relation module
+    def _attention(self, att, xq, nq, refs, nref, ld, out, boxes_q=None, boxes_k=None, m_valid=None, n_valid=None,
+                   n_valid_off=0):
+        """out = xq + Attention(xq, refs)   (attention_module_multi_head, extractors :567-646)"""
+        D = self.feat_dim
+        q, k, vt = self.Qb[:nq], self.Kb[:nref], self.Vt[ld]
+        s = self.S[ld][:16 * nq * ld].view(16, nq, ld)
+        ops.linear(xq, att.wq, q, bias=att.bq)
+        ops.linear(refs, att.wk, k, bias=att.bk)
+        ops.linear(att.wv, refs, vt)                                    # V'^T = Wv . refs^T  -> [1024, nref]
+        ops.conv_gemm(q.view(1, 1, nq, D), k.view(1, nref, D), s.view(16, 1, nq, ld), tile=(1, 128), cout=nref,
+                      k=64, batch=16, a_c_off=64, b_k_off=64, out_n_off=1, n_img=1)
+        pr = self.P[ld][:16 * nq * ld].view(16, nq, ld) if self.P is not None else None
+        ops.relation_softmax(s, nq, ld, 1.0 / math.sqrt(64.0), boxes_q=boxes_q, boxes_k=boxes_k,
+                             wg=att.wg if boxes_q is not None else None, bg=att.bg if boxes_q is not None else None,
+                             dim_mat=self.dim_mat if boxes_q is not None else None, m_valid=m_valid,
+                             m_host=nref, n_valid=n_valid, n_valid_off=n_valid_off, probs_f16=pr)
+        if pr is not None:
+            s = pr
+        ops.conv_gemm(s.view(16, 1, nq, ld), vt.view(1, D, ld), out.view(1, 1, nq, D), tile=(1, 128), cout=64, k=ld,
+                      batch=16, a_n_off=1, b_n_off=64, out_c_off=64, res_c_off=64, bias_z_off=64, bias=att.bv,
+                      residual=xq.view(1, 1, nq, D), block_n=64)
+        return out
+
+    def _alloc_attention(self, geoms, kmax):
+        """scratch of the relation module for the (query rows, key rows) geometries of an engine:
+        Q / K projections, V'^T per key-count pitch, fp32 logits (+ fp16 probabilities in fp16 mode)"""
+        D, dev, act = self.feat_dim, self.dev, self.act
+        self.Qb = torch.zeros(max(nq for nq, _ in geoms), D, device=dev, dtype=act)
+        self.Kb = torch.zeros(kmax, D, device=dev, dtype=act)
+        need = {}
+        for nq, ld in geoms:
+            need[ld] = max(need.get(ld, 0), 16 * nq * ld)
+        self.Vt = {ld: torch.zeros(D, ld, device=dev, dtype=act) for ld in need}
+        self.S = {ld: torch.zeros(n, device=dev) for ld, n in need.items()}
+        self.P = {ld: torch.zeros(n, device=dev, dtype=act) for ld, n in need.items()} if act != torch.float32 else None
+        feat_range = torch.arange(0, 8, dtype=torch.float32)
+        self.dim_mat = torch.full((8,), 1000.0).pow(8.0 / 64 * feat_range).to(dev)   # extractors :129-130
 
     def predict_and_postprocess(self, x, proposals, count, im_w, im_h):
         c = self.cfg
@@ -332,103 +387,16 @@ class HeadCommon:
         return Detections(*out)
 
 
-class MegaEngine(HeadCommon):
-    """GeneralizedRCNNMEGA._forward_test + MEGAFeatureExtractor test path
-    (detector/generalized_rcnn_mega.py:137-225; extractors :657-699, :754-774, :806-829, :885-933)."""
+class WindowedEngine(HeadCommon):
+    """what the windowed video methods (MEGA, RDN) share: the per-frame branch backbone -> RPN -> res5 -> ROIAlign ->
+    fcs[0], the ring of per-frame ROI features addressed by slot, and CUDA-graph capture of fixed launch sequences.
+    Subclasses provide KP / R / L, fc0_w / fc0_b, the pooled / fc0_out / roi_boxes scratch and the win_* ring."""
 
-    def __init__(self, sd, cfg=None, device="cuda"):
-        cfg = cfg or EngineConfig()
-        dev = torch.device(device)
-        super().__init__(sd, cfg, dev)
-        c = cfg
-        self.R, self.A, self.L, self.KP = c.ref_post_nms_top_n, c.advanced_num, c.all_frame_interval, c.post_nms_top_n
-        self.GF, self.MEMF = c.global_size, c.memory_size
-        assert c.stage == 3 and c.global_res_stage == 1, "engine is laid out for STAGE=3, GLOBAL.RES_STAGE=1"
-        R, A, L, KP, GF = self.R, self.A, self.L, self.KP, self.GF
-        res = c.pooler_resolution
-        # l_fcs[0]: reference column index c*49 + bin -> bin*2048 + c (ROIAlign output is bin-major here)
-        w0 = sd[FE + "l_fcs.0.weight"].float()
-        ch = w0.shape[1] // (res * res)
-        self.fc0_w = w0.reshape(w0.shape[0], ch, res * res).permute(0, 2, 1).reshape(w0.shape[0], -1).contiguous().to(dev)
-        self.fc0_b = sd[FE + "l_fcs.0.bias"].float().contiguous().to(dev)
-        self.fc_w = [None] + [sd[FE + "l_fcs.%d.weight" % i].float().contiguous().to(dev) for i in (1, 2)]
-        self.fc_b = [None] + [sd[FE + "l_fcs.%d.bias" % i].float().contiguous().to(dev) for i in (1, 2)]
-        self.att_l = [_Att(sd, FE + "l_", i, dev, True) for i in range(3)]
-        self.att_g = [_Att(sd, FE + "g_", i, dev, False) for i in range(2)]
-        feat_range = torch.arange(0, 8, dtype=torch.float32)
-        self.dim_mat = torch.full((8,), 1000.0).pow(8.0 / 64 * feat_range).to(dev)   # extractors :129-130
-        self.feat_dim = 1024
-        D = self.feat_dim
-        z = lambda *s, dtype=torch.float32: torch.zeros(*s, device=dev, dtype=dtype)
-        # ---- persistent state
-        self.win_x, self.win_boxes, self.win_cnt = z(L * KP, D), z(L * KP, 4), z(L, 1, dtype=torch.int32)
-        self.glob_x = z(GF * R, D)
-        self.nl0, self.nl12 = L * R, L * A                      # local reference rows per stage
-        self.mem_cap0, self.mem_cap12 = self.MEMF * R, self.MEMF * A
-        self.E0 = z(KP + self.nl0 + self.mem_cap0, D)           # [key 300 | refs 1875 | mem0 1875]
-        self.B0 = z(KP + self.nl0 + self.mem_cap0, 4)
-        self.nq = KP + self.nl12                                # 675 query rows of stages 0/1
-        self.Qin0, self.Bq0 = z(self.nq, D), z(self.nq, 4)
-        self.Y1E, self.Y2M = z(self.nq + self.mem_cap12, D), z(self.nq + self.mem_cap12, D)
-        self.B1, self.B2 = z(self.nl12 + self.mem_cap12, 4), z(self.nl12 + self.mem_cap12, 4)
-        self.X1, self.X2, self.X3, self.X4 = z(self.nq, D), z(self.nq, D), z(KP, D), z(KP, D)
-        self.cur_cnt = z(1, 1, dtype=torch.int32)
-        self.payload_in = z(KP * D + KP * 4 + 4 + R * D)
-        self.payload_all = None
-        # ---- attention scratch, one set per key-count geometry
-        self.ld_g = _round_up(GF * R, 32)
-        self.ld_0 = _round_up(self.nl0 + self.mem_cap0, 32)
-        self.ld_12 = _round_up(self.nl12 + self.mem_cap12, 32)
-        nq_g0 = KP + self.nl0
-        self.Qb = z(nq_g0, D)
-        self.Kb = z(max(self.nl0 + self.mem_cap0, GF * R), D)
-        self.Vt = {ld: z(D, ld) for ld in {self.ld_g, self.ld_0, self.ld_12}}
-        s_need = {}
-        for ld, rows in ((self.ld_g, nq_g0), (self.ld_0, self.nq), (self.ld_12, self.nq)):
-            s_need[ld] = max(s_need.get(ld, 0), 16 * rows * ld)
-        self.S = {ld: z(n) for ld, n in s_need.items()}
-        self.pooled = z(KP + R + KP, res * res * ch)            # up to (local 300 + global 75 [+ spare]) rois
-        self.fc0_out = z(KP + R + KP, D)
-        self.roi_boxes, self.roi_batch = z(KP + R + KP, 4), z(KP + R + KP, dtype=torch.int32)
-        # ---- per-frame index tables: pinned host mirror + device copy
-        o = {}
-        off = 0
-        for name, n in (("mvalid", 4), ("idx_e0", KP + self.nl0), ("idx_dis", self.nl12), ("dst_local", KP),
-                        ("dst_glob", R), ("dst_mem0", R), ("dst_mem12", A), ("dst_memb12", A), ("slot_new", 4),
-                        ("slot_key", 4)):
-            o[name] = (off, n)
-            off += _round_up(n, 4)
-        self._tab_off = o
-        # host mirrors are multi-buffered: the H2D copy of frame t may still be queued when the host
-        # prepares frame t+1 (each buffer is reused only after the event recorded behind its copy)
-        self._tab_ring = [torch.zeros(off, dtype=torch.int32).pin_memory() for _ in range(4)]
-        self._tab_ev = [None] * 4
-        self.tab_h = self._tab_ring[0]
-        self.tab_d = z(off, dtype=torch.int32)
-        # static tables
-        q_idx = list(range(KP)) + [KP + f * R + j for f in range(L) for j in range(A)]
-        self.idx_qin0 = torch.tensor(q_idx, dtype=torch.int32, device=dev)
+    def _init_window_state(self):
         self._roi_tabs = {}
         self._graphs, self._static_in, self._eager_done = {}, {}, {}
         self._side = None
         self.use_graph = False
-        self.reset()
-
-    # ------------------------------------------------------------------ host-side state machine
-    def reset(self):
-        self.win_slots = deque(maxlen=self.L)
-        self.next_slot = 0
-        self.glob_pushed = 0
-        self.mem_pushed = 0
-        self.frames = 0
-
-    def _tab(self, name):
-        o, n = self._tab_off[name]
-        return self.tab_d[o:o + n]
-
-    def _tab_h(self, name):
-        o, n = self._tab_off[name]
-        return self.tab_h[o:o + n]
 
     def _roi_table(self, kinds):
         """static gather table (per batch pattern): roi rows <- rpn output rows, + batch index"""
@@ -492,6 +460,131 @@ class MegaEngine(HeadCommon):
         self.win_slots.append(slot)
         return slot
 
+    # ---- the steady frame is two fixed launch sequences, each captured in its own CUDA graph:
+    #      "ref"    images -> payload (x300 | boxes300 | count | x75 of the global frame)
+    #      "ingest" payload -> ring buffers -> aggregation -> detections
+    #      (frame-parallel multi-GPU runs all-gather the payloads between the two)
+    def _graph_run(self, key, fn):
+        if self.use_graph and key not in self._graphs and self._eager_done.get(key, 0) >= 1:
+            torch.cuda.synchronize(self.dev)
+            graph = torch.cuda.CUDAGraph()
+            l0 = ops.LAUNCHES[0]
+            with torch.cuda.graph(graph):
+                out = fn()
+            self._graphs[key] = (graph, out, ops.LAUNCHES[0] - l0)
+        g = self._graphs.get(key)
+        if g is not None:
+            g[0].replay()
+            return g[1]
+        self._eager_done[key] = self._eager_done.get(key, 0) + 1
+        return fn()
+
+    @property
+    def launches_per_frame(self):
+        return sum(g[2] for g in self._graphs.values())
+
+    def static_input(self, shape):
+        """device buffer [2,3,H,W] the captured graph reads its (local, global) frame pair from;
+        writing the next pair straight into it saves the device-to-device copy"""
+        t = self._static_in.get(tuple(shape))
+        if t is None:
+            t = torch.zeros(*shape, device=self.dev)
+            self._static_in[tuple(shape)] = t
+        return t
+
+
+class MegaEngine(WindowedEngine):
+    """GeneralizedRCNNMEGA._forward_test + MEGAFeatureExtractor test path
+    (detector/generalized_rcnn_mega.py:137-225; extractors :657-699, :754-774, :806-829, :885-933)."""
+
+    def __init__(self, sd, cfg=None, device="cuda"):
+        cfg = cfg or EngineConfig()
+        dev = torch.device(device)
+        super().__init__(sd, cfg, dev)
+        c = cfg
+        self.R, self.A, self.L, self.KP = c.ref_post_nms_top_n, c.advanced_num, c.all_frame_interval, c.post_nms_top_n
+        self.GF, self.MEMF = c.global_size, c.memory_size
+        assert c.stage == 3 and c.global_res_stage == 1, "engine is laid out for STAGE=3, GLOBAL.RES_STAGE=1"
+        R, A, L, KP, GF = self.R, self.A, self.L, self.KP, self.GF
+        res = c.pooler_resolution
+        # l_fcs[0]: reference column index c*49 + bin -> bin*2048 + c (ROIAlign output is bin-major here)
+        w0 = sd[FE + "l_fcs.0.weight"].float()
+        ch = w0.shape[1] // (res * res)
+        act = self.act
+        self.fc0_w = (w0.reshape(w0.shape[0], ch, res * res).permute(0, 2, 1).reshape(w0.shape[0], -1).contiguous()
+                      .to(act).to(dev))
+        self.fc0_b = sd[FE + "l_fcs.0.bias"].float().contiguous().to(dev)
+        self.fc_w = [None] + [sd[FE + "l_fcs.%d.weight" % i].float().contiguous().to(dev).to(act) for i in (1, 2)]
+        self.fc_b = [None] + [sd[FE + "l_fcs.%d.bias" % i].float().contiguous().to(dev) for i in (1, 2)]
+        self.att_l = [_Att(sd, FE + "l_", i, dev, True, act) for i in range(3)]
+        self.att_g = [_Att(sd, FE + "g_", i, dev, False, act) for i in range(2)]
+        self.feat_dim = 1024
+        D = self.feat_dim
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, device=dev, dtype=dtype)
+        za = lambda *s: torch.zeros(*s, device=dev, dtype=act)       # feature rows / GEMM operands
+        self.fw = D * (2 if act == torch.float16 else 4) // 4            # 32-bit words per feature row
+        # ---- persistent state
+        self.win_x, self.win_boxes, self.win_cnt = za(L * KP, D), z(L * KP, 4), z(L, 1, dtype=torch.int32)
+        self.glob_x = za(GF * R, D)
+        self.nl0, self.nl12 = L * R, L * A                      # local reference rows per stage
+        self.mem_cap0, self.mem_cap12 = self.MEMF * R, self.MEMF * A
+        self.E0 = za(KP + self.nl0 + self.mem_cap0, D)          # [key 300 | refs 1875 | mem0 1875]
+        self.B0 = z(KP + self.nl0 + self.mem_cap0, 4)
+        self.nq = KP + self.nl12                                # 675 query rows of stages 0/1
+        self.Qin0, self.Bq0 = za(self.nq, D), z(self.nq, 4)
+        self.Y1E, self.Y2M = za(self.nq + self.mem_cap12, D), za(self.nq + self.mem_cap12, D)
+        self.B1, self.B2 = z(self.nl12 + self.mem_cap12, 4), z(self.nl12 + self.mem_cap12, 4)
+        self.X1, self.X2, self.X3, self.X4 = za(self.nq, D), za(self.nq, D), za(KP, D), za(KP, D)
+        self.cur_cnt = z(1, 1, dtype=torch.int32)
+        self.payload_in = z(KP * self.fw + KP * 4 + 4 + R * self.fw)   # 32-bit words: x300 | boxes | count | x75
+        self.payload_all = None
+        # ---- attention scratch, one set per key-count geometry
+        self.ld_g = _round_up(GF * R, 32)
+        self.ld_0 = _round_up(self.nl0 + self.mem_cap0, 32)
+        self.ld_12 = _round_up(self.nl12 + self.mem_cap12, 32)
+        nq_g0 = KP + self.nl0
+        self._alloc_attention([(nq_g0, self.ld_g), (self.nq, self.ld_0), (self.nq, self.ld_12)],
+                              max(self.nl0 + self.mem_cap0, GF * R))
+        self.pooled = za(KP + R + KP, res * res * ch)           # up to (local 300 + global 75 [+ spare]) rois
+        self.fc0_out = za(KP + R + KP, D)
+        self.roi_boxes, self.roi_batch = z(KP + R + KP, 4), z(KP + R + KP, dtype=torch.int32)
+        # ---- per-frame index tables: pinned host mirror + device copy
+        o = {}
+        off = 0
+        for name, n in (("mvalid", 4), ("idx_e0", KP + self.nl0), ("idx_dis", self.nl12), ("dst_local", KP),
+                        ("dst_glob", R), ("dst_mem0", R), ("dst_mem12", A), ("dst_memb12", A), ("slot_new", 4),
+                        ("slot_key", 4)):
+            o[name] = (off, n)
+            off += _round_up(n, 4)
+        self._tab_off = o
+        # host mirrors are multi-buffered: the H2D copy of frame t may still be queued when the host
+        # prepares frame t+1 (each buffer is reused only after the event recorded behind its copy)
+        self._tab_ring = [torch.zeros(off, dtype=torch.int32).pin_memory() for _ in range(4)]
+        self._tab_ev = [None] * 4
+        self.tab_h = self._tab_ring[0]
+        self.tab_d = z(off, dtype=torch.int32)
+        # static tables
+        q_idx = list(range(KP)) + [KP + f * R + j for f in range(L) for j in range(A)]
+        self.idx_qin0 = torch.tensor(q_idx, dtype=torch.int32, device=dev)
+        self._init_window_state()
+        self.reset()
+
+    # ------------------------------------------------------------------ host-side state machine
+    def reset(self):
+        self.win_slots = deque(maxlen=self.L)
+        self.next_slot = 0
+        self.glob_pushed = 0
+        self.mem_pushed = 0
+        self.frames = 0
+
+    def _tab(self, name):
+        o, n = self._tab_off[name]
+        return self.tab_d[o:o + n]
+
+    def _tab_h(self, name):
+        o, n = self._tab_off[name]
+        return self.tab_h[o:o + n]
+
     @_with_precision
     def start_video(self, cur, lookahead, globals_, im_w, im_h):
         """frame_category == 0 (generalized_rcnn_mega.py:163-193): the current frame fills window
@@ -532,29 +625,6 @@ class MegaEngine(HeadCommon):
         self._run_ref(imgs, im_w, im_h)
         return self._ingest_next(im_w, im_h)
 
-    # ---- the steady frame is two fixed launch sequences, each captured in its own CUDA graph:
-    #      "ref"    images -> payload (x300 | boxes300 | count | x75 of the global frame)
-    #      "ingest" payload -> ring buffers -> aggregation -> detections
-    #      (frame-parallel multi-GPU runs all-gather the payloads between the two)
-    def _graph_run(self, key, fn):
-        if self.use_graph and key not in self._graphs and self._eager_done.get(key, 0) >= 1:
-            torch.cuda.synchronize(self.dev)
-            graph = torch.cuda.CUDAGraph()
-            l0 = ops.LAUNCHES[0]
-            with torch.cuda.graph(graph):
-                out = fn()
-            self._graphs[key] = (graph, out, ops.LAUNCHES[0] - l0)
-        g = self._graphs.get(key)
-        if g is not None:
-            g[0].replay()
-            return g[1]
-        self._eager_done[key] = self._eager_done.get(key, 0) + 1
-        return fn()
-
-    @property
-    def launches_per_frame(self):
-        return sum(g[2] for g in self._graphs.values())
-
     def _run_ref(self, imgs, im_w, im_h):
         static_in = self.static_input(tuple(imgs.shape))
         if imgs.data_ptr() != static_in.data_ptr():
@@ -568,15 +638,6 @@ class MegaEngine(HeadCommon):
         self.glob_pushed += 1
         self._fill_tables(slot_new=slot_new, gslot=gslot)
         return self._graph_run(("ingest", im_w, im_h), lambda: self._ingest(im_w, im_h))
-
-    def static_input(self, shape):
-        """device buffer [2,3,H,W] the captured graph reads its (local, global) frame pair from;
-        writing the next pair straight into it saves the device-to-device copy"""
-        t = self._static_in.get(tuple(shape))
-        if t is None:
-            t = torch.zeros(*shape, device=self.dev)
-            self._static_in[tuple(shape)] = t
-        return t
 
     # ---- frame-parallel multi-GPU (SURVEY.md section 8e, option i): rank r runs the per-frame branch of
     #      frame pair r of every group of `world` key frames; one NCCL all-gather of the fixed-size payloads
@@ -638,15 +699,15 @@ class MegaEngine(HeadCommon):
         self.frames += 1
 
     def _payload_views(self, payload):
-        KP, R, D = self.KP, self.R, self.feat_dim
+        KP, R, D, fw = self.KP, self.R, self.feat_dim, self.fw
         o = 0
-        x = payload[o:o + KP * D].view(KP, D)
-        o += KP * D
+        x = payload[o:o + KP * fw].view(self.act).view(KP, D)
+        o += KP * fw
         boxes = payload[o:o + KP * 4].view(KP, 4)
         o += KP * 4
         cnt = payload[o:o + 4].view(1, 4)
         o += 4
-        xg = payload[o:o + R * D].view(R, D)
+        xg = payload[o:o + R * fw].view(self.act).view(R, D)
         return x, boxes, cnt, xg
 
     def _ref_to_payload(self, imgs, im_w, im_h, payload):
@@ -675,27 +736,6 @@ class MegaEngine(HeadCommon):
     def _steady_frame(self, imgs, im_w, im_h):
         self._ref_to_payload(imgs, im_w, im_h, self.payload_in)
         return self._ingest(im_w, im_h)
-
-    # ------------------------------------------------------------------ relation module
-    def _attention(self, att, xq, nq, refs, nref, ld, out, boxes_q=None, boxes_k=None, m_valid=None, n_valid=None,
-                   n_valid_off=0):
-        """out = xq + Attention(xq, refs)   (attention_module_multi_head, extractors :567-646)"""
-        D = self.feat_dim
-        q, k, vt = self.Qb[:nq], self.Kb[:nref], self.Vt[ld]
-        s = self.S[ld][:16 * nq * ld].view(16, nq, ld)
-        ops.linear(xq, att.wq, q, bias=att.bq)
-        ops.linear(refs, att.wk, k, bias=att.bk)
-        ops.linear(att.wv, refs, vt)                                    # V'^T = Wv . refs^T  -> [1024, nref]
-        ops.conv_gemm(q.view(1, 1, nq, D), k.view(1, nref, D), s.view(16, 1, nq, ld), tile=(1, 128), cout=nref,
-                      k=64, batch=16, a_c_off=64, b_k_off=64, out_n_off=1, n_img=1)
-        ops.relation_softmax(s, nq, ld, 1.0 / math.sqrt(64.0), boxes_q=boxes_q, boxes_k=boxes_k,
-                             wg=att.wg if boxes_q is not None else None, bg=att.bg if boxes_q is not None else None,
-                             dim_mat=self.dim_mat if boxes_q is not None else None, m_valid=m_valid,
-                             m_host=nref, n_valid=n_valid, n_valid_off=n_valid_off)
-        ops.conv_gemm(s.view(16, 1, nq, ld), vt.view(1, D, ld), out.view(1, 1, nq, D), tile=(1, 128), cout=64, k=ld,
-                      batch=16, a_n_off=1, b_n_off=64, out_c_off=64, res_c_off=64, bias_z_off=64, bias=att.bv,
-                      residual=xq.view(1, 1, nq, D), block_n=64)
-        return out
 
     def aggregate(self, im_w, im_h, new_local=True):
         """MEGAFeatureExtractor._forward_test after the per-frame features exist (extractors :898-933)."""
@@ -743,6 +783,170 @@ class MegaEngine(HeadCommon):
         return self.predict_and_postprocess(self.X4, self.Bq0[:KP], kcnt, im_w, im_h)
 
 
+class RdnEngine(WindowedEngine):
+    """GeneralizedRCNNRDN._forward_test + RDNFeatureExtractor test path (detector/generalized_rcnn_rdn.py:108-190;
+    roi_box_feature_extractors.py:400-454 with the base attention module :178-238), ATTENTION.STAGE = 2,
+    ADVANCED_STAGE = 1 (configs/RDN/vid_R_101_C4_RDN_1x.yaml), window of 37 frames with the key frame at 18.
+
+    Same restructuring as MegaEngine: every frame goes once through backbone -> RPN(300) -> res5 -> ROIAlign ->
+    fcs[0] when it ENTERS the window (its 75 reference proposals are the prefix of its 300 key proposals; the
+    reference recomputes res5 / ROIAlign / fcs[0] of the key frame 18 frames later, :419-428); the window is a ring
+    of slots read through a per-frame index table, so the steady frame is one fixed, graph-captured launch sequence."""
+
+    def __init__(self, sd, cfg=None, device="cuda"):
+        cfg = cfg or EngineConfig(all_frame_interval=37, key_frame_location=18, stage=2, advanced_stage=1)
+        dev = torch.device(device)
+        super().__init__(sd, cfg, dev)
+        c = cfg
+        assert c.stage == 2 and c.advanced_stage == 1, "engine is laid out for ATTENTION.STAGE=2, ADVANCED_STAGE=1"
+        self.R, self.A, self.L, self.KP = c.ref_post_nms_top_n, c.advanced_num, c.all_frame_interval, c.post_nms_top_n
+        R, A, L, KP = self.R, self.A, self.L, self.KP
+        res, act = c.pooler_resolution, self.act
+        w0 = sd[FE + "fcs.0.weight"].float()
+        ch = w0.shape[1] // (res * res)
+        self.fc0_w = (w0.reshape(w0.shape[0], ch, res * res).permute(0, 2, 1).reshape(w0.shape[0], -1).contiguous()
+                      .to(act).to(dev))
+        self.fc0_b = sd[FE + "fcs.0.bias"].float().contiguous().to(dev)
+        self.fc_w = [None] + [sd[FE + "fcs.%d.weight" % i].float().contiguous().to(dev).to(act) for i in (1, 2)]
+        self.fc_b = [None] + [sd[FE + "fcs.%d.bias" % i].float().contiguous().to(dev) for i in (1, 2)]
+        self.att = [_Att(sd, FE, i, dev, True, act) for i in range(4)]
+        self.feat_dim = D = 1024
+        z = lambda *s, dtype=torch.float32: torch.zeros(*s, device=dev, dtype=dtype)
+        za = lambda *s: torch.zeros(*s, device=dev, dtype=act)
+        self.win_x, self.win_boxes, self.win_cnt = za(L * KP, D), z(L * KP, 4), z(L, 1, dtype=torch.int32)
+        self.nref, self.nadv = L * R, L * A                     # 2775 reference rows, 555 distilled rows
+        self.E, self.B = za(KP + self.nref, D), z(KP + self.nref, 4)       # [key 300 | refs 2775]
+        self.Xadv, self.Badv = za(self.nadv, D), z(self.nadv, 4)
+        self.X1, self.Y1, self.X2, self.X3 = za(KP, D), za(KP, D), za(KP, D), za(KP, D)
+        self.Xa, self.Ya = za(self.nadv, D), za(self.nadv, D)
+        self.cur_cnt = z(1, 1, dtype=torch.int32)
+        self.ld_ref, self.ld_adv = _round_up(self.nref, 32), _round_up(self.nadv, 32)
+        self._alloc_attention([(max(KP, self.nadv), self.ld_ref), (KP, self.ld_adv)], self.nref)
+        self.pooled = za(KP, res * res * ch)
+        self.fc0_out = za(KP, D)
+        self.roi_boxes, self.roi_batch = z(KP, 4), z(KP, dtype=torch.int32)
+        o, off = {}, 0
+        for name, n in (("idx_e", KP + self.nref), ("idx_adv", self.nadv), ("dst_local", KP), ("slot_new", 4),
+                        ("slot_key", 4)):
+            o[name] = (off, n)
+            off += _round_up(n, 4)
+        self._tab_off = o
+        self._tab_ring = [torch.zeros(off, dtype=torch.int32).pin_memory() for _ in range(4)]
+        self._tab_ev = [None] * 4
+        self.tab_h = self._tab_ring[0]
+        self.tab_d = z(off, dtype=torch.int32)
+        self.payload = z(KP * (D * (2 if act == torch.float16 else 4) // 4) + KP * 4 + 4)
+        self._init_window_state()
+        self.reset()
+
+    def reset(self):
+        self.win_slots = deque(maxlen=self.L)
+        self.next_slot = 0
+        self.frames = 0
+
+    def _tab(self, name):
+        o, n = self._tab_off[name]
+        return self.tab_d[o:o + n]
+
+    def _fill_tables(self, slot_new=None):
+        KP, R, A = self.KP, self.R, self.A
+        slots = list(self.win_slots)
+        assert len(slots) == self.L
+        ring = self.frames % len(self._tab_ring)
+        if self._tab_ev[ring] is not None:
+            self._tab_ev[ring].synchronize()
+        th_all = self._tab_ring[ring]
+
+        def th(name):
+            o, n = self._tab_off[name]
+            return th_all[o:o + n]
+
+        kslot = slots[self.cfg.key_frame_location]
+        sl = np.asarray(slots, dtype=np.int32)
+        e = np.empty(KP + self.nref, dtype=np.int32)
+        e[:KP] = kslot * KP + np.arange(KP)
+        e[KP:] = (sl[:, None] * KP + np.arange(R)[None, :]).reshape(-1)
+        th("idx_e").copy_(torch.from_numpy(e))
+        th("idx_adv").copy_(torch.from_numpy((sl[:, None] * KP + np.arange(A)[None, :]).reshape(-1).astype(np.int32)))
+        if slot_new is not None:
+            th("dst_local").copy_(torch.arange(slot_new * KP, (slot_new + 1) * KP, dtype=torch.int32))
+            th("slot_new")[0] = slot_new
+        th("slot_key")[0] = kslot
+        self.tab_d.copy_(th_all, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._tab_ev[ring] = ev
+        self.frames += 1
+
+    @_with_precision
+    def start_video(self, cur, lookahead, im_w, im_h):
+        """frame_category == 0 (generalized_rcnn_rdn.py:137-164): the current frame fills window positions
+        0..key_frame_location, then the look-ahead frames."""
+        self.reset()
+        c = self.cfg
+        need = self.L - (c.key_frame_location + 1)
+        assert len(lookahead) >= need, "first frame of a video needs %d look-ahead frames" % need
+        frames = [cur] + list(lookahead[:need])
+        for i in range(0, len(frames), 2):
+            chunk = frames[i:i + 2]
+            imgs = torch.cat(chunk, 0) if len(chunk) > 1 else chunk[0]
+            x, boxes, cnt, spans = self.ref_branch(imgs, ["L"] * len(chunk), im_w, im_h)
+            for j in range(len(chunk)):
+                o, r = spans[j]
+                reps = (c.key_frame_location + 1) if (i + j) == 0 else 1
+                for _ in range(reps):
+                    self._push_local_rows(x[o:o + r], boxes[j], cnt[j:j + 1], self._claim_slot())
+        self._fill_tables()
+        return self.aggregate(im_w, im_h)
+
+    @_with_precision
+    def step(self, new_frame, im_w, im_h):
+        """frame_category == 1: one look-ahead frame [1,3,H,W] (infos["ref"][0], generalized_rcnn_rdn.py:166-170)"""
+        static_in = self.static_input(tuple(new_frame.shape))
+        if new_frame.data_ptr() != static_in.data_ptr():
+            static_in.copy_(new_frame, non_blocking=True)
+        slot_new = self._claim_slot()
+        self._fill_tables(slot_new=slot_new)
+        return self._graph_run(("rdn", tuple(new_frame.shape), im_w, im_h), lambda: self._steady_frame(static_in, im_w, im_h))
+
+    def _steady_frame(self, img, im_w, im_h):
+        KP = self.KP
+        x, boxes, cnt, spans = self.ref_branch(img, ["L"], im_w, im_h)
+        ops.copy_rows(x[:KP], self.win_x, KP, dst_idx=self._tab("dst_local"))
+        ops.copy_rows(boxes[0], self.win_boxes, KP, dst_idx=self._tab("dst_local"))
+        ops.copy_rows(cnt[0:1].view(torch.float32).view(1, 1), self.win_cnt.view(torch.float32), 1, row_len=1,
+                      dst_idx=self._tab("slot_new")[:1])
+        return self.aggregate(im_w, im_h)
+
+    def aggregate(self, im_w, im_h):
+        """RDNFeatureExtractor._forward_test after the per-frame features exist (extractors :412-454)."""
+        KP, nref, nadv = self.KP, self.nref, self.nadv
+        t = self._tab
+        ops.gather_rows(self.win_x, t("idx_e"), self.E, KP + nref)
+        ops.gather_rows(self.win_boxes, t("idx_e"), self.B, KP + nref)
+        ops.gather_rows(self.win_x, t("idx_adv"), self.Xadv, nadv)
+        ops.gather_rows(self.win_boxes, t("idx_adv"), self.Badv, nadv)
+        ops.gather_rows(self.win_cnt.view(torch.float32), t("slot_key")[:1], self.cur_cnt.view(torch.float32), 1,
+                        row_len=1)
+        kcnt = self.cur_cnt.view(-1)[:1]
+        xk, bk = self.E[:KP], self.B[:KP]
+        refs, bref = self.E[KP:], self.B[KP:]
+        # base stages (:431-436): x = relu(fcs[i](x)); x += attention_i(x, x_refs); fcs[0] was applied on entry
+        self._attention(self.att[0], xk, KP, refs, nref, self.ld_ref, self.X1, boxes_q=bk, boxes_k=bref,
+                        n_valid=kcnt, n_valid_off=KP)
+        ops.linear(self.X1, self.fc_w[1], self.Y1, bias=self.fc_b[1], relu=True)
+        self._attention(self.att[1], self.Y1, KP, refs, nref, self.ld_ref, self.X2, boxes_q=bk, boxes_k=bref,
+                        n_valid=kcnt, n_valid_off=KP)
+        # advanced stage (:438-452): the first 15 rows of every frame attend to all reference rows ...
+        self._attention(self.att[2], self.Xadv, nadv, refs, nref, self.ld_ref, self.Xa, boxes_q=self.Badv, boxes_k=bref)
+        ops.linear(self.Xa, self.fc_w[2], self.Ya, bias=self.fc_b[2], relu=True)
+        # ... and the key rows attend to those 555 distilled rows
+        self._attention(self.att[3], self.X2, KP, self.Ya, nadv, self.ld_adv, self.X3, boxes_q=bk, boxes_k=self.Badv,
+                        n_valid=kcnt, n_valid_off=KP)
+        self.last_props = bk
+        return self.predict_and_postprocess(self.X3, bk, kcnt, im_w, im_h)
+
+
 class BaseEngine(HeadCommon):
     """GeneralizedRCNN single-frame path (detector/generalized_rcnn.py:33-65) with
     ResNetConv52MLPFeatureExtractor (extractors :106-118, REDUCE_CHANNEL optional)."""
@@ -754,14 +958,15 @@ class BaseEngine(HeadCommon):
         res = cfg.pooler_resolution
         self.reduce = (FE + "conv.weight") in sd
         if self.reduce:
-            self.red_w = pack_conv(sd[FE + "conv.weight"], dev)
+            self.red_w = pack_conv(sd[FE + "conv.weight"], dev, self.act)
             self.red_b = sd[FE + "conv.bias"].float().contiguous().to(dev)
         w6 = sd[FE + "fc6.weight"].float()
         ch = w6.shape[1] // (res * res)
         self.ch = ch
-        self.fc6_w = w6.reshape(w6.shape[0], ch, res * res).permute(0, 2, 1).reshape(w6.shape[0], -1).contiguous().to(dev)
+        self.fc6_w = (w6.reshape(w6.shape[0], ch, res * res).permute(0, 2, 1).reshape(w6.shape[0], -1).contiguous()
+                      .to(dev).to(self.act))
         self.fc6_b = sd[FE + "fc6.bias"].float().contiguous().to(dev)
-        self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev)
+        self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev).to(self.act)
         self.fc7_b = sd[FE + "fc7.bias"].float().contiguous().to(dev)
 
     @_with_precision
@@ -773,15 +978,15 @@ class BaseEngine(HeadCommon):
         x = self.res5.forward(feats)
         if self.reduce:
             n, h, w, _ = x.shape
-            xr = self._buf("reduce", (n, h, w, self.red_w.shape[1]))
+            xr = self._buf("reduce", (n, h, w, self.red_w.shape[1]), self.act)
             ops.conv_gemm(x, self.red_w, xr, bias=self.red_b, relu=True)
             x = xr
         res = c.pooler_resolution
-        pooled = self._buf("pooled", (KP, res * res * self.ch))
+        pooled = self._buf("pooled", (KP, res * res * self.ch), self.act)
         ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)
-        f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]))
+        f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]), self.act)
         ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True)
-        f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]))
+        f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]), self.act)
         ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
         self.last_feats, self.last_props, self.last_cnt, self.last_pooled = feats, boxes[0], cnt, pooled
         return self.predict_and_postprocess(f7, boxes[0], cnt[0:1], im_w, im_h)

@@ -13,9 +13,12 @@ LAUNCHES = [0]
 
 def _launch_conv_gemm(d):
     """single choke point of the tcgen05 kernel (bench.py wraps it with CUDA events for the roofline)"""
-    check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
+    check(lib.mega_conv_gemm(ctypes.byref(d), stream_ptr()), "mega_conv_gemm")
     LAUNCHES[0] += 1
 
+
+# programmatic dependent launch of the GEMM kernels (prologue overlapped with the previous kernel's tail)
+PDL = [True]
 
 _gemm_ws = {}
 WS_LANE = [0]   # launches that may overlap on different streams must use different lanes
@@ -45,9 +48,11 @@ def pick_tile(h, w):
     return best[1], best[2]
 
 
-# ---- arithmetic of the dense contractions: 0 = TF32 operands, 1 = "3xTF32" split (near-fp32, strict parity)
+# ---- arithmetic of the dense contractions over fp32 tensors: 0 = TF32 operands, 1 = "3xTF32" split (near-fp32,
+#      strict parity). fp16 tensors always run as precision 2 (fp16 operands, fp32 accumulate): the engine selects
+#      that mode by allocating its activations / weights in fp16 (EngineConfig.precision == "f16").
 PRECISION = [0]
-PRECISION_NAMES = {"tf32": 0, "fp32x3": 1}
+PRECISION_NAMES = {"tf32": 0, "fp32x3": 1, "f16": 0}
 
 
 class precision(object):
@@ -88,6 +93,8 @@ def load_tuned(path):
     if torch.cuda.is_available() and data.get("device") != torch.cuda.get_device_name(0):
         return 0
     for k, v in data["entries"]:
+        if len(k) == 22:      # tables written before the fp16 modes existed: out_f16 = 0
+            k = list(k) + [0]
         TUNED.setdefault(tuple(bool(x) if isinstance(x, bool) else x for x in k), tuple(v))
     return len(data["entries"])
 
@@ -95,13 +102,15 @@ def load_tuned(path):
 def _shape_key(d):
     return (d.a_n, d.a_h, d.a_w, d.a_c, d.a_stride_w, d.b_n, d.b_k, d.taps_r, d.taps_s, d.dil, d.k_per_tap, d.n_img,
             d.out_h, d.out_w, d.cout, d.tile_h, d.tile_w, d.batch, bool(d.residual), d.out_ld, d.out_c_off,
-            d.precision)
+            d.precision, d.out_f16)
 
 
-def _candidates(cout, prec=0):
+def _candidates(cout, prec=0, out_f16=0):
     cands = []
     for bn in ((64, 128) if prec == 1 else BLOCK_NS):
-        if bn >= 2 * cout and bn > 32:
+        if out_f16 and bn % 64:
+            continue
+        if bn >= 2 * cout and bn > (64 if out_f16 else 32):
             continue
         for sk in (0, 1):
             cands.append((bn, sk))
@@ -112,15 +121,15 @@ def _autotune(d):
     """time every (block_n, stream_k) candidate for this exact problem on the device (CUDA events,
     3 warm + 5 timed launches each) and remember the fastest; outputs are overwritten identically"""
     best = None
-    for bn, sk in _candidates(d.cout, d.precision):
+    for bn, sk in _candidates(d.cout, d.precision, d.out_f16):
         d.block_n, d.stream_k = bn, sk
         try:
             for _ in range(2):
-                check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
+                check(lib.mega_conv_gemm(ctypes.byref(d), stream_ptr()), "mega_conv_gemm")
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(8):
-                check(lib.mega_conv_gemm_tf32(ctypes.byref(d), stream_ptr()), "mega_conv_gemm_tf32")
+                check(lib.mega_conv_gemm(ctypes.byref(d), stream_ptr()), "mega_conv_gemm")
             e1.record()
             e1.synchronize()
             t = e0.elapsed_time(e1) / 8
@@ -131,18 +140,20 @@ def _autotune(d):
     return best
 
 
-def pick_config(cout, m_tiles, batch, kb_per_tile):
+def pick_config(cout, m_tiles, batch, kb_per_tile, out_f16=False):
     """(block_n, stream_k) when no autotuned entry exists. Deep reductions balance best at k-block
     granularity (stream-K, widest tile); shallow ones run whole tiles, with the tile width chosen to
     minimise waves x bytes staged per k-block on 148 SMs."""
     if kb_per_tile >= 48:
         for bn in (32, 64, 128):
-            if cout <= bn:
+            if cout <= bn and not (out_f16 and bn % 64):
                 return bn, 1
         return 256, 1
     best = None
     for bn in BLOCK_NS:
-        if bn >= 2 * cout and bn > 32:
+        if out_f16 and bn % 64:
+            continue
+        if bn >= 2 * cout and bn > (64 if out_f16 else 32):
             continue
         tiles = m_tiles * (-(-cout // bn)) * batch
         cost = (-(-tiles // 148)) * (128 + bn)
@@ -159,14 +170,19 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
               relu=False, tile=None, block_n=None, cout=None, k=None, batch=1, a_c_off=0,
               a_n_off=0, b_k_off=0, b_n_off=0, out_c_off=0, out_n_off=0, res_c_off=0, res_n_off=0, bias_z_off=0,
               max_ctas=0, stream_k=None, out_hw=None, n_img=None):
-    """out[n,h,w,:] = act(scale * conv(a, w) + bias + residual)   (TF32 tensor cores)
+    """out[n,h,w,:] = act(scale * conv(a, w) + bias + residual)   (tcgen05 tensor cores, fp32 accumulate)
 
-    a   : [N,H,W,C] fp32 view (innermost stride 1; other strides multiples of 4 floats)
-    w   : [taps, rows, K] fp32 (K contiguous)
-    out : [N,Ho,Wo,>=cout] fp32 view (innermost stride 1)
+    a   : [N,H,W,C] fp32 or fp16 view (innermost stride 1; other strides multiples of 16 bytes)
+    w   : [taps, rows, K] same dtype as a (K contiguous)
+    out : [N,Ho,Wo,>=cout] fp32 view, or fp16 when a is fp16 (innermost stride 1); residual: same dtype as out
+    fp32 operands run as TF32 (or the 3xTF32 split under ops.precision("fp32x3")), fp16 operands as kind::f16.
     """
     require_cuda(a, w, out, scale, bias, residual)
-    assert a.dtype == torch.float32 and w.dtype == torch.float32 and out.dtype == torch.float32
+    f16 = a.dtype == torch.float16
+    assert a.dtype == w.dtype and a.dtype in (torch.float32, torch.float16), (a.dtype, w.dtype)
+    assert out.dtype == torch.float32 or (f16 and out.dtype == torch.float16), (a.dtype, out.dtype)
+    assert residual is None or residual.dtype == out.dtype
+    out_f16 = out.dtype == torch.float16
     assert a.dim() == 4 and w.dim() == 3 and out.dim() == 4
     assert a.stride(3) == 1 and w.stride(2) == 1 and out.stride(3) == 1
     n, h, wd, c = a.shape
@@ -197,9 +213,11 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.tile_h, d.tile_w = th, tw
     m_tiles = d.n_img * (-(-oh // th)) * (-(-ow // tw))
     d.batch = batch
-    kb_per_tile = taps[0] * taps[1] * (-(-d.k_per_tap // 32))
-    d.precision = PRECISION[0]
-    auto_bn, auto_sk = pick_config(d.cout, m_tiles, batch, kb_per_tile)
+    kb_per_tile = taps[0] * taps[1] * (-(-d.k_per_tap // (64 if f16 else 32)))
+    d.precision = 2 if f16 else PRECISION[0]
+    d.out_f16 = 1 if out_f16 else 0
+    d.pdl = 1 if PDL[0] else 0
+    auto_bn, auto_sk = pick_config(d.cout, m_tiles, batch, kb_per_tile, out_f16)
     if d.precision == 1:
         auto_bn = 64 if d.cout <= 64 else 128
         if block_n not in (None, 64, 128):
@@ -315,11 +333,13 @@ def roi_align_nchw(inp, rois, scale, ph, pw, sampling_ratio, out=None):
 
 
 def roi_align_nhwc(feat, boxes, roi_batch, scale, ph, pw, sampling_ratio, out):
-    """feat [N,H,W,C]; boxes [K,4]; roi_batch int32 [K] or None; out [K, ph*pw*C]."""
+    """feat [N,H,W,C] fp32 or fp16; boxes [K,4]; roi_batch int32 [K] or None; out [K, ph*pw*C] (dtype of feat)."""
     require_cuda(feat, boxes, roi_batch, out)
     n, h, w, c = feat.shape
     k = boxes.shape[0]
-    check(lib.mega_roi_align_forward_nhwc(ptr(feat), c, h, w, feat.stride(0), ptr(boxes), boxes.stride(0), 0,
+    assert out.dtype == feat.dtype
+    fn = lib.mega_roi_align_forward_nhwc_f16 if feat.dtype == torch.float16 else lib.mega_roi_align_forward_nhwc
+    check(fn(ptr(feat), c, h, w, feat.stride(0), ptr(boxes), boxes.stride(0), 0,
                                           ptr(roi_batch), k, float(scale), ph, pw, sampling_ratio, ptr(out),
                                           out.stride(0), stream_ptr()), "mega_roi_align_forward_nhwc")
     LAUNCHES[0] += 1
@@ -327,10 +347,12 @@ def roi_align_nhwc(feat, boxes, roi_batch, scale, ph, pw, sampling_ratio, out):
 
 
 def stem_im2col(img, out, kpad=160):
+    """img fp32 NCHW -> im2col rows, fp32 or fp16 by out.dtype"""
     require_cuda(img, out)
     n, c, h, w = img.shape
-    assert c == 3 and img.is_contiguous()
-    check(lib.mega_stem_im2col(ptr(img), n, h, w, kpad, ptr(out), stream_ptr()), "mega_stem_im2col")
+    assert c == 3 and img.is_contiguous() and img.dtype == torch.float32
+    fn = lib.mega_stem_im2col_f16 if out.dtype == torch.float16 else lib.mega_stem_im2col
+    check(fn(ptr(img), n, h, w, kpad, ptr(out), stream_ptr()), "mega_stem_im2col")
     LAUNCHES[0] += 1
     return out
 
@@ -338,14 +360,24 @@ def stem_im2col(img, out, kpad=160):
 def maxpool3x3s2(x, out):
     require_cuda(x, out)
     n, h, w, c = x.shape
-    check(lib.mega_maxpool3x3s2_nhwc(ptr(x), n, h, w, c, ptr(out), stream_ptr()), "mega_maxpool3x3s2_nhwc")
+    assert x.dtype == out.dtype
+    fn = lib.mega_maxpool3x3s2_nhwc_f16 if x.dtype == torch.float16 else lib.mega_maxpool3x3s2_nhwc
+    check(fn(ptr(x), n, h, w, c, ptr(out), stream_ptr()), "mega_maxpool3x3s2_nhwc")
     LAUNCHES[0] += 1
     return out
 
 
+def _as_f32_rows(t):
+    """rows of fp16 features are moved as rows of half as many 32-bit words"""
+    return t.view(torch.float32) if t.dtype == torch.float16 else t
+
+
 def gather_rows(src, idx, dst, n_rows=None, row_len=None):
     require_cuda(src, idx, dst)
-    assert idx.dtype == torch.int32
+    assert idx.dtype == torch.int32 and src.dtype == dst.dtype
+    if src.dtype == torch.float16:
+        assert row_len is None
+        src, dst = _as_f32_rows(src), _as_f32_rows(dst)
     n_rows = idx.numel() if n_rows is None else n_rows
     row_len = src.shape[-1] if row_len is None else row_len
     check(lib.mega_gather_rows(ptr(src), src.stride(-2), ptr(idx), n_rows, row_len, ptr(dst), dst.stride(-2),
@@ -357,6 +389,10 @@ def gather_rows(src, idx, dst, n_rows=None, row_len=None):
 def copy_rows(src, dst, n_rows, row_len=None, src_idx=None, dst_idx=None):
     """dst[dst_idx[i]] = src[src_idx[i]] for i < n_rows (either index optional); 2-D row views."""
     require_cuda(src, dst, src_idx, dst_idx)
+    assert src.dtype == dst.dtype
+    if src.dtype == torch.float16:
+        assert row_len is None
+        src, dst = _as_f32_rows(src), _as_f32_rows(dst)
     row_len = src.shape[-1] if row_len is None else row_len
     check(lib.mega_copy_rows(ptr(src), src.stride(-2), ptr(src_idx), ptr(dst), dst.stride(-2), ptr(dst_idx), n_rows,
                              row_len, stream_ptr()), "mega_copy_rows")
@@ -372,11 +408,18 @@ def transpose_2d(x, out, n_img, rows, cols):
 
 
 def relation_softmax(logits, n_rows, ldm, scale, boxes_q=None, boxes_k=None, wg=None, bg=None, dim_mat=None,
-                     m_valid=None, m_host=0, n_valid=None, n_valid_off=0):
-    require_cuda(logits, boxes_q, boxes_k, wg, bg, dim_mat, m_valid, n_valid)
-    check(lib.mega_relation_softmax(ptr(logits), n_rows, ldm, ptr(boxes_q), ptr(boxes_k), ptr(wg), ptr(bg),
-                                    ptr(dim_mat), ptr(m_valid), m_host, ptr(n_valid), n_valid_off, float(scale),
-                                    stream_ptr()), "mega_relation_softmax")
+                     m_valid=None, m_host=0, n_valid=None, n_valid_off=0, probs_f16=None):
+    """in place over fp32 logits [16, n_rows, ldm]; with probs_f16 (fp16, same shape) the probabilities go there"""
+    require_cuda(logits, boxes_q, boxes_k, wg, bg, dim_mat, m_valid, n_valid, probs_f16)
+    if probs_f16 is not None:
+        assert probs_f16.dtype == torch.float16
+        check(lib.mega_relation_softmax_f16(ptr(logits), ptr(probs_f16), n_rows, ldm, ptr(boxes_q), ptr(boxes_k),
+                                            ptr(wg), ptr(bg), ptr(dim_mat), ptr(m_valid), m_host, ptr(n_valid),
+                                            n_valid_off, float(scale), stream_ptr()), "mega_relation_softmax_f16")
+    else:
+        check(lib.mega_relation_softmax(ptr(logits), n_rows, ldm, ptr(boxes_q), ptr(boxes_k), ptr(wg), ptr(bg),
+                                        ptr(dim_mat), ptr(m_valid), m_host, ptr(n_valid), n_valid_off, float(scale),
+                                        stream_ptr()), "mega_relation_softmax")
     LAUNCHES[0] += 1
     return logits
 

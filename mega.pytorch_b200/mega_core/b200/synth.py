@@ -75,7 +75,7 @@ def _linear(sd, p, nout, nin, gen, std=None, gain=1.0):
 
 def make_state_dict(arch="mega_r101", seed=0, num_classes=31):
     """state_dict with the reference's key names/shapes for
-    arch in {"mega_r101", "mega_r50", "base_r50", "base_r101"} (+ "_tiny" suffix: 1 block per stage,
+    arch in {"mega_r101", "mega_r50", "rdn_r101", "rdn_r50", "base_r50", "base_r101"} (+ "_tiny" suffix: 1 block per stage,
     for fast CPU tests)."""
     gen = torch.Generator().manual_seed(seed)
     tiny = arch.endswith("_tiny")
@@ -105,6 +105,19 @@ def make_state_dict(arch="mega_r101", seed=0, num_classes=31):
         sd[fe + "conv.bias"] = torch.zeros(256)
         _linear(sd, fe + "fc6.", 1024, 256 * 49, gen)
         _linear(sd, fe + "fc7.", 1024, 1024, gen)
+    elif method == "rdn":
+        # RDNFeatureExtractor with ATTENTION.STAGE = 2, ADVANCED_STAGE = 1 (configs/RDN/vid_R_101_C4_RDN_1x.yaml):
+        # fcs[0..2], Wgs/Wqs/Wks/Wvs[0..3] (roi_box_feature_extractors.py:305-328)
+        _linear(sd, fe + "fcs.0.", 1024, 2048 * 49, gen)
+        for i in (1, 2):
+            _linear(sd, fe + "fcs.%d." % i, 1024, 1024, gen)
+        for i in range(4):
+            sd[fe + "Wgs.%d.weight" % i] = torch.randn(16, 64, 1, 1, generator=gen) * 0.2
+            sd[fe + "Wgs.%d.bias" % i] = torch.rand(16, generator=gen) * 0.5
+            _linear(sd, fe + "Wqs.%d." % i, 1024, 1024, gen)
+            _linear(sd, fe + "Wks.%d." % i, 1024, 1024, gen)
+            sd[fe + "Wvs.%d.weight" % i] = torch.randn(1024, 1024, 1, 1, generator=gen) * (0.5 / 32)
+            sd[fe + "Wvs.%d.bias" % i] = torch.randn(1024, generator=gen) * 0.01
     else:
         _linear(sd, fe + "l_fcs.0.", 1024, 2048 * 49, gen)
         for i in (1, 2):

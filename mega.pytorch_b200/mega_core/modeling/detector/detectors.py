@@ -1,9 +1,10 @@
 """build_detection_model(cfg) keyed by cfg.MODEL.META_ARCHITECTURE (detector/detectors.py:9-18)."""
 import os
 
-from .generalized_rcnn import GeneralizedRCNN, GeneralizedRCNNMEGA
+from .generalized_rcnn import GeneralizedRCNN, GeneralizedRCNNMEGA, GeneralizedRCNNRDN
 
-_DETECTION_META_ARCHITECTURES = {"GeneralizedRCNN": GeneralizedRCNN, "GeneralizedRCNNMEGA": GeneralizedRCNNMEGA}
+_DETECTION_META_ARCHITECTURES = {"GeneralizedRCNN": GeneralizedRCNN, "GeneralizedRCNNMEGA": GeneralizedRCNNMEGA,
+                                 "GeneralizedRCNNRDN": GeneralizedRCNNRDN}
 
 
 def build_detection_model(cfg):
@@ -26,6 +27,11 @@ def vid_config(method="mega", conv_body="R-101-C4", device="cuda"):
         c.merge_from_dict({"MODEL": {"META_ARCHITECTURE": "GeneralizedRCNNMEGA",
                                      "VID": {"METHOD": "mega", "ROI_BOX_HEAD": {"ATTENTION": {"ENABLE": True, "STAGE": 3}}},
                                      "ROI_BOX_HEAD": {"FEATURE_EXTRACTOR": "MEGAFeatureExtractor"}}})
+    elif method == "rdn":     # configs/RDN/vid_R_101_C4_RDN_1x.yaml
+        c.merge_from_dict({"MODEL": {"META_ARCHITECTURE": "GeneralizedRCNNRDN",
+                                     "VID": {"METHOD": "rdn", "IGNORE": True,
+                                             "ROI_BOX_HEAD": {"ATTENTION": {"ENABLE": True, "STAGE": 2, "ADVANCED_STAGE": 1}}},
+                                     "ROI_BOX_HEAD": {"FEATURE_EXTRACTOR": "RDNFeatureExtractor"}}})
     elif method == "base":
         c.merge_from_dict({"MODEL": {"META_ARCHITECTURE": "GeneralizedRCNN",
                                      "VID": {"METHOD": "base", "ROI_BOX_HEAD": {"REDUCE_CHANNEL": True}},
@@ -35,13 +41,15 @@ def vid_config(method="mega", conv_body="R-101-C4", device="cuda"):
     return c
 
 
-def build_detection_model_from_state_dict(sd, method="mega", device="cuda"):
+def build_detection_model_from_state_dict(sd, method="mega", device="cuda", precision=None):
     """convenience for benchmarks/tests: infer the conv body from the state dict, build, load, eval"""
     n3 = 0
     while ("backbone.body.layer3.%d.conv1.weight" % n3) in sd:
         n3 += 1
     body = {6: "R-50-C4", 23: "R-101-C4"}.get(n3)
     cfg = vid_config(method, body or "R-101-C4", device)
+    if precision is not None:
+        cfg.MODEL.B200.PRECISION = precision
     if method == "base" and "roi_heads.box.feature_extractor.conv.weight" not in sd:
         cfg.MODEL.VID.ROI_BOX_HEAD.REDUCE_CHANNEL = False
     model = build_detection_model(cfg)

@@ -2,6 +2,7 @@
 
 GeneralizedRCNN       -- detector/generalized_rcnn.py:16-65 (single frame)
 GeneralizedRCNNMEGA   -- detector/generalized_rcnn_mega.py:21-225 (per-video state machine)
+GeneralizedRCNNRDN    -- detector/generalized_rcnn_rdn.py:20-190 (per-video state machine, 37-frame window)
 
 `forward(images)` returns `list[BoxList]` (fields `scores`, `labels`) exactly like the reference in
 eval mode; the arithmetic runs in the B200 engine built lazily from this module's own state_dict
@@ -128,3 +129,33 @@ class GeneralizedRCNNMEGA(_EngineBacked):
                 img = img[0]
             frames.append(img.view(1, *img.shape))
         return frames
+
+
+class GeneralizedRCNNRDN(GeneralizedRCNNMEGA):
+    engine_cls = _engine.RdnEngine
+
+    def forward(self, images, targets=None):
+        """images: the dict VIDRDNDataset._get_test builds (data/datasets/vid_rdn.py): cur, ref (one look-ahead
+        frame for frame_category 1), frame_category, seg_len, pattern, img_dir, transforms; optional `lookahead`
+        (list of 18 pre-staged frames) replaces the disk reads of frame 0 (generalized_rcnn_rdn.py:154-164)."""
+        if self.training:
+            raise NotImplementedError("the B200 build covers inference (eval mode) only")
+        if targets is not None:
+            raise ValueError("In testing mode, targets should be None")
+        cur = to_image_list(images["cur"])
+        im_h, im_w = cur.image_sizes[0]
+        eng = self.engine
+        with torch.no_grad():
+            if images["frame_category"] == 0:
+                self.seg_len, self.end_id = images["seg_len"], 0
+                look = images.get("lookahead")
+                if look is None:
+                    look = self._read_lookahead(images, eng.L - eng.cfg.key_frame_location - 1)
+                det = eng.start_video(self._dev(cur), [self._dev(x) for x in look], im_w, im_h)
+            else:
+                self.end_id = min(getattr(self, "end_id", 0) + 1, getattr(self, "seg_len", 1) - 1)
+                assert len(images["ref"]) == 1, "steady-state frames carry one look-ahead frame"
+                buf = eng.static_input((1,) + tuple(cur.tensors.shape[1:]))
+                buf[0].copy_(self._host(images["ref"][0]), non_blocking=True)
+                det = eng.step(buf, im_w, im_h)
+        return [self._to_boxlist(det, im_w, im_h)]

@@ -7,6 +7,8 @@ l_Wqs, l_Wks, l_Wvs, l_us, g_Wqs, g_Wks, g_Wvs, g_us}, roi_heads.box.predictor.{
 (reference: modeling/backbone/resnet.py, rpn/rpn.py, roi_heads/box_head/*). The torch modules below
 only HOLD the tensors; all arithmetic runs in the B200 engine (mega_core/b200/engine.py).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -160,6 +162,28 @@ class MEGAFeatureExtractor(nn.Module):
         self.out_channels = dim
 
 
+@registry.ROI_BOX_FEATURE_EXTRACTORS.register("RDNFeatureExtractor")
+class RDNFeatureExtractor(nn.Module):
+    """parameters of roi_box_feature_extractors.py:254-330 (fcs, Wgs, Wqs, Wks, Wvs; no `u`)"""
+
+    def __init__(self, cfg, in_channels):
+        super().__init__()
+        self.head = ResNetHead(cfg.MODEL.RESNETS.RES5_DILATION)
+        self.conv = None
+        res = cfg.MODEL.ROI_BOX_HEAD.POOLER_RESOLUTION
+        dim = cfg.MODEL.ROI_BOX_HEAD.MLP_HEAD_DIM
+        att = cfg.MODEL.VID.ROI_BOX_HEAD.ATTENTION
+        emb, grp, base, adv = att.EMBED_DIM, att.GROUP, att.STAGE, att.ADVANCED_STAGE
+        n_att = base if adv == 0 else base + adv + 1
+        n_fc = base if adv == 0 else base + adv
+        self.fcs = nn.ModuleList([_fc(2048 * res * res if i == 0 else dim, dim) for i in range(n_fc)])
+        self.Wgs = nn.ModuleList([nn.Conv2d(emb, grp, 1) for _ in range(n_att)])
+        self.Wqs = nn.ModuleList([_fc(dim, dim) for _ in range(n_att)])
+        self.Wks = nn.ModuleList([_fc(dim, dim) for _ in range(n_att)])
+        self.Wvs = nn.ModuleList([nn.Conv2d(dim * grp, dim, 1, groups=grp) for _ in range(n_att)])
+        self.out_channels = dim
+
+
 @registry.ROI_BOX_PREDICTOR.register("FPNPredictor")
 class FPNPredictor(nn.Module):
     def __init__(self, cfg, in_channels):
@@ -203,10 +227,12 @@ def build_roi_heads(cfg, in_channels):
 def engine_config_from(cfg):
     m = cfg.MODEL
     v = m.VID
+    win = v.RDN if v.METHOD == "rdn" else v.MEGA            # window geometry of the method
     return _engine.EngineConfig(
         pre_nms_top_n=m.RPN.PRE_NMS_TOP_N_TEST, post_nms_top_n=m.RPN.POST_NMS_TOP_N_TEST,
         ref_post_nms_top_n=v.RPN.REF_POST_NMS_TOP_N, rpn_nms_thresh=m.RPN.NMS_THRESH, rpn_min_size=m.RPN.MIN_SIZE,
-        ratio=v.MEGA.RATIO, all_frame_interval=v.MEGA.ALL_FRAME_INTERVAL, key_frame_location=v.MEGA.KEY_FRAME_LOCATION,
+        ratio=win.RATIO, all_frame_interval=win.ALL_FRAME_INTERVAL, key_frame_location=win.KEY_FRAME_LOCATION,
+        advanced_stage=v.ROI_BOX_HEAD.ATTENTION.ADVANCED_STAGE,
         memory_size=v.MEGA.MEMORY.SIZE, global_size=v.MEGA.GLOBAL.SIZE, global_res_stage=v.MEGA.GLOBAL.RES_STAGE,
         stage=v.ROI_BOX_HEAD.ATTENTION.STAGE, groups=v.ROI_BOX_HEAD.ATTENTION.GROUP,
         pooler_resolution=m.ROI_BOX_HEAD.POOLER_RESOLUTION, pooler_scale=m.ROI_BOX_HEAD.POOLER_SCALES[0],
@@ -214,4 +240,5 @@ def engine_config_from(cfg):
         score_thresh=m.ROI_HEADS.SCORE_THRESH, nms_thresh=m.ROI_HEADS.NMS, detections_per_img=m.ROI_HEADS.DETECTIONS_PER_IMG,
         bbox_reg_weights=tuple(m.ROI_HEADS.BBOX_REG_WEIGHTS), anchor_sizes=tuple(m.RPN.ANCHOR_SIZES),
         aspect_ratios=tuple(m.RPN.ASPECT_RATIOS), anchor_stride=m.RPN.ANCHOR_STRIDE[0],
-        num_classes=m.ROI_BOX_HEAD.NUM_CLASSES)
+        num_classes=m.ROI_BOX_HEAD.NUM_CLASSES,
+        precision=os.environ.get("MEGA_B200_PRECISION", m.B200.PRECISION if "B200" in m else "f16"))

@@ -232,6 +232,61 @@ def golden_mega(h=192, w=320, n_frames=4, total=40):
             "frames": gold}
 
 
+def run_reference_rdn(sd, frames, n_frames):
+    cfg = ref_import.build_cfg("configs/RDN/vid_R_101_C4_RDN_1x.yaml")
+    from mega_core.modeling.detector import build_detection_model
+    from mega_core.structures.image_list import to_image_list
+    import mega_core.modeling.detector.generalized_rcnn_rdn as gr
+    model = build_detection_model(cfg).eval()
+    full = dict(sd)
+    full["rpn.anchor_generator.cell_anchors.0"] = model.state_dict()["rpn.anchor_generator.cell_anchors.0"]
+    model.load_state_dict(full, strict=True)
+    gr.Image = types.SimpleNamespace(open=lambda path: _FakeImage(int(os.path.basename(path).split(".")[0])))
+    outs, hooks = [], {}
+    pred = model.roi_heads.box.predictor
+    orig_pred = pred.forward
+
+    def pred_fwd(x):
+        r = orig_pred(x)
+        hooks["class_logits"], hooks["box_regression"] = r[0].clone(), r[1].clone()
+        return r
+
+    pred.forward = pred_fwd
+    with torch.no_grad():
+        for t in range(n_frames):
+            images = {"cur": frames[t][0].clone(),
+                      "ref": [] if t == 0 else [to_image_list(frames[min(t + 18, len(frames) - 1)][0].clone())],
+                      "frame_category": 0 if t == 0 else 1, "seg_len": len(frames), "pattern": "%06d",
+                      "img_dir": "/nonexistent/%s.JPEG", "transforms": lambda im: frames[im.idx][0].clone()}
+            res = model(images)[0]
+            outs.append({"boxes": res.bbox.clone(), "scores": res.get_field("scores").clone(),
+                         "labels": res.get_field("labels").clone(), **{k: v for k, v in hooks.items()}})
+    return outs
+
+
+def golden_rdn(h=192, w=320, n_frames=3, total=40):
+    print("  RDN R-101 @%dx%d: reference vs oracle, %d frames" % (h, w, n_frames))
+    sd = synth.make_state_dict("rdn_r101", seed=4)
+    frames = [synth.synthetic_frame(i, h, w) for i in range(total)]
+    ref = run_reference_rdn(sd, frames, n_frames)
+    orc = mo.RdnOracle(sd, record=True)
+    gold = []
+    for t in range(n_frames):
+        infos = {"frame_category": 0 if t == 0 else 1, "ref": frames[1:19] if t == 0 else [frames[min(t + 18, total - 1)]]}
+        b, s, l = orc.forward(frames[t], infos)
+        r = ref[t]
+        assert r["class_logits"].shape == orc.trace["class_logits"].shape, "proposal count differs"
+        close(orc.trace["class_logits"], r["class_logits"], 2e-5, "frame %d class_logits" % t)
+        close(orc.trace["box_regression"], r["box_regression"], 2e-5, "frame %d box_regression" % t)
+        assert torch.equal(l, r["labels"]) and b.shape == r["boxes"].shape, "detections differ (frame %d)" % t
+        close(b, r["boxes"], 1e-4, "frame %d det boxes" % t)
+        close(s, r["scores"], 1e-5, "frame %d det scores" % t)
+        gold.append({"class_logits": r["class_logits"], "box_regression": r["box_regression"],
+                     "proposals": orc.trace["proposals"], "boxes": r["boxes"], "scores": r["scores"],
+                     "labels": r["labels"]})
+    return {"arch": "rdn_r101", "seed": 4, "h": h, "w": w, "total": total, "frames": gold}
+
+
 def golden_base(h=192, w=320):
     print("  single-frame R-50-C4 @%dx%d: reference vs oracle" % (h, w))
     cfg = ref_import.build_cfg("configs/vid_R_50_C4_1x.yaml")
@@ -268,6 +323,10 @@ def golden_base(h=192, w=320):
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(8)
+    only = set(sys.argv[1:])
+    if "rdn" in only:
+        torch.save(golden_rdn(), os.path.join(GOLD, "rdn_r101_192x320.pt"))
+        return
     print("[1] reference unit-test vectors")
     torch.save(golden_from_reference_tests(), os.path.join(GOLD, "reference_unit_vectors.pt"))
     print("[2] op-level reference outputs")
@@ -275,6 +334,7 @@ def main():
     print("[3] end-to-end")
     torch.save(golden_base(), os.path.join(GOLD, "base_r50_192x320.pt"))
     torch.save(golden_mega(), os.path.join(GOLD, "mega_r101_192x320.pt"))
+    torch.save(golden_rdn(), os.path.join(GOLD, "rdn_r101_192x320.pt"))
     for f in sorted(os.listdir(GOLD)):
         print("  wrote", f, os.path.getsize(os.path.join(GOLD, f)), "bytes")
 

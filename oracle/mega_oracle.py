@@ -548,6 +548,93 @@ class BaseOracle:
                                c.detections_per_img, cuda_semantics=c.cuda_nms_semantics)
 
 
+class RdnOracle:
+    """GeneralizedRCNNRDN._forward_test (detector/generalized_rcnn_rdn.py:108-190) + RDNFeatureExtractor test path
+    (roi_heads/box_head/roi_box_feature_extractors.py:412-454, base attention module :178-238, no `u` term), restated.
+    Window of cfg.all_frame_interval (37) frames, key frame at cfg.key_frame_location (18); per frame the 75 "ref"
+    proposals and their fcs[0] features are cached (update_feature :116-131). Frame 0's look-ahead frames are passed
+    in infos["ref"] (a list of tensors) instead of being read from disk (:154-164)."""
+
+    def __init__(self, state_dict, cfg=None, record=False, base_stage=2, advanced_stage=1):
+        self.sd = {k: v.detach().float() for k, v in state_dict.items()}
+        self.cfg = cfg or Cfg(all_frame_interval=37, key_frame_location=18)
+        self.base_stage, self.advanced_stage = base_stage, advanced_stage
+        self.record = record
+        self.trace = {}
+
+    def _pool(self, feats, boxes):
+        c = self.cfg
+        x = res5_head(feats, self.sd, FE + "head.", c.res5_dilation)
+        rois = torch.cat([torch.zeros(boxes.shape[0], 1), boxes], dim=1)
+        x = roi_align(x, rois, c.pooler_scale, c.pooler_resolution, c.pooler_resolution, c.sampling_ratio)
+        return x.flatten(start_dim=1)
+
+    def _fc(self, i, x):
+        return F.relu(F.linear(x, self.sd[FE + "fcs.%d.weight" % i], self.sd[FE + "fcs.%d.bias" % i]))
+
+    def _ref_branch(self, img):
+        c = self.cfg
+        feats = resnet_c4_body(img, self.sd)
+        im_h, im_w = img.shape[-2:]
+        logits, deltas = rpn_head(feats, self.sd)
+        boxes, _ = rpn_select(logits, deltas, im_w, im_h, c.pre_nms_top_n, c.ref_post_nms_top_n, c.rpn_nms_thresh,
+                              cuda_semantics=c.cuda_nms_semantics)
+        return feats, boxes, self._fc(0, self._pool(feats, boxes))        # _forward_ref (:400-410)
+
+    def forward(self, img, infos):
+        c = self.cfg
+        im_h, im_w = img.shape[-2:]
+        L = c.all_frame_interval
+        if infos["frame_category"] == 0:
+            self.q_feats, self.q_boxes, self.q_pfeat = deque(maxlen=L), deque(maxlen=L), deque(maxlen=L)
+            cur = self._ref_branch(img)
+            while len(self.q_feats) < c.key_frame_location + 1:
+                for q, v in zip((self.q_feats, self.q_boxes, self.q_pfeat), cur):
+                    q.append(v)
+            for im in infos["ref"]:
+                if len(self.q_feats) >= L:
+                    break
+                for q, v in zip((self.q_feats, self.q_boxes, self.q_pfeat), self._ref_branch(im)):
+                    q.append(v)
+            assert len(self.q_feats) == L
+        else:
+            for q, v in zip((self.q_feats, self.q_boxes, self.q_pfeat), self._ref_branch(infos["ref"][0])):
+                q.append(v)
+        feats = self.q_feats[c.key_frame_location]
+        logits, deltas = rpn_head(feats, self.sd)
+        prop, obj = rpn_select(logits, deltas, im_w, im_h, c.pre_nms_top_n, c.post_nms_top_n, c.rpn_nms_thresh,
+                               cuda_semantics=c.cuda_nms_semantics)
+        rois_ref = torch.cat(list(self.q_boxes), 0)
+        x_refs = torch.cat(list(self.q_pfeat), 0)
+        # ---- RDNFeatureExtractor._forward_test (:412-454)
+        x = self._pool(feats, prop)
+        pe = position_embedding(prop, rois_ref)
+        for i in range(self.base_stage):
+            x = self._fc(i, x)
+            x = x + relation_attention(self.sd, FE, "", i, x, x_refs, pe, c.groups, u_term=False)
+        if self.advanced_stage > 0:
+            a, b = c.advanced_num, c.ref_post_nms_top_n
+            x_adv = torch.cat([t[:a] for t in torch.split(x_refs, b, dim=0)], 0)
+            rois_adv = torch.cat([t[:a] for t in torch.split(rois_ref, b, dim=0)], 0)
+            pe_adv = torch.cat([t[..., :a] for t in torch.split(pe, b, dim=-1)], -1)
+            pe2 = position_embedding(rois_adv, rois_ref)
+            for i in range(self.advanced_stage):
+                x_adv = x_adv + relation_attention(self.sd, FE, "", i + self.base_stage, x_adv, x_refs, pe2, c.groups,
+                                                   u_term=False)
+                x_adv = self._fc(i + self.base_stage, x_adv)
+            x = x + relation_attention(self.sd, FE, "", self.base_stage + self.advanced_stage, x, x_adv, pe_adv,
+                                       c.groups, u_term=False)
+        logits = F.linear(x, self.sd["roi_heads.box.predictor.cls_score.weight"],
+                          self.sd["roi_heads.box.predictor.cls_score.bias"])
+        bdelta = F.linear(x, self.sd["roi_heads.box.predictor.bbox_pred.weight"],
+                          self.sd["roi_heads.box.predictor.bbox_pred.bias"])
+        if self.record:
+            self.trace = {"proposals": prop.clone(), "x_final": x.clone(), "class_logits": logits.clone(),
+                          "box_regression": bdelta.clone()}
+        return box_postprocess(logits, bdelta, prop, im_w, im_h, c.score_thresh, c.nms_thresh,
+                               c.detections_per_img, cuda_semantics=c.cuda_nms_semantics)
+
+
 # --------------------------------------------------------------------------- ops outside the VID configs
 def sigmoid_focal_loss(logits, targets, gamma, alpha):
     """layers/sigmoid_focal_loss.py:40-50 (the reference's own CPU formula for RetinaNet's focal loss)."""

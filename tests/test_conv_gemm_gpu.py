@@ -141,3 +141,98 @@ def test_fp32x3_split_precision(cuda_dev, bn, sk):
     torch.cuda.synchronize()
     err = _rel_err(out.permute(0, 3, 1, 2), ref)
     assert err < 5e-5, err
+
+
+# ------------------------------------------------------------------ fp16-operand mode (kind::f16)
+def _f16_conv_case(dev, n, h, w, cin, cout, ks, dil, relu, use_res, out16, seed, block_n=None, stream_k=None, tile=None):
+    """operands rounded to fp16 up front, so the fp64 reference isolates the kernel's own error:
+    fp32 accumulation (<= 1e-5 x RMS) plus, for fp16 outputs, one final rounding (2^-11 relative)."""
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g).half()
+    wt = (torch.randn(cout, cin, ks, ks, generator=g) / (cin * ks * ks) ** 0.5).half()
+    scale = torch.rand(cout, generator=g) + 0.5
+    bias = torch.randn(cout, generator=g)
+    res = torch.randn(n, cout, h, w, generator=g).half() if use_res else None
+    pad = dil * (ks - 1) // 2
+    ref = F.conv2d(x.double(), wt.double(), None, 1, pad, dil) * scale.double().view(1, -1, 1, 1) + bias.double().view(1, -1, 1, 1)
+    if use_res:
+        ref = ref + res.double()
+    if relu:
+        ref = ref.relu()
+    a = x.permute(0, 2, 3, 1).contiguous().to(dev)
+    wp = wt.permute(2, 3, 0, 1).reshape(ks * ks, cout, cin).contiguous().to(dev)
+    out = torch.full((n, h, w, cout), float("nan"), device=dev, dtype=torch.float16 if out16 else torch.float32)
+    r = None
+    if use_res:
+        r = res.permute(0, 2, 3, 1).contiguous().to(dev)
+        if not out16:
+            r = r.float()
+            ref = ref   # same values (fp16-representable), passed as fp32
+    for _ in range(2):
+        ops.conv_gemm(a, wp, out, taps=(ks, ks), dil=dil, pad=pad, scale=scale.to(dev), bias=bias.to(dev),
+                      residual=r, relu=relu, block_n=block_n, stream_k=stream_k, tile=tile)
+    torch.cuda.synchronize()
+    got = out.float().permute(0, 3, 1, 2)
+    assert torch.isfinite(got).all(), "kernel left unwritten / non-finite outputs"
+    return _rel_err(got, ref.float())
+
+
+@pytest.mark.parametrize("case", [
+    # n, h, w, cin, cout, ks, dil, relu, res, out16, block_n, stream_k
+    (2, 38, 63, 1024, 256, 1, 1, True, False, True, None, None),
+    (2, 38, 63, 256, 256, 3, 1, True, False, True, 128, 0),
+    (2, 38, 63, 256, 1024, 1, 1, True, True, True, 256, 0),
+    (2, 38, 63, 256, 1024, 1, 1, True, True, True, 192, 1),
+    (1, 38, 63, 512, 512, 3, 2, True, False, True, 64, 1),
+    (1, 38, 63, 1024, 60, 1, 1, False, False, False, 64, 0),       # RPN head: fp16 operands, fp32 logits
+    (1, 19, 21, 96, 200, 3, 1, False, True, False, 96, 0),        # fp32 out + fp32 residual, odd tile width
+    (1, 75, 125, 160, 64, 1, 1, True, False, True, 64, 0),         # K tail (160 = 2.5 slabs of 64)
+])
+def test_f16_conv_matches_fp64(cuda_dev, case):
+    n, h, w, cin, cout, ks, dil, relu, res, out16, bn, sk = case
+    err = _f16_conv_case(cuda_dev, n, h, w, cin, cout, ks, dil, relu, res, out16, seed=hash(case) % 1000, block_n=bn,
+                         stream_k=sk)
+    assert err < (2e-3 if out16 else 2e-5), err
+
+
+def test_f16_linear_and_batched_heads(cuda_dev):
+    """l_fcs[0]-shaped GEMM (K = 100352, stream-K) and the per-head Q.K^T / P.V' batch offsets with fp16 operands"""
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(5)
+    m, k, n = 375, 100352, 1024
+    x = (torch.randn(m, k, generator=g)).half()
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).half()
+    b = torch.randn(n, generator=g)
+    xd, wd = x.to(cuda_dev), w.to(cuda_dev)
+    ref = (xd.double() @ wd.double().t() + b.to(cuda_dev).double()).relu().float().cpu()
+    out = torch.full((m, n), float("nan"), device=cuda_dev, dtype=torch.float16)
+    ops.linear(xd, wd, out, bias=b.to(cuda_dev), relu=True)
+    torch.cuda.synchronize()
+    assert _rel_err(out.float(), ref) < 2e-3
+    nq, mk, heads, dh = 300, 750, 16, 64
+    q = torch.randn(nq, heads * dh, generator=g).half()
+    kk = torch.randn(mk, heads * dh, generator=g).half()
+    ref = torch.einsum("ngd,mgd->gnm", q.view(nq, heads, dh).double(), kk.view(mk, heads, dh).double()).float()
+    mk_pad = 768
+    s = torch.zeros(heads, nq, mk_pad, device=cuda_dev)
+    ops.conv_gemm(q.to(cuda_dev).view(1, 1, nq, heads * dh), kk.to(cuda_dev).view(1, mk, heads * dh),
+                  s.view(heads, 1, nq, mk_pad), tile=(1, 128), cout=mk, k=dh, batch=heads, a_c_off=dh, b_k_off=dh,
+                  out_n_off=1, n_img=1)
+    torch.cuda.synchronize()
+    assert _rel_err(s[:, :, :mk], ref) < 2e-5
+    # P.V'^T with the residual / bias / channel-offset batching of the attention epilogue
+    p = torch.rand(heads, nq, mk_pad, generator=g).half()
+    p[:, :, mk:] = 0
+    vt = torch.randn(heads * dh, mk_pad, generator=g).half()
+    xq = torch.randn(nq, heads * dh, generator=g).half()
+    bv = torch.randn(heads * dh, generator=g)
+    ref = torch.einsum("gnm,gdm->ngd", p.double(), vt.view(heads, dh, mk_pad).double()).reshape(nq, heads * dh) \
+        + bv.double() + xq.double()
+    out = torch.full((nq, heads * dh), float("nan"), device=cuda_dev, dtype=torch.float16)
+    ops.conv_gemm(p.to(cuda_dev).view(heads, 1, nq, mk_pad), vt.to(cuda_dev).view(1, heads * dh, mk_pad),
+                  out.view(1, 1, nq, heads * dh), tile=(1, 128), cout=dh, k=mk_pad, batch=heads, a_n_off=1, b_n_off=dh,
+                  out_c_off=dh, res_c_off=dh, bias_z_off=dh, bias=bv.to(cuda_dev),
+                  residual=xq.to(cuda_dev).view(1, 1, nq, heads * dh), block_n=64)
+    torch.cuda.synchronize()
+    assert _rel_err(out.float(), ref.float()) < 2e-3

@@ -151,3 +151,79 @@ def test_mega_r101_fp32x3_product_path_matches_reference_fixture(cuda_dev):
         assert f["logits_maxabs"] < 1e-3, f
         assert f["deltas_maxabs"] < 1e-3, f
         assert f["dets"] == f["ref_dets"], f
+
+
+def test_mega_r101_f16_matches_reference_fixture(cuda_dev):
+    """The throughput mode (EngineConfig(precision="f16"): activations / weights of the GEMM chain stored in fp16,
+    kind::f16 tensor-core MMAs with fp32 accumulation). fp16 has the same 10-bit mantissa as TF32, so the same
+    statistical bounds as the TF32 test are asserted; the measured numbers land in gpurun_out/engine_parity.json."""
+    frames = _run_mega_against_fixture(cuda_dev, "mega_r101_f16", precision="f16")
+    for f in frames:
+        assert f["matched_frac"] >= 0.97, f
+        assert f["logits_maxabs"] < 8e-2, f
+        assert f["proposals"] == f["ref_proposals"], f
+
+
+def test_backbone_f16_matches_oracle(cuda_dev):
+    import mega_oracle as mo
+    from mega_core.b200 import engine, synth
+    sd = synth.make_state_dict("mega_r101_tiny", seed=2)
+    img = synth.synthetic_frame(1, 96, 160)
+    ref = mo.resnet_c4_body(img, sd)
+    bb = engine.Backbone({k: v for k, v in sd.items()}, cuda_dev, dtype=torch.float16)
+    got = bb.forward(img.to(cuda_dev)).float().permute(0, 3, 1, 2).cpu()
+    rel = ((got - ref).abs().max() / ref.pow(2).mean().sqrt()).item()
+    _METRICS["backbone_tiny_relerr_f16"] = rel
+    _dump()
+    assert rel < 2e-2, rel
+
+
+def _run_rdn_against_fixture(cuda_dev, label, precision):
+    from mega_core.b200 import engine, synth
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "rdn_r101_192x320.pt"))
+    h, w, total = gold["h"], gold["w"], gold["total"]
+    sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+    frames = [synth.synthetic_frame(i, h, w).to(cuda_dev) for i in range(total)]
+    eng = engine.RdnEngine(sd, engine.EngineConfig(all_frame_interval=37, key_frame_location=18, stage=2,
+                                                   advanced_stage=1, precision=precision), device=cuda_dev)
+    per_frame = []
+    for t, ref in enumerate(gold["frames"]):
+        if t == 0:
+            det = eng.start_video(frames[0], frames[1:19], w, h)
+        else:
+            det = eng.step(frames[min(t + 18, total - 1)], w, h)
+        torch.cuda.synchronize()
+        k = int(eng.cur_cnt.view(-1)[0].item())
+        props = eng.last_props[:k].cpu()
+        idx = _match_rows(props, ref["proposals"])
+        m = idx >= 0
+        pred = eng.last_pred[:k].cpu()
+        assert torch.isfinite(pred).all()
+        b, s, l = det.to_host()
+        per_frame.append({"proposals": k, "ref_proposals": int(ref["proposals"].shape[0]),
+                          "matched_frac": m.float().mean().item(),
+                          "logits_maxabs": (pred[idx[m], :31] - ref["class_logits"][m]).abs().max().item(),
+                          "deltas_maxabs": (pred[idx[m], 31:155] - ref["box_regression"][m]).abs().max().item(),
+                          "dets": int(b.shape[0]), "ref_dets": int(ref["boxes"].shape[0]),
+                          "logit_rms": ref["class_logits"].pow(2).mean().sqrt().item()})
+        _METRICS[label] = per_frame
+        _dump()
+    return per_frame
+
+
+def test_rdn_r101_strict_matches_reference_fixture(cuda_dev):
+    """RDN R-101 (BASELINE configs[3]) in the strict-parity arithmetic against the reference's outputs:
+    all proposals reproduced, class logits within 1e-3"""
+    for f in _run_rdn_against_fixture(cuda_dev, "rdn_r101_fp32x3", "fp32x3"):
+        assert f["matched_frac"] == 1.0, f
+        assert f["logits_maxabs"] < 1e-3, f
+        assert f["deltas_maxabs"] < 1e-3, f
+        assert f["dets"] == f["ref_dets"], f
+
+
+def test_rdn_r101_f16_matches_reference_fixture(cuda_dev):
+    """same in the throughput mode (fp16 operands): statistical bounds as for MEGA"""
+    for f in _run_rdn_against_fixture(cuda_dev, "rdn_r101_f16", "f16"):
+        assert f["matched_frac"] >= 0.97, f
+        assert f["logits_maxabs"] < 8e-2, f
+        assert f["proposals"] == f["ref_proposals"], f

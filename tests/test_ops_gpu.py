@@ -217,3 +217,65 @@ def test_box_postprocess_matches_oracle(cuda_dev):
         assert torch.equal(out[2][:n].cpu(), rl)
         assert torch.allclose(out[1][:n].cpu(), rs, rtol=0, atol=1e-6)    # 31-way softmax: exp + sum order
         assert torch.allclose(out[0][:n].cpu(), rb, rtol=0, atol=2e-3)
+
+
+def test_f16_variants_of_memory_bound_kernels(cuda_dev):
+    """fp16-storage variants used by the fp16-operand engine: same fp32 arithmetic as the fp32 kernels on
+    fp16-representable inputs, one rounding to fp16 at the store (exact for im2col / max-pool / row moves)."""
+    import torch.nn.functional as F
+    from mega_core.b200 import ops
+    mo = _oracle()
+    g = torch.Generator().manual_seed(11)
+    # ROIAlign: fp16 map in -> fp16 out == fp16(round) of the oracle on the same (fp16-valued) map
+    for c, h, w, k in ((2048, 38, 63, 75), (256, 20, 30, 40), (8, 13, 17, 9)):
+        feat = torch.randn(1, c, h, w, generator=g).half()
+        boxes = _rand_boxes(k, g, w * 16.0, h * 16.0, 1.0, w * 10.0)
+        boxes[0] = torch.tensor([-50.0, -60.0, 3000.0, 2000.0])
+        rois = torch.cat([torch.zeros(k, 1), boxes], 1)
+        ref = mo.roi_align(feat.float(), rois, 1.0 / 16, 7, 7, 0).half()
+        nhwc = feat.permute(0, 2, 3, 1).contiguous().to(cuda_dev)
+        out = torch.full((k, 49 * c), float("nan"), device=cuda_dev, dtype=torch.float16)
+        ops.roi_align_nhwc(nhwc, boxes.to(cuda_dev), None, 1.0 / 16, 7, 7, 0, out)
+        got = out.view(k, 49, c).permute(0, 2, 1).reshape(k, c, 7, 7).cpu()
+        assert torch.equal(got, ref), (got.float() - ref.float()).abs().max()
+    # stem im2col / max-pool
+    img = torch.randn(2, 3, 37, 53, generator=g)
+    col = torch.empty(2, 19 * 27, 160, device=cuda_dev, dtype=torch.float16)
+    ops.stem_im2col(img.to(cuda_dev), col)
+    ref = F.unfold(img, 7, padding=3, stride=2).transpose(1, 2).half()
+    assert torch.equal(col[:, :, :147].cpu(), ref) and (col[:, :, 147:] == 0).all()
+    x = torch.randn(2, 64, 21, 30, generator=g).half()
+    out = torch.empty(2, 11, 15, 64, device=cuda_dev, dtype=torch.float16)
+    ops.maxpool3x3s2(x.permute(0, 2, 3, 1).contiguous().to(cuda_dev), out)
+    assert torch.equal(out.permute(0, 3, 1, 2).cpu().float(), F.max_pool2d(x.float(), 3, 2, 1))
+    # row gathers over fp16 feature rows
+    src = torch.randn(50, 1024, generator=g).half()
+    idx = torch.tensor([3, 3, -1, 49, 0, 17], dtype=torch.int32)
+    dst = torch.full((6, 1024), 7.0, device=cuda_dev, dtype=torch.float16)
+    ops.gather_rows(src.to(cuda_dev), idx.to(cuda_dev), dst)
+    exp = src[idx.clamp_min(0).long()]
+    exp[2] = 0
+    assert torch.equal(dst.cpu(), exp)
+    # soft-max with fp16 probabilities: same values as the fp32 kernel, rounded once
+    n, m, ld = 37, 203, 224
+    bq, bk = _rand_boxes(n, g), _rand_boxes(m, g)
+    wg = torch.randn(16, 64, generator=g) * 0.2
+    bg = torch.rand(16, generator=g) * 0.5
+    aff = torch.randn(16, n, m, generator=g) * 8.0
+    dim_mat = torch.full((8,), 1000.0).pow(8.0 / 64 * torch.arange(0, 8, dtype=torch.float32))
+    mv = torch.tensor([m], dtype=torch.int32, device=cuda_dev)
+    outs = []
+    for use16 in (False, True):
+        s = torch.zeros(16, n, ld, device=cuda_dev)
+        s[:, :, :m] = aff.to(cuda_dev)
+        p16 = torch.full((16, n, ld), float("nan"), device=cuda_dev, dtype=torch.float16) if use16 else None
+        ops.relation_softmax(s, n, ld, 0.125, boxes_q=bq.to(cuda_dev), boxes_k=bk.to(cuda_dev), wg=wg.to(cuda_dev),
+                             bg=bg.to(cuda_dev), dim_mat=dim_mat.to(cuda_dev), m_valid=mv, probs_f16=p16)
+        outs.append((p16 if use16 else s).cpu())
+    assert torch.equal(outs[1], outs[0].half())
+    s = torch.zeros(16, n, ld, device=cuda_dev)
+    s[:, :, :m] = aff.to(cuda_dev)
+    p16 = torch.full((16, n, ld), float("nan"), device=cuda_dev, dtype=torch.float16)
+    ops.relation_softmax(s, n, ld, 0.125, m_host=m, probs_f16=p16)
+    assert (p16.float().cpu()[:, :, :m] - torch.softmax(aff * 0.125, dim=2)).abs().max() < 5e-4
+    assert (p16[:, :, m:] == 0).all()

@@ -116,3 +116,19 @@ def test_mega_r101_oracle_matches_reference_fixture():
         assert torch.allclose(orc.trace["class_logits"], ref["class_logits"], atol=1e-5)
         assert torch.equal(orc.trace["proposals"], ref["proposals"])
         assert torch.equal(l, ref["labels"]) and torch.allclose(b, ref["boxes"], atol=1e-4)
+
+
+def test_rdn_r101_oracle_matches_reference_fixture():
+    """2 frames of the unmodified reference's GeneralizedRCNNRDN (37-frame window, base stages + advanced stage)"""
+    synth = _synth()
+    gold = torch.load(os.path.join(GOLD, "rdn_r101_192x320.pt"))
+    h, w, total = gold["h"], gold["w"], gold["total"]
+    sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+    frames = [synth.synthetic_frame(i, h, w) for i in range(total)]
+    orc = mo.RdnOracle(sd, record=True)
+    for t, ref in enumerate(gold["frames"][:2]):
+        infos = {"frame_category": 0 if t == 0 else 1, "ref": frames[1:19] if t == 0 else [frames[min(t + 18, total - 1)]]}
+        b, s, l = orc.forward(frames[t], infos)
+        assert torch.allclose(orc.trace["class_logits"], ref["class_logits"], atol=1e-5)
+        assert torch.equal(orc.trace["proposals"], ref["proposals"])
+        assert torch.equal(l, ref["labels"]) and torch.allclose(b, ref["boxes"], atol=1e-4)
