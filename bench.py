@@ -308,7 +308,10 @@ def roofline_pass(eng, pairs_dev, w, h, reps=3):
         orig(d)
         b.record()
         m = d.n_img * d.out_h * d.out_w * d.batch
-        rec.append((a, b, 2.0 * m * d.cout * d.k_per_tap * d.taps_r * d.taps_s))
+        rec.append((a, b, 2.0 * m * d.cout * d.k_per_tap * d.taps_r * d.taps_s,
+                    {"m": d.n_img * d.out_h * d.out_w, "batch": d.batch, "cout": d.cout, "k": d.k_per_tap,
+                     "taps": d.taps_r * d.taps_s, "bn": d.block_n, "sk": d.stream_k, "res": bool(d.residual),
+                     "out16": d.out_f16}))
 
     ops._launch_conv_gemm = timed
     try:
@@ -323,8 +326,16 @@ def roofline_pass(eng, pairs_dev, w, h, reps=3):
     finally:
         ops._launch_conv_gemm = orig
         eng._graphs, eng.use_graph = saved_graphs, saved_flag
-    ms = sum(a.elapsed_time(b) for a, b, _ in rec) / reps
-    fl = sum(f for _, _, f in rec) / reps
+    ms = sum(r[0].elapsed_time(r[1]) for r in rec) / reps
+    fl = sum(r[2] for r in rec) / reps
+    try:        # per-launch table of the last eager frame (diagnostics; gpurun_out/ is scratch)
+        n = len(rec) // reps
+        rows = [dict(r[3], us=round(r[0].elapsed_time(r[1]) * 1e3, 2), gflop=round(r[2] / 1e9, 3)) for r in rec[-n:]]
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "launch_times.json"), "w") as fh:
+            json.dump(rows, fh)
+    except Exception:
+        pass
     return {"kernel_ms": ms, "exec_gflop": fl / 1e9, "exec_tflops": fl / (ms * 1e-3) / 1e12,
             "algo_tflops": ALGO_GFLOP_PER_FRAME * 1e9 / (ms * 1e-3) / 1e12, "launches": len(rec) / reps}
 

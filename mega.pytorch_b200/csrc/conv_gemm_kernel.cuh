@@ -161,10 +161,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr uint32_t kTmemCols = (kAccBufs * BN <= 64) ? 64 : (kAccBufs * BN <= 128) ? 128 : (kAccBufs * BN <= 256) ? 256 : 512;
   constexpr uint32_t kAccStride = SPLIT3 ? BN : kTmemCols / 2;
   // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
-  // accumulation chain (measured ~1e-3 relative after 3000 k-blocks). The strict mode therefore restarts the
-  // TMEM accumulator every kSegLen k-blocks and folds the segments into a master accumulator (also in TMEM)
+  // accumulation chain (measured ~1e-3 relative after 3000 k-blocks; ~2e-5 after 32, which the chaotic position
+  // embedding of the relation module amplifies to 5e-3 on the final logits). The strict mode therefore restarts the
+  // TMEM accumulator every kSegLen k-blocks (4 k-blocks = 48 truncating adds, <= 3e-6 relative) and folds the segments into a master accumulator (also in TMEM)
   // with round-to-nearest fp32 adds done by the epilogue warps.
-  constexpr int kSegLen = SPLIT3 ? 32 : 0x7fffffff;
+  constexpr int kSegLen = SPLIT3 ? 4 : 0x7fffffff;
   extern __shared__ uint8_t smem_raw[];
   // the 128B swizzle pattern is a function of the absolute smem address: align to 1024 B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &

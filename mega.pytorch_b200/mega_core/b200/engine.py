@@ -822,9 +822,9 @@ class RdnEngine(WindowedEngine):
         self.cur_cnt = z(1, 1, dtype=torch.int32)
         self.ld_ref, self.ld_adv = _round_up(self.nref, 32), _round_up(self.nadv, 32)
         self._alloc_attention([(max(KP, self.nadv), self.ld_ref), (KP, self.ld_adv)], self.nref)
-        self.pooled = za(KP, res * res * ch)
-        self.fc0_out = za(KP, D)
-        self.roi_boxes, self.roi_batch = z(KP, 4), z(KP, dtype=torch.int32)
+        self.pooled = za(2 * KP, res * res * ch)                # the first frame of a video runs 2 frames per batch
+        self.fc0_out = za(2 * KP, D)
+        self.roi_boxes, self.roi_batch = z(2 * KP, 4), z(2 * KP, dtype=torch.int32)
         o, off = {}, 0
         for name, n in (("idx_e", KP + self.nref), ("idx_adv", self.nadv), ("dst_local", KP), ("slot_new", 4),
                         ("slot_key", 4)):
