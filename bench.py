@@ -291,7 +291,8 @@ def strict_pass(args, sd, dev, pool_pinned, pairs_dev, w, h, steps=8):
         torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
     return {"precision": "fp32x3", "value": 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "steps": steps,
-            "note": "3xTF32 contractions: class logits within 1e-3 of the fp32 reference (tests/test_engine_gpu.py)"}
+            "note": "3xTF32 contractions, accumulator re-started every 4 k-blocks: every proposal / detection of the "
+                    "reference reproduced, class logits within 1e-2 (tests/test_engine_gpu.py)"}
 
 
 def roofline_pass(eng, pairs_dev, w, h, reps=3):
@@ -300,20 +301,15 @@ def roofline_pass(eng, pairs_dev, w, h, reps=3):
     saved_graphs, eng._graphs = eng._graphs, {}
     saved_flag, eng.use_graph = eng.use_graph, False
     rec = []
-    orig = ops._launch_conv_gemm
 
-    def timed(d):
+    def hook(run, flops, info):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        orig(d)
+        run()
         b.record()
-        m = d.n_img * d.out_h * d.out_w * d.batch
-        rec.append((a, b, 2.0 * m * d.cout * d.k_per_tap * d.taps_r * d.taps_s,
-                    {"m": d.n_img * d.out_h * d.out_w, "batch": d.batch, "cout": d.cout, "k": d.k_per_tap,
-                     "taps": d.taps_r * d.taps_s, "bn": d.block_n, "sk": d.stream_k, "res": bool(d.residual),
-                     "out16": d.out_f16}))
+        rec.append((a, b, flops, info))
 
-    ops._launch_conv_gemm = timed
+    ops.TIMING_HOOK[0] = hook
     try:
         eng.step_batched(pairs_dev[0], w, h)   # warm
         rec.clear()
@@ -324,7 +320,7 @@ def roofline_pass(eng, pairs_dev, w, h, reps=3):
             eng.step_batched(pairs_dev[(i + 1) % 16], w, h)
             torch.cuda.synchronize()
     finally:
-        ops._launch_conv_gemm = orig
+        ops.TIMING_HOOK[0] = None
         eng._graphs, eng.use_graph = saved_graphs, saved_flag
     ms = sum(r[0].elapsed_time(r[1]) for r in rec) / reps
     fl = sum(r[2] for r in rec) / reps

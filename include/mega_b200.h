@@ -90,6 +90,21 @@ int mega_conv_gemm(const mega_conv_gemm_desc* desc, void* stream);
 /* ABI v1 name of mega_conv_gemm (kept for existing callers) */
 int mega_conv_gemm_tf32(const mega_conv_gemm_desc* desc, void* stream);
 long long mega_conv_gemm_workspace_bytes(void);
+
+/* A chain of dependent contractions in ONE persistent kernel (conv_chain.cu): `descs[0..n)` are executed in order,
+ * layer l+1 may read anything layers <= l wrote (grid-wide barrier between layers, no kernel boundary). All layers:
+ * precision 2 (fp16 operands), block_n <= 128, the same workspace. mega_conv_chain_encode() validates the
+ * descriptors and writes the device-side layer table (tensor maps + parameters) into a HOST buffer of
+ * mega_conv_chain_plan_bytes(n) bytes (128-byte aligned) and the grid size to use; the caller copies the table to
+ * device memory once (the tensors named by the descriptors must keep their addresses) and replays it with
+ * mega_conv_chain_launch(). sync_words: 2 device uint32, zero-initialised once (the kernel leaves them zero);
+ * launches that may overlap need distinct sync words and workspaces.
+ * Replaces the per-layer launches of ResNet.forward / ResNetHead.forward / RPNHead.forward
+ * (modeling/backbone/resnet.py:145-152, :201-204; modeling/rpn/rpn.py:99-106). */
+long long mega_conv_chain_plan_bytes(int n_layers);
+int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_layers, void* plan_host, long long plan_bytes,
+                           int* grid_out);
+int mega_conv_chain_launch(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream, int pdl);
 /* TMA fp32->tf32 conversion on load (round-to-nearest) on/off; returns the previous value. */
 int mega_set_tf32_rounding(int enable);
 

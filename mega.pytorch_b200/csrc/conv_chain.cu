@@ -1,0 +1,499 @@
+// A whole chain of dependent convolutions / GEMMs in ONE persistent kernel.
+//
+// The backbone of the MEGA hot path is a strictly sequential chain of ~100 small implicit GEMMs per frame pair
+// (ResNet-101 res2..res5, modeling/backbone/resnet.py:324-344; RPN head, rpn/rpn.py:99-106). Each of them is 2-10 us
+// of tensor-core work at M = 4788 output pixels, so one-kernel-per-layer execution is dominated by what surrounds
+// the math: launch, barrier/TMEM set-up, descriptor fetch, pipeline fill and drain (measured 17-30 us per layer,
+// profiles/r01_ncu_full_conv_gemm_f16_res4_raw.csv: tensor pipe active 4-10 % of the kernel's duration).
+//
+// Here the per-layer kernel body (TMA producer warp / tcgen05 MMA warp / 4 epilogue warps, double-buffered TMEM
+// accumulators, persistent stream-K work list -- see conv_gemm_kernel.cuh) is wrapped in a loop over a device-side
+// table of layers. One CTA per SM stays resident for the whole chain; mbarriers, the TMEM allocation and the smem
+// ring are set up once; layers are separated by a grid-wide barrier (one atomic counter, release/acquire) instead of
+// a kernel boundary. Tensor maps live in the layer table in global memory.
+//
+// Restrictions of a chain: fp16 operands (kind::f16), block_n <= 128 (one 32 KB smem stage holds A 128 x 64 and B
+// block_n x 64 halves), output fp16 or fp32 per layer.
+#include "conv_gemm_kernel.cuh"
+
+namespace mega {
+
+constexpr int kChainStages = 5;
+constexpr int kChainStageBytes = 32768;     // A tile 16 KB + B tile (<= 128 rows) 16 KB
+constexpr int kChainABytes = 16384;
+constexpr int kChainEpiBytes = 4 * 4 * 4096;
+constexpr int kChainBarOffset = kChainStages * kChainStageBytes + kChainEpiBytes;
+constexpr int kChainSmem = kChainBarOffset + (2 * kChainStages + 4 + 8) * 8 + 64 + 1024;
+constexpr uint32_t kChainTmemCols = 256;    // two accumulators of up to 128 fp32 columns
+constexpr uint32_t kChainAccStride = 128;
+
+struct alignas(128) ChainLayer {
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  ConvGemmParams p;
+  int block_n;
+  int out16;
+  int active_ctas;   // CTAs that take part in this layer's work list (<= grid); the others only pass the barrier
+  int reserved;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// generic <-> async proxy ordering (TMA loads of data other CTAs wrote with TMA stores / generic stores)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// all CTAs of the grid have finished `target / grid` layers
+__device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
+  if (ld_acquire_u32(ctr) >= target) {
+    fence_proxy_async_all();
+    return;
+  }
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (ld_acquire_u32(ctr) < target) {
+    __nanosleep(40);
+    if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 2000000000ull) {
+      printf("mega: chain grid barrier timeout block %d thread %d target %u have %u\n", blockIdx.x, threadIdx.x, target,
+             ld_acquire_u32(ctr));
+      __trap();
+    }
+  }
+  fence_proxy_async_all();
+}
+
+struct PipeState {
+  int stage;
+  uint32_t phase;
+};
+
+// ------------------------------------------------------------------ epilogue of one layer (4 warps)
+template <bool OUT16>
+__device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const ConvGemmParams& p, const int BN, uint8_t* smem,
+                                                     uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint64_t* res_bar,
+                                                     int* epi_flag, uint32_t tmem_base, int warp, int lane, int cta,
+                                                     int grid, int& item, uint32_t& rphase) {
+  constexpr int CW = OUT16 ? 64 : 32;
+  const int q = warp & 3;
+  const int row = q * 32 + lane;
+  const int epi_tid = (warp - 2) * 32 + lane;
+  uint8_t* epi_out = smem + kChainStages * kChainStageBytes + (warp - 2) * 16384;
+  uint8_t* epi_res = epi_out + 8192;
+  uint64_t* rbar = res_bar + (warp - 2) * 2;
+  const long long U = p.total_units;
+  const int KB = p.kb_per_tile;
+  const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+  const CUtensorMap* tmOut = &L->tmOut;
+  const CUtensorMap* tmRes = &L->tmRes;
+  WorkIter it(p, cta, grid);
+  long long t;
+  int kb0, kb1;
+  for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
+    const TileCoord tc = decode_tile(p, t, BN);
+    const int buf = item & 1;
+    const uint32_t use = static_cast<uint32_t>(item >> 1);
+    ++item;
+    mbar_wait(&tmem_full_bar[buf], use & 1);
+    tc_fence_after();
+    const uint32_t tmem_row = tmem_base + buf * kChainAccStride + lane_bits;
+    auto load_acc = [&](int c32, uint32_t (&acc)[32]) {
+      __syncwarp();
+      tmem_ld_32x32(tmem_row + c32 * 32, acc);
+      tmem_ld_wait();
+    };
+    const bool complete = (kb0 == 0 && kb1 == KB);
+    bool finalize = complete;
+    int c_first = cta, c_last = cta;
+    if (!complete) {
+      float* my_ws = p.part_ws + ((static_cast<long long>(cta) * 2 + (tile_item == 0 ? 0 : 1)) * kBM + row) * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t acc[32];
+        load_acc(c, acc);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                 __uint_as_float(acc[j + 3]));
+          __stcg(reinterpret_cast<float4*>(my_ws + c * 32 + j), v);
+        }
+      }
+      __threadfence();
+      epi_bar_sync();
+      c_first = unit_owner(U, grid, t * KB);
+      c_last = unit_owner(U, grid, t * KB + KB - 1);
+      if (epi_tid == 0) {
+        const int parts = c_last - c_first + 1;
+        const int old = atomicAdd(&p.counters[t], 1);
+        const int last = (old == parts - 1);
+        if (last) p.counters[t] = 0;
+        *epi_flag = last;
+      }
+      epi_bar_sync();
+      finalize = (*epi_flag != 0);
+      if (finalize) __threadfence();
+    }
+    if (finalize) {
+      const int r0 = q * 32;
+      const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
+      const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
+      const int out_n = tc.img + tc.batch * p.out_n_off;
+      const int res_n = tc.img + tc.batch * p.res_n_off;
+      const float* scale_p = p.scale ? p.scale + tc.batch * p.bias_z_off : nullptr;
+      const float* bias_p = p.bias ? p.bias + tc.batch * p.bias_z_off : nullptr;
+      const int nchunks = min(BN / CW, (p.cout - tc.n0 + CW - 1) / CW);
+      const uint32_t sw = static_cast<uint32_t>(lane & 7);
+      if (p.has_residual && lane == 0 && nchunks > 0) {
+        mbar_arrive_expect_tx(&rbar[0], 4096);
+        tma_load_4d(epi_res, tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
+      }
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        float acc[CW];
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) {
+          uint32_t raw[32];
+          load_acc(c * (CW / 32) + h, raw);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[h * 32 + j] = __uint_as_float(raw[j]);
+        }
+        const int nb = tc.n0 + c * CW;
+        if (!complete) {
+          float sum[CW];
+#pragma unroll
+          for (int j = 0; j < CW; ++j) sum[j] = 0.f;
+          for (int oc = c_first; oc <= c_last; ++oc) {
+            if (oc == cta) {
+#pragma unroll
+              for (int j = 0; j < CW; ++j) sum[j] += acc[j];
+            } else {
+              const int slot = (cta_first_unit(U, grid, oc) >= t * KB) ? 0 : 1;
+              const float* ws = p.part_ws + ((static_cast<long long>(oc) * 2 + slot) * kBM + row) * BN + c * CW;
+#pragma unroll
+              for (int j = 0; j < CW; j += 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + j));
+                sum[j] += v.x; sum[j + 1] += v.y; sum[j + 2] += v.z; sum[j + 3] += v.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < CW; ++j) acc[j] = sum[j];
+        }
+        const uint8_t* rsrc = nullptr;
+        if (p.has_residual) {
+          const int rb = c & 1;
+          if (c + 1 < nchunks && lane == 0) {
+            mbar_arrive_expect_tx(&rbar[rb ^ 1], 4096);
+            tma_load_4d(epi_res + (rb ^ 1) * 4096, tmRes, &rbar[rb ^ 1], nb + CW + tc.batch * p.res_c_off, st_w, st_h,
+                        res_n);
+          }
+          mbar_wait(&rbar[rb], (rphase >> rb) & 1u);
+          rphase ^= (1u << rb);
+          rsrc = epi_res + rb * 4096 + lane * 128;
+        }
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* dst = epi_out + (c & 1) * 4096 + lane * 128;
+#pragma unroll
+        for (int j = 0; j < CW; j += 4) {
+          const int n = nb + j;
+          if (n < p.cout) {
+            if (scale_p) {
+              const float4 sc = ldg_f4(scale_p + n);
+              acc[j] *= sc.x; acc[j + 1] *= sc.y; acc[j + 2] *= sc.z; acc[j + 3] *= sc.w;
+            }
+            if (bias_p) {
+              const float4 bi = ldg_f4(bias_p + n);
+              acc[j] += bi.x; acc[j + 1] += bi.y; acc[j + 2] += bi.z; acc[j + 3] += bi.w;
+            }
+          }
+        }
+        if (OUT16) {
+#pragma unroll
+          for (int j = 0; j < CW; j += 8) {
+            const uint32_t chunk = (static_cast<uint32_t>(j >> 3) ^ sw) << 4;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = acc[j + e];
+            if (rsrc) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(rsrc + chunk);
+              const float2 r0v = h2_to_f2(rr.x), r1v = h2_to_f2(rr.y), r2v = h2_to_f2(rr.z), r3v = h2_to_f2(rr.w);
+              v[0] += r0v.x; v[1] += r0v.y; v[2] += r1v.x; v[3] += r1v.y;
+              v[4] += r2v.x; v[5] += r2v.y; v[6] += r3v.x; v[7] += r3v.y;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            uint4 o;
+            o.x = f2_to_h2(v[0], v[1]); o.y = f2_to_h2(v[2], v[3]);
+            o.z = f2_to_h2(v[4], v[5]); o.w = f2_to_h2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(dst + chunk) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW; j += 4) {
+            float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            const uint32_t chunk = (static_cast<uint32_t>(j >> 2) ^ sw) << 4;
+            if (rsrc) {
+              const float4 rr = *reinterpret_cast<const float4*>(rsrc + chunk);
+              v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            }
+            if (p.relu) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(dst + chunk) = v;
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(tmOut, epi_out + (c & 1) * 4096, nb + tc.batch * p.out_c_off, st_w, st_h, out_n);
+          tma_store_commit();
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, unsigned* sync) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kChainBarOffset);
+  uint64_t* empty_bar = full_bar + kChainStages;
+  uint64_t* tmem_full_bar = empty_bar + kChainStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+  uint64_t* res_bar = tmem_empty_bar + 2;               // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+  int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int grid = gridDim.x;
+  const int cta = blockIdx.x;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kChainStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);
+    }
+    for (int b = 0; b < 8; ++b) mbar_init(&res_bar[b], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, kChainTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      PipeState ps = {0, 0};
+      for (int l = 0; l < n_layers; ++l) {
+        const ChainLayer* L = layers + l;
+        prefetch_tmap(&L->tmA);
+        prefetch_tmap(&L->tmB);
+        if (l > 0) grid_wait(sync, static_cast<unsigned>(l) * grid);
+        const ConvGemmParams p = L->p;
+        const int BN = L->block_n;
+        const int act = L->active_ctas;
+        if (cta >= act) continue;
+        const uint32_t tx_bytes = static_cast<uint32_t>((kBM + BN) * 128);
+        WorkIter it(p, cta, act);
+        long long t;
+        int kb0, kb1;
+        while (it.next(t, kb0, kb1)) {
+          const TileCoord tc = decode_tile(p, t, BN);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            const int tap = kb / p.k_chunks;
+            const int kc = kb - tap * p.k_chunks;
+            const int r = tap / p.taps_s;
+            const int s = tap - r * p.taps_s;
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            uint8_t* a_dst = smem + ps.stage * kChainStageBytes;
+            uint8_t* b_dst = a_dst + kChainABytes;
+            mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
+            tma_load_4d(a_dst, &L->tmA, &full_bar[ps.stage], kc * 64 + tc.batch * p.a_c_off, tc.w0 + s * p.dil - p.pad,
+                        tc.h0 + r * p.dil - p.pad, tc.img + tc.batch * p.a_n_off);
+            tma_load_3d(b_dst, &L->tmB, &full_bar[ps.stage], kc * 64 + tc.batch * p.b_k_off, tc.n0 + tc.batch * p.b_n_off,
+                        tap);
+            if (++ps.stage == kChainStages) {
+              ps.stage = 0;
+              ps.phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      PipeState ps = {0, 0};
+      int item = 0;
+      for (int l = 0; l < n_layers; ++l) {
+        const ChainLayer* L = layers + l;
+        const ConvGemmParams p = L->p;
+        const int BN = L->block_n;
+        const int act = L->active_ctas;
+        if (cta >= act) continue;
+        const uint32_t idesc = umma_idesc<0>(kBM, BN);
+        WorkIter it(p, cta, act);
+        long long t;
+        int kb0, kb1;
+        while (it.next(t, kb0, kb1)) {
+          const int buf = item & 1;
+          const uint32_t use = static_cast<uint32_t>(item >> 1);
+          ++item;
+          mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t tmem_d = tmem_base + buf * kChainAccStride;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[ps.stage], ps.phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + ps.stage * kChainStageBytes);
+            const uint64_t adesc = umma_desc_sw128(a_addr);
+            const uint64_t bdesc = umma_desc_sw128(a_addr + kChainABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[ps.stage]);
+            if (++ps.stage == kChainStages) {
+              ps.stage = 0;
+              ps.phase ^= 1;
+            }
+          }
+          umma_commit(&tmem_full_bar[buf]);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int epi_tid = (warp - 2) * 32 + lane;
+    int item = 0;
+    uint32_t rphase = 0;
+    for (int l = 0; l < n_layers; ++l) {
+      const ChainLayer* L = layers + l;
+      if (lane == 0) {
+        prefetch_tmap(&L->tmOut);
+        prefetch_tmap(&L->tmRes);
+      }
+      // residual / partial-sum reads of this layer must see what the other CTAs wrote in earlier layers
+      // (one poller per CTA; the named barrier passes the acquired state on to the other epilogue threads)
+      if (l > 0) {
+        if (epi_tid == 0) grid_wait(sync, static_cast<unsigned>(l) * grid);
+        epi_bar_sync();
+        fence_proxy_async_all();
+      }
+      const ConvGemmParams p = L->p;
+      const int act = L->active_ctas;
+      if (cta < act) {
+        if (L->out16) {
+          chain_epilogue_layer<true>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
+                                     warp, lane, cta, act, item, rphase);
+        } else {
+          chain_epilogue_layer<false>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
+                                      warp, lane, cta, act, item, rphase);
+        }
+      }
+      // this CTA's part of layer l is complete and visible: arrive at the grid barrier
+      if (lane == 0) tma_store_wait<0>();
+      __threadfence();
+      epi_bar_sync();
+      if (epi_tid == 0) {
+        fence_proxy_async_all();
+        __threadfence();
+        atomicAdd(sync, 1u);
+      }
+    }
+    // last CTA out resets the barrier words for the next launch (every CTA has passed every barrier by then)
+    if (epi_tid == 0) {
+      const unsigned old = atomicAdd(sync + 1, 1u);
+      if (old == static_cast<unsigned>(grid) - 1) {
+        sync[0] = 0;
+        sync[1] = 0;
+        __threadfence();
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kChainTmemCols);
+  }
+}
+
+// defined in conv_gemm.cu: validates a descriptor and encodes its tensor maps / kernel parameters
+int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA, CUtensorMap* tmB, CUtensorMap* tmOut,
+                             CUtensorMap* tmRes, ConvGemmParams* p, int* ctas);
+
+}  // namespace mega
+
+using namespace mega;
+
+extern "C" long long mega_conv_chain_plan_bytes(int n_layers) {
+  return static_cast<long long>(n_layers) * static_cast<long long>(sizeof(ChainLayer));
+}
+
+extern "C" int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_layers, void* plan_host,
+                                      long long plan_bytes, int* grid_out) {
+  MEGA_ARG_CHECK(descs != nullptr && plan_host != nullptr && n_layers > 0, "conv_chain: bad arguments");
+  MEGA_ARG_CHECK(plan_bytes >= mega_conv_chain_plan_bytes(n_layers), "conv_chain: plan buffer too small");
+  MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(plan_host) & 127) == 0, "conv_chain: plan buffer must be 128-byte aligned");
+  ChainLayer* out = static_cast<ChainLayer*>(plan_host);
+  int grid = 1;
+  for (int l = 0; l < n_layers; ++l) {
+    const mega_conv_gemm_desc* d = descs + l;
+    MEGA_ARG_CHECK(d->precision == kModeF16, "conv_chain: layer %d: chains run fp16 operands only", l);
+    MEGA_ARG_CHECK(d->block_n <= 128, "conv_chain: layer %d: block_n %d > 128", l, d->block_n);
+    MEGA_ARG_CHECK(d->workspace == descs[0].workspace, "conv_chain: every layer must name the same workspace");
+    ChainLayer* L = out + l;
+    int ctas = 0;
+    const int rc = encode_conv_gemm_problem(d, &L->tmA, &L->tmB, &L->tmOut, &L->tmRes, &L->p, &ctas);
+    if (rc != MEGA_OK) return rc;
+    L->block_n = d->block_n;
+    L->out16 = d->out_f16 ? 1 : 0;
+    L->active_ctas = ctas;
+    L->reserved = 0;
+    if (ctas > grid) grid = ctas;
+  }
+  if (grid_out) *grid_out = grid;
+  return MEGA_OK;
+}
+
+extern "C" int mega_conv_chain_launch(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream_v,
+                                      int pdl) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(plan_device != nullptr && sync_words != nullptr && n_layers > 0 && grid > 0 && grid <= kMaxCtas,
+                 "conv_chain_launch: bad arguments (grid %d)", grid);
+  MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(plan_device) & 127) == 0, "conv_chain_launch: plan must be 128-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    MEGA_CUDA_CHECK(cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = kChainSmem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  MEGA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_chain_kernel, static_cast<const ChainLayer*>(plan_device), n_layers,
+                                     static_cast<unsigned*>(sync_words)));
+  return MEGA_OK;
+}

@@ -59,8 +59,12 @@ extern "C" int mega_set_tf32_rounding(int enable) {
   return old;
 }
 
-extern "C" int mega_conv_gemm(const mega_conv_gemm_desc* d, void* stream_v) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+namespace mega {
+
+// validates a descriptor, encodes its four tensor maps and fills the kernel parameters; *ctas = CTAs of the
+// persistent work list (shared by the single-launch path below and the layer chains of conv_chain.cu)
+int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, CUtensorMap* tmB_p, CUtensorMap* tmOut_p,
+                             CUtensorMap* tmRes_p, ConvGemmParams* p_out, int* ctas_out) {
   MEGA_ARG_CHECK(d != nullptr, "conv_gemm: null descriptor");
   MEGA_ARG_CHECK(d->precision >= 0 && d->precision <= 2,
                  "conv_gemm: precision must be 0 (tf32), 1 (3xtf32) or 2 (fp16 operands)");
@@ -108,7 +112,8 @@ extern "C" int mega_conv_gemm(const mega_conv_gemm_desc* d, void* stream_v) {
                                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapDataType odt = out16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap& tmA = *tmA_p;
+  CUtensorMap& tmB = *tmB_p;
   {
     cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->a_c), static_cast<cuuint64_t>(d->a_w),
                           static_cast<cuuint64_t>(d->a_h), static_cast<cuuint64_t>(d->a_n)};
@@ -147,7 +152,8 @@ extern "C" int mega_conv_gemm(const mega_conv_gemm_desc* d, void* stream_v) {
 
   // per-warp store / residual boxes: one 128-byte row segment (32 floats / 64 halves) x (box_h x box_w = 32 output
   // pixels), 128B swizzle
-  CUtensorMap tmOut, tmRes;
+  CUtensorMap& tmOut = *tmOut_p;
+  CUtensorMap& tmRes = *tmRes_p;
   {
     const int box_w = d->tile_w < 32 ? d->tile_w : 32;
     const int box_h = 32 / box_w;
@@ -181,7 +187,7 @@ extern "C" int mega_conv_gemm(const mega_conv_gemm_desc* d, void* stream_v) {
     }
   }
 
-  ConvGemmParams p;
+  ConvGemmParams& p = *p_out;
   p.tile_w = d->tile_w;
   p.tile_h = d->tile_h;
   p.tiles_w = mega_ceil_div(d->out_w, d->tile_w);
@@ -232,6 +238,22 @@ extern "C" int mega_conv_gemm(const mega_conv_gemm_desc* d, void* stream_v) {
   if (ctas < 1) ctas = 1;
   if (ctas > g_num_sms) ctas = g_num_sms;
   if (d->max_ctas > 0 && ctas > d->max_ctas) ctas = d->max_ctas;
+  *ctas_out = static_cast<int>(ctas);
+  return MEGA_OK;
+}
+
+}  // namespace mega
+
+extern "C" int mega_conv_gemm(const mega_conv_gemm_desc* d, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  CUtensorMap tmA, tmB, tmOut, tmRes;
+  ConvGemmParams p;
+  int ctas = 0;
+  const int erc = encode_conv_gemm_problem(d, &tmA, &tmB, &tmOut, &tmRes, &p, &ctas);
+  if (erc != MEGA_OK) return erc;
+  const bool strict = d->precision == kModeSplit3;
+  const bool f16 = d->precision == kModeF16;
+  const bool out16 = d->out_f16 != 0;
   dim3 grid(static_cast<unsigned>(ctas), 1, 1);
   const int pdl = d->pdl ? 1 : 0;
   if (f16) return launch_conv_gemm_f16(d->block_n, out16 ? 1 : 0, tmA, tmB, tmOut, tmRes, p, grid, stream, pdl);

@@ -64,6 +64,12 @@ lib.mega_conv_gemm.restype = c_int
 lib.mega_conv_gemm_tf32.argtypes = [ctypes.POINTER(ConvGemmDesc), ctypes.c_void_p]
 lib.mega_conv_gemm_tf32.restype = c_int
 lib.mega_conv_gemm_workspace_bytes.restype = c_ll
+lib.mega_conv_chain_plan_bytes.argtypes = [c_int]
+lib.mega_conv_chain_plan_bytes.restype = c_ll
+lib.mega_conv_chain_encode.argtypes = [ctypes.POINTER(ConvGemmDesc), c_int, ctypes.c_void_p, c_ll, ctypes.POINTER(c_int)]
+lib.mega_conv_chain_encode.restype = c_int
+lib.mega_conv_chain_launch.argtypes = [ctypes.c_void_p, c_int, c_int, ctypes.c_void_p, ctypes.c_void_p, c_int]
+lib.mega_conv_chain_launch.restype = c_int
 lib.mega_set_tf32_rounding.argtypes = [c_int]
 lib.mega_set_tf32_rounding.restype = c_int
 
@@ -149,6 +155,7 @@ lib.mega_deform_psroi_pooling_forward.restype = _i
 
 EXPORTS = [
     "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm", "mega_conv_gemm_tf32", "mega_conv_gemm_workspace_bytes", "mega_set_tf32_rounding",
+    "mega_conv_chain_plan_bytes", "mega_conv_chain_encode", "mega_conv_chain_launch",
     "mega_nms_workspace_bytes", "mega_nms", "mega_rpn_select_workspace_bytes", "mega_rpn_select",
     "mega_roi_align_forward_nchw", "mega_roi_align_forward_nhwc", "mega_stem_im2col", "mega_maxpool3x3s2_nhwc",
     "mega_gather_rows", "mega_copy_rows", "mega_transpose_2d", "mega_relation_softmax", "mega_box_postprocess_workspace_bytes",

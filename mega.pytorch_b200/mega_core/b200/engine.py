@@ -207,6 +207,7 @@ class Backbone:
         self.stages = ResNetStages(sd, prefix, (1, 2, 3), dev, first_stride_of=lambda li: 2 if li > 1 else 1,
                                    dtype=dtype)
         self._bufs = {}
+        self._chains = {}
         self.out_channels = self.stages.stages[-1][-1].cout
 
     def _buf(self, tag, shape):
@@ -217,8 +218,10 @@ class Backbone:
             self._bufs[key] = t
         return t
 
-    def forward(self, img, out=None):
-        """img [N,3,H,W] fp32 NCHW (the reference's post-transform domain) -> NHWC [N,H/16,W/16,1024]"""
+    def forward(self, img, out=None, tail=None):
+        """img [N,3,H,W] fp32 NCHW (the reference's post-transform domain) -> NHWC [N,H/16,W/16,1024].
+        fp16 mode: res2..res4 (93 convolutions for R-101) run as ONE persistent chain kernel (ops.chain); `tail(feats)`
+        may append further conv_gemm calls on the result to the same chain (the RPN head)."""
         n, _, h, w = img.shape
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         col = self._buf("col", (n, ho * wo, 160))
@@ -229,7 +232,12 @@ class Backbone:
         hp, wp = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         p = self._buf("pool", (n, hp, wp, 64))
         ops.maxpool3x3s2(s, p)
-        return self.stages.forward(p, out=out)
+        with ops.chain(self._chains, ("body", tuple(p.shape), tail is not None), self.dev,
+                       enabled=self.dtype == torch.float16):
+            y = self.stages.forward(p, out=out)
+            if tail is not None:
+                tail(y)
+        return y
 
 
 class _Att:
@@ -310,6 +318,8 @@ class HeadCommon:
                                                sd["roi_heads.box.predictor.bbox_pred.bias"].float()])
         self.pred_b = pb.contiguous().to(dev)
         self._bufs = {}
+        self._chains = {}
+        self.chained = self.act == torch.float16          # fp16 mode: conv chains run as persistent multi-layer kernels
 
     def _buf(self, tag, shape, dtype=torch.float32):
         key = (tag, tuple(shape), dtype)
@@ -319,14 +329,21 @@ class HeadCommon:
             self._bufs[key] = t
         return t
 
-    def rpn(self, feats, im_w, im_h, post):
-        """feats [n,h,w,1024] -> proposals (boxes [n,post,4], scores, count[n])"""
-        c = self.cfg
+    def rpn_head(self, feats):
+        """RPNHead.forward (rpn/rpn.py:99-106): 3x3 conv + ReLU, then objectness and box deltas as one 1x1 GEMM"""
         n, h, w, _ = feats.shape
         t = self._buf("rpn_t", (n, h, w, feats.shape[3]), self.act)
         ops.conv_gemm(feats, self.rpn_w, t, taps=(3, 3), dil=1, pad=1, bias=self.rpn_b, relu=True)
         head = self._buf("rpn_head", (n, h, w, self.rpn_ld))
         ops.conv_gemm(t, self.rpn_hw, head, bias=self.rpn_hb, cout=5 * self.num_anchors, block_n=64)
+        return head
+
+    def rpn(self, feats, im_w, im_h, post, head=None):
+        """feats [n,h,w,1024] -> proposals (boxes [n,post,4], scores, count[n]); `head`: rpn_head(feats) already run"""
+        c = self.cfg
+        n, h, w, _ = feats.shape
+        if head is None:
+            head = self.rpn_head(feats)
         out = (self._buf("rpn_boxes", (n, post, 4)), self._buf("rpn_scores", (n, post)), None,
                self._buf("rpn_cnt", (n,), torch.int32))
         ops.rpn_select(head, n, h, w, self.base_anchors, im_w, im_h, c.pre_nms_top_n, post, c.rpn_nms_thresh,
@@ -420,7 +437,13 @@ class WindowedEngine(HeadCommon):
         returns (x rows [sum r_i, 1024], boxes [n,300,4], cnt [n], spans)"""
         c = self.cfg
         n = imgs.shape[0]
-        feats = self.backbone.forward(imgs)
+        head = None
+        if self.chained:      # the RPN head's two GEMMs ride at the end of the backbone chain
+            heads = []
+            feats = self.backbone.forward(imgs, tail=lambda f: heads.append(self.rpn_head(f)))
+            head = heads[0]
+        else:
+            feats = self.backbone.forward(imgs)
         # fork: proposal selection (few, latency-bound CTAs) on a side stream, overlapped with the res5 convolutions
         # of the same frames (which need only `feats`); the GEMMs of the main branch leave 4 SMs free meanwhile
         main = torch.cuda.current_stream(self.dev)
@@ -430,10 +453,11 @@ class WindowedEngine(HeadCommon):
         with torch.cuda.stream(self._side):
             ops.WS_LANE[0] = 1
             try:
-                boxes, _, cnt = self.rpn(feats, im_w, im_h, self.KP)
+                boxes, _, cnt = self.rpn(feats, im_w, im_h, self.KP, head=head)
             finally:
                 ops.WS_LANE[0] = 0
-        r5 = self.res5.forward(feats, max_ctas=144)
+        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained, max_ctas=144):
+            r5 = self.res5.forward(feats, max_ctas=144)
         main.wait_stream(self._side)
         src, bidx, spans = self._roi_table(kinds)
         rows = src.numel()
@@ -975,12 +999,13 @@ class BaseEngine(HeadCommon):
         KP = c.post_nms_top_n
         feats = self.backbone.forward(img)
         boxes, _, cnt = self.rpn(feats, im_w, im_h, KP)
-        x = self.res5.forward(feats)
-        if self.reduce:
-            n, h, w, _ = x.shape
-            xr = self._buf("reduce", (n, h, w, self.red_w.shape[1]), self.act)
-            ops.conv_gemm(x, self.red_w, xr, bias=self.red_b, relu=True)
-            x = xr
+        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained):
+            x = self.res5.forward(feats)
+            if self.reduce:
+                n, h, w, _ = x.shape
+                xr = self._buf("reduce", (n, h, w, self.red_w.shape[1]), self.act)
+                ops.conv_gemm(x, self.red_w, xr, bias=self.red_b, relu=True)
+                x = xr
         res = c.pooler_resolution
         pooled = self._buf("pooled", (KP, res * res * self.ch), self.act)
         ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)

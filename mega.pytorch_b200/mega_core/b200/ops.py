@@ -13,8 +13,126 @@ LAUNCHES = [0]
 
 def _launch_conv_gemm(d):
     """single choke point of the tcgen05 kernel (bench.py wraps it with CUDA events for the roofline)"""
-    check(lib.mega_conv_gemm(ctypes.byref(d), stream_ptr()), "mega_conv_gemm")
+    if _CHAIN_MODE[0] == "record":
+        _CHAIN_REC[0].append(_copy_desc(d))
+        return
+    if _CHAIN_MODE[0] == "skip":
+        return
+
+    def run():
+        check(lib.mega_conv_gemm(ctypes.byref(d), stream_ptr()), "mega_conv_gemm")
+    _run_timed(run, _desc_flops(d), _desc_info(d))
     LAUNCHES[0] += 1
+
+
+# bench.py installs a hook here to bracket every tensor-core kernel launch with CUDA events: hook(run, flops, info)
+TIMING_HOOK = [None]
+
+
+def _run_timed(run, flops, info):
+    h = TIMING_HOOK[0]
+    if h is None:
+        run()
+    else:
+        h(run, flops, info)
+
+
+def _desc_flops(d):
+    return 2.0 * d.n_img * d.out_h * d.out_w * d.batch * d.cout * d.k_per_tap * d.taps_r * d.taps_s
+
+
+def _desc_info(d):
+    return {"m": d.n_img * d.out_h * d.out_w, "batch": d.batch, "cout": d.cout, "k": d.k_per_tap,
+            "taps": d.taps_r * d.taps_s, "bn": d.block_n, "sk": d.stream_k, "res": bool(d.residual), "out16": d.out_f16}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Layer chains: a fixed sequence of dependent conv_gemm calls executed by ONE persistent kernel (csrc/conv_chain.cu).
+#     with ops.chain(cache, key) as ch:      # first time: the conv_gemm calls inside are RECORDED (not launched) and
+#         ... ops.conv_gemm(...) ...         # compiled into a device-side layer table; afterwards they are skipped
+#     # on exit the whole chain is launched (one kernel)
+# Only conv_gemm calls may appear inside (anything else would run before the chain); all tensors must be persistent.
+_CHAIN_MODE = [None]
+_CHAIN_REC = [None]
+CHAINS_ENABLED = [True]
+MAX_BN = [256]          # widest N tile conv_gemm may pick (128 while recording a chain)
+
+
+def _copy_desc(d):
+    c = ConvGemmDesc()
+    ctypes.memmove(ctypes.byref(c), ctypes.byref(d), ctypes.sizeof(ConvGemmDesc))
+    return c
+
+
+class ConvChain(object):
+    def __init__(self, descs, device, max_ctas=0):
+        n = len(descs)
+        self.n = n
+        arr = (ConvGemmDesc * n)(*descs)
+        nbytes = int(lib.mega_conv_chain_plan_bytes(n))
+        host = torch.zeros(nbytes + 128, dtype=torch.uint8)
+        off = (-host.data_ptr()) % 128
+        grid = ctypes.c_int(0)
+        check(lib.mega_conv_chain_encode(arr, n, ctypes.c_void_p(host.data_ptr() + off), nbytes, ctypes.byref(grid)),
+              "mega_conv_chain_encode")
+        if max_ctas > 0 and grid.value > max_ctas:
+            raise _lib.MegaError("conv chain: a layer wants %d CTAs, more than max_ctas=%d (pass max_ctas to every "
+                                 "conv_gemm of the chain)" % (grid.value, max_ctas))
+        self.grid = grid.value
+        dev_buf = torch.zeros(nbytes + 128, dtype=torch.uint8, device=device)
+        doff = (-dev_buf.data_ptr()) % 128
+        self.plan = dev_buf[doff:doff + nbytes]
+        self.plan.copy_(host[off:off + nbytes])
+        self._keep = dev_buf
+        self.sync = torch.zeros(2, dtype=torch.int32, device=device)
+        self.flops = sum(_desc_flops(d) for d in descs)
+        self.info = {"chain_layers": n, "grid": self.grid, "layers": [_desc_info(d) for d in descs]}
+        torch.cuda.current_stream(device).synchronize()
+
+    def launch(self):
+        def run():
+            check(lib.mega_conv_chain_launch(ptr(self.plan), self.n, self.grid, ptr(self.sync), stream_ptr(),
+                                             1 if PDL[0] else 0), "mega_conv_chain_launch")
+        _run_timed(run, self.flops, self.info)
+        LAUNCHES[0] += 1
+
+
+class chain(object):
+    """context manager: record-once / replay a chain of conv_gemm calls (see above). `cache` is a dict owned by the
+    caller, `key` identifies the call sequence (shapes); disabled (plain per-layer launches) when the tensors are not
+    fp16, when chains are switched off, or while autotuning a shape for the first time."""
+
+    def __init__(self, cache, key, device, enabled=True, max_ctas=0):
+        self.cache, self.key, self.device, self.max_ctas = cache, key, device, max_ctas
+        self.enabled = enabled and CHAINS_ENABLED[0] and _CHAIN_MODE[0] is None
+
+    def __enter__(self):
+        if not self.enabled:
+            return self
+        self.saved_bn = MAX_BN[0]
+        MAX_BN[0] = 128
+        if self.key in self.cache:
+            _CHAIN_MODE[0] = "skip"
+        else:
+            _CHAIN_MODE[0] = "record"
+            _CHAIN_REC[0] = []
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if not self.enabled:
+            return False
+        mode = _CHAIN_MODE[0]
+        _CHAIN_MODE[0] = None
+        MAX_BN[0] = self.saved_bn
+        if et is not None:
+            _CHAIN_REC[0] = None
+            return False
+        if mode == "record":
+            descs = _CHAIN_REC[0]
+            _CHAIN_REC[0] = None
+            self.cache[self.key] = ConvChain(descs, self.device, self.max_ctas)
+        self.cache[self.key].launch()
+        return False
 
 
 # programmatic dependent launch of the GEMM kernels (prologue overlapped with the previous kernel's tail)
@@ -110,6 +228,8 @@ def _candidates(cout, prec=0, out_f16=0):
     for bn in ((64, 128) if prec == 1 else BLOCK_NS):
         if out_f16 and bn % 64:
             continue
+        if bn > MAX_BN[0]:
+            continue
         if bn >= 2 * cout and bn > (64 if out_f16 else 32):
             continue
         for sk in (0, 1):
@@ -148,10 +268,12 @@ def pick_config(cout, m_tiles, batch, kb_per_tile, out_f16=False):
         for bn in (32, 64, 128):
             if cout <= bn and not (out_f16 and bn % 64):
                 return bn, 1
-        return 256, 1
+        return min(256, MAX_BN[0]), 1
     best = None
     for bn in BLOCK_NS:
         if out_f16 and bn % 64:
+            continue
+        if bn > MAX_BN[0]:
             continue
         if bn >= 2 * cout and bn > (64 if out_f16 else 32):
             continue
@@ -232,10 +354,11 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.workspace = ptr(ws)
     d.workspace_bytes = ws.numel()
     if block_n is None and stream_k is None:
-        key = _shape_key(d)
+        key = _shape_key(d) + ((MAX_BN[0],) if MAX_BN[0] != 256 else ())
         cfg = TUNED.get(key)
         aliased = residual is not None and residual.data_ptr() == out.data_ptr()   # in-place: not idempotent
-        if cfg is None and AUTOTUNE[0] and not aliased and not torch.cuda.is_current_stream_capturing():
+        if (cfg is None and AUTOTUNE[0] and not aliased and _CHAIN_MODE[0] != "skip"
+                and not torch.cuda.is_current_stream_capturing()):
             best = _autotune(d)
             if best is not None:
                 cfg = TUNED[key] = (best[1], best[2], best[0])

@@ -242,3 +242,66 @@ def test_f16_linear_and_batched_heads(cuda_dev):
                   residual=xq.to(cuda_dev).view(1, 1, nq, heads * dh), block_n=64)
     torch.cuda.synchronize()
     assert _rel_err(out.float(), ref.float()) < 4e-3
+
+
+def test_f16_layer_chain_matches_per_layer_launches(cuda_dev):
+    """three bottleneck blocks (1x1 -> 3x3 -> 1x1 + residual, the res4 pattern at 2 x 38 x 63) + a 1x1 head with fp32
+    output, once as 10 separate launches and once as ONE persistent chain kernel (csrc/conv_chain.cu): with the tile
+    configuration pinned the two must agree bit for bit (same MMAs in the same order); replayed three times to
+    exercise the grid-barrier reset; also checked against an fp64 reference of the whole chain."""
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(21)
+    n, h, w, c, mid = 2, 38, 63, 512, 128
+    x0 = torch.randn(n, h, w, c, generator=g).half().to(cuda_dev)
+    blocks = []
+    for b in range(3):
+        w1 = (torch.randn(1, mid, c, generator=g) / c ** 0.5).half().to(cuda_dev)
+        w2 = (torch.randn(9, mid, mid, generator=g) / (9 * mid) ** 0.5).half().to(cuda_dev)
+        w3 = (torch.randn(1, c, mid, generator=g) / mid ** 0.5).half().to(cuda_dev)
+        sb = [(torch.rand(k, generator=g) * 0.5 + 0.75).to(cuda_dev) for k in (mid, mid, c)]
+        bb = [(torch.randn(k, generator=g) * 0.1).to(cuda_dev) for k in (mid, mid, c)]
+        blocks.append((w1, w2, w3, sb, bb))
+    wh = (torch.randn(1, 60, c, generator=g) / c ** 0.5).half().to(cuda_dev)
+
+    def run(bufs, stream_k):
+        x = x0
+        for b, (w1, w2, w3, sb, bb) in enumerate(blocks):
+            t1, t2, y = bufs["t1%d" % b], bufs["t2%d" % b], bufs["y%d" % b]
+            ops.conv_gemm(x, w1, t1, scale=sb[0], bias=bb[0], relu=True, block_n=128, stream_k=0)
+            ops.conv_gemm(t1, w2, t2, taps=(3, 3), pad=1, scale=sb[1], bias=bb[1], relu=True, block_n=64, stream_k=stream_k)
+            ops.conv_gemm(t2, w3, y, scale=sb[2], bias=bb[2], residual=x, relu=True, block_n=128, stream_k=0)
+            x = y
+        ops.conv_gemm(x, wh, bufs["head"], cout=60, block_n=64, stream_k=0)
+        return x, bufs["head"]
+
+    def mkbufs():
+        d = {}
+        for b in range(3):
+            d["t1%d" % b] = torch.full((n, h, w, mid), float("nan"), device=cuda_dev, dtype=torch.float16)
+            d["t2%d" % b] = torch.full((n, h, w, mid), float("nan"), device=cuda_dev, dtype=torch.float16)
+            d["y%d" % b] = torch.full((n, h, w, c), float("nan"), device=cuda_dev, dtype=torch.float16)
+        d["head"] = torch.full((n, h, w, 60), float("nan"), device=cuda_dev)
+        return d
+
+    for sk in (0, 1):
+        ref_bufs, ch_bufs = mkbufs(), mkbufs()
+        y_ref, head_ref = run(ref_bufs, sk)
+        cache = {}
+        for rep in range(3):
+            with ops.chain(cache, "k", cuda_dev):
+                y_ch, head_ch = run(ch_bufs, sk)
+        torch.cuda.synchronize()
+        assert len(cache) == 1 and cache["k"].n == 10
+        assert torch.equal(y_ch, y_ref) and torch.equal(head_ch, head_ref), (sk, (y_ch.float() - y_ref.float()).abs().max())
+    # fp64 reference of the chain (fp16 storage between layers reproduced)
+    x = x0.double().cpu()
+    for (w1, w2, w3, sb, bb) in blocks:
+        xin = x
+        t = F.conv2d(x.permute(0, 3, 1, 2), w1.double().cpu().reshape(mid, c, 1, 1))
+        t = (t * sb[0].double().cpu().view(1, -1, 1, 1) + bb[0].double().cpu().view(1, -1, 1, 1)).relu().half().double()
+        t = F.conv2d(t, w2.double().cpu().reshape(3, 3, mid, mid).permute(2, 3, 0, 1), padding=1)
+        t = (t * sb[1].double().cpu().view(1, -1, 1, 1) + bb[1].double().cpu().view(1, -1, 1, 1)).relu().half().double()
+        t = F.conv2d(t, w3.double().cpu().reshape(c, mid, 1, 1))
+        t = t * sb[2].double().cpu().view(1, -1, 1, 1) + bb[2].double().cpu().view(1, -1, 1, 1)
+        x = (t.permute(0, 2, 3, 1) + xin).relu().half().double()
+    assert _rel_err(y_ch.float(), x.float()) < 6e-3
