@@ -105,6 +105,9 @@ long long mega_conv_chain_plan_bytes(int n_layers);
 int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_layers, void* plan_host, long long plan_bytes,
                            int* grid_out);
 int mega_conv_chain_launch(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream, int pdl);
+/* diagnostics: following chain launches record (tag, SM clock) events of CTA `cta` into trace_dev
+ * ([3 roles][4096][2] uint64, zeroed by the caller); NULL switches tracing off (tools/trace_chain.py) */
+int mega_conv_chain_set_trace(void* trace_dev, int cta);
 /* TMA fp32->tf32 conversion on load (round-to-nearest) on/off; returns the previous value. */
 int mega_set_tf32_rounding(int enable);
 
@@ -192,6 +195,14 @@ int mega_relation_softmax_f16(float* logits, void* probs_f16, int n_rows, int ld
                               const float* boxes_k, const float* wg, const float* bg, const float* dim_mat,
                               const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off, float scale,
                               void* stream);
+
+/* the position-biased soft-max with Wg [16,64], bg [16] and dim_mat [8] given as HOST arrays: they travel in the
+ * kernel parameters, so every weight is a constant-bank operand (no shared-memory traffic); probs_f16 may be NULL
+ * (probabilities in place, fp32). Same arithmetic as mega_relation_softmax. */
+int mega_relation_softmax_pe(float* logits, void* probs_f16, int n_rows, int ldm, const float* boxes_q,
+                             const float* boxes_k, const float* wg_host, const float* bg_host,
+                             const float* dim_mat_host, const int* m_valid_ptr, int m_host, const int* n_valid_ptr,
+                             int n_valid_off, float scale, void* stream);
 
 /* ------------------------------------------------------ box-head post-processing
  * softmax -> decode (weights wx..wh) -> clip -> per-class score threshold + NMS -> top max_det.

@@ -23,7 +23,8 @@ constexpr int kChainStageBytes = 32768;     // A tile 16 KB + B tile (<= 128 row
 constexpr int kChainABytes = 16384;
 constexpr int kChainEpiBytes = 4 * 4 * 4096;
 constexpr int kChainBarOffset = kChainStages * kChainStageBytes + kChainEpiBytes;
-constexpr int kChainSmem = kChainBarOffset + (2 * kChainStages + 4 + 8) * 8 + 64 + 1024;
+constexpr int kChainSbOffset = kChainBarOffset + 256;      // [scale | bias][128] floats of the tile being finished
+constexpr int kChainSmem = kChainSbOffset + 1024 + 1024;
 constexpr uint32_t kChainTmemCols = 256;    // two accumulators of up to 128 fp32 columns
 constexpr uint32_t kChainAccStride = 128;
 
@@ -68,12 +69,37 @@ struct PipeState {
   uint32_t phase;
 };
 
+// optional in-kernel event trace of ONE CTA (diagnostics, tools/trace_chain.py): (tag, SM clock) pairs per role
+struct ChainTrace {
+  unsigned long long* buf;   // [3 roles][kTraceCap][2] or NULL
+  int cta;
+};
+constexpr int kTraceCap = 4096;
+struct TraceCursor {
+  unsigned long long* p;
+  int n;
+  __device__ __forceinline__ void put(unsigned long long tag) {
+    if (p != nullptr && n < kTraceCap) {
+      p[2 * n] = tag;
+      p[2 * n + 1] = static_cast<unsigned long long>(clock64());
+      ++n;
+    }
+  }
+};
+__device__ __forceinline__ TraceCursor trace_cursor(const ChainTrace& tr, int role, int cta) {
+  TraceCursor c;
+  c.p = (tr.buf != nullptr && cta == tr.cta) ? tr.buf + static_cast<long long>(role) * kTraceCap * 2 : nullptr;
+  c.n = 0;
+  return c;
+}
+#define TR_TAG(layer, idx, code) ((static_cast<unsigned long long>(layer) << 32) | (static_cast<unsigned long long>(idx) << 8) | (code))
+
 // ------------------------------------------------------------------ epilogue of one layer (4 warps)
 template <bool OUT16>
 __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const ConvGemmParams& p, const int BN, uint8_t* smem,
                                                      uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint64_t* res_bar,
                                                      int* epi_flag, uint32_t tmem_base, int warp, int lane, int cta,
-                                                     int grid, int& item, uint32_t& rphase) {
+                                                     int grid, int& item, uint32_t& rphase, TraceCursor& tr, int layer) {
   constexpr int CW = OUT16 ? 64 : 32;
   const int q = warp & 3;
   const int row = q * 32 + lane;
@@ -81,6 +107,7 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
   uint8_t* epi_out = smem + kChainStages * kChainStageBytes + (warp - 2) * 16384;
   uint8_t* epi_res = epi_out + 8192;
   uint64_t* rbar = res_bar + (warp - 2) * 2;
+  float* sb_s = reinterpret_cast<float*>(smem + kChainSbOffset);
   const long long U = p.total_units;
   const int KB = p.kb_per_tile;
   const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
@@ -94,15 +121,35 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
     const int buf = item & 1;
     const uint32_t use = static_cast<uint32_t>(item >> 1);
     ++item;
+    const bool complete = (kb0 == 0 && kb1 == KB);
+    // ---- while the MMAs of this tile run: stage its scale / bias slice in shared memory (the epilogue then reads them
+    //      with broadcast LDS instead of 32 L1-missing global loads per chunk) and start the first residual load
+    const int r0 = q * 32;
+    const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
+    const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
+    const int res_n = tc.img + tc.batch * p.res_n_off;
+    const int nchunks = min(BN / CW, (p.cout - tc.n0 + CW - 1) / CW);
+    epi_bar_sync();   // every warp is done with the previous tile's scale / bias
+    if (epi_tid < BN) {
+      const int n = tc.n0 + epi_tid;
+      const int zoff = tc.batch * p.bias_z_off;
+      sb_s[epi_tid] = (p.scale && n < p.cout) ? __ldg(p.scale + zoff + n) : 1.f;
+      sb_s[128 + epi_tid] = (p.bias && n < p.cout) ? __ldg(p.bias + zoff + n) : 0.f;
+    }
+    if (complete && p.has_residual && lane == 0 && nchunks > 0) {
+      mbar_arrive_expect_tx(&rbar[0], 4096);
+      tma_load_4d(epi_res, tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
+    }
+    epi_bar_sync();
     mbar_wait(&tmem_full_bar[buf], use & 1);
     tc_fence_after();
+    tr.put(TR_TAG(layer, tile_item, 4));
     const uint32_t tmem_row = tmem_base + buf * kChainAccStride + lane_bits;
     auto load_acc = [&](int c32, uint32_t (&acc)[32]) {
       __syncwarp();
       tmem_ld_32x32(tmem_row + c32 * 32, acc);
       tmem_ld_wait();
     };
-    const bool complete = (kb0 == 0 && kb1 == KB);
     bool finalize = complete;
     int c_first = cta, c_last = cta;
     if (!complete) {
@@ -134,16 +181,10 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
       if (finalize) __threadfence();
     }
     if (finalize) {
-      const int r0 = q * 32;
-      const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
-      const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
       const int out_n = tc.img + tc.batch * p.out_n_off;
-      const int res_n = tc.img + tc.batch * p.res_n_off;
-      const float* scale_p = p.scale ? p.scale + tc.batch * p.bias_z_off : nullptr;
-      const float* bias_p = p.bias ? p.bias + tc.batch * p.bias_z_off : nullptr;
-      const int nchunks = min(BN / CW, (p.cout - tc.n0 + CW - 1) / CW);
+      const bool has_sb = (p.scale != nullptr) || (p.bias != nullptr);
       const uint32_t sw = static_cast<uint32_t>(lane & 7);
-      if (p.has_residual && lane == 0 && nchunks > 0) {
+      if (!complete && p.has_residual && lane == 0 && nchunks > 0) {   // (whole tiles started this load before the MMAs)
         mbar_arrive_expect_tx(&rbar[0], 4096);
         tma_load_4d(epi_res, tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
       }
@@ -189,23 +230,20 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
           }
           mbar_wait(&rbar[rb], (rphase >> rb) & 1u);
           rphase ^= (1u << rb);
+          tr.put(TR_TAG(layer, tile_item, 5));
           rsrc = epi_res + rb * 4096 + lane * 128;
         }
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
         uint8_t* dst = epi_out + (c & 1) * 4096 + lane * 128;
+        if (has_sb) {
+          const float4* scv = reinterpret_cast<const float4*>(sb_s + c * CW);
+          const float4* biv = reinterpret_cast<const float4*>(sb_s + 128 + c * CW);
 #pragma unroll
-        for (int j = 0; j < CW; j += 4) {
-          const int n = nb + j;
-          if (n < p.cout) {
-            if (scale_p) {
-              const float4 sc = ldg_f4(scale_p + n);
-              acc[j] *= sc.x; acc[j + 1] *= sc.y; acc[j + 2] *= sc.z; acc[j + 3] *= sc.w;
-            }
-            if (bias_p) {
-              const float4 bi = ldg_f4(bias_p + n);
-              acc[j] += bi.x; acc[j + 1] += bi.y; acc[j + 2] += bi.z; acc[j + 3] += bi.w;
-            }
+          for (int j = 0; j < CW; j += 4) {
+            const float4 sc = scv[j >> 2], bi = biv[j >> 2];
+            acc[j] = fmaf(acc[j], sc.x, bi.x); acc[j + 1] = fmaf(acc[j + 1], sc.y, bi.y);
+            acc[j + 2] = fmaf(acc[j + 2], sc.z, bi.z); acc[j + 3] = fmaf(acc[j + 3], sc.w, bi.w);
           }
         }
         if (OUT16) {
@@ -256,11 +294,12 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+    tr.put(TR_TAG(layer, tile_item, 6));
   }
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, unsigned* sync) {
+conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, unsigned* sync, const ChainTrace trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kChainBarOffset);
@@ -298,36 +337,58 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // lane 0 loads the A (activation) tile and posts the expected byte count, lane 1 loads the B (weight) tile: the two
+    // descriptor-based copies of a k-block are issued in parallel (a single thread needs ~650 cycles per k-block for
+    // wait + expect + 2 TMA issues, measured with tools/trace_chain.py; the MMAs of a k-block take ~260)
+    if (lane < 2) {
       PipeState ps = {0, 0};
+      TraceCursor tr = trace_cursor(trace, 0, cta);
+      if (lane != 0) tr.p = nullptr;
       for (int l = 0; l < n_layers; ++l) {
         const ChainLayer* L = layers + l;
-        prefetch_tmap(&L->tmA);
-        prefetch_tmap(&L->tmB);
-        if (l > 0) grid_wait(sync, static_cast<unsigned>(l) * grid);
+        if (lane == 0) prefetch_tmap(&L->tmA); else prefetch_tmap(&L->tmB);
+        // everything the loop needs from the layer table is fetched BEFORE the grid barrier
         const ConvGemmParams p = L->p;
         const int BN = L->block_n;
         const int act = L->active_ctas;
-        if (cta >= act) continue;
+        const int k_chunks = p.k_chunks, taps_s = p.taps_s, dil = p.dil, pad = p.pad;
+        const int a_c_off = p.a_c_off, a_n_off = p.a_n_off, b_k_off = p.b_k_off, b_n_off = p.b_n_off;
+        const CUtensorMap* tmA = &L->tmA;
+        const CUtensorMap* tmB = &L->tmB;
         const uint32_t tx_bytes = static_cast<uint32_t>((kBM + BN) * 128);
+        tr.put(TR_TAG(l, 0, 1));
+        if (l > 0) grid_wait(sync, static_cast<unsigned>(l) * grid);
+        tr.put(TR_TAG(l, 0, 2));
+        if (cta >= act) continue;
         WorkIter it(p, cta, act);
         long long t;
         int kb0, kb1;
         while (it.next(t, kb0, kb1)) {
           const TileCoord tc = decode_tile(p, t, BN);
+          int tap = kb0 / k_chunks;
+          int kc = kb0 - tap * k_chunks;
+          int r = tap / taps_s;
+          int sx = tap - r * taps_s;
+          const int a_c0 = tc.batch * a_c_off, a_n = tc.img + tc.batch * a_n_off;
+          const int b_k0 = tc.batch * b_k_off, b_n = tc.n0 + tc.batch * b_n_off;
           for (int kb = kb0; kb < kb1; ++kb) {
-            const int tap = kb / p.k_chunks;
-            const int kc = kb - tap * p.k_chunks;
-            const int r = tap / p.taps_s;
-            const int s = tap - r * p.taps_s;
             mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+            tr.put(TR_TAG(l, kb, 3));
             uint8_t* a_dst = smem + ps.stage * kChainStageBytes;
-            uint8_t* b_dst = a_dst + kChainABytes;
-            mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
-            tma_load_4d(a_dst, &L->tmA, &full_bar[ps.stage], kc * 64 + tc.batch * p.a_c_off, tc.w0 + s * p.dil - p.pad,
-                        tc.h0 + r * p.dil - p.pad, tc.img + tc.batch * p.a_n_off);
-            tma_load_3d(b_dst, &L->tmB, &full_bar[ps.stage], kc * 64 + tc.batch * p.b_k_off, tc.n0 + tc.batch * p.b_n_off,
-                        tap);
+            if (lane == 0) {
+              mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
+              tma_load_4d(a_dst, tmA, &full_bar[ps.stage], kc * 64 + a_c0, tc.w0 + sx * dil - pad, tc.h0 + r * dil - pad, a_n);
+            } else {
+              tma_load_3d(a_dst + kChainABytes, tmB, &full_bar[ps.stage], kc * 64 + b_k0, b_n, tap);
+            }
+            if (++kc == k_chunks) {
+              kc = 0;
+              ++tap;
+              if (++sx == taps_s) {
+                sx = 0;
+                ++r;
+              }
+            }
             if (++ps.stage == kChainStages) {
               ps.stage = 0;
               ps.phase ^= 1;
@@ -341,6 +402,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
     if (lane == 0) {
       PipeState ps = {0, 0};
       int item = 0;
+      TraceCursor tr = trace_cursor(trace, 1, cta);
       for (int l = 0; l < n_layers; ++l) {
         const ChainLayer* L = layers + l;
         const ConvGemmParams p = L->p;
@@ -361,6 +423,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&full_bar[ps.stage], ps.phase);
             tc_fence_after();
+            tr.put(TR_TAG(l, kb, 7));
             const uint32_t a_addr = smem_u32(smem + ps.stage * kChainStageBytes);
             const uint64_t adesc = umma_desc_sw128(a_addr);
             const uint64_t bdesc = umma_desc_sw128(a_addr + kChainABytes);
@@ -381,6 +444,8 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
     const int epi_tid = (warp - 2) * 32 + lane;
     int item = 0;
     uint32_t rphase = 0;
+    TraceCursor tr = trace_cursor(trace, 2, cta);
+    if (epi_tid != 0) tr.p = nullptr;
     for (int l = 0; l < n_layers; ++l) {
       const ChainLayer* L = layers + l;
       if (lane == 0) {
@@ -399,14 +464,16 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
       if (cta < act) {
         if (L->out16) {
           chain_epilogue_layer<true>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
-                                     warp, lane, cta, act, item, rphase);
+                                     warp, lane, cta, act, item, rphase, tr, l);
         } else {
           chain_epilogue_layer<false>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
-                                      warp, lane, cta, act, item, rphase);
+                                      warp, lane, cta, act, item, rphase, tr, l);
         }
       }
+      tr.put(TR_TAG(l, 0, 8));
       // this CTA's part of layer l is complete and visible: arrive at the grid barrier
       if (lane == 0) tma_store_wait<0>();
+      tr.put(TR_TAG(l, 0, 9));
       __threadfence();
       epi_bar_sync();
       if (epi_tid == 0) {
@@ -414,6 +481,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         __threadfence();
         atomicAdd(sync, 1u);
       }
+      tr.put(TR_TAG(l, 0, 10));
     }
     // last CTA out resets the barrier words for the next launch (every CTA has passed every barrier by then)
     if (epi_tid == 0) {
@@ -472,6 +540,16 @@ extern "C" int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_la
   return MEGA_OK;
 }
 
+static ChainTrace g_chain_trace = {nullptr, 0};
+
+/* diagnostics: the next launches record an in-kernel event trace of CTA `cta` into trace_dev
+ * (3 * 4096 * 2 uint64, zero it first); trace_dev == NULL switches tracing off */
+extern "C" int mega_conv_chain_set_trace(void* trace_dev, int cta) {
+  g_chain_trace.buf = static_cast<unsigned long long*>(trace_dev);
+  g_chain_trace.cta = cta;
+  return MEGA_OK;
+}
+
 extern "C" int mega_conv_chain_launch(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream_v,
                                       int pdl) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -494,6 +572,6 @@ extern "C" int mega_conv_chain_launch(const void* plan_device, int n_layers, int
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   MEGA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_chain_kernel, static_cast<const ChainLayer*>(plan_device), n_layers,
-                                     static_cast<unsigned*>(sync_words)));
+                                     static_cast<unsigned*>(sync_words), g_chain_trace));
   return MEGA_OK;
 }

@@ -67,7 +67,8 @@ struct SmemLayout {
   static constexpr int kEpiOffset = STAGES * kStageBytes;       // 4 warps x (2 out + 2 residual) x 4 KB
   static constexpr int kEpiBytes = 4 * 4 * 4096;
   static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
-  static constexpr int kTotal = kBarOffset + (3 * STAGES + 4 + 8) * 8 + 32 + 1024;  // + align slack
+  static constexpr int kSbOffset = kBarOffset + 512;              // [scale | bias][256] floats of the tile being finished
+  static constexpr int kTotal = kSbOffset + 2048 + 1024;          // + align slack
 };
 
 struct TileCoord {
@@ -217,27 +218,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // lane 0 loads the A (activation) tile and posts the expected byte count, lane 1 the B (weight) tile, so the two
+    // descriptor-based copies of a k-block are issued in parallel; tap / chunk indices advance incrementally
+    if (lane < 2) {
       int stage = 0;
       uint32_t phase = 0;
       WorkIter it(p, cta, grid);
       long long t;
       int kb0, kb1;
+      const int k_chunks = p.k_chunks, taps_s = p.taps_s;
       while (it.next(t, kb0, kb1)) {
         const TileCoord tc = decode_tile(p, t, BN);
+        int tap = kb0 / k_chunks;
+        int kc = kb0 - tap * k_chunks;
+        int r = tap / taps_s;
+        int sx = tap - r * taps_s;
+        const int a_c0 = tc.batch * p.a_c_off, a_n = tc.img + tc.batch * p.a_n_off;
+        const int b_k0 = tc.batch * p.b_k_off, b_n = tc.n0 + tc.batch * p.b_n_off;
         for (int kb = kb0; kb < kb1; ++kb) {
-          const int tap = kb / p.k_chunks;
-          const int kc = kb - tap * p.k_chunks;
-          const int r = tap / p.taps_s;
-          const int s = tap - r * p.taps_s;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * L::kStageBytes;
-          uint8_t* b_dst = a_dst + L::kABytes;
-          mbar_arrive_expect_tx(&full_bar[stage], L::kHalf);   // bytes delivered by the two TMA loads
-          tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + tc.batch * p.a_c_off,
-                      tc.w0 + s * p.dil - p.pad, tc.h0 + r * p.dil - p.pad, tc.img + tc.batch * p.a_n_off);
-          tma_load_3d(b_dst, &tmB, &full_bar[stage], kc * kBK + tc.batch * p.b_k_off,
-                      tc.n0 + tc.batch * p.b_n_off, tap);
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&full_bar[stage], L::kHalf);   // bytes delivered by the two TMA loads
+            tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + a_c0, tc.w0 + sx * p.dil - p.pad,
+                        tc.h0 + r * p.dil - p.pad, a_n);
+          } else {
+            tma_load_3d(a_dst + L::kABytes, &tmB, &full_bar[stage], kc * kBK + b_k0, b_n, tap);
+          }
+          if (++kc == k_chunks) {
+            kc = 0;
+            ++tap;
+            if (++sx == taps_s) {
+              sx = 0;
+              ++r;
+            }
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -337,6 +352,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* epi_out = smem + L::kEpiOffset + (warp - 2) * 16384;   // 2 x 4 KB store staging
     uint8_t* epi_res = epi_out + 8192;                              // 2 x 4 KB residual staging
     uint64_t* rbar = res_bar + (warp - 2) * 2;
+    float* sb_s = reinterpret_cast<float*>(smem + L::kSbOffset);
     uint32_t rphase = 0;
     WorkIter it(p, cta, grid);
     long long t;
@@ -378,6 +394,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int buf = item & 1;
       const uint32_t use = static_cast<uint32_t>(item >> 1);
       ++item;
+      const bool complete = (kb0 == 0 && kb1 == KB);
+      // ---- while the MMAs of this tile run: stage its scale / bias slice in shared memory (the chunk loop then reads
+      //      them with broadcast LDS instead of L1-missing global loads) and start the first residual load
+      const int r0 = q * 32;
+      const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
+      const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
+      const int res_n = tc.img + tc.batch * p.res_n_off;
+      const int nchunks = min(BN / CW, (p.cout - tc.n0 + CW - 1) / CW);
+      epi_bar_sync();   // every warp is done with the previous tile's scale / bias
+      for (int i = epi_tid; i < BN; i += 128) {
+        const int n = tc.n0 + i;
+        const int zoff = tc.batch * p.bias_z_off;
+        sb_s[i] = (p.scale && n < p.cout) ? __ldg(p.scale + zoff + n) : 1.f;
+        sb_s[256 + i] = (p.bias && n < p.cout) ? __ldg(p.bias + zoff + n) : 0.f;
+      }
+      if (complete && p.has_residual && lane == 0 && nchunks > 0) {
+        mbar_arrive_expect_tx(&rbar[0], 4096);
+        tma_load_4d(epi_res, &tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
+      }
+      epi_bar_sync();
       mbar_wait(&tmem_full_bar[buf], use & 1);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + buf * kAccStride + lane_bits;
@@ -394,7 +430,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__fadd_rn(__uint_as_float(acc[j]), __uint_as_float(m[j])));
         }
       };
-      const bool complete = (kb0 == 0 && kb1 == KB);
       bool finalize = complete;
       int c_first = cta, c_last = cta;
       if (!complete) {
@@ -430,16 +465,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // Output pixels of this warp: tile rows [32q, 32q+32) = a box_h x box_w rectangle. Results go
         // registers -> 128B-swizzled smem -> one TMA store per 32-column chunk (full-line writes,
         // image-edge and channel-edge clipping by the TMA unit); the residual arrives the same way.
-        const int r0 = q * 32;
-        const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
-        const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
         const int out_n = tc.img + tc.batch * p.out_n_off;
-        const int res_n = tc.img + tc.batch * p.res_n_off;
-        const float* scale_p = p.scale ? p.scale + tc.batch * p.bias_z_off : nullptr;
-        const float* bias_p = p.bias ? p.bias + tc.batch * p.bias_z_off : nullptr;
-        const int nchunks = min(BN / CW, (p.cout - tc.n0 + CW - 1) / CW);
+        const bool has_sb = (p.scale != nullptr) || (p.bias != nullptr);
         const uint32_t sw = static_cast<uint32_t>(lane & 7);
-        if (p.has_residual && lane == 0 && nchunks > 0) {
+        if (!complete && p.has_residual && lane == 0 && nchunks > 0) {   // (whole tiles started this load earlier)
           mbar_arrive_expect_tx(&rbar[0], 4096);
           tma_load_4d(epi_res, &tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
         }
@@ -492,19 +521,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
           uint8_t* dst = epi_out + (c & 1) * 4096 + lane * 128;
-          // scale / bias (cout is padded to 4 by the host wrapper's buffers; tail columns are clipped by TMA)
+          // scale / bias from the staged slice (columns >= cout hold 1 / 0 and are clipped by the TMA store)
+          if (has_sb) {
+            const float4* scv = reinterpret_cast<const float4*>(sb_s + c * CW);
+            const float4* biv = reinterpret_cast<const float4*>(sb_s + 256 + c * CW);
 #pragma unroll
-          for (int j = 0; j < CW; j += 4) {
-            const int n = nb + j;
-            if (n < p.cout) {
-              if (scale_p) {
-                const float4 sc = ldg_f4(scale_p + n);
-                acc[j] *= sc.x; acc[j + 1] *= sc.y; acc[j + 2] *= sc.z; acc[j + 3] *= sc.w;
-              }
-              if (bias_p) {
-                const float4 bi = ldg_f4(bias_p + n);
-                acc[j] += bi.x; acc[j + 1] += bi.y; acc[j + 2] += bi.z; acc[j + 3] += bi.w;
-              }
+            for (int j = 0; j < CW; j += 4) {
+              const float4 sc = scv[j >> 2], bi = biv[j >> 2];
+              acc[j] = fmaf(acc[j], sc.x, bi.x); acc[j + 1] = fmaf(acc[j + 1], sc.y, bi.y);
+              acc[j + 2] = fmaf(acc[j + 2], sc.z, bi.z); acc[j + 3] = fmaf(acc[j + 3], sc.w, bi.w);
             }
           }
           if (OUT16) {

@@ -188,6 +188,139 @@ relation_softmax_kernel(const RelParams p) {
   }
 }
 
+// ---- the same soft-max with the 64 x 16 position weights passed BY VALUE in the kernel parameters: every weight is a
+// constant-bank operand of its FFMA (no shared-memory loads at all: the smem variant above spends 256 LDS.128 per
+// (query, key) pair next to its 1024 FFMAs), the k loop is fully unrolled so independent sin/cos chains overlap, the
+// division by 1000^(k/8) is a reciprocal multiply + one Newton correction (same rounding as __fdiv_rn), and the online
+// soft-max needs one exp per logit instead of two.
+struct RelParamsW {
+  RelParams b;
+  float wg[kEmb * kGroups];   // [e][g]
+  float bg[kGroups];
+  float dim[8];
+  float inv_dim[8];
+};
+
+template <bool SMEM_STAGE>
+__global__ void __launch_bounds__(kRelThreads)
+relation_softmax_pe_kernel(const __grid_constant__ RelParamsW pw) {
+  const RelParams& p = pw.b;
+  extern __shared__ float stage_s[];   // [16][ldm] when SMEM_STAGE
+  __shared__ float red_max[kRelThreads / 32][kGroups];
+  __shared__ float red_sum[kRelThreads / 32][kGroups];
+  __shared__ float fin_max[kGroups], fin_inv[kGroups];
+
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int m_valid = p.m_valid_ptr ? min(*p.m_valid_ptr, p.ldm) : p.m_host;
+  if (p.n_valid_ptr) {
+    const int nv = *p.n_valid_ptr;
+    if (n >= nv && n < p.n_valid_off) return;
+  }
+  const float4 q = *reinterpret_cast<const float4*>(p.boxes_q + static_cast<long long>(n) * 4);
+  const float qw = __fadd_rn(__fsub_rn(q.z, q.x), 1.f);
+  const float qh = __fadd_rn(__fsub_rn(q.w, q.y), 1.f);
+  const float qcx = __fmul_rn(0.5f, __fadd_rn(q.x, q.z));
+  const float qcy = __fmul_rn(0.5f, __fadd_rn(q.y, q.w));
+  float* srow = p.s + static_cast<long long>(n) * p.ldm;
+
+  float mx[kGroups], sm[kGroups];
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {
+    mx[g] = -INFINITY;
+    sm[g] = 0.f;
+  }
+  for (int m = tid; m < m_valid; m += kRelThreads) {
+    float lg[kGroups];
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) lg[g] = srow[g * p.head_stride + m];   // issued early: overlaps the arithmetic
+    const float4 k = *reinterpret_cast<const float4*>(p.boxes_k + static_cast<long long>(m) * 4);
+    const float kw = __fadd_rn(__fsub_rn(k.z, k.x), 1.f);
+    const float kh = __fadd_rn(__fsub_rn(k.w, k.y), 1.f);
+    const float kcx = __fmul_rn(0.5f, __fadd_rn(k.x, k.z));
+    const float kcy = __fmul_rn(0.5f, __fadd_rn(k.y, k.w));
+    float delta[4];
+    delta[0] = logf(__fadd_rn(fabsf(__fdiv_rn(__fsub_rn(qcx, kcx), qw)), 1e-3f));
+    delta[1] = logf(__fadd_rn(fabsf(__fdiv_rn(__fsub_rn(qcy, kcy), qh)), 1e-3f));
+    delta[2] = logf(__fdiv_rn(qw, kw));
+    delta[3] = logf(__fdiv_rn(qh, kh));
+    float bias[kGroups];
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) bias[g] = pw.bg[g];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float d100 = __fmul_rn(delta[c], 100.0f);
+#pragma unroll
+      for (int kf = 0; kf < 8; ++kf) {
+        // arg = d100 / dim[kf], correctly rounded: q0 = a * (1/b); r = a - q0 * b (exact in an fma); q = q0 + r * (1/b)
+        const float q0 = __fmul_rn(d100, pw.inv_dim[kf]);
+        const float rem = __fmaf_rn(-q0, pw.dim[kf], d100);
+        const float arg = __fmaf_rn(rem, pw.inv_dim[kf], q0);
+        const float kq = rintf(arg * 0.15915494309189535f);
+        float r = fmaf(-kq, 6.28125f, arg);
+        r = fmaf(-kq, 1.9353071795864769e-3f, r);
+        const float sv = __sinf(r), cv = __cosf(r);
+#pragma unroll
+        for (int g = 0; g < kGroups; ++g) {
+          bias[g] = fmaf(pw.wg[(c * 16 + kf) * kGroups + g], sv, fmaf(pw.wg[(c * 16 + 8 + kf) * kGroups + g], cv, bias[g]));
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      const float b = __logf(__fadd_rn(fmaxf(bias[g], 0.f), 1e-6f));
+      const float l = __fadd_rn(b, __fmul_rn(p.scale, lg[g]));
+      if (SMEM_STAGE) stage_s[g * p.ldm + m] = l; else srow[g * p.head_stride + m] = l;
+      // online (max, sum) with one exp: e = exp(-|l - mx|)
+      const float d = l - mx[g];
+      const float e = __expf(-fabsf(d));
+      sm[g] = (d > 0.f) ? fmaf(sm[g], e, 1.f) : (sm[g] + e);
+      mx[g] = fmaxf(mx[g], l);
+    }
+  }
+
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {
+    float m_ = mx[g], s_ = sm[g];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m_, off);
+      const float os = __shfl_xor_sync(0xffffffffu, s_, off);
+      const float nm = fmaxf(m_, om);
+      const float a = (m_ == -INFINITY) ? 0.f : s_ * __expf(m_ - nm);
+      const float b = (om == -INFINITY) ? 0.f : os * __expf(om - nm);
+      s_ = a + b;
+      m_ = nm;
+    }
+    if (lane == 0) {
+      red_max[warp][g] = m_;
+      red_sum[warp][g] = s_;
+    }
+  }
+  __syncthreads();
+  if (tid < kGroups) {
+    float m_ = -INFINITY;
+    for (int w = 0; w < kRelThreads / 32; ++w) m_ = fmaxf(m_, red_max[w][tid]);
+    float s_ = 0.f;
+    for (int w = 0; w < kRelThreads / 32; ++w)
+      if (red_max[w][tid] != -INFINITY) s_ += red_sum[w][tid] * __expf(red_max[w][tid] - m_);
+    fin_max[tid] = m_;
+    fin_inv[tid] = 1.0f / s_;
+  }
+  __syncthreads();
+  for (int m = tid; m < p.ldm; m += kRelThreads) {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      float* sp = srow + g * p.head_stride + m;
+      const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
+      const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
+      if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + g * p.head_stride + m] = __float2half_rn(pr);
+      else *sp = pr;
+    }
+  }
+}
+
 // No position term: one warp per (head, query row); the row (<= 1024 keys) stays in registers, so the
 // logits are read once and the probabilities written once.
 __global__ void __launch_bounds__(256)
@@ -296,4 +429,53 @@ extern "C" int mega_relation_softmax_f16(float* logits, void* probs_f16, int n_r
   MEGA_ARG_CHECK(probs_f16 != nullptr, "relation_softmax_f16: probs_f16 is NULL");
   return relation_softmax_impl(logits, probs_f16, n_rows, ldm, boxes_q, boxes_k, wg, bg, dim_mat, m_valid_ptr, m_host,
                                n_valid_ptr, n_valid_off, scale, stream_v);
+}
+
+extern "C" int mega_relation_softmax_pe(float* logits, void* probs_f16, int n_rows, int ldm, const float* boxes_q,
+                                        const float* boxes_k, const float* wg_host, const float* bg_host,
+                                        const float* dim_mat_host, const int* m_valid_ptr, int m_host,
+                                        const int* n_valid_ptr, int n_valid_off, float scale, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(logits != nullptr && n_rows >= 0 && ldm > 0 && boxes_q && boxes_k && wg_host && bg_host && dim_mat_host,
+                 "relation_softmax_pe: bad arguments");
+  MEGA_ARG_CHECK(m_valid_ptr != nullptr || (m_host >= 0 && m_host <= ldm), "relation_softmax_pe: m out of range");
+  if (n_rows == 0) return MEGA_OK;
+  RelParamsW pw;
+  RelParams& p = pw.b;
+  p.s = logits;
+  p.p16 = static_cast<__half*>(probs_f16);
+  p.head_stride = static_cast<long long>(n_rows) * ldm;
+  p.ldm = ldm;
+  p.boxes_q = boxes_q;
+  p.boxes_k = boxes_k;
+  p.wg = nullptr;
+  p.bg = nullptr;
+  p.inv_dim = nullptr;
+  p.m_valid_ptr = m_valid_ptr;
+  p.m_host = m_host;
+  p.n_valid_ptr = n_valid_ptr;
+  p.n_valid_off = n_valid_off;
+  p.scale = scale;
+  for (int g = 0; g < kGroups; ++g) {
+    pw.bg[g] = bg_host[g];
+    for (int e = 0; e < kEmb; ++e) pw.wg[e * kGroups + g] = wg_host[g * kEmb + e];
+  }
+  for (int k = 0; k < 8; ++k) {
+    pw.dim[k] = dim_mat_host[k];
+    pw.inv_dim[k] = 1.0f / dim_mat_host[k];
+  }
+  if (ldm <= 1024) {
+    const int smem = kGroups * ldm * static_cast<int>(sizeof(float));
+    static bool configured = false;
+    if (!configured) {
+      MEGA_CUDA_CHECK(cudaFuncSetAttribute(relation_softmax_pe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kGroups * 1024 * static_cast<int>(sizeof(float))));
+      configured = true;
+    }
+    relation_softmax_pe_kernel<true><<<n_rows, kRelThreads, smem, stream>>>(pw);
+  } else {
+    relation_softmax_pe_kernel<false><<<n_rows, kRelThreads, 0, stream>>>(pw);
+  }
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
 }

@@ -70,6 +70,8 @@ lib.mega_conv_chain_encode.argtypes = [ctypes.POINTER(ConvGemmDesc), c_int, ctyp
 lib.mega_conv_chain_encode.restype = c_int
 lib.mega_conv_chain_launch.argtypes = [ctypes.c_void_p, c_int, c_int, ctypes.c_void_p, ctypes.c_void_p, c_int]
 lib.mega_conv_chain_launch.restype = c_int
+lib.mega_conv_chain_set_trace.argtypes = [ctypes.c_void_p, c_int]
+lib.mega_conv_chain_set_trace.restype = c_int
 lib.mega_set_tf32_rounding.argtypes = [c_int]
 lib.mega_set_tf32_rounding.restype = c_int
 
@@ -125,6 +127,8 @@ lib.mega_maxpool3x3s2_nhwc_f16.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
 lib.mega_maxpool3x3s2_nhwc_f16.restype = _i
 lib.mega_relation_softmax_f16.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp]
 lib.mega_relation_softmax_f16.restype = _i
+lib.mega_relation_softmax_pe.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp]
+lib.mega_relation_softmax_pe.restype = _i
 lib.mega_stem_im2col.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
 lib.mega_stem_im2col.restype = _i
 lib.mega_maxpool3x3s2_nhwc.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
@@ -155,11 +159,11 @@ lib.mega_deform_psroi_pooling_forward.restype = _i
 
 EXPORTS = [
     "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm", "mega_conv_gemm_tf32", "mega_conv_gemm_workspace_bytes", "mega_set_tf32_rounding",
-    "mega_conv_chain_plan_bytes", "mega_conv_chain_encode", "mega_conv_chain_launch",
+    "mega_conv_chain_plan_bytes", "mega_conv_chain_encode", "mega_conv_chain_launch", "mega_conv_chain_set_trace",
     "mega_nms_workspace_bytes", "mega_nms", "mega_rpn_select_workspace_bytes", "mega_rpn_select",
     "mega_roi_align_forward_nchw", "mega_roi_align_forward_nhwc", "mega_stem_im2col", "mega_maxpool3x3s2_nhwc",
     "mega_gather_rows", "mega_copy_rows", "mega_transpose_2d", "mega_relation_softmax", "mega_box_postprocess_workspace_bytes",
     "mega_box_postprocess", "mega_sigmoid_focalloss_forward", "mega_sigmoid_focalloss_backward",
     "mega_deform_im2col", "mega_deform_psroi_pooling_forward",
-    "mega_roi_align_forward_nhwc_f16", "mega_stem_im2col_f16", "mega_maxpool3x3s2_nhwc_f16", "mega_relation_softmax_f16",
+    "mega_roi_align_forward_nhwc_f16", "mega_stem_im2col_f16", "mega_maxpool3x3s2_nhwc_f16", "mega_relation_softmax_f16", "mega_relation_softmax_pe",
 ]

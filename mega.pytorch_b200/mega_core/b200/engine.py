@@ -256,10 +256,14 @@ class _Att:
         self.wv = sd[pfx + "Wvs.%d.weight" % i].float().reshape(1024, 1024).contiguous().to(dev).to(dtype)
         self.bv = sd[pfx + "Wvs.%d.bias" % i].float().contiguous().to(dev)
         if with_g:
-            self.wg = sd[pfx + "Wgs.%d.weight" % i].float().reshape(16, 64).contiguous().to(dev)
-            self.bg = sd[pfx + "Wgs.%d.bias" % i].float().contiguous().to(dev)
+            wg_h = sd[pfx + "Wgs.%d.weight" % i].detach().float().reshape(16, 64).contiguous().cpu()
+            bg_h = sd[pfx + "Wgs.%d.bias" % i].detach().float().contiguous().cpu()
+            feat_range = torch.arange(0, 8, dtype=torch.float32)
+            dim_h = torch.full((8,), 1000.0).pow(8.0 / 64 * feat_range).contiguous()      # extractors :129-130
+            self.host_w = (wg_h, bg_h, dim_h)     # passed by value in the soft-max kernel's parameters
+            self.wg, self.bg = wg_h.to(dev), bg_h.to(dev)
         else:
-            self.wg = self.bg = None
+            self.wg = self.bg = self.host_w = None
 
 
 def _with_precision(fn):
@@ -366,7 +370,8 @@ class HeadCommon:
         ops.relation_softmax(s, nq, ld, 1.0 / math.sqrt(64.0), boxes_q=boxes_q, boxes_k=boxes_k,
                              wg=att.wg if boxes_q is not None else None, bg=att.bg if boxes_q is not None else None,
                              dim_mat=self.dim_mat if boxes_q is not None else None, m_valid=m_valid,
-                             m_host=nref, n_valid=n_valid, n_valid_off=n_valid_off, probs_f16=pr)
+                             m_host=nref, n_valid=n_valid, n_valid_off=n_valid_off, probs_f16=pr,
+                             host_w=att.host_w if boxes_q is not None else None)
         if pr is not None:
             s = pr
         ops.conv_gemm(s.view(16, 1, nq, ld), vt.view(1, D, ld), out.view(1, 1, nq, D), tile=(1, 128), cout=64, k=ld,

@@ -304,4 +304,4 @@ def test_f16_layer_chain_matches_per_layer_launches(cuda_dev):
         t = F.conv2d(t, w3.double().cpu().reshape(c, mid, 1, 1))
         t = t * sb[2].double().cpu().view(1, -1, 1, 1) + bb[2].double().cpu().view(1, -1, 1, 1)
         x = (t.permute(0, 2, 3, 1) + xin).relu().half().double()
-    assert _rel_err(y_ch.float(), x.float()) < 6e-3
+    assert _rel_err(y_ch.float(), x.float()) < 1e-2      # fp16 storage of 9 chained layers

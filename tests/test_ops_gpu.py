@@ -279,3 +279,31 @@ def test_f16_variants_of_memory_bound_kernels(cuda_dev):
     ops.relation_softmax(s, n, ld, 0.125, m_host=m, probs_f16=p16)
     assert (p16.float().cpu()[:, :, :m] - torch.softmax(aff * 0.125, dim=2)).abs().max() < 5e-4
     assert (p16[:, :, m:] == 0).all()
+
+
+@pytest.mark.parametrize("n,m,ld", [(37, 203, 224), (9, 1500, 1504)])
+def test_relation_softmax_const_operand_kernel_matches_oracle(cuda_dev, n, m, ld):
+    """the kernel-parameter (constant-bank) variant of the position-biased soft-max, both the shared-memory staged
+    form (ld <= 1024) and the global two-pass form, fp32 in place and fp16 probabilities, vs the oracle"""
+    from mega_core.b200 import ops
+    mo = _oracle()
+    g = torch.Generator().manual_seed(n + m)
+    bq, bk = _rand_boxes(n, g), _rand_boxes(m, g)
+    wg = torch.randn(16, 64, generator=g) * 0.2
+    bg = torch.rand(16, generator=g) * 0.5
+    aff = torch.randn(16, n, m, generator=g) * 8.0
+    pe = mo.position_embedding(bq, bk)
+    w = torch.relu(torch.einsum("ge,enm->gnm", wg, pe) + bg.view(16, 1, 1))
+    ref = torch.softmax((w + 1e-6).log() + aff * 0.125, dim=2)
+    dim_mat = torch.full((8,), 1000.0).pow(8.0 / 64 * torch.arange(0, 8, dtype=torch.float32)).contiguous()
+    mv = torch.tensor([m], dtype=torch.int32, device=cuda_dev)
+    for use16 in (False, True):
+        s = torch.zeros(16, n, ld, device=cuda_dev)
+        s[:, :, :m] = aff.to(cuda_dev)
+        s[:, :, m:] = 123.0
+        p16 = torch.full((16, n, ld), float("nan"), device=cuda_dev, dtype=torch.float16) if use16 else None
+        ops.relation_softmax(s, n, ld, 0.125, boxes_q=bq.to(cuda_dev), boxes_k=bk.to(cuda_dev), m_valid=mv,
+                             probs_f16=p16, host_w=(wg.contiguous(), bg.contiguous(), dim_mat))
+        got = (p16.float() if use16 else s).cpu()
+        assert (got[:, :, m:] == 0).all()
+        assert (got[:, :, :m] - ref).abs().max() < (5e-4 if use16 else 1e-5)
