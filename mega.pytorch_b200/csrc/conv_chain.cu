@@ -108,13 +108,13 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
   uint8_t* epi_res = epi_out + 8192;
   uint64_t* rbar = res_bar + (warp - 2) * 2;
   float* sb_s = reinterpret_cast<float*>(smem + kChainSbOffset);
-  const long long U = p.total_units;
+  const int U = static_cast<int>(p.total_units);
   const int KB = p.kb_per_tile;
   const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
   const CUtensorMap* tmOut = &L->tmOut;
   const CUtensorMap* tmRes = &L->tmRes;
   WorkIter it(p, cta, grid);
-  long long t;
+  int t;
   int kb0, kb1;
   for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
     const TileCoord tc = decode_tile(p, t, BN);
@@ -361,7 +361,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         tr.put(TR_TAG(l, 0, 2));
         if (cta >= act) continue;
         WorkIter it(p, cta, act);
-        long long t;
+        int t;
         int kb0, kb1;
         while (it.next(t, kb0, kb1)) {
           const TileCoord tc = decode_tile(p, t, BN);
@@ -411,7 +411,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         if (cta >= act) continue;
         const uint32_t idesc = umma_idesc<0>(kBM, BN);
         WorkIter it(p, cta, act);
-        long long t;
+        int t;
         int kb0, kb1;
         while (it.next(t, kb0, kb1)) {
           const int buf = item & 1;
@@ -472,9 +472,10 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
       }
       tr.put(TR_TAG(l, 0, 8));
       // this CTA's part of layer l is complete and visible: arrive at the grid barrier
+      // (stream-K partial sums were fenced by their writers; the TMA stores of every warp are complete after its
+      //  wait_group; the named barrier orders all of that before thread 0's single gpu-scope release)
       if (lane == 0) tma_store_wait<0>();
       tr.put(TR_TAG(l, 0, 9));
-      __threadfence();
       epi_bar_sync();
       if (epi_tid == 0) {
         fence_proxy_async_all();

@@ -225,6 +225,8 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   p.stream_k = d->stream_k ? 1 : 0;
   MEGA_ARG_CHECK(tiles <= kCounterSlots, "conv_gemm: %lld output tiles exceed the %d counter slots", tiles, kCounterSlots);
   MEGA_ARG_CHECK(p.total_units > 0, "conv_gemm: empty problem");
+  MEGA_ARG_CHECK(p.total_units * kMaxCtas < (1LL << 31), "conv_gemm: %lld work units exceed the 32-bit work-list range",
+                 p.total_units);
   p.counters = static_cast<int*>(d->workspace);
   p.part_ws = reinterpret_cast<float*>(static_cast<char*>(d->workspace) + kCounterSlots * sizeof(int));
   if (g_num_sms == 0) {

@@ -75,12 +75,14 @@ struct TileCoord {
   int img, h0, w0, n0, batch;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, long long t, int bn) {
+// Work-list indices are 32-bit (the host checks total_units * grid < 2^31): 64-bit divisions cost hundreds of cycles
+// on the single-thread critical paths of the producer / MMA roles.
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int t, int bn) {
   TileCoord c;
-  const int m_tile = static_cast<int>(t % p.m_tiles);
-  const long long rest = t / p.m_tiles;
-  const int n_tile = static_cast<int>(rest % p.n_tiles);
-  c.batch = static_cast<int>(rest / p.n_tiles);
+  const int m_tile = t % p.m_tiles;
+  const int rest = t / p.m_tiles;
+  const int n_tile = rest % p.n_tiles;
+  c.batch = rest / p.n_tiles;
   const int tw_i = m_tile % p.tiles_w;
   const int th_i = (m_tile / p.tiles_w) % p.tiles_h;
   c.img = m_tile / (p.tiles_w * p.tiles_h);
@@ -90,13 +92,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, long l
   return c;
 }
 
-__device__ __forceinline__ long long cta_first_unit(long long total, int grid, int c) {
-  return (total * c) / grid;
+__device__ __forceinline__ int cta_first_unit(int total, int grid, int c) {
+  return static_cast<int>((static_cast<unsigned>(total) * static_cast<unsigned>(c)) / static_cast<unsigned>(grid));
 }
 
 // the CTA whose unit range [first(c), first(c+1)) contains unit u
-__device__ __forceinline__ int unit_owner(long long total, int grid, long long u) {
-  int c = static_cast<int>((u * grid) / total);
+__device__ __forceinline__ int unit_owner(int total, int grid, int u) {
+  int c = static_cast<int>((static_cast<unsigned>(u) * static_cast<unsigned>(grid)) / static_cast<unsigned>(total));
   if (c >= grid) c = grid - 1;
   while (c + 1 < grid && cta_first_unit(total, grid, c + 1) <= u) ++c;
   while (c > 0 && cta_first_unit(total, grid, c) > u) --c;
@@ -105,20 +107,20 @@ __device__ __forceinline__ int unit_owner(long long total, int grid, long long u
 
 // the (tile, k-block range) items of one CTA, identical for the three warp roles
 struct WorkIter {
-  long long u, u_end, tile, tiles;
+  int u, u_end, tile, tiles;
   int KB, grid;
   bool sk;
   __device__ __forceinline__ WorkIter(const ConvGemmParams& p, int cta, int grid_)
-      : tile(cta), tiles(p.total_tiles), KB(p.kb_per_tile), grid(grid_), sk(p.stream_k != 0) {
-    u = cta_first_unit(p.total_units, grid_, cta);
-    u_end = cta_first_unit(p.total_units, grid_, cta + 1);
+      : tile(cta), tiles(static_cast<int>(p.total_tiles)), KB(p.kb_per_tile), grid(grid_), sk(p.stream_k != 0) {
+    u = cta_first_unit(static_cast<int>(p.total_units), grid_, cta);
+    u_end = cta_first_unit(static_cast<int>(p.total_units), grid_, cta + 1);
   }
-  __device__ __forceinline__ bool next(long long& t, int& kb0, int& kb1) {
+  __device__ __forceinline__ bool next(int& t, int& kb0, int& kb1) {
     if (sk) {
       if (u >= u_end) return false;
       t = u / KB;
-      kb0 = static_cast<int>(u - t * KB);
-      kb1 = static_cast<int>(min(static_cast<long long>(KB), kb0 + (u_end - u)));
+      kb0 = u - t * KB;
+      kb1 = min(KB, kb0 + (u_end - u));
       u += kb1 - kb0;
       return true;
     }
@@ -184,7 +186,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int grid = gridDim.x;
   const int cta = blockIdx.x;
-  const long long U = p.total_units;
+  const int U = static_cast<int>(p.total_units);
   const int KB = p.kb_per_tile;
 
   if (warp == 0 && lane == 0) {
@@ -224,7 +226,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       WorkIter it(p, cta, grid);
-      long long t;
+      int t;
       int kb0, kb1;
       const int k_chunks = p.k_chunks, taps_s = p.taps_s;
       while (it.next(t, kb0, kb1)) {
@@ -267,7 +269,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       WorkIter it(p, cta, grid);
-      long long t;
+      int t;
       int kb0, kb1;
       int item = 0;
       while (it.next(t, kb0, kb1)) {
@@ -316,7 +318,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       WorkIter it(p, cta, grid);
-      long long t;
+      int t;
       int kb0, kb1;
       while (it.next(t, kb0, kb1)) {
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -355,7 +357,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float* sb_s = reinterpret_cast<float*>(smem + L::kSbOffset);
     uint32_t rphase = 0;
     WorkIter it(p, cta, grid);
-    long long t;
+    int t;
     int kb0, kb1;
     int item = 0;   // accumulator-segment counter (ping-pong bookkeeping shared with the MMA warp)
     const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;

@@ -356,16 +356,20 @@ class HeadCommon:
 
     # ------------------------------------------------------------------ relation module
     def _attention(self, att, xq, nq, refs, nref, ld, out, boxes_q=None, boxes_k=None, m_valid=None, n_valid=None,
-                   n_valid_off=0):
-        """out = xq + Attention(xq, refs)   (attention_module_multi_head, extractors :567-646)"""
+                   n_valid_off=0, tail=None):
+        """out = xq + Attention(xq, refs)   (attention_module_multi_head, extractors :567-646).
+        fp16 mode: the four GEMMs in front of the soft-max (Q, K, V' projections and Q.K^T) are one chain kernel, the
+        P.V' GEMM (+ whatever `tail()` appends, e.g. the stage's next Linear) another."""
         D = self.feat_dim
         q, k, vt = self.Qb[:nq], self.Kb[:nref], self.Vt[ld]
         s = self.S[ld][:16 * nq * ld].view(16, nq, ld)
-        ops.linear(xq, att.wq, q, bias=att.bq)
-        ops.linear(refs, att.wk, k, bias=att.bk)
-        ops.linear(att.wv, refs, vt)                                    # V'^T = Wv . refs^T  -> [1024, nref]
-        ops.conv_gemm(q.view(1, 1, nq, D), k.view(1, nref, D), s.view(16, 1, nq, ld), tile=(1, 128), cout=nref,
-                      k=64, batch=16, a_c_off=64, b_k_off=64, out_n_off=1, n_img=1)
+        key = (id(att), xq.data_ptr(), nq, refs.data_ptr(), nref, out.data_ptr(), tail is not None)
+        with ops.chain(self._chains, ("qk",) + key, self.dev, enabled=self.chained):
+            ops.linear(xq, att.wq, q, bias=att.bq)
+            ops.linear(refs, att.wk, k, bias=att.bk)
+            ops.linear(att.wv, refs, vt)                                    # V'^T = Wv . refs^T  -> [1024, nref]
+            ops.conv_gemm(q.view(1, 1, nq, D), k.view(1, nref, D), s.view(16, 1, nq, ld), tile=(1, 128), cout=nref,
+                          k=64, batch=16, a_c_off=64, b_k_off=64, out_n_off=1, n_img=1)
         pr = self.P[ld][:16 * nq * ld].view(16, nq, ld) if self.P is not None else None
         ops.relation_softmax(s, nq, ld, 1.0 / math.sqrt(64.0), boxes_q=boxes_q, boxes_k=boxes_k,
                              wg=att.wg if boxes_q is not None else None, bg=att.bg if boxes_q is not None else None,
@@ -374,9 +378,12 @@ class HeadCommon:
                              host_w=att.host_w if boxes_q is not None else None)
         if pr is not None:
             s = pr
-        ops.conv_gemm(s.view(16, 1, nq, ld), vt.view(1, D, ld), out.view(1, 1, nq, D), tile=(1, 128), cout=64, k=ld,
-                      batch=16, a_n_off=1, b_n_off=64, out_c_off=64, res_c_off=64, bias_z_off=64, bias=att.bv,
-                      residual=xq.view(1, 1, nq, D), block_n=64)
+        with ops.chain(self._chains, ("pv",) + key, self.dev, enabled=self.chained):
+            ops.conv_gemm(s.view(16, 1, nq, ld), vt.view(1, D, ld), out.view(1, 1, nq, D), tile=(1, 128), cout=64, k=ld,
+                          batch=16, a_n_off=1, b_n_off=64, out_c_off=64, res_c_off=64, bias_z_off=64, bias=att.bv,
+                          residual=xq.view(1, 1, nq, D), block_n=64)
+            if tail is not None:
+                tail()
         return out
 
     def _alloc_attention(self, geoms, kmax):
@@ -791,17 +798,17 @@ class MegaEngine(WindowedEngine):
         # stage 0
         refs0 = self.E0[KP:]
         self._attention(self.att_l[0], self.Qin0, nq, refs0, nl0 + self.mem_cap0, self.ld_0, self.X1,
-                        boxes_q=self.Bq0, boxes_k=self.B0[KP:], m_valid=mv[0:1], n_valid=kcnt, n_valid_off=KP)
+                        boxes_q=self.Bq0, boxes_k=self.B0[KP:], m_valid=mv[0:1], n_valid=kcnt, n_valid_off=KP,
+                        tail=lambda: ops.linear(self.X1, self.fc_w[1], self.Y1E[:nq], bias=self.fc_b[1], relu=True))
         # update_memory(0): the oldest local frame's 75 enhanced rows (extractors :678-688)
         ops.copy_rows(self.E0[KP:KP + R], self.E0, R, dst_idx=t("dst_mem0"))
         ops.copy_rows(self.B0[KP:KP + R], self.B0, R, dst_idx=t("dst_mem0"))
-        ops.linear(self.X1, self.fc_w[1], self.Y1E[:nq], bias=self.fc_b[1], relu=True)
         # stage 1
         self._attention(self.att_l[1], self.Y1E[:nq], nq, self.Y1E[KP:], nl12 + self.mem_cap12, self.ld_12, self.X2,
-                        boxes_q=self.Bq0, boxes_k=self.B1, m_valid=mv[1:2], n_valid=kcnt, n_valid_off=KP)
+                        boxes_q=self.Bq0, boxes_k=self.B1, m_valid=mv[1:2], n_valid=kcnt, n_valid_off=KP,
+                        tail=lambda: ops.linear(self.X2, self.fc_w[2], self.Y2M[:nq], bias=self.fc_b[2], relu=True))
         ops.copy_rows(self.Y1E[KP:KP + A], self.Y1E, A, dst_idx=t("dst_mem12"))
         ops.copy_rows(self.B1[:A], self.B1, A, dst_idx=t("dst_memb12"))
-        ops.linear(self.X2, self.fc_w[2], self.Y2M[:nq], bias=self.fc_b[2], relu=True)
         # stage 2 (key rows only)
         self._attention(self.att_l[2], self.Y2M[:KP], KP, self.Y2M[KP:], nl12 + self.mem_cap12, self.ld_12, self.X3,
                         boxes_q=self.Bq0[:KP], boxes_k=self.B2, m_valid=mv[2:3])

@@ -260,6 +260,37 @@ def _autotune(d):
     return best
 
 
+def _autotune_chain(d):
+    """same, for a layer that is being recorded into a chain: every candidate is timed as a ONE-layer chain (the
+    persistent chain kernel is the code that will run it; launch overhead is the same constant for all candidates)"""
+    best = None
+    dev = torch.device("cuda", torch.cuda.current_device())
+    for bn, sk in _candidates(d.cout, d.precision, d.out_f16):
+        c = _copy_desc(d)
+        c.block_n, c.stream_k = bn, sk
+        try:
+            ch = ConvChain([c], dev, max_ctas=d.max_ctas)
+            hook, TIMING_HOOK[0] = TIMING_HOOK[0], None
+            try:
+                for _ in range(2):
+                    ch.launch()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(8):
+                    ch.launch()
+                e1.record()
+                e1.synchronize()
+            finally:
+                TIMING_HOOK[0] = hook
+            LAUNCHES[0] -= 10
+            t = e0.elapsed_time(e1) / 8
+        except _lib.MegaError:
+            continue
+        if best is None or t < best[0]:
+            best = (t, bn, sk)
+    return best
+
+
 def pick_config(cout, m_tiles, batch, kb_per_tile, out_f16=False):
     """(block_n, stream_k) when no autotuned entry exists. Deep reductions balance best at k-block
     granularity (stream-K, widest tile); shallow ones run whole tiles, with the tile width chosen to
@@ -359,7 +390,7 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
         aliased = residual is not None and residual.data_ptr() == out.data_ptr()   # in-place: not idempotent
         if (cfg is None and AUTOTUNE[0] and not aliased and _CHAIN_MODE[0] != "skip"
                 and not torch.cuda.is_current_stream_capturing()):
-            best = _autotune(d)
+            best = _autotune_chain(d) if _CHAIN_MODE[0] == "record" else _autotune(d)
             if best is not None:
                 cfg = TUNED[key] = (best[1], best[2], best[0])
         if cfg is not None:
