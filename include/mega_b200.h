@@ -60,7 +60,7 @@ typedef struct mega_conv_gemm_desc {
   const float* bias;     /* [cout] or NULL */
   const void* residual;  /* same indexing and element type as out, with res_ld, or NULL */
   long long res_ld;
-  int relu;
+  int relu; /* 0: none, 1: ReLU, 2: LeakyReLU(0.1) (backbone/flownet.py:47) */
   /* tiling: tile_h*tile_w == 128 output pixels per CTA, block_n in {32,64,96,128,160,192,256} */
   int tile_h, tile_w, block_n;
   /* batched mode (grid.z = batch): per-batch coordinate offsets */
@@ -84,6 +84,14 @@ typedef struct mega_conv_gemm_desc {
   int out_f16; /* 1: out / residual are __half (precision 2, block_n % 64 == 0); 0: fp32 */
   int pdl;     /* 1: programmatic dependent launch -- the kernel's prologue overlaps the tail of the previous kernel
                   on the stream (it orders its own memory accesses behind that kernel with griddepcontrol.wait) */
+  /* ABI v3 (zero = previous behaviour): */
+  int stride_h, stride_w; /* convolution stride (0 -> 1): output pixel (h, w) reads a[h*stride_h + r*dil - pad, ...]; the
+                             strided rectangle is fetched with TMA element strides (tile_w, tile_h <= 128) */
+  int pad_w_set, pad_w;   /* pad_w_set != 0: left padding pad_w differs from `pad` (which then applies to h only) */
+  long long out_stride_h, out_stride_n; /* element strides of the output rows / images (0: dense, out_ld * out_w and
+                                           out_ld * out_w * out_h) -- lets a conv write every other pixel of a larger
+                                           map (the four parity classes of a stride-2 transposed convolution) */
+  long long res_stride_h, res_stride_n; /* same for the residual */
 } mega_conv_gemm_desc;
 
 int mega_conv_gemm(const mega_conv_gemm_desc* desc, void* stream);
@@ -215,6 +223,26 @@ int mega_box_postprocess(const float* logits, int ld_logits, const float* deltas
                          float im_h, float score_thresh, float nms_thresh, int max_det, float wx, float wy, float ww,
                          float wh, void* workspace, long long workspace_bytes, float* out_boxes, float* out_scores,
                          long long* out_labels, int out_cap, int* out_count, void* stream);
+
+/* ------------------------------------------------------------------ FGFA (configs/FGFA)
+ * f16 != 0: element type __half, else float (the engine's activation type); arithmetic in fp32.
+ * pool_image: image [3,H,W] fp32 -> [ceil(H/2), ceil(W/2), 4] = avg_pool2d(image / 255, 2, ceil_mode) with a zero 4th
+ *   channel (FlowNetS.avgpool applied per frame, backbone/flownet.py:52-55; generalized_rcnn_fgfa.py:198).
+ * build_pairs: ring [slots][hq*wq*4] of pooled frames -> pairs [n_frames][hq+6][wq+8][8] (key frame channels 0..2,
+ *   frame i channels 4..6, zero borders): the A operand of FlowNetS.flow_conv1 as a row-wise implicit GEMM.
+ * avgpool2_nhwc: F.avg_pool2d(2, stride 2, ceil_mode=True) on an NHWC map (flownet.py:113).
+ * aggregate: resample (bilinear, border; generalized_rcnn_fgfa.py:45-62) of the cached [feats | embedding] maps of
+ *   the window frames along `flow` [n_frames][h*w][flow_ld] fp32, cosine-similarity weights against the key frame's
+ *   warped embedding, soft-max over frames, weighted sum of the warped feats (:64-76, :206-214) -> out [h*w][out_ld];
+ *   weights_out (optional) [n_frames][h*w] fp32. */
+int mega_fgfa_pool_image(const float* image, int height, int width, void* out, int f16, void* stream);
+int mega_fgfa_build_pairs(const void* ring, long long slot_stride, const int* slots, int n_frames, int key_pos, int hq,
+                          int wq, void* pairs, int f16, void* stream);
+int mega_avgpool2_nhwc(const void* input, int n_img, int height, int width, int channels, long long in_ld, void* out,
+                       long long out_ld, int f16, void* stream);
+int mega_fgfa_aggregate(const void* ring, long long slot_stride, int ld, int feat_channels, int embed_channels,
+                        const int* slots, int n_frames, int key_pos, const float* flow, int flow_ld, int height, int width,
+                        void* out, long long out_ld, float* weights_out, int f16, void* stream);
 
 /* -------------------------------------------- RetinaNet focal loss (csrc/SigmoidFocalLoss.h:10-32)
  * logits [N,C] fp32, targets [N] int32 in {-1 (ignore), 0 (background), 1..C}. */

@@ -260,8 +260,9 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
               v[4] += r2v.x; v[5] += r2v.y; v[6] += r3v.x; v[7] += r3v.y;
             }
             if (p.relu) {
+              const float slope = p.relu == 2 ? 0.1f : 0.f;
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], slope * v[e]);
             }
             uint4 o;
             o.x = f2_to_h2(v[0], v[1]); o.y = f2_to_h2(v[2], v[3]);
@@ -278,7 +279,9 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
               v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
             }
             if (p.relu) {
-              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              const float slope = p.relu == 2 ? 0.1f : 0.f;
+              v.x = fmaxf(v.x, slope * v.x); v.y = fmaxf(v.y, slope * v.y);
+              v.z = fmaxf(v.z, slope * v.z); v.w = fmaxf(v.w, slope * v.w);
             }
             *reinterpret_cast<float4*>(dst + chunk) = v;
           }
@@ -351,7 +354,8 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         const ConvGemmParams p = L->p;
         const int BN = L->block_n;
         const int act = L->active_ctas;
-        const int k_chunks = p.k_chunks, taps_s = p.taps_s, dil = p.dil, pad = p.pad;
+        const int k_chunks = p.k_chunks, taps_s = p.taps_s, dil = p.dil, pad = p.pad, pad_w = p.pad_w;
+        const int stride_h = p.stride_h, stride_w = p.stride_w;
         const int a_c_off = p.a_c_off, a_n_off = p.a_n_off, b_k_off = p.b_k_off, b_n_off = p.b_n_off;
         const CUtensorMap* tmA = &L->tmA;
         const CUtensorMap* tmB = &L->tmB;
@@ -377,7 +381,8 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
             uint8_t* a_dst = smem + ps.stage * kChainStageBytes;
             if (lane == 0) {
               mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
-              tma_load_4d(a_dst, tmA, &full_bar[ps.stage], kc * 64 + a_c0, tc.w0 + sx * dil - pad, tc.h0 + r * dil - pad, a_n);
+              tma_load_4d(a_dst, tmA, &full_bar[ps.stage], kc * 64 + a_c0, tc.w0 * stride_w + sx * dil - pad_w,
+                          tc.h0 * stride_h + r * dil - pad, a_n);
             } else {
               tma_load_3d(a_dst + kChainABytes, tmB, &full_bar[ps.stage], kc * 64 + b_k0, b_n, tap);
             }

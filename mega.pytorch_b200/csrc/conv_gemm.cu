@@ -78,6 +78,10 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   MEGA_ARG_CHECK(d->tile_h > 0 && d->tile_w > 0 && d->tile_h * d->tile_w == kBM,
                  "conv_gemm: tile_h*tile_w must be 128 (got %dx%d)", d->tile_h, d->tile_w);
   MEGA_ARG_CHECK(d->tile_w <= 256 && d->tile_h <= 256, "conv_gemm: tile too large for a TMA box");
+  const int stride_h = d->stride_h > 0 ? d->stride_h : 1, stride_w = d->stride_w > 0 ? d->stride_w : 1;
+  MEGA_ARG_CHECK((d->tile_w - 1) * stride_w + 1 <= 256 && (d->tile_h - 1) * stride_h + 1 <= 256,
+                 "conv_gemm: strided tile %dx%d (stride %dx%d) exceeds the 256-element TMA box", d->tile_h, d->tile_w,
+                 stride_h, stride_w);
   MEGA_ARG_CHECK(d->block_n == 32 || d->block_n == 64 || d->block_n == 96 || d->block_n == 128 ||
                      d->block_n == 160 || d->block_n == 192 || d->block_n == 256,
                  "conv_gemm: block_n must be one of 32/64/96/128/160/192/256");
@@ -119,9 +123,11 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
                           static_cast<cuuint64_t>(d->a_h), static_cast<cuuint64_t>(d->a_n)};
     cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->a_stride_w) * esz, static_cast<cuuint64_t>(d->a_stride_h) * esz,
                           static_cast<cuuint64_t>(d->a_stride_n) * esz};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(d->tile_w),
-                         static_cast<cuuint32_t>(d->tile_h), 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // a strided convolution samples every stride-th pixel of the rectangle: TMA element strides (the box is the
+    // bounding rectangle, the copy delivers tile_w x tile_h pixels)
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>((d->tile_w - 1) * stride_w + 1),
+                         static_cast<cuuint32_t>((d->tile_h - 1) * stride_h + 1), 1};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride_w), static_cast<cuuint32_t>(stride_h), 1};
     CUresult r = enc(&tmA, dt, 4, const_cast<void*>(d->a), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -171,8 +177,13 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
       cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->cout + (d->batch - 1) * c_off), static_cast<cuuint64_t>(d->out_w),
                             static_cast<cuuint64_t>(d->out_h),
                             static_cast<cuuint64_t>(d->n_img + (d->batch - 1) * n_off)};
-      cuuint64_t gstr[3] = {static_cast<cuuint64_t>(ld) * osz, static_cast<cuuint64_t>(ld) * d->out_w * osz,
-                            static_cast<cuuint64_t>(ld) * d->out_w * d->out_h * osz};
+      const long long sh = which == 0 ? d->out_stride_h : d->res_stride_h;
+      const long long sn = which == 0 ? d->out_stride_n : d->res_stride_n;
+      const long long str_h = sh > 0 ? sh : ld * d->out_w;
+      const long long str_n = sn > 0 ? sn : str_h * d->out_h;
+      MEGA_ARG_CHECK((str_h % oalign) == 0 && (str_n % oalign) == 0, "conv_gemm: output strides must be multiples of 16 bytes");
+      cuuint64_t gstr[3] = {static_cast<cuuint64_t>(ld) * osz, static_cast<cuuint64_t>(str_h) * osz,
+                            static_cast<cuuint64_t>(str_n) * osz};
       cuuint32_t box[4] = {static_cast<cuuint32_t>(cw), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
       CUresult r = enc(tm, odt, 4, const_cast<void*>(base), gdim, gstr, box, estr,
@@ -199,6 +210,9 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   p.taps_s = d->taps_s;
   p.dil = d->dil;
   p.pad = d->pad;
+  p.pad_w = d->pad_w_set ? d->pad_w : d->pad;
+  p.stride_h = stride_h;
+  p.stride_w = stride_w;
   p.k_chunks = mega_ceil_div(d->k_per_tap, bk);
   p.cout = d->cout;
   p.scale = d->scale;

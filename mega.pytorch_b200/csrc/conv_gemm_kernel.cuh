@@ -36,6 +36,8 @@ struct ConvGemmParams {
   int tiles_w, tiles_h, tile_w, tile_h;
   int out_h, out_w, n_img;
   int taps_r, taps_s, dil, pad;
+  int pad_w;                  // left padding (pad applies to the rows)
+  int stride_h, stride_w;     // convolution stride: output (h, w) reads input (h*stride_h + r*dil - pad, ...)
   int k_chunks;  // ceil(Cin / BK)
   int cout;
   const float* scale;
@@ -242,8 +244,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* a_dst = smem + stage * L::kStageBytes;
           if (lane == 0) {
             mbar_arrive_expect_tx(&full_bar[stage], L::kHalf);   // bytes delivered by the two TMA loads
-            tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + a_c0, tc.w0 + sx * p.dil - p.pad,
-                        tc.h0 + r * p.dil - p.pad, a_n);
+            tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + a_c0, tc.w0 * p.stride_w + sx * p.dil - p.pad_w,
+                        tc.h0 * p.stride_h + r * p.dil - p.pad, a_n);
           } else {
             tma_load_3d(a_dst + L::kABytes, &tmB, &full_bar[stage], kc * kBK + b_k0, b_n, tap);
           }
@@ -549,8 +551,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
               }
               if (p.relu) {
+                const float slope = p.relu == 2 ? 0.1f : 0.f;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], slope * v[e]);
               }
               uint4 o;
               o.x = f2_to_h2(v[0], v[1]); o.y = f2_to_h2(v[2], v[3]);
@@ -567,7 +570,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
               }
               if (p.relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                const float slope = p.relu == 2 ? 0.1f : 0.f;
+                v.x = fmaxf(v.x, slope * v.x); v.y = fmaxf(v.y, slope * v.y);
+                v.z = fmaxf(v.z, slope * v.z); v.w = fmaxf(v.w, slope * v.w);
               }
               *reinterpret_cast<float4*>(dst + chunk) = v;
             }

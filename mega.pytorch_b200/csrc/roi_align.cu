@@ -269,6 +269,124 @@ roi_align_nhwc_cached_kernel(const T* __restrict__ in, int channels, int height,
   }
 }
 
+// ---- fp16 fast path (the fp16-operand engine): same sampling geometry, but (i) the bilinear set-up is separable, so the
+// CTA computes it ONCE per roi -- 7 x grid_h row entries and 7 x grid_w column entries in shared memory -- instead of once
+// per (bin, sample, channel group); (ii) the blend uses fused multiply-adds in fp32 (results are rounded to fp16 at the
+// store anyway, so the bit-exact association order of the fp32 kernels buys nothing here).
+struct AxisSample {
+  int lo, hi;       // clamped cell indices
+  float wlo, whi;   // weights of the two cells; both 0 when the sample lies outside [-1, size]
+};
+constexpr int kRoiMaxGrid = 8;   // samples per bin and axis handled by the fast path (roi extent up to 8*7 cells)
+
+__device__ __forceinline__ AxisSample axis_sample(float c, int size) {
+  AxisSample a;
+  if (c < -1.0f || c > static_cast<float>(size)) {
+    a.lo = a.hi = 0;
+    a.wlo = a.whi = 0.f;
+    return a;
+  }
+  if (c <= 0) c = 0;
+  int lo = static_cast<int>(c), hi;
+  if (lo >= size - 1) {
+    hi = lo = size - 1;
+    c = static_cast<float>(lo);
+  } else {
+    hi = lo + 1;
+  }
+  const float l = c - static_cast<float>(lo);
+  a.lo = lo; a.hi = hi; a.wlo = 1.f - l; a.whi = l;
+  return a;
+}
+
+__global__ void __launch_bounds__(256)
+roi_align_nhwc_f16_fast_kernel(const __half* __restrict__ in, int channels, int height, int width, long long in_img_stride,
+                               const float* __restrict__ rois, int roi_ld, int roi_box_off,
+                               const int* __restrict__ roi_batch, float scale, int ph, int pw, int sampling_ratio,
+                               __half* __restrict__ out, long long out_roi_stride) {
+  constexpr int kSlice = kRoiSliceBytes / 2;     // 128 channels per CTA
+  extern __shared__ uint4 cell_s[];              // [cells][16] 16-byte vectors
+  __shared__ AxisSample ys[7 * kRoiMaxGrid], xs[7 * kRoiMaxGrid];
+  const int slice = blockIdx.x;
+  const int n = blockIdx.y;
+  float roi5[5];
+  roi5[0] = roi_batch ? static_cast<float>(roi_batch[n]) : 0.f;
+  const float* rb = rois + static_cast<long long>(n) * roi_ld + roi_box_off;
+  if (roi_box_off < 0) {
+    rb = rois + static_cast<long long>(n) * roi_ld;
+    roi5[0] = rb[0];
+    rb += 1;
+  }
+  roi5[1] = rb[0]; roi5[2] = rb[1]; roi5[3] = rb[2]; roi5[4] = rb[3];
+  const RoiGeom g = roi_geom(roi5, scale, ph, pw, sampling_ratio);
+  const __half* img = in + static_cast<long long>(g.batch) * in_img_stride + slice * kSlice;
+  const float end_h = __fadd_rn(g.start_h, __fmul_rn(g.bin_h, static_cast<float>(ph)));
+  const float end_w = __fadd_rn(g.start_w, __fmul_rn(g.bin_w, static_cast<float>(pw)));
+  int r0 = static_cast<int>(floorf(fmaxf(g.start_h, 0.f))), r1 = static_cast<int>(floorf(fmaxf(end_h, 0.f))) + 1;
+  int c0 = static_cast<int>(floorf(fmaxf(g.start_w, 0.f))), c1 = static_cast<int>(floorf(fmaxf(end_w, 0.f))) + 1;
+  r0 = min(max(r0, 0), height - 1); r1 = min(max(r1, 0), height - 1);
+  c0 = min(max(c0, 0), width - 1); c1 = min(max(c1, 0), width - 1);
+  const int rh = r1 - r0 + 1, rw = c1 - c0 + 1;
+  const bool cached = (rh * rw <= kRoiMaxCells);
+  if (cached) {
+    for (int i = threadIdx.x; i < rh * rw * 16; i += blockDim.x) {
+      const int cell = i >> 4, q = i & 15;
+      const int rr = cell / rw, cc = cell - rr * rw;
+      cell_s[i] = ldg_u4(img + (static_cast<long long>(r0 + rr) * width + (c0 + cc)) * channels + q * 8);
+    }
+  }
+  // rois with more than kRoiMaxGrid samples per bin and axis (boxes far larger than the map) compute the entries inline
+  const bool tabled = g.grid_h <= kRoiMaxGrid && g.grid_w <= kRoiMaxGrid;
+  if (tabled) {
+    for (int i = threadIdx.x; i < ph * g.grid_h; i += blockDim.x)
+      ys[i] = axis_sample(sample_coord(g.start_h, i / g.grid_h, g.bin_h, i % g.grid_h, g.grid_h), height);
+    for (int i = threadIdx.x; i < pw * g.grid_w; i += blockDim.x)
+      xs[i] = axis_sample(sample_coord(g.start_w, i / g.grid_w, g.bin_w, i % g.grid_w, g.grid_w), width);
+  }
+  __syncthreads();
+  const int q = threadIdx.x & 15;
+  const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
+  __half* obase = out + static_cast<long long>(n) * out_roi_stride + slice * kSlice + q * 8;
+  for (int bin = threadIdx.x >> 4; bin < ph * pw; bin += blockDim.x >> 4) {
+    const int phi = bin / pw, pwi = bin - phi * pw;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const AxisSample ay = tabled ? ys[phi * g.grid_h + iy]
+                                   : axis_sample(sample_coord(g.start_h, phi, g.bin_h, iy, g.grid_h), height);
+      for (int ix = 0; ix < g.grid_w; ++ix) {
+        const AxisSample ax = tabled ? xs[pwi * g.grid_w + ix]
+                                     : axis_sample(sample_coord(g.start_w, pwi, g.bin_w, ix, g.grid_w), width);
+        const float w1 = ay.wlo * ax.wlo, w2 = ay.wlo * ax.whi, w3 = ay.whi * ax.wlo, w4 = ay.whi * ax.whi;
+        uint4 v1, v2, v3, v4;
+        if (cached) {     // the footprint covers every clamped sample cell by construction
+          v1 = cell_s[((ay.lo - r0) * rw + (ax.lo - c0)) * 16 + q];
+          v2 = cell_s[((ay.lo - r0) * rw + (ax.hi - c0)) * 16 + q];
+          v3 = cell_s[((ay.hi - r0) * rw + (ax.lo - c0)) * 16 + q];
+          v4 = cell_s[((ay.hi - r0) * rw + (ax.hi - c0)) * 16 + q];
+        } else {
+          v1 = ldg_u4(img + (static_cast<long long>(ay.lo) * width + ax.lo) * channels + q * 8);
+          v2 = ldg_u4(img + (static_cast<long long>(ay.lo) * width + ax.hi) * channels + q * 8);
+          v3 = ldg_u4(img + (static_cast<long long>(ay.hi) * width + ax.lo) * channels + q * 8);
+          v4 = ldg_u4(img + (static_cast<long long>(ay.hi) * width + ax.hi) * channels + q * 8);
+        }
+        const uint32_t* p1 = &v1.x; const uint32_t* p2 = &v2.x; const uint32_t* p3 = &v3.x; const uint32_t* p4 = &v4.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = h2_to_f2(p1[e]), b = h2_to_f2(p2[e]), c = h2_to_f2(p3[e]), d = h2_to_f2(p4[e]);
+          acc[2 * e] = fmaf(w4, d.x, fmaf(w3, c.x, fmaf(w2, b.x, fmaf(w1, a.x, acc[2 * e]))));
+          acc[2 * e + 1] = fmaf(w4, d.y, fmaf(w3, c.y, fmaf(w2, b.y, fmaf(w1, a.y, acc[2 * e + 1]))));
+        }
+      }
+    }
+    uint4 o;
+    o.x = f2_to_h2(acc[0] * inv_count, acc[1] * inv_count); o.y = f2_to_h2(acc[2] * inv_count, acc[3] * inv_count);
+    o.z = f2_to_h2(acc[4] * inv_count, acc[5] * inv_count); o.w = f2_to_h2(acc[6] * inv_count, acc[7] * inv_count);
+    *reinterpret_cast<uint4*>(obase + static_cast<long long>(bin) * channels) = o;
+  }
+}
+
 template <typename T>
 static int roi_align_nhwc_launch(const T* input, int channels, int height, int width, long long in_img_stride,
                                  const float* rois, int roi_ld, int roi_box_off, const int* roi_batch, int num_rois,
@@ -339,8 +457,27 @@ extern "C" int mega_roi_align_forward_nhwc_f16(const void* input, int channels, 
                                                const int* roi_batch, int num_rois, float spatial_scale, int pooled_h,
                                                int pooled_w, int sampling_ratio, void* output,
                                                long long out_roi_stride, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  // fast path: 128-channel slices, up to 7x7 bins
+  const bool fast = (channels % 128) == 0 && pooled_h <= 7 && pooled_w <= 7 &&
+                    (reinterpret_cast<uintptr_t>(input) & 15) == 0 && (reinterpret_cast<uintptr_t>(output) & 15) == 0 &&
+                    (out_roi_stride % 8) == 0 && (in_img_stride % 8) == 0;
+  if (fast) {
+    if (num_rois == 0) return MEGA_OK;
+    static bool configured = false;
+    if (!configured) {
+      MEGA_CUDA_CHECK(cudaFuncSetAttribute(roi_align_nhwc_f16_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kRoiMaxCells * 256));
+      configured = true;
+    }
+    dim3 grid(channels / 128, num_rois);
+    roi_align_nhwc_f16_fast_kernel<<<grid, 256, kRoiMaxCells * 256, stream>>>(
+        static_cast<const __half*>(input), channels, height, width, in_img_stride, rois, roi_ld, roi_box_off, roi_batch,
+        spatial_scale, pooled_h, pooled_w, sampling_ratio, static_cast<__half*>(output), out_roi_stride);
+    MEGA_CUDA_CHECK(cudaGetLastError());
+    return MEGA_OK;
+  }
   return roi_align_nhwc_launch<__half>(static_cast<const __half*>(input), channels, height, width, in_img_stride, rois,
                                        roi_ld, roi_box_off, roi_batch, num_rois, spatial_scale, pooled_h, pooled_w,
-                                       sampling_ratio, static_cast<__half*>(output), out_roi_stride,
-                                       static_cast<cudaStream_t>(stream_v));
+                                       sampling_ratio, static_cast<__half*>(output), out_roi_stride, stream);
 }

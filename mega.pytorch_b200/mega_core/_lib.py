@@ -53,6 +53,8 @@ class ConvGemmDesc(ctypes.Structure):
         ("workspace_bytes", c_ll),
         ("out_f16", c_int),
         ("pdl", c_int),
+        ("stride_h", c_int), ("stride_w", c_int), ("pad_w_set", c_int), ("pad_w", c_int),
+        ("out_stride_h", c_ll), ("out_stride_n", c_ll), ("res_stride_h", c_ll), ("res_stride_n", c_ll),
     ]
 
 
@@ -129,6 +131,14 @@ lib.mega_relation_softmax_f16.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, 
 lib.mega_relation_softmax_f16.restype = _i
 lib.mega_relation_softmax_pe.argtypes = [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp]
 lib.mega_relation_softmax_pe.restype = _i
+lib.mega_fgfa_pool_image.argtypes = [_vp, _i, _i, _vp, _i, _vp]
+lib.mega_fgfa_pool_image.restype = _i
+lib.mega_fgfa_build_pairs.argtypes = [_vp, _ll, _vp, _i, _i, _i, _i, _vp, _i, _vp]
+lib.mega_fgfa_build_pairs.restype = _i
+lib.mega_avgpool2_nhwc.argtypes = [_vp, _i, _i, _i, _i, _ll, _vp, _ll, _i, _vp]
+lib.mega_avgpool2_nhwc.restype = _i
+lib.mega_fgfa_aggregate.argtypes = [_vp, _ll, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _ll, _vp, _i, _vp]
+lib.mega_fgfa_aggregate.restype = _i
 lib.mega_stem_im2col.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
 lib.mega_stem_im2col.restype = _i
 lib.mega_maxpool3x3s2_nhwc.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
@@ -166,4 +176,5 @@ EXPORTS = [
     "mega_box_postprocess", "mega_sigmoid_focalloss_forward", "mega_sigmoid_focalloss_backward",
     "mega_deform_im2col", "mega_deform_psroi_pooling_forward",
     "mega_roi_align_forward_nhwc_f16", "mega_stem_im2col_f16", "mega_maxpool3x3s2_nhwc_f16", "mega_relation_softmax_f16", "mega_relation_softmax_pe",
+    "mega_fgfa_pool_image", "mega_fgfa_build_pairs", "mega_avgpool2_nhwc", "mega_fgfa_aggregate",
 ]

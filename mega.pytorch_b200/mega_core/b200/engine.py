@@ -1027,3 +1027,262 @@ class BaseEngine(HeadCommon):
         ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
         self.last_feats, self.last_props, self.last_cnt, self.last_pooled = feats, boxes[0], cnt, pooled
         return self.predict_and_postprocess(f7, boxes[0], cnt[0:1], im_w, im_h)
+
+
+# =============================================================================================== FGFA
+class FlowNetS:
+    """FlowNetS.forward, method "fgfa" (modeling/backbone/flownet.py:54-118) over NHWC activations.
+
+    Every layer is a launch of the tcgen05 implicit-GEMM kernel:
+      * flow_conv1 (7x7 / stride 2 over 6 channels): the image pairs are stored with 8 channels per pixel, so the 7 taps of
+        one filter row are 56 (+8 zero-weighted) CONTIGUOUS elements -- one K slab per filter row through an overlapping
+        strided view (pixel pitch 16 elements = 2 input pixels), 7 k-blocks instead of a 49-tap / 6-channel gather;
+      * strided convolutions use TMA element strides; LeakyReLU(0.1) is an epilogue mode;
+      * the 4x4 / stride-2 transposed convolutions are four 2x2 convolutions, one per output parity class, each writing
+        every other pixel of the (cropped, flownet.py:7-11) target -- directly into its channel slice of the concat buffer,
+        so torch.cat / crop_like never materialise anything;
+      * the 2-channel flow predictions are written with channel-clipped TMA stores into 8-channel-padded buffers."""
+
+    def __init__(self, sd, dev, dtype, prefix="flownet."):
+        self.dev, self.dtype = dev, dtype
+        g = lambda k: sd[prefix + k].detach().float()
+        w1 = g("flow_conv1.weight")                                   # [64, 6, 7, 7]
+        wr = torch.zeros(7, 64, 64)
+        for s_ in range(7):
+            wr[:, :, s_ * 8 + 0:s_ * 8 + 3] = w1[:, 0:3, :, s_].permute(2, 0, 1)      # key-frame channels
+            wr[:, :, s_ * 8 + 4:s_ * 8 + 7] = w1[:, 3:6, :, s_].permute(2, 0, 1)      # window-frame channels
+        self.w1 = wr.contiguous().to(dev).to(dtype)
+        self.b = {}
+        self.w = {}
+        for name in ("conv2", "conv3", "conv3_1", "conv4", "conv4_1", "conv5", "conv5_1", "conv6", "conv6_1"):
+            self.w[name] = pack_conv(g(name + ".weight"), dev, dtype)
+        for name in ("flow_conv1", "conv2", "conv3", "conv3_1", "conv4", "conv4_1", "conv5", "conv5_1", "conv6", "conv6_1"):
+            self.b[name] = g(name + ".bias").contiguous().to(dev)
+        for i in range(1, 6):
+            w = g("Convolution%d.weight" % i)                         # [2, cin, 3, 3]
+            cin = w.shape[1]
+            wp = torch.zeros(9, 2, _round_up(cin, 8))
+            wp[:, :, :cin] = w.permute(2, 3, 0, 1).reshape(9, 2, cin)
+            self.w["Convolution%d" % i] = wp.contiguous().to(dev).to(dtype)
+            self.b["Convolution%d" % i] = g("Convolution%d.bias" % i).contiguous().to(dev)
+        self.b["Convolution5_x2.5"] = (g("Convolution5.bias") * 2.5).contiguous().to(dev)
+        self.scale25 = torch.full((4,), 2.5, device=dev)
+        for name in ("deconv5", "deconv4", "deconv3", "deconv2", "upsample_flow6to5", "upsample_flow5to4",
+                     "upsample_flow4to3", "upsample_flow3to2"):
+            w = g(name + ".weight")                                   # ConvTranspose2d: [cin, cout, 4, 4]
+            cin, cout = w.shape[:2]
+            cls = {}
+            for py in (0, 1):
+                for px in (0, 1):
+                    wp = torch.zeros(4, cout, _round_up(cin, 8))
+                    for r in (0, 1):
+                        for s_ in (0, 1):
+                            wp[r * 2 + s_, :, :cin] = w[:, :, py + 2 * (1 - r), px + 2 * (1 - s_)].t()
+                    cls[(py, px)] = wp.contiguous().to(dev).to(dtype)
+            self.w[name] = cls
+            self.b[name] = g(name + ".bias").contiguous().to(dev)
+        self._bufs = {}
+        self._chains = {}
+
+    def _buf(self, tag, shape, dtype=None):
+        key = (tag, tuple(shape), dtype or self.dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.zeros(*shape, device=self.dev, dtype=dtype or self.dtype)
+            self._bufs[key] = t
+        return t
+
+    def _deconv(self, name, x, target, c0, cout, act):
+        """target[..., c0:c0+cout] = crop_like(ConvTranspose2d(4, stride 2)(x), target) (+ LeakyReLU)"""
+        n, hi, wi, _ = x.shape
+        ht, wt = target.shape[1:3]
+        offy = 0 if 2 * hi + 2 == ht else 1
+        offx = 0 if 2 * wi + 2 == wt else 1
+        for py in (0, 1):
+            ry = (py - offy) & 1
+            du = (ry + offy - py) // 2
+            for px in (0, 1):
+                rx = (px - offx) & 1
+                dv = (rx + offx - px) // 2
+                view = target[:, ry::2, rx::2, c0:c0 + cout]
+                if view.shape[1] == 0 or view.shape[2] == 0:
+                    continue
+                ops.conv_gemm(x, self.w[name][(py, px)], view, taps=(2, 2), pad=1 - du, pad_w=1 - dv, bias=self.b[name],
+                              relu=act, cout=cout)
+
+    def forward(self, pairs):
+        """pairs [L, hq+6, wq+8, 8] (ops.fgfa_build_pairs) -> flow [L, hf, wf, 4] fp32 (channels 0,1 = x,y; x2.5 applied)"""
+        n, hp, wp, _ = pairs.shape
+        hq, wq = hp - 6, wp - 8
+        dim = lambda v: (v - 1) // 2 + 1                         # k odd, stride 2, "same" padding
+        h1, w1 = dim(hq), dim(wq)
+        h2, w2 = dim(h1), dim(w1)
+        h3, w3 = dim(h2), dim(w2)
+        h4, w4 = dim(h3), dim(w3)
+        h5, w5 = dim(h4), dim(w4)
+        h6, w6 = dim(h5), dim(w5)
+        B = self._buf
+        c1 = B("c1", (n, h1, w1, 64))
+        cat5 = B("cat5", (n, h2, w2, 200))
+        c3 = B("c3", (n, h3, w3, 256))
+        cat4 = B("cat4", (n, h3, w3, 392))
+        c4 = B("c4", (n, h4, w4, 512))
+        cat3 = B("cat3", (n, h4, w4, 776))
+        c5 = B("c5", (n, h5, w5, 512))
+        cat2 = B("cat2", (n, h5, w5, 1032))
+        c6 = B("c6", (n, h6, w6, 1024))
+        c61 = B("c61", (n, h6, w6, 1024))
+        fl6, fl5, fl4, fl3 = B("fl6", (n, h6, w6, 8)), B("fl5", (n, h5, w5, 8)), B("fl4", (n, h4, w4, 8)), B("fl3", (n, h3, w3, 8))
+        lk = "leaky"
+        with ops.chain(self._chains, ("flow_a", tuple(pairs.shape)), self.dev, enabled=self.dtype == torch.float16):
+            # flow_conv1 as 7 row slabs: A = overlapping windows of 64 elements, pitch 16 (two input pixels)
+            a = pairs.as_strided((n, hp, w1, 64), (hp * wp * 8, wp * 8, 16, 1))
+            ops.conv_gemm(a, self.w1, c1, taps=(7, 1), pad=0, stride=(2, 1), bias=self.b["flow_conv1"], relu=lk,
+                          out_hw=(h1, w1))
+            ops.conv_gemm(c1, self.w["conv2"], cat5[..., 0:128], taps=(5, 5), pad=2, stride=(2, 2), bias=self.b["conv2"], relu=lk)
+            ops.conv_gemm(cat5[..., 0:128], self.w["conv3"], c3, taps=(5, 5), pad=2, stride=(2, 2), bias=self.b["conv3"], relu=lk)
+            ops.conv_gemm(c3, self.w["conv3_1"], cat4[..., 0:256], taps=(3, 3), pad=1, bias=self.b["conv3_1"], relu=lk)
+            ops.conv_gemm(cat4[..., 0:256], self.w["conv4"], c4, taps=(3, 3), pad=1, stride=(2, 2), bias=self.b["conv4"], relu=lk)
+            ops.conv_gemm(c4, self.w["conv4_1"], cat3[..., 0:512], taps=(3, 3), pad=1, bias=self.b["conv4_1"], relu=lk)
+            ops.conv_gemm(cat3[..., 0:512], self.w["conv5"], c5, taps=(3, 3), pad=1, stride=(2, 2), bias=self.b["conv5"], relu=lk)
+            ops.conv_gemm(c5, self.w["conv5_1"], cat2[..., 0:512], taps=(3, 3), pad=1, bias=self.b["conv5_1"], relu=lk)
+            ops.conv_gemm(cat2[..., 0:512], self.w["conv6"], c6, taps=(3, 3), pad=1, stride=(2, 2), bias=self.b["conv6"], relu=lk)
+            ops.conv_gemm(c6, self.w["conv6_1"], c61, taps=(3, 3), pad=1, bias=self.b["conv6_1"], relu=lk)
+            # refinement: flow6 -> (upsampled flow, deconv) -> concat2 -> flow5 -> ... -> concat5
+            ops.conv_gemm(c61, self.w["Convolution1"], fl6[..., 0:2], taps=(3, 3), pad=1, bias=self.b["Convolution1"], cout=2)
+            self._deconv("deconv5", c61, cat2, 512, 512, lk)
+            self._deconv("upsample_flow6to5", fl6, cat2, 1024, 2, False)
+            ops.conv_gemm(cat2, self.w["Convolution2"], fl5[..., 0:2], taps=(3, 3), pad=1, bias=self.b["Convolution2"], cout=2)
+            self._deconv("deconv4", cat2, cat3, 512, 256, lk)
+            self._deconv("upsample_flow5to4", fl5, cat3, 768, 2, False)
+            ops.conv_gemm(cat3, self.w["Convolution3"], fl4[..., 0:2], taps=(3, 3), pad=1, bias=self.b["Convolution3"], cout=2)
+            self._deconv("deconv3", cat3, cat4, 256, 128, lk)
+            self._deconv("upsample_flow4to3", fl4, cat4, 384, 2, False)
+            ops.conv_gemm(cat4, self.w["Convolution4"], fl3[..., 0:2], taps=(3, 3), pad=1, bias=self.b["Convolution4"], cout=2)
+            self._deconv("deconv2", cat4, cat5, 128, 64, lk)
+            self._deconv("upsample_flow3to2", fl3, cat5, 192, 2, False)
+        hf, wf = (h2 + 1) // 2, (w2 + 1) // 2
+        pooled = B("pool5", (n, hf, wf, 200))
+        ops.avgpool2_nhwc(cat5, pooled)
+        flow = B("flow", (n, hf, wf, 4), torch.float32)
+        ops.conv_gemm(pooled, self.w["Convolution5"], flow[..., 0:2], taps=(3, 3), pad=1, scale=self.scale25,
+                      bias=self.b["Convolution5_x2.5"], cout=2)
+        return flow
+
+
+class FgfaEngine(HeadCommon):
+    """GeneralizedRCNNFGFA._forward_test (detector/generalized_rcnn_fgfa.py:144-219) with the single-frame box head
+    (ResNetConv52MLPFeatureExtractor without channel reduction). Per frame the backbone map, the EmbedNet embedding
+    (backbone/embednet.py:19-24) and the pooled image are cached in rings of 19 slots; every step FlowNetS runs on the 19
+    (key, frame) pairs and one kernel warps / weights / sums the cached maps (csrc/fgfa.cu)."""
+
+    def __init__(self, sd, cfg=None, device="cuda"):
+        cfg = cfg or EngineConfig(all_frame_interval=19, key_frame_location=9)
+        dev = torch.device(device)
+        super().__init__(sd, cfg, dev)
+        act = self.act
+        self.L, self.KL = cfg.all_frame_interval, cfg.key_frame_location
+        self.flownet = FlowNetS(sd, dev, act)
+        e = "embednet."
+        self.e_w = [pack_conv(sd[e + "embed_conv%d.weight" % i], dev, act) for i in (1, 2, 3)]
+        self.e_b = [sd[e + "embed_conv%d.bias" % i].float().contiguous().to(dev) for i in (1, 2, 3)]
+        res = cfg.pooler_resolution
+        w6 = sd[FE + "fc6.weight"].float()
+        ch = w6.shape[1] // (res * res)
+        self.ch = ch
+        self.fc6_w = (w6.reshape(w6.shape[0], ch, res * res).permute(0, 2, 1).reshape(w6.shape[0], -1).contiguous()
+                      .to(act).to(dev))
+        self.fc6_b = sd[FE + "fc6.bias"].float().contiguous().to(dev)
+        self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev).to(act)
+        self.fc7_b = sd[FE + "fc7.bias"].float().contiguous().to(dev)
+        self.slots_h = torch.zeros(self.L, dtype=torch.int32).pin_memory()
+        self.slots_d = torch.zeros(self.L, dtype=torch.int32, device=dev)
+        self.ring = None
+        self.reset()
+
+    def reset(self):
+        self.win_slots = deque(maxlen=self.L)
+        self.next_slot = 0
+
+    def _alloc(self, h, w):
+        fh, fw = (h - 1) // 16 + 1, (w - 1) // 16 + 1
+        hq, wq = (h + 1) // 2, (w + 1) // 2
+        assert wq % 2 == 0, "the row-slab form of flow_conv1 needs an even pooled width"
+        key = (h, w)
+        if self.ring is None or self._ring_key != key:
+            self.ring = torch.zeros(self.L, fh, fw, 3072, device=self.dev, dtype=self.act)       # [feats 1024 | embed 2048]
+            self.img_ring = torch.zeros(self.L, hq, wq, 4, device=self.dev, dtype=self.act)
+            self.pairs = torch.zeros(self.L, hq + 6, wq + 8, 8, device=self.dev, dtype=self.act)
+            self.agg = torch.zeros(1, fh, fw, 1024, device=self.dev, dtype=self.act)
+            self._ring_key = key
+
+    def _ingest_frame(self, img, slot):
+        """backbone + EmbedNet + pooled image of one frame into ring slot `slot` (update_feature, :152-158)"""
+        feats = self.backbone.forward(img)                                          # [1,fh,fw,1024]
+        n, fh, fw, _ = feats.shape
+        dst = self.ring[slot:slot + 1]
+        e1 = self._buf("emb1", (1, fh, fw, 512), self.act)
+        e2 = self._buf("emb2", (1, fh, fw, 512), self.act)
+        ops.conv_gemm(feats, self.e_w[0], e1, bias=self.e_b[0], relu=True)
+        ops.conv_gemm(e1, self.e_w[1], e2, taps=(3, 3), pad=1, bias=self.e_b[1], relu=True)
+        ops.conv_gemm(e2, self.e_w[2], dst[..., 1024:3072], bias=self.e_b[2])
+        ops.copy_rows(feats.view(fh * fw, 1024), dst.view(fh * fw, 3072)[:, 0:1024], fh * fw)
+        ops.fgfa_pool_image(img, self.img_ring[slot])
+
+    def static_input(self, shape):
+        t = getattr(self, "_static_in", {}).get(tuple(shape))
+        if t is None:
+            self._static_in = getattr(self, "_static_in", {})
+            t = self._static_in[tuple(shape)] = torch.zeros(*shape, device=self.dev)
+        return t
+
+    def _claim(self):
+        slot = self.next_slot
+        self.next_slot = (self.next_slot + 1) % self.L
+        self.win_slots.append(slot)
+        return slot
+
+    @_with_precision
+    def start_video(self, cur, lookahead, im_w, im_h):
+        self.reset()
+        self._alloc(cur.shape[-2], cur.shape[-1])
+        need = self.L - (self.KL + 1)
+        assert len(lookahead) >= need, "first frame of a video needs %d look-ahead frames" % need
+        s0 = self._claim()
+        self._ingest_frame(cur, s0)
+        for _ in range(self.KL):
+            self.win_slots.append(s0)                 # the first frame fills window positions 0..key (:173-176)
+        self.next_slot = 1
+        for f in lookahead[:need]:
+            self._ingest_frame(f, self._claim())
+        return self._detect(im_w, im_h)
+
+    @_with_precision
+    def step(self, new_frame, im_w, im_h):
+        self._ingest_frame(new_frame, self._claim())
+        return self._detect(im_w, im_h)
+
+    def _detect(self, im_w, im_h):
+        c = self.cfg
+        slots = list(self.win_slots)
+        assert len(slots) == self.L
+        self.slots_h.copy_(torch.tensor(slots, dtype=torch.int32))
+        self.slots_d.copy_(self.slots_h, non_blocking=True)
+        ops.fgfa_build_pairs(self.img_ring, self.slots_d, self.KL, self.pairs)
+        flow = self.flownet.forward(self.pairs)
+        self.last_flow = flow
+        ops.fgfa_aggregate(self.ring, self.slots_d, self.KL, flow, self.agg[0], 1024, 2048)
+        feats = self.agg
+        KP = c.post_nms_top_n
+        boxes, _, cnt = self.rpn(feats, im_w, im_h, KP)
+        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained):
+            x = self.res5.forward(feats)
+        res = c.pooler_resolution
+        pooled = self._buf("pooled", (KP, res * res * self.ch), self.act)
+        ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)
+        f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]), self.act)
+        ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True)
+        f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]), self.act)
+        ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
+        self.last_feats, self.last_props, self.last_cnt = feats, boxes[0], cnt
+        return self.predict_and_postprocess(f7, boxes[0], cnt[0:1], im_w, im_h)

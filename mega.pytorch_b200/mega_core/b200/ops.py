@@ -220,7 +220,7 @@ def load_tuned(path):
 def _shape_key(d):
     return (d.a_n, d.a_h, d.a_w, d.a_c, d.a_stride_w, d.b_n, d.b_k, d.taps_r, d.taps_s, d.dil, d.k_per_tap, d.n_img,
             d.out_h, d.out_w, d.cout, d.tile_h, d.tile_w, d.batch, bool(d.residual), d.out_ld, d.out_c_off,
-            d.precision, d.out_f16)
+            d.precision, d.out_f16) + ((d.stride_h, d.stride_w) if (d.stride_h, d.stride_w) != (1, 1) else ())
 
 
 def _candidates(cout, prec=0, out_f16=0):
@@ -322,13 +322,16 @@ def pick_block_n(cout, m_tiles=0, batch=1):
 def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, residual=None,
               relu=False, tile=None, block_n=None, cout=None, k=None, batch=1, a_c_off=0,
               a_n_off=0, b_k_off=0, b_n_off=0, out_c_off=0, out_n_off=0, res_c_off=0, res_n_off=0, bias_z_off=0,
-              max_ctas=0, stream_k=None, out_hw=None, n_img=None):
+              max_ctas=0, stream_k=None, out_hw=None, n_img=None, stride=(1, 1), pad_w=None):
     """out[n,h,w,:] = act(scale * conv(a, w) + bias + residual)   (tcgen05 tensor cores, fp32 accumulate)
 
     a   : [N,H,W,C] fp32 or fp16 view (innermost stride 1; other strides multiples of 16 bytes)
     w   : [taps, rows, K] same dtype as a (K contiguous)
     out : [N,Ho,Wo,>=cout] fp32 view, or fp16 when a is fp16 (innermost stride 1); residual: same dtype as out
     fp32 operands run as TF32 (or the 3xTF32 split under ops.precision("fp32x3")), fp16 operands as kind::f16.
+    relu: False / True / "leaky" (LeakyReLU 0.1). stride = (stride_h, stride_w) of the convolution; pad_w: left padding
+    when it differs from `pad` (rows). `out` (and `residual`) may be strided views in w / h / n (e.g. every other
+    pixel of a larger map).
     """
     require_cuda(a, w, out, scale, bias, residual)
     f16 = a.dtype == torch.float16
@@ -344,8 +347,6 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     on, oh, ow, oc = out.shape
     if out_hw is not None:
         oh, ow = out_hw
-    assert out.stride(1) == out.stride(2) * out.shape[2] or out.shape[1] == 1
-    assert out.stride(0) == out.stride(2) * out.shape[2] * out.shape[1] or out.shape[0] == 1
     d = ConvGemmDesc()
     d.a = ptr(a)
     d.a_n, d.a_h, d.a_w, d.a_c = n, h, wd, c
@@ -361,7 +362,19 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.cout = cout if cout is not None else rows
     d.scale, d.bias, d.residual = ptr(scale), ptr(bias), ptr(residual)
     d.res_ld = residual.stride(-2) if residual is not None else 0
-    d.relu = 1 if relu else 0
+    if oh > 1:
+        d.out_stride_h = out.stride(1)
+    if d.n_img > 1 or batch > 1:
+        d.out_stride_n = out.stride(0)
+    if residual is not None and residual.dim() == 4:
+        if oh > 1:
+            d.res_stride_h = residual.stride(1)
+        if d.n_img > 1 or batch > 1:
+            d.res_stride_n = residual.stride(0)
+    d.relu = 2 if relu == "leaky" else (1 if relu else 0)
+    d.stride_h, d.stride_w = stride
+    if pad_w is not None:
+        d.pad_w_set, d.pad_w = 1, pad_w
     th, tw = tile if tile is not None else pick_tile(oh, ow)
     d.tile_h, d.tile_w = th, tw
     m_tiles = d.n_img * (-(-oh // th)) * (-(-ow // tw))
@@ -605,4 +618,52 @@ def box_postprocess(logits, deltas, proposals, count, num_classes, im_w, im_h, s
                                    ptr(ob), ptr(os_), ptr(ol), ob.shape[0], ptr(oc), stream_ptr()),
           "mega_box_postprocess")
     LAUNCHES[0] += 2
+    return out
+
+
+# --------------------------------------------------------------------------- FGFA helpers (csrc/fgfa.cu)
+def _is16(t):
+    return 1 if t.dtype == torch.float16 else 0
+
+
+def fgfa_pool_image(img, out):
+    """img [1,3,H,W] or [3,H,W] fp32 -> out [ceil(H/2), ceil(W/2), 4] = avg_pool2d(img / 255, 2, ceil_mode)"""
+    require_cuda(img, out)
+    h, w = img.shape[-2:]
+    assert img.dtype == torch.float32 and img.is_contiguous()
+    check(lib.mega_fgfa_pool_image(ptr(img), h, w, ptr(out), _is16(out), stream_ptr()), "mega_fgfa_pool_image")
+    LAUNCHES[0] += 1
+    return out
+
+
+def fgfa_build_pairs(ring, slots, key_pos, pairs):
+    """ring [S, hq, wq, 4]; slots int32 [L] (device); pairs [L, hq+6, wq+8, 8]"""
+    require_cuda(ring, slots, pairs)
+    s, hq, wq, _ = ring.shape
+    assert ring.dtype == pairs.dtype and slots.dtype == torch.int32
+    check(lib.mega_fgfa_build_pairs(ptr(ring), ring.stride(0), ptr(slots), slots.numel(), key_pos, hq, wq, ptr(pairs),
+                                    _is16(ring), stream_ptr()), "mega_fgfa_build_pairs")
+    LAUNCHES[0] += 1
+    return pairs
+
+
+def avgpool2_nhwc(x, out):
+    require_cuda(x, out)
+    n, h, w, c = x.shape
+    assert x.dtype == out.dtype and x.stride(3) == 1 and out.stride(3) == 1
+    check(lib.mega_avgpool2_nhwc(ptr(x), n, h, w, c, x.stride(2), ptr(out), out.stride(2), _is16(x), stream_ptr()),
+          "mega_avgpool2_nhwc")
+    LAUNCHES[0] += 1
+    return out
+
+
+def fgfa_aggregate(ring, slots, key_pos, flow, out, feat_channels, embed_channels, weights_out=None):
+    """ring [S, h, w, ld] ([feats | embeds] per pixel); flow [L, h, w, fl] fp32; out [h, w, >= feat_channels]"""
+    require_cuda(ring, slots, flow, out, weights_out)
+    s, h, w, ld = ring.shape
+    assert flow.dtype == torch.float32 and ring.dtype == out.dtype
+    check(lib.mega_fgfa_aggregate(ptr(ring), ring.stride(0), ld, feat_channels, embed_channels, ptr(slots), slots.numel(),
+                                  key_pos, ptr(flow), flow.stride(2), h, w, ptr(out), out.stride(-2), ptr(weights_out),
+                                  _is16(ring), stream_ptr()), "mega_fgfa_aggregate")
+    LAUNCHES[0] += 1
     return out

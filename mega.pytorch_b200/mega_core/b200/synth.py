@@ -75,7 +75,7 @@ def _linear(sd, p, nout, nin, gen, std=None, gain=1.0):
 
 def make_state_dict(arch="mega_r101", seed=0, num_classes=31):
     """state_dict with the reference's key names/shapes for
-    arch in {"mega_r101", "mega_r50", "rdn_r101", "rdn_r50", "base_r50", "base_r101"} (+ "_tiny" suffix: 1 block per stage,
+    arch in {"mega_r101", "mega_r50", "rdn_r101", "fgfa_r101", "base_r50", "base_r101"} (+ "_tiny" suffix: 1 block per stage,
     for fast CPU tests)."""
     gen = torch.Generator().manual_seed(seed)
     tiny = arch.endswith("_tiny")
@@ -105,6 +105,38 @@ def make_state_dict(arch="mega_r101", seed=0, num_classes=31):
         sd[fe + "conv.bias"] = torch.zeros(256)
         _linear(sd, fe + "fc6.", 1024, 256 * 49, gen)
         _linear(sd, fe + "fc7.", 1024, 1024, gen)
+    elif method == "fgfa":
+        # GeneralizedRCNNFGFA: FlowNetS + EmbedNet next to the backbone (backbone/flownet.py, embednet.py), box head =
+        # ResNetConv52MLPFeatureExtractor without the channel reduction (configs/FGFA/vid_R_101_C4_FGFA_1x.yaml)
+        _linear(sd, fe + "fc6.", 1024, 2048 * 49, gen)
+        _linear(sd, fe + "fc7.", 1024, 1024, gen)
+
+        def conv(name, cout, cin, k, gain=math.sqrt(2.0 / 1.01), bias=0.01):
+            sd[name + ".weight"] = _kaiming((cout, cin, k, k), gen, gain=gain)
+            sd[name + ".bias"] = torch.randn(cout, generator=gen) * bias
+
+        conv("flownet.flow_conv1", 64, 6, 7)
+        conv("flownet.conv2", 128, 64, 5)
+        conv("flownet.conv3", 256, 128, 5)
+        conv("flownet.conv3_1", 256, 256, 3)
+        conv("flownet.conv4", 512, 256, 3)
+        conv("flownet.conv4_1", 512, 512, 3)
+        conv("flownet.conv5", 512, 512, 3)
+        conv("flownet.conv5_1", 512, 512, 3)
+        conv("flownet.conv6", 1024, 512, 3)
+        conv("flownet.conv6_1", 1024, 1024, 3)
+        for i, cin in zip(range(1, 6), (1024, 1026, 770, 386, 194)):
+            conv("flownet.Convolution%d" % i, 2, cin, 3, gain=0.5)
+        for name, cin, cout in (("deconv5", 1024, 512), ("deconv4", 1026, 256), ("deconv3", 770, 128), ("deconv2", 386, 64)):
+            # ConvTranspose2d weight [cin, cout, 4, 4]; every output pixel sums 4 taps x cin inputs
+            sd["flownet.%s.weight" % name] = torch.randn(cin, cout, 4, 4, generator=gen) * (1.4 / math.sqrt(4.0 * cin))
+            sd["flownet.%s.bias" % name] = torch.randn(cout, generator=gen) * 0.01
+        for name in ("upsample_flow6to5", "upsample_flow5to4", "upsample_flow4to3", "upsample_flow3to2"):
+            sd["flownet.%s.weight" % name] = torch.randn(2, 2, 4, 4, generator=gen) * 0.25
+            sd["flownet.%s.bias" % name] = torch.zeros(2)
+        conv("embednet.embed_conv1", 512, 1024, 1)
+        conv("embednet.embed_conv2", 512, 512, 3)
+        conv("embednet.embed_conv3", 2048, 512, 1, gain=1.0)
     elif method == "rdn":
         # RDNFeatureExtractor with ATTENTION.STAGE = 2, ADVANCED_STAGE = 1 (configs/RDN/vid_R_101_C4_RDN_1x.yaml):
         # fcs[0..2], Wgs/Wqs/Wks/Wvs[0..3] (roi_box_feature_extractors.py:305-328)

@@ -1,10 +1,10 @@
 """build_detection_model(cfg) keyed by cfg.MODEL.META_ARCHITECTURE (detector/detectors.py:9-18)."""
 import os
 
-from .generalized_rcnn import GeneralizedRCNN, GeneralizedRCNNMEGA, GeneralizedRCNNRDN
+from .generalized_rcnn import GeneralizedRCNN, GeneralizedRCNNFGFA, GeneralizedRCNNMEGA, GeneralizedRCNNRDN
 
 _DETECTION_META_ARCHITECTURES = {"GeneralizedRCNN": GeneralizedRCNN, "GeneralizedRCNNMEGA": GeneralizedRCNNMEGA,
-                                 "GeneralizedRCNNRDN": GeneralizedRCNNRDN}
+                                 "GeneralizedRCNNRDN": GeneralizedRCNNRDN, "GeneralizedRCNNFGFA": GeneralizedRCNNFGFA}
 
 
 def build_detection_model(cfg):
@@ -32,6 +32,9 @@ def vid_config(method="mega", conv_body="R-101-C4", device="cuda"):
                                      "VID": {"METHOD": "rdn", "IGNORE": True,
                                              "ROI_BOX_HEAD": {"ATTENTION": {"ENABLE": True, "STAGE": 2, "ADVANCED_STAGE": 1}}},
                                      "ROI_BOX_HEAD": {"FEATURE_EXTRACTOR": "RDNFeatureExtractor"}}})
+    elif method == "fgfa":    # configs/FGFA/vid_R_101_C4_FGFA_1x.yaml
+        c.merge_from_dict({"MODEL": {"META_ARCHITECTURE": "GeneralizedRCNNFGFA", "VID": {"METHOD": "fgfa"},
+                                     "ROI_BOX_HEAD": {"FEATURE_EXTRACTOR": "ResNetConv52MLPFeatureExtractor"}}})
     elif method == "base":
         c.merge_from_dict({"MODEL": {"META_ARCHITECTURE": "GeneralizedRCNN",
                                      "VID": {"METHOD": "base", "ROI_BOX_HEAD": {"REDUCE_CHANNEL": True}},

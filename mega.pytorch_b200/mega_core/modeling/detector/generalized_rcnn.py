@@ -3,6 +3,7 @@
 GeneralizedRCNN       -- detector/generalized_rcnn.py:16-65 (single frame)
 GeneralizedRCNNMEGA   -- detector/generalized_rcnn_mega.py:21-225 (per-video state machine)
 GeneralizedRCNNRDN    -- detector/generalized_rcnn_rdn.py:20-190 (per-video state machine, 37-frame window)
+GeneralizedRCNNFGFA   -- detector/generalized_rcnn_fgfa.py:19-219 (flow-guided aggregation over a 19-frame window)
 
 `forward(images)` returns `list[BoxList]` (fields `scores`, `labels`) exactly like the reference in
 eval mode; the arithmetic runs in the B200 engine built lazily from this module's own state_dict
@@ -11,7 +12,7 @@ eval mode; the arithmetic runs in the B200 engine built lazily from this module'
 import torch
 from torch import nn
 
-from ..nets import build_backbone, build_roi_heads, build_rpn, engine_config_from
+from ..nets import EmbedNet, FlowNetS, build_backbone, build_roi_heads, build_rpn, engine_config_from
 from ...b200 import engine as _engine
 from ...structures.bounding_box import BoxList
 from ...structures.image_list import to_image_list
@@ -159,3 +160,14 @@ class GeneralizedRCNNRDN(GeneralizedRCNNMEGA):
                 buf[0].copy_(self._host(images["ref"][0]), non_blocking=True)
                 det = eng.step(buf, im_w, im_h)
         return [self._to_boxlist(det, im_w, im_h)]
+
+
+class GeneralizedRCNNFGFA(GeneralizedRCNNRDN):
+    """same call contract as the RDN detector (images dict with cur / ref / frame_category / ...); the module tree
+    additionally holds `flownet` and `embednet` (detector/generalized_rcnn_fgfa.py:30-35)"""
+    engine_cls = _engine.FgfaEngine
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.flownet = FlowNetS(cfg)
+        self.embednet = EmbedNet(cfg)

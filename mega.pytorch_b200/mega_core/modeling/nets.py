@@ -212,6 +212,41 @@ class CombinedROIHeads(nn.ModuleDict):
         self.cfg = cfg.clone()
 
 
+class FlowNetS(nn.Module):
+    """parameters of modeling/backbone/flownet.py:14-50 (method "fgfa")"""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.flow_conv1 = nn.Conv2d(6, 64, 7, stride=2, padding=3)
+        self.conv2 = nn.Conv2d(64, 128, 5, stride=2, padding=2)
+        self.conv3 = nn.Conv2d(128, 256, 5, stride=2, padding=2)
+        self.conv3_1 = nn.Conv2d(256, 256, 3, padding=1)
+        self.conv4 = nn.Conv2d(256, 512, 3, stride=2, padding=1)
+        self.conv4_1 = nn.Conv2d(512, 512, 3, padding=1)
+        self.conv5 = nn.Conv2d(512, 512, 3, stride=2, padding=1)
+        self.conv5_1 = nn.Conv2d(512, 512, 3, padding=1)
+        self.conv6 = nn.Conv2d(512, 1024, 3, stride=2, padding=1)
+        self.conv6_1 = nn.Conv2d(1024, 1024, 3, padding=1)
+        for i, cin in zip(range(1, 6), (1024, 1026, 770, 386, 194)):
+            setattr(self, "Convolution%d" % i, nn.Conv2d(cin, 2, 3, padding=1))
+        self.deconv5 = nn.ConvTranspose2d(1024, 512, 4, stride=2)
+        self.deconv4 = nn.ConvTranspose2d(1026, 256, 4, stride=2)
+        self.deconv3 = nn.ConvTranspose2d(770, 128, 4, stride=2)
+        self.deconv2 = nn.ConvTranspose2d(386, 64, 4, stride=2)
+        for n_ in ("6to5", "5to4", "4to3", "3to2"):
+            setattr(self, "upsample_flow" + n_, nn.ConvTranspose2d(2, 2, 4, stride=2))
+
+
+class EmbedNet(nn.Module):
+    """parameters of modeling/backbone/embednet.py:9-17"""
+
+    def __init__(self, cfg):
+        super().__init__()
+        self.embed_conv1 = nn.Conv2d(1024, 512, 1)
+        self.embed_conv2 = nn.Conv2d(512, 512, 3, padding=1)
+        self.embed_conv3 = nn.Conv2d(512, 2048, 1)
+
+
 def build_backbone(cfg):
     return registry.BACKBONES[cfg.MODEL.BACKBONE.CONV_BODY](cfg)
 
@@ -227,11 +262,11 @@ def build_roi_heads(cfg, in_channels):
 def engine_config_from(cfg):
     m = cfg.MODEL
     v = m.VID
-    win = v.RDN if v.METHOD == "rdn" else v.MEGA            # window geometry of the method
+    win = {"rdn": v.RDN, "fgfa": v.FGFA}.get(v.METHOD, v.MEGA)     # window geometry of the method
     return _engine.EngineConfig(
         pre_nms_top_n=m.RPN.PRE_NMS_TOP_N_TEST, post_nms_top_n=m.RPN.POST_NMS_TOP_N_TEST,
         ref_post_nms_top_n=v.RPN.REF_POST_NMS_TOP_N, rpn_nms_thresh=m.RPN.NMS_THRESH, rpn_min_size=m.RPN.MIN_SIZE,
-        ratio=win.RATIO, all_frame_interval=win.ALL_FRAME_INTERVAL, key_frame_location=win.KEY_FRAME_LOCATION,
+        ratio=win.get("RATIO", 0.2), all_frame_interval=win.ALL_FRAME_INTERVAL, key_frame_location=win.KEY_FRAME_LOCATION,
         advanced_stage=v.ROI_BOX_HEAD.ATTENTION.ADVANCED_STAGE,
         memory_size=v.MEGA.MEMORY.SIZE, global_size=v.MEGA.GLOBAL.SIZE, global_res_stage=v.MEGA.GLOBAL.RES_STAGE,
         stage=v.ROI_BOX_HEAD.ATTENTION.STAGE, groups=v.ROI_BOX_HEAD.ATTENTION.GROUP,

@@ -287,6 +287,79 @@ def golden_rdn(h=192, w=320, n_frames=3, total=40):
     return {"arch": "rdn_r101", "seed": 4, "h": h, "w": w, "total": total, "frames": gold}
 
 
+def run_reference_fgfa(sd, frames, n_frames):
+    cfg = ref_import.build_cfg("configs/FGFA/vid_R_101_C4_FGFA_1x.yaml")
+    from mega_core.modeling.detector import build_detection_model
+    from mega_core.structures.image_list import to_image_list
+    import mega_core.modeling.detector.generalized_rcnn_fgfa as gf
+    model = build_detection_model(cfg).eval()
+    full = dict(sd)
+    full["rpn.anchor_generator.cell_anchors.0"] = model.state_dict()["rpn.anchor_generator.cell_anchors.0"]
+    model.load_state_dict(full, strict=True)
+    gf.Image = types.SimpleNamespace(open=lambda path: _FakeImage(int(os.path.basename(path).split(".")[0])))
+    outs, hooks = [], {}
+    pred = model.roi_heads.box.predictor
+    orig_pred = pred.forward
+
+    def pred_fwd(x):
+        r = orig_pred(x)
+        hooks["class_logits"], hooks["box_regression"] = r[0].clone(), r[1].clone()
+        return r
+
+    pred.forward = pred_fwd
+    orig_flow = model.flownet.forward
+
+    def flow_fwd(x):
+        r = orig_flow(x)
+        hooks["flow"] = r.clone()
+        return r
+
+    model.flownet.forward = flow_fwd
+    orig_rpn = model.rpn.forward
+
+    def rpn_fwd(images, features, targets=None):
+        hooks["feats"] = features[0].clone()
+        return orig_rpn(images, features, targets)
+
+    model.rpn.forward = rpn_fwd
+    with torch.no_grad():
+        for t in range(n_frames):
+            images = {"cur": frames[t][0].clone(),
+                      "ref": [] if t == 0 else [to_image_list(frames[min(t + 9, len(frames) - 1)][0].clone())],
+                      "frame_category": 0 if t == 0 else 1, "seg_len": len(frames), "pattern": "%06d",
+                      "img_dir": "/nonexistent/%s.JPEG", "transforms": lambda im: frames[im.idx][0].clone()}
+            res = model(images)[0]
+            outs.append({"boxes": res.bbox.clone(), "scores": res.get_field("scores").clone(),
+                         "labels": res.get_field("labels").clone(), **{k: v for k, v in hooks.items()}})
+    return outs
+
+
+def golden_fgfa(h=192, w=320, n_frames=3, total=30):
+    print("  FGFA R-101 @%dx%d: reference vs oracle, %d frames" % (h, w, n_frames))
+    sd = synth.make_state_dict("fgfa_r101", seed=5)
+    frames = [synth.synthetic_frame(i, h, w) for i in range(total)]
+    ref = run_reference_fgfa(sd, frames, n_frames)
+    orc = mo.FgfaOracle(sd, record=True)
+    gold = []
+    for t in range(n_frames):
+        infos = {"frame_category": 0 if t == 0 else 1, "ref": frames[1:10] if t == 0 else [frames[min(t + 9, total - 1)]]}
+        b, s, l = orc.forward(frames[t], infos)
+        r = ref[t]
+        close(orc.trace["flow"], r["flow"], 2e-5, "frame %d flow" % t)
+        close(orc.trace["feats"], r["feats"], 2e-5, "frame %d aggregated feats" % t)
+        assert r["class_logits"].shape == orc.trace["class_logits"].shape, "proposal count differs"
+        close(orc.trace["class_logits"], r["class_logits"], 2e-5, "frame %d class_logits" % t)
+        close(orc.trace["box_regression"], r["box_regression"], 2e-5, "frame %d box_regression" % t)
+        assert torch.equal(l, r["labels"]) and b.shape == r["boxes"].shape, "detections differ (frame %d)" % t
+        close(b, r["boxes"], 1e-4, "frame %d det boxes" % t)
+        print("    flow rms %.3f max %.3f" % (r["flow"].pow(2).mean().sqrt().item(), r["flow"].abs().max().item()))
+        gold.append({"class_logits": r["class_logits"], "box_regression": r["box_regression"],
+                     "proposals": orc.trace["proposals"], "boxes": r["boxes"], "scores": r["scores"],
+                     "labels": r["labels"], "flow": r["flow"], "feats_sample": r["feats"][:, ::64].clone(),
+                     "feats_rms": r["feats"].pow(2).mean().sqrt().item()})
+    return {"arch": "fgfa_r101", "seed": 5, "h": h, "w": w, "total": total, "frames": gold}
+
+
 def golden_base(h=192, w=320):
     print("  single-frame R-50-C4 @%dx%d: reference vs oracle" % (h, w))
     cfg = ref_import.build_cfg("configs/vid_R_50_C4_1x.yaml")
@@ -327,6 +400,9 @@ def main():
     if "rdn" in only:
         torch.save(golden_rdn(), os.path.join(GOLD, "rdn_r101_192x320.pt"))
         return
+    if "fgfa" in only:
+        torch.save(golden_fgfa(), os.path.join(GOLD, "fgfa_r101_192x320.pt"))
+        return
     print("[1] reference unit-test vectors")
     torch.save(golden_from_reference_tests(), os.path.join(GOLD, "reference_unit_vectors.pt"))
     print("[2] op-level reference outputs")
@@ -335,6 +411,7 @@ def main():
     torch.save(golden_base(), os.path.join(GOLD, "base_r50_192x320.pt"))
     torch.save(golden_mega(), os.path.join(GOLD, "mega_r101_192x320.pt"))
     torch.save(golden_rdn(), os.path.join(GOLD, "rdn_r101_192x320.pt"))
+    torch.save(golden_fgfa(), os.path.join(GOLD, "fgfa_r101_192x320.pt"))
     for f in sorted(os.listdir(GOLD)):
         print("  wrote", f, os.path.getsize(os.path.join(GOLD, f)), "bytes")
 

@@ -635,6 +635,133 @@ class RdnOracle:
                                c.detections_per_img, cuda_semantics=c.cuda_nms_semantics)
 
 
+def _crop_like(x, target):
+    """backbone/flownet.py:7-11"""
+    if x.shape[2:] == target.shape[2:]:
+        return x
+    return x[:, :, 1:target.shape[2] + 1, 1:target.shape[3] + 1]
+
+
+def flownet_s(x, sd, p="flownet."):
+    """FlowNetS.forward, method "fgfa" (backbone/flownet.py:54-118): x [B,6,H,W] (image pairs / 255) -> flow [B,2,H/16,W/16] * 2.5"""
+    def conv(name, t, stride=1, pad=1):
+        return F.conv2d(t, sd[p + name + ".weight"], sd[p + name + ".bias"], stride, pad)
+
+    def deconv(name, t):
+        return F.conv_transpose2d(t, sd[p + name + ".weight"], sd[p + name + ".bias"], stride=2)
+
+    lrelu = lambda t: F.leaky_relu(t, 0.1)
+    pool = lambda t: F.avg_pool2d(t, 2, stride=2, ceil_mode=True)
+    x = pool(x)
+    relu1 = lrelu(conv("flow_conv1", x, 2, 3))
+    relu2 = lrelu(conv("conv2", relu1, 2, 2))
+    relu3 = lrelu(conv("conv3", relu2, 2, 2))
+    relu4 = lrelu(conv("conv3_1", relu3))
+    relu5 = lrelu(conv("conv4", relu4, 2))
+    relu6 = lrelu(conv("conv4_1", relu5))
+    relu7 = lrelu(conv("conv5", relu6, 2))
+    relu8 = lrelu(conv("conv5_1", relu7))
+    relu9 = lrelu(conv("conv6", relu8, 2))
+    relu10 = lrelu(conv("conv6_1", relu9))
+    flow6 = conv("Convolution1", relu10)
+    concat2 = torch.cat((relu8, lrelu(_crop_like(deconv("deconv5", relu10), relu8)),
+                         _crop_like(deconv("upsample_flow6to5", flow6), relu8)), dim=1)
+    flow5 = conv("Convolution2", concat2)
+    concat3 = torch.cat((relu6, lrelu(_crop_like(deconv("deconv4", concat2), relu6)),
+                         _crop_like(deconv("upsample_flow5to4", flow5), relu6)), dim=1)
+    flow4 = conv("Convolution3", concat3)
+    concat4 = torch.cat((relu4, lrelu(_crop_like(deconv("deconv3", concat3), relu4)),
+                         _crop_like(deconv("upsample_flow4to3", flow4), relu4)), dim=1)
+    flow3 = conv("Convolution4", concat4)
+    concat5 = torch.cat((relu2, lrelu(_crop_like(deconv("deconv2", concat4), relu2)),
+                         _crop_like(deconv("upsample_flow3to2", flow3), relu2)), dim=1)
+    return conv("Convolution5", pool(concat5)) * 2.5
+
+
+def embednet(x, sd, p="embednet."):
+    """EmbedNet.forward (backbone/embednet.py:19-24)"""
+    x = F.relu(F.conv2d(x, sd[p + "embed_conv1.weight"], sd[p + "embed_conv1.bias"]))
+    x = F.relu(F.conv2d(x, sd[p + "embed_conv2.weight"], sd[p + "embed_conv2.bias"], 1, 1))
+    return F.conv2d(x, sd[p + "embed_conv3.weight"], sd[p + "embed_conv3.bias"])
+
+
+def fgfa_warp(feats, flow):
+    """get_grid + resample (detector/generalized_rcnn_fgfa.py:45-62): bilinear, border padding, grid_sample's default
+    align_corners (False in this container's torch, as when the reference itself runs here)"""
+    m, n = flow.shape[-2:]
+    sy, sx = torch.meshgrid(torch.arange(0, m, 1, dtype=torch.float32), torch.arange(0, n, 1, dtype=torch.float32),
+                            indexing="ij")
+    grid_dst = torch.stack((sx, sy)).unsqueeze(0)
+    workspace = torch.tensor([(n - 1) / 2, (m - 1) / 2]).view(1, 2, 1, 1)
+    flow_grid = ((flow + grid_dst) / workspace - 1).permute(0, 2, 3, 1)
+    return F.grid_sample(feats, flow_grid, mode="bilinear", padding_mode="border")
+
+
+class FgfaOracle:
+    """GeneralizedRCNNFGFA._forward_test (detector/generalized_rcnn_fgfa.py:144-219), restated: window of 19 frames,
+    key frame at 9; per frame backbone features + EmbedNet embedding are cached; every step FlowNetS estimates the
+    flow from the key frame to all 19 window frames, the cached maps are warped, weighted per pixel by the cosine
+    similarity of the warped embeddings (soft-max over frames) and summed; the single-frame box head follows.
+    Frame 0's look-ahead frames come in infos["ref"] (list of tensors) instead of being read from disk (:180-190)."""
+
+    def __init__(self, state_dict, cfg=None, record=False):
+        self.sd = {k: v.detach().float() for k, v in state_dict.items()}
+        self.cfg = cfg or Cfg(all_frame_interval=19, key_frame_location=9)
+        self.record = record
+        self.trace = {}
+
+    def _frame(self, img):
+        feats = resnet_c4_body(img, self.sd)
+        return img, torch.cat([feats, embednet(feats, self.sd)], dim=1)
+
+    def forward(self, img, infos):
+        c, sd = self.cfg, self.sd
+        im_h, im_w = img.shape[-2:]
+        L, kl = c.all_frame_interval, c.key_frame_location
+        if infos["frame_category"] == 0:
+            self.images, self.features = deque(maxlen=L), deque(maxlen=L)
+            cur = self._frame(img)
+            while len(self.images) < kl + 1:
+                self.images.append(cur[0]); self.features.append(cur[1])
+            for im in infos["ref"]:
+                if len(self.images) >= L:
+                    break
+                f = self._frame(im)
+                self.images.append(f[0]); self.features.append(f[1])
+            assert len(self.images) == L
+        else:
+            f = self._frame(infos["ref"][0])
+            self.images.append(f[0]); self.features.append(f[1])
+        all_images = torch.cat(list(self.images), 0)
+        all_features = torch.cat(list(self.features), 0)
+        cur_image = self.images[kl]
+        pairs = torch.cat([cur_image.repeat(L, 1, 1, 1) / 255, all_images / 255], dim=1)
+        flow = flownet_s(pairs, sd)
+        warped = fgfa_warp(all_features, flow)
+        wf, emb = torch.split(warped, (1024, 2048), dim=1)
+        emb = emb.contiguous()
+        emb_cur = emb[kl:kl + 1]
+        en = emb / (torch.norm(emb, dim=1, keepdim=True) + 1e-10)
+        ec = emb_cur / (torch.norm(emb_cur, dim=1, keepdim=True) + 1e-10)
+        weights = F.softmax(torch.sum(en * ec, dim=1, keepdim=True), dim=0)
+        feats = torch.sum(weights * wf, dim=0, keepdim=True)
+        logits, deltas = rpn_head(feats, sd)
+        prop, obj = rpn_select(logits, deltas, im_w, im_h, c.pre_nms_top_n, c.post_nms_top_n, c.rpn_nms_thresh,
+                               cuda_semantics=c.cuda_nms_semantics)
+        x = res5_head(feats, sd, FE + "head.", c.res5_dilation)
+        rois = torch.cat([torch.zeros(prop.shape[0], 1), prop], dim=1)
+        x = roi_align(x, rois, c.pooler_scale, c.pooler_resolution, c.pooler_resolution, c.sampling_ratio).flatten(start_dim=1)
+        x = F.relu(F.linear(x, sd[FE + "fc6.weight"], sd[FE + "fc6.bias"]))
+        x = F.relu(F.linear(x, sd[FE + "fc7.weight"], sd[FE + "fc7.bias"]))
+        cl = F.linear(x, sd["roi_heads.box.predictor.cls_score.weight"], sd["roi_heads.box.predictor.cls_score.bias"])
+        bd = F.linear(x, sd["roi_heads.box.predictor.bbox_pred.weight"], sd["roi_heads.box.predictor.bbox_pred.bias"])
+        if self.record:
+            self.trace = {"proposals": prop.clone(), "class_logits": cl.clone(), "box_regression": bd.clone(),
+                          "flow": flow.clone(), "feats": feats.clone(), "weights": weights.clone()}
+        return box_postprocess(cl, bd, prop, im_w, im_h, c.score_thresh, c.nms_thresh, c.detections_per_img,
+                               cuda_semantics=c.cuda_nms_semantics)
+
+
 # --------------------------------------------------------------------------- ops outside the VID configs
 def sigmoid_focal_loss(logits, targets, gamma, alpha):
     """layers/sigmoid_focal_loss.py:40-50 (the reference's own CPU formula for RetinaNet's focal loss)."""

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 def _shadow_conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, residual=None, relu=False,
                       tile=None, block_n=None, cout=None, k=None, batch=1, a_c_off=0, a_n_off=0, b_k_off=0, b_n_off=0,
                       out_c_off=0, out_n_off=0, res_c_off=0, res_n_off=0, bias_z_off=0, max_ctas=0, stream_k=None,
-                      out_hw=None, n_img=None):
+                      out_hw=None, n_img=None, stride=(1, 1), pad_w=None):
     t, rows, kk = w.shape
     cout = rows if cout is None else cout
     k = kk if k is None else k
@@ -28,7 +28,10 @@ def _shadow_conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=
         wz = w[:, z * b_n_off: z * b_n_off + cout, z * b_k_off: z * b_k_off + k]   # [t, cout, k]
         x = az.permute(0, 3, 1, 2).double()
         wt = wz.reshape(taps[0], taps[1], cout, k).permute(2, 3, 0, 1).double()
-        y = F.conv2d(x, wt, None, 1, pad, dil)[:, :, :oh, :ow].permute(0, 2, 3, 1)   # [n,oh,ow,cout]
+        pw_ = pad if pad_w is None else pad_w
+        extra_h, extra_w = taps[0] * dil + stride[0], taps[1] * dil + stride[1]     # zero fill beyond the map, like TMA
+        x = F.pad(x, (pw_, extra_w, pad, extra_h))
+        y = F.conv2d(x, wt, None, stride, 0, dil)[:, :, :oh, :ow].permute(0, 2, 3, 1)   # [n,oh,ow,cout]
         if scale is not None:
             y = y * scale[z * bias_z_off: z * bias_z_off + cout].double()
         if bias is not None:
@@ -39,7 +42,9 @@ def _shadow_conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=
                                  (residual.stride(0), residual.stride(1), residual.stride(2), 1),
                                  residual.storage_offset() + z * res_z_off)
             y = y + r.double()
-        if relu:
+        if relu == "leaky":
+            y = F.leaky_relu(y, 0.1)
+        elif relu:
             y = y.relu()
         o = torch.as_strided(out, (on, oh, ow, cout), (out.stride(0), out.stride(1), ld, 1),
                              out.storage_offset() + z * out_z_off)

@@ -305,3 +305,58 @@ def test_f16_layer_chain_matches_per_layer_launches(cuda_dev):
         t = t * sb[2].double().cpu().view(1, -1, 1, 1) + bb[2].double().cpu().view(1, -1, 1, 1)
         x = (t.permute(0, 2, 3, 1) + xin).relu().half().double()
     assert _rel_err(y_ch.float(), x.float()) < 1e-2      # fp16 storage of 9 chained layers
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_strided_conv_leaky_and_transposed_conv(cuda_dev, dtype):
+    """the generalisations FlowNetS needs (backbone/flownet.py): stride-2 k x k convolutions through TMA element
+    strides, LeakyReLU(0.1) in the epilogue, ConvTranspose2d(4, stride 2) + crop_like as four parity-class 2x2
+    convolutions writing every other pixel of a channel slice of a wider (concat) buffer, 2-channel outputs."""
+    from mega_core.b200 import engine, ops
+    g = torch.Generator().manual_seed(3)
+    tol = 4e-3 if dtype == torch.float16 else TOL
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    q = (lambda t: t.half().float()) if dtype == torch.float16 else (lambda t: t)
+    # ---- 5x5 stride 2 conv + leaky relu, odd sizes
+    n, h, w, cin, cout = 2, 37, 45, 64, 128
+    x, wt, b = q(rnd(n, cin, h, w)), q(rnd(cout, cin, 5, 5) / (cin * 25) ** 0.5), rnd(cout)
+    ref = F.leaky_relu(F.conv2d(x, wt, b, 2, 2), 0.1)
+    out = torch.full((n, ref.shape[2], ref.shape[3], cout), float("nan"), device=cuda_dev, dtype=dtype)
+    ops.conv_gemm(x.permute(0, 2, 3, 1).contiguous().to(cuda_dev).to(dtype), engine.pack_conv(wt, cuda_dev, dtype), out,
+                  taps=(5, 5), pad=2, stride=(2, 2), bias=b.to(cuda_dev), relu="leaky")
+    torch.cuda.synchronize()
+    assert _rel_err(out.float().permute(0, 3, 1, 2), ref) < tol
+    # ---- ConvTranspose2d(cin, cout, 4, 2) + crop_like + leaky into channels [16, 16+cout) of a 72-channel buffer
+    sd = {"flownet.flow_conv1.weight": torch.zeros(64, 6, 7, 7)}
+    n, hi, wi, cin, cout = 2, 9, 13, 24, 40
+    xi = q(rnd(n, cin, hi, wi))
+    wd, bd = q(rnd(cin, cout, 4, 4) / (4 * cin) ** 0.5), rnd(cout)
+    full = F.conv_transpose2d(xi, wd, bd, stride=2)                       # [n, cout, 2hi+2, 2wi+2]
+    for ht, wt_ in ((2 * hi, 2 * wi), (2 * hi - 1, 2 * wi + 1), (2 * hi + 2, 2 * wi + 2)):
+        ref = full if (ht, wt_) == tuple(full.shape[2:]) else full[:, :, 1:ht + 1, 1:wt_ + 1]
+        ref = F.leaky_relu(ref, 0.1)
+        fl = engine.FlowNetS.__new__(engine.FlowNetS)
+        fl.dev, fl.dtype = cuda_dev, dtype
+        cls = {}
+        for py in (0, 1):
+            for px in (0, 1):
+                wp = torch.zeros(4, cout, cin)
+                for r in (0, 1):
+                    for s_ in (0, 1):
+                        wp[r * 2 + s_] = wd[:, :, py + 2 * (1 - r), px + 2 * (1 - s_)].t()
+                cls[(py, px)] = wp.contiguous().to(cuda_dev).to(dtype)
+        fl.w, fl.b = {"d": cls}, {"d": bd.to(cuda_dev)}
+        target = torch.full((n, ht, wt_, 72), 7.0, device=cuda_dev, dtype=dtype)
+        fl._deconv("d", xi.permute(0, 2, 3, 1).contiguous().to(cuda_dev).to(dtype), target, 16, cout, "leaky")
+        torch.cuda.synchronize()
+        assert (target[..., :16] == 7).all() and (target[..., 16 + cout:] == 7).all()
+        assert _rel_err(target[..., 16:16 + cout].float().permute(0, 3, 1, 2), ref) < tol, (ht, wt_)
+    # ---- 3x3 conv to 2 channels written into an 8-channel-padded buffer (channel-clipped TMA store)
+    xc, wc, bc = q(rnd(2, 200, 19, 32)), q(rnd(2, 200, 3, 3) / 1800 ** 0.5), rnd(2)
+    ref = F.conv2d(xc, wc, bc, 1, 1)
+    buf = torch.zeros(2, 19, 32, 8, device=cuda_dev, dtype=dtype)
+    ops.conv_gemm(xc.permute(0, 2, 3, 1).contiguous().to(cuda_dev).to(dtype), engine.pack_conv(wc, cuda_dev, dtype), buf[..., 0:2],
+                  taps=(3, 3), pad=1, bias=bc.to(cuda_dev), cout=2)
+    torch.cuda.synchronize()
+    assert (buf[..., 2:] == 0).all()
+    assert _rel_err(buf[..., 0:2].float().permute(0, 3, 1, 2), ref) < tol

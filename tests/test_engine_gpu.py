@@ -250,3 +250,62 @@ def test_rdn_r101_f16_matches_reference_fixture(cuda_dev):
         assert f["matched_frac"] >= 0.95, f
         assert f["logits_maxabs"] < 0.3, f        # measured 0.07 .. 0.17 at logit RMS 1.07
         assert f["proposals"] == f["ref_proposals"], f
+
+
+def _run_fgfa_against_fixture(cuda_dev, label, precision):
+    from mega_core.b200 import engine, synth
+    if precision == "shadow":
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from fp32_shadow import fp32_shadow
+        with fp32_shadow():
+            return _run_fgfa_against_fixture(cuda_dev, label, "tf32")
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "fgfa_r101_192x320.pt"))
+    h, w, total = gold["h"], gold["w"], gold["total"]
+    sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+    frames = [synth.synthetic_frame(i, h, w).to(cuda_dev) for i in range(total)]
+    eng = engine.FgfaEngine(sd, engine.EngineConfig(all_frame_interval=19, key_frame_location=9, precision=precision),
+                            device=cuda_dev)
+    per_frame = []
+    for t, ref in enumerate(gold["frames"]):
+        det = eng.start_video(frames[0], frames[1:10], w, h) if t == 0 else eng.step(frames[min(t + 9, total - 1)], w, h)
+        torch.cuda.synchronize()
+        k = int(eng.last_cnt[0].item())
+        idx = _match_rows(eng.last_props[:k].cpu(), ref["proposals"])
+        m = idx >= 0
+        pred = eng.last_pred[:k].cpu()
+        assert torch.isfinite(pred).all()
+        flow = eng.last_flow[..., :2].permute(0, 3, 1, 2).float().cpu()
+        feats = eng.last_feats.float().permute(0, 3, 1, 2).cpu()[:, ::64]
+        b, s, l = det.to_host()
+        per_frame.append({"proposals": k, "ref_proposals": int(ref["proposals"].shape[0]), "matched_frac": m.float().mean().item(),
+                          "logits_maxabs": (pred[idx[m], :31] - ref["class_logits"][m]).abs().max().item(),
+                          "flow_maxabs": (flow - ref["flow"]).abs().max().item(),
+                          "flow_rms": ref["flow"].pow(2).mean().sqrt().item(),
+                          "feats_maxabs": (feats - ref["feats_sample"]).abs().max().item(), "feats_rms": ref["feats_rms"],
+                          "dets": int(b.shape[0]), "ref_dets": int(ref["boxes"].shape[0]),
+                          "logit_rms": ref["class_logits"].pow(2).mean().sqrt().item()})
+        _METRICS[label] = per_frame
+        _dump()
+    return per_frame
+
+
+def test_fgfa_r101_logic_matches_reference_with_exact_fp32_contractions(cuda_dev):
+    """FGFA R-101 (BASELINE configs[4]): frame / image rings, pair building, FlowNetS wiring (strided convs, the four
+    parity classes of every transposed convolution, crops, concats), warp + adaptive weights + aggregation, box head --
+    against the REFERENCE's outputs with exact-fp32 contractions: flow within 1e-4 cells, every proposal reproduced,
+    class logits within 1e-3"""
+    for f in _run_fgfa_against_fixture(cuda_dev, "fgfa_r101_fp32_shadow", "shadow"):
+        assert f["flow_maxabs"] < 1e-4, f
+        assert f["feats_maxabs"] < 1e-3 * max(f["feats_rms"], 1.0), f
+        assert f["matched_frac"] == 1.0, f
+        assert f["logits_maxabs"] < 1e-3, f
+        assert f["dets"] == f["ref_dets"], f
+
+
+@pytest.mark.parametrize("precision", ["f16", "tf32"])
+def test_fgfa_r101_product_path_matches_reference_fixture(cuda_dev, precision):
+    """same on the tensor-core arithmetic: flow within 2 % of its RMS-scaled range, >= 95 % of the proposals reproduced"""
+    for f in _run_fgfa_against_fixture(cuda_dev, "fgfa_r101_" + precision, precision):
+        assert f["flow_maxabs"] < 0.05, f
+        assert f["matched_frac"] >= 0.95, f
+        assert f["logits_maxabs"] < 0.3, f

@@ -132,3 +132,18 @@ def test_rdn_r101_oracle_matches_reference_fixture():
         assert torch.allclose(orc.trace["class_logits"], ref["class_logits"], atol=1e-5)
         assert torch.equal(orc.trace["proposals"], ref["proposals"])
         assert torch.equal(l, ref["labels"]) and torch.allclose(b, ref["boxes"], atol=1e-4)
+
+
+def test_fgfa_r101_oracle_matches_reference_fixture():
+    """frame 0 of the unmodified reference's GeneralizedRCNNFGFA (FlowNetS + EmbedNet + warp / weights / aggregation)"""
+    synth = _synth()
+    gold = torch.load(os.path.join(GOLD, "fgfa_r101_192x320.pt"))
+    h, w, total = gold["h"], gold["w"], gold["total"]
+    sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+    frames = [synth.synthetic_frame(i, h, w) for i in range(10)]
+    orc = mo.FgfaOracle(sd, record=True)
+    ref = gold["frames"][0]
+    b, s, l = orc.forward(frames[0], {"frame_category": 0, "ref": frames[1:10]})
+    assert torch.allclose(orc.trace["flow"], ref["flow"], atol=1e-5)
+    assert torch.allclose(orc.trace["class_logits"], ref["class_logits"], atol=1e-5)
+    assert torch.equal(orc.trace["proposals"], ref["proposals"]) and torch.equal(l, ref["labels"])
