@@ -274,15 +274,15 @@ roi_align_nhwc_cached_kernel(const T* __restrict__ in, int channels, int height,
 // per (bin, sample, channel group); (ii) the blend uses fused multiply-adds in fp32 (results are rounded to fp16 at the
 // store anyway, so the bit-exact association order of the fp32 kernels buys nothing here).
 struct AxisSample {
-  int lo, hi;       // clamped cell indices
-  float wlo, whi;   // weights of the two cells; both 0 when the sample lies outside [-1, size]
+  int lo, hi;       // clamped cell indices; -1 when the sample lies outside [-1, size] (contributes nothing)
+  float wlo, whi;   // weights of the two cells
 };
 constexpr int kRoiMaxGrid = 8;   // samples per bin and axis handled by the fast path (roi extent up to 8*7 cells)
 
 __device__ __forceinline__ AxisSample axis_sample(float c, int size) {
   AxisSample a;
-  if (c < -1.0f || c > static_cast<float>(size)) {
-    a.lo = a.hi = 0;
+  if (c < -1.0f || c > static_cast<float>(size)) {   // the reference adds exactly 0 for such samples
+    a.lo = a.hi = -1;
     a.wlo = a.whi = 0.f;
     return a;
   }
@@ -355,9 +355,11 @@ roi_align_nhwc_f16_fast_kernel(const __half* __restrict__ in, int channels, int 
     for (int iy = 0; iy < g.grid_h; ++iy) {
       const AxisSample ay = tabled ? ys[phi * g.grid_h + iy]
                                    : axis_sample(sample_coord(g.start_h, phi, g.bin_h, iy, g.grid_h), height);
+      if (ay.lo < 0) continue;
       for (int ix = 0; ix < g.grid_w; ++ix) {
         const AxisSample ax = tabled ? xs[pwi * g.grid_w + ix]
                                      : axis_sample(sample_coord(g.start_w, pwi, g.bin_w, ix, g.grid_w), width);
+        if (ax.lo < 0) continue;
         const float w1 = ay.wlo * ax.wlo, w2 = ay.wlo * ax.whi, w3 = ay.whi * ax.wlo, w4 = ay.whi * ax.whi;
         uint4 v1, v2, v3, v4;
         if (cached) {     // the footprint covers every clamped sample cell by construction
