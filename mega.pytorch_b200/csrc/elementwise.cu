@@ -181,6 +181,33 @@ __global__ void maxpool3x3s2_nhwc_f16_kernel(const __half* __restrict__ in, int 
   }
 }
 
+// NCHW fp32 image -> zero-bordered NHWC (8 channels per pixel: c0..c2 + 5 zeros) [N][H+6][WP][8], WP >= W+8 even:
+// the A operand of BaseStem.conv1 (7x7 / stride 2 / pad 3) as a row-slab implicit GEMM -- the 7 taps of one filter
+// row are 56 (+8 zero-weighted) contiguous elements, fetched by TMA through an overlapping strided view (no im2col)
+template <typename T>
+__global__ void stem_prep_kernel(const float* __restrict__ in, int n_img, int height, int width, int wp, T* __restrict__ out) {
+  const int hp = height + 6;
+  const long long total = static_cast<long long>(n_img) * hp * wp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % wp) - 3;
+    const int y = static_cast<int>((i / wp) % hp) - 3;
+    const int n = static_cast<int>(i / (static_cast<long long>(wp) * hp));
+    float v[3] = {0.f, 0.f, 0.f};
+    if (y >= 0 && y < height && x >= 0 && x < width) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __ldg(in + ((static_cast<long long>(n) * 3 + c) * height + y) * width + x);
+    }
+    T* o = out + i * 8;
+    if (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(o) = make_uint4(f2_to_h2(v[0], v[1]), f2_to_h2(v[2], 0.f), 0u, 0u);
+    } else {
+      reinterpret_cast<float4*>(o)[0] = make_float4(v[0], v[1], v[2], 0.f);
+      reinterpret_cast<float4*>(o)[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long b = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -210,6 +237,17 @@ extern "C" int mega_stem_im2col_f16(const float* input, int n_img, int height, i
   const long long total = static_cast<long long>(n_img) * ho * wo * (kpad / 8);
   stem_im2col_f16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(input, n_img, height, width, ho, wo, kpad,
                                                                    static_cast<__half*>(out));
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_stem_prep(const float* input, int n_img, int height, int width, int wp, void* out, int f16,
+                              void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(wp >= width + 8 && (wp & 1) == 0, "stem_prep: padded width must be even and >= width + 8");
+  const long long total = static_cast<long long>(n_img) * (height + 6) * wp;
+  if (f16) stem_prep_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>(input, n_img, height, width, wp, static_cast<__half*>(out));
+  else stem_prep_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(input, n_img, height, width, wp, static_cast<float*>(out));
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }

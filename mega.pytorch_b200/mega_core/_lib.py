@@ -139,6 +139,8 @@ lib.mega_avgpool2_nhwc.argtypes = [_vp, _i, _i, _i, _i, _ll, _vp, _ll, _i, _vp]
 lib.mega_avgpool2_nhwc.restype = _i
 lib.mega_fgfa_aggregate.argtypes = [_vp, _ll, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp, _ll, _vp, _i, _vp]
 lib.mega_fgfa_aggregate.restype = _i
+lib.mega_stem_prep.argtypes = [_vp, _i, _i, _i, _i, _vp, _i, _vp]
+lib.mega_stem_prep.restype = _i
 lib.mega_stem_im2col.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
 lib.mega_stem_im2col.restype = _i
 lib.mega_maxpool3x3s2_nhwc.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
@@ -176,5 +178,5 @@ EXPORTS = [
     "mega_box_postprocess", "mega_sigmoid_focalloss_forward", "mega_sigmoid_focalloss_backward",
     "mega_deform_im2col", "mega_deform_psroi_pooling_forward",
     "mega_roi_align_forward_nhwc_f16", "mega_stem_im2col_f16", "mega_maxpool3x3s2_nhwc_f16", "mega_relation_softmax_f16", "mega_relation_softmax_pe",
-    "mega_fgfa_pool_image", "mega_fgfa_build_pairs", "mega_avgpool2_nhwc", "mega_fgfa_aggregate",
+    "mega_stem_prep", "mega_fgfa_pool_image", "mega_fgfa_build_pairs", "mega_avgpool2_nhwc", "mega_fgfa_aggregate",
 ]

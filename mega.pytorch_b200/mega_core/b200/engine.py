@@ -121,6 +121,10 @@ def pack_conv(w, dev, dtype=torch.float32):
     return w.float().permute(2, 3, 0, 1).reshape(kh * kw, co, ci).contiguous().to(dev).to(dtype)
 
 
+# BaseStem.conv1 as a row-slab implicit GEMM over the bordered NHWC8 image (True) or through an im2col buffer (False)
+STEM_ROW_SLABS = [True]
+
+
 class _Block:
     pass
 
@@ -203,6 +207,12 @@ class Backbone:
         wp = torch.zeros(1, 64, 160)
         wp[0, :, :147] = w
         self.stem_w = wp.contiguous().to(dev).to(dtype)
+        # row-slab form of the 7x7 / stride-2 stem (no im2col): [7 filter rows][64 cout][7 taps x 8 channels + 8 zeros]
+        w7 = sd[prefix + "stem.conv1.weight"].float()
+        wr = torch.zeros(7, 64, 64)
+        for s_ in range(7):
+            wr[:, :, s_ * 8:s_ * 8 + 3] = w7[:, :, :, s_].permute(2, 0, 1)
+        self.stem_wr = wr.contiguous().to(dev).to(dtype)
         self.stem_s, self.stem_b = fold_bn(sd, prefix + "stem.bn1.", dev)
         self.stages = ResNetStages(sd, prefix, (1, 2, 3), dev, first_stride_of=lambda li: 2 if li > 1 else 1,
                                    dtype=dtype)
@@ -224,11 +234,21 @@ class Backbone:
         may append further conv_gemm calls on the result to the same chain (the RPN head)."""
         n, _, h, w = img.shape
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
-        col = self._buf("col", (n, ho * wo, 160))
-        ops.stem_im2col(img, col)
         s = self._buf("stem", (n, ho, wo, 64))
-        ops.conv_gemm(col.view(n, 1, ho * wo, 160), self.stem_w, s.view(n, 1, ho * wo, 64), scale=self.stem_s,
-                      bias=self.stem_b, relu=True, tile=(1, 128), block_n=64)
+        if STEM_ROW_SLABS[0]:
+            # BaseStem.conv1 straight from a zero-bordered NHWC8 copy of the image: output (oh, ow), filter row r reads the
+            # 64 contiguous elements starting at pixel (2 oh + r, 2 ow) of the bordered image
+            wp = _round_up(w + 8, 2)
+            pad = self._buf("stem_in", (n, h + 6, wp, 8))
+            ops.stem_prep(img, pad)
+            a = pad.as_strided((n, h + 6, wo, 64), ((h + 6) * wp * 8, wp * 8, 16, 1))
+            ops.conv_gemm(a, self.stem_wr, s, taps=(7, 1), pad=0, stride=(2, 1), scale=self.stem_s, bias=self.stem_b,
+                          relu=True, block_n=64)
+        else:
+            col = self._buf("col", (n, ho * wo, 160))
+            ops.stem_im2col(img, col)
+            ops.conv_gemm(col.view(n, 1, ho * wo, 160), self.stem_w, s.view(n, 1, ho * wo, 64), scale=self.stem_s,
+                          bias=self.stem_b, relu=True, tile=(1, 128), block_n=64)
         hp, wp = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         p = self._buf("pool", (n, hp, wp, 64))
         ops.maxpool3x3s2(s, p)

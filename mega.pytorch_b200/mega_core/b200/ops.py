@@ -524,6 +524,17 @@ def stem_im2col(img, out, kpad=160):
     return out
 
 
+def stem_prep(img, out):
+    """img [N,3,H,W] fp32 -> out [N, H+6, WP, 8] (zero border of 3 pixels, 3 real channels)"""
+    require_cuda(img, out)
+    n, c, h, w = img.shape
+    assert c == 3 and img.is_contiguous() and img.dtype == torch.float32 and out.shape[1] == h + 6 and out.shape[3] == 8
+    check(lib.mega_stem_prep(ptr(img), n, h, w, out.shape[2], ptr(out), 1 if out.dtype == torch.float16 else 0,
+                             stream_ptr()), "mega_stem_prep")
+    LAUNCHES[0] += 1
+    return out
+
+
 def maxpool3x3s2(x, out):
     require_cuda(x, out)
     n, h, w, c = x.shape
