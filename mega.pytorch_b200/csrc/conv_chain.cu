@@ -14,7 +14,6 @@
 //
 // Restrictions of a chain: fp16 operands (kind::f16), block_n <= 128 (one 32 KB smem stage holds A 128 x 64 and B
 // block_n x 64 halves), output fp16 or fp32 per layer.
-#include <stdlib.h>
 #include "conv_gemm_kernel.cuh"
 
 namespace mega {
@@ -24,48 +23,18 @@ constexpr int kChainStageBytes = 32768;     // A tile 16 KB + B tile (<= 128 row
 constexpr int kChainABytes = 16384;
 constexpr int kChainEpiBytes = 4 * 4 * 4096;
 constexpr int kChainBarOffset = kChainStages * kChainStageBytes + kChainEpiBytes;
-constexpr int kChainSbOffset = kChainBarOffset + 320;      // [scale | bias][128] floats of the tile being finished
+constexpr int kChainSbOffset = kChainBarOffset + 256;      // [scale | bias][128] floats of the tile being finished
 constexpr int kChainSmem = kChainSbOffset + 1024 + 1024;
 constexpr uint32_t kChainTmemCols = 256;    // two accumulators of up to 128 fp32 columns
 constexpr uint32_t kChainAccStride = 128;
 
-constexpr int kClusterSize = 2;   // CTA pairs (one TPC): the two CTAs of a pair work on adjacent N tiles of the same M tile
-
 struct alignas(128) ChainLayer {
   CUtensorMap tmA, tmB, tmOut, tmRes;
-  CUtensorMap tmAh;  // multicast mode: half of the A tile (64 of the 128 pixels)
   ConvGemmParams p;
   int block_n;
   int out16;
   int active_ctas;   // CTAs that take part in this layer's work list (<= grid); the others only pass the barrier
-  // multicast mode (mc != 0): the CTA pair (cluster) q takes "pair tiles" (m tile, pair of adjacent n tiles); CTA rank r
-  // computes n tile 2*np + r; each CTA loads only half of the shared A tile and multicasts it to both, so the L2->SM
-  // operand traffic per CTA drops from (128 + BN) to (64 + BN) rows per k-block
-  int mc;
-  int half_w;        // 1: the halves split the tile along w (tile_h == 1), 0: along h
-  int half_off;      // pixels between the halves along that axis (tile_w / 2 or tile_h / 2)
-  int pair_tiles;    // batch * m_tiles * n_tiles / 2
   int reserved;
-};
-
-// pair-tile work list of multicast layers (both CTAs of a pair walk it in lockstep)
-struct McIter {
-  int pt, pts, step, m_tiles, half_n, n_tiles, rank, KB;
-  __device__ __forceinline__ McIter(const ConvGemmParams& p, int pair_tiles, int cluster, int n_clusters, int rank_)
-      : pt(cluster), pts(pair_tiles), step(n_clusters), m_tiles(p.m_tiles), half_n(p.n_tiles / 2), n_tiles(p.n_tiles),
-        rank(rank_), KB(p.kb_per_tile) {}
-  __device__ __forceinline__ bool next(int& t, int& kb0, int& kb1) {
-    if (pt >= pts) return false;
-    const int m = pt % m_tiles;
-    const int rest = pt / m_tiles;
-    const int np = rest % half_n;
-    const int b = rest / half_n;
-    t = m + m_tiles * (2 * np + rank + n_tiles * b);
-    kb0 = 0;
-    kb1 = KB;
-    pt += step;
-    return true;
-  }
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -126,12 +95,11 @@ __device__ __forceinline__ TraceCursor trace_cursor(const ChainTrace& tr, int ro
 #define TR_TAG(layer, idx, code) ((static_cast<unsigned long long>(layer) << 32) | (static_cast<unsigned long long>(idx) << 8) | (code))
 
 // ------------------------------------------------------------------ epilogue of one layer (4 warps)
-template <bool OUT16, typename Iter>
+template <bool OUT16>
 __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const ConvGemmParams& p, const int BN, uint8_t* smem,
                                                      uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint64_t* res_bar,
                                                      int* epi_flag, uint32_t tmem_base, int warp, int lane, int cta,
-                                                     int grid, int& item, uint32_t& rphase, TraceCursor& tr, int layer,
-                                                     Iter it) {
+                                                     int grid, int& item, uint32_t& rphase, TraceCursor& tr, int layer) {
   constexpr int CW = OUT16 ? 64 : 32;
   const int q = warp & 3;
   const int row = q * 32 + lane;
@@ -145,6 +113,7 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
   const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
   const CUtensorMap* tmOut = &L->tmOut;
   const CUtensorMap* tmRes = &L->tmRes;
+  WorkIter it(p, cta, grid);
   int t;
   int kb0, kb1;
   for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
@@ -336,14 +305,11 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, unsigned* sync, const ChainTrace trace) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  // two sets of pipeline barriers over the same smem ring: [0] CTA-local layers (empty count 1), [1] multicast layers
-  // (a stage is free once the MMAs of BOTH CTAs of the pair have read it: empty count 2). All stages are drained at
-  // every layer boundary (grid barrier), so switching sets between layers is safe; each set keeps its own phase.
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kChainBarOffset);   // [2][kChainStages]
-  uint64_t* empty_bar = full_bar + 2 * kChainStages;                          // [2][kChainStages]
-  uint64_t* tmem_full_bar = empty_bar + 2 * kChainStages;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;             // [2]
-  uint64_t* res_bar = tmem_empty_bar + 2;                   // [4 warps][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kChainBarOffset);
+  uint64_t* empty_bar = full_bar + kChainStages;
+  uint64_t* tmem_full_bar = empty_bar + kChainStages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
+  uint64_t* res_bar = tmem_empty_bar + 2;               // [4 warps][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
   int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
@@ -351,17 +317,11 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
   const int lane = threadIdx.x & 31;
   const int grid = gridDim.x;
   const int cta = blockIdx.x;
-  const int rank = static_cast<int>(cluster_ctarank());
-  const int cluster = cta / kClusterSize;
-  const int n_clusters = grid / kClusterSize;
-  constexpr uint16_t kPairMask = (1u << kClusterSize) - 1u;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kChainStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&full_bar[kChainStages + s], 1);
-      mbar_init(&empty_bar[kChainStages + s], kClusterSize);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
@@ -374,7 +334,6 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_slot;
   griddep_wait();
   griddep_launch_dependents();
@@ -385,13 +344,12 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
     // descriptor-based copies of a k-block are issued in parallel (a single thread needs ~650 cycles per k-block for
     // wait + expect + 2 TMA issues, measured with tools/trace_chain.py; the MMAs of a k-block take ~260)
     if (lane < 2) {
-      PipeState ps[2] = {{0, 0}, {0, 0}};
+      PipeState ps = {0, 0};
       TraceCursor tr = trace_cursor(trace, 0, cta);
       if (lane != 0) tr.p = nullptr;
       for (int l = 0; l < n_layers; ++l) {
         const ChainLayer* L = layers + l;
-        const int mc = L->mc;
-        if (lane == 0) prefetch_tmap(mc ? &L->tmAh : &L->tmA); else prefetch_tmap(&L->tmB);
+        if (lane == 0) prefetch_tmap(&L->tmA); else prefetch_tmap(&L->tmB);
         // everything the loop needs from the layer table is fetched BEFORE the grid barrier
         const ConvGemmParams p = L->p;
         const int BN = L->block_n;
@@ -399,25 +357,17 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         const int k_chunks = p.k_chunks, taps_s = p.taps_s, dil = p.dil, pad = p.pad, pad_w = p.pad_w;
         const int stride_h = p.stride_h, stride_w = p.stride_w;
         const int a_c_off = p.a_c_off, a_n_off = p.a_n_off, b_k_off = p.b_k_off, b_n_off = p.b_n_off;
-        const CUtensorMap* tmA = mc ? &L->tmAh : &L->tmA;
+        const CUtensorMap* tmA = &L->tmA;
         const CUtensorMap* tmB = &L->tmB;
         const uint32_t tx_bytes = static_cast<uint32_t>((kBM + BN) * 128);
-        // this CTA's half of a shared A tile: pixel offset inside the tile and smem offset of the 64 rows
-        const int half_dw = (mc && L->half_w) ? rank * L->half_off : 0;
-        const int half_dh = (mc && !L->half_w) ? rank * L->half_off : 0;
-        const int half_smem = mc ? rank * (kChainABytes / kClusterSize) : 0;
-        const int pair_tiles = L->pair_tiles;
-        uint64_t* fb = full_bar + mc * kChainStages;
-        uint64_t* eb = empty_bar + mc * kChainStages;
-        PipeState& st = ps[mc];
         tr.put(TR_TAG(l, 0, 1));
         if (l > 0) grid_wait(sync, static_cast<unsigned>(l) * grid);
         tr.put(TR_TAG(l, 0, 2));
         if (cta >= act) continue;
-        WorkIter wi(p, cta, act);
-        McIter mi(p, pair_tiles, cluster, act / kClusterSize, rank);
-        int t, kb0, kb1;
-        while (mc ? mi.next(t, kb0, kb1) : wi.next(t, kb0, kb1)) {
+        WorkIter it(p, cta, act);
+        int t;
+        int kb0, kb1;
+        while (it.next(t, kb0, kb1)) {
           const TileCoord tc = decode_tile(p, t, BN);
           int tap = kb0 / k_chunks;
           int kc = kb0 - tap * k_chunks;
@@ -425,21 +375,16 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
           int sx = tap - r * taps_s;
           const int a_c0 = tc.batch * a_c_off, a_n = tc.img + tc.batch * a_n_off;
           const int b_k0 = tc.batch * b_k_off, b_n = tc.n0 + tc.batch * b_n_off;
-          const int aw0 = (tc.w0 + half_dw) * stride_w - pad_w, ah0 = (tc.h0 + half_dh) * stride_h - pad;
           for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&eb[st.stage], st.phase ^ 1);
+            mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
             tr.put(TR_TAG(l, kb, 3));
-            uint8_t* a_dst = smem + st.stage * kChainStageBytes;
+            uint8_t* a_dst = smem + ps.stage * kChainStageBytes;
             if (lane == 0) {
-              mbar_arrive_expect_tx(&fb[st.stage], tx_bytes);
-              if (mc) {
-                tma_load_4d_multicast(a_dst + half_smem, tmA, &fb[st.stage], kc * 64 + a_c0, aw0 + sx * dil, ah0 + r * dil, a_n,
-                                      kPairMask);
-              } else {
-                tma_load_4d(a_dst, tmA, &fb[st.stage], kc * 64 + a_c0, aw0 + sx * dil, ah0 + r * dil, a_n);
-              }
+              mbar_arrive_expect_tx(&full_bar[ps.stage], tx_bytes);
+              tma_load_4d(a_dst, tmA, &full_bar[ps.stage], kc * 64 + a_c0, tc.w0 * stride_w + sx * dil - pad_w,
+                          tc.h0 * stride_h + r * dil - pad, a_n);
             } else {
-              tma_load_3d(a_dst + kChainABytes, tmB, &fb[st.stage], kc * 64 + b_k0, b_n, tap);
+              tma_load_3d(a_dst + kChainABytes, tmB, &full_bar[ps.stage], kc * 64 + b_k0, b_n, tap);
             }
             if (++kc == k_chunks) {
               kc = 0;
@@ -449,9 +394,9 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
                 ++r;
               }
             }
-            if (++st.stage == kChainStages) {
-              st.stage = 0;
-              st.phase ^= 1;
+            if (++ps.stage == kChainStages) {
+              ps.stage = 0;
+              ps.phase ^= 1;
             }
           }
         }
@@ -460,7 +405,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      PipeState ps[2] = {{0, 0}, {0, 0}};
+      PipeState ps = {0, 0};
       int item = 0;
       TraceCursor tr = trace_cursor(trace, 1, cta);
       for (int l = 0; l < n_layers; ++l) {
@@ -468,16 +413,12 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         const ConvGemmParams p = L->p;
         const int BN = L->block_n;
         const int act = L->active_ctas;
-        const int mc = L->mc;
         if (cta >= act) continue;
         const uint32_t idesc = umma_idesc<0>(kBM, BN);
-        uint64_t* fb = full_bar + mc * kChainStages;
-        uint64_t* eb = empty_bar + mc * kChainStages;
-        PipeState& st = ps[mc];
-        WorkIter wi(p, cta, act);
-        McIter mi(p, L->pair_tiles, cluster, act / kClusterSize, rank);
-        int t, kb0, kb1;
-        while (mc ? mi.next(t, kb0, kb1) : wi.next(t, kb0, kb1)) {
+        WorkIter it(p, cta, act);
+        int t;
+        int kb0, kb1;
+        while (it.next(t, kb0, kb1)) {
           const int buf = item & 1;
           const uint32_t use = static_cast<uint32_t>(item >> 1);
           ++item;
@@ -485,19 +426,18 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * kChainAccStride;
           for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(&fb[st.stage], st.phase);
+            mbar_wait(&full_bar[ps.stage], ps.phase);
             tc_fence_after();
             tr.put(TR_TAG(l, kb, 7));
-            const uint32_t a_addr = smem_u32(smem + st.stage * kChainStageBytes);
+            const uint32_t a_addr = smem_u32(smem + ps.stage * kChainStageBytes);
             const uint64_t adesc = umma_desc_sw128(a_addr);
             const uint64_t bdesc = umma_desc_sw128(a_addr + kChainABytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            // the stage is free once these MMAs retire -- in multicast layers both CTAs of the pair are told
-            if (mc) umma_commit_multicast(&eb[st.stage], kPairMask); else umma_commit(&eb[st.stage]);
-            if (++st.stage == kChainStages) {
-              st.stage = 0;
-              st.phase ^= 1;
+            umma_commit(&empty_bar[ps.stage]);
+            if (++ps.stage == kChainStages) {
+              ps.stage = 0;
+              ps.phase ^= 1;
             }
           }
           umma_commit(&tmem_full_bar[buf]);
@@ -527,24 +467,12 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
       const ConvGemmParams p = L->p;
       const int act = L->active_ctas;
       if (cta < act) {
-        if (L->mc) {
-          McIter it(p, L->pair_tiles, cluster, act / kClusterSize, rank);
-          if (L->out16) {
-            chain_epilogue_layer<true>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
-                                       warp, lane, cta, act, item, rphase, tr, l, it);
-          } else {
-            chain_epilogue_layer<false>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
-                                        warp, lane, cta, act, item, rphase, tr, l, it);
-          }
+        if (L->out16) {
+          chain_epilogue_layer<true>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
+                                     warp, lane, cta, act, item, rphase, tr, l);
         } else {
-          WorkIter it(p, cta, act);
-          if (L->out16) {
-            chain_epilogue_layer<true>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
-                                       warp, lane, cta, act, item, rphase, tr, l, it);
-          } else {
-            chain_epilogue_layer<false>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
-                                        warp, lane, cta, act, item, rphase, tr, l, it);
-          }
+          chain_epilogue_layer<false>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
+                                      warp, lane, cta, act, item, rphase, tr, l);
         }
       }
       tr.put(TR_TAG(l, 0, 8));
@@ -574,7 +502,6 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
 
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();   // no CTA of the pair exits while the other may still multicast into it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kChainTmemCols);
@@ -584,38 +511,6 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
 // defined in conv_gemm.cu: validates a descriptor and encodes its tensor maps / kernel parameters
 int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA, CUtensorMap* tmB, CUtensorMap* tmOut,
                              CUtensorMap* tmRes, ConvGemmParams* p, int* ctas);
-int encode_a_tensormap(const mega_conv_gemm_desc* d, int box_tile_w, int box_tile_h, CUtensorMap* out);
-
-// CTAs of the chain kernel that can be co-resident as pairs (the kernel spins on a grid barrier, so the grid must fit)
-static int chain_max_grid() {
-  static int cached = 0;
-  if (cached) return cached;
-  if (cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem) != cudaSuccess) return 0;
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms > kMaxCtas) sms = kMaxCtas;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(static_cast<unsigned>(sms / kClusterSize * kClusterSize), 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
-  cfg.dynamicSmemBytes = kChainSmem;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kClusterSize;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&clusters, conv_chain_kernel, &cfg) != cudaSuccess || clusters <= 0) {
-    cudaGetLastError();
-    return 0;
-  }
-  int g = clusters * kClusterSize;
-  if (g > sms) g = sms / kClusterSize * kClusterSize;
-  cached = g;
-  return g;
-}
 
 }  // namespace mega
 
@@ -631,16 +526,7 @@ extern "C" int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_la
   MEGA_ARG_CHECK(plan_bytes >= mega_conv_chain_plan_bytes(n_layers), "conv_chain: plan buffer too small");
   MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(plan_host) & 127) == 0, "conv_chain: plan buffer must be 128-byte aligned");
   ChainLayer* out = static_cast<ChainLayer*>(plan_host);
-  const int grid_max = chain_max_grid();
-  MEGA_ARG_CHECK(grid_max >= kClusterSize, "conv_chain: the chain kernel does not fit this device (pairs of CTAs, %d B smem)",
-                 kChainSmem);
-  // Multicast pairs are OFF by default: measured with tools/trace_chain.py they do not shorten the k-block period
-  // (~600 cycles per 32 KB stage with or without): the limit is the SM's inbound fill rate (~64 B/clk), and a
-  // multicast half still lands in this SM's shared memory -- only L2 / crossbar requests drop. MEGA_B200_MULTICAST=1
-  // switches them on (bit-identical results).
-  const char* mc_env = getenv("MEGA_B200_MULTICAST");
-  const bool mc_allowed = (mc_env && mc_env[0] == '1');
-  int grid = kClusterSize;
+  int grid = 1;
   for (int l = 0; l < n_layers; ++l) {
     const mega_conv_gemm_desc* d = descs + l;
     MEGA_ARG_CHECK(d->precision == kModeF16, "conv_chain: layer %d: chains run fp16 operands only", l);
@@ -652,36 +538,10 @@ extern "C" int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_la
     if (rc != MEGA_OK) return rc;
     L->block_n = d->block_n;
     L->out16 = d->out_f16 ? 1 : 0;
-    if (ctas > grid_max) ctas = grid_max;
-    if (d->max_ctas > 0 && ctas > d->max_ctas) ctas = d->max_ctas;
     L->active_ctas = ctas;
     L->reserved = 0;
-    L->tmAh = L->tmA;
-    L->mc = 0;
-    L->half_w = 0;
-    L->half_off = 0;
-    L->pair_tiles = 0;
-    // multicast pairs: whole tiles, an even number of N tiles, and a tile that splits into two 64-pixel halves
-    const bool split_h = (d->tile_h % 2) == 0;
-    const bool split_w = d->tile_h == 1 && (d->tile_w % 2) == 0;
-    if (mc_allowed && !L->p.stream_k && (L->p.n_tiles % 2) == 0 && (split_h || split_w)) {
-      const int hw = split_h ? d->tile_w : d->tile_w / 2, hh = split_h ? d->tile_h / 2 : d->tile_h;
-      const int rc2 = encode_a_tensormap(d, hw, hh, &L->tmAh);
-      if (rc2 != MEGA_OK) return rc2;
-      L->mc = 1;
-      L->half_w = split_h ? 0 : 1;
-      L->half_off = split_h ? d->tile_h / 2 : d->tile_w / 2;
-      L->pair_tiles = static_cast<int>(L->p.total_tiles / 2);
-      int limit = grid_max;
-      if (d->max_ctas > 0 && limit > d->max_ctas) limit = d->max_ctas;
-      int clusters = limit / kClusterSize;
-      if (clusters > L->pair_tiles) clusters = L->pair_tiles;
-      L->active_ctas = clusters * kClusterSize;
-    }
-    if (L->active_ctas > grid) grid = L->active_ctas;
+    if (ctas > grid) grid = ctas;
   }
-  grid = (grid + kClusterSize - 1) / kClusterSize * kClusterSize;
-  if (grid > grid_max) grid = grid_max;
   if (grid_out) *grid_out = grid;
   return MEGA_OK;
 }
@@ -699,9 +559,8 @@ extern "C" int mega_conv_chain_set_trace(void* trace_dev, int cta) {
 extern "C" int mega_conv_chain_launch(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream_v,
                                       int pdl) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  MEGA_ARG_CHECK(plan_device != nullptr && sync_words != nullptr && n_layers > 0 && grid > 0 && grid <= kMaxCtas &&
-                     (grid % kClusterSize) == 0,
-                 "conv_chain_launch: bad arguments (grid %d must be a multiple of %d)", grid, kClusterSize);
+  MEGA_ARG_CHECK(plan_device != nullptr && sync_words != nullptr && n_layers > 0 && grid > 0 && grid <= kMaxCtas,
+                 "conv_chain_launch: bad arguments (grid %d)", grid);
   MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(plan_device) & 127) == 0, "conv_chain_launch: plan must be 128-byte aligned");
   static bool configured = false;
   if (!configured) {
@@ -713,15 +572,11 @@ extern "C" int mega_conv_chain_launch(const void* plan_device, int n_layers, int
   cfg.blockDim = dim3(kThreads, 1, 1);
   cfg.dynamicSmemBytes = kChainSmem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kClusterSize;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 2 : 1;
+  cfg.numAttrs = pdl ? 1 : 0;
   MEGA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_chain_kernel, static_cast<const ChainLayer*>(plan_device), n_layers,
                                      static_cast<unsigned*>(sync_words), g_chain_trace));
   return MEGA_OK;

@@ -61,41 +61,6 @@ extern "C" int mega_set_tf32_rounding(int enable) {
 
 namespace mega {
 
-// tensor map of the A operand for a (box_tile_h x box_tile_w)-pixel rectangle of output positions (the whole tile, or
-// one half of it for the multicast pairs of conv_chain.cu)
-int encode_a_tensormap(const mega_conv_gemm_desc* d, int box_tile_w, int box_tile_h, CUtensorMap* out) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) {
-    mega_set_error("conv_gemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-    return MEGA_ERR_CUDA;
-  }
-  const bool strict = d->precision == kModeSplit3;
-  const bool f16 = d->precision == kModeF16;
-  const int esz = f16 ? 2 : 4;
-  const int bk = mode_bk(d->precision);
-  const int stride_h = d->stride_h > 0 ? d->stride_h : 1, stride_w = d->stride_w > 0 ? d->stride_w : 1;
-  const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
-                                     : (g_tf32_round && !strict) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
-                                                                 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->a_c), static_cast<cuuint64_t>(d->a_w),
-                        static_cast<cuuint64_t>(d->a_h), static_cast<cuuint64_t>(d->a_n)};
-  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->a_stride_w) * esz, static_cast<cuuint64_t>(d->a_stride_h) * esz,
-                        static_cast<cuuint64_t>(d->a_stride_n) * esz};
-  // a strided convolution samples every stride-th pixel of the rectangle: TMA element strides (the box is the
-  // bounding rectangle, the copy delivers box_tile_w x box_tile_h pixels)
-  cuuint32_t box[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>((box_tile_w - 1) * stride_w + 1),
-                       static_cast<cuuint32_t>((box_tile_h - 1) * stride_h + 1), 1};
-  cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride_w), static_cast<cuuint32_t>(stride_h), 1};
-  CUresult r = enc(out, dt, 4, const_cast<void*>(d->a), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    mega_set_error("conv_gemm: encode A tensor map failed (CUresult %d) dims %d %d %d %d strides %lld %lld %lld",
-                   static_cast<int>(r), d->a_c, d->a_w, d->a_h, d->a_n, d->a_stride_w, d->a_stride_h, d->a_stride_n);
-    return MEGA_ERR_CUDA;
-  }
-  return MEGA_OK;
-}
-
 // validates a descriptor, encodes its four tensor maps and fills the kernel parameters; *ctas = CTAs of the
 // persistent work list (shared by the single-launch path below and the layer chains of conv_chain.cu)
 int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, CUtensorMap* tmB_p, CUtensorMap* tmOut_p,
@@ -154,8 +119,24 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   CUtensorMap& tmA = *tmA_p;
   CUtensorMap& tmB = *tmB_p;
   {
-    const int rc_a = encode_a_tensormap(d, d->tile_w, d->tile_h, &tmA);
-    if (rc_a != MEGA_OK) return rc_a;
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->a_c), static_cast<cuuint64_t>(d->a_w),
+                          static_cast<cuuint64_t>(d->a_h), static_cast<cuuint64_t>(d->a_n)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->a_stride_w) * esz, static_cast<cuuint64_t>(d->a_stride_h) * esz,
+                          static_cast<cuuint64_t>(d->a_stride_n) * esz};
+    // a strided convolution samples every stride-th pixel of the rectangle: TMA element strides (the box is the
+    // bounding rectangle, the copy delivers tile_w x tile_h pixels)
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>((d->tile_w - 1) * stride_w + 1),
+                         static_cast<cuuint32_t>((d->tile_h - 1) * stride_h + 1), 1};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(stride_w), static_cast<cuuint32_t>(stride_h), 1};
+    CUresult r = enc(&tmA, dt, 4, const_cast<void*>(d->a), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      mega_set_error("conv_gemm: encode A tensor map failed (CUresult %d) dims %d %d %d %d strides %lld %lld %lld",
+                     static_cast<int>(r), d->a_c, d->a_w, d->a_h, d->a_n, d->a_stride_w, d->a_stride_h,
+                     d->a_stride_n);
+      return MEGA_ERR_CUDA;
+    }
   }
   {
     const int taps = d->taps_r * d->taps_s;

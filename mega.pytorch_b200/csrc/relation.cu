@@ -9,6 +9,7 @@
 // registers and the soft-max is taken in place over the [G,N,M] logits produced by the
 // tcgen05 Q.K^T GEMM. One CTA per query row; two passes over its [16,M] slice (L2-resident):
 // logits + online (max, sum), then normalise.
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "mega_b200.h"
@@ -321,6 +322,203 @@ relation_softmax_pe_kernel(const __grid_constant__ RelParamsW pw) {
   }
 }
 
+// ---- the position bias as a tensor-core product. bias[m, g] = sum_e emb[m, e] * Wg[g, e] is a [keys x 64] x [64 x 16]
+// GEMM per query row: 1024 FFMAs per (query, key) pair on the SIMT pipe, but 3 x 32 warp-level m16n8k8 MMAs per 32 pairs
+// on the tensor cores. To keep fp32-level accuracy (the bias feeds log(relu(.) + 1e-6)) both operands are split
+// x = hi + lo with hi = x truncated to TF32 (exactly representable) and the product is hi*hi + hi*lo + lo*hi with fp32
+// accumulation ("3xTF32", relative error ~1e-6). Each thread computes exactly the sin / cos values of its own A
+// fragment slots (pairs g, g+8 x frequencies t, t+4 of the lane = 4g + t), so nothing is transposed through memory.
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+constexpr int kWgPitch = 24;   // floats per feature row of the smem weight tables (conflict-free B-fragment reads)
+
+template <bool SMEM_STAGE>
+__global__ void __launch_bounds__(kRelThreads)
+relation_softmax_mma_kernel(const __grid_constant__ RelParamsW pw) {
+  const RelParams& p = pw.b;
+  extern __shared__ float stage_s[];   // [16][ldm] when SMEM_STAGE
+  __shared__ uint32_t wg_hi[kEmb * kWgPitch], wg_lo[kEmb * kWgPitch];
+  __shared__ float red_max[kRelThreads / 32][kGroups];
+  __shared__ float red_sum[kRelThreads / 32][kGroups];
+  __shared__ float fin_max[kGroups], fin_inv[kGroups];
+
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int m_valid = p.m_valid_ptr ? min(*p.m_valid_ptr, p.ldm) : p.m_host;
+  if (p.n_valid_ptr) {
+    const int nv = *p.n_valid_ptr;
+    if (n >= nv && n < p.n_valid_off) return;
+  }
+  for (int i = tid; i < kEmb * kGroups; i += kRelThreads) {
+    const int e = i / kGroups, h = i - e * kGroups;
+    uint32_t hi, lo;
+    split_tf32(pw.wg[e * kGroups + h], hi, lo);
+    wg_hi[e * kWgPitch + h] = hi;
+    wg_lo[e * kWgPitch + h] = lo;
+  }
+  __syncthreads();
+  const float4 q = *reinterpret_cast<const float4*>(p.boxes_q + static_cast<long long>(n) * 4);
+  const float qw = __fadd_rn(__fsub_rn(q.z, q.x), 1.f);
+  const float qh = __fadd_rn(__fsub_rn(q.w, q.y), 1.f);
+  const float qcx = __fmul_rn(0.5f, __fadd_rn(q.x, q.z));
+  const float qcy = __fmul_rn(0.5f, __fadd_rn(q.y, q.w));
+  float* srow = p.s + static_cast<long long>(n) * p.ldm;
+  // this lane's two frequencies (k columns t and t + 4 of every 8-wide k-step)
+  const float dimA = pw.dim[t], invA = pw.inv_dim[t], dimB = pw.dim[t + 4], invB = pw.inv_dim[t + 4];
+  // this lane's four heads: columns 2t, 2t+1 of the two n-tiles
+  const int hd[4] = {2 * t, 2 * t + 1, 8 + 2 * t, 9 + 2 * t};
+  float bgv[4], mx[4], sm[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bgv[j] = pw.bg[hd[j]];
+    mx[j] = -INFINITY;
+    sm[j] = 0.f;
+  }
+
+  for (int m0 = warp * 32; m0 < m_valid; m0 += (kRelThreads / 32) * 32) {
+    // ---- lane L: the four 100 x log-ratios of key m0 + L
+    const int mk = min(m0 + lane, m_valid - 1);
+    const float4 k = *reinterpret_cast<const float4*>(p.boxes_k + static_cast<long long>(mk) * 4);
+    const float kw = __fadd_rn(__fsub_rn(k.z, k.x), 1.f);
+    const float kh = __fadd_rn(__fsub_rn(k.w, k.y), 1.f);
+    const float kcx = __fmul_rn(0.5f, __fadd_rn(k.x, k.z));
+    const float kcy = __fmul_rn(0.5f, __fadd_rn(k.y, k.w));
+    float d100[4];
+    d100[0] = __fmul_rn(logf(__fadd_rn(fabsf(__fdiv_rn(__fsub_rn(qcx, kcx), qw)), 1e-3f)), 100.0f);
+    d100[1] = __fmul_rn(logf(__fadd_rn(fabsf(__fdiv_rn(__fsub_rn(qcy, kcy), qh)), 1e-3f)), 100.0f);
+    d100[2] = __fmul_rn(logf(__fdiv_rn(qw, kw)), 100.0f);
+    d100[3] = __fmul_rn(logf(__fdiv_rn(qh, kh)), 100.0f);
+    // the 16 logits of this lane's C-fragment slots, issued before the arithmetic so their latency is covered
+    float lg[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int m = min(m0 + mt * 16 + g + half * 8, m_valid - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) lg[mt][half][j] = srow[hd[j] * p.head_stride + m];
+      }
+    float acc[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // A-fragment slots of this lane: rows (pairs) g, g + 8 of the m-tile; k columns (frequencies) t, t + 4
+        const float dlo = __shfl_sync(0xffffffffu, d100[c], mt * 16 + g);
+        const float dhi = __shfl_sync(0xffffffffu, d100[c], mt * 16 + g + 8);
+        float sv[4], cv[4];
+#pragma unroll
+        for (int slot = 0; slot < 4; ++slot) {
+          const float d = (slot & 1) ? dhi : dlo;                 // a0/a2: row g, a1/a3: row g + 8
+          const float dm = (slot & 2) ? dimB : dimA, iv = (slot & 2) ? invB : invA;   // a0/a1: col t, a2/a3: col t + 4
+          const float q0 = __fmul_rn(d, iv);
+          const float rem = __fmaf_rn(-q0, dm, d);
+          const float arg = __fmaf_rn(rem, iv, q0);
+          const float kq = rintf(arg * 0.15915494309189535f);
+          float r = fmaf(-kq, 6.28125f, arg);
+          r = fmaf(-kq, 1.9353071795864769e-3f, r);
+          sv[slot] = __sinf(r);
+          cv[slot] = __cosf(r);
+        }
+#pragma unroll
+        for (int sc = 0; sc < 2; ++sc) {            // k-step 2c: the sin block of coordinate c, 2c + 1: the cos block
+          uint32_t ahi[4], alo[4];
+#pragma unroll
+          for (int slot = 0; slot < 4; ++slot) split_tf32(sc ? cv[slot] : sv[slot], ahi[slot], alo[slot]);
+          const int e0 = (2 * c + sc) * 8;          // first feature of this k-step
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const int o0 = (e0 + t) * kWgPitch + nt * 8 + g, o1 = (e0 + t + 4) * kWgPitch + nt * 8 + g;
+            const uint32_t bh0 = wg_hi[o0], bh1 = wg_hi[o1], bl0 = wg_lo[o0], bl1 = wg_lo[o1];
+            mma_tf32_16x8x8(acc[mt][nt], alo, bh0, bh1);
+            mma_tf32_16x8x8(acc[mt][nt], ahi, bl0, bl1);
+            mma_tf32_16x8x8(acc[mt][nt], ahi, bh0, bh1);
+          }
+        }
+      }
+    }
+    // ---- C fragments: (pair g | g + 8 of m-tile mt) x (heads 2t, 2t+1 of n-tile nt)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int m = m0 + mt * 16 + g + half * 8;
+        if (m < m_valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float bsum = acc[mt][j >> 1][half * 2 + (j & 1)] + bgv[j];
+            const float b = __logf(__fadd_rn(fmaxf(bsum, 0.f), 1e-6f));
+            const float l = __fadd_rn(b, __fmul_rn(p.scale, lg[mt][half][j]));
+            if (SMEM_STAGE) stage_s[hd[j] * p.ldm + m] = l; else srow[hd[j] * p.head_stride + m] = l;
+            const float d = l - mx[j];
+            const float e = __expf(-fabsf(d));
+            sm[j] = (d > 0.f) ? fmaf(sm[j], e, 1.f) : (sm[j] + e);
+            mx[j] = fmaxf(mx[j], l);
+          }
+        }
+      }
+    }
+  }
+
+  // ---- (max, sum) per head: lanes with the same t (8 lanes: xor 4, 8, 16), then across warps
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float m_ = mx[j], s_ = sm[j];
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m_, off);
+      const float os = __shfl_xor_sync(0xffffffffu, s_, off);
+      const float nm = fmaxf(m_, om);
+      const float a = (m_ == -INFINITY) ? 0.f : s_ * __expf(m_ - nm);
+      const float b = (om == -INFINITY) ? 0.f : os * __expf(om - nm);
+      s_ = a + b;
+      m_ = nm;
+    }
+    if (g == 0) {
+      red_max[warp][hd[j]] = m_;
+      red_sum[warp][hd[j]] = s_;
+    }
+  }
+  __syncthreads();
+  if (tid < kGroups) {
+    float m_ = -INFINITY;
+    for (int w = 0; w < kRelThreads / 32; ++w) m_ = fmaxf(m_, red_max[w][tid]);
+    float s_ = 0.f;
+    for (int w = 0; w < kRelThreads / 32; ++w)
+      if (red_max[w][tid] != -INFINITY) s_ += red_sum[w][tid] * __expf(red_max[w][tid] - m_);
+    fin_max[tid] = m_;
+    fin_inv[tid] = 1.0f / s_;
+  }
+  __syncthreads();
+  for (int m = tid; m < p.ldm; m += kRelThreads) {
+#pragma unroll
+    for (int h = 0; h < kGroups; ++h) {
+      float* sp = srow + h * p.head_stride + m;
+      const float l = SMEM_STAGE ? stage_s[h * p.ldm + (m < m_valid ? m : 0)] : *sp;
+      const float pr = (m < m_valid) ? __expf(l - fin_max[h]) * fin_inv[h] : 0.f;
+      if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + h * p.head_stride + m] = __float2half_rn(pr);
+      else *sp = pr;
+    }
+  }
+}
+
 // No position term: one warp per (head, query row); the row (<= 1024 keys) stays in registers, so the
 // logits are read once and the probabilities written once.
 __global__ void __launch_bounds__(256)
@@ -464,17 +662,29 @@ extern "C" int mega_relation_softmax_pe(float* logits, void* probs_f16, int n_ro
     pw.dim[k] = dim_mat_host[k];
     pw.inv_dim[k] = 1.0f / dim_mat_host[k];
   }
-  if (ldm <= 1024) {
-    const int smem = kGroups * ldm * static_cast<int>(sizeof(float));
-    static bool configured = false;
-    if (!configured) {
-      MEGA_CUDA_CHECK(cudaFuncSetAttribute(relation_softmax_pe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kGroups * 1024 * static_cast<int>(sizeof(float))));
-      configured = true;
-    }
-    relation_softmax_pe_kernel<true><<<n_rows, kRelThreads, smem, stream>>>(pw);
+  static int use_mma = -1;
+  if (use_mma < 0) {
+    const char* e = getenv("MEGA_B200_SOFTMAX_SIMT");
+    use_mma = (e && e[0] == '1') ? 0 : 1;
+  }
+  static bool configured = false;
+  if (!configured) {
+    MEGA_CUDA_CHECK(cudaFuncSetAttribute(relation_softmax_pe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kGroups * 1024 * static_cast<int>(sizeof(float))));
+    MEGA_CUDA_CHECK(cudaFuncSetAttribute(relation_softmax_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kGroups * 1024 * static_cast<int>(sizeof(float))));
+    configured = true;
+  }
+  const int smem = kGroups * ldm * static_cast<int>(sizeof(float));
+  // measured (B200, 675 query rows): keys <= 1024 (logits staged in smem) 60 us with the tensor-core bias vs 70 us
+  // with FFMAs; 3750 keys (two passes over 163 MB of fp32 logits in global memory: bandwidth-bound) 250 vs 242 us
+  if (use_mma && ldm <= 1024) {
+    relation_softmax_mma_kernel<true><<<n_rows, kRelThreads, smem, stream>>>(pw);
+  } else if (use_mma > 1) {
+    relation_softmax_mma_kernel<false><<<n_rows, kRelThreads, 0, stream>>>(pw);
   } else {
-    relation_softmax_pe_kernel<false><<<n_rows, kRelThreads, 0, stream>>>(pw);
+    if (ldm <= 1024) relation_softmax_pe_kernel<true><<<n_rows, kRelThreads, smem, stream>>>(pw);
+    else relation_softmax_pe_kernel<false><<<n_rows, kRelThreads, 0, stream>>>(pw);
   }
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
