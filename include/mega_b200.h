@@ -185,6 +185,19 @@ int mega_gather_rows(const float* src, long long src_ld, const int* idx, int n_r
  * zeros, negative destination index -> skipped): ring-buffer pushes of the window and the long-range memory. */
 int mega_copy_rows(const float* src, long long src_ld, const int* src_idx, float* dst, long long dst_ld,
                    const int* dst_idx, int n_rows, int row_len, void* stream);
+/* up to 16 independent mega_copy_rows jobs in one launch (rows of 32-bit words; the job table is a HOST array, it
+ * travels in the kernel parameters). */
+typedef struct mega_copy_job {
+  const void* src;
+  long long src_ld;
+  const int* src_idx;
+  void* dst;
+  long long dst_ld;
+  const int* dst_idx;
+  int n_rows;
+  int row_len;
+} mega_copy_job;
+int mega_copy_rows_batch(const mega_copy_job* jobs_host, int n_jobs, void* stream);
 /* per image [rows, cols] -> [cols, rows] (NCHW <-> NHWC at the module boundary). */
 int mega_transpose_2d(const float* input, int n_img, int rows, int cols, float* out, void* stream);
 

@@ -208,6 +208,45 @@ __global__ void stem_prep_kernel(const float* __restrict__ in, int n_img, int he
   }
 }
 
+// several independent row copies in ONE launch (blockIdx.y = job): the window / memory plumbing of a frame is a dozen
+// tiny gathers whose launch gaps cost more than the bytes they move
+constexpr int kMaxCopyJobs = 16;
+struct CopyJobs {
+  mega_copy_job j[kMaxCopyJobs];
+};
+
+__global__ void copy_rows_batch_kernel(const __grid_constant__ CopyJobs jobs) {
+  const mega_copy_job& jb = jobs.j[blockIdx.y];
+  const float* src = static_cast<const float*>(jb.src);
+  float* dst = static_cast<float*>(jb.dst);
+  const bool vec = !((jb.row_len & 3) || (jb.src_ld & 3) || (jb.dst_ld & 3) || (reinterpret_cast<uintptr_t>(src) & 15) ||
+                     (reinterpret_cast<uintptr_t>(dst) & 15));
+  if (vec) {
+    const int nv = jb.row_len / 4;
+    const long long total = static_cast<long long>(jb.n_rows) * nv;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int r = static_cast<int>(i / nv), c = static_cast<int>(i - static_cast<long long>(r) * nv);
+      const int s = jb.src_idx ? jb.src_idx[r] : r;
+      const int d = jb.dst_idx ? jb.dst_idx[r] : r;
+      if (d < 0) continue;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (s >= 0) v = ldg_f4(src + static_cast<long long>(s) * jb.src_ld + c * 4);
+      *reinterpret_cast<float4*>(dst + static_cast<long long>(d) * jb.dst_ld + c * 4) = v;
+    }
+  } else {
+    const long long total = static_cast<long long>(jb.n_rows) * jb.row_len;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int r = static_cast<int>(i / jb.row_len), c = static_cast<int>(i - static_cast<long long>(r) * jb.row_len);
+      const int s = jb.src_idx ? jb.src_idx[r] : r;
+      const int d = jb.dst_idx ? jb.dst_idx[r] : r;
+      if (d < 0) continue;
+      dst[static_cast<long long>(d) * jb.dst_ld + c] = (s >= 0) ? src[static_cast<long long>(s) * jb.src_ld + c] : 0.f;
+    }
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long b = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -318,6 +357,24 @@ extern "C" int mega_transpose_2d(const float* input, int n_img, int rows, int co
   if (n_img == 0 || rows == 0 || cols == 0) return MEGA_OK;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, n_img), block(32, 8);
   transpose_kernel<<<grid, block, 0, stream>>>(input, rows, cols, out);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_copy_rows_batch(const mega_copy_job* jobs_host, int n_jobs, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(jobs_host != nullptr && n_jobs >= 0 && n_jobs <= kMaxCopyJobs, "copy_rows_batch: at most %d jobs", kMaxCopyJobs);
+  if (n_jobs == 0) return MEGA_OK;
+  CopyJobs jobs;
+  long long most = 1;
+  for (int i = 0; i < n_jobs; ++i) {
+    jobs.j[i] = jobs_host[i];
+    const long long words = static_cast<long long>(jobs_host[i].n_rows) * jobs_host[i].row_len;
+    if (words / 4 > most) most = words / 4;
+  }
+  for (int i = n_jobs; i < kMaxCopyJobs; ++i) jobs.j[i] = jobs_host[0];
+  dim3 grid(grid_for(most, 256) > 148 ? 148 : grid_for(most, 256), n_jobs);
+  copy_rows_batch_kernel<<<grid, 256, 0, stream>>>(jobs);
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }

@@ -149,6 +149,15 @@ lib.mega_gather_rows.argtypes = [_vp, _ll, _vp, _i, _i, _vp, _ll, _vp]
 lib.mega_gather_rows.restype = _i
 lib.mega_copy_rows.argtypes = [_vp, _ll, _vp, _vp, _ll, _vp, _i, _i, _vp]
 lib.mega_copy_rows.restype = _i
+class CopyJob(ctypes.Structure):
+    """mirror of `mega_copy_job`"""
+    _fields_ = [("src", ctypes.c_void_p), ("src_ld", ctypes.c_longlong), ("src_idx", ctypes.c_void_p),
+                ("dst", ctypes.c_void_p), ("dst_ld", ctypes.c_longlong), ("dst_idx", ctypes.c_void_p),
+                ("n_rows", ctypes.c_int), ("row_len", ctypes.c_int)]
+
+
+lib.mega_copy_rows_batch.argtypes = [ctypes.POINTER(CopyJob), _i, _vp]
+lib.mega_copy_rows_batch.restype = _i
 lib.mega_transpose_2d.argtypes = [_vp, _i, _i, _i, _vp, _vp]
 lib.mega_transpose_2d.restype = _i
 lib.mega_relation_softmax.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp]
@@ -174,7 +183,7 @@ EXPORTS = [
     "mega_conv_chain_plan_bytes", "mega_conv_chain_encode", "mega_conv_chain_launch", "mega_conv_chain_set_trace",
     "mega_nms_workspace_bytes", "mega_nms", "mega_rpn_select_workspace_bytes", "mega_rpn_select",
     "mega_roi_align_forward_nchw", "mega_roi_align_forward_nhwc", "mega_stem_im2col", "mega_maxpool3x3s2_nhwc",
-    "mega_gather_rows", "mega_copy_rows", "mega_transpose_2d", "mega_relation_softmax", "mega_box_postprocess_workspace_bytes",
+    "mega_gather_rows", "mega_copy_rows", "mega_copy_rows_batch", "mega_transpose_2d", "mega_relation_softmax", "mega_box_postprocess_workspace_bytes",
     "mega_box_postprocess", "mega_sigmoid_focalloss_forward", "mega_sigmoid_focalloss_backward",
     "mega_deform_im2col", "mega_deform_psroi_pooling_forward",
     "mega_roi_align_forward_nhwc_f16", "mega_stem_im2col_f16", "mega_maxpool3x3s2_nhwc_f16", "mega_relation_softmax_f16", "mega_relation_softmax_pe",

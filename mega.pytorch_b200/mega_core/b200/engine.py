@@ -421,11 +421,16 @@ class HeadCommon:
         feat_range = torch.arange(0, 8, dtype=torch.float32)
         self.dim_mat = torch.full((8,), 1000.0).pow(8.0 / 64 * feat_range).to(dev)   # extractors :129-130
 
-    def predict_and_postprocess(self, x, proposals, count, im_w, im_h):
+    def predict_gemm(self, x):
+        """FPNPredictor (roi_box_predictors.py:50-57): class logits and box deltas as one GEMM, fp32 output"""
+        pred = self._buf("pred", (x.shape[0], self.pred_ld))
+        ops.linear(x, self.pred_w, pred, bias=self.pred_b)
+        return pred
+
+    def predict_and_postprocess(self, x, proposals, count, im_w, im_h, gemm_done=False):
         c = self.cfg
         r = proposals.shape[0]
-        pred = self._buf("pred", (r, self.pred_ld))
-        ops.linear(x, self.pred_w, pred, bias=self.pred_b)
+        pred = self._buf("pred", (r, self.pred_ld)) if gemm_done else self.predict_gemm(x)
         ncls = self.num_classes
         cap = (ncls - 1) * r
         out = (self._buf("det_boxes", (cap, 4)), self._buf("det_scores", (cap,)),
@@ -772,10 +777,11 @@ class MegaEngine(WindowedEngine):
         x, boxes, cnt, spans = self.ref_branch(imgs, ["L", "G"], im_w, im_h)
         (ol, rl), (og, rg) = spans
         px, pb, pc, pg = self._payload_views(payload)
-        ops.copy_rows(x[ol:ol + rl], px, KP)
-        ops.copy_rows(boxes[0], pb, KP)
-        ops.copy_rows(cnt[0:1].view(torch.float32).view(1, 1), pc, 1, row_len=1)   # raw 32-bit count
-        ops.copy_rows(x[og:og + rg], pg, R)
+        with ops.copy_batch():
+            ops.copy_rows(x[ol:ol + rl], px, KP)
+            ops.copy_rows(boxes[0], pb, KP)
+            ops.copy_rows(cnt[0:1].view(torch.float32).view(1, 1), pc, 1, row_len=1)   # raw 32-bit count
+            ops.copy_rows(x[og:og + rg], pg, R)
         return payload
 
     def _ingest(self, im_w, im_h):
@@ -783,10 +789,11 @@ class MegaEngine(WindowedEngine):
         frame-dependent address comes from `tab_d`)"""
         KP, R = self.KP, self.R
         px, pb, pc, pg = self._payload_views(self.payload_in)
-        ops.copy_rows(px, self.win_x, KP, dst_idx=self._tab("dst_local"))
-        ops.copy_rows(pb, self.win_boxes, KP, dst_idx=self._tab("dst_local"))
-        ops.copy_rows(pc[:, :1], self.win_cnt.view(torch.float32), 1, row_len=1, dst_idx=self._tab("slot_new")[:1])
-        ops.copy_rows(pg, self.glob_x, R, dst_idx=self._tab("dst_glob"))
+        with ops.copy_batch():
+            ops.copy_rows(px, self.win_x, KP, dst_idx=self._tab("dst_local"))
+            ops.copy_rows(pb, self.win_boxes, KP, dst_idx=self._tab("dst_local"))
+            ops.copy_rows(pc[:, :1], self.win_cnt.view(torch.float32), 1, row_len=1, dst_idx=self._tab("slot_new")[:1])
+            ops.copy_rows(pg, self.glob_x, R, dst_idx=self._tab("dst_glob"))
         return self.aggregate(im_w, im_h, new_local=True)
 
     def _steady_frame(self, imgs, im_w, im_h):
@@ -801,14 +808,15 @@ class MegaEngine(WindowedEngine):
         t = self._tab
         nl0, nl12, nq = self.nl0, self.nl12, self.nq
         # window assembly (replaces the torch.cat of the deques, generalized_rcnn_mega.py:213-216)
-        ops.gather_rows(self.win_x, t("idx_e0"), self.E0, KP + nl0)
-        ops.gather_rows(self.win_boxes, t("idx_e0"), self.B0, KP + nl0)
-        ops.gather_rows(self.win_boxes, t("idx_e0")[:KP], self.Bq0, KP)
-        ops.gather_rows(self.win_boxes, t("idx_dis"), self.Bq0[KP:], nl12)
-        ops.gather_rows(self.win_boxes, t("idx_dis"), self.B1, nl12)
-        ops.gather_rows(self.win_boxes, t("idx_dis"), self.B2, nl12)
-        ops.gather_rows(self.win_cnt.view(torch.float32), t("slot_key")[:1], self.cur_cnt.view(torch.float32), 1,
-                        row_len=1)
+        with ops.copy_batch():
+            ops.gather_rows(self.win_x, t("idx_e0"), self.E0, KP + nl0)
+            ops.gather_rows(self.win_boxes, t("idx_e0"), self.B0, KP + nl0)
+            ops.gather_rows(self.win_boxes, t("idx_e0")[:KP], self.Bq0, KP)
+            ops.gather_rows(self.win_boxes, t("idx_dis"), self.Bq0[KP:], nl12)
+            ops.gather_rows(self.win_boxes, t("idx_dis"), self.B1, nl12)
+            ops.gather_rows(self.win_boxes, t("idx_dis"), self.B2, nl12)
+            ops.gather_rows(self.win_cnt.view(torch.float32), t("slot_key")[:1], self.cur_cnt.view(torch.float32), 1,
+                            row_len=1)
         kcnt = self.cur_cnt.view(-1)[:1]
         mv = t("mvalid")
         # G0: global aggregation of key / ref rows (update_lm index 0, extractors :757-760, :690-699)
@@ -821,22 +829,26 @@ class MegaEngine(WindowedEngine):
                         boxes_q=self.Bq0, boxes_k=self.B0[KP:], m_valid=mv[0:1], n_valid=kcnt, n_valid_off=KP,
                         tail=lambda: ops.linear(self.X1, self.fc_w[1], self.Y1E[:nq], bias=self.fc_b[1], relu=True))
         # update_memory(0): the oldest local frame's 75 enhanced rows (extractors :678-688)
-        ops.copy_rows(self.E0[KP:KP + R], self.E0, R, dst_idx=t("dst_mem0"))
-        ops.copy_rows(self.B0[KP:KP + R], self.B0, R, dst_idx=t("dst_mem0"))
+        with ops.copy_batch():
+            ops.copy_rows(self.E0[KP:KP + R], self.E0, R, dst_idx=t("dst_mem0"))
+            ops.copy_rows(self.B0[KP:KP + R], self.B0, R, dst_idx=t("dst_mem0"))
         # stage 1
         self._attention(self.att_l[1], self.Y1E[:nq], nq, self.Y1E[KP:], nl12 + self.mem_cap12, self.ld_12, self.X2,
                         boxes_q=self.Bq0, boxes_k=self.B1, m_valid=mv[1:2], n_valid=kcnt, n_valid_off=KP,
                         tail=lambda: ops.linear(self.X2, self.fc_w[2], self.Y2M[:nq], bias=self.fc_b[2], relu=True))
-        ops.copy_rows(self.Y1E[KP:KP + A], self.Y1E, A, dst_idx=t("dst_mem12"))
-        ops.copy_rows(self.B1[:A], self.B1, A, dst_idx=t("dst_memb12"))
+        with ops.copy_batch():
+            ops.copy_rows(self.Y1E[KP:KP + A], self.Y1E, A, dst_idx=t("dst_mem12"))
+            ops.copy_rows(self.B1[:A], self.B1, A, dst_idx=t("dst_memb12"))
         # stage 2 (key rows only)
         self._attention(self.att_l[2], self.Y2M[:KP], KP, self.Y2M[KP:], nl12 + self.mem_cap12, self.ld_12, self.X3,
                         boxes_q=self.Bq0[:KP], boxes_k=self.B2, m_valid=mv[2:3])
-        ops.copy_rows(self.Y2M[KP:KP + A], self.Y2M, A, dst_idx=t("dst_mem12"))
-        ops.copy_rows(self.B2[:A], self.B2, A, dst_idx=t("dst_memb12"))
+        with ops.copy_batch():
+            ops.copy_rows(self.Y2M[KP:KP + A], self.Y2M, A, dst_idx=t("dst_mem12"))
+            ops.copy_rows(self.B2[:A], self.B2, A, dst_idx=t("dst_memb12"))
         # G1: update_lm(x, 1) (extractors :930-931)
-        self._attention(self.att_g[1], self.X3, KP, self.glob_x, self.GF * R, self.ld_g, self.X4)
-        return self.predict_and_postprocess(self.X4, self.Bq0[:KP], kcnt, im_w, im_h)
+        self._attention(self.att_g[1], self.X3, KP, self.glob_x, self.GF * R, self.ld_g, self.X4,
+                        tail=lambda: self.predict_gemm(self.X4))       # the predictor rides in the last P.V' chain
+        return self.predict_and_postprocess(self.X4, self.Bq0[:KP], kcnt, im_w, im_h, gemm_done=True)
 
 
 class RdnEngine(WindowedEngine):

@@ -558,6 +558,9 @@ def gather_rows(src, idx, dst, n_rows=None, row_len=None):
         src, dst = _as_f32_rows(src), _as_f32_rows(dst)
     n_rows = idx.numel() if n_rows is None else n_rows
     row_len = src.shape[-1] if row_len is None else row_len
+    if copy_batch.active[0] is not None:
+        copy_batch.active[0].append(_copy_job(src, idx, dst, None, n_rows, row_len))
+        return dst
     check(lib.mega_gather_rows(ptr(src), src.stride(-2), ptr(idx), n_rows, row_len, ptr(dst), dst.stride(-2),
                                stream_ptr()), "mega_gather_rows")
     LAUNCHES[0] += 1
@@ -572,10 +575,42 @@ def copy_rows(src, dst, n_rows, row_len=None, src_idx=None, dst_idx=None):
         assert row_len is None
         src, dst = _as_f32_rows(src), _as_f32_rows(dst)
     row_len = src.shape[-1] if row_len is None else row_len
+    if copy_batch.active[0] is not None:
+        copy_batch.active[0].append(_copy_job(src, src_idx, dst, dst_idx, n_rows, row_len))
+        return dst
     check(lib.mega_copy_rows(ptr(src), src.stride(-2), ptr(src_idx), ptr(dst), dst.stride(-2), ptr(dst_idx), n_rows,
                              row_len, stream_ptr()), "mega_copy_rows")
     LAUNCHES[0] += 1
     return dst
+
+
+class copy_batch(object):
+    """with ops.copy_batch(): the gather_rows / copy_rows calls inside are collected and issued as ONE launch on exit
+    (they must be independent of each other)"""
+    active = [None]
+
+    def __enter__(self):
+        copy_batch.active[0] = []
+        return self
+
+    def __exit__(self, et, ev, tb):
+        jobs, copy_batch.active[0] = copy_batch.active[0], None
+        if et is not None or not jobs:
+            return False
+        for i in range(0, len(jobs), 16):
+            part = jobs[i:i + 16]
+            arr = (_lib.CopyJob * len(part))(*part)
+            check(lib.mega_copy_rows_batch(arr, len(part), stream_ptr()), "mega_copy_rows_batch")
+            LAUNCHES[0] += 1
+        return False
+
+
+def _copy_job(src, src_idx, dst, dst_idx, n_rows, row_len):
+    j = _lib.CopyJob()
+    j.src, j.src_ld, j.src_idx = src.data_ptr(), src.stride(-2), (src_idx.data_ptr() if src_idx is not None else None)
+    j.dst, j.dst_ld, j.dst_idx = dst.data_ptr(), dst.stride(-2), (dst_idx.data_ptr() if dst_idx is not None else None)
+    j.n_rows, j.row_len = n_rows, row_len
+    return j
 
 
 def transpose_2d(x, out, n_img, rows, cols):

@@ -370,3 +370,36 @@ def test_fgfa_kernels_match_oracle(cuda_dev, dtype):
     ops.fgfa_aggregate(fring, slots_d, key, flow_d, out, cf, ce, weights_out=wout)
     assert (wout.cpu() - wts[:, 0]).abs().max() < 1e-5
     assert (out.float().cpu().permute(2, 0, 1) - ref).abs().max() < (3e-3 if dtype == torch.float16 else 1e-5)
+
+
+def test_copy_batch_matches_individual_copies(cuda_dev):
+    """ops.copy_batch(): a group of independent gather / scatter row copies issued as one launch"""
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(2)
+    src = torch.randn(60, 1024, generator=g).to(cuda_dev)
+    src16 = torch.randn(40, 1024, generator=g).half().to(cuda_dev)
+    boxes = torch.randn(60, 4, generator=g).to(cuda_dev)
+    cnt = torch.tensor([[7], [9], [11]], dtype=torch.int32, device=cuda_dev)
+    idx = torch.tensor([5, -1, 59, 0, 0, 33], dtype=torch.int32, device=cuda_dev)
+    didx = torch.tensor([3, 1, -1, 0], dtype=torch.int32, device=cuda_dev)
+    sel = torch.tensor([2], dtype=torch.int32, device=cuda_dev)
+
+    def run(batched):
+        outs = [torch.full((6, 1024), 5.0, device=cuda_dev), torch.full((6, 4), 5.0, device=cuda_dev),
+                torch.full((8, 1024), 5.0, device=cuda_dev, dtype=torch.float16), torch.zeros(1, 1, dtype=torch.int32, device=cuda_dev)]
+        ctx = ops.copy_batch() if batched else None
+        if ctx:
+            ctx.__enter__()
+        ops.gather_rows(src, idx, outs[0])
+        ops.gather_rows(boxes, idx, outs[1])
+        ops.copy_rows(src16[:4], outs[2], 4, dst_idx=didx)
+        ops.gather_rows(cnt.view(torch.float32), sel, outs[3].view(torch.float32), 1, row_len=1)
+        if ctx:
+            ctx.__exit__(None, None, None)
+        torch.cuda.synchronize()
+        return outs
+
+    a, b = run(False), run(True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert int(b[3].item()) == 11
