@@ -45,7 +45,7 @@ H, W = 600, 1000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--arch", default="mega_r101")
@@ -253,7 +253,10 @@ def run_b200(args, rank, world):
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "detections_per_frame": ndet / args.steps},
         "gpu_launches": int(round(launches_per_step * args.steps * (1 if world == 1 else 1))),
         "roofline": {"bound": "tensor", "achieved": roof["algo_tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": roof["algo_tflops"] / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                     "frac": roof["algo_tflops"] / pk["tflops"], "traffic": traffic_bytes(), "peak_source": pk["src"],
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, one ncu --set full "
+                                     "capture (profiles/r01_traffic.json)",
+                     "dominant_kernel": roof["dominant"],
                      "kernel": KERNEL_NOTE[args.precision],
                      "algorithmic_gflop_per_frame": ALGO_GFLOP_PER_FRAME, "executed_gflop_per_frame": roof["exec_gflop"],
                      "kernel_ms_per_frame": roof["kernel_ms"], "launches_per_frame": roof["launches"],
@@ -266,7 +269,8 @@ def run_b200(args, rank, world):
 
 PRECISION_DTYPE = {"f16": "f16 operands / f32 accumulate", "tf32": "tf32 operands / f32 accumulate",
                    "fp32x3": "3xtf32 split (near-f32) / f32 accumulate"}
-KERNEL_NOTE = {"f16": "conv_gemm_kernel<.., kModeF16> (tcgen05 kind::f16, fp16 operands; same dense peak as bf16)",
+KERNEL_NOTE = {"f16": "conv_chain_kernel + conv_gemm_kernel<.., kModeF16> (tcgen05 kind::f16, fp16 operands; same dense peak as "
+                      "bf16): all tensor-core launches of the frame",
                "tf32": "conv_gemm_kernel<.., kModeTf32> (tcgen05 kind::tf32; TF32 dense peak is half the bf16 figure)",
                "fp32x3": "conv_gemm_kernel<.., kModeSplit3> (3 tcgen05 kind::tf32 MMAs per product)"}
 
@@ -294,6 +298,15 @@ def strict_pass(args, sd, dev, pool_pinned, pairs_dev, w, h, steps=8):
     return {"precision": "fp32x3", "value": 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "steps": steps,
             "note": "3xTF32 contractions, accumulator re-started every 4 k-blocks: every proposal / detection of the "
                     "reference reproduced, class logits within 1e-2 (tests/test_engine_gpu.py)"}
+
+
+def traffic_bytes():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (null when absent)"""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(path))["traffic_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def roofline_pass(eng, pairs_dev, w, h, reps=3):
@@ -333,8 +346,17 @@ def roofline_pass(eng, pairs_dev, w, h, reps=3):
             json.dump(rows, fh)
     except Exception:
         pass
+    # the dominant launch: the persistent chain kernel that runs res2-res4 + the RPN head (95 layers for R-101)
+    dom = None
+    n = max(len(rec) // reps, 1)
+    for i, r in enumerate(rec):
+        if isinstance(r[3], dict) and r[3].get("chain_layers", 0) >= 20:
+            t = sum(q[0].elapsed_time(q[1]) for q in rec[i % n::n]) / reps
+            dom = {"name": "conv_chain_kernel (res2-res4 + RPN head, %d layers, grid %d)" % (r[3]["chain_layers"], r[3]["grid"]),
+                   "executed_gflop": r[2] / 1e9, "ms": t, "executed_tflops": r[2] / (t * 1e-3) / 1e12}
+            break
     return {"kernel_ms": ms, "exec_gflop": fl / 1e9, "exec_tflops": fl / (ms * 1e-3) / 1e12,
-            "algo_tflops": ALGO_GFLOP_PER_FRAME * 1e9 / (ms * 1e-3) / 1e12, "launches": len(rec) / reps}
+            "algo_tflops": ALGO_GFLOP_PER_FRAME * 1e9 / (ms * 1e-3) / 1e12, "launches": len(rec) / reps, "dominant": dom}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm

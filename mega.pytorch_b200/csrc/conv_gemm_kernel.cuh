@@ -478,44 +478,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c) {
-          float acc[CW];
-#pragma unroll
-          for (int h = 0; h < CW / 32; ++h) {
-            uint32_t raw[32];
-            load_acc(c * (CW / 32) + h, raw);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[h * 32 + j] = __uint_as_float(raw[j]);
-          }
           const int nb = tc.n0 + c * CW;
-          if (!complete) {
-            // deterministic reduction: parts summed in CTA order, own part from TMEM
-            float sum[CW];
-#pragma unroll
-            for (int j = 0; j < CW; ++j) sum[j] = 0.f;
-            for (int oc = c_first; oc <= c_last; ++oc) {
-              if (oc == cta) {
-#pragma unroll
-                for (int j = 0; j < CW; ++j) sum[j] += acc[j];
-              } else {
-                const int slot = (cta_first_unit(U, grid, oc) >= t * KB) ? 0 : 1;
-                const float* ws = p.part_ws + ((static_cast<long long>(oc) * 2 + slot) * kBM + row) * BN + c * CW;
-#pragma unroll
-                for (int j = 0; j < CW; j += 4) {
-                  const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + j));
-                  sum[j] += v.x; sum[j + 1] += v.y; sum[j + 2] += v.z; sum[j + 3] += v.w;
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < CW; ++j) acc[j] = sum[j];
-          }
           const uint8_t* rsrc = nullptr;
           if (p.has_residual) {
             const int rb = c & 1;
             if (c + 1 < nchunks && lane == 0) {   // prefetch the next residual chunk into the other buffer
               mbar_arrive_expect_tx(&rbar[rb ^ 1], 4096);
-              tma_load_4d(epi_res + (rb ^ 1) * 4096, &tmRes, &rbar[rb ^ 1], nb + CW + tc.batch * p.res_c_off, st_w,
-                          st_h, res_n);
+              tma_load_4d(epi_res + (rb ^ 1) * 4096, &tmRes, &rbar[rb ^ 1], nb + CW + tc.batch * p.res_c_off, st_w, st_h,
+                          res_n);
             }
             mbar_wait(&rbar[rb], (rphase >> rb) & 1u);
             rphase ^= (1u << rb);
@@ -525,56 +495,86 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
           uint8_t* dst = epi_out + (c & 1) * 4096 + lane * 128;
-          // scale / bias from the staged slice (columns >= cout hold 1 / 0 and are clipped by the TMA store)
-          if (has_sb) {
-            const float4* scv = reinterpret_cast<const float4*>(sb_s + c * CW);
-            const float4* biv = reinterpret_cast<const float4*>(sb_s + 256 + c * CW);
-#pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-              const float4 sc = scv[j >> 2], bi = biv[j >> 2];
-              acc[j] = fmaf(acc[j], sc.x, bi.x); acc[j + 1] = fmaf(acc[j + 1], sc.y, bi.y);
-              acc[j + 2] = fmaf(acc[j + 2], sc.z, bi.z); acc[j + 3] = fmaf(acc[j + 3], sc.w, bi.w);
+          // 32 accumulator columns at a time (keeps the live registers at 32 + a handful: the 64-wide form spilled)
+        #pragma unroll
+          for (int h = 0; h < CW / 32; ++h) {
+            uint32_t raw[32];
+            load_acc(c * (CW / 32) + h, raw);
+            float acc[32];
+        #pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(raw[j]);
+            const int col0 = c * CW + h * 32;     // first column of this half inside the tile
+            if (!complete) {
+              // deterministic reduction: parts summed in CTA order, own part from TMEM
+              float sum[32];
+        #pragma unroll
+              for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+              for (int oc = c_first; oc <= c_last; ++oc) {
+                if (oc == cta) {
+        #pragma unroll
+                  for (int j = 0; j < 32; ++j) sum[j] += acc[j];
+                } else {
+                  const int slot = (cta_first_unit(U, grid, oc) >= t * KB) ? 0 : 1;
+                  const float* ws = p.part_ws + ((static_cast<long long>(oc) * 2 + slot) * kBM + row) * BN + col0;
+        #pragma unroll
+                  for (int j = 0; j < 32; j += 4) {
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + j));
+                    sum[j] += v.x; sum[j + 1] += v.y; sum[j + 2] += v.z; sum[j + 3] += v.w;
+                  }
+                }
+              }
+        #pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = sum[j];
             }
-          }
-          if (OUT16) {
-            // 64 halves per row: 16-byte groups of 8 halves, swizzled like the TMA box
-#pragma unroll
-            for (int j = 0; j < CW; j += 8) {
-              const uint32_t chunk = (static_cast<uint32_t>(j >> 3) ^ sw) << 4;
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = acc[j + e];
-              if (rsrc) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(rsrc + chunk);
-                const float2 r0 = h2_to_f2(rr.x), r1 = h2_to_f2(rr.y), r2 = h2_to_f2(rr.z), r3 = h2_to_f2(rr.w);
-                v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-                v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
+            if (has_sb) {
+              const float4* scv = reinterpret_cast<const float4*>(sb_s + col0);
+              const float4* biv = reinterpret_cast<const float4*>(sb_s + 256 + col0);
+        #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 sc = scv[j >> 2], bi = biv[j >> 2];
+                acc[j] = fmaf(acc[j], sc.x, bi.x); acc[j + 1] = fmaf(acc[j + 1], sc.y, bi.y);
+                acc[j + 2] = fmaf(acc[j + 2], sc.z, bi.z); acc[j + 3] = fmaf(acc[j + 3], sc.w, bi.w);
               }
-              if (p.relu) {
-                const float slope = p.relu == 2 ? 0.1f : 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], slope * v[e]);
-              }
-              uint4 o;
-              o.x = f2_to_h2(v[0], v[1]); o.y = f2_to_h2(v[2], v[3]);
-              o.z = f2_to_h2(v[4], v[5]); o.w = f2_to_h2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(dst + chunk) = o;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-              float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-              const uint32_t chunk = (static_cast<uint32_t>(j >> 2) ^ sw) << 4;
-              if (rsrc) {
-                const float4 rr = *reinterpret_cast<const float4*>(rsrc + chunk);
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            const float slope = p.relu == 2 ? 0.1f : 0.f;
+            if (OUT16) {
+              // 64 halves per staging row: 16-byte groups of 8 halves, swizzled like the TMA box
+        #pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint32_t chunk = (static_cast<uint32_t>((h * 32 + j) >> 3) ^ sw) << 4;
+                float v[8];
+        #pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = acc[j + e];
+                if (rsrc) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(rsrc + chunk);
+                  const float2 r0v = h2_to_f2(rr.x), r1v = h2_to_f2(rr.y), r2v = h2_to_f2(rr.z), r3v = h2_to_f2(rr.w);
+                  v[0] += r0v.x; v[1] += r0v.y; v[2] += r1v.x; v[3] += r1v.y;
+                  v[4] += r2v.x; v[5] += r2v.y; v[6] += r3v.x; v[7] += r3v.y;
+                }
+                if (p.relu) {
+        #pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], slope * v[e]);
+                }
+                uint4 o;
+                o.x = f2_to_h2(v[0], v[1]); o.y = f2_to_h2(v[2], v[3]);
+                o.z = f2_to_h2(v[4], v[5]); o.w = f2_to_h2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(dst + chunk) = o;
               }
-              if (p.relu) {
-                const float slope = p.relu == 2 ? 0.1f : 0.f;
-                v.x = fmaxf(v.x, slope * v.x); v.y = fmaxf(v.y, slope * v.y);
-                v.z = fmaxf(v.z, slope * v.z); v.w = fmaxf(v.w, slope * v.w);
+            } else {
+        #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+                const uint32_t chunk = (static_cast<uint32_t>(j >> 2) ^ sw) << 4;
+                if (rsrc) {
+                  const float4 rr = *reinterpret_cast<const float4*>(rsrc + chunk);
+                  v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+                }
+                if (p.relu) {
+                  v.x = fmaxf(v.x, slope * v.x); v.y = fmaxf(v.y, slope * v.y);
+                  v.z = fmaxf(v.z, slope * v.z); v.w = fmaxf(v.w, slope * v.w);
+                }
+                *reinterpret_cast<float4*>(dst + chunk) = v;
               }
-              *reinterpret_cast<float4*>(dst + chunk) = v;
             }
           }
           fence_async_smem();
