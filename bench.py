@@ -244,8 +244,9 @@ def run_b200(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": PRECISION_DTYPE[args.precision], "data": "synthetic",
         "config": {"workload": workload(args), "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
-                   "parallelism": ("frame-parallel over %d GPUs, NCCL all-gather of ROI-feature payloads, replicated "
-                                   "aggregation" % world) if world > 1 else "single GPU",
+                   "parallelism": ("frame-parallel over %d GPUs: per-frame branch on the frame's owner, NCCL all-gather of "
+                                   "ROI-feature payloads, memory-feeding rows of the aggregation replicated, key-frame "
+                                   "rows / predictor / post-processing on the owner" % world) if world > 1 else "single GPU",
                    "cuda_graph": bool(eng._graphs), "precision": args.precision,
                    "l2": "per-step working set (0.7 GB fp32 weights + >0.5 GB activations) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,

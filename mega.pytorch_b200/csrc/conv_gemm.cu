@@ -254,6 +254,14 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   if (ctas < 1) ctas = 1;
   if (ctas > g_num_sms) ctas = g_num_sms;
   if (d->max_ctas > 0 && ctas > d->max_ctas) ctas = d->max_ctas;
+  // Very deep reductions (the 100352-deep l_fcs[0]) stream operands larger than L2. With a grid that is a multiple of
+  // the tile count every tile is cut at the same k offsets, so the CTAs that share an A row block or a B column block
+  // read the same k-blocks at the same time and each operand byte comes from DRAM once (3.08 CTAs per tile let the
+  // m-tiles of one weight slab drift > L2 apart: 571 MB of DRAM reads for 280 MB of operands).
+  if (p.stream_k && p.kb_per_tile >= 256 && tiles <= ctas) {
+    const long long aligned = (ctas / tiles) * tiles;
+    if (aligned * 100 >= ctas * 85) ctas = aligned;
+  }
   *ctas_out = static_cast<int>(ctas);
   return MEGA_OK;
 }

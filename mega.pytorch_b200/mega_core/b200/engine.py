@@ -376,18 +376,20 @@ class HeadCommon:
 
     # ------------------------------------------------------------------ relation module
     def _attention(self, att, xq, nq, refs, nref, ld, out, boxes_q=None, boxes_k=None, m_valid=None, n_valid=None,
-                   n_valid_off=0, tail=None):
+                   n_valid_off=0, tail=None, reuse_kv=False):
         """out = xq + Attention(xq, refs)   (attention_module_multi_head, extractors :567-646).
         fp16 mode: the four GEMMs in front of the soft-max (Q, K, V' projections and Q.K^T) are one chain kernel, the
-        P.V' GEMM (+ whatever `tail()` appends, e.g. the stage's next Linear) another."""
+        P.V' GEMM (+ whatever `tail()` appends, e.g. the stage's next Linear) another.
+        reuse_kv: the previous call had the same (att, refs): its K / V' projections are still in the scratch."""
         D = self.feat_dim
         q, k, vt = self.Qb[:nq], self.Kb[:nref], self.Vt[ld]
         s = self.S[ld][:16 * nq * ld].view(16, nq, ld)
-        key = (id(att), xq.data_ptr(), nq, refs.data_ptr(), nref, out.data_ptr(), tail is not None)
+        key = (id(att), xq.data_ptr(), nq, refs.data_ptr(), nref, out.data_ptr(), tail is not None, reuse_kv)
         with ops.chain(self._chains, ("qk",) + key, self.dev, enabled=self.chained):
             ops.linear(xq, att.wq, q, bias=att.bq)
-            ops.linear(refs, att.wk, k, bias=att.bk)
-            ops.linear(att.wv, refs, vt)                                    # V'^T = Wv . refs^T  -> [1024, nref]
+            if not reuse_kv:
+                ops.linear(refs, att.wk, k, bias=att.bk)
+                ops.linear(att.wv, refs, vt)                                # V'^T = Wv . refs^T  -> [1024, nref]
             ops.conv_gemm(q.view(1, 1, nq, D), k.view(1, nref, D), s.view(16, 1, nq, ld), tile=(1, 128), cout=nref,
                           k=64, batch=16, a_c_off=64, b_k_off=64, out_n_off=1, n_img=1)
         pr = self.P[ld][:16 * nq * ld].view(16, nq, ld) if self.P is not None else None
@@ -503,8 +505,25 @@ class WindowedEngine(HeadCommon):
         ops.roi_align_nhwc(r5, self.roi_boxes[:rows], bidx, c.pooler_scale, c.pooler_resolution,
                            c.pooler_resolution, c.sampling_ratio, pooled)
         x = self.fc0_out[:rows]
-        ops.linear(pooled, self.fc0_w, x, bias=self.fc0_b, relu=True)
+        self._fc0(pooled, x)
         return x, boxes, cnt, spans
+
+    @staticmethod
+    def pack_fc0(w_rows):
+        """[1024, K] (K = bin-major ROI feature) -> [K/64, 1024, 64]: every 64-deep slice of the reduction is one contiguous
+        128 KB block, so a CTA's 128-row weight tile of a k-block is 16 KB of consecutive DRAM instead of 128 lines 200 KB
+        apart (the 411 MB fp32 / 205 MB fp16 matrix is the one operand of the frame that streams from DRAM)."""
+        n, k = w_rows.shape
+        assert k % 64 == 0
+        return w_rows.reshape(n, k // 64, 64).permute(1, 0, 2).contiguous()
+
+    def _fc0(self, pooled, x):
+        """l_fcs[0] / fcs[0] + ReLU (make_layers.py:80-92) on [rows, K] ROI features: a GEMM written as a 1 x (K/64)-tap
+        convolution over a [rows, K/64] 'image' with 64 channels, whose weight layout is k-block-major (pack_fc0)."""
+        rows, k = pooled.shape
+        kb = k // 64
+        ops.conv_gemm(pooled.view(1, rows, kb, 64), self.fc0_w, x.view(1, rows, 1, x.shape[1]), taps=(1, kb), pad=0,
+                      bias=self.fc0_b, relu=True, tile=(128, 1), out_hw=(rows, 1))
 
     def _push_local_rows(self, x_rows, boxes300, cnt_row, slot):
         """device copies of one local frame's 300 rows into ring slot `slot` (host-known offsets; used
@@ -572,8 +591,8 @@ class MegaEngine(WindowedEngine):
         w0 = sd[FE + "l_fcs.0.weight"].float()
         ch = w0.shape[1] // (res * res)
         act = self.act
-        self.fc0_w = (w0.reshape(w0.shape[0], ch, res * res).permute(0, 2, 1).reshape(w0.shape[0], -1).contiguous()
-                      .to(act).to(dev))
+        self.fc0_w = self.pack_fc0(w0.reshape(w0.shape[0], ch, res * res).permute(0, 2, 1).reshape(w0.shape[0], -1)
+                                   .to(act)).to(dev)
         self.fc0_b = sd[FE + "l_fcs.0.bias"].float().contiguous().to(dev)
         self.fc_w = [None] + [sd[FE + "l_fcs.%d.weight" % i].float().contiguous().to(dev).to(act) for i in (1, 2)]
         self.fc_b = [None] + [sd[FE + "l_fcs.%d.bias" % i].float().contiguous().to(dev) for i in (1, 2)]
@@ -599,6 +618,7 @@ class MegaEngine(WindowedEngine):
         self.cur_cnt = z(1, 1, dtype=torch.int32)
         self.payload_in = z(KP * self.fw + KP * 4 + 4 + R * self.fw)   # 32-bit words: x300 | boxes | count | x75
         self.payload_all = None
+        self.owner_only = True          # frame-parallel runs: key-frame rows only on the frame's owner
         # ---- attention scratch, one set per key-count geometry
         self.ld_g = _round_up(GF * R, 32)
         self.ld_0 = _round_up(self.nl0 + self.mem_cap0, 32)
@@ -693,32 +713,49 @@ class MegaEngine(WindowedEngine):
         self._graph_run(("ref", tuple(imgs.shape), im_w, im_h),
                         lambda: self._ref_to_payload(static_in, im_w, im_h, self.payload_in))
 
-    def _ingest_next(self, im_w, im_h):
+    def _ingest_next(self, im_w, im_h, mode="fused"):
         slot_new = self._claim_slot()
         gslot = self.glob_pushed % self.GF
         self.glob_pushed += 1
         self._fill_tables(slot_new=slot_new, gslot=gslot)
-        return self._graph_run(("ingest", im_w, im_h), lambda: self._ingest(im_w, im_h))
+        return self._graph_run(("ingest", im_w, im_h, mode), lambda: self._ingest(im_w, im_h, mode))
 
     # ---- frame-parallel multi-GPU (option i): rank r runs the per-frame branch of
     #      frame pair r of every group of `world` key frames; one NCCL all-gather of the fixed-size payloads
     #      (1.54 MB per rank) in frame order; every rank then ingests all `world` frames so the window /
-    #      global pool / long-range memory stay replicated and results do not depend on `world`.
+    #      global pool / long-range memory stay replicated and results do not depend on `world`. Of a foreign
+    #      frame a rank runs only the rows that feed the memory (_aggregate_split); the key-frame rows, the
+    #      predictor and the post-processing run on the frame's owner.
     @_with_precision
-    def dist_step(self, imgs, im_w, im_h, group=None):
-        import torch.distributed as dist
-        from . import parallel
-        world = dist.get_world_size(group)
-        self._run_ref(imgs, im_w, im_h)
-        if self.payload_all is None or self.payload_all.shape[0] != world:
-            self.payload_all = torch.zeros(world, self.payload_in.numel(), device=self.dev)
-        parallel.gather_payloads(self.payload_in, self.payload_all, group)
+    def dist_step(self, imgs, im_w, im_h, group=None, rank=None, world=None, payloads=None):
+        """returns a list of `world` entries: Detections of this rank's key frame at index `rank`, None elsewhere
+        (owner_only=False: every rank aggregates every frame with the single-GPU launch sequence and all entries are
+        filled). `payloads` [world, words] replaces the all-gather (single-process tests of the host logic)."""
+        if payloads is None:
+            import torch.distributed as dist
+            from . import parallel
+            world = dist.get_world_size(group)
+            rank = dist.get_rank(group)
+            self._run_ref(imgs, im_w, im_h)
+            if self.payload_all is None or self.payload_all.shape[0] != world:
+                self.payload_all = torch.zeros(world, self.payload_in.numel(), device=self.dev)
+            parallel.gather_payloads(self.payload_in, self.payload_all, group)
+            payloads = self.payload_all
         dets = []
         for g in range(world):
-            self.payload_in.copy_(self.payload_all[g], non_blocking=True)
-            det = self._ingest_next(im_w, im_h)
-            dets.append(Detections(det.boxes.clone(), det.scores.clone(), det.labels.clone(), det.count.clone()))
+            self.payload_in.copy_(payloads[g], non_blocking=True)
+            mode = "fused" if not self.owner_only else ("owner" if g == rank else "state")
+            det = self._ingest_next(im_w, im_h, mode)
+            if det is not None and world > 1 and not self.owner_only:
+                det = Detections(det.boxes.clone(), det.scores.clone(), det.labels.clone(), det.count.clone())
+            dets.append(det)
         return dets
+
+    def ref_payload(self, imgs, im_w, im_h):
+        """per-frame branch of one (local, global) pair -> a copy of its payload (what a rank contributes to the gather)"""
+        with ops.precision(self.cfg.precision):
+            self._run_ref(imgs, im_w, im_h)
+        return self.payload_in.clone()
 
     def _fill_tables(self, slot_new=None, gslot=None):
         KP, R, A, L = self.KP, self.R, self.A, self.L
@@ -784,7 +821,7 @@ class MegaEngine(WindowedEngine):
             ops.copy_rows(x[og:og + rg], pg, R)
         return payload
 
-    def _ingest(self, im_w, im_h):
+    def _ingest(self, im_w, im_h, mode="fused"):
         """payload_in -> ring slots named by the index tables -> aggregation (graph-capturable: every
         frame-dependent address comes from `tab_d`)"""
         KP, R = self.KP, self.R
@@ -794,14 +831,15 @@ class MegaEngine(WindowedEngine):
             ops.copy_rows(pb, self.win_boxes, KP, dst_idx=self._tab("dst_local"))
             ops.copy_rows(pc[:, :1], self.win_cnt.view(torch.float32), 1, row_len=1, dst_idx=self._tab("slot_new")[:1])
             ops.copy_rows(pg, self.glob_x, R, dst_idx=self._tab("dst_glob"))
-        return self.aggregate(im_w, im_h, new_local=True)
+        return self.aggregate(im_w, im_h, new_local=True, mode=mode)
 
     def _steady_frame(self, imgs, im_w, im_h):
         self._ref_to_payload(imgs, im_w, im_h, self.payload_in)
         return self._ingest(im_w, im_h)
 
-    def aggregate(self, im_w, im_h, new_local=True):
-        """MEGAFeatureExtractor._forward_test after the per-frame features exist (extractors :898-933)."""
+    def aggregate(self, im_w, im_h, new_local=True, mode="fused"):
+        """MEGAFeatureExtractor._forward_test after the per-frame features exist (extractors :898-933).
+        mode: "fused" (single-GPU launch sequence), or the row-split sequence as "owner" / "state" (_aggregate_split)."""
         KP, R, A, L, D = self.KP, self.R, self.A, self.L, self.feat_dim
         if not new_local:
             self._fill_tables()
@@ -819,6 +857,8 @@ class MegaEngine(WindowedEngine):
                             row_len=1)
         kcnt = self.cur_cnt.view(-1)[:1]
         mv = t("mvalid")
+        if mode != "fused":
+            return self._aggregate_split(im_w, im_h, kcnt, mv, owner=(mode == "owner"))
         # G0: global aggregation of key / ref rows (update_lm index 0, extractors :757-760, :690-699)
         nq0 = KP + nl0
         self._attention(self.att_g[0], self.E0[:nq0], nq0, self.glob_x, self.GF * R, self.ld_g, self.E0[:nq0])
@@ -828,27 +868,82 @@ class MegaEngine(WindowedEngine):
         self._attention(self.att_l[0], self.Qin0, nq, refs0, nl0 + self.mem_cap0, self.ld_0, self.X1,
                         boxes_q=self.Bq0, boxes_k=self.B0[KP:], m_valid=mv[0:1], n_valid=kcnt, n_valid_off=KP,
                         tail=lambda: ops.linear(self.X1, self.fc_w[1], self.Y1E[:nq], bias=self.fc_b[1], relu=True))
-        # update_memory(0): the oldest local frame's 75 enhanced rows (extractors :678-688)
-        with ops.copy_batch():
-            ops.copy_rows(self.E0[KP:KP + R], self.E0, R, dst_idx=t("dst_mem0"))
-            ops.copy_rows(self.B0[KP:KP + R], self.B0, R, dst_idx=t("dst_mem0"))
+        self._push_mem0()
         # stage 1
         self._attention(self.att_l[1], self.Y1E[:nq], nq, self.Y1E[KP:], nl12 + self.mem_cap12, self.ld_12, self.X2,
                         boxes_q=self.Bq0, boxes_k=self.B1, m_valid=mv[1:2], n_valid=kcnt, n_valid_off=KP,
                         tail=lambda: ops.linear(self.X2, self.fc_w[2], self.Y2M[:nq], bias=self.fc_b[2], relu=True))
-        with ops.copy_batch():
-            ops.copy_rows(self.Y1E[KP:KP + A], self.Y1E, A, dst_idx=t("dst_mem12"))
-            ops.copy_rows(self.B1[:A], self.B1, A, dst_idx=t("dst_memb12"))
+        self._push_mem12(self.Y1E, self.B1)
         # stage 2 (key rows only)
         self._attention(self.att_l[2], self.Y2M[:KP], KP, self.Y2M[KP:], nl12 + self.mem_cap12, self.ld_12, self.X3,
                         boxes_q=self.Bq0[:KP], boxes_k=self.B2, m_valid=mv[2:3])
-        with ops.copy_batch():
-            ops.copy_rows(self.Y2M[KP:KP + A], self.Y2M, A, dst_idx=t("dst_mem12"))
-            ops.copy_rows(self.B2[:A], self.B2, A, dst_idx=t("dst_memb12"))
+        self._push_mem12(self.Y2M, self.B2)
         # G1: update_lm(x, 1) (extractors :930-931)
         self._attention(self.att_g[1], self.X3, KP, self.glob_x, self.GF * R, self.ld_g, self.X4,
                         tail=lambda: self.predict_gemm(self.X4))       # the predictor rides in the last P.V' chain
         return self.predict_and_postprocess(self.X4, self.Bq0[:KP], kcnt, im_w, im_h, gemm_done=True)
+
+    def _push_mem0(self):
+        """update_memory(0): the oldest local frame's 75 globally enhanced rows (extractors :678-688)"""
+        KP, R, t = self.KP, self.R, self._tab
+        with ops.copy_batch():
+            ops.copy_rows(self.E0[KP:KP + R], self.E0, R, dst_idx=t("dst_mem0"))
+            ops.copy_rows(self.B0[KP:KP + R], self.B0, R, dst_idx=t("dst_mem0"))
+
+    def _push_mem12(self, Y, B):
+        """update_memory(1 / 2): the first 15 distilled rows of the stage that was just read (extractors :924-928)"""
+        KP, A, t = self.KP, self.A, self._tab
+        with ops.copy_batch():
+            ops.copy_rows(Y[KP:KP + A], Y, A, dst_idx=t("dst_mem12"))
+            ops.copy_rows(B[:A], B, A, dst_idx=t("dst_memb12"))
+
+    def _aggregate_split(self, im_w, im_h, kcnt, mv, owner):
+        """The aggregation with every relation call cut by query rows into a STATE part (the rows that later frames read
+        back through the long-range memory: reference rows of G0, distilled rows of stages 0 / 1) and a KEY part (the
+        key frame's <= 300 proposals, which only produce this frame's detections). Frame-parallel runs (SURVEY.md
+        section 8e) execute the state part on every rank and the key part on the frame's owner only, so the replicated
+        work per foreign frame drops to the state rows; since the state rows always go through the same launches, the
+        memory - hence every detection - is bit-identical for any number of GPUs (including 1 with mode "owner")."""
+        KP, R, A, D = self.KP, self.R, self.A, self.feat_dim
+        nl0, nl12, nq = self.nl0, self.nl12, self.nq
+        nq0 = KP + nl0
+        E0, Qin0, Bq0 = self.E0, self.Qin0, self.Bq0
+        fc = lambda x, i, out: (lambda: ops.linear(x, self.fc_w[i], out, bias=self.fc_b[i], relu=True))
+        # G0 (no position term): reference rows, then key rows against the same K / V'
+        self._attention(self.att_g[0], E0[KP:nq0], nl0, self.glob_x, self.GF * R, self.ld_g, E0[KP:nq0])
+        if owner:
+            self._attention(self.att_g[0], E0[:KP], KP, self.glob_x, self.GF * R, self.ld_g, E0[:KP], reuse_kv=True)
+            ops.gather_rows(E0, self.idx_qin0, Qin0, nq)
+        else:
+            ops.gather_rows(E0, self.idx_qin0[KP:], Qin0[KP:], nl12)
+        # stage 0
+        refs0, m0 = E0[KP:], nl0 + self.mem_cap0
+        self._attention(self.att_l[0], Qin0[KP:], nl12, refs0, m0, self.ld_0, self.X1[KP:], boxes_q=Bq0[KP:],
+                        boxes_k=self.B0[KP:], m_valid=mv[0:1], tail=fc(self.X1[KP:], 1, self.Y1E[KP:nq]))
+        if owner:
+            self._attention(self.att_l[0], Qin0[:KP], KP, refs0, m0, self.ld_0, self.X1[:KP], boxes_q=Bq0[:KP],
+                            boxes_k=self.B0[KP:], m_valid=mv[0:1], n_valid=kcnt, n_valid_off=KP, reuse_kv=True,
+                            tail=fc(self.X1[:KP], 1, self.Y1E[:KP]))
+        self._push_mem0()
+        # stage 1
+        m12 = nl12 + self.mem_cap12
+        self._attention(self.att_l[1], self.Y1E[KP:nq], nl12, self.Y1E[KP:], m12, self.ld_12, self.X2[KP:],
+                        boxes_q=Bq0[KP:], boxes_k=self.B1, m_valid=mv[1:2], tail=fc(self.X2[KP:], 2, self.Y2M[KP:nq]))
+        if owner:
+            self._attention(self.att_l[1], self.Y1E[:KP], KP, self.Y1E[KP:], m12, self.ld_12, self.X2[:KP],
+                            boxes_q=Bq0[:KP], boxes_k=self.B1, m_valid=mv[1:2], n_valid=kcnt, n_valid_off=KP,
+                            reuse_kv=True, tail=fc(self.X2[:KP], 2, self.Y2M[:KP]))
+        self._push_mem12(self.Y1E, self.B1)
+        if owner:
+            # stage 2 and G1 have key-row queries only
+            self._attention(self.att_l[2], self.Y2M[:KP], KP, self.Y2M[KP:], m12, self.ld_12, self.X3,
+                            boxes_q=Bq0[:KP], boxes_k=self.B2, m_valid=mv[2:3])
+        self._push_mem12(self.Y2M, self.B2)
+        if not owner:
+            return None
+        self._attention(self.att_g[1], self.X3, KP, self.glob_x, self.GF * R, self.ld_g, self.X4,
+                        tail=lambda: self.predict_gemm(self.X4))
+        return self.predict_and_postprocess(self.X4, Bq0[:KP], kcnt, im_w, im_h, gemm_done=True)
 
 
 class RdnEngine(WindowedEngine):
@@ -872,8 +967,8 @@ class RdnEngine(WindowedEngine):
         res, act = c.pooler_resolution, self.act
         w0 = sd[FE + "fcs.0.weight"].float()
         ch = w0.shape[1] // (res * res)
-        self.fc0_w = (w0.reshape(w0.shape[0], ch, res * res).permute(0, 2, 1).reshape(w0.shape[0], -1).contiguous()
-                      .to(act).to(dev))
+        self.fc0_w = self.pack_fc0(w0.reshape(w0.shape[0], ch, res * res).permute(0, 2, 1).reshape(w0.shape[0], -1)
+                                   .to(act)).to(dev)
         self.fc0_b = sd[FE + "fcs.0.bias"].float().contiguous().to(dev)
         self.fc_w = [None] + [sd[FE + "fcs.%d.weight" % i].float().contiguous().to(dev).to(act) for i in (1, 2)]
         self.fc_b = [None] + [sd[FE + "fcs.%d.bias" % i].float().contiguous().to(dev) for i in (1, 2)]

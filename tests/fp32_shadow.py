@@ -26,12 +26,18 @@ def _shadow_conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=
         az = a[z * a_n_off: z * a_n_off + on] if a_n_off else a
         az = az[..., z * a_c_off: z * a_c_off + k]                       # [n,h,w,k]
         wz = w[:, z * b_n_off: z * b_n_off + cout, z * b_k_off: z * b_k_off + k]   # [t, cout, k]
-        x = az.permute(0, 3, 1, 2).double()
-        wt = wz.reshape(taps[0], taps[1], cout, k).permute(2, 3, 0, 1).double()
         pw_ = pad if pad_w is None else pad_w
-        extra_h, extra_w = taps[0] * dil + stride[0], taps[1] * dil + stride[1]     # zero fill beyond the map, like TMA
-        x = F.pad(x, (pw_, extra_w, pad, extra_h))
-        y = F.conv2d(x, wt, None, stride, 0, dil)[:, :, :oh, :ow].permute(0, 2, 3, 1)   # [n,oh,ow,cout]
+        if taps[0] == 1 and taps[1] == az.shape[2] and pad == 0 and pw_ == 0 and tuple(stride) == (1, 1) and ow == 1 \
+                and dil == 1:
+            # a kernel as wide as the map (the l_fcs[0] GEMM written as a convolution): one dot product per row
+            y = (az.reshape(az.shape[0], az.shape[1], -1).double()
+                 @ wz.permute(1, 0, 2).reshape(cout, -1).double().t()).view(az.shape[0], az.shape[1], 1, cout)[:, :oh]
+        else:
+            x = az.permute(0, 3, 1, 2).double()
+            wt = wz.reshape(taps[0], taps[1], cout, k).permute(2, 3, 0, 1).double()
+            extra_h, extra_w = taps[0] * dil + stride[0], taps[1] * dil + stride[1]     # zero fill beyond the map, like TMA
+            x = F.pad(x, (pw_, extra_w, pad, extra_h))
+            y = F.conv2d(x, wt, None, stride, 0, dil)[:, :, :oh, :ow].permute(0, 2, 3, 1)   # [n,oh,ow,cout]
         if scale is not None:
             y = y * scale[z * bias_z_off: z * bias_z_off + cout].double()
         if bias is not None:
