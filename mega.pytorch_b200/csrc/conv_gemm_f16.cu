@@ -20,7 +20,7 @@ int launch_conv_gemm_f16(int block_n, int out_f16, const CUtensorMap& tmA, const
     MEGA_F16_CASE(32, 6)
     MEGA_F16_CASE(64, 6)
     MEGA_F16_CASE(96, 5)
-    MEGA_F16_CASE(128, 4)
+    MEGA_F16_CASE(128, 5)
     MEGA_F16_CASE(160, 4)
     MEGA_F16_CASE(192, 3)
     MEGA_F16_CASE(256, 3)

@@ -69,8 +69,9 @@ struct SmemLayout {
   static constexpr int kEpiOffset = STAGES * kStageBytes;       // 4 warps x (2 out + 2 residual) x 4 KB
   static constexpr int kEpiBytes = 4 * 4 * 4096;
   static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
-  static constexpr int kSbOffset = kBarOffset + 512;              // [scale | bias][256] floats of the tile being finished
-  static constexpr int kTotal = kSbOffset + 2048 + 1024;          // + align slack
+  static constexpr int kSbCols = BN <= 128 ? 128 : 256;
+  static constexpr int kSbOffset = kBarOffset + 512;              // [scale | bias][kSbCols] floats of the tile being finished
+  static constexpr int kTotal = kSbOffset + 8 * kSbCols + 1024;   // + align slack
 };
 
 struct TileCoord {
@@ -160,6 +161,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int kBK = mode_bk(MODE);
   constexpr int CW = OUT16 ? 64 : 32;   // epilogue chunk: columns per 128-byte output row segment
   static_assert(!OUT16 || BN % 64 == 0, "fp16 output needs block_n % 64 == 0");
+  static_assert(SmemLayout<BN, STAGES, MODE>::kTotal <= 227 * 1024, "pipeline + staging exceed the 227 KB of a CTA");
   using L = SmemLayout<BN, STAGES, MODE>;
   // accumulators: two ping-pong buffers (+ a master accumulator in 3xTF32 mode, see kSegLen)
   constexpr uint32_t kAccBufs = SPLIT3 ? 3 : 2;
@@ -411,7 +413,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n = tc.n0 + i;
         const int zoff = tc.batch * p.bias_z_off;
         sb_s[i] = (p.scale && n < p.cout) ? __ldg(p.scale + zoff + n) : 1.f;
-        sb_s[256 + i] = (p.bias && n < p.cout) ? __ldg(p.bias + zoff + n) : 0.f;
+        sb_s[L::kSbCols + i] = (p.bias && n < p.cout) ? __ldg(p.bias + zoff + n) : 0.f;
       }
       if (complete && p.has_residual && lane == 0 && nchunks > 0) {
         mbar_arrive_expect_tx(&rbar[0], 4096);
@@ -528,7 +530,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (has_sb) {
               const float4* scv = reinterpret_cast<const float4*>(sb_s + col0);
-              const float4* biv = reinterpret_cast<const float4*>(sb_s + 256 + col0);
+              const float4* biv = reinterpret_cast<const float4*>(sb_s + L::kSbCols + col0);
         #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 sc = scv[j >> 2], bi = biv[j >> 2];
