@@ -66,6 +66,29 @@ __device__ __forceinline__ float iou_plus1(const float4 a, const float4 b) {
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
 }
 
+__device__ __forceinline__ float box_area_plus1(const float4 a) {
+  return __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
+}
+
+// iou_plus1(a, b) > thresh with the SAME outcome for every input, but without the division unless the quotient is
+// within 2^-20 (relative) of the threshold: RN(inter / u) > t is decided by inter vs t*u whenever the true quotient is
+// more than a few ulps away from t (t_lo = t*(1-2^-20), t_hi = t*(1+2^-20); the two products carry 2^-24 relative
+// error each, far inside the band). sa / sb: box_area_plus1 of a / b.
+__device__ __forceinline__ bool iou_plus1_gt(const float4 a, const float sa, const float4 b, const float sb,
+                                             const float thresh, const float t_lo, const float t_hi) {
+  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
+  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
+  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
+  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
+  const float inter = __fmul_rn(width, height);
+  const float u = __fsub_rn(__fadd_rn(sa, sb), inter);
+  if (u > 0.f) {
+    if (inter > __fmul_rn(t_hi, u)) return true;
+    if (inter < __fmul_rn(t_lo, u)) return false;
+  }
+  return __fdiv_rn(inter, u) > thresh;
+}
+
 // mask[img][i][cb]: bit j of word c set <=> IoU(box i, box c*64+j) > thresh (only c >= i/64)
 __global__ void nms_mask_kernel(const float4* __restrict__ boxes, long long boxes_img_stride,
                                 const int* __restrict__ n_ptr, int n_host, float thresh,
@@ -295,9 +318,24 @@ __global__ void __launch_bounds__(kSortThreads, 1) rpn_topk_decode_kernel(const 
     for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     const uint32_t prefix = s_prefix;
-    for (int i = tid; i < n; i += blockDim.x) {
-      const uint32_t key = keys[i];
-      if ((key & sel_mask) == prefix) atomicAdd(&hist[(key >> shift) & 255], 1);
+    // detection scores cluster (most anchors are background): whole warps fall into one bin, and 28 k same-address
+    // shared-memory atomics would serialise -> one atomic per warp when its live lanes agree on the bin
+    for (int base = 0; base < n; base += blockDim.x) {
+      const int i = base + tid;
+      const uint32_t key = i < n ? keys[i] : 0u;
+      const bool live = i < n && (key & sel_mask) == prefix;
+      const uint32_t bin = (key >> shift) & 255u;
+      const unsigned m = __ballot_sync(0xffffffffu, live);
+      if (m != 0u) {
+        const int leader = __ffs(m) - 1;
+        const uint32_t lb = __shfl_sync(0xffffffffu, bin, leader);
+        const unsigned same = __ballot_sync(0xffffffffu, live && bin == lb);
+        if (same == m) {
+          if ((tid & 31) == leader) atomicAdd(&hist[lb], __popc(m));
+        } else if (live) {
+          atomicAdd(&hist[bin], 1);
+        }
+      }
     }
     __syncthreads();
     if (tid == 0) {
@@ -325,12 +363,15 @@ __global__ void __launch_bounds__(kSortThreads, 1) rpn_topk_decode_kernel(const 
     s_running = 0;
   }
   __syncthreads();
-  for (int i = tid; i < n; i += blockDim.x) {
-    const uint32_t key = keys[i];
-    if (key < T) {
-      const int pos = atomicAdd(&s_cnt, 1);
-      skeys[pos] = (static_cast<uint64_t>(key) << 32) | static_cast<uint32_t>(i);
-    }
+  for (int base = 0; base < n; base += blockDim.x) {       // order inside the sort buffer is irrelevant: one atomic per warp
+    const int i = base + tid;
+    const uint32_t key = i < n ? keys[i] : 0xffffffffu;
+    const bool lt = i < n && key < T;
+    const unsigned m = __ballot_sync(0xffffffffu, lt);
+    int pos0 = 0;
+    if ((tid & 31) == 0 && m != 0u) pos0 = atomicAdd(&s_cnt, __popc(m));
+    pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+    if (lt) skeys[pos0 + __popc(m & ((1u << (tid & 31)) - 1u))] = (static_cast<uint64_t>(key) << 32) | static_cast<uint32_t>(i);
   }
   for (int base = 0; base < n; base += blockDim.x) {
     const int i = base + tid;
@@ -429,8 +470,10 @@ rpn_nms_greedy_kernel(const float4* __restrict__ sorted_boxes, const float* __re
                       const int* __restrict__ n_ptr, int n_host, float thresh, int post, float4* __restrict__ out_boxes,
                       float* __restrict__ out_scores, int* __restrict__ out_anchor, int* __restrict__ out_count) {
   __shared__ float4 kept_b[kGreedyMaxKeep];
+  __shared__ float kept_a[kGreedyMaxKeep];
   __shared__ int kept_p[kGreedyMaxKeep];
   __shared__ float4 cand[64];
+  __shared__ float cand_a[64];
   __shared__ unsigned long long diag[64];
   __shared__ unsigned long long sup_s;
   __shared__ int nk_s;
@@ -439,6 +482,7 @@ rpn_nms_greedy_kernel(const float4* __restrict__ sorted_boxes, const float* __re
   const int n = n_ptr ? n_ptr[img] : n_host;
   const float4* boxes = sorted_boxes + static_cast<long long>(img) * kNmsMaxBoxes;
   const unsigned char* v = valid ? valid + static_cast<long long>(img) * kNmsMaxBoxes : nullptr;
+  const float t_lo = __fmul_rn(thresh, 1.f - 9.5367431640625e-07f), t_hi = __fmul_rn(thresh, 1.f + 9.5367431640625e-07f);
   if (tid == 0) nk_s = 0;
   __syncthreads();
   const int chunks = (n + 63) / 64;
@@ -446,7 +490,9 @@ rpn_nms_greedy_kernel(const float4* __restrict__ sorted_boxes, const float* __re
     const int base = c * 64;
     const int csz = min(64, n - base);
     if (tid < 64) {
-      cand[tid] = tid < csz ? boxes[base + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 b = tid < csz ? boxes[base + tid] : make_float4(0.f, 0.f, 0.f, 0.f);
+      cand[tid] = b;
+      cand_a[tid] = box_area_plus1(b);
       diag[tid] = 0ULL;
     }
     if (tid == 0) {
@@ -460,39 +506,42 @@ rpn_nms_greedy_kernel(const float4* __restrict__ sorted_boxes, const float* __re
     for (int qq = 0; qq < 64 / (kGreedyThreads / 32); ++qq) {
       const int q = warp * (64 / (kGreedyThreads / 32)) + qq;
       const float4 cq = cand[q];
+      const float aq = cand_a[q];
       bool hit = false;
-      for (int k = lane; k < nk; k += 32) hit |= (iou_plus1(kept_b[k], cq) > thresh);
+      for (int k = lane; k < nk; k += 32) hit |= iou_plus1_gt(kept_b[k], kept_a[k], cq, aq, thresh, t_lo, t_hi);
       if (__any_sync(0xffffffffu, hit) && lane == 0) atomicOr(&sup_s, 1ULL << q);
     }
     // ---- 2. the chunk against itself: thread (q, part) evaluates 8 later candidates
     {
       const int q = tid >> 3, part = tid & 7;
       const float4 cq = cand[q];
+      const float aq = cand_a[q];
       unsigned long long bits = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int o = part * 8 + j;
-        if (o > q && o < csz && iou_plus1(cq, cand[o]) > thresh) bits |= 1ULL << o;
+        if (o > q && o < csz && iou_plus1_gt(cq, aq, cand[o], cand_a[o], thresh, t_lo, t_hi)) bits |= 1ULL << o;
       }
       if (bits) atomicOr(&diag[q], bits);
     }
     __syncthreads();
-    // ---- 3. warp 0 resolves the chunk in order (every lane tracks the same state; lane 0 appends)
+    // ---- 3. warp 0 resolves the chunk in order: every lane tracks the same removed-set `r` and jumps from one
+    //         surviving candidate to the next (a kept candidate removes itself and the later ones it overlaps)
     if (warp == 0) {
       const unsigned long long d0 = diag[lane], d1 = diag[lane + 32];
       unsigned long long r = sup_s;
       int cnt = nk;
-      for (int i = 0; i < csz && cnt < post; ++i) {
+      while (cnt < post && r != ~0ULL) {
+        const int i = __ffsll(static_cast<long long>(~r)) - 1;
         const unsigned long long di_lo = __shfl_sync(0xffffffffu, d0, i & 31);
         const unsigned long long di_hi = __shfl_sync(0xffffffffu, d1, i & 31);
-        if (!((r >> i) & 1ULL)) {
-          r |= (i < 32) ? di_lo : di_hi;
-          if (lane == 0) {
-            kept_b[cnt] = cand[i];
-            kept_p[cnt] = base + i;
-          }
-          ++cnt;
+        r |= ((i < 32) ? di_lo : di_hi) | (1ULL << i);
+        if (lane == 0) {
+          kept_b[cnt] = cand[i];
+          kept_a[cnt] = cand_a[i];
+          kept_p[cnt] = base + i;
         }
+        ++cnt;
       }
       if (lane == 0) nk_s = cnt;
     }
