@@ -7,6 +7,7 @@
 // concatenate class by class; if more than `detections_per_img` survive, keep those whose score is
 // >= the (n - D + 1)-th smallest (torch.kthvalue on the CPU, inference.py:141-148).
 #include "common.cuh"
+#include "iou.cuh"
 #include "mega_b200.h"
 
 namespace mega {
@@ -51,6 +52,7 @@ struct PostParams {
 __global__ void __launch_bounds__(kPostThreads, 1) box_class_nms_kernel(const PostParams p) {
   __shared__ uint64_t skeys[kMaxRois];
   __shared__ float4 sbox[kMaxRois];
+  __shared__ float sarea[kMaxRois];
   __shared__ unsigned long long smask[kMaxRois][kMaxRois / 64];
   __shared__ int s_n;
   const int j = blockIdx.x + 1;
@@ -122,16 +124,24 @@ __global__ void __launch_bounds__(kPostThreads, 1) box_class_nms_kernel(const Po
   }
   __syncthreads();
   const int n = s_n;
-  for (int i = tid; i < n; i += blockDim.x) sbox[i] = ob[static_cast<int>(skeys[i] & 0xffffffffu)];
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float4 b = ob[static_cast<int>(skeys[i] & 0xffffffffu)];
+    sbox[i] = b;
+    sarea[i] = box_area_plus1(b);
+  }
   __syncthreads();
   const int cb = (n + 63) / 64;
+  // same keep / suppress outcome as dividing (iou.cuh): the division only runs within 2^-20 of the threshold
+  const float t_lo = __fmul_rn(p.nms_thresh, 1.f - 9.5367431640625e-07f), t_hi = __fmul_rn(p.nms_thresh, 1.f + 9.5367431640625e-07f);
   for (int t = tid; t < n * cb; t += blockDim.x) {
     const int i = t / cb, c = t - i * cb;
     unsigned long long bits = 0;
     const int jend = min(64, n - c * 64);
-    for (int q = 0; q < jend; ++q) {
+    const float4 bi = sbox[i];
+    const float ai = sarea[i];
+    for (int q = max(0, i + 1 - c * 64); q < jend; ++q) {
       const int o = c * 64 + q;
-      if (o > i && iou_p1(sbox[i], sbox[o]) > p.nms_thresh) bits |= 1ULL << q;
+      if (iou_plus1_gt(bi, ai, sbox[o], sarea[o], p.nms_thresh, t_lo, t_hi)) bits |= 1ULL << q;
     }
     smask[i][c] = bits;
   }
