@@ -20,17 +20,6 @@ __device__ __forceinline__ uint32_t pf2ord(float f) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-__device__ __forceinline__ float iou_p1(const float4 a, const float4 b) {
-  const float left = fmaxf(a.x, b.x), right = fminf(a.z, b.z);
-  const float top = fmaxf(a.y, b.y), bottom = fminf(a.w, b.w);
-  const float width = fmaxf(__fadd_rn(__fsub_rn(right, left), 1.f), 0.f);
-  const float height = fmaxf(__fadd_rn(__fsub_rn(bottom, top), 1.f), 0.f);
-  const float inter = __fmul_rn(width, height);
-  const float sa = __fmul_rn(__fadd_rn(__fsub_rn(a.z, a.x), 1.f), __fadd_rn(__fsub_rn(a.w, a.y), 1.f));
-  const float sb = __fmul_rn(__fadd_rn(__fsub_rn(b.z, b.x), 1.f), __fadd_rn(__fsub_rn(b.w, b.y), 1.f));
-  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(sa, sb), inter));
-}
-
 struct PostParams {
   const float* logits;   // [R, ld_logits], num_classes valid columns
   int ld_logits;
