@@ -10,6 +10,7 @@
 // Arithmetic is written with explicit round-to-nearest ops (no FMA contraction) in the
 // reference's association order, so results are bit-identical to the C oracle.
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "common.cuh"
 #include "mega_b200.h"
 
@@ -389,6 +390,141 @@ roi_align_nhwc_f16_fast_kernel(const __half* __restrict__ in, int channels, int 
   }
 }
 
+// ---- fp16 separable path (feature maps up to 64 x 64 cells). The samples of a bin form a grid_h x grid_w lattice and a
+// sample's four bilinear weights are (row weight) x (column weight), so the sum over the lattice factorises:
+//     out[ph, pw] = 1/count * sum_y Wy[ph][y] * ( sum_x Wx[pw][x] * f[y, x] ),
+// Wy[ph][y] = total weight the grid_h sample rows of bin-row ph put on map row y (same for columns). Every cell of the
+// roi's footprint is then read ~once per bin-row it touches (not 4 times per sample) and costs one FMA per channel in
+// the row pass: rois larger than the shared-memory cache of the kernel above - the common case for VID objects - get
+// ~4x fewer loads and FMAs. Same skipping (samples outside [-1, size]) and clamping rules, applied per axis.
+constexpr int kSepMaxDim = 64;
+// MEGA_B200_ROI_SEPARABLE=0 keeps the per-sample kernel above for every roi
+static const bool g_roi_separable = [] {
+  const char* e = getenv("MEGA_B200_ROI_SEPARABLE");
+  return e != nullptr ? e[0] != '0' : false;
+}();
+
+__global__ void __launch_bounds__(256)
+roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int height, int width, long long in_img_stride,
+                              const float* __restrict__ rois, int roi_ld, int roi_box_off,
+                              const int* __restrict__ roi_batch, float scale, int ph, int pw, int sampling_ratio,
+                              __half* __restrict__ out, long long out_roi_stride) {
+  constexpr int kSlice = kRoiSliceBytes / 2;     // 128 channels per CTA
+  __shared__ float Wy[7][kSepMaxDim], Wx[7][kSepMaxDim];
+  __shared__ int ylo[7], yhi[7], xlo[7], xhi[7];
+  __shared__ float4 U[kSepMaxDim][kSlice / 4];   // row-weighted partial sums, fp32: [x][128 channels]
+  const int slice = blockIdx.x;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  float roi5[5];
+  roi5[0] = roi_batch ? static_cast<float>(roi_batch[n]) : 0.f;
+  const float* rb = rois + static_cast<long long>(n) * roi_ld + roi_box_off;
+  if (roi_box_off < 0) {
+    rb = rois + static_cast<long long>(n) * roi_ld;
+    roi5[0] = rb[0];
+    rb += 1;
+  }
+  roi5[1] = rb[0]; roi5[2] = rb[1]; roi5[3] = rb[2]; roi5[4] = rb[3];
+  const RoiGeom g = roi_geom(roi5, scale, ph, pw, sampling_ratio);
+  const __half* img = in + static_cast<long long>(g.batch) * in_img_stride + slice * kSlice;
+  if (tid < 7) {
+    ylo[tid] = kSepMaxDim; yhi[tid] = -1;
+    xlo[tid] = kSepMaxDim; xhi[tid] = -1;
+  }
+  __syncthreads();
+  // 1. per-axis weight tables (deterministic: one thread per (bin index, cell), samples in order)
+  for (int i = tid; i < ph * height; i += blockDim.x) {
+    const int p = i / height, r = i - p * height;
+    float wsum = 0.f;
+    for (int iy = 0; iy < g.grid_h; ++iy) {
+      const AxisSample a = axis_sample(sample_coord(g.start_h, p, g.bin_h, iy, g.grid_h), height);
+      if (a.lo == r) wsum += a.wlo;
+      if (a.hi == r) wsum += a.whi;
+    }
+    Wy[p][r] = wsum;
+    if (wsum != 0.f) {
+      atomicMin(&ylo[p], r);
+      atomicMax(&yhi[p], r);
+    }
+  }
+  for (int i = tid; i < pw * width; i += blockDim.x) {
+    const int p = i / width, c = i - p * width;
+    float wsum = 0.f;
+    for (int ix = 0; ix < g.grid_w; ++ix) {
+      const AxisSample a = axis_sample(sample_coord(g.start_w, p, g.bin_w, ix, g.grid_w), width);
+      if (a.lo == c) wsum += a.wlo;
+      if (a.hi == c) wsum += a.whi;
+    }
+    Wx[p][c] = wsum;
+    if (wsum != 0.f) {
+      atomicMin(&xlo[p], c);
+      atomicMax(&xhi[p], c);
+    }
+  }
+  __syncthreads();
+  int c_first = kSepMaxDim, c_last = -1;          // columns any bin-column needs
+  for (int p = 0; p < pw; ++p) {
+    c_first = min(c_first, xlo[p]);
+    c_last = max(c_last, xhi[p]);
+  }
+  const int q = tid & 15, worker = tid >> 4;
+  const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
+  __half* obase = out + static_cast<long long>(n) * out_roi_stride + slice * kSlice + q * 8;
+  for (int phi = 0; phi < ph; ++phi) {
+    // 2. row pass: U[x] = sum_y Wy[phi][y] * f[y, x]   (thread = 8 channels of one column; 16 columns in flight)
+    const int y0 = ylo[phi], y1 = yhi[phi];
+    for (int x = c_first + worker; x <= c_last; x += 16) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      const __half* col = img + static_cast<long long>(x) * channels + q * 8;
+      const long long row_stride = static_cast<long long>(width) * channels;
+      for (int y = y0; y <= y1; y += 4) {          // four rows in flight per thread (L2 latency)
+        uint4 v[4];
+        float w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool live = y + j <= y1;
+          w[j] = live ? Wy[phi][y + j] : 0.f;
+          v[j] = ldg_u4(col + static_cast<long long>(live ? y + j : y1) * row_stride);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t* pv = &v[j].x;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = h2_to_f2(pv[e]);
+            acc[2 * e] = fmaf(w[j], f.x, acc[2 * e]);
+            acc[2 * e + 1] = fmaf(w[j], f.y, acc[2 * e + 1]);
+          }
+        }
+      }
+      U[x][q * 2] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      U[x][q * 2 + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    __syncthreads();
+    // 3. column pass: one thread per (bin column, 8 channels)
+    if (worker < pw) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      for (int x = xlo[worker]; x <= xhi[worker]; ++x) {
+        const float w = Wx[worker][x];
+        const float4 u0 = U[x][q * 2], u1 = U[x][q * 2 + 1];
+        acc[0] = fmaf(w, u0.x, acc[0]); acc[1] = fmaf(w, u0.y, acc[1]);
+        acc[2] = fmaf(w, u0.z, acc[2]); acc[3] = fmaf(w, u0.w, acc[3]);
+        acc[4] = fmaf(w, u1.x, acc[4]); acc[5] = fmaf(w, u1.y, acc[5]);
+        acc[6] = fmaf(w, u1.z, acc[6]); acc[7] = fmaf(w, u1.w, acc[7]);
+      }
+      uint4 o;
+      o.x = f2_to_h2(acc[0] * inv_count, acc[1] * inv_count); o.y = f2_to_h2(acc[2] * inv_count, acc[3] * inv_count);
+      o.z = f2_to_h2(acc[4] * inv_count, acc[5] * inv_count); o.w = f2_to_h2(acc[6] * inv_count, acc[7] * inv_count);
+      *reinterpret_cast<uint4*>(obase + static_cast<long long>(phi * pw + worker) * channels) = o;
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T>
 static int roi_align_nhwc_launch(const T* input, int channels, int height, int width, long long in_img_stride,
                                  const float* rois, int roi_ld, int roi_box_off, const int* roi_batch, int num_rois,
@@ -464,6 +600,15 @@ extern "C" int mega_roi_align_forward_nhwc_f16(const void* input, int channels, 
   const bool fast = (channels % 128) == 0 && pooled_h <= 7 && pooled_w <= 7 &&
                     (reinterpret_cast<uintptr_t>(input) & 15) == 0 && (reinterpret_cast<uintptr_t>(output) & 15) == 0 &&
                     (out_roi_stride % 8) == 0 && (in_img_stride % 8) == 0;
+  if (fast && height <= kSepMaxDim && width <= kSepMaxDim && g_roi_separable) {
+    if (num_rois == 0) return MEGA_OK;
+    dim3 grid(channels / 128, num_rois);
+    roi_align_nhwc_f16_sep_kernel<<<grid, 256, 0, stream>>>(
+        static_cast<const __half*>(input), channels, height, width, in_img_stride, rois, roi_ld, roi_box_off, roi_batch,
+        spatial_scale, pooled_h, pooled_w, sampling_ratio, static_cast<__half*>(output), out_roi_stride);
+    MEGA_CUDA_CHECK(cudaGetLastError());
+    return MEGA_OK;
+  }
   if (fast) {
     if (num_rois == 0) return MEGA_OK;
     static bool configured = false;
