@@ -398,6 +398,7 @@ roi_align_nhwc_f16_fast_kernel(const __half* __restrict__ in, int channels, int 
 // the row pass: rois larger than the shared-memory cache of the kernel above - the common case for VID objects - get
 // ~4x fewer loads and FMAs. Same skipping (samples outside [-1, size]) and clamping rules, applied per axis.
 constexpr int kSepMaxDim = 64;
+constexpr int kSepMaxGrid = 16;    // samples per bin and axis kept in the coordinate tables (else computed inline)
 // MEGA_B200_ROI_SEPARABLE=0 keeps the per-sample kernel above for every roi
 static const bool g_roi_separable = [] {
   const char* e = getenv("MEGA_B200_ROI_SEPARABLE");
@@ -411,6 +412,7 @@ roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int h
                               __half* __restrict__ out, long long out_roi_stride) {
   constexpr int kSlice = kRoiSliceBytes / 2;     // 128 channels per CTA
   __shared__ float Wy[7][kSepMaxDim], Wx[7][kSepMaxDim];
+  __shared__ AxisSample ys[7 * kSepMaxGrid], xs[7 * kSepMaxGrid];
   __shared__ int ylo[7], yhi[7], xlo[7], xhi[7];
   __shared__ float4 U[kSepMaxDim][kSlice / 4];   // row-weighted partial sums, fp32: [x][128 channels]
   const int slice = blockIdx.x;
@@ -432,12 +434,22 @@ roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int h
     xlo[tid] = kSepMaxDim; xhi[tid] = -1;
   }
   __syncthreads();
-  // 1. per-axis weight tables (deterministic: one thread per (bin index, cell), samples in order)
+  // 1. per-axis weight tables. First every sample coordinate once (7 x grid entries per axis), then one thread per
+  //    (bin index, cell) adds up the samples that touch its cell, in sample order (deterministic, no float atomics).
+  const bool tabled = g.grid_h <= kSepMaxGrid && g.grid_w <= kSepMaxGrid;
+  if (tabled) {
+    for (int i = tid; i < ph * g.grid_h; i += blockDim.x)
+      ys[i] = axis_sample(sample_coord(g.start_h, i / g.grid_h, g.bin_h, i % g.grid_h, g.grid_h), height);
+    for (int i = tid; i < pw * g.grid_w; i += blockDim.x)
+      xs[i] = axis_sample(sample_coord(g.start_w, i / g.grid_w, g.bin_w, i % g.grid_w, g.grid_w), width);
+    __syncthreads();
+  }
   for (int i = tid; i < ph * height; i += blockDim.x) {
     const int p = i / height, r = i - p * height;
     float wsum = 0.f;
     for (int iy = 0; iy < g.grid_h; ++iy) {
-      const AxisSample a = axis_sample(sample_coord(g.start_h, p, g.bin_h, iy, g.grid_h), height);
+      const AxisSample a = tabled ? ys[p * g.grid_h + iy]
+                                  : axis_sample(sample_coord(g.start_h, p, g.bin_h, iy, g.grid_h), height);
       if (a.lo == r) wsum += a.wlo;
       if (a.hi == r) wsum += a.whi;
     }
@@ -451,7 +463,8 @@ roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int h
     const int p = i / width, c = i - p * width;
     float wsum = 0.f;
     for (int ix = 0; ix < g.grid_w; ++ix) {
-      const AxisSample a = axis_sample(sample_coord(g.start_w, p, g.bin_w, ix, g.grid_w), width);
+      const AxisSample a = tabled ? xs[p * g.grid_w + ix]
+                                  : axis_sample(sample_coord(g.start_w, p, g.bin_w, ix, g.grid_w), width);
       if (a.lo == c) wsum += a.wlo;
       if (a.hi == c) wsum += a.whi;
     }
