@@ -282,6 +282,52 @@ int mega_deform_psroi_pooling_forward(const float* input, const float* rois, con
                                       int sample_per_part, float trans_std, int num_classes, float* out,
                                       float* top_count, void* stream);
 
+/* ================================================================================================ ABI v4
+ * Training-side / non-VID half of `mega_core._C` (csrc/vision.cpp:9-25): the backward ops and ROIPool. None of them is
+ * on the inference hot path; they complete the 14-function operator surface. Scatter targets
+ * (grad_input, trans_grad, and `out` of mega_channel_sum_nchw) are ACCUMULATED into with red.global.add.f32 and must be
+ * initialised by the caller (the reference allocates them with at::zeros / torch.zeros_like). */
+
+/* `_C.roi_align_backward` (csrc/ROIAlign.h:27-45 -> ROIAlign_cuda.cu:178-246, :302-346): grad [K,C,ph,pw], rois [K,5]
+ * -> grad_input [batch,C,H,W] (zero-initialised by the caller). */
+int mega_roi_align_backward_nchw(const float* grad, const float* rois, int num_rois, float spatial_scale, int pooled_h,
+                                 int pooled_w, int batch, int channels, int height, int width, int sampling_ratio,
+                                 float* grad_input, void* stream);
+
+/* `_C.roi_pool_forward` / `_C.roi_pool_backward` (csrc/ROIPool.h:11-47 -> ROIPool_cuda.cu:16-202): max pooling over
+ * integer bins; argmax [K,C,ph,pw] int32 = offset inside the (batch, c) plane, -1 for an empty bin. */
+int mega_roi_pool_forward(const float* input, const float* rois, int num_rois, float spatial_scale, int channels,
+                          int height, int width, int pooled_h, int pooled_w, float* output, int* argmax, void* stream);
+int mega_roi_pool_backward(const float* grad, const int* argmax, const float* rois, int num_rois, int channels,
+                           int height, int width, int pooled_h, int pooled_w, float* grad_input, void* stream);
+
+/* Deformable convolution backward, v1 and modulated (csrc/deform_conv.h:45-113, :152-190). Column matrices use the
+ * reference's own layout cols[k][b*ldp + p], k = c*kh*kw + i*kw + j, p = h_col*Wo + w_col, ldp >= Ho*Wo (pad to a
+ * multiple of 4 so that a row is a TMA-legal GEMM operand; padding columns are not written -- zero them once).
+ *   mega_deform_im2col_kq     : bilinear im2col of `input` (x mask when mask != NULL) into that layout: the B operand
+ *                               of grad_weight = grad_out . cols^T;
+ *   mega_deform_col2im_fused  : given gcols = weight^T . grad_out in that layout, ONE pass that produces grad_offset
+ *                               (assigned), grad_mask (assigned; mask/grad_mask both NULL for v1) and scatters
+ *                               grad_input (accumulated) -- the reference's deformable_col2im_coord + deformable_col2im
+ *                               (deform_conv_kernel_cuda.cu:292-338, :375-426, :662-712, :714-780);
+ *   mega_channel_sum_nchw     : out[c] += sum_{b,p} x[b,c,p] -- grad_bias (deform_conv_cuda.cu:667-672). */
+int mega_deform_im2col_kq(const float* input, const float* offset, const float* mask, int batch, int channels,
+                          int height, int width, int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w,
+                          int dil_h, int dil_w, int deformable_group, int ldp, float* cols, void* stream);
+int mega_deform_col2im_fused(const float* gcols, const float* input, const float* offset, const float* mask, int batch,
+                             int channels, int height, int width, int kh, int kw, int pad_h, int pad_w, int stride_h,
+                             int stride_w, int dil_h, int dil_w, int deformable_group, int ldp, float* grad_input,
+                             float* grad_offset, float* grad_mask, void* stream);
+int mega_channel_sum_nchw(const float* x, int batch, int channels, int plane, float* out, void* stream);
+
+/* `_C.deform_psroi_pooling_backward` (csrc/deform_pool.h:41-69 -> deform_pool_kernel_cuda.cu:144-280): accumulates
+ * input_grad [N,C,H,W] and trans_grad [K,2*num_classes,part,part] (trans / trans_grad may be NULL when no_trans). */
+int mega_deform_psroi_pooling_backward(const float* out_grad, const float* input, const float* rois, const float* trans,
+                                       const float* top_count, int num_rois, int channels, int height, int width,
+                                       int no_trans, float spatial_scale, int output_dim, int group_size,
+                                       int pooled_size, int part_size, int sample_per_part, float trans_std,
+                                       int num_classes, float* input_grad, float* trans_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

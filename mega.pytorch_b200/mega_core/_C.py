@@ -125,18 +125,182 @@ def deform_psroi_pooling_forward(input, bbox, trans, out, top_count, no_trans, s
         "mega_deform_psroi_pooling_forward")
 
 
-def _not_yet(name):
-    def f(*a, **k):
-        raise NotImplementedError("mega_core._C.%s: training-side / non-VID op, outside the inference hot path "
-                                  "(SURVEY.md section 8f)" % name)
-    f.__name__ = name
-    return f
+def roi_align_backward(grad, rois, spatial_scale, pooled_height, pooled_width, batch_size, channels, height, width,
+                       sampling_ratio):
+    """(csrc/ROIAlign.h:27-45) grad [K,C,ph,pw], rois [K,5] -> grad_input [batch,C,H,W] (newly allocated, zeros + scatter)"""
+    _cuda_only("roi_align_backward", grad, rois)
+    grad_input = torch.zeros(int(batch_size), int(channels), int(height), int(width), device=grad.device)
+    if grad.numel() == 0:                                   # ROIAlign_cuda.cu:324-327
+        return grad_input
+    grad = grad.contiguous().float()
+    rois = rois.contiguous().float()
+    _lib.check(_lib.lib.mega_roi_align_backward_nchw(
+        _lib.ptr(grad), _lib.ptr(rois), rois.shape[0], float(spatial_scale), int(pooled_height), int(pooled_width),
+        int(batch_size), int(channels), int(height), int(width), int(sampling_ratio), _lib.ptr(grad_input),
+        _lib.stream_ptr()), "mega_roi_align_backward_nchw")
+    return grad_input
 
 
-roi_align_backward = _not_yet("roi_align_backward")
-roi_pool_forward = _not_yet("roi_pool_forward")
-roi_pool_backward = _not_yet("roi_pool_backward")
-deform_conv_backward_input = _not_yet("deform_conv_backward_input")
-deform_conv_backward_parameters = _not_yet("deform_conv_backward_parameters")
-modulated_deform_conv_backward = _not_yet("modulated_deform_conv_backward")
-deform_psroi_pooling_backward = _not_yet("deform_psroi_pooling_backward")
+def roi_pool_forward(input, rois, spatial_scale, pooled_height, pooled_width):
+    """(csrc/ROIPool.h:11-24) -> (output [K,C,ph,pw], argmax int32 [K,C,ph,pw])"""
+    _cuda_only("roi_pool_forward", input, rois)
+    input = input.contiguous().float()
+    rois = rois.contiguous().float()
+    k, (n, c, h, w) = rois.shape[0], input.shape
+    out = torch.empty(k, c, int(pooled_height), int(pooled_width), device=input.device)
+    argmax = torch.zeros(k, c, int(pooled_height), int(pooled_width), device=input.device, dtype=torch.int32)
+    if out.numel():
+        _lib.check(_lib.lib.mega_roi_pool_forward(_lib.ptr(input), _lib.ptr(rois), k, float(spatial_scale), c, h, w,
+                                                  int(pooled_height), int(pooled_width), _lib.ptr(out),
+                                                  _lib.ptr(argmax), _lib.stream_ptr()), "mega_roi_pool_forward")
+    return out, argmax
+
+
+def roi_pool_backward(grad, input, rois, argmax, spatial_scale, pooled_height, pooled_width, batch_size, channels,
+                      height, width):
+    """(csrc/ROIPool.h:26-47) -> grad_input [batch,C,H,W]"""
+    _cuda_only("roi_pool_backward", grad, rois, argmax)
+    grad_input = torch.zeros(int(batch_size), int(channels), int(height), int(width), device=grad.device)
+    if grad.numel() == 0:
+        return grad_input
+    grad = grad.contiguous().float()
+    rois = rois.contiguous().float()
+    argmax = argmax.contiguous().to(torch.int32)
+    _lib.check(_lib.lib.mega_roi_pool_backward(_lib.ptr(grad), _lib.ptr(argmax), _lib.ptr(rois), rois.shape[0],
+                                               int(channels), int(height), int(width), int(pooled_height),
+                                               int(pooled_width), _lib.ptr(grad_input), _lib.stream_ptr()),
+               "mega_roi_pool_backward")
+    return grad_input
+
+
+def _writable(name, t):
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        raise RuntimeError("%s must be a contiguous float32 tensor (it is written in place)" % name)
+
+
+def _dcn_backward(input, offset, mask, weight_shape, weight, grad_output, grad_input, grad_offset, grad_mask,
+                  grad_weight, grad_bias, scale, kh, kw, sh, sw, ph, pw, dh, dw, group, deformable_group):
+    """Backward of (modulated) deformable convolution on the reference's column layout cols[k][b*ldp + p]
+    (deform_conv_cuda.cu:300-302):
+      input / offset / mask gradients: gcols = W^T . grad_out (one tcgen05 GEMM per group), then ONE fused pass
+        (mega_deform_col2im_fused) instead of the reference's col2im_coord + col2im kernels;
+      weight gradient: cols = deformable im2col of the input, grad_W += scale * grad_out . cols^T (one GEMM per group
+        with K = batch * Ho * Wo, where the reference loops over im2col_step slices of the batch);
+      bias gradient: per-channel sum of grad_out.
+    Operand re-layouts (NCHW <-> pixel-major, zero padding of Ho*Wo to a multiple of 4 for TMA) are torch copies."""
+    _cuda_only("deform_conv_backward", input, offset, grad_output)
+    if not input.is_contiguous():
+        raise RuntimeError("input tensor has to be contiguous")                 # deform_conv_cuda.cu:586
+    b, c, h, w = input.shape
+    cout, cpg_w = weight_shape[0], weight_shape[1]
+    if tuple(weight_shape[2:]) != (kh, kw):
+        raise RuntimeError("Input shape and kernel shape wont match: (%d x %d vs %d x %d)." % (kh, kw, weight_shape[2], weight_shape[3]))
+    if c != cpg_w * group:
+        raise RuntimeError("Input shape and kernel channels wont match: (%d vs %d)." % (c, cpg_w * group))
+    ho = (h + 2 * ph - (dh * (kh - 1) + 1)) // sh + 1
+    wo = (w + 2 * pw - (dw * (kw - 1) + 1)) // sw + 1
+    if tuple(grad_output.shape) != (b, cout, ho, wo):
+        raise RuntimeError("invalid spatial size of gradOutput: expected %s, got %s" % ((b, cout, ho, wo), tuple(grad_output.shape)))
+    if offset.shape[0] != b:
+        raise RuntimeError("invalid batch size of offset")                      # deform_conv_cuda.cu:306
+    cog = cout // group
+    if cog % 4:
+        raise RuntimeError("deform_conv backward (B200 build): Cout / group must be a multiple of 4")
+    taps, pt = kh * kw, ho * wo
+    ldp = (pt + 3) // 4 * 4
+    kg = cpg_w * taps
+    dev = input.device
+    x = input.float()
+    off = offset.contiguous().float()
+    msk = mask.contiguous().float() if mask is not None else None
+    go = grad_output.contiguous().float().view(b, cout, pt)
+    geo = (b, c, h, w, kh, kw, ph, pw, sh, sw, dh, dw, deformable_group, ldp)
+    if grad_input is not None:
+        _writable("grad_input", grad_input)
+        _writable("grad_offset", grad_offset)
+        if grad_mask is not None:
+            _writable("grad_mask", grad_mask)
+        go_t = torch.zeros(b, ldp, cout, device=dev)                # pixel-major grad_out: [b*ldp, cout]
+        go_t[:, :pt] = go.transpose(1, 2)
+        go_t = go_t.view(b * ldp, cout)
+        gcols = torch.empty(c * taps, b * ldp, device=dev)
+        w2 = weight.float().reshape(cout, kg)
+        for g in range(group):
+            wt_g = w2[g * cog:(g + 1) * cog].t().contiguous()                   # [kg, cog]
+            ops.linear(wt_g, go_t[:, g * cog:(g + 1) * cog], gcols[g * kg:(g + 1) * kg])
+        _lib.check(_lib.lib.mega_deform_col2im_fused(_lib.ptr(gcols), _lib.ptr(x), _lib.ptr(off), _lib.ptr(msk), *geo,
+                                                     _lib.ptr(grad_input), _lib.ptr(grad_offset), _lib.ptr(grad_mask),
+                                                     _lib.stream_ptr()), "mega_deform_col2im_fused")
+    if grad_weight is not None:
+        _writable("grad_weight", grad_weight)
+        cols = torch.zeros(c * taps, b * ldp, device=dev)
+        _lib.check(_lib.lib.mega_deform_im2col_kq(_lib.ptr(x), _lib.ptr(off), _lib.ptr(msk), *geo, _lib.ptr(cols),
+                                                  _lib.stream_ptr()), "mega_deform_im2col_kq")
+        go_p = torch.zeros(cout, b, ldp, device=dev)                # channel-major grad_out: [cout, b*ldp]
+        go_p[:, :, :pt] = go.permute(1, 0, 2)
+        go_p = go_p.view(cout, b * ldp)
+        kgp = (kg + 3) // 4 * 4
+        tmp = torch.empty(cout, kgp, device=dev)
+        for g in range(group):
+            ops.linear(go_p[g * cog:(g + 1) * cog], cols[g * kg:(g + 1) * kg], tmp[g * cog:(g + 1) * cog, :kg])
+        grad_weight.view(cout, kg).add_(tmp[:, :kg], alpha=float(scale))        # addmm_(..., beta=1, alpha=scale)
+    if grad_bias is not None:
+        _writable("grad_bias", grad_bias)
+        _lib.check(_lib.lib.mega_channel_sum_nchw(_lib.ptr(go), b, cout, pt, _lib.ptr(grad_bias), _lib.stream_ptr()),
+                   "mega_channel_sum_nchw")
+
+
+def deform_conv_backward_input(input, offset, gradOutput, gradInput, gradOffset, weight, columns, kW, kH, dW, dH, padW,
+                               padH, dilationW, dilationH, group, deformable_group, im2col_step):
+    """(csrc/deform_conv.h:45-77) v1: accumulates into `gradInput`, assigns `gradOffset` (both caller-allocated,
+    deform_conv_func.py:87-88), returns 1. `columns` / im2col_step are the reference's scratch management: unused."""
+    if not weight.is_contiguous():
+        raise RuntimeError("weight tensor has to be contiguous")
+    _dcn_backward(input.contiguous(), offset, None, weight.shape, weight, gradOutput, gradInput, gradOffset, None, None,
+                  None, 1.0, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group, deformable_group)
+    return 1
+
+
+def deform_conv_backward_parameters(input, offset, gradOutput, gradWeight, columns, ones, kW, kH, dW, dH, padW, padH,
+                                    dilationW, dilationH, group, deformable_group, scale, im2col_step):
+    """(csrc/deform_conv.h:79-113) v1: gradWeight += scale * grad_out . cols^T, returns 1"""
+    _dcn_backward(input.contiguous(), offset, None, gradWeight.shape, None, gradOutput, None, None, None, gradWeight,
+                  None, scale, kH, kW, dH, dW, padH, padW, dilationH, dilationW, group, deformable_group)
+    return 1
+
+
+def modulated_deform_conv_backward(input, weight, bias, ones, offset, mask, columns, grad_input, grad_weight, grad_bias,
+                                   grad_offset, grad_mask, grad_output, kernel_h, kernel_w, stride_h, stride_w, pad_h,
+                                   pad_w, dilation_h, dilation_w, group, deformable_group, with_bias):
+    """(csrc/deform_conv.h:152-190) v2: accumulates grad_input / grad_weight / grad_bias, assigns grad_offset /
+    grad_mask (all caller-allocated, deform_conv_func.py:206-210)"""
+    if not weight.is_contiguous():
+        raise RuntimeError("weight tensor has to be contiguous")                # deform_conv_cuda.cu:587
+    _dcn_backward(input, offset, mask, weight.shape, weight, grad_output, grad_input, grad_offset, grad_mask,
+                  grad_weight, grad_bias if with_bias else None, 1.0, kernel_h, kernel_w, stride_h, stride_w, pad_h,
+                  pad_w, dilation_h, dilation_w, group, deformable_group)
+
+
+def deform_psroi_pooling_backward(out_grad, input, bbox, trans, top_count, input_grad, trans_grad, no_trans,
+                                  spatial_scale, output_dim, group_size, pooled_size, part_size, sample_per_part,
+                                  trans_std):
+    """(csrc/deform_pool.h:41-69) accumulates `input_grad` and `trans_grad` in place"""
+    _cuda_only("deform_psroi_pooling_backward", out_grad, input, bbox, top_count, input_grad)
+    if not out_grad.is_contiguous():
+        raise RuntimeError("out_grad tensor has to be contiguous")              # deform_pool_cuda.cu:66
+    if not input.is_contiguous():
+        raise RuntimeError("input tensor has to be contiguous")
+    n, c, h, w = input.shape
+    if bbox.shape[0] != out_grad.shape[0]:
+        raise RuntimeError("Output shape and bbox number wont match: (%d vs %d)." % (out_grad.shape[0], bbox.shape[0]))
+    _writable("input_grad", input_grad)
+    num_classes = 1 if no_trans else trans.shape[1] // 2
+    tr = tg = None
+    if not no_trans:
+        _writable("trans_grad", trans_grad)
+        tr, tg = trans.contiguous().float(), trans_grad
+    _lib.check(_lib.lib.mega_deform_psroi_pooling_backward(
+        _lib.ptr(out_grad.float()), _lib.ptr(input.float()), _lib.ptr(bbox.contiguous().float()), _lib.ptr(tr),
+        _lib.ptr(top_count.contiguous().float()), bbox.shape[0], c, h, w, int(bool(no_trans)), float(spatial_scale),
+        int(output_dim), int(group_size), int(pooled_size), int(part_size), int(sample_per_part), float(trans_std),
+        num_classes, _lib.ptr(input_grad), _lib.ptr(tg), _lib.stream_ptr()), "mega_deform_psroi_pooling_backward")

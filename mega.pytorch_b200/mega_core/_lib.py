@@ -178,6 +178,23 @@ lib.mega_deform_psroi_pooling_forward.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i,
                                                   _vp, _vp]
 lib.mega_deform_psroi_pooling_forward.restype = _i
 
+# ---- ABI v4: training-side ops (csrc/train_ops.cu)
+lib.mega_roi_align_backward_nchw.argtypes = [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]
+lib.mega_roi_align_backward_nchw.restype = _i
+lib.mega_roi_pool_forward.argtypes = [_vp, _vp, _i, _f, _i, _i, _i, _i, _i, _vp, _vp, _vp]
+lib.mega_roi_pool_forward.restype = _i
+lib.mega_roi_pool_backward.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]
+lib.mega_roi_pool_backward.restype = _i
+lib.mega_deform_im2col_kq.argtypes = [_vp, _vp, _vp] + [_i] * 14 + [_vp, _vp]
+lib.mega_deform_im2col_kq.restype = _i
+lib.mega_deform_col2im_fused.argtypes = [_vp, _vp, _vp, _vp] + [_i] * 14 + [_vp, _vp, _vp, _vp]
+lib.mega_deform_col2im_fused.restype = _i
+lib.mega_channel_sum_nchw.argtypes = [_vp, _i, _i, _i, _vp, _vp]
+lib.mega_channel_sum_nchw.restype = _i
+lib.mega_deform_psroi_pooling_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _i,
+                                                   _f, _i, _vp, _vp, _vp]
+lib.mega_deform_psroi_pooling_backward.restype = _i
+
 EXPORTS = [
     "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm", "mega_conv_gemm_tf32", "mega_conv_gemm_workspace_bytes", "mega_set_tf32_rounding",
     "mega_conv_chain_plan_bytes", "mega_conv_chain_encode", "mega_conv_chain_launch", "mega_conv_chain_set_trace",
@@ -188,4 +205,6 @@ EXPORTS = [
     "mega_deform_im2col", "mega_deform_psroi_pooling_forward",
     "mega_roi_align_forward_nhwc_f16", "mega_stem_im2col_f16", "mega_maxpool3x3s2_nhwc_f16", "mega_relation_softmax_f16", "mega_relation_softmax_pe",
     "mega_stem_prep", "mega_fgfa_pool_image", "mega_fgfa_build_pairs", "mega_avgpool2_nhwc", "mega_fgfa_aggregate",
+    "mega_roi_align_backward_nchw", "mega_roi_pool_forward", "mega_roi_pool_backward", "mega_deform_im2col_kq",
+    "mega_deform_col2im_fused", "mega_channel_sum_nchw", "mega_deform_psroi_pooling_backward",
 ]

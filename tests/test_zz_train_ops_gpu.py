@@ -1,0 +1,133 @@
+"""GPU parity of the training-side half of `mega_core._C` through the C ABI: roi_align_backward, roi_pool_forward /
+backward, deform_conv_backward_input / _parameters, modulated_deform_conv_backward, deform_psroi_pooling_backward
+(8f row 3). Oracles: oracle/train_ops_oracle.py (autograd of forward restatements anchored in
+tests/test_train_ops_cpu.py). Scatter kernels accumulate with red.global.add.f32 in an unspecified order, as the
+reference's atomicAdd does, so float results are compared to 1e-5-level tolerances; arg-max indices are exact.
+(This file sorts last on purpose: these kernels were added after the last GPU session of round 1 and are verified on
+the CPU through their host build only; a failure here must not hide the hot-path tests.)"""
+import os
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def _rois(g, k, n_img, w_img, h_img):
+    x1 = torch.rand(k, generator=g) * w_img * 0.7 - 10
+    y1 = torch.rand(k, generator=g) * h_img * 0.7 - 10
+    bw = torch.rand(k, generator=g) * w_img * 0.6 + 1
+    bh = torch.rand(k, generator=g) * h_img * 0.6 + 1
+    b = torch.randint(0, n_img, (k,), generator=g).float()
+    return torch.stack([b, x1, y1, x1 + bw, y1 + bh], 1)
+
+
+@pytest.mark.parametrize("sr,c", [(0, 5), (2, 19), (0, 16)])
+def test_roi_align_backward(cuda_dev, sr, c):
+    import train_ops_oracle as to
+    from mega_core import _C
+    g = torch.Generator().manual_seed(31 + c)
+    n, h, w, k = 2, 12, 17, 6
+    rois = _rois(g, k, n, w * 16, h * 16)
+    rois[5] = torch.tensor([1.0, 250.0, 170.0, 252.0, 500.0])
+    grad = torch.randn(k, c, 7, 7, generator=g)
+    ref = to.roi_align_backward(grad, rois, 1 / 16.0, 7, 7, n, c, h, w, sr)
+    got = _C.roi_align_backward(grad.to(cuda_dev), rois.to(cuda_dev), 1 / 16.0, 7, 7, n, c, h, w, sr).cpu()
+    assert got.shape == (n, c, h, w)
+    assert torch.allclose(got, ref, atol=2e-5, rtol=1e-5)
+    empty = _C.roi_align_backward(torch.zeros(0, c, 7, 7, device=cuda_dev), torch.zeros(0, 5, device=cuda_dev),
+                                  1 / 16.0, 7, 7, n, c, h, w, sr)
+    assert empty.shape == (n, c, h, w) and empty.abs().sum().item() == 0
+
+
+def test_roi_pool_forward_backward(cuda_dev):
+    import train_ops_oracle as to
+    from mega_core import _C
+    g = torch.Generator().manual_seed(41)
+    n, c, h, w, k = 2, 6, 13, 19, 7
+    feat = torch.randn(n, c, h, w, generator=g)
+    rois = _rois(g, k, n, w * 16, h * 16)
+    rois[6] = torch.tensor([0.0, 400.0, 300.0, 420.0, 310.0])
+    ref, ref_arg = to.roi_pool(feat, rois, 1 / 16.0, 7, 7)
+    out, arg = _C.roi_pool_forward(feat.to(cuda_dev), rois.to(cuda_dev), 1 / 16.0, 7, 7)
+    assert arg.dtype == torch.int32
+    assert torch.equal(out.cpu(), ref) and torch.equal(arg.cpu(), ref_arg)
+    grad = torch.randn(k, c, 7, 7, generator=g)
+    gin = _C.roi_pool_backward(grad.to(cuda_dev), feat.to(cuda_dev), rois.to(cuda_dev), arg, 1 / 16.0, 7, 7, n, c, h, w)
+    assert torch.allclose(gin.cpu(), to.roi_pool_backward(grad, feat, rois, 1 / 16.0, 7, 7), atol=1e-6)
+
+
+def _rel_err(a, b):
+    return ((a - b).abs().max() / b.pow(2).mean().sqrt().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("modulated,groups,dg,stride,pad,dil", [(False, 1, 1, 1, 1, 1), (True, 1, 1, 1, 1, 1),
+                                                                (True, 2, 2, 2, 1, 1), (False, 2, 4, 1, 2, 2)])
+def test_deform_conv_backward(cuda_dev, modulated, groups, dg, stride, pad, dil):
+    import train_ops_oracle as to
+    from mega_core import _C
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(60 + groups + dg)
+    b, c, h, w, cout, k = 2, 32, 19, 23, 64, 3
+    x = torch.randn(b, c, h, w, generator=g)
+    wt = torch.randn(cout, c // groups, k, k, generator=g) / (c * 9 / groups) ** 0.5
+    bias = torch.randn(cout, generator=g) if modulated else None
+    ho = (h + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    wo = (w + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    off = torch.randn(b, dg * 2 * k * k, ho, wo, generator=g) * 2.0
+    mask = torch.rand(b, dg * k * k, ho, wo, generator=g) if modulated else None
+    go = torch.randn(b, cout, ho, wo, generator=g)
+    ref = to.deform_conv2d_grads(x, off, mask, wt, bias, go, (stride, stride), (pad, pad), (dil, dil), groups, dg)
+    d = cuda_dev
+    xd, offd, wtd, god = x.to(d), off.to(d), wt.to(d), go.to(d)
+    gin, goff, gw = torch.zeros_like(xd), torch.zeros_like(offd), torch.zeros_like(wtd)
+    with ops.precision("fp32x3"):
+        if modulated:
+            maskd, biasd = mask.to(d), bias.to(d)
+            gmask, gb = torch.zeros_like(maskd), torch.zeros_like(biasd)
+            _C.modulated_deform_conv_backward(xd, wtd, biasd, None, offd, maskd, None, gin, gw, gb, goff, gmask, god, k, k,
+                                              stride, stride, pad, pad, dil, dil, groups, dg, True)
+        else:
+            assert _C.deform_conv_backward_input(xd, offd, god, gin, goff, wtd, None, k, k, stride, stride, pad, pad, dil,
+                                                 dil, groups, dg, b) == 1
+            assert _C.deform_conv_backward_parameters(xd, offd, god, gw, None, None, k, k, stride, stride, pad, pad, dil,
+                                                      dil, groups, dg, 1.0, b) == 1
+    torch.cuda.synchronize()
+    assert _rel_err(gin.cpu(), ref["input"]) < 2e-4
+    assert _rel_err(goff.cpu(), ref["offset"]) < 2e-4
+    assert _rel_err(gw.cpu(), ref["weight"]) < 2e-4
+    if modulated:
+        assert _rel_err(gmask.cpu(), ref["mask"]) < 2e-4
+        assert _rel_err(gb.cpu(), ref["bias"]) < 1e-5
+
+
+@pytest.mark.parametrize("no_trans", [True, False])
+def test_deform_psroi_pooling_backward(cuda_dev, no_trans):
+    import train_ops_oracle as to
+    from mega_core import _C
+    g = torch.Generator().manual_seed(3)
+    gs, ps, od, ncls = 3, 3, 4, 2
+    data = torch.randn(2, od * gs * gs, 11, 13, generator=g)
+    rois = torch.tensor([[0, 8.0, 10.0, 120.0, 90.0], [1, 40.2, 33.7, 150.9, 160.1], [0, -10.0, -5.0, 30.0, 20.0],
+                         [1, 300.0, 300.0, 320.0, 330.0]])
+    k = rois.shape[0]
+    trans = torch.randn(k, 2 * ncls, ps, ps, generator=g) * 0.5
+    og = torch.randn(k, od, ps, ps, generator=g)
+    ref_in, ref_tr = to.deform_psroi_pool_grads(data, rois, trans, og, no_trans, 1 / 16.0, od, gs, ps, ps, 4, 0.1)
+    d = cuda_dev
+    out = torch.zeros(k, od, ps, ps, device=d)
+    cnt = torch.zeros(k, od, ps, ps, device=d)
+    _C.deform_psroi_pooling_forward(data.to(d), rois.to(d), trans.to(d), out, cnt, no_trans, 1 / 16.0, od, gs, ps, ps, 4,
+                                    0.1)
+    gin = torch.zeros(data.shape, device=d)
+    gtr = torch.zeros(trans.shape, device=d)
+    _C.deform_psroi_pooling_backward(og.to(d), data.to(d), rois.to(d), trans.to(d), cnt, gin, gtr, no_trans, 1 / 16.0, od,
+                                     gs, ps, ps, 4, 0.1)
+    assert torch.allclose(gin.cpu(), ref_in, atol=2e-5, rtol=1e-4)
+    if no_trans:
+        assert gtr.abs().sum().item() == 0
+    else:
+        assert torch.allclose(gtr.cpu(), ref_tr, atol=2e-4, rtol=1e-3)
