@@ -1,4 +1,5 @@
-"""Layer wrappers with the reference's names (mega_core/layers/__init__.py:4-46), inference side."""
+"""Layer wrappers with the reference's names (mega_core/layers/__init__.py:4-46): nms and the parameter holders here,
+the differentiable `_C` ops (ROIAlign / ROIPool / focal loss / deformable convolution and pooling) in train_ops.py."""
 import torch
 from torch import nn
 
@@ -10,24 +11,10 @@ def nms(boxes, scores, threshold):
     return _C.nms(boxes.float(), scores.float(), threshold)
 
 
-def roi_align(input, rois, output_size, spatial_scale, sampling_ratio):
-    oh, ow = (output_size, output_size) if isinstance(output_size, int) else output_size
-    return _C.roi_align_forward(input.float(), rois.float(), spatial_scale, oh, ow, sampling_ratio)
-
-
-class ROIAlign(nn.Module):
-    """layers/roi_align.py:47-60"""
-
-    def __init__(self, output_size, spatial_scale, sampling_ratio):
-        super().__init__()
-        self.output_size, self.spatial_scale, self.sampling_ratio = output_size, spatial_scale, sampling_ratio
-
-    def forward(self, input, rois):
-        return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio)
-
-    def __repr__(self):
-        return "ROIAlign(output_size=%s, spatial_scale=%s, sampling_ratio=%s)" % (
-            self.output_size, self.spatial_scale, self.sampling_ratio)
+from .train_ops import (ROIAlign, ROIPool, SigmoidFocalLoss, DeformConv, ModulatedDeformConv,  # noqa: E402,F401
+                        ModulatedDeformConvPack, DeformRoIPooling, DeformRoIPoolingPack,
+                        ModulatedDeformRoIPoolingPack, deform_conv, modulated_deform_conv, deform_roi_pooling,
+                        roi_align, roi_pool, sigmoid_focal_loss_cuda, smooth_l1_loss)
 
 
 class FrozenBatchNorm2d(nn.Module):
@@ -43,3 +30,9 @@ class FrozenBatchNorm2d(nn.Module):
 
 
 Conv2d = nn.Conv2d   # the reference's empty-batch-safe subclass (layers/misc.py:30-43) is a parameter holder here
+
+
+__all__ = ["nms", "roi_align", "ROIAlign", "roi_pool", "ROIPool", "smooth_l1_loss", "Conv2d", "FrozenBatchNorm2d",
+           "SigmoidFocalLoss", "deform_conv", "modulated_deform_conv", "DeformConv", "ModulatedDeformConv",
+           "ModulatedDeformConvPack", "deform_roi_pooling", "DeformRoIPooling", "DeformRoIPoolingPack",
+           "ModulatedDeformRoIPoolingPack"]

@@ -260,3 +260,109 @@ def test_C_deform_psroi_backward(cpu_C, no_trans):
     else:
         assert torch.allclose(gtr, ref_tr, atol=2e-4, rtol=1e-3)
         assert ref_tr.abs().sum() > 0
+
+
+# ------------------------------------------------ mega_core.layers autograd wrappers (backward on the host build)
+@pytest.fixture
+def cpu_layers(cpu_C, monkeypatch):
+    """mega_core.layers on CPU tensors: backward ops as in cpu_C; the forward ops that have no host build are stood in
+    by their oracles (test-only), so that the autograd plumbing of layers/train_ops.py can be exercised end to end"""
+    from mega_core import layers
+
+    def roi_align_forward(x, r, scale, ph, pw, sr):
+        return mo.roi_align(x, r, scale, ph, pw, sr)
+
+    def dcn_v1(x, w, off, out, cols, ones, kW, kH, dW, dH, pW, pH, dlW, dlH, group, dg, step):
+        out.copy_(to.deform_conv2d(x, off, None, w, None, (dH, dW), (pH, pW), (dlH, dlW), group, dg))
+        return 1
+
+    def dcn_v2(x, w, b, ones, off, m, out, cols, kh, kw, sh, sw, ph, pw, dh, dw, group, dg, with_bias):
+        out.copy_(to.deform_conv2d(x, off, m, w, b if with_bias else None, (sh, sw), (ph, pw), (dh, dw), group, dg))
+
+    def psroi(x, r, tr, out, cnt, no_trans, scale, od, gs, ps, part, spp, std):
+        o, c = to.deform_psroi_pool(x, r, tr, no_trans, scale, od, gs, ps, part, spp, std)
+        out.copy_(o)
+        cnt.copy_(c)
+    monkeypatch.setattr(cpu_C, "roi_align_forward", roi_align_forward)
+    monkeypatch.setattr(cpu_C, "deform_conv_forward", dcn_v1)
+    monkeypatch.setattr(cpu_C, "modulated_deform_conv_forward", dcn_v2)
+    monkeypatch.setattr(cpu_C, "deform_psroi_pooling_forward", psroi)
+    return layers
+
+
+def test_layers_roi_align_and_pool_autograd(cpu_layers):
+    import torchvision
+    g = torch.Generator().manual_seed(71)
+    feat = torch.randn(2, 6, 12, 17, generator=g)
+    rois = _rois(g, 5, 2, 17 * 16, 12 * 16)
+    wgt = torch.randn(5, 6, 7, 7, generator=g)
+    x = feat.clone().requires_grad_(True)
+    out = cpu_layers.ROIAlign((7, 7), 1 / 16.0, 2)(x, rois)
+    (out * wgt).sum().backward()
+    y = feat.clone().requires_grad_(True)
+    ref = torchvision.ops.roi_align(y, rois, (7, 7), 1 / 16.0, 2, aligned=False)
+    (ref * wgt).sum().backward()
+    assert torch.allclose(out, ref, atol=2e-6) and torch.allclose(x.grad, y.grad, atol=1e-5)
+    x = feat.clone().requires_grad_(True)
+    out = cpu_layers.ROIPool(7, 1 / 16.0)(x, rois)
+    (out * wgt).sum().backward()
+    y = feat.clone().requires_grad_(True)
+    ref = torchvision.ops.roi_pool(y, rois, 7, 1 / 16.0)
+    (ref * wgt).sum().backward()
+    assert torch.equal(out, ref) and torch.allclose(x.grad, y.grad, atol=1e-6)
+
+
+@pytest.mark.parametrize("modulated", [False, True])
+def test_layers_deform_conv_autograd(cpu_layers, modulated):
+    import torchvision
+    case = (modulated, 2, 2, 1, 1, 1, 3)
+    x, off, mask, wt, bias, go, ho, wo = _dcn_inputs(81, *case, c=16, cout=24)
+    mine = [t.clone().requires_grad_(True) if t is not None else None for t in (x, off, mask, wt, bias)]
+    theirs = [t.clone().requires_grad_(True) if t is not None else None for t in (x, off, mask, wt, bias)]
+    if modulated:
+        out = cpu_layers.modulated_deform_conv(mine[0], mine[1], mine[2], mine[3], mine[4], 1, 1, 1, 2, 2)
+    else:
+        out = cpu_layers.deform_conv(mine[0], mine[1], mine[3], 1, 1, 1, 2, 2)
+    ref = torchvision.ops.deform_conv2d(theirs[0], theirs[1], theirs[3], theirs[4], stride=1, padding=1, dilation=1,
+                                        mask=theirs[2])
+    assert torch.allclose(out, ref, atol=1e-4)
+    (out * go).sum().backward()
+    (ref * go).sum().backward()
+    for a, b_ in zip(mine, theirs):
+        if a is not None:
+            assert torch.allclose(a.grad, b_.grad, atol=3e-4, rtol=1e-4)
+
+
+def test_layers_modulated_pack_zero_init_is_half_a_convolution(cpu_layers):
+    """ModulatedDeformConvPack starts with zero offsets and masks sigmoid(0) = 0.5: out = 0.5 * conv(x, w) + b"""
+    torch.manual_seed(5)
+    m = cpu_layers.ModulatedDeformConvPack(8, 12, 3, stride=1, padding=1, deformable_groups=2)
+    with torch.no_grad():
+        m.bias.normal_()
+    x = torch.randn(2, 8, 9, 11, requires_grad=True)
+    out = m(x)
+    ref = 0.5 * torch.nn.functional.conv2d(x, m.weight, None, 1, 1) + m.bias.view(1, -1, 1, 1)
+    assert torch.allclose(out, ref, atol=1e-5)
+    out.sum().backward()
+    assert m.conv_offset_mask.weight.grad is not None and m.weight.grad.abs().sum() > 0 and x.grad is not None
+    gw = torch.autograd.grad(ref.sum(), m.weight)[0]
+    assert torch.allclose(m.weight.grad, gw, atol=1e-4)
+
+
+def test_layers_deform_roi_pooling_autograd(cpu_layers):
+    g = torch.Generator().manual_seed(3)
+    gs, ps, od = 3, 3, 4
+    data = torch.randn(2, od * gs * gs, 11, 13, generator=g)
+    rois = torch.tensor([[0, 8.0, 10.0, 120.0, 90.0], [1, 40.2, 33.7, 150.9, 160.1]])
+    trans = torch.randn(2, 2, ps, ps, generator=g) * 0.5
+    og = torch.randn(2, od, ps, ps, generator=g)
+    x, t = data.clone().requires_grad_(True), trans.clone().requires_grad_(True)
+    out = cpu_layers.DeformRoIPooling(1 / 16.0, ps, od, False, gs, ps, 4, 0.1)(x, rois, t)
+    (out * og).sum().backward()
+    ref_in, ref_tr = to.deform_psroi_pool_grads(data, rois, trans, og, False, 1 / 16.0, od, gs, ps, ps, 4, 0.1)
+    assert torch.allclose(x.grad, ref_in, atol=2e-5, rtol=1e-4) and torch.allclose(t.grad, ref_tr, atol=2e-4, rtol=1e-3)
+    pack = cpu_layers.ModulatedDeformRoIPoolingPack(1 / 16.0, ps, od * gs * gs, False, 1, ps, 4, 0.1, deform_fc_channels=32)
+    y = pack(data.clone().requires_grad_(True), rois)
+    assert y.shape == (2, od * gs * gs, ps, ps)
+    y.sum().backward()
+    assert pack.mask_fc[2].weight.grad is not None

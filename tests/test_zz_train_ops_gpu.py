@@ -131,3 +131,35 @@ def test_deform_psroi_pooling_backward(cuda_dev, no_trans):
         assert gtr.abs().sum().item() == 0
     else:
         assert torch.allclose(gtr.cpu(), ref_tr, atol=2e-4, rtol=1e-3)
+
+
+def test_layers_autograd_on_device(cuda_dev):
+    """mega_core.layers wrappers: forward and backward both on the sm_100a kernels"""
+    import train_ops_oracle as to
+    from mega_core import layers
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(71)
+    feat = torch.randn(2, 6, 12, 17, generator=g)
+    rois = _rois(g, 5, 2, 17 * 16, 12 * 16)
+    wgt = torch.randn(5, 6, 7, 7, generator=g)
+    x = feat.to(cuda_dev).requires_grad_(True)
+    out = layers.ROIAlign((7, 7), 1 / 16.0, 2)(x, rois.to(cuda_dev))
+    (out * wgt.to(cuda_dev)).sum().backward()
+    assert torch.allclose(out.detach().cpu(), to.roi_align(feat, rois, 1 / 16.0, 7, 7, 2), atol=2e-6)
+    assert torch.allclose(x.grad.cpu(), to.roi_align_backward(wgt, rois, 1 / 16.0, 7, 7, 2, 6, 12, 17, 2), atol=2e-5)
+    # ModulatedDeformConvPack starts as 0.5 * conv(x, w) + b (zero offsets, masks sigmoid(0))
+    torch.manual_seed(5)
+    m = layers.ModulatedDeformConvPack(32, 64, 3, stride=1, padding=1, deformable_groups=2).to(cuda_dev)
+    with torch.no_grad():
+        m.bias.normal_()
+    xx = torch.randn(2, 32, 9, 11, device=cuda_dev, requires_grad=True)
+    with ops.precision("fp32x3"):
+        y = m(xx)
+        y.sum().backward()
+    xr = xx.detach().cpu().double().requires_grad_(True)
+    wr = m.weight.detach().cpu().double().requires_grad_(True)
+    ref = 0.5 * torch.nn.functional.conv2d(xr, wr, None, 1, 1) + m.bias.detach().cpu().double().view(1, -1, 1, 1)
+    ref.sum().backward()
+    assert _rel_err(y.detach().cpu(), ref.detach().float()) < 1e-4
+    assert _rel_err(m.weight.grad.cpu(), wr.grad.float()) < 2e-4
+    assert _rel_err(xx.grad.cpu(), xr.grad.float()) < 2e-4
