@@ -55,6 +55,10 @@ def parse():
                     help="contraction arithmetic of the timed engine (EngineConfig.precision)")
     ap.add_argument("--no-strict", action="store_true", help="skip the extra fp32x3 (strict-parity mode) timing")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--wave", action="store_true",
+                    help="N > 1: wavefront schedule (MegaEngine.dist_step_wave: a rank aggregates only its own key frame, "
+                         "memory increments exchanged per stage) instead of the replicated-state dist_step; "
+                         "also MEGA_B200_WAVE=1. Experimental: first GPU run pending")
     ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -171,9 +175,14 @@ def run_b200(args, rank, world):
     pairs_dev = [torch.cat([pool_dev[(i + 12) % 16], pool_dev[(5 * i + 3) % 16]], 0) for i in range(16)]
     pairs_pinned = [torch.cat([pool[(i + 12) % 16], pool[(5 * i + 3) % 16]], 0).pin_memory() for i in range(16)]
 
+    wave = world > 1 and (args.wave or os.environ.get("MEGA_B200_WAVE", "0") == "1")
+
+    def dstep(pair):
+        return eng.dist_step_wave(pair, w, h) if wave else eng.dist_step(pair, w, h)[rank]
+
     def step_dev(i):
         if world > 1:
-            return eng.dist_step(pairs_dev[(i * world + rank) % 16], w, h)[rank]
+            return dstep(pairs_dev[(i * world + rank) % 16])
         return eng.step_batched(pairs_dev[i % 16], w, h)
 
     def step_e2e(i):
@@ -182,7 +191,7 @@ def run_b200(args, rank, world):
             # the call a user of the reference makes, followed by the .to(cpu) of engine/inference.py:43
             return model(infos_next(i))[0].to("cpu")
         static_in.copy_(pairs_pinned[(i * world + rank) % 16], non_blocking=True)
-        det = eng.dist_step(static_in, w, h)[rank]
+        det = dstep(static_in)
         return det.to_host()[0]
 
     launches0 = ops.LAUNCHES[0]
@@ -246,7 +255,10 @@ def run_b200(args, rank, world):
         "config": {"workload": workload(args), "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
                    "parallelism": ("frame-parallel over %d GPUs: per-frame branch on the frame's owner, NCCL all-gather of "
                                    "ROI-feature payloads, memory-feeding rows of the aggregation replicated, key-frame "
-                                   "rows / predictor / post-processing on the owner" % world) if world > 1 else "single GPU",
+                                   "rows / predictor / post-processing on the owner" % world) if world > 1 and not wave else
+                                  ("frame-parallel over %d GPUs, wavefront schedule: per-frame branch and the whole aggregation "
+                                   "of a key frame on its owner, NCCL all-gather of the ROI-feature payloads + one all-gather of "
+                                   "the memory increments per relation stage" % world) if wave else "single GPU",
                    "cuda_graph": bool(eng._graphs), "precision": args.precision,
                    "l2": "per-step working set (0.7 GB fp32 weights + >0.5 GB activations) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,

@@ -163,3 +163,50 @@ def test_layers_autograd_on_device(cuda_dev):
     assert _rel_err(y.detach().cpu(), ref.detach().float()) < 1e-4
     assert _rel_err(m.weight.grad.cpu(), wr.grad.float()) < 2e-4
     assert _rel_err(xx.grad.cpu(), xr.grad.float()) < 2e-4
+
+
+def test_mega_wavefront_step_equals_replicated_state_step(cuda_dev):
+    """MegaEngine._wave (SURVEY.md section 8e option ii; schedule verified symbolically in
+    tests/test_wave_schedule_cpu.py): both ranks of a 2-GPU group played on one device with parallel.play() must give
+    the detections and predictor outputs of the sequential owner-mode step BIT for bit, and leave the same memory."""
+    from mega_core.b200 import engine, parallel, synth
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "mega_r101_192x320.pt"))
+    h, w = gold["h"], gold["w"]
+    sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+    frames = [synth.synthetic_frame(i, h, w).to(cuda_dev) for i in range(24)]
+    glob0 = [frames[(3 * j + 1) % 24] for j in range(10)]
+    pair = lambda t: torch.cat([frames[(t + 12) % 24], frames[(5 * t + 3) % 24]], 0)
+    steps = 6
+
+    def make():
+        e = engine.MegaEngine(sd, engine.EngineConfig(precision="f16"), device=cuda_dev)
+        e.start_video(frames[0], frames[1:13], glob0, w, h)
+        return e
+
+    def snap(e, det):
+        torch.cuda.synchronize()
+        b, s, l = det.to_host()
+        k = int(e.cur_cnt.view(-1)[0].item())
+        return e.last_pred[:k].clone().cpu(), b, s, l
+
+    ranker = make()
+    payloads = [ranker.ref_payload(pair(t), w, h) for t in range(1, steps + 1)]
+    solo = make()
+    out_solo = [snap(solo, solo.dist_step(None, w, h, rank=0, world=1, payloads=payloads[t][None])[0])
+                for t in range(steps)]
+    ranks = [make(), make()]
+    out_wave = [None] * steps
+    for t in range(0, steps, 2):
+        gens = [ranks[r]._wave(None, w, h, r, 2, payload=payloads[t + r]) for r in range(2)]
+        dets = parallel.play(gens)
+        for r in range(2):
+            out_wave[t + r] = snap(ranks[r], dets[r])
+    for t in range(steps):
+        for a, b in zip(out_solo[t], out_wave[t]):
+            assert torch.equal(a, b), "frame %d differs between the sequential and the wavefront schedule" % t
+    torch.cuda.synchronize()
+    for name in ("E0", "B0", "Y1E", "Y2M", "B1", "B2", "win_x", "glob_x"):
+        ring = {"E0": solo.KP + solo.nl0, "B0": solo.KP + solo.nl0, "Y1E": solo.nq, "Y2M": solo.nq, "B1": solo.nl12,
+                "B2": solo.nl12}.get(name, 0)
+        for r in range(2):
+            assert torch.equal(getattr(ranks[r], name)[ring:], getattr(solo, name)[ring:]), (name, r)
