@@ -210,3 +210,24 @@ def test_mega_wavefront_step_equals_replicated_state_step(cuda_dev):
                 "B2": solo.nl12}.get(name, 0)
         for r in range(2):
             assert torch.equal(getattr(ranks[r], name)[ring:], getattr(solo, name)[ring:]), (name, r)
+
+
+@pytest.mark.parametrize("h,w", [(720, 1280), (480, 640), (600, 1000), (375, 500)])
+def test_device_image_transform_matches_reference_pipeline(cuda_dev, h, w):
+    """mega_image_transform_u8 vs the reference's CPU pipeline (PIL resize -> to_tensor -> BGR255 -> normalize), bit for
+    bit, at ImageNet-VID frame sizes and MIN_SIZE_TEST / MAX_SIZE_TEST = 600 / 1000"""
+    import numpy as np
+    import image_oracle as io
+    from mega_core.data.transforms import DeviceTestTransform
+    mean, std = [102.9801, 115.9465, 122.7717], [1.0, 1.0, 1.0]
+    g = np.random.default_rng(h + w)
+    base = g.integers(0, 256, (h // 16 + 2, w // 16 + 2, 3), dtype=np.uint8)
+    img = np.kron(base, np.ones((16, 16, 1), dtype=np.uint8))[:h, :w]
+    img = np.clip(img.astype(np.int16) + g.integers(-20, 20, (h, w, 3), dtype=np.int16), 0, 255).astype(np.uint8)
+    ref = io.reference_pipeline(img, 600, 1000, mean, std, True)
+    tr = DeviceTestTransform(600, 1000, mean, std, True, device=cuda_dev)
+    out, _ = tr(img)
+    assert out.is_cuda and out.shape == ref.shape
+    assert torch.equal(out.cpu(), ref)
+    out2, _ = tr(torch.from_numpy(img).pin_memory())              # pinned host frame, tables cached from the first call
+    assert torch.equal(out2.cpu(), ref)
