@@ -11,7 +11,9 @@ import sys
 import pytest
 import torch
 
-pytestmark = pytest.mark.gpu
+# first GPU run of these kernels happens without supervision: a generous per-test timeout that ends the PROCESS (thread
+# method: a signal cannot interrupt a blocked CUDA call) keeps a surprise from stalling the whole GPU tier
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
