@@ -260,6 +260,12 @@ int mega_fgfa_aggregate(const void* ring, long long slot_stride, int ld, int fea
                         const int* slots, int n_frames, int key_pos, const float* flow, int flow_ld, int height, int width,
                         void* out, long long out_ld, float* weights_out, int f16, void* stream);
 
+/* DFF (configs/DFF): out[h*w][out_ld] = resample(key_feats [h*w][ld], flow [h*w][flow_ld] fp32)
+ * * scale [h*w][scale_ld] -- bilinear / border warp of the key frame's feature map along the flow, times FlowNetS's
+ * scale map (detector/generalized_rcnn_dff.py:41-58, :131-134). channels % 8 == 0; f16 as above. */
+int mega_dff_warp_scale(const void* key_feats, int ld, int channels, const float* flow, int flow_ld, const void* scale,
+                        long long scale_ld, int height, int width, void* out, long long out_ld, int f16, void* stream);
+
 /* -------------------------------------------- RetinaNet focal loss (csrc/SigmoidFocalLoss.h:10-32)
  * logits [N,C] fp32, targets [N] int32 in {-1 (ignore), 0 (background), 1..C}. */
 int mega_sigmoid_focalloss_forward(const float* logits, const int* targets, int num_samples, int num_classes,

@@ -192,6 +192,31 @@ fgfa_aggregate_kernel(const T* __restrict__ ring, long long slot_stride, int ld,
   }
 }
 
+// DFF (detector/generalized_rcnn_dff.py:131-134): out = resample(key_feats, flow) * scale_map. One thread per
+// (pixel, 8 channels): the four bilinear corners of a pixel are shared by its 1024 channels (consecutive threads),
+// channel-fastest so every corner read / scale read / store is a coalesced 16- or 32-byte access.
+template <typename T>
+__global__ void dff_warp_scale_kernel(const T* __restrict__ key, int ld, int channels, const float* __restrict__ flow,
+                                      int flow_ld, const T* __restrict__ scale, long long scale_ld, int h, int w,
+                                      T* __restrict__ out, long long out_ld) {
+  const int groups = channels / 8;
+  const long long total = static_cast<long long>(h) * w * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const int pix = static_cast<int>(i / groups);
+    const int y = pix / w, x = pix - y * w;
+    const float* f = flow + static_cast<long long>(pix) * flow_ld;
+    const Corner c = flow_corners(f[0], f[1], x, y, w, h, ld);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = g * 8 + e;
+      const float v = sample<T>(key, c, ch) * to_f<T>(scale[static_cast<long long>(pix) * scale_ld + ch]);
+      out[static_cast<long long>(pix) * out_ld + ch] = from_f<T>(v);
+    }
+  }
+}
+
 static int grid_for(long long total, int block) {
   long long b = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -244,6 +269,18 @@ extern "C" int mega_fgfa_aggregate(const void* ring, long long slot_stride, int 
   const int pixels = height * width;
   if (f16) fgfa_aggregate_kernel<__half><<<pixels, kAggThreads, 0, stream>>>(static_cast<const __half*>(ring), slot_stride, ld, feat_channels, embed_channels, slots, n_frames, key_pos, flow, flow_ld, height, width, static_cast<__half*>(out), out_ld, weights_out);
   else fgfa_aggregate_kernel<float><<<pixels, kAggThreads, 0, stream>>>(static_cast<const float*>(ring), slot_stride, ld, feat_channels, embed_channels, slots, n_frames, key_pos, flow, flow_ld, height, width, static_cast<float*>(out), out_ld, weights_out);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_dff_warp_scale(const void* key_feats, int ld, int channels, const float* flow, int flow_ld,
+                                   const void* scale, long long scale_ld, int height, int width, void* out,
+                                   long long out_ld, int f16, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(channels > 0 && channels % 8 == 0 && height > 0 && width > 0, "dff_warp_scale: channels must be a multiple of 8");
+  const long long total = static_cast<long long>(height) * width * (channels / 8);
+  if (f16) dff_warp_scale_kernel<__half><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const __half*>(key_feats), ld, channels, flow, flow_ld, static_cast<const __half*>(scale), scale_ld, height, width, static_cast<__half*>(out), out_ld);
+  else dff_warp_scale_kernel<float><<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const float*>(key_feats), ld, channels, flow, flow_ld, static_cast<const float*>(scale), scale_ld, height, width, static_cast<float*>(out), out_ld);
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }

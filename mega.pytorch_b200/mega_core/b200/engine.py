@@ -1371,6 +1371,13 @@ class FlowNetS:
             self.w["Convolution%d" % i] = wp.contiguous().to(dev).to(dtype)
             self.b["Convolution%d" % i] = g("Convolution%d.bias" % i).contiguous().to(dev)
         self.b["Convolution5_x2.5"] = (g("Convolution5.bias") * 2.5).contiguous().to(dev)
+        self.w_scale = None
+        if (prefix + "Convolution5_scale.weight") in sd:              # method "dff" (flownet.py:36-38, :112-116)
+            ws = g("Convolution5_scale.weight")                       # [1024, 194, 1, 1], no bias
+            wp = torch.zeros(1, ws.shape[0], _round_up(ws.shape[1], 8))
+            wp[0, :, :ws.shape[1]] = ws[:, :, 0, 0]
+            self.w_scale = wp.contiguous().to(dev).to(dtype)
+            self.b_one = torch.ones(ws.shape[0], device=dev)          # "+ torch.ones_like" as the epilogue bias
         self.scale25 = torch.full((4,), 2.5, device=dev)
         for name in ("deconv5", "deconv4", "deconv3", "deconv2", "upsample_flow6to5", "upsample_flow5to4",
                      "upsample_flow4to3", "upsample_flow3to2"):
@@ -1415,8 +1422,9 @@ class FlowNetS:
                 ops.conv_gemm(x, self.w[name][(py, px)], view, taps=(2, 2), pad=1 - du, pad_w=1 - dv, bias=self.b[name],
                               relu=act, cout=cout)
 
-    def forward(self, pairs):
-        """pairs [L, hq+6, wq+8, 8] (ops.fgfa_build_pairs) -> flow [L, hf, wf, 4] fp32 (channels 0,1 = x,y; x2.5 applied)"""
+    def forward(self, pairs, want_scale=False):
+        """pairs [L, hq+6, wq+8, 8] (ops.fgfa_build_pairs) -> flow [L, hf, wf, 4] fp32 (channels 0,1 = x,y; x2.5 applied);
+        want_scale (method "dff"): also the scale map Convolution5_scale(concat5) + 1, [L, hf, wf, 1024]"""
         n, hp, wp, _ = pairs.shape
         hq, wq = hp - 6, wp - 8
         dim = lambda v: (v - 1) // 2 + 1                         # k odd, stride 2, "same" padding
@@ -1472,6 +1480,10 @@ class FlowNetS:
         flow = B("flow", (n, hf, wf, 4), torch.float32)
         ops.conv_gemm(pooled, self.w["Convolution5"], flow[..., 0:2], taps=(3, 3), pad=1, scale=self.scale25,
                       bias=self.b["Convolution5_x2.5"], cout=2)
+        if want_scale:
+            scale = B("scale", (n, hf, wf, self.w_scale.shape[1]))
+            ops.conv_gemm(pooled, self.w_scale, scale, bias=self.b_one)
+            return flow, scale
         return flow
 
 
@@ -1578,6 +1590,85 @@ class FgfaEngine(HeadCommon):
         self.last_flow = flow
         ops.fgfa_aggregate(self.ring, self.slots_d, self.KL, flow, self.agg[0], 1024, 2048)
         feats = self.agg
+        KP = c.post_nms_top_n
+        boxes, _, cnt = self.rpn(feats, im_w, im_h, KP)
+        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained):
+            x = self.res5.forward(feats)
+        res = c.pooler_resolution
+        pooled = self._buf("pooled", (KP, res * res * self.ch), self.act)
+        ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)
+        f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]), self.act)
+        ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True)
+        f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]), self.act)
+        ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
+        self.last_feats, self.last_props, self.last_cnt = feats, boxes[0], cnt
+        return self.predict_and_postprocess(f7, boxes[0], cnt[0:1], im_w, im_h)
+
+
+# =============================================================================================== DFF
+class DffEngine(HeadCommon):
+    """GeneralizedRCNNDFF._forward_test (detector/generalized_rcnn_dff.py:119-138): the backbone runs on key frames only
+    (every 10th frame, data/datasets/vid_dff.py:52-55); every frame runs FlowNetS on the pair (frame, key frame), warps
+    the key frame's feature map along the flow, multiplies it by FlowNetS's scale map (one kernel, csrc/fgfa.cu) and
+    feeds the single-frame RPN + box head (ResNetConv52MLPFeatureExtractor without channel reduction).
+    Built from the FGFA parts (FlowNetS over row-slab / parity-class implicit GEMMs, pooled-image ring, pair builder).
+    NOT YET RUN ON A GPU (written after the last GPU session of round 1); parity test in tests/test_zz_train_ops_gpu.py
+    against the fixture of the unmodified reference (tests/golden/dff_r101_192x320.pt)."""
+
+    def __init__(self, sd, cfg=None, device="cuda"):
+        cfg = cfg or EngineConfig()
+        dev = torch.device(device)
+        super().__init__(sd, cfg, dev)
+        act = self.act
+        self.flownet = FlowNetS(sd, dev, act)
+        assert self.flownet.w_scale is not None, "state_dict has no flownet.Convolution5_scale (not a DFF model)"
+        res = cfg.pooler_resolution
+        w6 = sd[FE + "fc6.weight"].float()
+        ch = w6.shape[1] // (res * res)
+        self.ch = ch
+        self.fc6_w = (w6.reshape(w6.shape[0], ch, res * res).permute(0, 2, 1).reshape(w6.shape[0], -1).contiguous()
+                      .to(act).to(dev))
+        self.fc6_b = sd[FE + "fc6.bias"].float().contiguous().to(dev)
+        self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev).to(act)
+        self.fc7_b = sd[FE + "fc7.bias"].float().contiguous().to(dev)
+        self.slots_d = torch.tensor([0, 1], dtype=torch.int32, device=dev)      # ring slot 0: current frame, 1: key frame
+        self._shape, self.has_key = None, False
+
+    def reset(self):
+        self.has_key = False
+
+    def _alloc(self, h, w):
+        if self._shape == (h, w):
+            return
+        fh, fw = (h - 1) // 16 + 1, (w - 1) // 16 + 1
+        hq, wq = (h + 1) // 2, (w + 1) // 2
+        assert wq % 2 == 0, "the row-slab form of flow_conv1 needs an even pooled width"
+        z = lambda *s: torch.zeros(*s, device=self.dev, dtype=self.act)
+        self.img_ring, self.pairs = z(2, hq, wq, 4), z(2, hq + 6, wq + 8, 8)
+        self.key_feats, self.warped = z(1, fh, fw, 1024), z(1, fh, fw, 1024)
+        self._shape, self.has_key = (h, w), False
+
+    @_with_precision
+    def forward(self, img, is_key_frame, im_w, im_h):
+        """img [1,3,H,W] fp32 on the device; is_key_frame as in the dataset's test-time dict (vid_dff.py:63-65)"""
+        c = self.cfg
+        self._alloc(img.shape[-2], img.shape[-1])
+        if is_key_frame:
+            feats = self.backbone.forward(img)                              # [1, fh, fw, 1024]
+            n, fh, fw, d = feats.shape
+            ops.copy_rows(feats.view(fh * fw, d), self.key_feats.view(fh * fw, d), fh * fw)
+            ops.fgfa_pool_image(img, self.img_ring[1])
+            self.has_key = True
+        if not self.has_key:
+            raise RuntimeError("DFF: the first frame of a video has to be a key frame")
+        ops.fgfa_pool_image(img, self.img_ring[0])
+        # pairs[f] = (ring[slots[0]] | ring[slots[f]]): pairs[1] = (current frame | key frame), the FlowNetS input order
+        # of generalized_rcnn_dff.py:130 (pairs[0] = (current | current) is not used)
+        ops.fgfa_build_pairs(self.img_ring, self.slots_d, 0, self.pairs)
+        flow, scale = self.flownet.forward(self.pairs[1:2], want_scale=True)
+        self.last_flow, self.last_scale = flow, scale
+        ops.dff_warp_scale(self.key_feats[0], flow[0], scale[0], self.warped[0])
+        feats = self.warped
         KP = c.post_nms_top_n
         boxes, _, cnt = self.rpn(feats, im_w, im_h, KP)
         with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained):

@@ -713,3 +713,16 @@ def fgfa_aggregate(ring, slots, key_pos, flow, out, feat_channels, embed_channel
                                   _is16(ring), stream_ptr()), "mega_fgfa_aggregate")
     LAUNCHES[0] += 1
     return out
+
+
+def dff_warp_scale(key_feats, flow, scale, out):
+    """key_feats [h, w, C]; flow [h, w, fl] fp32 (x, y in cells); scale [h, w, >=C]; out [h, w, >=C] = warp(key_feats) * scale"""
+    require_cuda(key_feats, flow, scale, out)
+    h, w, c = key_feats.shape
+    assert flow.dtype == torch.float32 and key_feats.dtype == scale.dtype == out.dtype
+    assert key_feats.stride(2) == 1 and scale.stride(2) == 1 and out.stride(2) == 1 and key_feats.stride(0) == w * key_feats.stride(1)
+    check(lib.mega_dff_warp_scale(ptr(key_feats), key_feats.stride(1), c, ptr(flow), flow.stride(1), ptr(scale),
+                                  scale.stride(1), h, w, ptr(out), out.stride(1), _is16(key_feats), stream_ptr()),
+          "mega_dff_warp_scale")
+    LAUNCHES[0] += 1
+    return out

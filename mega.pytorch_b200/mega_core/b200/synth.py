@@ -75,7 +75,7 @@ def _linear(sd, p, nout, nin, gen, std=None, gain=1.0):
 
 def make_state_dict(arch="mega_r101", seed=0, num_classes=31):
     """state_dict with the reference's key names/shapes for
-    arch in {"mega_r101", "mega_r50", "rdn_r101", "fgfa_r101", "base_r50", "base_r101"} (+ "_tiny" suffix: 1 block per stage,
+    arch in {"mega_r101", "mega_r50", "rdn_r101", "fgfa_r101", "dff_r101", "base_r50", "base_r101"} (+ "_tiny" suffix: 1 block per stage,
     for fast CPU tests)."""
     gen = torch.Generator().manual_seed(seed)
     tiny = arch.endswith("_tiny")
@@ -105,9 +105,10 @@ def make_state_dict(arch="mega_r101", seed=0, num_classes=31):
         sd[fe + "conv.bias"] = torch.zeros(256)
         _linear(sd, fe + "fc6.", 1024, 256 * 49, gen)
         _linear(sd, fe + "fc7.", 1024, 1024, gen)
-    elif method == "fgfa":
-        # GeneralizedRCNNFGFA: FlowNetS + EmbedNet next to the backbone (backbone/flownet.py, embednet.py), box head =
-        # ResNetConv52MLPFeatureExtractor without the channel reduction (configs/FGFA/vid_R_101_C4_FGFA_1x.yaml)
+    elif method in ("fgfa", "dff"):
+        # GeneralizedRCNNFGFA / GeneralizedRCNNDFF: FlowNetS (+ EmbedNet for FGFA) next to the backbone
+        # (backbone/flownet.py, embednet.py), box head = ResNetConv52MLPFeatureExtractor without the channel reduction
+        # (configs/FGFA/vid_R_101_C4_FGFA_1x.yaml, configs/DFF/vid_R_101_C4_DFF_1x.yaml)
         _linear(sd, fe + "fc6.", 1024, 2048 * 49, gen)
         _linear(sd, fe + "fc7.", 1024, 1024, gen)
 
@@ -134,9 +135,14 @@ def make_state_dict(arch="mega_r101", seed=0, num_classes=31):
         for name in ("upsample_flow6to5", "upsample_flow5to4", "upsample_flow4to3", "upsample_flow3to2"):
             sd["flownet.%s.weight" % name] = torch.randn(2, 2, 4, 4, generator=gen) * 0.25
             sd["flownet.%s.bias" % name] = torch.zeros(2)
-        conv("embednet.embed_conv1", 512, 1024, 1)
-        conv("embednet.embed_conv2", 512, 512, 3)
-        conv("embednet.embed_conv3", 2048, 512, 1, gain=1.0)
+        if method == "fgfa":
+            conv("embednet.embed_conv1", 512, 1024, 1)
+            conv("embednet.embed_conv2", 512, 512, 3)
+            conv("embednet.embed_conv3", 2048, 512, 1, gain=1.0)
+        else:
+            # the reference zero-initialises the scale head (flownet.py:36-38: scale map == 1); a trained one is not
+            # zero, so give it a spread of about +-0.3 around 1 to make the parity test see the branch
+            sd["flownet.Convolution5_scale.weight"] = _kaiming((1024, 194, 1, 1), gen, gain=0.3)
     elif method == "rdn":
         # RDNFeatureExtractor with ATTENTION.STAGE = 2, ADVANCED_STAGE = 1 (configs/RDN/vid_R_101_C4_RDN_1x.yaml):
         # fcs[0..2], Wgs/Wqs/Wks/Wvs[0..3] (roi_box_feature_extractors.py:305-328)

@@ -1,10 +1,12 @@
 """build_detection_model(cfg) keyed by cfg.MODEL.META_ARCHITECTURE (detector/detectors.py:9-18)."""
 import os
 
-from .generalized_rcnn import GeneralizedRCNN, GeneralizedRCNNFGFA, GeneralizedRCNNMEGA, GeneralizedRCNNRDN
+from .generalized_rcnn import (GeneralizedRCNN, GeneralizedRCNNDFF, GeneralizedRCNNFGFA, GeneralizedRCNNMEGA,
+                               GeneralizedRCNNRDN)
 
 _DETECTION_META_ARCHITECTURES = {"GeneralizedRCNN": GeneralizedRCNN, "GeneralizedRCNNMEGA": GeneralizedRCNNMEGA,
-                                 "GeneralizedRCNNRDN": GeneralizedRCNNRDN, "GeneralizedRCNNFGFA": GeneralizedRCNNFGFA}
+                                 "GeneralizedRCNNRDN": GeneralizedRCNNRDN, "GeneralizedRCNNFGFA": GeneralizedRCNNFGFA,
+                                 "GeneralizedRCNNDFF": GeneralizedRCNNDFF}
 
 
 def build_detection_model(cfg):
@@ -34,6 +36,9 @@ def vid_config(method="mega", conv_body="R-101-C4", device="cuda"):
                                      "ROI_BOX_HEAD": {"FEATURE_EXTRACTOR": "RDNFeatureExtractor"}}})
     elif method == "fgfa":    # configs/FGFA/vid_R_101_C4_FGFA_1x.yaml
         c.merge_from_dict({"MODEL": {"META_ARCHITECTURE": "GeneralizedRCNNFGFA", "VID": {"METHOD": "fgfa"},
+                                     "ROI_BOX_HEAD": {"FEATURE_EXTRACTOR": "ResNetConv52MLPFeatureExtractor"}}})
+    elif method == "dff":     # configs/DFF/vid_R_101_C4_DFF_1x.yaml
+        c.merge_from_dict({"MODEL": {"META_ARCHITECTURE": "GeneralizedRCNNDFF", "VID": {"METHOD": "dff"},
                                      "ROI_BOX_HEAD": {"FEATURE_EXTRACTOR": "ResNetConv52MLPFeatureExtractor"}}})
     elif method == "base":
         c.merge_from_dict({"MODEL": {"META_ARCHITECTURE": "GeneralizedRCNN",

@@ -4,6 +4,7 @@ GeneralizedRCNN       -- detector/generalized_rcnn.py:16-65 (single frame)
 GeneralizedRCNNMEGA   -- detector/generalized_rcnn_mega.py:21-225 (per-video state machine)
 GeneralizedRCNNRDN    -- detector/generalized_rcnn_rdn.py:20-190 (per-video state machine, 37-frame window)
 GeneralizedRCNNFGFA   -- detector/generalized_rcnn_fgfa.py:19-219 (flow-guided aggregation over a 19-frame window)
+GeneralizedRCNNDFF    -- detector/generalized_rcnn_dff.py:19-138 (key-frame features warped along FlowNetS flow)
 
 `forward(images)` returns `list[BoxList]` (fields `scores`, `labels`) exactly like the reference in
 eval mode; the arithmetic runs in the B200 engine built lazily from this module's own state_dict
@@ -171,3 +172,23 @@ class GeneralizedRCNNFGFA(GeneralizedRCNNRDN):
         super().__init__(cfg)
         self.flownet = FlowNetS(cfg)
         self.embednet = EmbedNet(cfg)
+
+
+class GeneralizedRCNNDFF(_EngineBacked):
+    """images: the dict VIDDFFDataset._get_test builds (data/datasets/vid_dff.py:48-67): `cur` and `is_key_frame`"""
+    engine_cls = _engine.DffEngine
+
+    def __init__(self, cfg):
+        super().__init__(cfg)
+        self.flownet = FlowNetS(cfg)
+
+    def forward(self, images, targets=None):
+        if self.training:
+            raise NotImplementedError("the B200 build covers inference (eval mode) only")
+        if targets is not None:
+            raise ValueError("In testing mode, targets should be None")
+        cur = to_image_list(images["cur"])
+        im_h, im_w = cur.image_sizes[0]
+        with torch.no_grad():
+            det = self.engine.forward(self._dev(cur), bool(images["is_key_frame"]), im_w, im_h)
+        return [self._to_boxlist(det, im_w, im_h)]

@@ -213,7 +213,7 @@ class CombinedROIHeads(nn.ModuleDict):
 
 
 class FlowNetS(nn.Module):
-    """parameters of modeling/backbone/flownet.py:14-50 (method "fgfa")"""
+    """parameters of modeling/backbone/flownet.py:14-50 (methods "fgfa" and "dff")"""
 
     def __init__(self, cfg):
         super().__init__()
@@ -235,6 +235,9 @@ class FlowNetS(nn.Module):
         self.deconv2 = nn.ConvTranspose2d(386, 64, 4, stride=2)
         for n_ in ("6to5", "5to4", "4to3", "3to2"):
             setattr(self, "upsample_flow" + n_, nn.ConvTranspose2d(2, 2, 4, stride=2))
+        if cfg.MODEL.VID.METHOD == "dff":                      # flownet.py:36-38: zero-initialised scale head
+            self.Convolution5_scale = nn.Conv2d(194, 1024, 1, bias=False)
+            nn.init.zeros_(self.Convolution5_scale.weight)
 
 
 class EmbedNet(nn.Module):

@@ -360,6 +360,73 @@ def golden_fgfa(h=192, w=320, n_frames=3, total=30):
     return {"arch": "fgfa_r101", "seed": 5, "h": h, "w": w, "total": total, "frames": gold}
 
 
+def run_reference_dff(sd, frames, key_flags):
+    cfg = ref_import.build_cfg("configs/DFF/vid_R_101_C4_DFF_1x.yaml")
+    from mega_core.modeling.detector import build_detection_model
+    model = build_detection_model(cfg).eval()
+    full = dict(sd)
+    full["rpn.anchor_generator.cell_anchors.0"] = model.state_dict()["rpn.anchor_generator.cell_anchors.0"]
+    model.load_state_dict(full, strict=True)
+    outs, hooks = [], {}
+    pred = model.roi_heads.box.predictor
+    orig_pred = pred.forward
+
+    def pred_fwd(x):
+        r = orig_pred(x)
+        hooks["class_logits"], hooks["box_regression"] = r[0].clone(), r[1].clone()
+        return r
+
+    pred.forward = pred_fwd
+    orig_flow = model.flownet.forward
+
+    def flow_fwd(x):
+        r = orig_flow(x)
+        hooks["flow"], hooks["scale"] = r[0].clone(), r[1].clone()
+        return r
+
+    model.flownet.forward = flow_fwd
+    orig_rpn = model.rpn.forward
+
+    def rpn_fwd(images, features, targets=None):
+        hooks["feats"] = features[0].clone()
+        return orig_rpn(images, features, targets)
+
+    model.rpn.forward = rpn_fwd
+    with torch.no_grad():
+        for t, key in enumerate(key_flags):
+            res = model({"cur": frames[t][0].clone(), "is_key_frame": key})[0]      # vid_dff.py test-time dict
+            outs.append({"boxes": res.bbox.clone(), "scores": res.get_field("scores").clone(),
+                         "labels": res.get_field("labels").clone(), **{k: v for k, v in hooks.items()}})
+    return outs
+
+
+def golden_dff(h=192, w=320, key_flags=(True, False, False, True, False)):
+    print("  DFF R-101 @%dx%d: reference vs oracle, %d frames" % (h, w, len(key_flags)))
+    sd = synth.make_state_dict("dff_r101", seed=6)
+    frames = [synth.synthetic_frame(3 * i, h, w) for i in range(len(key_flags))]       # 3-frame stride: visible motion
+    ref = run_reference_dff(sd, frames, key_flags)
+    orc = mo.DffOracle(sd, record=True)
+    gold = []
+    for t, key in enumerate(key_flags):
+        b, s, l = orc.forward(frames[t], key)
+        r = ref[t]
+        close(orc.trace["flow"], r["flow"], 2e-5, "frame %d flow" % t)
+        close(orc.trace["scale"], r["scale"], 2e-5, "frame %d scale map" % t)
+        close(orc.trace["feats"], r["feats"], 2e-5, "frame %d warped feats" % t)
+        assert r["class_logits"].shape == orc.trace["class_logits"].shape, "proposal count differs"
+        close(orc.trace["class_logits"], r["class_logits"], 2e-5, "frame %d class_logits" % t)
+        close(orc.trace["box_regression"], r["box_regression"], 2e-5, "frame %d box_regression" % t)
+        assert torch.equal(l, r["labels"]) and b.shape == r["boxes"].shape, "detections differ (frame %d)" % t
+        close(b, r["boxes"], 1e-4, "frame %d det boxes" % t)
+        print("    flow rms %.3f, scale in [%.2f, %.2f]" % (r["flow"].pow(2).mean().sqrt().item(), r["scale"].min().item(),
+                                                          r["scale"].max().item()))
+        gold.append({"class_logits": r["class_logits"], "box_regression": r["box_regression"],
+                     "proposals": orc.trace["proposals"], "boxes": r["boxes"], "scores": r["scores"],
+                     "labels": r["labels"], "flow": r["flow"], "scale_sample": r["scale"][:, ::64].clone(),
+                     "feats_sample": r["feats"][:, ::64].clone(), "feats_rms": r["feats"].pow(2).mean().sqrt().item()})
+    return {"arch": "dff_r101", "seed": 6, "h": h, "w": w, "key_flags": list(key_flags), "frame_stride": 3, "frames": gold}
+
+
 def golden_base(h=192, w=320):
     print("  single-frame R-50-C4 @%dx%d: reference vs oracle" % (h, w))
     cfg = ref_import.build_cfg("configs/vid_R_50_C4_1x.yaml")
@@ -403,6 +470,9 @@ def main():
     if "fgfa" in only:
         torch.save(golden_fgfa(), os.path.join(GOLD, "fgfa_r101_192x320.pt"))
         return
+    if "dff" in only:
+        torch.save(golden_dff(), os.path.join(GOLD, "dff_r101_192x320.pt"))
+        return
     print("[1] reference unit-test vectors")
     torch.save(golden_from_reference_tests(), os.path.join(GOLD, "reference_unit_vectors.pt"))
     print("[2] op-level reference outputs")
@@ -412,6 +482,7 @@ def main():
     torch.save(golden_mega(), os.path.join(GOLD, "mega_r101_192x320.pt"))
     torch.save(golden_rdn(), os.path.join(GOLD, "rdn_r101_192x320.pt"))
     torch.save(golden_fgfa(), os.path.join(GOLD, "fgfa_r101_192x320.pt"))
+    torch.save(golden_dff(), os.path.join(GOLD, "dff_r101_192x320.pt"))
     for f in sorted(os.listdir(GOLD)):
         print("  wrote", f, os.path.getsize(os.path.join(GOLD, f)), "bytes")
 

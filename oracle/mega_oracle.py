@@ -642,8 +642,9 @@ def _crop_like(x, target):
     return x[:, :, 1:target.shape[2] + 1, 1:target.shape[3] + 1]
 
 
-def flownet_s(x, sd, p="flownet."):
-    """FlowNetS.forward, method "fgfa" (backbone/flownet.py:54-118): x [B,6,H,W] (image pairs / 255) -> flow [B,2,H/16,W/16] * 2.5"""
+def flownet_s(x, sd, p="flownet.", with_scale=False):
+    """FlowNetS.forward (backbone/flownet.py:54-118): x [B,6,H,W] (image pairs / 255) -> flow [B,2,H/16,W/16] * 2.5;
+    with_scale (method "dff", :112-116): also the scale map Convolution5_scale(concat5) + 1, [B,1024,H/16,W/16]"""
     def conv(name, t, stride=1, pad=1):
         return F.conv2d(t, sd[p + name + ".weight"], sd[p + name + ".bias"], stride, pad)
 
@@ -675,7 +676,12 @@ def flownet_s(x, sd, p="flownet."):
     flow3 = conv("Convolution4", concat4)
     concat5 = torch.cat((relu2, lrelu(_crop_like(deconv("deconv2", concat4), relu2)),
                          _crop_like(deconv("upsample_flow3to2", flow3), relu2)), dim=1)
-    return conv("Convolution5", pool(concat5)) * 2.5
+    concat5 = pool(concat5)
+    flow = conv("Convolution5", concat5) * 2.5
+    if with_scale:
+        scale = F.conv2d(concat5, sd[p + "Convolution5_scale.weight"])
+        return flow, scale + torch.ones_like(scale)
+    return flow
 
 
 def embednet(x, sd, p="embednet."):
@@ -758,6 +764,44 @@ class FgfaOracle:
         if self.record:
             self.trace = {"proposals": prop.clone(), "class_logits": cl.clone(), "box_regression": bd.clone(),
                           "flow": flow.clone(), "feats": feats.clone(), "weights": weights.clone()}
+        return box_postprocess(cl, bd, prop, im_w, im_h, c.score_thresh, c.nms_thresh, c.detections_per_img,
+                               cuda_semantics=c.cuda_nms_semantics)
+
+
+class DffOracle:
+    """GeneralizedRCNNDFF._forward_test (detector/generalized_rcnn_dff.py:119-138), restated: the backbone runs on key
+    frames only; every frame (key frames included) gets FlowNetS on the pair (frame, key frame) -> flow + scale map, the
+    key frame's feature map is warped along the flow (get_grid / resample, :41-58 -- the same code as FGFA's) and
+    multiplied by the scale map; the single-frame RPN + box head (ResNetConv52MLPFeatureExtractor, no channel
+    reduction) follow."""
+
+    def __init__(self, state_dict, cfg=None, record=False):
+        self.sd = {k: v.detach().float() for k, v in state_dict.items()}
+        self.cfg = cfg or Cfg()
+        self.record = record
+        self.trace = {}
+        self.key_image = self.key_feats = None
+
+    def forward(self, img, is_key_frame):
+        c, sd = self.cfg, self.sd
+        im_h, im_w = img.shape[-2:]
+        if is_key_frame:
+            self.key_image, self.key_feats = img, resnet_c4_body(img, sd)
+        flow, scale = flownet_s(torch.cat([img / 255, self.key_image / 255], dim=1), sd, with_scale=True)
+        feats = fgfa_warp(self.key_feats, flow) * scale
+        logits, deltas = rpn_head(feats, sd)
+        prop, obj = rpn_select(logits, deltas, im_w, im_h, c.pre_nms_top_n, c.post_nms_top_n, c.rpn_nms_thresh,
+                               cuda_semantics=c.cuda_nms_semantics)
+        x = res5_head(feats, sd, FE + "head.", c.res5_dilation)
+        rois = torch.cat([torch.zeros(prop.shape[0], 1), prop], dim=1)
+        x = roi_align(x, rois, c.pooler_scale, c.pooler_resolution, c.pooler_resolution, c.sampling_ratio).flatten(start_dim=1)
+        x = F.relu(F.linear(x, sd[FE + "fc6.weight"], sd[FE + "fc6.bias"]))
+        x = F.relu(F.linear(x, sd[FE + "fc7.weight"], sd[FE + "fc7.bias"]))
+        cl = F.linear(x, sd["roi_heads.box.predictor.cls_score.weight"], sd["roi_heads.box.predictor.cls_score.bias"])
+        bd = F.linear(x, sd["roi_heads.box.predictor.bbox_pred.weight"], sd["roi_heads.box.predictor.bbox_pred.bias"])
+        if self.record:
+            self.trace = {"proposals": prop.clone(), "class_logits": cl.clone(), "box_regression": bd.clone(),
+                          "flow": flow.clone(), "scale": scale.clone(), "feats": feats.clone()}
         return box_postprocess(cl, bd, prop, im_w, im_h, c.score_thresh, c.nms_thresh, c.detections_per_img,
                                cuda_semantics=c.cuda_nms_semantics)
 

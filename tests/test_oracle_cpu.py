@@ -155,3 +155,21 @@ def test_fgfa_r101_oracle_matches_reference_fixture():
     assert torch.allclose(orc.trace["flow"], ref["flow"], atol=1e-5)
     assert torch.allclose(orc.trace["class_logits"], ref["class_logits"], atol=1e-5)
     assert _same_boxes(orc.trace["proposals"], ref["proposals"]) and torch.equal(l, ref["labels"])
+
+
+def test_dff_r101_oracle_matches_reference_fixture():
+    """5 frames (key, 2 non-key, key, non-key) of the unmodified reference's GeneralizedRCNNDFF: FlowNetS flow + scale
+    map, warped key-frame features, single-frame head"""
+    synth = _synth()
+    gold = torch.load(os.path.join(GOLD, "dff_r101_192x320.pt"))
+    h, w = gold["h"], gold["w"]
+    sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+    orc = mo.DffOracle(sd, record=True)
+    for t, (key, ref) in enumerate(zip(gold["key_flags"], gold["frames"])):
+        if t >= 3:
+            break                                                      # keep the CPU suite short
+        b, s, l = orc.forward(synth.synthetic_frame(gold["frame_stride"] * t, h, w), key)
+        assert torch.allclose(orc.trace["flow"], ref["flow"], atol=1e-5)
+        assert torch.allclose(orc.trace["scale"][:, ::64], ref["scale_sample"], atol=1e-5)
+        assert torch.allclose(orc.trace["class_logits"], ref["class_logits"], atol=1e-5)
+        assert _same_boxes(orc.trace["proposals"], ref["proposals"]) and torch.equal(l, ref["labels"])

@@ -233,3 +233,69 @@ def test_device_image_transform_matches_reference_pipeline(cuda_dev, h, w):
     assert torch.equal(out.cpu(), ref)
     out2, _ = tr(torch.from_numpy(img).pin_memory())              # pinned host frame, tables cached from the first call
     assert torch.equal(out2.cpu(), ref)
+
+
+@pytest.mark.parametrize("precision", ["shadow", "fp32x3", "f16"])
+def test_dff_r101_matches_reference_fixture(cuda_dev, precision):
+    """DFF R-101 (configs/DFF): DffEngine against the outputs of the unmodified reference's
+    GeneralizedRCNNDFF (tests/golden/dff_r101_192x320.pt: key, non-key, non-key, key, non-key frames). "shadow": all
+    kernels ours, dense contractions in exact fp32 (logic check: flow within 1e-4 cells, every proposal reproduced, class
+    logits within 1e-3); product arithmetics with the statistical bounds of the FGFA tests."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mega_core.b200 import engine, synth
+    from test_engine_gpu import _match_rows
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "dff_r101_192x320.pt"))
+    h, w = gold["h"], gold["w"]
+    sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+
+    def run(prec):
+        eng = engine.DffEngine(sd, engine.EngineConfig(precision=prec), device=cuda_dev)
+        out = []
+        for t, (key, ref) in enumerate(zip(gold["key_flags"], gold["frames"])):
+            img = synth.synthetic_frame(gold["frame_stride"] * t, h, w).to(cuda_dev)
+            det = eng.forward(img, key, w, h)
+            torch.cuda.synchronize()
+            k = int(eng.last_cnt[0].item())
+            idx = _match_rows(eng.last_props[:k].cpu(), ref["proposals"])
+            m = idx >= 0
+            pred = eng.last_pred[:k].cpu()
+            assert torch.isfinite(pred).all()
+            flow = eng.last_flow[..., :2].permute(0, 3, 1, 2).float().cpu()
+            scale = eng.last_scale.float().permute(0, 3, 1, 2).cpu()[:, ::64]
+            feats = eng.last_feats.float().permute(0, 3, 1, 2).cpu()[:, ::64]
+            b, s, l = det.to_host()
+            out.append({"matched_frac": m.float().mean().item(),
+                        "logits_maxabs": (pred[idx[m], :31] - ref["class_logits"][m]).abs().max().item(),
+                        "flow_maxabs": (flow - ref["flow"]).abs().max().item(),
+                        "scale_maxabs": (scale - ref["scale_sample"]).abs().max().item(),
+                        "feats_maxabs": (feats - ref["feats_sample"]).abs().max().item(), "feats_rms": ref["feats_rms"],
+                        "dets": int(b.shape[0]), "ref_dets": int(ref["boxes"].shape[0])})
+        return out
+
+    if precision == "shadow":
+        from fp32_shadow import fp32_shadow
+        with fp32_shadow():
+            frames = run("tf32")
+        for f in frames:
+            assert f["flow_maxabs"] < 1e-4 and f["scale_maxabs"] < 1e-4, f
+            assert f["feats_maxabs"] < 1e-3 * max(f["feats_rms"], 1.0), f
+            assert f["matched_frac"] == 1.0 and f["logits_maxabs"] < 1e-3 and f["dets"] == f["ref_dets"], f
+    else:
+        for f in run(precision):
+            assert f["flow_maxabs"] < 0.05 and f["scale_maxabs"] < 0.05, f
+            assert f["matched_frac"] >= 0.95 and f["logits_maxabs"] < 0.3, f
+
+
+def test_dff_module_api(cuda_dev):
+    """build_detection_model(cfg) for META_ARCHITECTURE GeneralizedRCNNDFF: reference state_dict keys, dataset dict in,
+    list[BoxList] out; a non-key first frame is rejected"""
+    from mega_core.b200 import synth
+    from mega_core.modeling.detector import build_detection_model_from_state_dict
+    sd = synth.make_state_dict("dff_r101", seed=6)
+    model = build_detection_model_from_state_dict(sd, method="dff", device=cuda_dev)
+    h, w = 192, 320
+    with pytest.raises(RuntimeError):
+        model({"cur": synth.synthetic_frame(0, h, w)[0], "is_key_frame": False})
+    for t, key in enumerate((True, False)):
+        out = model({"cur": synth.synthetic_frame(3 * t, h, w)[0], "is_key_frame": key})
+        assert len(out) == 1 and out[0].bbox.shape[1] == 4 and out[0].has_field("scores") and out[0].has_field("labels")
