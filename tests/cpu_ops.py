@@ -93,6 +93,78 @@ def box_postprocess(logits, deltas, proposals, count, num_classes, im_w, im_h, s
     return out
 
 
+# ------------------------------------------------------------------- per-frame branch (backbone, proposals, ROIAlign)
+def stem_prep(img, out):
+    """NCHW fp32 image -> zero-bordered NHWC8 [N, H+6, wp, 8] (3 real channels)"""
+    n, _, h, w = img.shape
+    out.zero_()
+    out[:, 3:3 + h, 3:3 + w, 0:3] = img.permute(0, 2, 3, 1).to(out.dtype)
+    return out
+
+
+def maxpool3x3s2(x, out):
+    out.copy_(F.max_pool2d(x.permute(0, 3, 1, 2).float(), 3, 2, 1).permute(0, 2, 3, 1).to(out.dtype))
+    return out
+
+
+def rpn_select(head, n_img, h, w, base_anchors, im_w, im_h, pre_nms, post_nms, nms_thresh, min_size=0.0, stride=16,
+               out=None, want_anchor=False):
+    """head [n, h, w, ld]: [0, A) objectness logits, [A, 5A) deltas (a*4 + c) -> the oracle's proposal selection"""
+    a = base_anchors.shape[0]
+    boxes, scores, anchor, count = out
+    boxes.zero_(), scores.zero_()
+    for i in range(n_img):
+        hd = head[i].float()
+        logits = hd[..., :a].permute(2, 0, 1)[None]
+        deltas = hd[..., a:5 * a].permute(2, 0, 1)[None]
+        prop, obj = mo.rpn_select(logits, deltas, im_w, im_h, pre_nms, post_nms, nms_thresh, min_size, stride,
+                                  cuda_semantics=True)
+        k = prop.shape[0]
+        boxes[i, :k], scores[i, :k] = prop, obj
+        count[i] = k
+    return boxes, scores, anchor, count
+
+
+def roi_align_nhwc(feat, boxes, roi_batch, scale, ph, pw, sampling_ratio, out):
+    k = boxes.shape[0]
+    b = roi_batch.float().view(-1, 1) if roi_batch is not None else torch.zeros(k, 1)
+    pooled = mo.roi_align(feat.permute(0, 3, 1, 2).float().contiguous(), torch.cat([b, boxes.float()], 1), scale, ph, pw,
+                          sampling_ratio)                                   # [K, C, ph, pw]
+    out.copy_(pooled.permute(0, 2, 3, 1).reshape(k, -1).to(out.dtype))      # bin-major, channel-minor
+    return out
+
+
+# ------------------------------------------------------------------------------------------- FGFA / DFF helpers
+def fgfa_pool_image(img, out):
+    p = F.avg_pool2d(img.reshape(1, 3, img.shape[-2], img.shape[-1]) / 255, 2, stride=2, ceil_mode=True)[0]
+    out.zero_()
+    out[..., 0:3] = p.permute(1, 2, 0).to(out.dtype)
+    return out
+
+
+def fgfa_build_pairs(ring, slots, key_pos, pairs):
+    hq, wq = ring.shape[1], ring.shape[2]
+    pairs.zero_()
+    key = ring[int(slots[key_pos])]
+    for f in range(slots.numel()):
+        pairs[f, 3:3 + hq, 3:3 + wq, 0:3] = key[..., 0:3]
+        pairs[f, 3:3 + hq, 3:3 + wq, 4:7] = ring[int(slots[f])][..., 0:3]
+    return pairs
+
+
+def avgpool2_nhwc(x, out):
+    y = F.avg_pool2d(x.permute(0, 3, 1, 2).float(), 2, stride=2, ceil_mode=True, count_include_pad=False)
+    out.copy_(y.permute(0, 2, 3, 1).to(out.dtype))
+    return out
+
+
+def dff_warp_scale(key_feats, flow, scale, out):
+    c = key_feats.shape[2]
+    warped = mo.fgfa_warp(key_feats.permute(2, 0, 1)[None].float(), flow[..., :2].permute(2, 0, 1)[None].float())
+    out[..., :c] = (warped[0].permute(1, 2, 0) * scale[..., :c].float()).to(out.dtype)
+    return out
+
+
 class _Event(object):
     def record(self, *a):
         pass
@@ -105,13 +177,17 @@ class _Event(object):
 def cpu_ops():
     from mega_core import _lib
     from mega_core.b200 import ops
-    saved_ops = {n: getattr(ops, n) for n in ("conv_gemm", "gather_rows", "copy_rows", "copy_batch", "relation_softmax",
-                                              "box_postprocess")}
+    mine = {"conv_gemm": _shadow_conv_gemm, "gather_rows": gather_rows, "copy_rows": copy_rows, "copy_batch": copy_batch,
+            "relation_softmax": relation_softmax, "box_postprocess": box_postprocess, "stem_prep": stem_prep,
+            "maxpool3x3s2": maxpool3x3s2, "rpn_select": rpn_select, "roi_align_nhwc": roi_align_nhwc,
+            "fgfa_pool_image": fgfa_pool_image, "fgfa_build_pairs": fgfa_build_pairs, "avgpool2_nhwc": avgpool2_nhwc,
+            "dff_warp_scale": dff_warp_scale}
+    saved_ops = {n: getattr(ops, n) for n in mine}
     saved = (torch.Tensor.pin_memory, torch.cuda.Event, _lib.require_cuda, ops.require_cuda, ops.AUTOTUNE[0])
     saved_chains = ops.CHAINS_ENABLED[0]
     ops.CHAINS_ENABLED[0] = False                   # fp16 engines: per-layer calls instead of the persistent chain kernel
-    ops.conv_gemm, ops.gather_rows, ops.copy_rows, ops.copy_batch = _shadow_conv_gemm, gather_rows, copy_rows, copy_batch
-    ops.relation_softmax, ops.box_postprocess = relation_softmax, box_postprocess
+    for n, f in mine.items():
+        setattr(ops, n, f)
     torch.Tensor.pin_memory = lambda self, *a, **k: self
     torch.cuda.Event = _Event
     _lib.require_cuda = ops.require_cuda = lambda *a: None
