@@ -165,12 +165,40 @@ def dff_warp_scale(key_feats, flow, scale, out):
     return out
 
 
+def fgfa_aggregate(ring, slots, key_pos, flow, out, feat_channels, embed_channels, weights_out=None):
+    """warp every cached [feats | embedding] map along its flow, cosine-similarity weights against the key frame's
+    warped embedding, soft-max over frames, weighted sum (generalized_rcnn_fgfa.py:45-76, :206-214)"""
+    maps = torch.stack([ring[int(s_)] for s_ in slots]).permute(0, 3, 1, 2).float()          # [L, C, h, w]
+    warped = mo.fgfa_warp(maps, flow[..., :2].permute(0, 3, 1, 2).float())
+    wf, emb = warped[:, :feat_channels], warped[:, feat_channels:feat_channels + embed_channels]
+    en = emb / (torch.norm(emb, dim=1, keepdim=True) + 1e-10)
+    ec = en[key_pos:key_pos + 1]
+    wts = torch.softmax(torch.sum(en * ec, dim=1, keepdim=True), dim=0)
+    out[..., :feat_channels] = torch.sum(wts * wf, dim=0).permute(1, 2, 0).to(out.dtype)
+    if weights_out is not None:
+        weights_out.copy_(wts[:, 0].reshape(weights_out.shape))
+    return out
+
+
 class _Event(object):
     def record(self, *a):
         pass
 
     def synchronize(self):
         pass
+
+
+class _Stream(object):
+    def __init__(self, *a, **k):
+        pass
+
+    def wait_stream(self, other):
+        pass
+
+
+@contextlib.contextmanager
+def _stream_ctx(stream):
+    yield
 
 
 @contextlib.contextmanager
@@ -181,9 +209,11 @@ def cpu_ops():
             "relation_softmax": relation_softmax, "box_postprocess": box_postprocess, "stem_prep": stem_prep,
             "maxpool3x3s2": maxpool3x3s2, "rpn_select": rpn_select, "roi_align_nhwc": roi_align_nhwc,
             "fgfa_pool_image": fgfa_pool_image, "fgfa_build_pairs": fgfa_build_pairs, "avgpool2_nhwc": avgpool2_nhwc,
-            "dff_warp_scale": dff_warp_scale}
+            "dff_warp_scale": dff_warp_scale, "fgfa_aggregate": fgfa_aggregate}
     saved_ops = {n: getattr(ops, n) for n in mine}
     saved = (torch.Tensor.pin_memory, torch.cuda.Event, _lib.require_cuda, ops.require_cuda, ops.AUTOTUNE[0])
+    saved_streams = (torch.cuda.current_stream, torch.cuda.Stream, torch.cuda.stream)
+    torch.cuda.current_stream, torch.cuda.Stream, torch.cuda.stream = (lambda *a, **k: _Stream()), _Stream, _stream_ctx
     saved_chains = ops.CHAINS_ENABLED[0]
     ops.CHAINS_ENABLED[0] = False                   # fp16 engines: per-layer calls instead of the persistent chain kernel
     for n, f in mine.items():
@@ -198,3 +228,4 @@ def cpu_ops():
             setattr(ops, n, f)
         torch.Tensor.pin_memory, torch.cuda.Event, _lib.require_cuda, ops.require_cuda, ops.AUTOTUNE[0] = saved
         ops.CHAINS_ENABLED[0] = saved_chains
+        torch.cuda.current_stream, torch.cuda.Stream, torch.cuda.stream = saved_streams
