@@ -443,6 +443,50 @@ class HeadCommon:
         return Detections(*out)
 
 
+class MlpHeadMixin:
+    """the single-frame box head shared by the base / FGFA / DFF engines: res5 (+ the optional channel-reduction conv) ->
+    ROIAlign -> fc6 -> fc7 -> predictor -> post-processing (ResNetConv52MLPFeatureExtractor, extractors :106-118)"""
+
+    def _init_mlp_head(self, sd):
+        dev, act = self.dev, self.act
+        res = self.cfg.pooler_resolution
+        self.reduce = (FE + "conv.weight") in sd
+        if self.reduce:
+            self.red_w = pack_conv(sd[FE + "conv.weight"], dev, act)
+            self.red_b = sd[FE + "conv.bias"].float().contiguous().to(dev)
+        w6 = sd[FE + "fc6.weight"].float()
+        ch = w6.shape[1] // (res * res)
+        self.ch = ch
+        # fc6 columns: reference order c * 49 + bin -> bin * C + c (the ROIAlign output is bin-major here)
+        self.fc6_w = (w6.reshape(w6.shape[0], ch, res * res).permute(0, 2, 1).reshape(w6.shape[0], -1).contiguous()
+                      .to(dev).to(act))
+        self.fc6_b = sd[FE + "fc6.bias"].float().contiguous().to(dev)
+        self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev).to(act)
+        self.fc7_b = sd[FE + "fc7.bias"].float().contiguous().to(dev)
+
+    def _mlp_head(self, feats, im_w, im_h):
+        """feats [1, h, w, 1024] (backbone map, or its aggregated / warped replacement) -> Detections"""
+        c = self.cfg
+        KP = c.post_nms_top_n
+        boxes, _, cnt = self.rpn(feats, im_w, im_h, KP)
+        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained):
+            x = self.res5.forward(feats)
+            if self.reduce:
+                n, h, w, _ = x.shape
+                xr = self._buf("reduce", (n, h, w, self.red_w.shape[1]), self.act)
+                ops.conv_gemm(x, self.red_w, xr, bias=self.red_b, relu=True)
+                x = xr
+        res = c.pooler_resolution
+        pooled = self._buf("pooled", (KP, res * res * self.ch), self.act)
+        ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)
+        f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]), self.act)
+        ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True)
+        f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]), self.act)
+        ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
+        self.last_feats, self.last_props, self.last_cnt, self.last_pooled = feats, boxes[0], cnt, pooled
+        return self.predict_and_postprocess(f7, boxes[0], cnt[0:1], im_w, im_h)
+
+
 class WindowedEngine(HeadCommon):
     """what the windowed video methods (MEGA, RDN) share: the per-frame branch backbone -> RPN -> res5 -> ROIAlign ->
     fcs[0], the ring of per-frame ROI features addressed by slot, and CUDA-graph capture of fixed launch sequences.
@@ -1288,7 +1332,7 @@ class RdnEngine(WindowedEngine):
         return self.predict_and_postprocess(self.X3, bk, kcnt, im_w, im_h)
 
 
-class BaseEngine(HeadCommon):
+class BaseEngine(HeadCommon, MlpHeadMixin):
     """GeneralizedRCNN single-frame path (detector/generalized_rcnn.py:33-65) with
     ResNetConv52MLPFeatureExtractor (extractors :106-118, REDUCE_CHANNEL optional)."""
 
@@ -1296,42 +1340,11 @@ class BaseEngine(HeadCommon):
         cfg = cfg or EngineConfig()
         dev = torch.device(device)
         super().__init__(sd, cfg, dev)
-        res = cfg.pooler_resolution
-        self.reduce = (FE + "conv.weight") in sd
-        if self.reduce:
-            self.red_w = pack_conv(sd[FE + "conv.weight"], dev, self.act)
-            self.red_b = sd[FE + "conv.bias"].float().contiguous().to(dev)
-        w6 = sd[FE + "fc6.weight"].float()
-        ch = w6.shape[1] // (res * res)
-        self.ch = ch
-        self.fc6_w = (w6.reshape(w6.shape[0], ch, res * res).permute(0, 2, 1).reshape(w6.shape[0], -1).contiguous()
-                      .to(dev).to(self.act))
-        self.fc6_b = sd[FE + "fc6.bias"].float().contiguous().to(dev)
-        self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev).to(self.act)
-        self.fc7_b = sd[FE + "fc7.bias"].float().contiguous().to(dev)
+        self._init_mlp_head(sd)
 
     @_with_precision
     def forward(self, img, im_w, im_h):
-        c = self.cfg
-        KP = c.post_nms_top_n
-        feats = self.backbone.forward(img)
-        boxes, _, cnt = self.rpn(feats, im_w, im_h, KP)
-        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained):
-            x = self.res5.forward(feats)
-            if self.reduce:
-                n, h, w, _ = x.shape
-                xr = self._buf("reduce", (n, h, w, self.red_w.shape[1]), self.act)
-                ops.conv_gemm(x, self.red_w, xr, bias=self.red_b, relu=True)
-                x = xr
-        res = c.pooler_resolution
-        pooled = self._buf("pooled", (KP, res * res * self.ch), self.act)
-        ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)
-        f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]), self.act)
-        ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True)
-        f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]), self.act)
-        ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
-        self.last_feats, self.last_props, self.last_cnt, self.last_pooled = feats, boxes[0], cnt, pooled
-        return self.predict_and_postprocess(f7, boxes[0], cnt[0:1], im_w, im_h)
+        return self._mlp_head(self.backbone.forward(img), im_w, im_h)
 
 
 # =============================================================================================== FGFA
@@ -1487,7 +1500,7 @@ class FlowNetS:
         return flow
 
 
-class FgfaEngine(HeadCommon):
+class FgfaEngine(HeadCommon, MlpHeadMixin):
     """GeneralizedRCNNFGFA._forward_test (detector/generalized_rcnn_fgfa.py:144-219) with the single-frame box head
     (ResNetConv52MLPFeatureExtractor without channel reduction). Per frame the backbone map, the EmbedNet embedding
     (backbone/embednet.py:19-24) and the pooled image are cached in rings of 19 slots; every step FlowNetS runs on the 19
@@ -1503,15 +1516,7 @@ class FgfaEngine(HeadCommon):
         e = "embednet."
         self.e_w = [pack_conv(sd[e + "embed_conv%d.weight" % i], dev, act) for i in (1, 2, 3)]
         self.e_b = [sd[e + "embed_conv%d.bias" % i].float().contiguous().to(dev) for i in (1, 2, 3)]
-        res = cfg.pooler_resolution
-        w6 = sd[FE + "fc6.weight"].float()
-        ch = w6.shape[1] // (res * res)
-        self.ch = ch
-        self.fc6_w = (w6.reshape(w6.shape[0], ch, res * res).permute(0, 2, 1).reshape(w6.shape[0], -1).contiguous()
-                      .to(act).to(dev))
-        self.fc6_b = sd[FE + "fc6.bias"].float().contiguous().to(dev)
-        self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev).to(act)
-        self.fc7_b = sd[FE + "fc7.bias"].float().contiguous().to(dev)
+        self._init_mlp_head(sd)
         self.slots_h = torch.zeros(self.L, dtype=torch.int32).pin_memory()
         self.slots_d = torch.zeros(self.L, dtype=torch.int32, device=dev)
         self.ring = None
@@ -1589,24 +1594,11 @@ class FgfaEngine(HeadCommon):
         flow = self.flownet.forward(self.pairs)
         self.last_flow = flow
         ops.fgfa_aggregate(self.ring, self.slots_d, self.KL, flow, self.agg[0], 1024, 2048)
-        feats = self.agg
-        KP = c.post_nms_top_n
-        boxes, _, cnt = self.rpn(feats, im_w, im_h, KP)
-        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained):
-            x = self.res5.forward(feats)
-        res = c.pooler_resolution
-        pooled = self._buf("pooled", (KP, res * res * self.ch), self.act)
-        ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)
-        f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]), self.act)
-        ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True)
-        f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]), self.act)
-        ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
-        self.last_feats, self.last_props, self.last_cnt = feats, boxes[0], cnt
-        return self.predict_and_postprocess(f7, boxes[0], cnt[0:1], im_w, im_h)
+        return self._mlp_head(self.agg, im_w, im_h)
 
 
 # =============================================================================================== DFF
-class DffEngine(HeadCommon):
+class DffEngine(HeadCommon, MlpHeadMixin):
     """GeneralizedRCNNDFF._forward_test (detector/generalized_rcnn_dff.py:119-138): the backbone runs on key frames only
     (every 10th frame, data/datasets/vid_dff.py:52-55); every frame runs FlowNetS on the pair (frame, key frame), warps
     the key frame's feature map along the flow, multiplies it by FlowNetS's scale map (one kernel, csrc/fgfa.cu) and
@@ -1622,15 +1614,7 @@ class DffEngine(HeadCommon):
         act = self.act
         self.flownet = FlowNetS(sd, dev, act)
         assert self.flownet.w_scale is not None, "state_dict has no flownet.Convolution5_scale (not a DFF model)"
-        res = cfg.pooler_resolution
-        w6 = sd[FE + "fc6.weight"].float()
-        ch = w6.shape[1] // (res * res)
-        self.ch = ch
-        self.fc6_w = (w6.reshape(w6.shape[0], ch, res * res).permute(0, 2, 1).reshape(w6.shape[0], -1).contiguous()
-                      .to(act).to(dev))
-        self.fc6_b = sd[FE + "fc6.bias"].float().contiguous().to(dev)
-        self.fc7_w = sd[FE + "fc7.weight"].float().contiguous().to(dev).to(act)
-        self.fc7_b = sd[FE + "fc7.bias"].float().contiguous().to(dev)
+        self._init_mlp_head(sd)
         self.slots_d = torch.tensor([0, 1], dtype=torch.int32, device=dev)      # ring slot 0: current frame, 1: key frame
         self._shape, self.has_key = None, False
 
@@ -1668,17 +1652,4 @@ class DffEngine(HeadCommon):
         flow, scale = self.flownet.forward(self.pairs[1:2], want_scale=True)
         self.last_flow, self.last_scale = flow, scale
         ops.dff_warp_scale(self.key_feats[0], flow[0], scale[0], self.warped[0])
-        feats = self.warped
-        KP = c.post_nms_top_n
-        boxes, _, cnt = self.rpn(feats, im_w, im_h, KP)
-        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained):
-            x = self.res5.forward(feats)
-        res = c.pooler_resolution
-        pooled = self._buf("pooled", (KP, res * res * self.ch), self.act)
-        ops.roi_align_nhwc(x, boxes[0], None, c.pooler_scale, res, res, c.sampling_ratio, pooled)
-        f6 = self._buf("fc6", (KP, self.fc6_w.shape[0]), self.act)
-        ops.linear(pooled, self.fc6_w, f6, bias=self.fc6_b, relu=True)
-        f7 = self._buf("fc7", (KP, self.fc7_w.shape[0]), self.act)
-        ops.linear(f6, self.fc7_w, f7, bias=self.fc7_b, relu=True)
-        self.last_feats, self.last_props, self.last_cnt = feats, boxes[0], cnt
-        return self.predict_and_postprocess(f7, boxes[0], cnt[0:1], im_w, im_h)
+        return self._mlp_head(self.warped, im_w, im_h)

@@ -25,10 +25,6 @@ import mega_oracle as mo  # noqa: E402
 from fp32_shadow import _shadow_conv_gemm  # noqa: E402
 
 
-def _rows(t, n, row_len):
-    return t.reshape(-1, t.shape[-1])[:, :row_len] if t.dim() != 2 else t[:, :row_len]
-
-
 def gather_rows(src, idx, dst, n_rows=None, row_len=None):
     n_rows = idx.numel() if n_rows is None else n_rows
     row_len = src.shape[-1] if row_len is None else row_len
