@@ -159,3 +159,26 @@ def test_wavefront_engine_step_over_gloo():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+def test_replicated_state_step_does_not_depend_on_world_size():
+    """the DEFAULT multi-GPU step (dist_step: owner rows on the frame's owner, memory-feeding rows replicated) on the
+    stand-ins: both ranks of a 2-rank group, played one after the other with the payloads handed over, give the
+    1-rank results bit for bit (CPU counterpart of the GPU test of the same name in tests/test_engine_gpu.py)"""
+    from mega_core.b200 import synth
+    sd = synth.make_state_dict("mega_r101_tiny", seed=3)
+    frames = 6
+    with cpu_ops():
+        solo = _make(sd)
+        _prime(solo, 1)
+        payloads = [_payload(solo, 100 + t) for t in range(frames)]
+        seq = [_snap(solo, solo.dist_step(None, W_IMG, H_IMG, rank=0, world=1, payloads=payloads[t][None])[0])
+               for t in range(frames)]
+        for rank in (0, 1):
+            e = _make(sd)
+            _prime(e, 1)
+            for t in range(0, frames, 2):
+                dets = e.dist_step(None, W_IMG, H_IMG, rank=rank, world=2, payloads=torch.stack(payloads[t:t + 2]))
+                assert dets[1 - rank] is None
+                for a, b in zip(seq[t + rank], _snap(e, dets[rank])):
+                    assert torch.equal(a, b), (rank, t)
