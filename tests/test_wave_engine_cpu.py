@@ -55,8 +55,8 @@ def _payload(eng, seed):
     return p
 
 
-def _snap(eng, det):
-    k = int(eng.cur_cnt.view(-1)[0])
+def _snap(eng, det, k=None):
+    k = int(eng.cur_cnt.view(-1)[0]) if k is None else k
     n = int(det.count.reshape(-1)[0])
     return eng.last_pred[:k].clone(), det.boxes[:n].clone(), det.scores[:n].clone(), det.labels[:n].clone()
 
@@ -172,13 +172,16 @@ def test_replicated_state_step_does_not_depend_on_world_size():
         solo = _make(sd)
         _prime(solo, 1)
         payloads = [_payload(solo, 100 + t) for t in range(frames)]
-        seq = [_snap(solo, solo.dist_step(None, W_IMG, H_IMG, rank=0, world=1, payloads=payloads[t][None])[0])
-               for t in range(frames)]
+        seq, seq_k = [], []
+        for t in range(frames):
+            seq.append(_snap(solo, solo.dist_step(None, W_IMG, H_IMG, rank=0, world=1, payloads=payloads[t][None])[0]))
+            seq_k.append(int(solo.cur_cnt.view(-1)[0]))         # live proposals of key frame t
         for rank in (0, 1):
             e = _make(sd)
             _prime(e, 1)
             for t in range(0, frames, 2):
                 dets = e.dist_step(None, W_IMG, H_IMG, rank=rank, world=2, payloads=torch.stack(payloads[t:t + 2]))
                 assert dets[1 - rank] is None
-                for a, b in zip(seq[t + rank], _snap(e, dets[rank])):
+                # (rank 0 has meanwhile assembled the window of the foreign frame t + 1: its cur_cnt is that frame's)
+                for a, b in zip(seq[t + rank], _snap(e, dets[rank], seq_k[t + rank])):
                     assert torch.equal(a, b), (rank, t)
