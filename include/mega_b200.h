@@ -346,6 +346,14 @@ int mega_image_transform_u8(const unsigned char* src, int src_h, int src_w, long
                             int out_w, const float* mean_host, const float* std_host, int to_bgr255, float* out,
                             void* stream);
 
+/* HOST function (no device work, all pointers are host pointers): greedy matching of one image's detections of one class,
+ * already sorted by descending score, against that class's ground-truth boxes -- the inner loops of
+ * calc_detection_vid_prec_rec (data/datasets/evaluation/vid/vid_eval.py:201-262).
+ * match_out[j] in {0, 1}; pred_ignore_out[j] = the reference's pred_ignore entry (0, 1, a fraction, or empty_weight). */
+int mega_vid_match_host(const float* pred_boxes, int n_pred, const float* gt_boxes, const unsigned char* gt_ignore,
+                        int n_gt, float iou_thresh, double empty_weight, signed char* match_out,
+                        double* pred_ignore_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -198,6 +198,8 @@ lib.mega_image_transform_u8.argtypes = [_vp, _i, _i, _ll, _vp, _vp, _i, _vp, _vp
 lib.mega_image_transform_u8.restype = _i
 lib.mega_dff_warp_scale.argtypes = [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _vp, _ll, _i, _vp]
 lib.mega_dff_warp_scale.restype = _i
+lib.mega_vid_match_host.argtypes = [_vp, _i, _vp, _vp, _i, _f, ctypes.c_double, _vp, _vp]
+lib.mega_vid_match_host.restype = _i
 
 EXPORTS = [
     "mega_last_error", "mega_abi_version", "mega_device_ok", "mega_conv_gemm", "mega_conv_gemm_tf32", "mega_conv_gemm_workspace_bytes", "mega_set_tf32_rounding",
@@ -211,5 +213,5 @@ EXPORTS = [
     "mega_stem_prep", "mega_fgfa_pool_image", "mega_fgfa_build_pairs", "mega_avgpool2_nhwc", "mega_fgfa_aggregate",
     "mega_roi_align_backward_nchw", "mega_roi_pool_forward", "mega_roi_pool_backward", "mega_deform_im2col_kq",
     "mega_deform_col2im_fused", "mega_channel_sum_nchw", "mega_deform_psroi_pooling_backward",
-    "mega_image_transform_u8", "mega_dff_warp_scale",
+    "mega_image_transform_u8", "mega_dff_warp_scale", "mega_vid_match_host",
 ]
