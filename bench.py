@@ -56,9 +56,12 @@ def parse():
     ap.add_argument("--no-strict", action="store_true", help="skip the extra fp32x3 (strict-parity mode) timing")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--wave", action="store_true",
-                    help="N > 1: wavefront schedule (MegaEngine.dist_step_wave: a rank aggregates only its own key frame, "
-                         "memory increments exchanged per stage) instead of the replicated-state dist_step; "
-                         "also MEGA_B200_WAVE=1. Experimental: first GPU run pending")
+                    help="N > 1: force the wavefront schedule (MegaEngine.dist_step_wave: a rank aggregates only its own "
+                         "key frame, memory increments exchanged per stage) without the self-check; also MEGA_B200_WAVE=1")
+    ap.add_argument("--no-wave", action="store_true",
+                    help="N > 1: keep the replicated-state schedule (dist_step). Default: every rank replays "
+                         "parallel.wave_selfcheck on its own GPU (wavefront vs sequential step, bit-identity of outputs "
+                         "and memory rings, with CUDA graphs) and the run uses the wavefront schedule only if ALL ranks pass")
     ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -176,6 +179,24 @@ def run_b200(args, rank, world):
     pairs_pinned = [torch.cat([pool[(i + 12) % 16], pool[(5 * i + 3) % 16]], 0).pin_memory() for i in range(16)]
 
     wave = world > 1 and (args.wave or os.environ.get("MEGA_B200_WAVE", "0") == "1")
+    wave_note = "forced" if wave else None
+    if world > 1 and not wave and not args.no_wave:
+        # the wavefront schedule was verified on the CPU only when it was written; each rank proves it on its own device
+        # first (no communication inside the check, one MIN all-reduce of the verdicts after it)
+        from mega_core.b200 import parallel
+        ok, wave_note = False, ""
+        try:
+            with torch.no_grad():
+                ok, wave_note = parallel.wave_selfcheck(lambda: engine.MegaEngine(sd, eng.cfg, dev), w, h, world=2, groups=3,
+                                                        use_graph=not args.no_graph)
+        except Exception as e:                      # any surprise keeps the proven schedule
+            ok, wave_note = False, "self-check raised %s: %s" % (type(e).__name__, str(e)[:200])
+        verdict = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(verdict, op=dist.ReduceOp.MIN)
+        wave = int(verdict.item()) == 1
+        if not wave and ok:
+            wave_note = "another rank failed the self-check"
+        torch.cuda.empty_cache()
 
     def dstep(pair):
         return eng.dist_step_wave(pair, w, h) if wave else eng.dist_step(pair, w, h)[rank]
@@ -259,6 +280,8 @@ def run_b200(args, rank, world):
                                   ("frame-parallel over %d GPUs, wavefront schedule: per-frame branch and the whole aggregation "
                                    "of a key frame on its owner, NCCL all-gather of the ROI-feature payloads + one all-gather of "
                                    "the memory increments per relation stage" % world) if wave else "single GPU",
+                   "schedule": ("wavefront" if wave else "replicated-state") if world > 1 else None,
+                   "wave_selfcheck": wave_note,
                    "cuda_graph": bool(eng._graphs), "precision": args.precision,
                    "l2": "per-step working set (0.7 GB fp32 weights + >0.5 GB activations) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,

@@ -103,3 +103,75 @@ def play(gens):
             except StopIteration as stop:
                 results[r], done[r] = stop.value, True
     return results
+
+
+# ---------------------------------------------------------------------------------------------- wavefront self-check
+# Before a multi-GPU run switches to the wavefront schedule, every rank can replay this check on its own device without
+# any communication: random (but valid) window / global-pool state and frame payloads, the sequential owner-mode step as
+# the truth, both ranks of a 2-rank wavefront group played in-process; it passes only if every predictor output, every
+# detection and every memory ring is bit-identical. The engines run with CUDA graphs on, over enough groups that each
+# wavefront segment is executed eagerly, captured and replayed. Cheap: no backbone work is involved.
+def _rand_boxes(gen, n, im_w, im_h):
+    x1 = torch.rand(n, generator=gen) * (im_w - 80)
+    y1 = torch.rand(n, generator=gen) * (im_h - 80)
+    return torch.stack([x1, y1, x1 + 10 + torch.rand(n, generator=gen) * 60, y1 + 10 + torch.rand(n, generator=gen) * 60], 1)
+
+
+def random_state(eng, seed, im_w, im_h):
+    """put a MegaEngine into the state of a video whose window and global pool are full (memory still empty)"""
+    gen = torch.Generator().manual_seed(seed)
+    eng.reset()
+    for _ in range(eng.L):
+        eng._claim_slot()
+    eng.win_x.copy_((torch.randn(eng.win_x.shape, generator=gen) * 0.5).to(eng.win_x.dtype))
+    eng.win_boxes.copy_(_rand_boxes(gen, eng.win_boxes.shape[0], im_w, im_h))
+    eng.win_cnt.fill_(eng.KP - 3)
+    eng.glob_x.copy_((torch.randn(eng.glob_x.shape, generator=gen) * 0.5).to(eng.glob_x.dtype))
+    eng.glob_pushed = eng.GF
+
+
+def random_payload(eng, seed, im_w, im_h):
+    """what a rank's per-frame branch hands to the gather: x300 | boxes | count | x75, filled with seeded noise"""
+    gen = torch.Generator().manual_seed(seed)
+    p = torch.zeros_like(eng.payload_in)
+    px, pb, pc, pg = eng._payload_views(p)
+    px.copy_((torch.randn(px.shape, generator=gen) * 0.5).to(px.dtype))
+    pb.copy_(_rand_boxes(gen, pb.shape[0], im_w, im_h))
+    pc.view(torch.int32)[0, 0] = eng.KP - 1 - seed % 4
+    pg.copy_((torch.randn(pg.shape, generator=gen) * 0.5).to(pg.dtype))
+    return p
+
+
+def wave_selfcheck(make_engine, im_w=1000, im_h=600, world=2, groups=3, seed=0, use_graph=True):
+    """-> (ok, message). `make_engine()` must return fresh MegaEngines with identical weights on the current device."""
+    def snap(eng, det):
+        if eng.dev.type == "cuda":
+            torch.cuda.synchronize(eng.dev)
+        k, n = int(eng.cur_cnt.view(-1)[0]), int(det.count.reshape(-1)[0])
+        return [eng.last_pred[:k].clone(), det.boxes[:n].clone(), det.scores[:n].clone(), det.labels[:n].clone()]
+
+    solo = make_engine()
+    ranks = [make_engine() for _ in range(world)]
+    for e in [solo] + ranks:
+        e.use_graph = use_graph
+        random_state(e, seed, im_w, im_h)
+    frames = groups * world
+    payloads = [random_payload(solo, seed + 100 + t, im_w, im_h) for t in range(frames)]
+    truth = [snap(solo, solo.dist_step(None, im_w, im_h, rank=0, world=1, payloads=payloads[t][None])[0])
+             for t in range(frames)]
+    if not any(t[1].shape[0] for t in truth):
+        return False, "self-check is degenerate: the sequential step produced no detections"
+    for t0 in range(0, frames, world):
+        dets = play([ranks[r]._wave(None, im_w, im_h, r, world, payload=payloads[t0 + r]) for r in range(world)])
+        for r in range(world):
+            for i, (a, b) in enumerate(zip(truth[t0 + r], snap(ranks[r], dets[r]))):
+                if not torch.equal(a, b):
+                    return False, "key frame %d: %s differs from the sequential step" % (
+                        t0 + r, ("predictor output", "boxes", "scores", "labels")[i])
+    rings = {"E0": solo.KP + solo.nl0, "B0": solo.KP + solo.nl0, "Y1E": solo.nq, "Y2M": solo.nq, "B1": solo.nl12,
+             "B2": solo.nl12, "win_x": 0, "win_boxes": 0, "win_cnt": 0, "glob_x": 0}
+    for r in range(world):
+        for name, off in rings.items():
+            if not torch.equal(getattr(ranks[r], name)[off:], getattr(solo, name)[off:]):
+                return False, "rank %d: ring %s differs from the sequential state" % (r, name)
+    return True, "wavefront == sequential over %d key frames (bit-identical outputs and rings)" % frames

@@ -185,3 +185,27 @@ def test_replicated_state_step_does_not_depend_on_world_size():
                 # (rank 0 has meanwhile assembled the window of the foreign frame t + 1: its cur_cnt is that frame's)
                 for a, b in zip(seq[t + rank], _snap(e, dets[rank], seq_k[t + rank])):
                     assert torch.equal(a, b), (rank, t)
+
+
+def test_wave_selfcheck_function():
+    """parallel.wave_selfcheck (what bench.py runs on every rank before it switches a multi-GPU run to the wavefront
+    schedule) on the stand-ins: passes on the real engine, and reports a deliberately broken schedule"""
+    from mega_core.b200 import parallel, synth
+    sd = synth.make_state_dict("mega_r101_tiny", seed=3)
+    with cpu_ops():
+        ok, msg = parallel.wave_selfcheck(lambda: _make(sd), W_IMG, H_IMG, world=2, groups=3, use_graph=False)
+        assert ok, msg
+        orig = parallel.wave_tables
+
+        def broken(*a, **k):                 # apply every increment BEFORE the reads: later frames' slots get clobbered
+            t = orig(*a, **k)
+            for key in ("0", "12", "b12"):
+                both = torch.from_numpy(t["pre" + key]).maximum(torch.from_numpy(t["post" + key])).numpy()
+                t["pre" + key], t["post" + key] = both, 0 * both - 1
+            return t
+        parallel.wave_tables = broken
+        try:
+            ok, msg = parallel.wave_selfcheck(lambda: _make(sd), W_IMG, H_IMG, world=2, groups=3, use_graph=False)
+        finally:
+            parallel.wave_tables = orig
+        assert not ok and "differs" in msg

@@ -14,7 +14,7 @@ if [ -z "$WAVE" ]; then
 else
   # 3. wavefront schedule vs replicated-state schedule at N GPUs (N = number of visible devices)
   N=$(python -c "import torch; print(torch.cuda.device_count())")
-  for mode in "" "--wave"; do
+  for mode in "--no-wave" ""; do        # "" = default: wavefront if every rank passes parallel.wave_selfcheck
     timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 \
       bench.py --gpus $N --steps 30 --warmup 6 --skip-cpu-baseline --no-strict $mode > gpurun_out/r2_bench_${N}gpu${mode}.json 2> gpurun_out/r2_bench_${N}gpu${mode}.err
     echo "N=$N mode='$mode' rc=$?"; tail -2 gpurun_out/r2_bench_${N}gpu${mode}.err
