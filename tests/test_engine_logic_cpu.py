@@ -56,23 +56,46 @@ def _check_frame(eng, det, ref, t, logit_tol=1e-3):
     assert n == ref["boxes"].shape[0] and torch.equal(det.labels[:n], ref["labels"]), "frame %d: detections" % t
 
 
-def test_mega_engine_logic_matches_reference_fixture():
-    """MegaEngine (the hot path: start_video with 13 local + 10 global frames, then a steady-state step through the
-    index tables, window / global rings, long-range memory pushes, fused aggregation) vs the unmodified reference's
-    GeneralizedRCNNMEGA outputs"""
+def test_mega_module_and_engine_logic_match_reference_fixture():
+    """The hot path through the reference-facing module API: GeneralizedRCNNMEGA built by
+    build_detection_model(cfg), weights through load_state_dict, `model(images)` with the dict VIDMEGADataset builds
+    (frame 0 with its look-ahead and global frames, then a steady-state frame) -> list[BoxList]; underneath, MegaEngine's
+    start_video / step: index tables, window / global rings, long-range memory pushes, fused aggregation. Against the
+    unmodified reference's GeneralizedRCNNMEGA outputs."""
     from mega_core.b200 import engine, synth
+    from mega_core.modeling.detector import build_detection_model_from_state_dict
+    from mega_core.modeling.nets import engine_config_from
     gold = torch.load(os.path.join(ROOT, "tests", "golden", "mega_r101_192x320.pt"))
     h, w, total = gold["h"], gold["w"], gold["total"]
     sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
     frames = [synth.synthetic_frame(i, h, w) for i in range(total)]
     gpf = gold["globals_per_frame"]
     with cpu_ops():
-        eng = engine.MegaEngine(sd, engine.EngineConfig(precision="tf32"), device="cpu")
+        model = build_detection_model_from_state_dict(sd, method="mega", device="cpu", precision="tf32")
+        # the module refuses to build its engine off-GPU; hand it one on the stand-ins (test only)
+        model._engine = eng = engine.MegaEngine(model.state_dict(), engine_config_from(model.cfg), "cpu")
         eng.use_graph = False
-        det = eng.start_video(frames[0], frames[1:13], [frames[j] for j in gpf[0]], w, h)
-        _check_frame(eng, det, gold["frames"][0], 0)
-        det = eng.step(frames[min(1 + 12, total - 1)], frames[gpf[1][0]], w, h)
-        _check_frame(eng, det, gold["frames"][1], 1)
+        common = {"seg_len": total, "pattern": "%06d", "img_dir": "/nonexistent/%s.JPEG"}
+        out = model({"cur": frames[0][0], "ref_l": [], "ref_g": [frames[j][0] for j in gpf[0]], "frame_category": 0,
+                     "lookahead": [f[0] for f in frames[1:13]], **common})
+        ref = gold["frames"][0]
+        assert len(out) == 1 and out[0].size == (w, h)
+        assert torch.equal(out[0].get_field("labels"), ref["labels"])
+        assert torch.allclose(out[0].bbox, ref["boxes"], atol=2e-2) and torch.allclose(out[0].get_field("scores"), ref["scores"], atol=1e-3)
+        _check_frame(eng, eng_det(eng), ref, 0)
+        out = model({"cur": frames[1][0], "ref_l": [frames[min(1 + 12, total - 1)][0]], "ref_g": [frames[gpf[1][0]][0]],
+                     "frame_category": 1, **common})
+        ref = gold["frames"][1]
+        assert torch.equal(out[0].get_field("labels"), ref["labels"]) and torch.allclose(out[0].bbox, ref["boxes"], atol=2e-2)
+        _check_frame(eng, eng_det(eng), ref, 1)
+
+
+def eng_det(eng):
+    """the engine's static detection buffers of the last frame"""
+    from mega_core.b200.engine import Detections
+    b = eng._bufs
+    get = lambda tag: [v for (t, _, _), v in b.items() if t == tag][0]        # noqa: E731
+    return Detections(get("det_boxes"), get("det_scores"), get("det_labels"), get("det_count"))
 
 
 def test_base_engine_logic_matches_reference_fixture():
@@ -115,3 +138,27 @@ def test_fgfa_engine_logic_matches_reference_fixture():
         ref = gold["frames"][0]
         assert (eng.last_flow[..., :2].permute(0, 3, 1, 2) - ref["flow"]).abs().max() < 1e-4
         _check_frame(eng, det, ref, 0)
+
+
+def test_base_and_dff_module_api_on_standins():
+    """GeneralizedRCNN (list-of-images call) and GeneralizedRCNNDFF ({cur, is_key_frame} dict) through
+    build_detection_model / load_state_dict / model(...) -> list[BoxList], against the reference fixtures"""
+    from mega_core.b200 import engine, synth
+    from mega_core.modeling.detector import build_detection_model_from_state_dict
+    from mega_core.modeling.nets import engine_config_from
+    with cpu_ops():
+        gold = torch.load(os.path.join(ROOT, "tests", "golden", "base_r50_192x320.pt"))
+        sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+        model = build_detection_model_from_state_dict(sd, method="base", device="cpu", precision="tf32")
+        model._engine = engine.BaseEngine(model.state_dict(), engine_config_from(model.cfg), "cpu")
+        out = model([synth.synthetic_frame(gold["frame_index"], gold["h"], gold["w"])[0]])
+        assert torch.equal(out[0].get_field("labels"), gold["labels"]) and torch.allclose(out[0].bbox, gold["boxes"], atol=2e-2)
+        gold = torch.load(os.path.join(ROOT, "tests", "golden", "dff_r101_192x320.pt"))
+        sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+        model = build_detection_model_from_state_dict(sd, method="dff", device="cpu", precision="tf32")
+        model._engine = engine.DffEngine(model.state_dict(), engine_config_from(model.cfg), "cpu")
+        for t in range(2):
+            out = model({"cur": synth.synthetic_frame(gold["frame_stride"] * t, gold["h"], gold["w"])[0],
+                         "is_key_frame": gold["key_flags"][t]})
+            ref = gold["frames"][t]
+            assert torch.equal(out[0].get_field("labels"), ref["labels"]) and torch.allclose(out[0].bbox, ref["boxes"], atol=2e-2)
