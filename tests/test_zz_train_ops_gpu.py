@@ -3,6 +3,9 @@ backward, deform_conv_backward_input / _parameters, modulated_deform_conv_backwa
 (8f row 3). Oracles: oracle/train_ops_oracle.py (autograd of forward restatements anchored in
 tests/test_train_ops_cpu.py). Scatter kernels accumulate with red.global.add.f32 in an unspecified order, as the
 reference's atomicAdd does, so float results are compared to 1e-5-level tolerances; arg-max indices are exact.
+Order inside the file (the GPU tier runs with -x): most certain first -- integer-exact image transform, the simple
+scatter kernels, the engine-level wavefront / DFF checks (all-existing kernels in a new order), then the ops that also
+drive the tcgen05 GEMM with shapes it has not seen (deformable-conv backward, the layer wrappers).
 (This file sorts last on purpose: these kernels were added after the last GPU session of round 1 and are verified on
 the CPU through their host build only; a failure here must not hide the hot-path tests.)"""
 import os
@@ -25,6 +28,31 @@ def _rois(g, k, n_img, w_img, h_img):
     bh = torch.rand(k, generator=g) * h_img * 0.6 + 1
     b = torch.randint(0, n_img, (k,), generator=g).float()
     return torch.stack([b, x1, y1, x1 + bw, y1 + bh], 1)
+
+
+def _rel_err(a, b):
+    return ((a - b).abs().max() / b.pow(2).mean().sqrt().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("h,w", [(720, 1280), (480, 640), (600, 1000), (375, 500)])
+def test_device_image_transform_matches_reference_pipeline(cuda_dev, h, w):
+    """mega_image_transform_u8 vs the reference's CPU pipeline (PIL resize -> to_tensor -> BGR255 -> normalize), bit for
+    bit, at ImageNet-VID frame sizes and MIN_SIZE_TEST / MAX_SIZE_TEST = 600 / 1000 (SURVEY.md section 8f row 1)"""
+    import numpy as np
+    import image_oracle as io
+    from mega_core.data.transforms import DeviceTestTransform
+    mean, std = [102.9801, 115.9465, 122.7717], [1.0, 1.0, 1.0]
+    g = np.random.default_rng(h + w)
+    base = g.integers(0, 256, (h // 16 + 2, w // 16 + 2, 3), dtype=np.uint8)
+    img = np.kron(base, np.ones((16, 16, 1), dtype=np.uint8))[:h, :w]
+    img = np.clip(img.astype(np.int16) + g.integers(-20, 20, (h, w, 3), dtype=np.int16), 0, 255).astype(np.uint8)
+    ref = io.reference_pipeline(img, 600, 1000, mean, std, True)
+    tr = DeviceTestTransform(600, 1000, mean, std, True, device=cuda_dev)
+    out, _ = tr(img)
+    assert out.is_cuda and out.shape == ref.shape
+    assert torch.equal(out.cpu(), ref)
+    out2, _ = tr(torch.from_numpy(img).pin_memory())              # pinned host frame, tables cached from the first call
+    assert torch.equal(out2.cpu(), ref)
 
 
 @pytest.mark.parametrize("sr,c", [(0, 5), (2, 19), (0, 16)])
@@ -62,50 +90,6 @@ def test_roi_pool_forward_backward(cuda_dev):
     assert torch.allclose(gin.cpu(), to.roi_pool_backward(grad, feat, rois, 1 / 16.0, 7, 7), atol=1e-6)
 
 
-def _rel_err(a, b):
-    return ((a - b).abs().max() / b.pow(2).mean().sqrt().clamp_min(1e-12)).item()
-
-
-@pytest.mark.parametrize("modulated,groups,dg,stride,pad,dil", [(False, 1, 1, 1, 1, 1), (True, 1, 1, 1, 1, 1),
-                                                                (True, 2, 2, 2, 1, 1), (False, 2, 4, 1, 2, 2)])
-def test_deform_conv_backward(cuda_dev, modulated, groups, dg, stride, pad, dil):
-    import train_ops_oracle as to
-    from mega_core import _C
-    from mega_core.b200 import ops
-    g = torch.Generator().manual_seed(60 + groups + dg)
-    b, c, h, w, cout, k = 2, 32, 19, 23, 64, 3
-    x = torch.randn(b, c, h, w, generator=g)
-    wt = torch.randn(cout, c // groups, k, k, generator=g) / (c * 9 / groups) ** 0.5
-    bias = torch.randn(cout, generator=g) if modulated else None
-    ho = (h + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
-    wo = (w + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
-    off = torch.randn(b, dg * 2 * k * k, ho, wo, generator=g) * 2.0
-    mask = torch.rand(b, dg * k * k, ho, wo, generator=g) if modulated else None
-    go = torch.randn(b, cout, ho, wo, generator=g)
-    ref = to.deform_conv2d_grads(x, off, mask, wt, bias, go, (stride, stride), (pad, pad), (dil, dil), groups, dg)
-    d = cuda_dev
-    xd, offd, wtd, god = x.to(d), off.to(d), wt.to(d), go.to(d)
-    gin, goff, gw = torch.zeros_like(xd), torch.zeros_like(offd), torch.zeros_like(wtd)
-    with ops.precision("fp32x3"):
-        if modulated:
-            maskd, biasd = mask.to(d), bias.to(d)
-            gmask, gb = torch.zeros_like(maskd), torch.zeros_like(biasd)
-            _C.modulated_deform_conv_backward(xd, wtd, biasd, None, offd, maskd, None, gin, gw, gb, goff, gmask, god, k, k,
-                                              stride, stride, pad, pad, dil, dil, groups, dg, True)
-        else:
-            assert _C.deform_conv_backward_input(xd, offd, god, gin, goff, wtd, None, k, k, stride, stride, pad, pad, dil,
-                                                 dil, groups, dg, b) == 1
-            assert _C.deform_conv_backward_parameters(xd, offd, god, gw, None, None, k, k, stride, stride, pad, pad, dil,
-                                                      dil, groups, dg, 1.0, b) == 1
-    torch.cuda.synchronize()
-    assert _rel_err(gin.cpu(), ref["input"]) < 2e-4
-    assert _rel_err(goff.cpu(), ref["offset"]) < 2e-4
-    assert _rel_err(gw.cpu(), ref["weight"]) < 2e-4
-    if modulated:
-        assert _rel_err(gmask.cpu(), ref["mask"]) < 2e-4
-        assert _rel_err(gb.cpu(), ref["bias"]) < 1e-5
-
-
 @pytest.mark.parametrize("no_trans", [True, False])
 def test_deform_psroi_pooling_backward(cuda_dev, no_trans):
     import train_ops_oracle as to
@@ -133,38 +117,6 @@ def test_deform_psroi_pooling_backward(cuda_dev, no_trans):
         assert gtr.abs().sum().item() == 0
     else:
         assert torch.allclose(gtr.cpu(), ref_tr, atol=2e-4, rtol=1e-3)
-
-
-def test_layers_autograd_on_device(cuda_dev):
-    """mega_core.layers wrappers: forward and backward both on the sm_100a kernels"""
-    import train_ops_oracle as to
-    from mega_core import layers
-    from mega_core.b200 import ops
-    g = torch.Generator().manual_seed(71)
-    feat = torch.randn(2, 6, 12, 17, generator=g)
-    rois = _rois(g, 5, 2, 17 * 16, 12 * 16)
-    wgt = torch.randn(5, 6, 7, 7, generator=g)
-    x = feat.to(cuda_dev).requires_grad_(True)
-    out = layers.ROIAlign((7, 7), 1 / 16.0, 2)(x, rois.to(cuda_dev))
-    (out * wgt.to(cuda_dev)).sum().backward()
-    assert torch.allclose(out.detach().cpu(), to.roi_align(feat, rois, 1 / 16.0, 7, 7, 2), atol=2e-6)
-    assert torch.allclose(x.grad.cpu(), to.roi_align_backward(wgt, rois, 1 / 16.0, 7, 7, 2, 6, 12, 17, 2), atol=2e-5)
-    # ModulatedDeformConvPack starts as 0.5 * conv(x, w) + b (zero offsets, masks sigmoid(0))
-    torch.manual_seed(5)
-    m = layers.ModulatedDeformConvPack(32, 64, 3, stride=1, padding=1, deformable_groups=2).to(cuda_dev)
-    with torch.no_grad():
-        m.bias.normal_()
-    xx = torch.randn(2, 32, 9, 11, device=cuda_dev, requires_grad=True)
-    with ops.precision("fp32x3"):
-        y = m(xx)
-        y.sum().backward()
-    xr = xx.detach().cpu().double().requires_grad_(True)
-    wr = m.weight.detach().cpu().double().requires_grad_(True)
-    ref = 0.5 * torch.nn.functional.conv2d(xr, wr, None, 1, 1) + m.bias.detach().cpu().double().view(1, -1, 1, 1)
-    ref.sum().backward()
-    assert _rel_err(y.detach().cpu(), ref.detach().float()) < 1e-4
-    assert _rel_err(m.weight.grad.cpu(), wr.grad.float()) < 2e-4
-    assert _rel_err(xx.grad.cpu(), xr.grad.float()) < 2e-4
 
 
 def test_mega_wavefront_step_equals_replicated_state_step(cuda_dev):
@@ -212,27 +164,6 @@ def test_mega_wavefront_step_equals_replicated_state_step(cuda_dev):
                 "B2": solo.nl12}.get(name, 0)
         for r in range(2):
             assert torch.equal(getattr(ranks[r], name)[ring:], getattr(solo, name)[ring:]), (name, r)
-
-
-@pytest.mark.parametrize("h,w", [(720, 1280), (480, 640), (600, 1000), (375, 500)])
-def test_device_image_transform_matches_reference_pipeline(cuda_dev, h, w):
-    """mega_image_transform_u8 vs the reference's CPU pipeline (PIL resize -> to_tensor -> BGR255 -> normalize), bit for
-    bit, at ImageNet-VID frame sizes and MIN_SIZE_TEST / MAX_SIZE_TEST = 600 / 1000 (SURVEY.md section 8f row 1)"""
-    import numpy as np
-    import image_oracle as io
-    from mega_core.data.transforms import DeviceTestTransform
-    mean, std = [102.9801, 115.9465, 122.7717], [1.0, 1.0, 1.0]
-    g = np.random.default_rng(h + w)
-    base = g.integers(0, 256, (h // 16 + 2, w // 16 + 2, 3), dtype=np.uint8)
-    img = np.kron(base, np.ones((16, 16, 1), dtype=np.uint8))[:h, :w]
-    img = np.clip(img.astype(np.int16) + g.integers(-20, 20, (h, w, 3), dtype=np.int16), 0, 255).astype(np.uint8)
-    ref = io.reference_pipeline(img, 600, 1000, mean, std, True)
-    tr = DeviceTestTransform(600, 1000, mean, std, True, device=cuda_dev)
-    out, _ = tr(img)
-    assert out.is_cuda and out.shape == ref.shape
-    assert torch.equal(out.cpu(), ref)
-    out2, _ = tr(torch.from_numpy(img).pin_memory())              # pinned host frame, tables cached from the first call
-    assert torch.equal(out2.cpu(), ref)
 
 
 @pytest.mark.parametrize("precision", ["shadow", "fp32x3", "f16"])
@@ -299,3 +230,76 @@ def test_dff_module_api(cuda_dev):
     for t, key in enumerate((True, False)):
         out = model({"cur": synth.synthetic_frame(3 * t, h, w)[0], "is_key_frame": key})
         assert len(out) == 1 and out[0].bbox.shape[1] == 4 and out[0].has_field("scores") and out[0].has_field("labels")
+
+
+
+@pytest.mark.parametrize("modulated,groups,dg,stride,pad,dil", [(False, 1, 1, 1, 1, 1), (True, 1, 1, 1, 1, 1),
+                                                                (True, 2, 2, 2, 1, 1), (False, 2, 4, 1, 2, 2)])
+def test_deform_conv_backward(cuda_dev, modulated, groups, dg, stride, pad, dil):
+    import train_ops_oracle as to
+    from mega_core import _C
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(60 + groups + dg)
+    b, c, h, w, cout, k = 2, 32, 19, 23, 64, 3
+    x = torch.randn(b, c, h, w, generator=g)
+    wt = torch.randn(cout, c // groups, k, k, generator=g) / (c * 9 / groups) ** 0.5
+    bias = torch.randn(cout, generator=g) if modulated else None
+    ho = (h + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    wo = (w + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+    off = torch.randn(b, dg * 2 * k * k, ho, wo, generator=g) * 2.0
+    mask = torch.rand(b, dg * k * k, ho, wo, generator=g) if modulated else None
+    go = torch.randn(b, cout, ho, wo, generator=g)
+    ref = to.deform_conv2d_grads(x, off, mask, wt, bias, go, (stride, stride), (pad, pad), (dil, dil), groups, dg)
+    d = cuda_dev
+    xd, offd, wtd, god = x.to(d), off.to(d), wt.to(d), go.to(d)
+    gin, goff, gw = torch.zeros_like(xd), torch.zeros_like(offd), torch.zeros_like(wtd)
+    with ops.precision("fp32x3"):
+        if modulated:
+            maskd, biasd = mask.to(d), bias.to(d)
+            gmask, gb = torch.zeros_like(maskd), torch.zeros_like(biasd)
+            _C.modulated_deform_conv_backward(xd, wtd, biasd, None, offd, maskd, None, gin, gw, gb, goff, gmask, god, k, k,
+                                              stride, stride, pad, pad, dil, dil, groups, dg, True)
+        else:
+            assert _C.deform_conv_backward_input(xd, offd, god, gin, goff, wtd, None, k, k, stride, stride, pad, pad, dil,
+                                                 dil, groups, dg, b) == 1
+            assert _C.deform_conv_backward_parameters(xd, offd, god, gw, None, None, k, k, stride, stride, pad, pad, dil,
+                                                      dil, groups, dg, 1.0, b) == 1
+    torch.cuda.synchronize()
+    assert _rel_err(gin.cpu(), ref["input"]) < 2e-4
+    assert _rel_err(goff.cpu(), ref["offset"]) < 2e-4
+    assert _rel_err(gw.cpu(), ref["weight"]) < 2e-4
+    if modulated:
+        assert _rel_err(gmask.cpu(), ref["mask"]) < 2e-4
+        assert _rel_err(gb.cpu(), ref["bias"]) < 1e-5
+
+
+def test_layers_autograd_on_device(cuda_dev):
+    """mega_core.layers wrappers: forward and backward both on the sm_100a kernels"""
+    import train_ops_oracle as to
+    from mega_core import layers
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(71)
+    feat = torch.randn(2, 6, 12, 17, generator=g)
+    rois = _rois(g, 5, 2, 17 * 16, 12 * 16)
+    wgt = torch.randn(5, 6, 7, 7, generator=g)
+    x = feat.to(cuda_dev).requires_grad_(True)
+    out = layers.ROIAlign((7, 7), 1 / 16.0, 2)(x, rois.to(cuda_dev))
+    (out * wgt.to(cuda_dev)).sum().backward()
+    assert torch.allclose(out.detach().cpu(), to.roi_align(feat, rois, 1 / 16.0, 7, 7, 2), atol=2e-6)
+    assert torch.allclose(x.grad.cpu(), to.roi_align_backward(wgt, rois, 1 / 16.0, 7, 7, 2, 6, 12, 17, 2), atol=2e-5)
+    # ModulatedDeformConvPack starts as 0.5 * conv(x, w) + b (zero offsets, masks sigmoid(0))
+    torch.manual_seed(5)
+    m = layers.ModulatedDeformConvPack(32, 64, 3, stride=1, padding=1, deformable_groups=2).to(cuda_dev)
+    with torch.no_grad():
+        m.bias.normal_()
+    xx = torch.randn(2, 32, 9, 11, device=cuda_dev, requires_grad=True)
+    with ops.precision("fp32x3"):
+        y = m(xx)
+        y.sum().backward()
+    xr = xx.detach().cpu().double().requires_grad_(True)
+    wr = m.weight.detach().cpu().double().requires_grad_(True)
+    ref = 0.5 * torch.nn.functional.conv2d(xr, wr, None, 1, 1) + m.bias.detach().cpu().double().view(1, -1, 1, 1)
+    ref.sum().backward()
+    assert _rel_err(y.detach().cpu(), ref.detach().float()) < 1e-4
+    assert _rel_err(m.weight.grad.cpu(), wr.grad.float()) < 2e-4
+    assert _rel_err(xx.grad.cpu(), xr.grad.float()) < 2e-4
