@@ -684,8 +684,10 @@ class MegaEngine(WindowedEngine):
         self._tab_off = o
         # host mirrors are multi-buffered: the H2D copy of frame t may still be queued when the host
         # prepares frame t+1 (each buffer is reused only after the event recorded behind its copy)
-        self._tab_ring = [torch.zeros(off, dtype=torch.int32).pin_memory() for _ in range(4)]
-        self._tab_ev = [None] * 4
+        # (16 deep: a multi-GPU step fills the tables once per frame of the group, up to 8 times back to back, while the
+        # copies of the first fills still wait behind that step's aggregation)
+        self._tab_ring = [torch.zeros(off, dtype=torch.int32).pin_memory() for _ in range(16)]
+        self._tab_ev = [None] * 16
         self.tab_h = self._tab_ring[0]
         self.tab_d = z(off, dtype=torch.int32)
         # static tables
