@@ -693,6 +693,8 @@ class MegaEngine(WindowedEngine):
         # static tables
         q_idx = list(range(KP)) + [KP + f * R + j for f in range(L) for j in range(A)]
         self.idx_qin0 = torch.tensor(q_idx, dtype=torch.int32, device=dev)
+        self._aranges = {"KP": np.arange(KP, dtype=np.int32), "R": np.arange(R, dtype=np.int32),
+                         "A": np.arange(A, dtype=np.int32)}
         self._init_window_state()
         self.reset()
 
@@ -812,29 +814,32 @@ class MegaEngine(WindowedEngine):
         if self._tab_ev[ring] is not None:
             self._tab_ev[ring].synchronize()
         self.tab_h = self._tab_ring[ring]
-        th = self._tab_h
+        tn = self.tab_h.numpy()                       # written through a numpy view of the pinned buffer: no torch op
+        off = self._tab_off                           # overheads on the per-frame host path (8 fills per 8-GPU step)
+
+        def put(name, values):
+            o, n = off[name]
+            tn[o:o + n] = values
+
+        ar = self._aranges
         mem_frames = min(self.mem_pushed, self.MEMF)
-        mv = th("mvalid")
-        mv[0] = self.nl0 + mem_frames * R
-        mv[1] = self.nl12 + mem_frames * A
-        mv[2] = self.nl12 + mem_frames * A
-        e0 = np.empty(KP + self.nl0, dtype=np.int32)
-        e0[:KP] = kslot * KP + np.arange(KP)
+        o = off["mvalid"][0]
+        tn[o], tn[o + 1], tn[o + 2] = self.nl0 + mem_frames * R, self.nl12 + mem_frames * A, self.nl12 + mem_frames * A
         sl = np.asarray(slots, dtype=np.int32)
-        e0[KP:] = (sl[:, None] * KP + np.arange(R)[None, :]).reshape(-1)
-        th("idx_e0").copy_(torch.from_numpy(e0))
-        th("idx_dis").copy_(torch.from_numpy((sl[:, None] * KP + np.arange(A)[None, :]).reshape(-1).astype(np.int32)))
+        o = off["idx_e0"][0]
+        tn[o:o + KP] = kslot * KP + ar["KP"]
+        tn[o + KP:o + KP + self.nl0] = (sl[:, None] * KP + ar["R"][None, :]).reshape(-1)
+        put("idx_dis", (sl[:, None] * KP + ar["A"][None, :]).reshape(-1))
         if slot_new is not None:
-            th("dst_local").copy_(torch.arange(slot_new * KP, (slot_new + 1) * KP, dtype=torch.int32))
-            th("slot_new")[0] = slot_new
+            put("dst_local", slot_new * KP + ar["KP"])
+            tn[off["slot_new"][0]] = slot_new
         if gslot is not None:
-            th("dst_glob").copy_(torch.arange(gslot * R, (gslot + 1) * R, dtype=torch.int32))
+            put("dst_glob", gslot * R + ar["R"])
         mslot = self.mem_pushed % self.MEMF
-        base0 = KP + self.nl0
-        th("dst_mem0").copy_(torch.arange(base0 + mslot * R, base0 + (mslot + 1) * R, dtype=torch.int32))
-        th("dst_mem12").copy_(torch.arange(self.nq + mslot * A, self.nq + (mslot + 1) * A, dtype=torch.int32))
-        th("dst_memb12").copy_(torch.arange(self.nl12 + mslot * A, self.nl12 + (mslot + 1) * A, dtype=torch.int32))
-        th("slot_key")[0] = kslot
+        put("dst_mem0", KP + self.nl0 + mslot * R + ar["R"])
+        put("dst_mem12", self.nq + mslot * A + ar["A"])
+        put("dst_memb12", self.nl12 + mslot * A + ar["A"])
+        tn[off["slot_key"][0]] = kslot
         self.tab_d.copy_(self.tab_h, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
