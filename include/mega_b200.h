@@ -334,15 +334,17 @@ int mega_deform_psroi_pooling_backward(const float* out_grad, const float* input
                                        int pooled_size, int part_size, int sample_per_part, float trans_std,
                                        int num_classes, float* input_grad, float* trans_grad, void* stream);
 
-/* Test-time input transform of one decoded frame: uint8 RGB [src_h, src_w, 3] (device,
- * src_row_stride bytes between rows) -> fp32 [3, out_h, out_w], bit-identical to the reference's CPU pipeline
+/* Test-time input transform of one decoded frame: uint8 RGB on the device, interleaved
+ * [src_h, src_w, 3] (src_pix_stride 3, src_ch_stride 1; what PIL / OpenCV decoders give) or planar [3, src_h, src_w]
+ * (src_pix_stride 1, src_ch_stride = plane size; what nvJPEG via torchvision.io.decode_jpeg(device="cuda") gives),
+ * src_row_stride bytes between rows -> fp32 [3, out_h, out_w], bit-identical to the reference's CPU pipeline
  * Resize (PIL bilinear) -> ToTensor -> Normalize(to_bgr255) (data/transforms/transforms.py:27-63, :117-135;
  * data/transforms/build.py:5-49). bounds_* / kk_* are Pillow's per-output (first tap, count) pairs and 2^22-scaled
  * integer coefficients (Resample.c precompute_coeffs + normalize_coeffs_8bpc), computed on the host by
  * mega_core.data.transforms.resample_tables and resident on the device; ksize_* == 0 skips a pass (size unchanged).
  * mean_host / std_host: 3 floats each, HOST pointers, in output channel order. */
-int mega_image_transform_u8(const unsigned char* src, int src_h, int src_w, long long src_row_stride, const int* bounds_h,
-                            const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v, int out_h,
+int mega_image_transform_u8(const unsigned char* src, int src_h, int src_w, long long src_row_stride,
+                            long long src_pix_stride, long long src_ch_stride, const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v, const int* kk_v, int ksize_v, int out_h,
                             int out_w, const float* mean_host, const float* std_host, int to_bgr255, float* out,
                             void* stream);
 

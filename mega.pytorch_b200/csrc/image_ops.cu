@@ -20,12 +20,16 @@ __global__ void image_transform_kernel(long long total, mega_image::ResizeGeom g
 }  // namespace mega
 
 extern "C" int mega_image_transform_u8(const unsigned char* src, int src_h, int src_w, long long src_row_stride,
-                                       const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v,
+                                       long long src_pix_stride, long long src_ch_stride, const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v,
                                        const int* kk_v, int ksize_v, int out_h, int out_w, const float* mean_host,
                                        const float* std_host, int to_bgr255, float* out, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   MEGA_ARG_CHECK(src_h > 0 && src_w > 0 && out_h > 0 && out_w > 0, "image_transform: empty image");
-  MEGA_ARG_CHECK(src_row_stride >= 3LL * src_w, "image_transform: row stride smaller than 3 * width");
+  MEGA_ARG_CHECK((src_pix_stride == 3 && src_ch_stride == 1 && src_row_stride >= 3LL * src_w) ||
+                     (src_pix_stride == 1 && src_ch_stride >= static_cast<long long>(src_h) * src_row_stride &&
+                      src_row_stride >= src_w),
+                 "image_transform: source must be interleaved HWC (pixel stride 3, channel stride 1) or planar CHW "
+                 "(pixel stride 1, channel stride >= H * row stride)");
   MEGA_ARG_CHECK(ksize_h >= 0 && ksize_v >= 0, "image_transform: negative kernel size");
   MEGA_ARG_CHECK(ksize_h > 0 || out_w == src_w, "image_transform: horizontal pass skipped but widths differ");
   MEGA_ARG_CHECK(ksize_v > 0 || out_h == src_h, "image_transform: vertical pass skipped but heights differ");
@@ -34,6 +38,7 @@ extern "C" int mega_image_transform_u8(const unsigned char* src, int src_h, int 
   MEGA_ARG_CHECK(mean_host && std_host, "image_transform: mean / std missing");
   mega_image::ResizeGeom g;
   g.src_h = src_h, g.src_w = src_w, g.out_h = out_h, g.out_w = out_w, g.src_row_stride = src_row_stride;
+  g.src_pix_stride = src_pix_stride, g.src_ch_stride = src_ch_stride;
   g.ksize_h = ksize_h, g.ksize_v = ksize_v;
   g.bounds_h = bounds_h, g.kk_h = kk_h, g.bounds_v = bounds_v, g.kk_v = kk_v;
   for (int c = 0; c < 3; ++c) g.mean[c] = mean_host[c], g.stdv[c] = std_host[c];

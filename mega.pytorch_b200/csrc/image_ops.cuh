@@ -37,7 +37,9 @@ constexpr int kPrecisionBits = 32 - 8 - 2;   // Resample.c: PRECISION_BITS
 
 struct ResizeGeom {
   int src_h, src_w, out_h, out_w;
-  long long src_row_stride;   // bytes between source rows (HWC, 3 bytes per pixel)
+  long long src_row_stride;   // bytes between source rows
+  long long src_pix_stride;   // bytes between pixels of a row: 3 for interleaved HWC, 1 for planar CHW
+  long long src_ch_stride;    // bytes between the R, G, B samples of a pixel: 1 for HWC, H * W for planar CHW
   int ksize_h, ksize_v;       // coefficients per output column / row (0: that pass is skipped, sizes equal)
   // device tables: bounds_* [2 * out] = (first source index, count), kk_* [out * ksize] fixed-point coefficients
   const int* bounds_h;
@@ -56,18 +58,19 @@ MEGA_IMG_HD int clip8(int v) {
 // horizontal pass value of source row `row` at output column x (3 channels), rounded to uint8 like imTemp
 MEGA_IMG_HD void horiz_rgb(const ResizeGeom& g, const uint8_t* src, int row, int x, int rgb[3]) {
   const uint8_t* line = src + row * g.src_row_stride;
+  const long long ps = g.src_pix_stride, cs = g.src_ch_stride;
   if (g.ksize_h == 0) {
-    rgb[0] = line[x * 3 + 0], rgb[1] = line[x * 3 + 1], rgb[2] = line[x * 3 + 2];
+    rgb[0] = line[x * ps], rgb[1] = line[x * ps + cs], rgb[2] = line[x * ps + 2 * cs];
     return;
   }
   const int xmin = g.bounds_h[2 * x], n = g.bounds_h[2 * x + 1];
   const int* k = g.kk_h + static_cast<long long>(x) * g.ksize_h;
   int s0 = 1 << (kPrecisionBits - 1), s1 = s0, s2 = s0;
-  const uint8_t* p = line + xmin * 3;
+  const uint8_t* p = line + xmin * ps;
   for (int i = 0; i < n; ++i) {
-    s0 += p[3 * i + 0] * k[i];
-    s1 += p[3 * i + 1] * k[i];
-    s2 += p[3 * i + 2] * k[i];
+    s0 += p[i * ps] * k[i];
+    s1 += p[i * ps + cs] * k[i];
+    s2 += p[i * ps + 2 * cs] * k[i];
   }
   rgb[0] = clip8(s0), rgb[1] = clip8(s1), rgb[2] = clip8(s2);
 }

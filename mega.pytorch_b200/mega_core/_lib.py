@@ -194,7 +194,7 @@ lib.mega_channel_sum_nchw.restype = _i
 lib.mega_deform_psroi_pooling_backward.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _i, _i, _i, _i, _i,
                                                    _f, _i, _vp, _vp, _vp]
 lib.mega_deform_psroi_pooling_backward.restype = _i
-lib.mega_image_transform_u8.argtypes = [_vp, _i, _i, _ll, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]
+lib.mega_image_transform_u8.argtypes = [_vp, _i, _i, _ll, _ll, _ll, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp]
 lib.mega_image_transform_u8.restype = _i
 lib.mega_dff_warp_scale.argtypes = [_vp, _i, _i, _vp, _i, _vp, _ll, _i, _i, _vp, _ll, _i, _vp]
 lib.mega_dff_warp_scale.restype = _i

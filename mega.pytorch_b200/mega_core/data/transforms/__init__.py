@@ -1,2 +1,2 @@
 from .build import build_transforms  # noqa: F401
-from .transforms import DeviceTestTransform, get_size, resample_tables  # noqa: F401
+from .transforms import DeviceTestTransform, decode_jpeg, get_size, resample_tables  # noqa: F401

@@ -66,10 +66,21 @@ def resample_tables(in_size, out_size):
     return bounds, kk, ksize
 
 
+def decode_jpeg(data, device="cuda"):
+    """encoded JPEG bytes (bytes / uint8 tensor) -> planar uint8 RGB [3, H, W] on the device through nvJPEG
+    (torchvision.io.decode_jpeg: a library decoder, like PIL's libjpeg in the reference's data loader; their IDCTs
+    differ in the last bit, so pixel values are not bit-identical across decoders -- the transform after it is)"""
+    import torchvision
+    if not torch.is_tensor(data):
+        data = torch.frombuffer(bytearray(data), dtype=torch.uint8)
+    return torchvision.io.decode_jpeg(data, device=device, mode=torchvision.io.ImageReadMode.RGB)
+
+
 class DeviceTestTransform(object):
     """callable with the reference's transform signature `(image, target=None) -> (tensor, target)`.
-    image: PIL.Image (RGB), uint8 ndarray / tensor [H, W, 3] on the host, or a uint8 [H, W, 3] tensor already on the
-    device (e.g. out of a GPU JPEG decoder). Returns a float32 [3, H', W'] device tensor."""
+    image: PIL.Image (RGB), uint8 ndarray / tensor [H, W, 3] on the host or on the device, or a planar uint8 [3, H, W]
+    tensor (what `decode_jpeg` below / torchvision.io.decode_jpeg(device="cuda") returns: nvJPEG output is consumed in
+    place, no re-layout). Returns a float32 [3, H', W'] device tensor."""
 
     def __init__(self, min_size, max_size, mean, std, to_bgr255=True, device="cuda"):
         if isinstance(min_size, (list, tuple)):
@@ -95,15 +106,21 @@ class DeviceTestTransform(object):
         return t
 
     def __call__(self, image, target=None, out=None):
-        if hasattr(image, "mode"):                                           # PIL.Image
+        if not torch.is_tensor(image) and hasattr(image, "convert"):         # PIL.Image
             image = np.asarray(image.convert("RGB"))
         if isinstance(image, np.ndarray):
             image = torch.from_numpy(np.array(image, copy=True))
-        if image.dtype != torch.uint8 or image.dim() != 3 or image.shape[2] != 3:
-            raise ValueError("expected a uint8 [H, W, 3] RGB image, got %s %s" % (image.dtype, tuple(image.shape)))
+        if image.dtype != torch.uint8 or image.dim() != 3 or 3 not in (image.shape[0], image.shape[2]):
+            raise ValueError("expected a uint8 [H, W, 3] or [3, H, W] RGB image, got %s %s" % (image.dtype, tuple(image.shape)))
         src = image.to(self.device, non_blocking=True).contiguous()
         _lib.require_cuda(src)
-        h, w = src.shape[0], src.shape[1]
+        planar = src.shape[2] != 3                      # [3, H, W]; a [3, W, 3] strip counts as interleaved
+        if planar:
+            h, w = src.shape[1], src.shape[2]
+            row, pix, ch = src.stride(1), 1, src.stride(0)
+        else:
+            h, w = src.shape[0], src.shape[1]
+            row, pix, ch = src.stride(0), 3, 1
         oh, ow = get_size((w, h), self.min_size, self.max_size)
         bh, kh, ksh = self._axis(w, ow)
         bv, kv, ksv = self._axis(h, oh)
@@ -111,7 +128,7 @@ class DeviceTestTransform(object):
             out = torch.empty(3, oh, ow, device=self.device)
         assert out.shape == (3, oh, ow) and out.dtype == torch.float32 and out.is_contiguous()
         _lib.check(_lib.lib.mega_image_transform_u8(
-            _lib.ptr(src), h, w, src.stride(0), _lib.ptr(bh), _lib.ptr(kh), ksh, _lib.ptr(bv), _lib.ptr(kv), ksv, oh, ow,
+            _lib.ptr(src), h, w, row, pix, ch, _lib.ptr(bh), _lib.ptr(kh), ksh, _lib.ptr(bv), _lib.ptr(kv), ksv, oh, ow,
             self.mean.ctypes.data, self.std.ctypes.data, int(self.to_bgr255), _lib.ptr(out), _lib.stream_ptr()),
             "mega_image_transform_u8")
         if target is not None and hasattr(target, "resize"):

@@ -5,12 +5,13 @@
 #include "image_ops.cuh"
 
 extern "C" int mega_image_transform_u8(const unsigned char* src, int src_h, int src_w, long long src_row_stride,
-                                       const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v,
+                                       long long src_pix_stride, long long src_ch_stride, const int* bounds_h, const int* kk_h, int ksize_h, const int* bounds_v,
                                        const int* kk_v, int ksize_v, int out_h, int out_w, const float* mean_host,
                                        const float* std_host, int to_bgr255, float* out, void* stream) {
   (void)stream;
   mega_image::ResizeGeom g;
   g.src_h = src_h, g.src_w = src_w, g.out_h = out_h, g.out_w = out_w, g.src_row_stride = src_row_stride;
+  g.src_pix_stride = src_pix_stride, g.src_ch_stride = src_ch_stride;
   g.ksize_h = ksize_h, g.ksize_v = ksize_v;
   g.bounds_h = bounds_h, g.kk_h = kk_h, g.bounds_v = bounds_v, g.kk_v = kk_v;
   for (int c = 0; c < 3; ++c) g.mean[c] = mean_host[c], g.stdv[c] = std_host[c];

@@ -72,6 +72,9 @@ def test_device_transform_body_matches_reference_pipeline(host_transform, h, w, 
     from PIL import Image
     out2, _ = tr(Image.fromarray(img, "RGB"))                     # the reference hands the transform a PIL image
     assert torch.equal(out2, ref)
+    planar = torch.from_numpy(img).permute(2, 0, 1).contiguous()  # [3, H, W]: the layout of a GPU JPEG decoder's output
+    out3, _ = tr(planar)
+    assert torch.equal(out3, ref)
 
 
 def test_device_transform_rgb_unit_range(host_transform):
