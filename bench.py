@@ -62,6 +62,10 @@ def parse():
                     help="N > 1: keep the replicated-state schedule (dist_step). Default: every rank replays "
                          "parallel.wave_selfcheck on its own GPU (wavefront vs sequential step, bit-identity of outputs "
                          "and memory rings, with CUDA graphs) and the run uses the wavefront schedule only if ALL ranks pass")
+    ap.add_argument("--frames-per-step", type=int, default=1, choices=[1, 2],
+                    help="N = 1: key frames per step. 2 = MegaEngine.step2_batched (the per-frame branch of two key frames "
+                         "as one batch of four images, then the two aggregations; same results, one frame more latency). "
+                         "Experimental: first GPU run pending")
     ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
     ap.add_argument("--cpu-sample-frames", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -201,13 +205,25 @@ def run_b200(args, rank, world):
     def dstep(pair):
         return eng.dist_step_wave(pair, w, h) if wave else eng.dist_step(pair, w, h)[rank]
 
+    fps = args.frames_per_step if world == 1 else 1
+    if fps == 2:
+        quads_dev = [torch.cat([pairs_dev[(2 * i) % 16], pairs_dev[(2 * i + 1) % 16]], 0) for i in range(8)]
+        quads_pinned = [torch.cat([pairs_pinned[(2 * i) % 16], pairs_pinned[(2 * i + 1) % 16]], 0).pin_memory() for i in range(8)]
+        static_in4 = eng.static_input((4,) + pair_shape[1:])
+
     def step_dev(i):
         if world > 1:
             return dstep(pairs_dev[(i * world + rank) % 16])
+        if fps == 2:
+            return eng.step2_batched(quads_dev[i % 8], w, h)
         return eng.step_batched(pairs_dev[i % 16], w, h)
 
     def step_e2e(i):
         """pinned host frames -> device, one step, detections of this rank's key frame back on the host"""
+        if world == 1 and fps == 2:
+            static_in4.copy_(quads_pinned[i % 8], non_blocking=True)
+            d0, d1 = eng.step2_batched(static_in4, w, h)
+            return torch.cat([d0.to_host()[0], d1.to_host()[0]])
         if world == 1:
             # the call a user of the reference makes, followed by the .to(cpu) of engine/inference.py:43
             return model(infos_next(i))[0].to("cpu")
@@ -248,8 +264,8 @@ def run_b200(args, rank, world):
     e3.record()
     barrier()
     e2e_ms = e2.elapsed_time(e3)
-    h2d = 2 * 3 * h * w * 4 + eng.tab_h.numel() * 4 * world
-    d2h = model.d2h_bytes_per_frame if world == 1 else 4 + 300 * 28
+    h2d = fps * 2 * 3 * h * w * 4 + eng.tab_h.numel() * 4 * world * fps
+    d2h = (model.d2h_bytes_per_frame if world == 1 and fps == 1 else 4 + 300 * 28) * fps
 
     # ---- roofline of the dominant kernel (tcgen05 conv/GEMM): eager frames with an event pair per launch
     roof = roofline_pass(eng, pairs_dev, w, h)
@@ -270,7 +286,7 @@ def run_b200(args, rank, world):
         return None
     pk = peaks()
     line = {
-        "metric": METRIC, "value": world * args.steps / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+        "metric": METRIC, "value": world * fps * args.steps / (dev_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": PRECISION_DTYPE[args.precision], "data": "synthetic",
         "config": {"workload": workload(args), "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
@@ -280,13 +296,14 @@ def run_b200(args, rank, world):
                                   ("frame-parallel over %d GPUs, wavefront schedule: per-frame branch and the whole aggregation "
                                    "of a key frame on its owner, NCCL all-gather of the ROI-feature payloads + one all-gather of "
                                    "the memory increments per relation stage" % world) if wave else "single GPU",
+                   "key_frames_per_step": world * fps,
                    "schedule": ("wavefront" if wave else "replicated-state") if world > 1 else None,
                    "wave_selfcheck": wave_note,
                    "cuda_graph": bool(eng._graphs), "precision": args.precision,
                    "l2": "per-step working set (0.7 GB fp32 weights + >0.5 GB activations) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,
-        "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "detections_per_frame": ndet / args.steps},
+        "e2e": {"value": world * fps * args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps, "detections_per_frame": ndet / (args.steps * fps)},
         "gpu_launches": int(round(launches_per_step * args.steps * (1 if world == 1 else 1))),
         "roofline": {"bound": "tensor", "achieved": roof["algo_tflops"], "peak": pk["tflops"], "unit": "TFLOP/s",
                      "frac": roof["algo_tflops"] / pk["tflops"], "traffic": traffic_bytes(), "peak_source": pk["src"],

@@ -670,9 +670,10 @@ class MegaEngine(WindowedEngine):
         nq_g0 = KP + self.nl0
         self._alloc_attention([(nq_g0, self.ld_g), (self.nq, self.ld_0), (self.nq, self.ld_12)],
                               max(self.nl0 + self.mem_cap0, GF * R))
-        self.pooled = za(KP + R + KP, res * res * ch)           # up to (local 300 + global 75 [+ spare]) rois
-        self.fc0_out = za(KP + R + KP, D)
-        self.roi_boxes, self.roi_batch = z(KP + R + KP, 4), z(KP + R + KP, dtype=torch.int32)
+        nroi = 2 * (KP + R)                                     # two (local 300 + global 75) pairs: step2_batched
+        self.pooled = za(nroi, res * res * ch)
+        self.fc0_out = za(nroi, D)
+        self.roi_boxes, self.roi_batch = z(nroi, 4), z(nroi, dtype=torch.int32)
         # ---- per-frame index tables: pinned host mirror + device copy
         o = {}
         off = 0
@@ -861,16 +862,46 @@ class MegaEngine(WindowedEngine):
 
     def _ref_to_payload(self, imgs, im_w, im_h, payload):
         """per-frame branch of one (local, global) pair, packed into `payload`"""
-        KP, R = self.KP, self.R
-        x, boxes, cnt, spans = self.ref_branch(imgs, ["L", "G"], im_w, im_h)
-        (ol, rl), (og, rg) = spans
-        px, pb, pc, pg = self._payload_views(payload)
-        with ops.copy_batch():
-            ops.copy_rows(x[ol:ol + rl], px, KP)
-            ops.copy_rows(boxes[0], pb, KP)
-            ops.copy_rows(cnt[0:1].view(torch.float32).view(1, 1), pc, 1, row_len=1)   # raw 32-bit count
-            ops.copy_rows(x[og:og + rg], pg, R)
+        self._ref_to_payloads(imgs, im_w, im_h, [payload])
         return payload
+
+    def _ref_to_payloads(self, imgs, im_w, im_h, payloads):
+        """per-frame branch of len(payloads) (local, global) frame pairs as ONE batch (imgs [2n,3,H,W] in pair order),
+        pair i packed into payloads[i]"""
+        KP, R = self.KP, self.R
+        x, boxes, cnt, spans = self.ref_branch(imgs, ["L", "G"] * len(payloads), im_w, im_h)
+        with ops.copy_batch():
+            for i, payload in enumerate(payloads):
+                (ol, rl), (og, rg) = spans[2 * i], spans[2 * i + 1]
+                px, pb, pc, pg = self._payload_views(payload)
+                ops.copy_rows(x[ol:ol + rl], px, KP)
+                ops.copy_rows(boxes[2 * i], pb, KP)
+                ops.copy_rows(cnt[2 * i:2 * i + 1].view(torch.float32).view(1, 1), pc, 1, row_len=1)   # raw 32-bit count
+                ops.copy_rows(x[og:og + rg], pg, R)
+        return payloads
+
+    @_with_precision
+    def step2_batched(self, imgs4, im_w, im_h):
+        """TWO key frames per call (offline streams: all frames are at hand): imgs4 [4,3,H,W] = (local t, global t,
+        local t+1, global t+1). The per-frame branch -- a pure function of each frame -- runs once on the batch of four
+        (twice the rows per layer of the 2.5 ms branch), then the two aggregations run in order. Same results as two
+        step_batched calls; returns [Detections t (a copy), Detections t+1]. EXPERIMENTAL: logic verified on the CPU
+        stand-ins (tests/test_engine_logic_cpu.py), first GPU run / timing pending (bench.py --frames-per-step 2)."""
+        static_in = self.static_input(tuple(imgs4.shape))
+        if imgs4.data_ptr() != static_in.data_ptr():
+            static_in.copy_(imgs4, non_blocking=True)
+        if getattr(self, "payload2", None) is None:
+            self.payload2 = torch.zeros(2, self.payload_in.numel(), device=self.dev)
+        self._graph_run(("ref2", tuple(imgs4.shape), im_w, im_h),
+                        lambda: self._ref_to_payloads(static_in, im_w, im_h, [self.payload2[0], self.payload2[1]]))
+        dets = []
+        for i in range(2):
+            self.payload_in.copy_(self.payload2[i], non_blocking=True)
+            det = self._ingest_next(im_w, im_h)
+            if i == 0:          # the detection buffers are static: keep frame t's before frame t+1 overwrites them
+                det = Detections(det.boxes.clone(), det.scores.clone(), det.labels.clone(), det.count.clone())
+            dets.append(det)
+        return dets
 
     def _payload_to_rings(self):
         """payload_in -> window / global-pool ring slots named by the index tables"""

@@ -162,3 +162,34 @@ def test_base_and_dff_module_api_on_standins():
                          "is_key_frame": gold["key_flags"][t]})
             ref = gold["frames"][t]
             assert torch.equal(out[0].get_field("labels"), ref["labels"]) and torch.allclose(out[0].bbox, ref["boxes"], atol=2e-2)
+
+
+def test_two_key_frames_per_call_equal_two_calls():
+    """MegaEngine.step2_batched (the per-frame branch of two key frames as one batch of four images, then the two
+    aggregations in order) gives exactly what two step_batched calls give -- detections, predictor rows, every ring"""
+    from mega_core.b200 import engine, synth
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "mega_r101_192x320.pt"))
+    h, w = 96, 160
+    sd = synth.make_state_dict("mega_r101_tiny", seed=gold["seed"])
+    frames = [synth.synthetic_frame(i, h, w) for i in range(40)]
+    snap = lambda e, d: (e.last_pred[:int(e.cur_cnt.view(-1)[0])].clone(), d.boxes[:int(d.count[0])].clone(),   # noqa: E731
+                         d.labels[:int(d.count[0])].clone())
+    with cpu_ops():
+        a = engine.MegaEngine(sd, engine.EngineConfig(precision="tf32"), device="cpu")
+        b = engine.MegaEngine(sd, engine.EngineConfig(precision="tf32"), device="cpu")
+        from mega_core.b200 import parallel
+        for e in (a, b):
+            e.use_graph = False
+            parallel.random_state(e, 4, w, h)          # a full window / global pool without 23 backbone passes
+        for t in range(1, 5, 2):
+            quad = torch.cat([frames[t + 12], frames[30 + t], frames[t + 13], frames[31 + t]], 0)
+            one = [snap(a, a.step_batched(quad[0:2], w, h)), snap(a, a.step_batched(quad[2:4], w, h))]
+            d0, d1 = b.step2_batched(quad, w, h)
+            k0 = one[0][0].shape[0]
+            assert torch.equal(d0.boxes[:int(d0.count[0])], one[0][1]) and torch.equal(d0.labels[:int(d0.count[0])], one[0][2])
+            two1 = snap(b, d1)
+            for x, y in zip(one[1], two1):
+                assert torch.equal(x, y)
+            assert k0 > 0 and one[1][1].shape[0] > 0
+        for name in ("E0", "B0", "Y1E", "Y2M", "B1", "B2", "win_x", "win_boxes", "win_cnt", "glob_x"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name

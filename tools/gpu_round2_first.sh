@@ -10,6 +10,18 @@ if [ -z "$WAVE" ]; then
   echo "zz rc=$?" >> gpurun_out/r2_zz.log; grep -E "PASSED|FAILED|ERROR|rc=" gpurun_out/r2_zz.log | tail -30
   # 2. timing of the separable ROIAlign candidate and of the training-side kernels
   timeout 200 python tools/roi_probe.py > gpurun_out/r2_roi_probe.log 2>&1; tail -6 gpurun_out/r2_roi_probe.log
+  # 2b. two key frames per launch of the per-frame branch against the default step
+  for f in 1 2; do
+    timeout 300 python bench.py --steps 30 --warmup 5 --no-strict --skip-cpu-baseline --frames-per-step $f > gpurun_out/r2_bench_fps$f.json 2> gpurun_out/r2_bench_fps$f.err
+    python - <<PY
+import json
+try:
+    l = [x for x in open("gpurun_out/r2_bench_fps$f.json").read().splitlines() if x.startswith("{")][-1]
+    d = json.loads(l); print("frames/step $f:", "value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1))
+except Exception as e:
+    print("frames/step $f: no line", e)
+PY
+  done
   timeout 200 python tools/train_ops_probe.py > gpurun_out/r2_train_ops_probe.log 2>&1; tail -12 gpurun_out/r2_train_ops_probe.log
 else
   # 3. wavefront schedule vs replicated-state schedule at N GPUs (N = number of visible devices)
