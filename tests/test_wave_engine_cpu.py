@@ -209,3 +209,32 @@ def test_wave_selfcheck_function():
         finally:
             parallel.wave_tables = orig
         assert not ok and "differs" in msg
+
+
+def test_switching_from_the_replicated_step_to_the_wavefront_step():
+    """what bench.py does at N > 1: the video is primed with the replicated-state step (dist_step) and continues with the
+    wavefront step -- both leave every rank in the sequential state, so they can be mixed"""
+    from mega_core.b200 import parallel, synth
+    sd = synth.make_state_dict("mega_r101_tiny", seed=3)
+    world, frames = 2, 8
+    with cpu_ops():
+        solo = _make(sd)
+        _prime(solo, 1)
+        payloads = [_payload(solo, 100 + t) for t in range(frames)]
+        seq, seq_k = [], []
+        for t in range(frames):
+            seq.append(_snap(solo, solo.dist_step(None, W_IMG, H_IMG, rank=0, world=1, payloads=payloads[t][None])[0]))
+            seq_k.append(int(solo.cur_cnt.view(-1)[0]))
+        ranks = [_make(sd) for _ in range(world)]
+        for e in ranks:
+            _prime(e, 1)
+        for t0 in (0, 2):                                   # two groups with the replicated-state step
+            for r in range(world):
+                dets = ranks[r].dist_step(None, W_IMG, H_IMG, rank=r, world=world, payloads=torch.stack(payloads[t0:t0 + 2]))
+                for a, b in zip(seq[t0 + r], _snap(ranks[r], dets[r], seq_k[t0 + r])):
+                    assert torch.equal(a, b)
+        for t0 in (4, 6):                                   # then the wavefront step
+            dets = parallel.play([ranks[r]._wave(None, W_IMG, H_IMG, r, world, payload=payloads[t0 + r]) for r in range(world)])
+            for r in range(world):
+                for a, b in zip(seq[t0 + r], _snap(ranks[r], dets[r])):
+                    assert torch.equal(a, b), (t0, r)
