@@ -5,8 +5,8 @@ Inference side only: native `.pth` checkpoints (the released MEGA / RDN / FGFA /
 "model" state_dict, or a bare state_dict), with the reference's key alignment -- a "module." prefix of a
 (Distributed)DataParallel save is stripped, then every model key takes the loaded key that is its LONGEST SUFFIX
 (so a checkpoint saved under extra or missing name prefixes still lands on the right parameters). Caffe2 `.pkl`
-ImageNet backbones (`load_c2_format`), catalog / URL resolution and optimizer / scheduler state are training-time
-concerns and raise a clear error here. The module classes of mega_core.modeling build their B200 engine lazily from the
+ImageNet backbones go through `c2_model_loading.load_c2_format` (C4 / C5 ResNet bodies); catalog / URL resolution and
+optimizer / scheduler state are training-time concerns (the former raises a clear error, the latter is dropped). The module classes of mega_core.modeling build their B200 engine lazily from the
 module's state_dict, so weights loaded this way are what the kernels use."""
 import logging
 import os
@@ -93,7 +93,7 @@ class DetectronCheckpointer(Checkpointer):
             raise NotImplementedError("mega_core (B200 build): resolve %s to a local .pth file first (catalog / URL lookup "
                                       "is part of the reference's training-side tooling)" % f)
         if f.endswith(".pkl"):
-            raise NotImplementedError("mega_core (B200 build): Caffe2 .pkl backbones (load_c2_format) are training-time "
-                                      "initialisation; inference loads the released .pth checkpoints")
+            from .c2_model_loading import load_c2_format
+            return load_c2_format(self.cfg, f)
         loaded = super()._load_file(f)
         return loaded if "model" in loaded else dict(model=loaded)

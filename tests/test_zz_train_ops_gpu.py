@@ -6,8 +6,9 @@ reference's atomicAdd does, so float results are compared to 1e-5-level toleranc
 Order inside the file (the GPU tier runs with -x): most certain first -- integer-exact image transform, the simple
 scatter kernels, the engine-level wavefront / DFF checks (all-existing kernels in a new order), then the ops that also
 drive the tcgen05 GEMM with shapes it has not seen (deformable-conv backward, the layer wrappers).
-(This file sorts last on purpose: these kernels were added after the last GPU session of round 1 and are verified on
-the CPU through their host build only; a failure here must not hide the hot-path tests.)"""
+(This file sorts last on purpose: these kernels were added after the last full GPU session of round 1 and verified on
+the CPU first, through their host builds; a surprise here must not hide the hot-path tests. First B200 run: 20 of 21
+passed unchanged, see profiles/r01_summary.md.)"""
 import os
 import sys
 
@@ -309,9 +310,12 @@ def test_layers_autograd_on_device(cuda_dev):
 
 
 def test_nvjpeg_decode_feeds_the_transform(cuda_dev):
-    """encoded JPEG -> nvJPEG (torchvision.io.decode_jpeg on the device, a library decoder) -> planar uint8 -> the device
-    transform, without a host round trip. Decoders differ in the last bit of the IDCT, so the comparison with the
-    PIL-decoded pipeline is statistical; the transform itself is exact (previous test)."""
+    """encoded JPEG -> nvJPEG (torchvision.io.decode_jpeg on the device, a library decoder) -> planar uint8 [3, H, W] ->
+    the device transform, without a host round trip or re-layout. The transform must be bit-exact on the pixels nvJPEG
+    produced (checked against the reference pipeline fed with those very pixels). The decoders themselves are NOT
+    pixel-identical -- libjpeg-turbo (PIL) interpolates the subsampled chroma, nvJPEG replicates it, +-80 in a channel at a
+    sharp colour edge (first B200 run: mean |diff| 2.9 after the transform) -- so against the PIL-decoded frame only a
+    loose sanity bound is asserted."""
     import io
     import numpy as np
     import image_oracle as io_
@@ -323,12 +327,13 @@ def test_nvjpeg_decode_feeds_the_transform(cuda_dev):
     img = np.kron(base, np.ones((16, 16, 1), dtype=np.uint8))[:720, :1280]
     buf = io.BytesIO()
     Image.fromarray(img, "RGB").save(buf, format="JPEG", quality=92)
-    ref = io_.reference_pipeline(np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")), 600, 1000, mean, std, True)
     try:
         dec = decode_jpeg(buf.getvalue(), device=cuda_dev)
     except RuntimeError as e:                       # a torchvision build without nvJPEG: the library is absent, not ours
         pytest.skip("torchvision.io.decode_jpeg on the device is unavailable: %s" % str(e)[:80])
     assert dec.is_cuda and dec.dtype == torch.uint8 and tuple(dec.shape) == (3, 720, 1280)
     out, _ = DeviceTestTransform(600, 1000, mean, std, True, device=cuda_dev)(dec)
-    d = (out.cpu() - ref).abs()
-    assert out.shape == ref.shape and d.mean() < 0.5 and d.max() <= 12, (d.mean().item(), d.max().item())
+    same_pixels = io_.reference_pipeline(dec.permute(1, 2, 0).contiguous().cpu().numpy(), 600, 1000, mean, std, True)
+    assert torch.equal(out.cpu(), same_pixels)
+    pil = io_.reference_pipeline(np.asarray(Image.open(io.BytesIO(buf.getvalue())).convert("RGB")), 600, 1000, mean, std, True)
+    assert (out.cpu() - pil).abs().mean() < 10.0
