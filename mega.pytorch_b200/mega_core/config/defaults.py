@@ -8,6 +8,7 @@ merge_from_list, freeze/defrost, clone.
 """
 import ast
 import copy
+import os
 
 
 class CfgNode(dict):
@@ -136,5 +137,6 @@ _C = CfgNode({
                "WARMUP_ITERS": 500},
     "TEST": {"EXPECTED_RESULTS": [], "EXPECTED_RESULTS_SIGMA_TOL": 4, "IMS_PER_BATCH": 8, "DETECTIONS_PER_IMG": 100,
              "BBOX_AUG": {"ENABLED": False}},
-    "OUTPUT_DIR": ".", "DTYPE": "float32",
+    "OUTPUT_DIR": ".", "DTYPE": "float32", "AMP_VERBOSE": False,
+    "PATHS_CATALOG": os.path.join(os.path.dirname(os.path.abspath(__file__)), "paths_catalog.py"),
 })
