@@ -48,8 +48,11 @@ def make_tree(root, videos=(("val/vidA", 14, 160, 96), ("val/vidB", 9, 128, 80))
 class CpuTransform(object):
     """the reference's test-time transform (PIL pipeline) with its (image, target) -> (tensor, target) signature"""
 
+    def __init__(self, min_size=60, max_size=100):
+        self.min_size, self.max_size = min_size, max_size
+
     def __call__(self, image, target=None):
-        t = io_.reference_pipeline(np.asarray(image), 60, 100, MEAN, STD, True)
+        t = io_.reference_pipeline(np.asarray(image), self.min_size, self.max_size, MEAN, STD, True)
         if target is not None:
             target = target.resize((t.shape[2], t.shape[1]))
         return t, target
