@@ -52,9 +52,14 @@ def test_unmodified_tools_test_net_runs_on_this_package(tmp_path, monkeypatch):
                                       "INPUT.MAX_SIZE_TEST", "160", "MODEL.B200.PRECISION", "tf32"])
     np.random.seed(0)
     from mega_core.config import cfg
-    cfg.defrost()
-    with cpu_ops():
-        runpy.run_path(os.path.join(REF, "tools", "test_net.py"), run_name="__main__")
+    saved = cfg.clone()                      # the script merges into and freezes the package's GLOBAL cfg: put it back
+    try:
+        with cpu_ops():
+            runpy.run_path(os.path.join(REF, "tools", "test_net.py"), run_name="__main__")
+    finally:
+        cfg.defrost()
+        dict.clear(cfg)
+        dict.update(cfg, saved)
     folder = os.path.join(out_dir, "inference", "VID_val_videos")
     text = open(os.path.join(folder, "result.txt")).read()
     assert "AP50 | motion=   all" in text and "Category AP" in text
