@@ -1,20 +1,25 @@
-"""utils/logger.py:7-25: console (+ file) logger for rank 0, silent elsewhere"""
+"""`setup_logger(name, save_dir, distributed_rank)` as tools/test_net.py calls it (utils/logger.py of the reference):
+rank 0 logs to the console and, when a directory is given, to <save_dir>/log.txt; the other ranks stay silent."""
 import logging
 import os
 import sys
 
+_FORMAT = "%(asctime)s %(name)s %(levelname)s: %(message)s"
+
+
+def _sinks(save_dir, filename):
+    yield logging.StreamHandler(stream=sys.stdout)
+    if save_dir:
+        yield logging.FileHandler(os.path.join(save_dir, filename))
+
 
 def setup_logger(name, save_dir, distributed_rank, filename="log.txt"):
-    logger = logging.getLogger(name)
-    logger.setLevel(logging.DEBUG)
-    if distributed_rank > 0:
-        return logger
-    fmt = logging.Formatter("%(asctime)s %(name)s %(levelname)s: %(message)s")
-    handlers = [logging.StreamHandler(stream=sys.stdout)]
-    if save_dir:
-        handlers.append(logging.FileHandler(os.path.join(save_dir, filename)))
-    for h in handlers:
-        h.setLevel(logging.DEBUG)
-        h.setFormatter(fmt)
-        logger.addHandler(h)
-    return logger
+    log = logging.getLogger(name)
+    log.setLevel(logging.DEBUG)
+    if distributed_rank == 0:
+        formatter = logging.Formatter(_FORMAT)
+        for sink in _sinks(save_dir, filename):
+            sink.setLevel(logging.DEBUG)
+            sink.setFormatter(formatter)
+            log.addHandler(sink)
+    return log
