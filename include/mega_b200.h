@@ -113,9 +113,22 @@ long long mega_conv_chain_plan_bytes(int n_layers);
 int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_layers, void* plan_host, long long plan_bytes,
                            int* grid_out);
 int mega_conv_chain_launch(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream, int pdl);
+/* ABI v5: barrier depth. depth 1 = the calls above. depth 2: layer l waits for layer l-2 only, i.e. descs must be two
+ * INDEPENDENT chains interleaved A0 B0 A1 B1 ... (the per-frame branch of the two halves of an image batch: chain B's
+ * layer keeps every SM's TMA / MMA pipeline busy while chain A's layer drains its epilogue, stores and barrier), or any
+ * order in which a layer reads nothing the layer directly before it wrote. sync_words: depth + 1 device uint32, zeroed
+ * once. Odd layers use the second half of the workspace (tile counters / stream-K partial sums). */
+int mega_conv_chain_encode2(const mega_conv_gemm_desc* descs, int n_layers, void* plan_host, long long plan_bytes,
+                            int* grid_out, int depth);
+int mega_conv_chain_launch2(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream, int pdl,
+                            int depth);
 /* diagnostics: following chain launches record (tag, SM clock) events of CTA `cta` into trace_dev
  * ([3 roles][4096][2] uint64, zeroed by the caller); NULL switches tracing off (tools/trace_chain.py) */
 int mega_conv_chain_set_trace(void* trace_dev, int cta);
+/* 3xTF32 (precision 1): the tensor core adds into its fp32 TMEM accumulator with truncation, a bias that grows with
+ * the number of MMAs accumulated; the kernel restarts the accumulator every `k_blocks` k-blocks (12 MMAs each) and folds
+ * the segments into a master accumulator with round-to-nearest adds. 1..64, default 4; returns the previous value. */
+int mega_set_split3_seg_len(int k_blocks);
 /* TMA fp32->tf32 conversion on load (round-to-nearest) on/off; returns the previous value. */
 int mega_set_tf32_rounding(int enable);
 

@@ -12,6 +12,15 @@
 // ring are set up once; layers are separated by a grid-wide barrier (one atomic counter, release/acquire) instead of
 // a kernel boundary. Tensor maps live in the layer table in global memory.
 //
+// Barrier depth. With depth 1 layer l starts when every CTA has finished layer l-1: the tensor pipe idles through every
+// layer's tail (last epilogue ~2.2 us, store drain + gpu-scope release ~1 us, barrier ~0.8 us, first operand fetch
+// ~0.8 us: 5-6 us against 3-10 us of MMAs per ResNet-101 layer at two 600x1000 frames -- tools/trace_chain.py). With
+// depth 2 layer l only waits for layer l-2 (one arrival counter per layer parity), so a table that INTERLEAVES two
+// independent chains A0 B0 A1 B1 ... (the per-frame branch of two halves of an image batch) keeps the TMA / MMA warps of
+// every CTA streaming chain B's layer while chain A's tail drains, and vice versa. Stream-K partial sums and tile
+// counters of odd layers live in the second half of the workspace (a CTA may already publish partials of layer l+1
+// while a slower CTA still reduces layer l).
+//
 // Restrictions of a chain: fp16 operands (kind::f16), block_n <= 128 (one 32 KB smem stage holds A 128 x 64 and B
 // block_n x 64 halves), output fp16 or fp32 per layer.
 #include "conv_gemm_kernel.cuh"
@@ -306,7 +315,8 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, unsigned* sync, const ChainTrace trace) {
+conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, unsigned* sync, const ChainTrace trace,
+                  const int depth) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kChainBarOffset);
@@ -365,7 +375,8 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         const CUtensorMap* tmB = &L->tmB;
         const uint32_t tx_bytes = static_cast<uint32_t>((kBM + BN) * 128);
         tr.put(TR_TAG(l, 0, 1));
-        if (l > 0) grid_wait(sync, static_cast<unsigned>(l) * grid);
+        // layer l may read what layers <= l - depth wrote: all CTAs have arrived l / depth times at counter l % depth
+        if (l >= depth) grid_wait(sync + (l % depth), static_cast<unsigned>(l / depth) * grid);
         tr.put(TR_TAG(l, 0, 2));
         if (cta >= act) continue;
         WorkIter it(p, cta, act);
@@ -463,8 +474,8 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
       }
       // residual / partial-sum reads of this layer must see what the other CTAs wrote in earlier layers
       // (one poller per CTA; the named barrier passes the acquired state on to the other epilogue threads)
-      if (l > 0) {
-        if (epi_tid == 0) grid_wait(sync, static_cast<unsigned>(l) * grid);
+      if (l >= depth) {
+        if (epi_tid == 0) grid_wait(sync + (l % depth), static_cast<unsigned>(l / depth) * grid);
         epi_bar_sync();
         fence_proxy_async_all();
       }
@@ -489,16 +500,15 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
       if (epi_tid == 0) {
         fence_proxy_async_all();
         __threadfence();
-        atomicAdd(sync, 1u);
+        atomicAdd(sync + (l % depth), 1u);
       }
       tr.put(TR_TAG(l, 0, 10));
     }
     // last CTA out resets the barrier words for the next launch (every CTA has passed every barrier by then)
     if (epi_tid == 0) {
-      const unsigned old = atomicAdd(sync + 1, 1u);
+      const unsigned old = atomicAdd(sync + depth, 1u);
       if (old == static_cast<unsigned>(grid) - 1) {
-        sync[0] = 0;
-        sync[1] = 0;
+        for (int i = 0; i <= depth; ++i) sync[i] = 0;
         __threadfence();
       }
     }
@@ -524,9 +534,10 @@ extern "C" long long mega_conv_chain_plan_bytes(int n_layers) {
   return static_cast<long long>(n_layers) * static_cast<long long>(sizeof(ChainLayer));
 }
 
-extern "C" int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_layers, void* plan_host,
-                                      long long plan_bytes, int* grid_out) {
+extern "C" int mega_conv_chain_encode2(const mega_conv_gemm_desc* descs, int n_layers, void* plan_host,
+                                       long long plan_bytes, int* grid_out, int depth) {
   MEGA_ARG_CHECK(descs != nullptr && plan_host != nullptr && n_layers > 0, "conv_chain: bad arguments");
+  MEGA_ARG_CHECK(depth == 1 || depth == 2, "conv_chain: barrier depth must be 1 or 2 (got %d)", depth);
   MEGA_ARG_CHECK(plan_bytes >= mega_conv_chain_plan_bytes(n_layers), "conv_chain: plan buffer too small");
   MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(plan_host) & 127) == 0, "conv_chain: plan buffer must be 128-byte aligned");
   ChainLayer* out = static_cast<ChainLayer*>(plan_host);
@@ -545,9 +556,24 @@ extern "C" int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_la
     L->active_ctas = ctas;
     L->reserved = 0;
     if (ctas > grid) grid = ctas;
+    if (depth == 2) {
+      // two layers are in flight: odd layers take the second half of the tile counters and of the partial-sum area
+      // (block_n <= 128 in a chain, so one half holds kMaxCtas x 2 x 128 x 128 floats)
+      MEGA_ARG_CHECK(L->p.total_tiles <= 32768, "conv_chain: layer %d: %lld tiles exceed the 32768 counters of a depth-2 chain", l,
+                     L->p.total_tiles);
+      if (l & 1) {
+        L->p.counters += 32768;
+        L->p.part_ws += static_cast<long long>(kMaxCtas) * 2 * kBM * 128;
+      }
+    }
   }
   if (grid_out) *grid_out = grid;
   return MEGA_OK;
+}
+
+extern "C" int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_layers, void* plan_host,
+                                      long long plan_bytes, int* grid_out) {
+  return mega_conv_chain_encode2(descs, n_layers, plan_host, plan_bytes, grid_out, 1);
 }
 
 static ChainTrace g_chain_trace = {nullptr, 0};
@@ -560,11 +586,12 @@ extern "C" int mega_conv_chain_set_trace(void* trace_dev, int cta) {
   return MEGA_OK;
 }
 
-extern "C" int mega_conv_chain_launch(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream_v,
-                                      int pdl) {
+extern "C" int mega_conv_chain_launch2(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream_v,
+                                       int pdl, int depth) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   MEGA_ARG_CHECK(plan_device != nullptr && sync_words != nullptr && n_layers > 0 && grid > 0 && grid <= kMaxCtas,
                  "conv_chain_launch: bad arguments (grid %d)", grid);
+  MEGA_ARG_CHECK(depth == 1 || depth == 2, "conv_chain_launch: barrier depth must be 1 or 2 (got %d)", depth);
   MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(plan_device) & 127) == 0, "conv_chain_launch: plan must be 128-byte aligned");
   static bool configured = false;
   if (!configured) {
@@ -582,6 +609,11 @@ extern "C" int mega_conv_chain_launch(const void* plan_device, int n_layers, int
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   MEGA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_chain_kernel, static_cast<const ChainLayer*>(plan_device), n_layers,
-                                     static_cast<unsigned*>(sync_words), g_chain_trace));
+                                     static_cast<unsigned*>(sync_words), g_chain_trace, depth));
   return MEGA_OK;
+}
+
+extern "C" int mega_conv_chain_launch(const void* plan_device, int n_layers, int grid, void* sync_words, void* stream_v,
+                                      int pdl) {
+  return mega_conv_chain_launch2(plan_device, n_layers, grid, sync_words, stream_v, pdl, 1);
 }

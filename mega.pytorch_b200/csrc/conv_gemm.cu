@@ -41,6 +41,7 @@ static EncodeTiledFn get_encode_fn() {
 static int g_tf32_round = 1;  // TMA converts fp32 -> tf32 (round to nearest) while loading
 
 static int g_num_sms = 0;
+static int g_seg_len = 4;      // 3xTF32: k-blocks per accumulator segment
 constexpr int kCounterSlots = 65536;   // ints at the head of the workspace
 constexpr int kMinUnits = 4;
 
@@ -51,6 +52,12 @@ using namespace mega;
 extern "C" long long mega_conv_gemm_workspace_bytes(void) {
   return static_cast<long long>(kCounterSlots) * sizeof(int) +
          static_cast<long long>(kMaxCtas) * 2 * kBM * 256 * sizeof(float);
+}
+
+extern "C" int mega_set_split3_seg_len(int k_blocks) {
+  int old = g_seg_len;
+  if (k_blocks >= 1 && k_blocks <= 64) g_seg_len = k_blocks;
+  return old;
 }
 
 extern "C" int mega_set_tf32_rounding(int enable) {
@@ -237,6 +244,7 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   p.total_units = tiles * p.kb_per_tile;
   p.total_tiles = tiles;
   p.stream_k = d->stream_k ? 1 : 0;
+  p.seg_len = g_seg_len;
   MEGA_ARG_CHECK(tiles <= kCounterSlots, "conv_gemm: %lld output tiles exceed the %d counter slots", tiles, kCounterSlots);
   MEGA_ARG_CHECK(p.total_units > 0, "conv_gemm: empty problem");
   MEGA_ARG_CHECK(p.total_units * kMaxCtas < (1LL << 31), "conv_gemm: %lld work units exceed the 32-bit work-list range",

@@ -57,6 +57,7 @@ struct ConvGemmParams {
   int stream_k;              // 1: k-block granular split across CTAs, 0: whole tiles round-robin
   float* part_ws;            // [grid][2][128][BN] partial accumulators
   int* counters;             // [tiles], zero between launches
+  int seg_len;               // 3xTF32 only: k-blocks accumulated in TMEM before the RN fold into the master accumulator
 };
 
 template <int BN, int STAGES, int MODE = kModeTf32>
@@ -172,7 +173,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // embedding of the relation module amplifies to 5e-3 on the final logits). The strict mode therefore restarts the
   // TMEM accumulator every kSegLen k-blocks (4 k-blocks = 48 truncating adds, <= 3e-6 relative) and folds the segments into a master accumulator (also in TMEM)
   // with round-to-nearest fp32 adds done by the epilogue warps.
-  constexpr int kSegLen = SPLIT3 ? 4 : 0x7fffffff;
+  const int kSegLen = SPLIT3 ? p.seg_len : 0x7fffffff;   // k-blocks per accumulator segment (mega_set_split3_seg_len, default 4)
   extern __shared__ uint8_t smem_raw[];
   // the 128B swizzle pattern is a function of the absolute smem address: align to 1024 B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &

@@ -161,14 +161,40 @@ class ResNetStages:
                 b += 1
             self.stages.append(blocks)
         self._bufs = {}
+        self.lane = 0       # interleaved chains (ops.chain(interleave=True)): each lane owns its scratch buffers
 
     def _buf(self, tag, shape):
-        key = (tag, tuple(shape))
+        key = (tag, tuple(shape), self.lane)
         t = self._bufs.get(key)
         if t is None:
             t = torch.zeros(*shape, device=self.dev, dtype=self.dtype)
             self._bufs[key] = t
         return t
+
+    def out_shape(self, shape):
+        """[N,H,W,C] of the input -> [N,H',W',C'] of forward()'s result"""
+        n, h, w, _ = shape
+        for blocks in self.stages:
+            if blocks[0].stride == 2:
+                h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        return (n, h, w, self.stages[-1][-1].cout)
+
+    def forward_lanes(self, x, ch, out, max_ctas=0, tail=None):
+        """forward() on the two halves of the batch as the two lanes of an interleaved chain `ch` (results in `out`)"""
+        n = x.shape[0]
+        h = n // 2
+        assert n == 2 * h and out.shape[0] == n
+        for lane in (0, 1):
+            if lane:
+                ch.next_lane()
+            self.lane = lane
+            try:
+                y = self.forward(x[lane * h:(lane + 1) * h], out=out[lane * h:(lane + 1) * h], max_ctas=max_ctas)
+            finally:
+                self.lane = 0
+            if tail is not None:
+                tail(y, lane)
+        return out
 
     def forward(self, x, out=None, max_ctas=0):
         """x [N,H,W,C] NHWC -> [N,H',W',C'] (max_ctas > 0: leave SMs free for a concurrent stream)"""
@@ -231,8 +257,9 @@ class Backbone:
 
     def forward(self, img, out=None, tail=None):
         """img [N,3,H,W] fp32 NCHW (the reference's post-transform domain) -> NHWC [N,H/16,W/16,1024].
-        fp16 mode: res2..res4 (93 convolutions for R-101) run as ONE persistent chain kernel (ops.chain); `tail(feats)`
-        may append further conv_gemm calls on the result to the same chain (the RPN head)."""
+        fp16 mode: res2..res4 (93 convolutions for R-101) run as ONE persistent chain kernel (ops.chain); `tail(feats, lane)`
+        may append further conv_gemm calls on the result to the same chain (the RPN head). An even batch runs as two
+        interleaved lanes (depth-2 chain): `tail` is then called once per half with lane = 0 / 1 (None otherwise)."""
         n, _, h, w = img.shape
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         s = self._buf("stem", (n, ho, wo, 64))
@@ -253,11 +280,18 @@ class Backbone:
         hp, wp = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         p = self._buf("pool", (n, hp, wp, 64))
         ops.maxpool3x3s2(s, p)
-        with ops.chain(self._chains, ("body", tuple(p.shape), tail is not None), self.dev,
-                       enabled=self.dtype == torch.float16):
-            y = self.stages.forward(p, out=out)
-            if tail is not None:
-                tail(y)
+        chained = self.dtype == torch.float16
+        dual = chained and ops.DUAL_CHAIN[0] and n >= 2 and n % 2 == 0
+        with ops.chain(self._chains, ("body", tuple(p.shape), tail is not None, dual), self.dev, enabled=chained,
+                       interleave=dual) as ch:
+            if dual and ch.interleave:
+                if out is None:
+                    out = self._buf("feats", self.stages.out_shape(p.shape))
+                y = self.stages.forward_lanes(p, ch, out, tail=tail)
+            else:
+                y = self.stages.forward(p, out=out)
+                if tail is not None:
+                    tail(y, None)
         return y
 
 
@@ -354,13 +388,20 @@ class HeadCommon:
             self._bufs[key] = t
         return t
 
-    def rpn_head(self, feats):
-        """RPNHead.forward (rpn/rpn.py:99-106): 3x3 conv + ReLU, then objectness and box deltas as one 1x1 GEMM"""
+    def rpn_head(self, feats, lane=None, n_total=None):
+        """RPNHead.forward (rpn/rpn.py:99-106): 3x3 conv + ReLU, then objectness and box deltas as one 1x1 GEMM.
+        lane 0 / 1: `feats` is one half of a batch of n_total images run as an interleaved chain -- own scratch per lane,
+        the result goes into that half of the full-batch head buffer (which is returned)"""
         n, h, w, _ = feats.shape
-        t = self._buf("rpn_t", (n, h, w, feats.shape[3]), self.act)
+        if lane is None:
+            t = self._buf("rpn_t", (n, h, w, feats.shape[3]), self.act)
+            head = out = self._buf("rpn_head", (n, h, w, self.rpn_ld))
+        else:
+            t = self._buf("rpn_t_lane%d" % lane, (n, h, w, feats.shape[3]), self.act)
+            head = self._buf("rpn_head", (n_total, h, w, self.rpn_ld))
+            out = head[lane * n:(lane + 1) * n]
         ops.conv_gemm(feats, self.rpn_w, t, taps=(3, 3), dil=1, pad=1, bias=self.rpn_b, relu=True)
-        head = self._buf("rpn_head", (n, h, w, self.rpn_ld))
-        ops.conv_gemm(t, self.rpn_hw, head, bias=self.rpn_hb, cout=5 * self.num_anchors, block_n=64)
+        ops.conv_gemm(t, self.rpn_hw, out, bias=self.rpn_hb, cout=5 * self.num_anchors, block_n=64)
         return head
 
     def rpn(self, feats, im_w, im_h, post, head=None):
@@ -524,7 +565,7 @@ class WindowedEngine(HeadCommon):
         head = None
         if self.chained:      # the RPN head's two GEMMs ride at the end of the backbone chain
             heads = []
-            feats = self.backbone.forward(imgs, tail=lambda f: heads.append(self.rpn_head(f)))
+            feats = self.backbone.forward(imgs, tail=lambda f, lane: heads.append(self.rpn_head(f, lane, n)))
             head = heads[0]
         else:
             feats = self.backbone.forward(imgs)
@@ -540,8 +581,16 @@ class WindowedEngine(HeadCommon):
                 boxes, _, cnt = self.rpn(feats, im_w, im_h, self.KP, head=head)
             finally:
                 ops.WS_LANE[0] = 0
-        with ops.chain(self._chains, ("res5", tuple(feats.shape)), self.dev, enabled=self.chained, max_ctas=144):
-            r5 = self.res5.forward(feats, max_ctas=144)
+        side_ctas = max(4, n)       # the proposal selection runs one latency-bound CTA per image beside the res5 chain
+        mc = 148 - side_ctas
+        dual = self.chained and ops.DUAL_CHAIN[0] and n >= 2 and n % 2 == 0
+        with ops.chain(self._chains, ("res5", tuple(feats.shape), dual), self.dev, enabled=self.chained, max_ctas=mc,
+                       interleave=dual) as ch:
+            if dual and ch.interleave:
+                r5 = self.res5.forward_lanes(feats, ch, self._buf("res5_out", self.res5.out_shape(feats.shape), self.act),
+                                             max_ctas=mc)
+            else:
+                r5 = self.res5.forward(feats, max_ctas=mc)
         main.wait_stream(self._side)
         src, bidx, spans = self._roi_table(kinds)
         rows = src.numel()
@@ -621,6 +670,7 @@ class WindowedEngine(HeadCommon):
 class MegaEngine(WindowedEngine, WavefrontMixin):
     """GeneralizedRCNNMEGA._forward_test + MEGAFeatureExtractor test path
     (detector/generalized_rcnn_mega.py:137-225; extractors :657-699, :754-774, :806-829, :885-933)."""
+    MAX_FRAMES_PER_STEP = 4      # key frames whose per-frame branch stepn_batched may run as one batch
 
     def __init__(self, sd, cfg=None, device="cuda"):
         cfg = cfg or EngineConfig()
@@ -671,7 +721,7 @@ class MegaEngine(WindowedEngine, WavefrontMixin):
         nq_g0 = KP + self.nl0
         self._alloc_attention([(nq_g0, self.ld_g), (self.nq, self.ld_0), (self.nq, self.ld_12)],
                               max(self.nl0 + self.mem_cap0, GF * R))
-        nroi = 2 * (KP + R)                                     # two (local 300 + global 75) pairs: step2_batched
+        nroi = self.MAX_FRAMES_PER_STEP * (KP + R)              # n (local 300 + global 75) pairs: stepn_batched
         self.pooled = za(nroi, res * res * ch)
         self.fc0_out = za(nroi, D)
         self.roi_boxes, self.roi_batch = z(nroi, 4), z(nroi, dtype=torch.int32)
@@ -882,27 +932,34 @@ class MegaEngine(WindowedEngine, WavefrontMixin):
         return payloads
 
     @_with_precision
-    def step2_batched(self, imgs4, im_w, im_h):
-        """TWO key frames per call (offline streams: all frames are at hand): imgs4 [4,3,H,W] = (local t, global t,
-        local t+1, global t+1). The per-frame branch -- a pure function of each frame -- runs once on the batch of four
-        (twice the rows per layer of the 2.5 ms branch), then the two aggregations run in order. Same results as two
-        step_batched calls; returns [Detections t (a copy), Detections t+1]. EXPERIMENTAL: logic verified on the CPU
-        stand-ins (tests/test_engine_logic_cpu.py), first GPU run / timing pending (bench.py --frames-per-step 2)."""
-        static_in = self.static_input(tuple(imgs4.shape))
-        if imgs4.data_ptr() != static_in.data_ptr():
-            static_in.copy_(imgs4, non_blocking=True)
-        if getattr(self, "payload2", None) is None:
-            self.payload2 = torch.zeros(2, self.payload_in.numel(), device=self.dev)
-        self._graph_run(("ref2", tuple(imgs4.shape), im_w, im_h),
-                        lambda: self._ref_to_payloads(static_in, im_w, im_h, [self.payload2[0], self.payload2[1]]))
+    def stepn_batched(self, imgs, im_w, im_h):
+        """n key frames per call (offline streams: all frames are at hand): imgs [2n,3,H,W] = (local t, global t,
+        local t+1, global t+1, ...). The per-frame branch -- a pure function of each frame -- runs once on the batch of
+        2n images (n times the rows per layer of the per-frame chain kernels), then the n aggregations run in order. Same
+        results as n step_batched calls up to the re-association noise of differently tiled GEMMs; n - 1 frames more
+        latency. Returns [Detections t, ..., Detections t+n-1] (all but the last are copies: the detection buffers are
+        static)."""
+        n = imgs.shape[0] // 2
+        assert imgs.shape[0] == 2 * n and 1 <= n <= self.MAX_FRAMES_PER_STEP, imgs.shape
+        static_in = self.static_input(tuple(imgs.shape))
+        if imgs.data_ptr() != static_in.data_ptr():
+            static_in.copy_(imgs, non_blocking=True)
+        if getattr(self, "payload_n", None) is None:
+            self.payload_n = torch.zeros(self.MAX_FRAMES_PER_STEP, self.payload_in.numel(), device=self.dev)
+        self._graph_run(("refn", tuple(imgs.shape), im_w, im_h),
+                        lambda: self._ref_to_payloads(static_in, im_w, im_h, [self.payload_n[i] for i in range(n)]))
         dets = []
-        for i in range(2):
-            self.payload_in.copy_(self.payload2[i], non_blocking=True)
+        for i in range(n):
+            self.payload_in.copy_(self.payload_n[i], non_blocking=True)
             det = self._ingest_next(im_w, im_h)
-            if i == 0:          # the detection buffers are static: keep frame t's before frame t+1 overwrites them
+            if i < n - 1:
                 det = Detections(det.boxes.clone(), det.scores.clone(), det.labels.clone(), det.count.clone())
             dets.append(det)
         return dets
+
+    def step2_batched(self, imgs4, im_w, im_h):
+        """two key frames per call (stepn_batched with n = 2)"""
+        return self.stepn_batched(imgs4, im_w, im_h)
 
     def _payload_to_rings(self):
         """payload_in -> window / global-pool ring slots named by the index tables"""

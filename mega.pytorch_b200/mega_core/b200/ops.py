@@ -65,16 +65,16 @@ def _copy_desc(d):
 
 
 class ConvChain(object):
-    def __init__(self, descs, device, max_ctas=0):
+    def __init__(self, descs, device, max_ctas=0, depth=1):
         n = len(descs)
-        self.n = n
+        self.n, self.depth = n, depth
         arr = (ConvGemmDesc * n)(*descs)
         nbytes = int(lib.mega_conv_chain_plan_bytes(n))
         host = torch.zeros(nbytes + 128, dtype=torch.uint8)
         off = (-host.data_ptr()) % 128
         grid = ctypes.c_int(0)
-        check(lib.mega_conv_chain_encode(arr, n, ctypes.c_void_p(host.data_ptr() + off), nbytes, ctypes.byref(grid)),
-              "mega_conv_chain_encode")
+        check(lib.mega_conv_chain_encode2(arr, n, ctypes.c_void_p(host.data_ptr() + off), nbytes, ctypes.byref(grid), depth),
+              "mega_conv_chain_encode2")
         if max_ctas > 0 and grid.value > max_ctas:
             raise _lib.MegaError("conv chain: a layer wants %d CTAs, more than max_ctas=%d (pass max_ctas to every "
                                  "conv_gemm of the chain)" % (grid.value, max_ctas))
@@ -84,15 +84,15 @@ class ConvChain(object):
         self.plan = dev_buf[doff:doff + nbytes]
         self.plan.copy_(host[off:off + nbytes])
         self._keep = dev_buf
-        self.sync = torch.zeros(2, dtype=torch.int32, device=device)
+        self.sync = torch.zeros(4, dtype=torch.int32, device=device)
         self.flops = sum(_desc_flops(d) for d in descs)
-        self.info = {"chain_layers": n, "grid": self.grid, "layers": [_desc_info(d) for d in descs]}
+        self.info = {"chain_layers": n, "grid": self.grid, "depth": depth, "layers": [_desc_info(d) for d in descs]}
         torch.cuda.current_stream(device).synchronize()
 
     def launch(self):
         def run():
-            check(lib.mega_conv_chain_launch(ptr(self.plan), self.n, self.grid, ptr(self.sync), stream_ptr(),
-                                             1 if PDL[0] else 0), "mega_conv_chain_launch")
+            check(lib.mega_conv_chain_launch2(ptr(self.plan), self.n, self.grid, ptr(self.sync), stream_ptr(),
+                                              1 if PDL[0] else 0, self.depth), "mega_conv_chain_launch2")
         _run_timed(run, self.flops, self.info)
         LAUNCHES[0] += 1
 
@@ -100,11 +100,23 @@ class ConvChain(object):
 class chain(object):
     """context manager: record-once / replay a chain of conv_gemm calls (see above). `cache` is a dict owned by the
     caller, `key` identifies the call sequence (shapes); disabled (plain per-layer launches) when the tensors are not
-    fp16, when chains are switched off, or while autotuning a shape for the first time."""
+    fp16, when chains are switched off, or while autotuning a shape for the first time.
 
-    def __init__(self, cache, key, device, enabled=True, max_ctas=0):
+    interleave=True: the body issues the SAME layer sequence twice, on two independent halves of its batch (disjoint
+    buffers), calling `next_lane()` between them; the two recordings are interleaved A0 B0 A1 B1 ... and run with barrier
+    depth 2 (csrc/conv_chain.cu): a CTA streams lane B's layer while lane A's layer drains its epilogue / stores / grid
+    barrier. Results are those of the two sequences run one after the other."""
+
+    def __init__(self, cache, key, device, enabled=True, max_ctas=0, interleave=False):
         self.cache, self.key, self.device, self.max_ctas = cache, key, device, max_ctas
         self.enabled = enabled and CHAINS_ENABLED[0] and _CHAIN_MODE[0] is None
+        self.interleave = interleave and self.enabled
+        self.split = None
+
+    def next_lane(self):
+        if self.enabled and _CHAIN_MODE[0] == "record":
+            assert self.interleave and self.split is None
+            self.split = len(_CHAIN_REC[0])
 
     def __enter__(self):
         if not self.enabled:
@@ -130,10 +142,20 @@ class chain(object):
         if mode == "record":
             descs = _CHAIN_REC[0]
             _CHAIN_REC[0] = None
-            self.cache[self.key] = ConvChain(descs, self.device, self.max_ctas)
+            depth = 1
+            if self.interleave:
+                assert self.split is not None and 2 * self.split == len(descs), \
+                    "interleaved chain: the two lanes must record the same number of layers (%s / %d)" % (self.split, len(descs))
+                descs = [d for pair in zip(descs[:self.split], descs[self.split:]) for d in pair]
+                depth = 2
+            self.cache[self.key] = ConvChain(descs, self.device, self.max_ctas, depth)
         self.cache[self.key].launch()
         return False
 
+
+# interleaved (depth-2) chains for the per-frame branch when the image batch splits into two halves
+import os as _os
+DUAL_CHAIN = [_os.environ.get("MEGA_B200_DUAL_CHAIN", "1") != "0"]
 
 # programmatic dependent launch of the GEMM kernels (prologue overlapped with the previous kernel's tail)
 PDL = [True]

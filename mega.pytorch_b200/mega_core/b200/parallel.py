@@ -18,6 +18,11 @@ def frames_of_step(step, world):
     return list(range(step * world, (step + 1) * world))
 
 
+# diagnostics: when COMM_EVENTS[0] is a list, every device all-gather appends its (start, end) CUDA events to it
+# (bench.py's per-rank breakdown of a multi-GPU step; never set inside a timed region)
+COMM_EVENTS = [None]
+
+
 def gather_payloads(payload, out=None, group=None):
     """all-gather equal-size 1-D payloads -> [world, n] in rank (= frame) order. NCCL on GPUs
     (`all_gather_into_tensor`), gloo for the CPU tests of this host logic."""
@@ -25,7 +30,14 @@ def gather_payloads(payload, out=None, group=None):
     if out is None:
         out = torch.empty(world, payload.numel(), dtype=payload.dtype, device=payload.device)
     if payload.is_cuda:
+        rec = COMM_EVENTS[0]
+        if rec is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
         dist.all_gather_into_tensor(out.view(-1), payload.contiguous(), group=group)
+        if rec is not None:
+            b.record()
+            rec.append((a, b))
     else:
         parts = [out[i] for i in range(world)]
         dist.all_gather(parts, payload.contiguous(), group=group)

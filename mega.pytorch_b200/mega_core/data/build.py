@@ -38,7 +38,15 @@ def make_data_loader(cfg, is_train=False, is_distributed=False, start_iter=0, is
         transforms = build_transforms(cfg, is_train=False)
     loaders = []
     for dataset in build_dataset(cfg.DATASETS.TEST, transforms, dataset_catalog, False, method):
-        if is_distributed:
+        if is_distributed and method == "base":
+            # make_data_sampler (data/build.py:62-77): the single-frame baseline shards IMAGES (the base VIDDataset has no
+            # video index; samplers.DistributedSampler there == torch's, padding the tail so every rank gets equally many)
+            from torch.utils.data.distributed import DistributedSampler
+            from ..utils.comm import get_rank
+            sampler = DistributedSampler(dataset, num_replicas=world, rank=get_rank(), shuffle=False)
+        elif is_distributed:
+            if method not in ("rdn", "mega", "fgfa", "dff"):
+                raise NotImplementedError("Method {} is not implemented.".format(method))
             sampler = VIDTestDistributedSampler(dataset, shuffle=False)
         else:
             sampler = torch.utils.data.sampler.SequentialSampler(dataset)

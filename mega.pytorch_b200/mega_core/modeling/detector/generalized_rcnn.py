@@ -113,6 +113,34 @@ class GeneralizedRCNNMEGA(_EngineBacked):
                 det = eng.step_batched(pair, im_w, im_h)
         return [self._to_boxlist(det, im_w, im_h)]
 
+    def forward_frames(self, images_list):
+        """Offline streams (tools/test_net.py reads every frame from disk, so the frames after `cur` are at hand):
+        n consecutive steady-state frames (each the dict forward() takes, frame_category 1) in ONE call. The per-frame
+        branch -- backbone / RPN / res5 / ROIAlign / l_fcs[0], a pure function of each frame -- runs as one batch of
+        2n images (MegaEngine.stepn_batched), the n aggregations in order. Returns n results, each what forward()
+        returns for that frame; n <= MegaEngine.MAX_FRAMES_PER_STEP."""
+        if self.training:
+            raise NotImplementedError("the B200 build covers inference (eval mode) only")
+        eng = self.engine
+        n = len(images_list)
+        assert all(im["frame_category"] == 1 and len(im["ref_l"]) == 1 and len(im["ref_g"]) == 1 for im in images_list), \
+            "forward_frames takes steady-state frames (one look-ahead local frame and one global frame each)"
+        cur = to_image_list(images_list[0]["cur"])
+        im_h, im_w = cur.image_sizes[0]
+        with torch.no_grad():
+            buf = eng.static_input((2 * n,) + tuple(cur.tensors.shape[1:]))
+            for i, im in enumerate(images_list):
+                self.end_id = min(getattr(self, "end_id", 0) + 1, getattr(self, "seg_len", 1) - 1)
+                buf[2 * i].copy_(self._host(im["ref_l"][0]), non_blocking=True)
+                buf[2 * i + 1].copy_(self._host(im["ref_g"][0]), non_blocking=True)
+            dets = eng.stepn_batched(buf, im_w, im_h)
+        out, d2h = [], 0
+        for det in dets:
+            out.append([self._to_boxlist(det, im_w, im_h)])
+            d2h += self.d2h_bytes_per_frame
+        self.d2h_bytes_per_frame = d2h / n
+        return out
+
     @staticmethod
     def _host(t):
         t = t.tensors if hasattr(t, "tensors") else t

@@ -263,15 +263,33 @@ def build_roi_heads(cfg, in_channels):
 
 
 def engine_config_from(cfg):
+    """reference config -> EngineConfig. Keys that change the reference's behaviour but whose non-default values the
+    engines do not implement are REJECTED here instead of being ignored (a non-default YAML must not give silently
+    different detections)."""
     m = cfg.MODEL
     v = m.VID
     win = {"rdn": v.RDN, "fgfa": v.FGFA}.get(v.METHOD, v.MEGA)     # window geometry of the method
+    unsupported = []
+    if not m.RESNETS.STRIDE_IN_1X1:
+        unsupported.append("MODEL.RESNETS.STRIDE_IN_1X1 = False (the engines put the stride on the 1x1 conv, resnet.py:288-291)")
+    if v.METHOD in ("rdn", "mega") and v.RPN.REF_PRE_NMS_TOP_N != m.RPN.PRE_NMS_TOP_N_TEST:
+        unsupported.append("MODEL.VID.RPN.REF_PRE_NMS_TOP_N != MODEL.RPN.PRE_NMS_TOP_N_TEST (the reference proposals of a frame "
+                           "are taken as the prefix of its key proposals, which needs equal pre-NMS sets)")
+    if v.METHOD == "mega":
+        if not (v.MEGA.MEMORY.ENABLE and v.MEGA.GLOBAL.ENABLE):
+            unsupported.append("MODEL.VID.MEGA.MEMORY.ENABLE / GLOBAL.ENABLE = False (MegaEngine is laid out for memory + "
+                               "global aggregation, generalized_rcnn_mega.py:36-40)")
+    if unsupported:
+        raise NotImplementedError("mega_core (B200 build): " + "; ".join(unsupported))
+    # the reference sizes the long-range memory deques with ALL_FRAME_INTERVAL (roi_box_feature_extractors.py:660-668:
+    # deque(maxlen=self.all_frame_interval)); MODEL.VID.MEGA.MEMORY.SIZE is not read at test time
+    memory_size = v.MEGA.ALL_FRAME_INTERVAL if v.METHOD == "mega" else v.MEGA.MEMORY.SIZE
     return _engine.EngineConfig(
         pre_nms_top_n=m.RPN.PRE_NMS_TOP_N_TEST, post_nms_top_n=m.RPN.POST_NMS_TOP_N_TEST,
         ref_post_nms_top_n=v.RPN.REF_POST_NMS_TOP_N, rpn_nms_thresh=m.RPN.NMS_THRESH, rpn_min_size=m.RPN.MIN_SIZE,
         ratio=win.get("RATIO", 0.2), all_frame_interval=win.ALL_FRAME_INTERVAL, key_frame_location=win.KEY_FRAME_LOCATION,
         advanced_stage=v.ROI_BOX_HEAD.ATTENTION.ADVANCED_STAGE,
-        memory_size=v.MEGA.MEMORY.SIZE, global_size=v.MEGA.GLOBAL.SIZE, global_res_stage=v.MEGA.GLOBAL.RES_STAGE,
+        memory_size=memory_size, global_size=v.MEGA.GLOBAL.SIZE, global_res_stage=v.MEGA.GLOBAL.RES_STAGE,
         stage=v.ROI_BOX_HEAD.ATTENTION.STAGE, groups=v.ROI_BOX_HEAD.ATTENTION.GROUP,
         pooler_resolution=m.ROI_BOX_HEAD.POOLER_RESOLUTION, pooler_scale=m.ROI_BOX_HEAD.POOLER_SCALES[0],
         sampling_ratio=m.ROI_BOX_HEAD.POOLER_SAMPLING_RATIO, res5_dilation=m.RESNETS.RES5_DILATION,

@@ -307,6 +307,68 @@ def test_f16_layer_chain_matches_per_layer_launches(cuda_dev):
     assert _rel_err(y_ch.float(), x.float()) < 1e-2      # fp16 storage of 9 chained layers
 
 
+def test_f16_interleaved_chain_matches_per_layer_launches(cuda_dev):
+    """barrier depth 2 (ops.chain(interleave=True)): the res4 pattern on the two halves of a batch of four 38 x 63 maps as
+    two interleaved lanes A0 B0 A1 B1 ... of ONE chain kernel, every layer waiting only for the layer two positions back.
+    With the tile configuration pinned the result must be bit-identical to the separate launches of the same layers
+    (stream-K on and off: odd layers keep their partial sums / tile counters in the second half of the workspace);
+    replayed several times (barrier reset) and with unequal work per lane position (3x3 vs 1x1) back to back."""
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(22)
+    n, h, w, c, mid = 4, 38, 63, 512, 128
+    x0 = torch.randn(n, h, w, c, generator=g).half().to(cuda_dev)
+    blocks = []
+    for b in range(4):
+        w1 = (torch.randn(1, mid, c, generator=g) / c ** 0.5).half().to(cuda_dev)
+        w2 = (torch.randn(9, mid, mid, generator=g) / (9 * mid) ** 0.5).half().to(cuda_dev)
+        w3 = (torch.randn(1, c, mid, generator=g) / mid ** 0.5).half().to(cuda_dev)
+        sb = [(torch.rand(k, generator=g) * 0.5 + 0.75).to(cuda_dev) for k in (mid, mid, c)]
+        bb = [(torch.randn(k, generator=g) * 0.1).to(cuda_dev) for k in (mid, mid, c)]
+        blocks.append((w1, w2, w3, sb, bb))
+    wh = (torch.randn(1, 60, c, generator=g) / c ** 0.5).half().to(cuda_dev)
+
+    def run(bufs, x, lane, stream_k):
+        """the layer sequence on one half of the batch; scratch per lane, outputs into the lane's half of `y` / `head`"""
+        hn = x.shape[0]
+        sl = slice(lane * hn, (lane + 1) * hn)
+        for b, (w1, w2, w3, sb, bb) in enumerate(blocks):
+            t1, t2 = bufs["t1_%d" % lane], bufs["t2_%d" % lane]
+            y = bufs["y%d" % (b & 1)][sl]
+            ops.conv_gemm(x, w1, t1, scale=sb[0], bias=bb[0], relu=True, block_n=128, stream_k=stream_k)
+            ops.conv_gemm(t1, w2, t2, taps=(3, 3), pad=1, scale=sb[1], bias=bb[1], relu=True, block_n=64, stream_k=stream_k)
+            ops.conv_gemm(t2, w3, y, scale=sb[2], bias=bb[2], residual=x, relu=True, block_n=128, stream_k=0)
+            x = y
+        ops.conv_gemm(x, wh, bufs["head"][sl], cout=60, block_n=64, stream_k=stream_k)
+
+    def mkbufs():
+        d = {}
+        for lane in range(2):
+            d["t1_%d" % lane] = torch.full((n // 2, h, w, mid), float("nan"), device=cuda_dev, dtype=torch.float16)
+            d["t2_%d" % lane] = torch.full((n // 2, h, w, mid), float("nan"), device=cuda_dev, dtype=torch.float16)
+        for b in range(2):
+            d["y%d" % b] = torch.full((n, h, w, c), float("nan"), device=cuda_dev, dtype=torch.float16)
+        d["head"] = torch.full((n, h, w, 60), float("nan"), device=cuda_dev)
+        return d
+
+    for sk in (0, 1):
+        ref = mkbufs()
+        for lane in range(2):
+            run(ref, x0[lane * 2:(lane + 1) * 2], lane, sk)
+        torch.cuda.synchronize()
+        got = mkbufs()
+        cache = {}
+        for rep in range(4):
+            with ops.chain(cache, "k", cuda_dev, interleave=True) as ch:
+                run(got, x0[0:2], 0, sk)
+                ch.next_lane()
+                run(got, x0[2:4], 1, sk)
+        torch.cuda.synchronize()
+        assert len(cache) == 1 and cache["k"].n == 26 and cache["k"].depth == 2
+        for name in ("y1", "head"):
+            assert torch.isfinite(got[name].float()).all()
+            assert torch.equal(got[name], ref[name]), (sk, name, (got[name].float() - ref[name].float()).abs().max())
+
+
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
 def test_strided_conv_leaky_and_transposed_conv(cuda_dev, dtype):
     """the generalisations FlowNetS needs (backbone/flownet.py): stride-2 k x k convolutions through TMA element

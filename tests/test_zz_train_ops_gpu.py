@@ -344,7 +344,7 @@ def test_two_key_frames_per_call_on_device(cuda_dev):
     step_batched calls on the CPU stand-ins) on the device: a different batch size moves the stream-K split points of the
     tcgen05 GEMMs, so the comparison with two single-frame steps is statistical (the fp16 re-association noise bound of
     the frame-parallel test); the window / global rings, which are plain copies of identical payload rows up to that
-    noise, must stay close as well. Not run on a GPU yet when written (round 1 ended)."""
+    noise, must stay close as well."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from mega_core.b200 import engine, synth
     from test_engine_gpu import _match_rows
@@ -376,4 +376,22 @@ def test_two_key_frames_per_call_on_device(cuda_dev):
         worst = max(worst, torch.quantile(diff.flatten(), 0.99).item())
         assert abs(int(d0.count.item()) - outs[0][1]) <= 3 and abs(int(d1.count.item()) - outs[1][1]) <= 3
     assert worst < 2e-2, worst
-    assert (a.win_x.float() - b.win_x.float()).abs().max().item() < 0.25
+    # the window rings hold the same frames in the same slots; inside a slot a flipped near-tie of the RPN's NMS shifts the
+    # rows behind it, so rows are matched by box (like the logits above), not by position (first B200 run: one swapped
+    # proposal put a different row at the same position and the positional comparison failed)
+    KP = a.KP
+    ring_worst, matched = 0.0, []
+    for slot in range(a.L):
+        ba, bb = a.win_boxes[slot * KP:(slot + 1) * KP].cpu(), b.win_boxes[slot * KP:(slot + 1) * KP].cpu()
+        ka, kb = int(a.win_cnt[slot, 0].item()), int(b.win_cnt[slot, 0].item())
+        assert abs(ka - kb) <= 3, (slot, ka, kb)
+        idx = _match_rows(bb[:kb], ba[:ka])
+        m = idx >= 0
+        matched.append(m.float().mean().item())
+        xa = a.win_x[slot * KP:slot * KP + ka].float().cpu()[m]
+        xb = b.win_x[slot * KP:slot * KP + kb].float().cpu()[idx[m]]
+        ring_worst = max(ring_worst, torch.quantile((xa - xb).abs().flatten()[:4_000_000], 0.999).item())
+    assert min(matched) >= 0.95, matched
+    assert ring_worst < 2e-2, ring_worst
+    # global pool (75 rows per frame, no boxes kept): a swap inside the first 75 proposals shifts a few rows of one frame
+    assert ((a.glob_x.float() - b.glob_x.float()).abs() > 0.05).float().mean().item() < 0.05
