@@ -98,7 +98,7 @@ def parse():
     return ap.parse_args()
 
 
-DEFAULT_FPS = 1
+DEFAULT_FPS = 4      # key frames per step at N = 1 (the per-frame branch of 4 key frames = one batch of 8 images)
 
 
 def peaks():

@@ -125,9 +125,11 @@ int mega_conv_chain_launch2(const void* plan_device, int n_layers, int grid, voi
 /* diagnostics: following chain launches record (tag, SM clock) events of CTA `cta` into trace_dev
  * ([3 roles][4096][2] uint64, zeroed by the caller); NULL switches tracing off (tools/trace_chain.py) */
 int mega_conv_chain_set_trace(void* trace_dev, int cta);
+/* level 1: per-layer events only, so that a 100-layer chain fits the buffer (tools/trace_backbone.py) */
+int mega_conv_chain_set_trace2(void* trace_dev, int cta, int level);
 /* 3xTF32 (precision 1): the tensor core adds into its fp32 TMEM accumulator with truncation, a bias that grows with
  * the number of MMAs accumulated; the kernel restarts the accumulator every `k_blocks` k-blocks (12 MMAs each) and folds
- * the segments into a master accumulator with round-to-nearest adds. 1..64, default 4; returns the previous value. */
+ * the segments into a master accumulator with round-to-nearest adds. 1..64, default 2; returns the previous value. */
 int mega_set_split3_seg_len(int k_blocks);
 /* TMA fp32->tf32 conversion on load (round-to-nearest) on/off; returns the previous value. */
 int mega_set_tf32_rounding(int enable);

@@ -6,7 +6,7 @@
 // the math: launch, barrier/TMEM set-up, descriptor fetch, pipeline fill and drain (measured 17-30 us per layer,
 // profiles/r01_ncu_full_conv_gemm_f16_res4_raw.csv: tensor pipe active 4-10 % of the kernel's duration).
 //
-// Here the per-layer kernel body (TMA producer warp / tcgen05 MMA warp / 4 epilogue warps, double-buffered TMEM
+// Here the per-layer kernel body (TMA producer warp / tcgen05 MMA warp / 8 epilogue warps, double-buffered TMEM
 // accumulators, persistent stream-K work list -- see conv_gemm_kernel.cuh) is wrapped in a loop over a device-side
 // table of layers. One CTA per SM stays resident for the whole chain; mbarriers, the TMEM allocation and the smem
 // ring are set up once; layers are separated by a grid-wide barrier (one atomic counter, release/acquire) instead of
@@ -43,7 +43,9 @@ struct alignas(128) ChainLayer {
   int block_n;
   int out16;
   int active_ctas;   // CTAs that take part in this layer's work list (<= grid); the others only pass the barrier
-  int reserved;
+  int cta_rot;       // physical CTA (cta_rot + i) % grid plays logical CTA i of this layer's work list (depth-2 chains:
+                     // the work lists of consecutive layers start where the previous one ended, so a layer whose tile
+                     // count is not a multiple of the grid does not leave the same SMs idle every time)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -82,13 +84,17 @@ struct PipeState {
 struct ChainTrace {
   unsigned long long* buf;   // [3 roles][kTraceCap][2] or NULL
   int cta;
+  int level;                 // 0: every event; 1: per-layer events only (a 100-layer chain fits the buffer)
 };
 constexpr int kTraceCap = 4096;
 struct TraceCursor {
   unsigned long long* p;
   int n;
+  int level;
   __device__ __forceinline__ void put(unsigned long long tag) {
     if (p != nullptr && n < kTraceCap) {
+      const unsigned code = static_cast<unsigned>(tag & 0xff);
+      if (level == 1 && code >= 3 && code <= 7) return;      // per-k-block / per-tile events
       p[2 * n] = tag;
       p[2 * n + 1] = static_cast<unsigned long long>(clock64());
       ++n;
@@ -99,29 +105,137 @@ __device__ __forceinline__ TraceCursor trace_cursor(const ChainTrace& tr, int ro
   TraceCursor c;
   c.p = (tr.buf != nullptr && cta == tr.cta) ? tr.buf + static_cast<long long>(role) * kTraceCap * 2 : nullptr;
   c.n = 0;
+  c.level = tr.level;
   return c;
 }
 #define TR_TAG(layer, idx, code) ((static_cast<unsigned long long>(layer) << 32) | (static_cast<unsigned long long>(idx) << 8) | (code))
 
-// ------------------------------------------------------------------ epilogue of one layer (4 warps)
+// ------------------------------------------------------------------ epilogue of one layer (8 warps)
+// Eight epilogue warps: warp w reads TMEM lane quarter (w & 3) (the hardware restriction: a warp touches lanes
+// 32*(warp_id % 4) .. +31), and of the tile's 64-column (fp16 out) / 32-column (fp32 out) chunks it takes those with
+// chunk % 2 == (w - 2) / 4. Round 1 ran 4 warps over all chunks with ~300 executed instructions per 32 columns (generic
+// LD / ST to the staging buffers, per-element branches on the layer's flags, FMUL + FMNMX for every ReLU): 4.1 us per
+// 128 x 128 tile with a residual against 1.2 us of MMAs for K = 256 (tools/trace_backbone.py), which made every
+// 1x1-expand layer of the backbone epilogue-bound. Here the flags are template parameters of the inner loop, staging
+// goes through explicit ld/st.shared with precomputed swizzled offsets, and two warps share a lane quarter.
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kChainThreads = 64 + kEpiThreads;
+
+__device__ __forceinline__ void epi_bar_sync_all() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 32 accumulator columns (one thread = one output pixel) -> scale / bias -> (+ residual) -> activation -> staging row.
+// sb: shared address of scale[col0 ..] (bias at +512 bytes); dst / rsrc: shared addresses of this lane's 128-byte staging
+// rows; off[g]: byte offset of 16-byte group g inside the swizzled row. H: which 32-column half of a 64-half row (OUT16).
+template <bool OUT16, bool RES, int RELU>
+__device__ __forceinline__ void epi_half(const uint32_t (&raw)[32], uint32_t sb, uint32_t dst, uint32_t rsrc,
+                                         const uint32_t (&off)[8], const int H) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const uint4 sc = lds128(sb + j * 4), bi = lds128(sb + 512 + j * 4);
+    v[j] = fmaf(__uint_as_float(raw[j]), __uint_as_float(sc.x), __uint_as_float(bi.x));
+    v[j + 1] = fmaf(__uint_as_float(raw[j + 1]), __uint_as_float(sc.y), __uint_as_float(bi.y));
+    v[j + 2] = fmaf(__uint_as_float(raw[j + 2]), __uint_as_float(sc.z), __uint_as_float(bi.z));
+    v[j + 3] = fmaf(__uint_as_float(raw[j + 3]), __uint_as_float(sc.w), __uint_as_float(bi.w));
+  }
+  if (OUT16) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {          // 8 halves = 16 bytes per group
+      const int j = g * 8;
+      if (RES) {
+        const uint4 rr = lds128(rsrc + off[H * 4 + g]);
+        const float2 r0 = h2_to_f2(rr.x), r1 = h2_to_f2(rr.y), r2 = h2_to_f2(rr.z), r3 = h2_to_f2(rr.w);
+        v[j] += r0.x; v[j + 1] += r0.y; v[j + 2] += r1.x; v[j + 3] += r1.y;
+        v[j + 4] += r2.x; v[j + 5] += r2.y; v[j + 6] += r3.x; v[j + 7] += r3.y;
+      }
+      if (RELU == 1) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j + e] = fmaxf(v[j + e], 0.f);
+      } else if (RELU == 2) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[j + e] = fmaxf(v[j + e], 0.1f * v[j + e]);
+      }
+      uint4 o;
+      o.x = f2_to_h2(v[j], v[j + 1]); o.y = f2_to_h2(v[j + 2], v[j + 3]);
+      o.z = f2_to_h2(v[j + 4], v[j + 5]); o.w = f2_to_h2(v[j + 6], v[j + 7]);
+      sts128(dst + off[H * 4 + g], o);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {          // 4 floats = 16 bytes per group
+      const int j = g * 4;
+      if (RES) {
+        const uint4 rr = lds128(rsrc + off[g]);
+        v[j] += __uint_as_float(rr.x); v[j + 1] += __uint_as_float(rr.y);
+        v[j + 2] += __uint_as_float(rr.z); v[j + 3] += __uint_as_float(rr.w);
+      }
+      if (RELU == 1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[j + e] = fmaxf(v[j + e], 0.f);
+      } else if (RELU == 2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[j + e] = fmaxf(v[j + e], 0.1f * v[j + e]);
+      }
+      uint4 o;
+      o.x = __float_as_uint(v[j]); o.y = __float_as_uint(v[j + 1]); o.z = __float_as_uint(v[j + 2]); o.w = __float_as_uint(v[j + 3]);
+      sts128(dst + off[g], o);
+    }
+  }
+}
+
 template <bool OUT16>
-__device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const ConvGemmParams& p, const int BN, uint8_t* smem,
-                                                     uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint64_t* res_bar,
-                                                     int* epi_flag, uint32_t tmem_base, int warp, int lane, int cta,
-                                                     int grid, int& item, uint32_t& rphase, TraceCursor& tr, int layer) {
-  constexpr int CW = OUT16 ? 64 : 32;
-  const int q = warp & 3;
+__device__ __forceinline__ void epi_half_dispatch(const uint32_t (&raw)[32], uint32_t sb, uint32_t dst, uint32_t rsrc,
+                                                  const uint32_t (&off)[8], const int H, const bool res, const int relu) {
+  // the flags are uniform over the layer: one branch per 32 columns instead of one per element
+  if (relu == 1) {
+    if (res) epi_half<OUT16, true, 1>(raw, sb, dst, rsrc, off, H);
+    else epi_half<OUT16, false, 1>(raw, sb, dst, rsrc, off, H);
+  } else if (relu == 0) {
+    if (res) epi_half<OUT16, true, 0>(raw, sb, dst, rsrc, off, H);
+    else epi_half<OUT16, false, 0>(raw, sb, dst, rsrc, off, H);
+  } else {
+    if (res) epi_half<OUT16, true, 2>(raw, sb, dst, rsrc, off, H);
+    else epi_half<OUT16, false, 2>(raw, sb, dst, rsrc, off, H);
+  }
+}
+
+template <bool OUT16>
+__device__ __noinline__ void chain_epilogue_layer(const ChainLayer* L, const ConvGemmParams& p, const int BN, uint8_t* smem,
+                                                  uint64_t* tmem_full_bar, uint64_t* tmem_empty_bar, uint64_t* res_bar,
+                                                  int* epi_flag, uint32_t tmem_base, int warp, int lane, int cta,
+                                                  int grid, int& item, uint32_t& rphase, TraceCursor& tr, int layer) {
+  constexpr int CW = OUT16 ? 64 : 32;          // columns per chunk (= one 128-byte staging row)
+  constexpr int HPC = CW / 32;                 // 32-column halves per chunk
+  const int ew = warp - 2;                     // epilogue warp 0..7
+  const int q = warp & 3;                      // TMEM lane quarter
+  const int half = ew >> 2;                    // parity of the chunks this warp takes
   const int row = q * 32 + lane;
-  const int epi_tid = (warp - 2) * 32 + lane;
-  uint8_t* epi_out = smem + kChainStages * kChainStageBytes + (warp - 2) * 16384;
-  uint8_t* epi_res = epi_out + 8192;
-  uint64_t* rbar = res_bar + (warp - 2) * 2;
+  const int epi_tid = ew * 32 + lane;
+  const uint32_t stage_base = smem_u32(smem + kChainStages * kChainStageBytes + ew * 8192);
+  const uint32_t out_row = stage_base + lane * 128;          // 4 KB store staging | 4 KB residual staging per warp
+  const uint32_t res_row = out_row + 4096;
+  uint64_t* rbar = res_bar + ew;
+  const uint32_t sb_u32 = smem_u32(smem + kChainSbOffset);
   float* sb_s = reinterpret_cast<float*>(smem + kChainSbOffset);
   const int U = static_cast<int>(p.total_units);
   const int KB = p.kb_per_tile;
   const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
   const CUtensorMap* tmOut = &L->tmOut;
   const CUtensorMap* tmRes = &L->tmRes;
+  const bool has_res = p.has_residual != 0;
+  const int relu = p.relu;
+  uint32_t off[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) off[g] = (static_cast<uint32_t>(g) ^ static_cast<uint32_t>(lane & 7)) << 4;
   WorkIter it(p, cta, grid);
   int t;
   int kb0, kb1;
@@ -131,51 +245,53 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
     const uint32_t use = static_cast<uint32_t>(item >> 1);
     ++item;
     const bool complete = (kb0 == 0 && kb1 == KB);
-    // ---- while the MMAs of this tile run: stage its scale / bias slice in shared memory (the epilogue then reads them
-    //      with broadcast LDS instead of 32 L1-missing global loads per chunk) and start the first residual load
     const int r0 = q * 32;
     const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
     const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
     const int res_n = tc.img + tc.batch * p.res_n_off;
     const int nchunks = min(BN / CW, (p.cout - tc.n0 + CW - 1) / CW);
-    epi_bar_sync();   // every warp is done with the previous tile's scale / bias
+    // ---- while the MMAs of this tile run: stage its scale / bias slice in shared memory and start this warp's first
+    //      residual load
+    epi_bar_sync_all();   // every warp is done with the previous tile's scale / bias
     if (epi_tid < BN) {
       const int n = tc.n0 + epi_tid;
       const int zoff = tc.batch * p.bias_z_off;
       sb_s[epi_tid] = (p.scale && n < p.cout) ? __ldg(p.scale + zoff + n) : 1.f;
       sb_s[128 + epi_tid] = (p.bias && n < p.cout) ? __ldg(p.bias + zoff + n) : 0.f;
     }
-    if (complete && p.has_residual && lane == 0 && nchunks > 0) {
-      mbar_arrive_expect_tx(&rbar[0], 4096);
-      tma_load_4d(epi_res, tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
+    if (complete && has_res && lane == 0 && half < nchunks) {
+      mbar_arrive_expect_tx(rbar, 4096);
+      tma_load_4d(reinterpret_cast<void*>(smem + kChainStages * kChainStageBytes + ew * 8192 + 4096), tmRes, rbar,
+                  tc.n0 + half * CW + tc.batch * p.res_c_off, st_w, st_h, res_n);
     }
-    epi_bar_sync();
+    epi_bar_sync_all();
     mbar_wait(&tmem_full_bar[buf], use & 1);
     tc_fence_after();
     tr.put(TR_TAG(layer, tile_item, 4));
     const uint32_t tmem_row = tmem_base + buf * kChainAccStride + lane_bits;
-    auto load_acc = [&](int c32, uint32_t (&acc)[32]) {
-      __syncwarp();
-      tmem_ld_32x32(tmem_row + c32 * 32, acc);
-      tmem_ld_wait();
-    };
     bool finalize = complete;
     int c_first = cta, c_last = cta;
     if (!complete) {
+      // ---- publish this CTA's partial accumulator (each warp its own columns), then find out whether it arrived last
       float* my_ws = p.part_ws + ((static_cast<long long>(cta) * 2 + (tile_item == 0 ? 0 : 1)) * kBM + row) * BN;
+      for (int c = half; c < BN / CW; c += 2) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t acc[32];
-        load_acc(c, acc);
+        for (int h = 0; h < HPC; ++h) {
+          const int g32 = c * HPC + h;
+          uint32_t acc[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_row + g32 * 32, acc);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
-                                 __uint_as_float(acc[j + 3]));
-          __stcg(reinterpret_cast<float4*>(my_ws + c * 32 + j), v);
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(acc[j]), __uint_as_float(acc[j + 1]), __uint_as_float(acc[j + 2]),
+                                   __uint_as_float(acc[j + 3]));
+            __stcg(reinterpret_cast<float4*>(my_ws + g32 * 32 + j), v);
+          }
         }
       }
       __threadfence();
-      epi_bar_sync();
+      epi_bar_sync_all();
       c_first = unit_owner(U, grid, t * KB);
       c_last = unit_owner(U, grid, t * KB + KB - 1);
       if (epi_tid == 0) {
@@ -185,124 +301,64 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
         if (last) p.counters[t] = 0;
         *epi_flag = last;
       }
-      epi_bar_sync();
+      epi_bar_sync_all();
       finalize = (*epi_flag != 0);
       if (finalize) __threadfence();
     }
     if (finalize) {
       const int out_n = tc.img + tc.batch * p.out_n_off;
-      const bool has_sb = (p.scale != nullptr) || (p.bias != nullptr);
-      const uint32_t sw = static_cast<uint32_t>(lane & 7);
-      if (!complete && p.has_residual && lane == 0 && nchunks > 0) {   // (whole tiles started this load before the MMAs)
-        mbar_arrive_expect_tx(&rbar[0], 4096);
-        tma_load_4d(epi_res, tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
-      }
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = half; c < nchunks; c += 2) {
         const int nb = tc.n0 + c * CW;
-        const uint8_t* rsrc = nullptr;
-        if (p.has_residual) {
-          const int rb = c & 1;
-          if (c + 1 < nchunks && lane == 0) {   // prefetch the next residual chunk into the other buffer
-            mbar_arrive_expect_tx(&rbar[rb ^ 1], 4096);
-            tma_load_4d(epi_res + (rb ^ 1) * 4096, tmRes, &rbar[rb ^ 1], nb + CW + tc.batch * p.res_c_off, st_w, st_h,
-                        res_n);
+        if (has_res) {
+          if ((!complete || c != half) && lane == 0) {   // (whole tiles started their first load before the MMAs)
+            mbar_arrive_expect_tx(rbar, 4096);
+            tma_load_4d(reinterpret_cast<void*>(smem + kChainStages * kChainStageBytes + ew * 8192 + 4096), tmRes, rbar,
+                        nb + tc.batch * p.res_c_off, st_w, st_h, res_n);
           }
-          mbar_wait(&rbar[rb], (rphase >> rb) & 1u);
-          rphase ^= (1u << rb);
+          mbar_wait(rbar, (rphase >> ew) & 1u);
+          rphase ^= (1u << ew);
           tr.put(TR_TAG(layer, tile_item, 5));
-          rsrc = epi_res + rb * 4096 + lane * 128;
         }
-        // the out staging buffer (c & 1) was handed to a TMA store two chunks ago: wait until read
-        if (lane == 0) tma_store_wait_read<1>();
+        // this warp's store staging was handed to a TMA store one chunk (usually one tile) ago: wait until it was read
+        if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
-        uint8_t* dst = epi_out + (c & 1) * 4096 + lane * 128;
-        // 32 accumulator columns at a time (keeps the live registers at 32 + a handful: the 64-wide form spilled)
-      #pragma unroll
-        for (int h = 0; h < CW / 32; ++h) {
-          uint32_t raw[32];
-          load_acc(c * (CW / 32) + h, raw);
-          float acc[32];
-      #pragma unroll
-          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(raw[j]);
+#pragma unroll
+        for (int h = 0; h < HPC; ++h) {
           const int col0 = c * CW + h * 32;     // first column of this half inside the tile
+          uint32_t raw[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_row + col0, raw);
+          tmem_ld_wait();
           if (!complete) {
             // deterministic reduction: parts summed in CTA order, own part from TMEM
             float sum[32];
-      #pragma unroll
+#pragma unroll
             for (int j = 0; j < 32; ++j) sum[j] = 0.f;
             for (int oc = c_first; oc <= c_last; ++oc) {
               if (oc == cta) {
-      #pragma unroll
-                for (int j = 0; j < 32; ++j) sum[j] += acc[j];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(raw[j]);
               } else {
                 const int slot = (cta_first_unit(U, grid, oc) >= t * KB) ? 0 : 1;
                 const float* ws = p.part_ws + ((static_cast<long long>(oc) * 2 + slot) * kBM + row) * BN + col0;
-      #pragma unroll
+#pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                   const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + j));
                   sum[j] += v.x; sum[j + 1] += v.y; sum[j + 2] += v.z; sum[j + 3] += v.w;
                 }
               }
             }
-      #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = sum[j];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(sum[j]);
           }
-          if (has_sb) {
-            const float4* scv = reinterpret_cast<const float4*>(sb_s + col0);
-            const float4* biv = reinterpret_cast<const float4*>(sb_s + 128 + col0);
-      #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 sc = scv[j >> 2], bi = biv[j >> 2];
-              acc[j] = fmaf(acc[j], sc.x, bi.x); acc[j + 1] = fmaf(acc[j + 1], sc.y, bi.y);
-              acc[j + 2] = fmaf(acc[j + 2], sc.z, bi.z); acc[j + 3] = fmaf(acc[j + 3], sc.w, bi.w);
-            }
-          }
-          const float slope = p.relu == 2 ? 0.1f : 0.f;
-          if (OUT16) {
-            // 64 halves per staging row: 16-byte groups of 8 halves, swizzled like the TMA box
-      #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const uint32_t chunk = (static_cast<uint32_t>((h * 32 + j) >> 3) ^ sw) << 4;
-              float v[8];
-      #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = acc[j + e];
-              if (rsrc) {
-                const uint4 rr = *reinterpret_cast<const uint4*>(rsrc + chunk);
-                const float2 r0v = h2_to_f2(rr.x), r1v = h2_to_f2(rr.y), r2v = h2_to_f2(rr.z), r3v = h2_to_f2(rr.w);
-                v[0] += r0v.x; v[1] += r0v.y; v[2] += r1v.x; v[3] += r1v.y;
-                v[4] += r2v.x; v[5] += r2v.y; v[6] += r3v.x; v[7] += r3v.y;
-              }
-              if (p.relu) {
-      #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], slope * v[e]);
-              }
-              uint4 o;
-              o.x = f2_to_h2(v[0], v[1]); o.y = f2_to_h2(v[2], v[3]);
-              o.z = f2_to_h2(v[4], v[5]); o.w = f2_to_h2(v[6], v[7]);
-              *reinterpret_cast<uint4*>(dst + chunk) = o;
-            }
-          } else {
-      #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 v = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-              const uint32_t chunk = (static_cast<uint32_t>(j >> 2) ^ sw) << 4;
-              if (rsrc) {
-                const float4 rr = *reinterpret_cast<const float4*>(rsrc + chunk);
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-              }
-              if (p.relu) {
-                v.x = fmaxf(v.x, slope * v.x); v.y = fmaxf(v.y, slope * v.y);
-                v.z = fmaxf(v.z, slope * v.z); v.w = fmaxf(v.w, slope * v.w);
-              }
-              *reinterpret_cast<float4*>(dst + chunk) = v;
-            }
-          }
+          epi_half_dispatch<OUT16>(raw, sb_u32 + col0 * 4, out_row, res_row, off, h, has_res, relu);
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(tmOut, epi_out + (c & 1) * 4096, nb + tc.batch * p.out_c_off, st_w, st_h, out_n);
+          tma_store_4d(tmOut, smem + kChainStages * kChainStageBytes + ew * 8192, nb + tc.batch * p.out_c_off, st_w, st_h,
+                       out_n);
           tma_store_commit();
         }
       }
@@ -314,16 +370,18 @@ __device__ __forceinline__ void chain_epilogue_layer(const ChainLayer* L, const 
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kChainThreads, 1)
 conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, unsigned* sync, const ChainTrace trace,
                   const int depth) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment (the 128B swizzle pattern is a function of the absolute address) as an OFFSET into the shared
+  // array, so that the compiler keeps the shared address space (ld/st.shared instead of generic accesses)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kChainBarOffset);
   uint64_t* empty_bar = full_bar + kChainStages;
   uint64_t* tmem_full_bar = empty_bar + kChainStages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2]
-  uint64_t* res_bar = tmem_empty_bar + 2;               // [4 warps][2]
+  uint64_t* res_bar = tmem_empty_bar + 2;               // [8 epilogue warps]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
   int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
@@ -339,9 +397,9 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);
+      mbar_init(&tmem_empty_bar[b], kEpiWarps);
     }
-    for (int b = 0; b < 8; ++b) mbar_init(&res_bar[b], 1);
+    for (int b = 0; b < kEpiWarps; ++b) mbar_init(&res_bar[b], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, kChainTmemCols);
@@ -378,8 +436,10 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         // layer l may read what layers <= l - depth wrote: all CTAs have arrived l / depth times at counter l % depth
         if (l >= depth) grid_wait(sync + (l % depth), static_cast<unsigned>(l / depth) * grid);
         tr.put(TR_TAG(l, 0, 2));
-        if (cta >= act) continue;
-        WorkIter it(p, cta, act);
+        int lc = cta - L->cta_rot;
+        if (lc < 0) lc += grid;
+        if (lc >= act) continue;
+        WorkIter it(p, lc, act);
         int t;
         int kb0, kb1;
         while (it.next(t, kb0, kb1)) {
@@ -428,9 +488,11 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
         const ConvGemmParams p = L->p;
         const int BN = L->block_n;
         const int act = L->active_ctas;
-        if (cta >= act) continue;
+        int lc = cta - L->cta_rot;
+        if (lc < 0) lc += grid;
+        if (lc >= act) continue;
         const uint32_t idesc = umma_idesc<0>(kBM, BN);
-        WorkIter it(p, cta, act);
+        WorkIter it(p, lc, act);
         int t;
         int kb0, kb1;
         while (it.next(t, kb0, kb1)) {
@@ -460,7 +522,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int epi_tid = (warp - 2) * 32 + lane;
     int item = 0;
     uint32_t rphase = 0;
@@ -476,18 +538,20 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
       // (one poller per CTA; the named barrier passes the acquired state on to the other epilogue threads)
       if (l >= depth) {
         if (epi_tid == 0) grid_wait(sync + (l % depth), static_cast<unsigned>(l / depth) * grid);
-        epi_bar_sync();
+        epi_bar_sync_all();
         fence_proxy_async_all();
       }
       const ConvGemmParams p = L->p;
       const int act = L->active_ctas;
-      if (cta < act) {
+      int lc = cta - L->cta_rot;
+      if (lc < 0) lc += grid;
+      if (lc < act) {
         if (L->out16) {
           chain_epilogue_layer<true>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
-                                     warp, lane, cta, act, item, rphase, tr, l);
+                                     warp, lane, lc, act, item, rphase, tr, l);
         } else {
           chain_epilogue_layer<false>(L, p, L->block_n, smem, tmem_full_bar, tmem_empty_bar, res_bar, epi_flag, tmem_base,
-                                      warp, lane, cta, act, item, rphase, tr, l);
+                                      warp, lane, lc, act, item, rphase, tr, l);
         }
       }
       tr.put(TR_TAG(l, 0, 8));
@@ -496,7 +560,7 @@ conv_chain_kernel(const ChainLayer* __restrict__ layers, const int n_layers, uns
       //  wait_group; the named barrier orders all of that before thread 0's single gpu-scope release)
       if (lane == 0) tma_store_wait<0>();
       tr.put(TR_TAG(l, 0, 9));
-      epi_bar_sync();
+      epi_bar_sync_all();
       if (epi_tid == 0) {
         fence_proxy_async_all();
         __threadfence();
@@ -554,7 +618,7 @@ extern "C" int mega_conv_chain_encode2(const mega_conv_gemm_desc* descs, int n_l
     L->block_n = d->block_n;
     L->out16 = d->out_f16 ? 1 : 0;
     L->active_ctas = ctas;
-    L->reserved = 0;
+    L->cta_rot = 0;
     if (ctas > grid) grid = ctas;
     if (depth == 2) {
       // two layers are in flight: odd layers take the second half of the tile counters and of the partial-sum area
@@ -567,6 +631,18 @@ extern "C" int mega_conv_chain_encode2(const mega_conv_gemm_desc* descs, int n_l
       }
     }
   }
+  if (depth == 2) {
+    // rolling work lists: layer l starts at the physical CTA where layer l-1's list ended
+    long long start = 0;
+    for (int l = 0; l < n_layers; ++l) {
+      out[l].cta_rot = static_cast<int>(start % grid);
+      // whole-tile layers occupy min(tiles, ctas) CTAs for (about) one tile time each; advance by the tiles of the last,
+      // partial wave so that the next layer begins on the CTAs this one leaves idle
+      const long long tiles = out[l].p.total_tiles;
+      const int act = out[l].active_ctas;
+      start += out[l].p.stream_k ? act : (tiles % act == 0 ? act : tiles % act);
+    }
+  }
   if (grid_out) *grid_out = grid;
   return MEGA_OK;
 }
@@ -576,13 +652,22 @@ extern "C" int mega_conv_chain_encode(const mega_conv_gemm_desc* descs, int n_la
   return mega_conv_chain_encode2(descs, n_layers, plan_host, plan_bytes, grid_out, 1);
 }
 
-static ChainTrace g_chain_trace = {nullptr, 0};
+static ChainTrace g_chain_trace = {nullptr, 0, 0};
 
 /* diagnostics: the next launches record an in-kernel event trace of CTA `cta` into trace_dev
  * (3 * 4096 * 2 uint64, zero it first); trace_dev == NULL switches tracing off */
 extern "C" int mega_conv_chain_set_trace(void* trace_dev, int cta) {
   g_chain_trace.buf = static_cast<unsigned long long*>(trace_dev);
   g_chain_trace.cta = cta;
+  g_chain_trace.level = 0;
+  return MEGA_OK;
+}
+
+/* level 1: only the per-layer events (layer begin / barrier passed / tiles done / stores drained / arrived) */
+extern "C" int mega_conv_chain_set_trace2(void* trace_dev, int cta, int level) {
+  g_chain_trace.buf = static_cast<unsigned long long*>(trace_dev);
+  g_chain_trace.cta = cta;
+  g_chain_trace.level = level;
   return MEGA_OK;
 }
 
@@ -600,7 +685,7 @@ extern "C" int mega_conv_chain_launch2(const void* plan_device, int n_layers, in
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(grid), 1, 1);
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(kChainThreads, 1, 1);
   cfg.dynamicSmemBytes = kChainSmem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

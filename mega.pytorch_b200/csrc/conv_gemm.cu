@@ -41,7 +41,7 @@ static EncodeTiledFn get_encode_fn() {
 static int g_tf32_round = 1;  // TMA converts fp32 -> tf32 (round to nearest) while loading
 
 static int g_num_sms = 0;
-static int g_seg_len = 4;      // 3xTF32: k-blocks per accumulator segment
+static int g_seg_len = 2;      // 3xTF32: k-blocks per accumulator segment
 constexpr int kCounterSlots = 65536;   // ints at the head of the workspace
 constexpr int kMinUnits = 4;
 

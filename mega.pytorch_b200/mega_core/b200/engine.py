@@ -281,7 +281,7 @@ class Backbone:
         p = self._buf("pool", (n, hp, wp, 64))
         ops.maxpool3x3s2(s, p)
         chained = self.dtype == torch.float16
-        dual = chained and ops.DUAL_CHAIN[0] and n >= 2 and n % 2 == 0
+        dual = chained and ops.DUAL_CHAIN[0] and n >= ops.DUAL_MIN_IMAGES and n % 2 == 0
         with ops.chain(self._chains, ("body", tuple(p.shape), tail is not None, dual), self.dev, enabled=chained,
                        interleave=dual) as ch:
             if dual and ch.interleave:
@@ -583,7 +583,7 @@ class WindowedEngine(HeadCommon):
                 ops.WS_LANE[0] = 0
         side_ctas = max(4, n)       # the proposal selection runs one latency-bound CTA per image beside the res5 chain
         mc = 148 - side_ctas
-        dual = self.chained and ops.DUAL_CHAIN[0] and n >= 2 and n % 2 == 0
+        dual = self.chained and ops.DUAL_CHAIN[0] and n >= ops.DUAL_MIN_IMAGES and n % 2 == 0
         with ops.chain(self._chains, ("res5", tuple(feats.shape), dual), self.dev, enabled=self.chained, max_ctas=mc,
                        interleave=dual) as ch:
             if dual and ch.interleave:
@@ -601,6 +601,42 @@ class WindowedEngine(HeadCommon):
         x = self.fc0_out[:rows]
         self._fc0(pooled, x)
         return x, boxes, cnt, spans
+
+    # ---- the reference's sub-module calls (model.backbone / model.rpn / feature_extractor(pre_calculate=True),
+    #      generalized_rcnn_mega.py:145-158) served piecewise, for callers that drive the parts themselves
+    def to_nhwc(self, feats_nchw):
+        """reference layout [n,C,h,w] fp32 -> the engine's NHWC activation dtype"""
+        return feats_nchw.permute(0, 2, 3, 1).contiguous().to(self.act)
+
+    @_with_precision
+    def backbone_nchw(self, imgs):
+        """ResNet.forward (resnet.py:145-152): [n,3,H,W] -> [n,1024,H/16,W/16] fp32 in the reference's layout"""
+        return self.backbone.forward(imgs).permute(0, 3, 1, 2).float().contiguous()
+
+    @_with_precision
+    def rpn_nchw(self, feats_nchw, im_w, im_h, post):
+        """RPNModule.forward in eval mode (rpn.py:213-243): -> (boxes [n,post,4], objectness [n,post], count [n])"""
+        boxes, scores, cnt = self.rpn(self.to_nhwc(feats_nchw), im_w, im_h, post)
+        return boxes.clone(), scores.clone(), cnt.clone()
+
+    @_with_precision
+    def roi_features(self, feats_nchw, boxes, batch_idx=None):
+        """feature_extractor(x, proposals, pre_calculate=True) (extractors :885-896): res5 on the map, ROIAlign of the
+        given boxes [K,4] (image index per box in batch_idx, int32), fcs[0] + ReLU -> [K, 1024] fp32"""
+        c = self.cfg
+        k = boxes.shape[0]
+        assert k <= self.pooled.shape[0], "at most %d rois per call" % self.pooled.shape[0]
+        feats = self.to_nhwc(feats_nchw)
+        with ops.chain(self._chains, ("res5x", tuple(feats.shape)), self.dev, enabled=self.chained):
+            r5 = self.res5.forward(feats)
+        rb = self.roi_boxes[:k]
+        rb.copy_(boxes)
+        pooled = self.pooled[:k]
+        ops.roi_align_nhwc(r5, rb, batch_idx, c.pooler_scale, c.pooler_resolution, c.pooler_resolution, c.sampling_ratio,
+                           pooled)
+        x = self.fc0_out[:k]
+        self._fc0(pooled, x)
+        return x.float().clone()
 
     @staticmethod
     def pack_fc0(w_rows):
@@ -757,6 +793,21 @@ class MegaEngine(WindowedEngine, WavefrontMixin):
         self.glob_pushed = 0
         self.mem_pushed = 0
         self.frames = 0
+
+    # ---- MEGAFeatureExtractor.init_memory / init_global / update_global (extractors :657-676) on the engine's rings
+    def init_memory(self):
+        self.mem_pushed = 0
+
+    def init_global(self):
+        self.glob_pushed = 0
+
+    def update_global(self, feats):
+        """push one global frame's [75, 1024] rows (what feature_extractor(..., pre_calculate=True) returned)"""
+        R = self.R
+        assert tuple(feats.shape) == (R, self.feat_dim), feats.shape
+        g = self.glob_pushed % self.GF
+        self.glob_x[g * R:(g + 1) * R].copy_(feats.to(self.dev))
+        self.glob_pushed += 1
 
     def _tab(self, name):
         o, n = self._tab_off[name]

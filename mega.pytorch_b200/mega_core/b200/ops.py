@@ -155,7 +155,11 @@ class chain(object):
 
 # interleaved (depth-2) chains for the per-frame branch when the image batch splits into two halves
 import os as _os
+# Measured on a B200 (backbone chain, fp16, 600x1000; ms for 2 / 4 / 8 images): one chain 1.61 / 2.49 / 4.06, two
+# interleaved lanes 1.87 / 2.33 / 3.75 -- lanes of a single image leave too few tiles per layer, so the engine interleaves
+# from 4 images on (DUAL_MIN_IMAGES); MEGA_B200_DUAL_CHAIN=0 switches it off
 DUAL_CHAIN = [_os.environ.get("MEGA_B200_DUAL_CHAIN", "1") != "0"]
+DUAL_MIN_IMAGES = 4
 
 # programmatic dependent launch of the GEMM kernels (prologue overlapped with the previous kernel's tail)
 PDL = [True]

@@ -29,6 +29,9 @@ class _EngineBacked(nn.Module):
         self.backbone = build_backbone(cfg)
         self.rpn = build_rpn(cfg, self.backbone.out_channels)
         self.roi_heads = build_roi_heads(cfg, self.backbone.out_channels)
+        for sub in (self.backbone, self.rpn, self.roi_heads["box"].feature_extractor):
+            if hasattr(sub, "_bind"):        # callable sub-modules (model.rpn(...), feature_extractor(..., pre_calculate=True))
+                sub._bind(self)
         self._engine = None
         self._sd_override = None
         self.d2h_bytes_per_frame = 0

@@ -8,6 +8,7 @@ l_Wqs, l_Wks, l_Wvs, l_us, g_Wqs, g_Wks, g_Wvs, g_us}, roi_heads.box.predictor.{
 only HOLD the tensors; all arithmetic runs in the B200 engine (mega_core/b200/engine.py).
 """
 import os
+import weakref
 
 import torch
 from torch import nn
@@ -17,6 +18,33 @@ from ..layers import Conv2d, FrozenBatchNorm2d
 from ..b200 import engine as _engine
 
 BLOCKS = {"R-50-C4": (3, 4, 6), "R-101-C4": (3, 4, 23)}
+
+
+class _EngineServed(object):
+    """mix-in of the sub-modules a caller of the reference may invoke on its own (model.backbone, model.rpn,
+    model.roi_heads.box.feature_extractor): their forward() runs on the detector's engine. The detector registers
+    itself with `_bind` (a weak reference: the parent must not become a sub-module of its child)."""
+
+    def _bind(self, detector):
+        object.__setattr__(self, "_detector_ref", weakref.ref(detector))
+
+    @property
+    def _engine(self):
+        ref = getattr(self, "_detector_ref", None)
+        det = ref() if ref is not None else None
+        if det is None:
+            raise RuntimeError("this sub-module computes through its detector's B200 engine; build it with "
+                               "build_detection_model(cfg)")
+        return det.engine
+
+
+def _image_size(images):
+    """(w, h) of the first image of an ImageList / tensor, as AnchorGenerator reads it (anchor_generator.py:112-125)"""
+    if hasattr(images, "image_sizes"):
+        h, w = images.image_sizes[0]
+        return int(w), int(h)
+    t = images.tensors if hasattr(images, "tensors") else images
+    return int(t.shape[-1]), int(t.shape[-2])
 
 
 class Bottleneck(nn.Module):
@@ -69,10 +97,23 @@ class ResNetHead(nn.Module):
         self.out_channels = 2048
 
 
+class _Backbone(nn.Sequential, _EngineServed):
+    """`model.backbone` = Sequential(body) (backbone/backbone.py:16-20); forward(x [n,3,H,W]) -> [feats [n,1024,H/16,W/16]]
+    like ResNet.forward (resnet.py:145-152), computed by the detector's engine"""
+
+    def forward(self, x):
+        if self.training:
+            raise NotImplementedError("the B200 build covers inference (eval mode) only")
+        x = x.tensors if hasattr(x, "tensors") else x
+        eng = self._engine
+        with torch.no_grad():
+            return [eng.backbone_nchw(x.to(eng.dev).float().contiguous())]
+
+
 @registry.BACKBONES.register("R-50-C4")
 @registry.BACKBONES.register("R-101-C4")
 def build_resnet_backbone(cfg):
-    model = nn.Sequential()
+    model = _Backbone()
     model.add_module("body", ResNetBody(cfg.MODEL.BACKBONE.CONV_BODY))
     model.out_channels = cfg.MODEL.RESNETS.BACKBONE_OUT_CHANNELS
     return model
@@ -104,7 +145,7 @@ class RPNHead(nn.Module):
         self.bbox_pred = nn.Conv2d(in_channels, num_anchors * 4, 1)
 
 
-class RPNModule(nn.Module):
+class RPNModule(nn.Module, _EngineServed):
     """`model.rpn` (rpn/rpn.py:109-243): holds head + anchors; forward() is served by the detector's engine"""
 
     def __init__(self, cfg, in_channels):
@@ -112,6 +153,25 @@ class RPNModule(nn.Module):
         r = cfg.MODEL.RPN
         self.anchor_generator = AnchorGenerator(r.ANCHOR_SIZES, r.ASPECT_RATIOS, r.ANCHOR_STRIDE[0])
         self.head = registry.RPN_HEADS[r.RPN_HEAD](cfg, in_channels, self.anchor_generator.num_anchors_per_location()[0])
+
+    def forward(self, images, features, targets=None, version="key"):
+        """RPNWithRefModule.forward in eval mode (rpn/rpn.py:213-243): `features` = (feats [n,1024,h,w],) as
+        model.backbone returns them; version "key" -> POST_NMS_TOP_N_TEST proposals, "ref" -> REF_POST_NMS_TOP_N.
+        Returns list[BoxList] with the field `objectness` (rpn/inference.py:118-123), one per image."""
+        if self.training:
+            raise NotImplementedError("the B200 build covers inference (eval mode) only")
+        from ..structures.bounding_box import BoxList
+        eng = self._engine
+        im_w, im_h = _image_size(images)
+        post = eng.cfg.post_nms_top_n if version == "key" else eng.cfg.ref_post_nms_top_n
+        with torch.no_grad():
+            boxes, scores, cnt = eng.rpn_nchw(features[0], im_w, im_h, post)
+        out = []
+        for i, k in enumerate(cnt.tolist()):
+            bl = BoxList(boxes[i, :k], (im_w, im_h), mode="xyxy")
+            bl.add_field("objectness", scores[i, :k])
+            out.append(bl)
+        return out
 
 
 def _fc(i, o):
@@ -136,9 +196,35 @@ class ResNetConv52MLPFeatureExtractor(nn.Module):
         self.out_channels = dim
 
 
+class _WindowedExtractorForward(_EngineServed):
+    def forward(self, x, proposals, pre_calculate=False):
+        """pre_calculate=True (extractors :885-896 / :401-410): x = feats [n,1024,h,w] (model.backbone's output or a tuple
+        holding it), proposals = list[BoxList], one per image -> ROI features [sum K, 1024] after fcs[0] + ReLU.
+        The aggregation call (pre_calculate=False, extractors :898-933) reads the per-video state the DETECTOR keeps in the
+        engine's ring buffers; it is served through model(images) only."""
+        if not pre_calculate:
+            raise NotImplementedError("feature_extractor(x, proposals_list): the aggregation over window / global pool / "
+                                      "memory runs inside model(images) (MegaEngine.aggregate); call the detector")
+        x = x[0] if isinstance(x, (tuple, list)) else x
+        boxes = torch.cat([p.bbox for p in proposals], 0).float()
+        bidx = torch.cat([torch.full((len(p),), i, dtype=torch.int32) for i, p in enumerate(proposals)]).to(boxes.device)
+        with torch.no_grad():
+            return self._engine.roi_features(x, boxes, bidx)
+
+
 @registry.ROI_BOX_FEATURE_EXTRACTORS.register("MEGAFeatureExtractor")
-class MEGAFeatureExtractor(nn.Module):
-    """parameters of roi_box_feature_extractors.py:457-565"""
+class MEGAFeatureExtractor(_WindowedExtractorForward, nn.Module):
+    """parameters of roi_box_feature_extractors.py:457-565; forward(pre_calculate=True) / init_memory / init_global /
+    update_global (:657-676) act on the detector's engine"""
+
+    def init_memory(self):
+        self._engine.init_memory()
+
+    def init_global(self):
+        self._engine.init_global()
+
+    def update_global(self, feats):
+        self._engine.update_global(feats)
 
     def __init__(self, cfg, in_channels):
         super().__init__()
@@ -163,7 +249,7 @@ class MEGAFeatureExtractor(nn.Module):
 
 
 @registry.ROI_BOX_FEATURE_EXTRACTORS.register("RDNFeatureExtractor")
-class RDNFeatureExtractor(nn.Module):
+class RDNFeatureExtractor(_WindowedExtractorForward, nn.Module):
     """parameters of roi_box_feature_extractors.py:254-330 (fcs, Wgs, Wqs, Wks, Wvs; no `u`)"""
 
     def __init__(self, cfg, in_channels):

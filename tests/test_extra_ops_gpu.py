@@ -75,3 +75,56 @@ def test_deform_psroi_pooling(cuda_dev):
                                         1 / 16.0, od, gs, ps, ps, 4, 0.1)
         assert torch.equal(cnt.cpu(), rc)
         assert torch.allclose(out.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_callable_submodules_match_the_oracle_pieces(cuda_dev):
+    """model.backbone(x), model.rpn(images, (feats,), version=...), feature_extractor(feats, proposals, pre_calculate=True),
+    feature_extractor.init_memory / init_global / update_global -- the calls GeneralizedRCNNMEGA._forward_test makes on its
+    parts (generalized_rcnn_mega.py:145-158, :173-175, :208; rpn/rpn.py:213-243; extractors :657-676, :885-896) -- served
+    by the detector's engine, against the oracle's functions of the same steps on the same inputs."""
+    import mega_oracle as mo
+    from mega_core.b200 import synth
+    from mega_core.modeling.detector import build_detection_model_from_state_dict
+    from mega_core.structures.image_list import to_image_list
+    sd = synth.make_state_dict("mega_r101_tiny", seed=3)
+    model = build_detection_model_from_state_dict(sd, method="mega", device=cuda_dev, precision="fp32x3")
+    h, w = 96, 160
+    img = synth.synthetic_frame(2, h, w)
+    images = to_image_list(img[0])
+    feats = model.backbone(img.to(cuda_dev))[0]
+    ref_feats = mo.resnet_c4_body(img, sd)
+    assert feats.shape == ref_feats.shape and feats.dtype == torch.float32
+    assert ((feats.cpu() - ref_feats).abs().max() / ref_feats.pow(2).mean().sqrt()).item() < 1e-3
+    # proposals on the ORACLE's map (identical inputs): the key set, and the ref set as its prefix
+    dfeats = ref_feats.to(cuda_dev)
+    key = model.rpn(images, (dfeats,), version="key")
+    ref = model.rpn(images, (dfeats,), version="ref")
+    assert len(key) == 1 and len(ref) == 1 and len(ref[0]) == 75 and len(key[0]) <= 300
+    logits, deltas = mo.rpn_head(ref_feats, sd)
+    ob, osc = mo.rpn_select(logits, deltas, w, h, post_nms_top_n=300, cuda_semantics=True)[:2]
+    kb = key[0].bbox.cpu()
+    assert kb.shape == ob.shape
+    d = (kb[:, None, :] - ob[None, :, :]).abs().amax(2)            # a near-tied NMS decision may flip: match by box
+    val, idx = d.min(0)
+    m = val < 0.05
+    assert m.float().mean().item() >= 0.97, m.float().mean().item()
+    assert (key[0].get_field("objectness").cpu()[idx[m]] - osc[m]).abs().max().item() < 1e-4
+    assert torch.equal(ref[0].bbox, key[0].bbox[:75])
+    # ROI features of the ref proposals
+    fe = model.roi_heads.box.feature_extractor
+    x = fe((dfeats,), ref, pre_calculate=True)
+    r5 = mo.res5_head(ref_feats, sd, "roi_heads.box.feature_extractor.head.")
+    rois = torch.cat([torch.zeros(75, 1), ref[0].bbox.cpu()], 1)
+    pooled = mo.roi_align(r5, rois, 1.0 / 16, 7, 7, 0).flatten(1)
+    want = torch.relu(pooled @ sd["roi_heads.box.feature_extractor.l_fcs.0.weight"].t()
+                      + sd["roi_heads.box.feature_extractor.l_fcs.0.bias"])
+    assert x.shape == want.shape and ((x.cpu() - want).abs().max() / want.pow(2).mean().sqrt()).item() < 2e-3
+    # global pool: init + push lands in ring slot 0
+    fe.init_memory()
+    fe.init_global()
+    fe.update_global(x)
+    eng = model.engine
+    assert eng.glob_pushed == 1 and eng.mem_pushed == 0
+    assert torch.allclose(eng.glob_x[:75].float(), x, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        fe((dfeats,), [key[0]], pre_calculate=False)
