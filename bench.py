@@ -196,8 +196,7 @@ class MegaBench:
         self.pool_dev = [f.to(self.dev) for f in pool]
         self.pairs_dev = [torch.cat([self.pool_dev[(i + 12) % 16], self.pool_dev[(5 * i + 3) % 16]], 0) for i in range(16)]
         self.pairs_pinned = [torch.cat([pool[(i + 12) % 16], pool[(5 * i + 3) % 16]], 0).pin_memory() for i in range(16)]
-        fps = args.frames_per_step or DEFAULT_FPS
-        self.fps = fps if world == 1 else 1
+        self.fps = args.frames_per_step or DEFAULT_FPS      # N > 1: per rank (wavefront schedule), see measure()
         self.gold = None
         if not args.no_parity and os.path.exists(FIXTURE) and (self.h, self.w) == (H, W):
             self.gold = torch.load(FIXTURE)
@@ -288,21 +287,35 @@ class MegaBench:
                 wave_note = "another rank failed the self-check"
             torch.cuda.empty_cache()
 
+        if world > 1 and not wave:
+            fps = 1          # the replicated-state fallback schedule runs one key frame per rank and step
+
         def dstep(pair):
             return eng.dist_step_wave(pair, w, h) if wave else eng.dist_step(pair, w, h)[rank]
 
-        if fps > 1:
-            nb = 16 // fps
-            multi_dev = [torch.cat([pairs_dev[(fps * i + j) % 16] for j in range(fps)], 0) for i in range(nb)]
+        def pair_index(i, g):
+            """pool index of the frame pair of step i, round g on this rank (key frame (i * fps + g) * world + rank)"""
+            return ((i * fps + g) * world + rank) % 16
+
+        batches = {}
+
+        def batch_dev(i):
+            key = tuple(pair_index(i, g) for g in range(fps))
+            if key not in batches:
+                batches[key] = torch.cat([pairs_dev[k] for k in key], 0) if fps > 1 else pairs_dev[key[0]]
+            return batches[key]
 
         def step_dev(i):
+            if world > 1 and fps == 1:
+                return dstep(pairs_dev[pair_index(i, 0)])
+            batch = batch_dev(i)
             if world > 1:
-                return dstep(pairs_dev[(i * world + rank) % 16])
+                return eng.dist_stepn_wave(batch, w, h)
             if fps > 1:
-                return eng.stepn_batched(multi_dev[i % nb], w, h)
-            return eng.step_batched(pairs_dev[i % 16], w, h)
+                return eng.stepn_batched(batch, w, h)
+            return eng.step_batched(batch, w, h)
 
-        static_in = eng.static_input((2, 3, h, w))
+        static_in = eng.static_input((2 * fps, 3, h, w))
         state = {"t": t}
 
         def step_e2e():
@@ -316,8 +329,11 @@ class MegaBench:
             if world == 1:
                 # the call a user of the reference makes, followed by the .to(cpu) of engine/inference.py:43
                 return len(model(self.infos_next(t0))[0].to("cpu"))
-            static_in.copy_(pairs_pinned[(t0 * world + rank) % 16], non_blocking=True)
-            return len(dstep(static_in).to_host()[0])
+            for g in range(fps):
+                static_in[2 * g:2 * g + 2].copy_(pairs_pinned[pair_index(t0, g)], non_blocking=True)
+            if fps == 1:
+                return len(dstep(static_in).to_host()[0])
+            return sum(len(d.to_host()[0]) for d in eng.dist_stepn_wave(static_in, w, h))
 
         with torch.no_grad():
             # ---- settle: every CUDA graph of the schedule captured AND replayed, every collective size seen, before the
@@ -390,7 +406,7 @@ class MegaBench:
             dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dev_ms, e2e_ms = times[0].item(), times[1].item()
         kf = world * fps
-        res.update({"dev_ms": dev_ms, "e2e_ms": e2e_ms, "value": kf * args.steps / (dev_ms * 1e-3),
+        res.update({"fps": fps, "dev_ms": dev_ms, "e2e_ms": e2e_ms, "value": kf * args.steps / (dev_ms * 1e-3),
                     "e2e_value": kf * args.steps / (e2e_ms * 1e-3), "ms_per_step": dev_ms / args.steps,
                     "launches_per_step": launches_per_step, "h2d": h2d, "d2h": d2h,
                     "detections_per_frame": ndet / float(args.steps * fps), "wave": wave, "wave_note": wave_note,
@@ -478,8 +494,8 @@ def roofline_block(args, roof, step_ms, key_frames_per_step, precision):
             "executed_gflop_per_step": roof["exec_gflop"], "kernel_ms_per_step": roof["kernel_ms"],
             "launches_per_step": roof["launches"], "executed_tflops": roof["exec_tflops"],
             "kernel_share_of_step": roof["kernel_ms"] / step_ms if step_ms else None,
-            "whole_step": {"achieved": ALGO_GFLOP[args.arch] * key_frames_per_step / step_ms / 1e3,
-                           "frac": ALGO_GFLOP[args.arch] * key_frames_per_step / step_ms / 1e3 / pk["tflops"],
+            "whole_step": {"achieved": ALGO_GFLOP[args.arch] * key_frames_per_step / step_ms,     # GFLOP / ms = TFLOP/s
+                           "frac": ALGO_GFLOP[args.arch] * key_frames_per_step / step_ms / pk["tflops"],
                            "note": "algorithmic GFLOP of the step / device-timed ms_per_step (everything included)"}
             if step_ms else None}
 
@@ -511,7 +527,7 @@ def run_mega(args, rank, world):
         dist.broadcast(idx, src=0)
         head = modes[int(idx.item())]
     R = results[head]
-    eng, fps, kf = R["eng"], mb.fps, world * mb.fps
+    eng, fps, kf = R["eng"], R["fps"], world * R["fps"]
     clocks = mb.sampler.stop() if mb.sampler is not None else None
     # ---- roofline of the tensor-core kernels: eager steps with an event pair per launch (rank 0)
     roofs = {}
@@ -557,7 +573,8 @@ def run_mega(args, rank, world):
         "e2e": {"value": R["e2e_value"], "unit": "frames/s", "h2d_bytes_per_step": R["h2d"], "d2h_bytes_per_step": R["d2h"],
                 "ms_per_step": R["e2e_ms"] / args.steps, "detections_per_frame": R["detections_per_frame"],
                 "api": "model(images) per key frame" if fps == 1 and world == 1 else
-                       ("model.forward_frames([images] * %d)" % fps if world == 1 else "MegaEngine.dist_step* (one video stream)")},
+                       ("model.forward_frames([images] * %d)" % fps if world == 1 else
+                        "MegaEngine.dist_step%s (one video stream)" % ("n_wave" if R["fps"] > 1 else "_wave" if R["wave"] else ""))},
         "gpu_launches": int(round(R["launches_per_step"] * args.steps)),
         "parity": {"fixture": "tests/golden/mega_r101_600x1000.pt (unmodified reference, %s key frames)" % (
                        len(mb.gold["frames"]) if mb.gold else "n/a"),

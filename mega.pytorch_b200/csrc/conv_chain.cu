@@ -84,7 +84,8 @@ struct PipeState {
 struct ChainTrace {
   unsigned long long* buf;   // [3 roles][kTraceCap][2] or NULL
   int cta;
-  int level;                 // 0: every event; 1: per-layer events only (a 100-layer chain fits the buffer)
+  int level;                 // 0: every event; 1: per-layer events only (a 100-layer chain fits the buffer);
+                             // 2 + l: every event of layer l only
 };
 constexpr int kTraceCap = 4096;
 struct TraceCursor {
@@ -95,6 +96,7 @@ struct TraceCursor {
     if (p != nullptr && n < kTraceCap) {
       const unsigned code = static_cast<unsigned>(tag & 0xff);
       if (level == 1 && code >= 3 && code <= 7) return;      // per-k-block / per-tile events
+      if (level >= 2 && static_cast<int>(tag >> 32) != level - 2) return;
       p[2 * n] = tag;
       p[2 * n + 1] = static_cast<unsigned long long>(clock64());
       ++n;

@@ -185,3 +185,31 @@ class WavefrontMixin:
         from . import parallel
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         return parallel.drive(self._wave(imgs, im_w, im_h, rank, world), group)
+
+    def dist_stepn_wave(self, imgs, im_w, im_h, group=None):
+        """n wavefront rounds per call: imgs [2n,3,H,W] = this rank's (local, global) frame pairs of the key frames
+        (g * world + rank), g = 0..n-1, of a block of n * world consecutive key frames. The per-frame branch of the n pairs
+        runs as ONE batch (like stepn_batched on a single GPU), then the n rounds run in order, each a dist_step_wave on
+        its precomputed payload (4 small all-gathers). Returns the n Detections of this rank's key frames (all but the
+        last are copies)."""
+        import torch.distributed as dist
+        from . import parallel
+        from .engine import Detections
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        n = imgs.shape[0] // 2
+        assert imgs.shape[0] == 2 * n and 1 <= n <= self.MAX_FRAMES_PER_STEP, imgs.shape
+        static_in = self.static_input(tuple(imgs.shape))
+        if imgs.data_ptr() != static_in.data_ptr():
+            static_in.copy_(imgs, non_blocking=True)
+        if getattr(self, "payload_n", None) is None:
+            self.payload_n = torch.zeros(self.MAX_FRAMES_PER_STEP, self.payload_in.numel(), device=self.dev)
+        with ops.precision(self.cfg.precision):
+            self._graph_run(("refn", tuple(imgs.shape), im_w, im_h),
+                            lambda: self._ref_to_payloads(static_in, im_w, im_h, [self.payload_n[i] for i in range(n)]))
+        dets = []
+        for g in range(n):
+            det = parallel.drive(self._wave(None, im_w, im_h, rank, world, payload=self.payload_n[g]), group)
+            if g < n - 1:
+                det = Detections(det.boxes.clone(), det.scores.clone(), det.labels.clone(), det.count.clone())
+            dets.append(det)
+        return dets

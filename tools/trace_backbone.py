@@ -20,6 +20,7 @@ from mega_core.b200 import engine, ops, synth  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--fps", type=int, default=1)
 ap.add_argument("--cta", type=int, default=0)
+ap.add_argument("--layer", type=int, default=-1, help="print every event of this layer instead of the per-layer table")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 h, w = 600, 1000
@@ -39,7 +40,7 @@ with torch.no_grad():
     assert len(chains) == 1, [(c.n, c.info["layers"][0]["m"]) for c in eng.backbone._chains.values()]
     ch = chains[0]
     trace = torch.zeros(3 * 4096 * 2, dtype=torch.int64, device=dev)
-    lib.mega_conv_chain_set_trace2(ctypes.c_void_p(trace.data_ptr()), args.cta, 1)
+    lib.mega_conv_chain_set_trace2(ctypes.c_void_p(trace.data_ptr()), args.cta, 1 if args.layer < 0 else 2 + args.layer)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     ch.launch()
@@ -47,6 +48,23 @@ with torch.no_grad():
     torch.cuda.synchronize()
     lib.mega_conv_chain_set_trace2(None, 0, 0)
 t = trace.cpu().view(3, 4096, 2)
+if args.layer >= 0:
+    CODES = {1: "prod:layer_begin", 2: "prod:barrier_passed", 3: "prod:issue_kb", 7: "mma:kb_ready", 4: "epi:tile_acc_ready",
+             5: "epi:residual_ready", 6: "epi:tile_done", 8: "epi:layer_tiles_done", 9: "epi:stores_drained", 10: "epi:arrived"}
+    evs = []
+    for role in range(3):
+        for tag, clk in t[role].tolist():
+            if tag or clk:
+                evs.append((clk, role, (tag >> 8) & 0xffffff, tag & 0xff))
+    evs.sort()
+    print("layer", args.layer, ch.info["layers"][args.layer])
+    t0, last = evs[0][0], evs[0][0]
+    for clk, role, idx, code in evs:
+        if code in (3, 7) and idx % 4:
+            continue
+        print("%9.3f us +%6.3f  %-22s idx %d" % ((clk - t0) / 1965.0, (clk - last) / 1965.0, CODES.get(code, code), idx))
+        last = clk
+    sys.exit(0)
 ev = collections.defaultdict(dict)
 for role in range(3):
     for tag, clk in t[role].tolist():
@@ -78,6 +96,6 @@ for r in rows:
     g[0] += 1; g[1] += r["us"]; g[2] += r["gflop"]; g[3] += r["tiles_done_us"]; g[4] += r["arrived_us"]
 print("%-52s %3s %9s %8s %8s %10s %10s" % ("(m, cout, k, taps, bn, sk, res)", "n", "us", "GF", "TF/s", "tiles_done", "arrived"))
 for k, g in sorted(grp.items(), key=lambda kv: -kv[1][1]):
-    print("%-52s %3d %9.1f %8.1f %8.1f %10.1f %10.1f" % (str(k), g[0], g[1], g[2], g[2] / g[1] * 1e-3, g[3] / g[0], g[4] / g[0]))
+    print("%-52s %3d %9.1f %8.1f %8.1f %10.1f %10.1f" % (str(k), g[0], g[1], g[2], g[2] / g[1] * 1e3, g[3] / g[0], g[4] / g[0]))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump({"chain_us": e0.elapsed_time(e1) * 1e3, "rows": rows}, open(os.path.join(ROOT, "gpurun_out", "backbone_trace_fps%d.json" % n), "w"))
