@@ -391,6 +391,34 @@ class MegaBench:
                 comm = {"collectives_per_step": len(rec) / 6.0,
                         "collective_ms_per_step": sum(a.elapsed_time(b) for a, b in rec) / 6.0,
                         "step_ms_instrumented": s0.elapsed_time(s1) / 6.0}
+        # ---- N > 1: the hand-off that follows the path in tools/test_net.py (engine/inference.py:50-69): every rank's
+        #      detections of its last key frames to rank 0 through mega_core.utils.comm.gather_predictions over NCCL,
+        #      checked on rank 0 against the count every rank reports (outside the timed regions)
+        handoff = None
+        if world > 1:
+            from mega_core.structures.bounding_box import BoxList
+            from mega_core.utils import comm as comm_utils
+            with torch.no_grad():
+                dets = step_dev(0)
+            dets = dets if isinstance(dets, list) else [dets]
+            preds, mine = {}, 0
+            for g, det in enumerate(dets):
+                b, sc, lb = det.to_host()
+                bl = BoxList(b, (w, h), mode="xyxy")
+                bl.add_field("scores", sc)
+                bl.add_field("labels", lb)
+                preds[g * world + rank] = bl
+                mine += len(bl)
+            t0 = time.time()
+            merged = comm_utils.gather_predictions(preds)
+            dt = time.time() - t0
+            tot = torch.tensor([mine], device=dev, dtype=torch.int64)
+            dist.all_reduce(tot)
+            if rank == 0:
+                handoff = {"images": len(merged), "detections": int(sum(len(m) for m in merged)),
+                           "expected_images": world * len(dets), "expected_detections": int(tot.item()),
+                           "ok": len(merged) == world * len(dets) and sum(len(m) for m in merged) == int(tot.item()),
+                           "backend": dist.get_backend(), "seconds": round(dt, 4)}
         h2d = fps * 2 * 3 * h * w * 4 + eng.tab_h.numel() * 4 * world * fps
         d2h = (model.d2h_bytes_per_frame if world == 1 else 4 + 300 * 28) * fps
         times = torch.tensor([dev_ms, e2e_ms, comm["collective_ms_per_step"] if comm else 0.0,
@@ -410,7 +438,7 @@ class MegaBench:
                     "e2e_value": kf * args.steps / (e2e_ms * 1e-3), "ms_per_step": dev_ms / args.steps,
                     "launches_per_step": launches_per_step, "h2d": h2d, "d2h": d2h,
                     "detections_per_frame": ndet / float(args.steps * fps), "wave": wave, "wave_note": wave_note,
-                    "per_rank": per_rank, "comm": comm, "cuda_graph": bool(eng._graphs)})
+                    "per_rank": per_rank, "comm": comm, "cuda_graph": bool(eng._graphs), "handoff": handoff})
         return res
 
 
@@ -592,6 +620,7 @@ def run_mega(args, rank, world):
     if R["per_rank"] is not None:
         line["per_rank"] = R["per_rank"]
         line["comm"] = R["comm"]
+        line["prediction_handoff"] = R["handoff"]
     return line
 
 

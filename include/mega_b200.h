@@ -143,6 +143,16 @@ long long mega_nms_workspace_bytes(int n);
 int mega_nms(const float* boxes /*[n,4]*/, const float* scores /*[n]*/, int n, float thresh, void* workspace,
              long long workspace_bytes, long long* keep_out /*[n]*/, int* count_out, void* stream);
 
+/* CPU tensors behind the same `_C` names (ABI v5): the reference dispatches nms / roi_align_forward on the tensor's
+ * device (csrc/nms.h:10-28 -> cpu/nms_cpu.cpp:6-75; csrc/ROIAlign.h:11-25 -> cpu/ROIAlign_cpu.cpp:221-257; BASELINE
+ * configs[0] runs with MODEL.DEVICE cpu). HOST pointers, fp32 (is_double 0) or fp64 (1) like AT_DISPATCH_FLOATING_TYPES;
+ * bit-identical to the reference's CPU kernels, incl. the CPU rule "suppress when IoU >= thresh". */
+int mega_nms_host(const void* boxes /*[n,4]*/, const void* scores /*[n]*/, int n, float thresh, int is_double,
+                  long long* keep_out /*[n]*/, int* count_out);
+int mega_roi_align_forward_nchw_host(const void* input, int batch, int channels, int height, int width, const void* rois,
+                                     int num_rois, float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                                     int is_double, void* output);
+
 /* ------------------------------------------------------- RPN proposal selection
  * sigmoid -> top-k (sorted) -> decode -> clip -> remove-small -> NMS -> first post_nms, per image.
  * Replaces RPNPostProcessor.forward_for_single_feature_map (modeling/rpn/inference.py:76-123),

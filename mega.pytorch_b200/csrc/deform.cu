@@ -13,47 +13,72 @@
 
 namespace mega {
 
-__global__ void focal_loss_fwd_kernel(long long total, const float* __restrict__ logits, const int* __restrict__ targets,
-                                      int num_classes, float gamma, float alpha, float* __restrict__ losses) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = i / num_classes;
-    const int d = static_cast<int>(i - n * num_classes);
-    const int t = targets[n];
-    const float c1 = (t == (d + 1)) ? 1.f : 0.f;
-    const float c2 = (t >= 0 && t != (d + 1)) ? 1.f : 0.f;
-    const float x = logits[i];
-    const float p = 1.f / (1.f + expf(-x));
-    const float term1 = powf(1.f - p, gamma) * logf(fmaxf(p, FLT_MIN));
-    const float pos = (x >= 0.f) ? 1.f : 0.f;
-    const float term2 = powf(p, gamma) * (-1.f * x * pos - logf(1.f + expf(x - 2.f * x * pos)));
-    float l = 0.f;
-    l += -c1 * term1 * alpha;
-    l += -c2 * term2 * (1.f - alpha);
-    losses[i] = l;
-  }
+// Sigmoid focal loss (SigmoidFocalLoss_cuda.cu:20-103) through the log-sigmoid identities
+//     log p = -softplus(-x),   log(1 - p) = -softplus(x),   softplus(x) = max(x, 0) + log1p(exp(-|x|)),
+// i.e. ONE exp and ONE log1p per logit (+ the two powers) instead of three exps and two logs; p itself comes from the same
+// e = exp(-|x|). One thread handles four consecutive logits of a row when the class count allows it (128-bit loads /
+// stores); the target of a row is read once per thread.
+struct FocalTerms {
+  float p, log_p, log_1mp;
+};
+__device__ __forceinline__ FocalTerms focal_terms(float x) {
+  const float e = __expf(-fabsf(x));
+  const float l = log1pf(e);
+  FocalTerms t;
+  const float inv = 1.f / (1.f + e);
+  t.p = x >= 0.f ? inv : e * inv;
+  t.log_p = -(fmaxf(-x, 0.f) + l);
+  t.log_1mp = -(fmaxf(x, 0.f) + l);
+  return t;
+}
+__device__ __forceinline__ float focal_fwd_one(float x, int t, int d, float gamma, float alpha) {
+  const FocalTerms f = focal_terms(x);
+  if (t == d + 1) return -alpha * powf(1.f - f.p, gamma) * fmaxf(f.log_p, logf(FLT_MIN));
+  if (t >= 0) return -(1.f - alpha) * powf(f.p, gamma) * f.log_1mp;
+  return 0.f;
+}
+__device__ __forceinline__ float focal_bwd_one(float x, int t, int d, float gamma, float alpha) {
+  const FocalTerms f = focal_terms(x);
+  if (t == d + 1) return -alpha * powf(1.f - f.p, gamma) * (1.f - f.p - f.p * gamma * fmaxf(f.log_p, logf(FLT_MIN)));
+  if (t >= 0) return -(1.f - alpha) * powf(f.p, gamma) * (f.log_1mp * (1.f - f.p) * gamma - f.p);
+  return 0.f;
 }
 
-__global__ void focal_loss_bwd_kernel(long long total, const float* __restrict__ logits, const int* __restrict__ targets,
-                                      const float* __restrict__ d_losses, int num_classes, float gamma, float alpha,
-                                      float* __restrict__ d_logits) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long n = i / num_classes;
-    const int d = static_cast<int>(i - n * num_classes);
-    const int t = targets[n];
-    const float c1 = (t == (d + 1)) ? 1.f : 0.f;
-    const float c2 = (t >= 0 && t != (d + 1)) ? 1.f : 0.f;
-    const float x = logits[i];
-    const float p = 1.f / (1.f + expf(-x));
-    const float term1 = powf(1.f - p, gamma) * (1.f - p - (p * gamma * logf(fmaxf(p, FLT_MIN))));
-    const float pos = (x >= 0.f) ? 1.f : 0.f;
-    const float term2 =
-        powf(p, gamma) * ((-1.f * x * pos - logf(1.f + expf(x - 2.f * x * pos))) * (1.f - p) * gamma - p);
-    float g = 0.f;
-    g += -c1 * term1 * alpha;
-    g += -c2 * term2 * (1.f - alpha);
-    d_logits[i] = g * d_losses[i];
+template <bool BWD>
+__global__ void focal_loss_kernel(long long total, const float* __restrict__ logits, const int* __restrict__ targets,
+                                  const float* __restrict__ d_losses, int num_classes, float gamma, float alpha,
+                                  float* __restrict__ out) {
+  const bool vec = (num_classes & 3) == 0;       // a float4 never straddles two rows
+  const long long items = vec ? total / 4 : total;
+  for (long long it = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; it < items;
+       it += static_cast<long long>(gridDim.x) * blockDim.x) {
+    if (vec) {
+      const long long i = it * 4;
+      const long long n = i / num_classes;
+      const int d = static_cast<int>(i - n * num_classes);
+      const int t = __ldg(targets + n);
+      const float4 x = __ldg(reinterpret_cast<const float4*>(logits + i));
+      float4 r;
+      if (BWD) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(d_losses + i));
+        r.x = focal_bwd_one(x.x, t, d, gamma, alpha) * g.x;
+        r.y = focal_bwd_one(x.y, t, d + 1, gamma, alpha) * g.y;
+        r.z = focal_bwd_one(x.z, t, d + 2, gamma, alpha) * g.z;
+        r.w = focal_bwd_one(x.w, t, d + 3, gamma, alpha) * g.w;
+      } else {
+        r.x = focal_fwd_one(x.x, t, d, gamma, alpha);
+        r.y = focal_fwd_one(x.y, t, d + 1, gamma, alpha);
+        r.z = focal_fwd_one(x.z, t, d + 2, gamma, alpha);
+        r.w = focal_fwd_one(x.w, t, d + 3, gamma, alpha);
+      }
+      *reinterpret_cast<float4*>(out + i) = r;
+    } else {
+      const long long n = it / num_classes;
+      const int d = static_cast<int>(it - n * num_classes);
+      const int t = __ldg(targets + n);
+      const float x = __ldg(logits + it);
+      out[it] = BWD ? focal_bwd_one(x, t, d, gamma, alpha) * __ldg(d_losses + it) : focal_fwd_one(x, t, d, gamma, alpha);
+    }
   }
 }
 
@@ -70,7 +95,117 @@ __device__ __forceinline__ float dcn_bilinear(const float* __restrict__ plane, i
   return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4;
 }
 
-// one thread per (b, c, h_col, w_col); writes the kh*kw taps of that channel into the pixel's K-major row
+// Deformable im2col, tile form. A CTA (4 warps) owns 32 consecutive output pixels of one output row and kDcnCh
+// channels of one deformable group:
+//   1. the sample geometry of every (tap, pixel) -- offsets read once, floor / weights / the four corner indices with
+//      their validity folded into the weights -- goes to shared memory; it is shared by all channels of the group (the
+//      reference recomputes it per channel, deform_conv_kernel_cuda.cu:197-250);
+//   2. lane = pixel, so the four gathers of a (channel, tap) read neighbouring addresses of ONE channel plane (the
+//      reference layout is NCHW) -- round 1's thread-per-(pixel, channel) mapping read 32 different planes per warp;
+//   3. the K-major rows cols[pixel][c*kh*kw + tap] are staged in shared memory and written with 128-bit stores, a row
+//      segment of kDcnCh*kh*kw floats per pixel (round 1 wrote 4 bytes every kh*kw*4).
+// The arithmetic per element is unchanged (dcn_bilinear), so results are bit-identical to the scalar kernel.
+constexpr int kDcnPix = 32;
+constexpr int kDcnCh = 16;
+constexpr int kDcnMaxTaps = 49;     // up to 7x7 kernels in shared memory; larger ones take the scalar kernel
+
+struct DcnTap {          // geometry of one (tap, pixel) sample
+  int i00, i01, i10, i11;
+  float w00, w01, w10, w11;
+};
+
+__global__ void __launch_bounds__(128)
+deform_im2col_tile_kernel(const float* __restrict__ im, const float* __restrict__ offset, const float* __restrict__ mask,
+                          int channels, int height, int width, int kh, int kw, int pad_h, int pad_w, int stride_h,
+                          int stride_w, int dil_h, int dil_w, int deformable_group, int ho, int wo, int kpad,
+                          float* __restrict__ cols) {
+  extern __shared__ float dcn_smem[];
+  const int taps = kh * kw;
+  DcnTap* geo = reinterpret_cast<DcnTap*>(dcn_smem);                      // [taps][32] sample geometry
+  float* mvals = dcn_smem + taps * kDcnPix * (sizeof(DcnTap) / 4);        // [taps][32] modulation scalars (DCN v2)
+  float* stage = mvals + taps * kDcnPix;                                  // [32][kDcnCh * taps + 1] output rows
+  const int ld = kDcnCh * taps + 1;
+  const int cpg = channels / deformable_group;
+  const int ch_tiles = (cpg + kDcnCh - 1) / kDcnCh;
+  const int w_tiles = (wo + kDcnPix - 1) / kDcnPix;
+  int bid = blockIdx.x;
+  const int wt = bid % w_tiles; bid /= w_tiles;
+  const int ct = bid % ch_tiles; bid /= ch_tiles;
+  const int dg = bid % deformable_group; bid /= deformable_group;
+  const int h_col = bid % ho;
+  const int b = bid / ho;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w_col = wt * kDcnPix + lane;
+  const bool live = w_col < wo;
+  const long long plane_sz = static_cast<long long>(height) * width;
+  // ---- 1. geometry
+  const float* off = offset + (static_cast<long long>(b) * deformable_group + dg) * 2 * taps * ho * wo;
+  const float* msk = mask ? mask + (static_cast<long long>(b) * deformable_group + dg) * taps * ho * wo : nullptr;
+  for (int tap = warp; tap < taps; tap += 4) {
+    DcnTap g = {0, 0, 0, 0, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const int i = tap / kw, j = tap - i * kw;
+      const long long o = (static_cast<long long>(2 * tap) * ho + h_col) * wo + w_col;
+      const float h_im = h_col * stride_h - pad_h + i * dil_h + __ldg(off + o);
+      const float w_im = w_col * stride_w - pad_w + j * dil_w + __ldg(off + o + static_cast<long long>(ho) * wo);
+      if (h_im > -1 && w_im > -1 && h_im < height && w_im < width) {
+        const int h_low = static_cast<int>(floorf(h_im)), w_low = static_cast<int>(floorf(w_im));
+        const int h_high = h_low + 1, w_high = w_low + 1;
+        const float lh = h_im - h_low, lw = w_im - w_low, hh = 1.f - lh, hw = 1.f - lw;
+        const bool t0 = h_low >= 0, t1 = h_high <= height - 1, l0 = w_low >= 0, l1 = w_high <= width - 1;
+        g.i00 = (t0 && l0) ? h_low * width + w_low : -1;
+        g.i01 = (t0 && l1) ? h_low * width + w_high : -1;
+        g.i10 = (t1 && l0) ? h_high * width + w_low : -1;
+        g.i11 = (t1 && l1) ? h_high * width + w_high : -1;
+        g.w00 = hh * hw; g.w01 = hh * lw; g.w10 = lh * hw; g.w11 = lh * lw;
+      } else {
+        g.i00 = g.i01 = g.i10 = g.i11 = -2;     // the whole sample is outside: value 0
+      }
+      // the modulation scalar of DCN v2 multiplies the interpolated value (kept as a separate factor, like the reference)
+      if (msk) mvals[tap * kDcnPix + lane] = __ldg(msk + (static_cast<long long>(tap) * ho + h_col) * wo + w_col);
+    }
+    geo[tap * kDcnPix + lane] = g;
+  }
+  __syncthreads();
+  // ---- 2. gather: items = (channel of the tile, tap), lane = pixel
+  const int c0 = dg * cpg + ct * kDcnCh;
+  const int nch = min(kDcnCh, cpg - ct * kDcnCh);
+  for (int item = warp; item < nch * taps; item += 4) {
+    const int cl = item / taps, tap = item - cl * taps;
+    const DcnTap g = geo[tap * kDcnPix + lane];
+    const float* plane = im + (static_cast<long long>(b) * channels + c0 + cl) * plane_sz;
+    float val = 0.f;
+    if (live && g.i00 != -2) {
+      const float v1 = g.i00 >= 0 ? __ldg(plane + g.i00) : 0.f;
+      const float v2 = g.i01 >= 0 ? __ldg(plane + g.i01) : 0.f;
+      const float v3 = g.i10 >= 0 ? __ldg(plane + g.i10) : 0.f;
+      const float v4 = g.i11 >= 0 ? __ldg(plane + g.i11) : 0.f;
+      val = g.w00 * v1 + g.w01 * v2 + g.w10 * v3 + g.w11 * v4;
+    }
+    if (msk && live) val *= mvals[tap * kDcnPix + lane];
+    stage[lane * ld + cl * taps + tap] = val;
+  }
+  __syncthreads();
+  // ---- 3. rows out: pixel p of the tile, nch*taps consecutive floats starting at column c0*taps
+  const int seg = nch * taps;
+  for (int p = warp; p < kDcnPix; p += 4) {
+    const int wc = wt * kDcnPix + p;
+    if (wc >= wo) break;
+    float* row = cols + ((static_cast<long long>(b) * ho + h_col) * wo + wc) * kpad + static_cast<long long>(c0) * taps;
+    const float* src = stage + p * ld;
+    if (((reinterpret_cast<uintptr_t>(row) & 15) == 0) && (seg & 3) == 0) {
+      for (int v = lane; v < seg / 4; v += 32) {
+        float4 o = make_float4(src[4 * v], src[4 * v + 1], src[4 * v + 2], src[4 * v + 3]);
+        *reinterpret_cast<float4*>(row + 4 * v) = o;
+      }
+    } else {
+      for (int v = lane; v < seg; v += 32) row[v] = src[v];
+    }
+  }
+}
+
+// scalar form (kernels larger than 7x7): one thread per (b, c, h_col, w_col); writes the kh*kw taps of that channel into
+// the pixel's K-major row
 __global__ void deform_im2col_kernel(long long total, const float* __restrict__ im, const float* __restrict__ offset,
                                      const float* __restrict__ mask, int batch, int channels, int height, int width,
                                      int kh, int kw, int pad_h, int pad_w, int stride_h, int stride_w, int dil_h,
@@ -191,8 +326,8 @@ extern "C" int mega_sigmoid_focalloss_forward(const float* logits, const int* ta
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const long long total = static_cast<long long>(num_samples) * num_classes;
   if (total == 0) return MEGA_OK;
-  focal_loss_fwd_kernel<<<grid_dcn(total, 256), 256, 0, stream>>>(total, logits, targets, num_classes, gamma, alpha,
-                                                                  losses);
+  focal_loss_kernel<false><<<grid_dcn(total / 2, 256), 256, 0, stream>>>(total, logits, targets, nullptr, num_classes,
+                                                                         gamma, alpha, losses);
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }
@@ -203,8 +338,8 @@ extern "C" int mega_sigmoid_focalloss_backward(const float* logits, const int* t
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const long long total = static_cast<long long>(num_samples) * num_classes;
   if (total == 0) return MEGA_OK;
-  focal_loss_bwd_kernel<<<grid_dcn(total, 256), 256, 0, stream>>>(total, logits, targets, d_losses, num_classes, gamma,
-                                                                  alpha, d_logits);
+  focal_loss_kernel<true><<<grid_dcn(total / 2, 256), 256, 0, stream>>>(total, logits, targets, d_losses, num_classes,
+                                                                        gamma, alpha, d_logits);
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }
@@ -221,6 +356,25 @@ extern "C" int mega_deform_im2col(const float* input, const float* offset, const
   const int wo = (width + 2 * pad_w - (dil_w * (kw - 1) + 1)) / stride_w + 1;
   const long long total = static_cast<long long>(batch) * channels * ho * wo;
   if (total == 0) return MEGA_OK;
+  const int taps = kh * kw;
+  if (taps <= kDcnMaxTaps) {
+    const int cpg = channels / deformable_group;
+    const long long blocks = static_cast<long long>(batch) * ho * deformable_group * ((cpg + kDcnCh - 1) / kDcnCh) *
+                             ((wo + kDcnPix - 1) / kDcnPix);
+    MEGA_ARG_CHECK(blocks < (1LL << 31), "deform_im2col: grid too large");
+    const size_t smem = (static_cast<size_t>(taps) * kDcnPix * (sizeof(DcnTap) / 4 + 1) +
+                         static_cast<size_t>(kDcnPix) * (kDcnCh * taps + 1)) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      MEGA_CUDA_CHECK(cudaFuncSetAttribute(deform_im2col_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      configured = true;
+    }
+    deform_im2col_tile_kernel<<<static_cast<unsigned>(blocks), 128, smem, stream>>>(
+        input, offset, mask, channels, height, width, kh, kw, pad_h, pad_w, stride_h, stride_w, dil_h, dil_w,
+        deformable_group, ho, wo, kpad, cols);
+    MEGA_CUDA_CHECK(cudaGetLastError());
+    return MEGA_OK;
+  }
   deform_im2col_kernel<<<grid_dcn(total, 256), 256, 0, stream>>>(total, input, offset, mask, batch, channels, height,
                                                                  width, kh, kw, pad_h, pad_w, stride_h, stride_w, dil_h,
                                                                  dil_w, deformable_group, ho, wo, kpad, cols);

@@ -1,6 +1,8 @@
 """`mega_core._C` -- the reference's native-op module (csrc/vision.cpp:9-25), served by the sm_100a
 kernels of libmega_b200.so. Signatures are positional and identical to the reference's pybind
-functions; device tensors only: there is no CPU implementation behind these names."""
+functions. Device tensors run the CUDA kernels; like the reference (csrc/nms.h:10-28, csrc/ROIAlign.h:11-25) `nms` and
+`roi_align_forward` also accept CPU tensors (host implementations in csrc/host_ops.cu, bit-identical to the reference's
+cpu/*.cpp); every other name is CUDA-only, as in the reference ("Not implemented on the CPU")."""
 import torch
 
 from . import _lib
@@ -19,14 +21,48 @@ def nms(dets, scores, threshold):
     Kept original indices in ascending order, on the input's device (nms.cu:127-130); an empty
     input returns an empty long tensor."""
     if dets.numel() == 0:
-        return torch.empty(0, dtype=torch.int64, device=dets.device)
+        return torch.empty(0, dtype=torch.int64, device="cpu")            # nms.h:17-18 / nms_cpu.cpp:13-15
+    if not dets.is_cuda:
+        return _nms_cpu(dets, scores, float(threshold))
     _cuda_only("nms", dets, scores)
     keep, count = ops.nms_device(dets, scores, float(threshold))
     return keep[: int(count.item())]        # the one host read the dynamic output size requires
 
 
+def _nms_cpu(dets, scores, threshold):
+    """nms_cpu (cpu/nms_cpu.cpp:6-75): suppress when IoU >= threshold, kept original indices ascending"""
+    if scores.is_cuda:
+        raise RuntimeError("scores must be a CPU tensor")
+    if dets.dtype != scores.dtype:
+        raise RuntimeError("dets should have the same type as scores")
+    if dets.dtype not in (torch.float32, torch.float64):
+        raise RuntimeError("nms: \"nms\" not implemented for '%s'" % dets.dtype)
+    d, s = dets.contiguous(), scores.contiguous()
+    n = d.shape[0]
+    keep = torch.empty(n, dtype=torch.int64)
+    count = torch.zeros(1, dtype=torch.int32)
+    _lib.check(_lib.lib.mega_nms_host(d.data_ptr(), s.data_ptr(), n, threshold, 1 if d.dtype == torch.float64 else 0,
+                                      keep.data_ptr(), count.data_ptr()), "mega_nms_host")
+    return keep[: int(count[0])]
+
+
 def roi_align_forward(input, rois, spatial_scale, pooled_height, pooled_width, sampling_ratio):
     """(csrc/ROIAlign.h:11-25) NCHW fp32 input, rois [K,5] = (batch, x1, y1, x2, y2) -> [K,C,ph,pw]"""
+    if not input.is_cuda:
+        if rois.is_cuda:
+            raise RuntimeError("rois must be a CPU tensor")
+        if input.dtype not in (torch.float32, torch.float64) or rois.dtype != input.dtype:
+            raise RuntimeError("ROIAlign_forward: input and rois must both be float32 or both float64 CPU tensors")
+        x, r = input.contiguous(), rois.contiguous()
+        out = torch.empty(r.shape[0], x.shape[1], int(pooled_height), int(pooled_width), dtype=x.dtype)
+        if out.numel() == 0:
+            return out
+        _lib.check(_lib.lib.mega_roi_align_forward_nchw_host(x.data_ptr(), x.shape[0], x.shape[1], x.shape[2], x.shape[3],
+                                                             r.data_ptr(), r.shape[0], float(spatial_scale),
+                                                             int(pooled_height), int(pooled_width), int(sampling_ratio),
+                                                             1 if x.dtype == torch.float64 else 0, out.data_ptr()),
+                   "mega_roi_align_forward_nchw_host")
+        return out
     _cuda_only("roi_align_forward", input, rois)
     return ops.roi_align_nchw(input, rois, float(spatial_scale), int(pooled_height), int(pooled_width),
                               int(sampling_ratio))

@@ -427,7 +427,9 @@ class HeadCommon:
         q, k, vt = self.Qb[:nq], self.Kb[:nref], self.Vt[ld]
         s = self.S[ld][:16 * nq * ld].view(16, nq, ld)
         key = (id(att), xq.data_ptr(), nq, refs.data_ptr(), nref, out.data_ptr(), tail is not None, reuse_kv)
-        with ops.chain(self._chains, ("qk",) + key, self.dev, enabled=self.chained):
+        # [Q, K, V', Q.K^T]: the product reads Q (3 back) and K (2 back), so every layer may start once the layer TWO
+        # positions back is complete (depth-2 barrier: V' and Q.K^T overlap the tails of K and V')
+        with ops.chain(self._chains, ("qk",) + key, self.dev, enabled=self.chained, depth=1 if reuse_kv else 2):
             ops.linear(xq, att.wq, q, bias=att.bq)
             if not reuse_kv:
                 ops.linear(refs, att.wk, k, bias=att.bk)

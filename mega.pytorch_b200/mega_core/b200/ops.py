@@ -107,10 +107,11 @@ class chain(object):
     depth 2 (csrc/conv_chain.cu): a CTA streams lane B's layer while lane A's layer drains its epilogue / stores / grid
     barrier. Results are those of the two sequences run one after the other."""
 
-    def __init__(self, cache, key, device, enabled=True, max_ctas=0, interleave=False):
+    def __init__(self, cache, key, device, enabled=True, max_ctas=0, interleave=False, depth=1):
         self.cache, self.key, self.device, self.max_ctas = cache, key, device, max_ctas
         self.enabled = enabled and CHAINS_ENABLED[0] and _CHAIN_MODE[0] is None
         self.interleave = interleave and self.enabled
+        self.depth = depth          # 2: the caller guarantees that no layer reads what the layer directly before it wrote
         self.split = None
 
     def next_lane(self):
@@ -142,7 +143,7 @@ class chain(object):
         if mode == "record":
             descs = _CHAIN_REC[0]
             _CHAIN_REC[0] = None
-            depth = 1
+            depth = self.depth
             if self.interleave:
                 assert self.split is not None and 2 * self.split == len(descs), \
                     "interleaved chain: the two lanes must record the same number of layers (%s / %d)" % (self.split, len(descs))

