@@ -445,8 +445,10 @@ class MegaBench:
 def roofline_pass(eng, step, reps=3):
     """sum of the tensor-core kernel durations of one step (CUDA events on the launching stream, eager launches)"""
     from mega_core.b200 import ops
-    saved_graphs, eng._graphs = eng._graphs, {}
-    saved_flag, eng.use_graph = eng.use_graph, False
+    has_graphs = hasattr(eng, "_graphs")         # the windowed engines replay CUDA graphs; FGFA / DFF / base launch eagerly
+    if has_graphs:
+        saved_graphs, eng._graphs = eng._graphs, {}
+        saved_flag, eng.use_graph = eng.use_graph, False
     rec = []
 
     def hook(run, flops, info):
@@ -469,7 +471,8 @@ def roofline_pass(eng, step, reps=3):
                 torch.cuda.synchronize()
     finally:
         ops.TIMING_HOOK[0] = None
-        eng._graphs, eng.use_graph = saved_graphs, saved_flag
+        if has_graphs:
+            eng._graphs, eng.use_graph = saved_graphs, saved_flag
     ms = sum(r[0].elapsed_time(r[1]) for r in rec) / reps
     fl = sum(r[2] for r in rec) / reps
     n = max(len(rec) // reps, 1)
@@ -637,7 +640,8 @@ def run_windowed(args, rank, world):
     sd = synth.make_state_dict(args.arch, seed={"rdn": 4, "fgfa": 5}[method])
     model = build_detection_model_from_state_dict(sd, method=method, device=dev, precision=precision)
     eng = model.engine
-    eng.use_graph = not args.no_graph
+    if hasattr(eng, "use_graph"):
+        eng.use_graph = not args.no_graph
     pool = frame_pool(16, h, w)
     pinned = [f.pin_memory() for f in pool]
     pdev = [f.to(dev) for f in pool]
@@ -697,13 +701,13 @@ def run_windowed(args, rank, world):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": PRECISION_DTYPE[precision],
             "data": "synthetic",
             "config": {"workload": workload(args), "arch": args.arch, "weights": "seeded synthetic init (mega_core.b200.synth)",
-                       "parallelism": "single GPU", "key_frames_per_step": 1, "cuda_graph": bool(eng._graphs),
+                       "parallelism": "single GPU", "key_frames_per_step": 1, "cuda_graph": bool(getattr(eng, "_graphs", None)),
                        "precision": precision, "l2": "per-step working set exceeds the 126 MB L2; no flush"},
             "clocks": clocks,
             "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 3 * h * w * 4,
                     "d2h_bytes_per_step": model.d2h_bytes_per_frame, "ms_per_step": e2e_ms / args.steps,
                     "detections_per_frame": ndet / float(args.steps), "api": "model(images) per key frame"},
-            "gpu_launches": int(round((eng.launches_per_frame if eng._graphs else lps) * args.steps)),
+            "gpu_launches": int(round((eng.launches_per_frame if getattr(eng, "_graphs", None) else lps) * args.steps)),
             "parity": {"note": "tests/test_engine_gpu.py replays the reference's 192x320 %s fixture through this engine in the "
                                "exact-fp32 shadow / fp32x3 / f16 modes; no full-size fixture for this arch" % method.upper()}}
     if roof is not None:

@@ -120,6 +120,10 @@ __device__ __forceinline__ TraceCursor trace_cursor(const ChainTrace& tr, int ro
 // 128 x 128 tile with a residual against 1.2 us of MMAs for K = 256 (tools/trace_backbone.py), which made every
 // 1x1-expand layer of the backbone epilogue-bound. Here the flags are template parameters of the inner loop, staging
 // goes through explicit ld/st.shared with precomputed swizzled offsets, and two warps share a lane quarter.
+// (Tried on top and reverted: walking the work list one tile ahead to prefetch the next tile's scale / bias into registers
+// and its residual chunk by TMA. The residual still arrived 0.5 us after the accumulator -- it queues behind the main
+// loop's operand loads in the SM's TMA FIFO -- and the second decode_tile per tile cost more than the barriers it saved:
+// backbone chain 1.61 -> 1.70 ms at 2 images, 3.75 -> 4.04 ms at 8.)
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kChainThreads = 64 + kEpiThreads;
@@ -238,18 +242,10 @@ __device__ __noinline__ void chain_epilogue_layer(const ChainLayer* L, const Con
   uint32_t off[8];
 #pragma unroll
   for (int g = 0; g < 8; ++g) off[g] = (static_cast<uint32_t>(g) ^ static_cast<uint32_t>(lane & 7)) << 4;
-  // the work list is walked one item ahead: while tile i is finished, the scale / bias slice and the residual of tile i+1
-  // are already on their way (round 2 trace of a K = 256 expand layer: 1.4-1.9 us between two tiles of a CTA went to the
-  // global loads of scale / bias behind two CTA-wide barriers, 0.4-0.7 us to the residual load issued at tile start)
   WorkIter it(p, cta, grid);
-  int t, kb0, kb1;
-  int tn = 0, kbn0 = 0, kbn1 = 0;
-  bool have = it.next(t, kb0, kb1);
-  int sb_key = -1, pref_key = -1;       // (n0, batch) whose scale / bias are in shared memory / in nsc, nbi
-  float nsc = 1.f, nbi = 0.f;
-  bool res_inflight = false;            // this warp's first residual chunk of the CURRENT tile was issued during the previous one
-  for (int tile_item = 0; have; ++tile_item) {
-    const bool have_next = it.next(tn, kbn0, kbn1);
+  int t;
+  int kb0, kb1;
+  for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
     const TileCoord tc = decode_tile(p, t, BN);
     const int buf = item & 1;
     const uint32_t use = static_cast<uint32_t>(item >> 1);
@@ -260,45 +256,21 @@ __device__ __noinline__ void chain_epilogue_layer(const ChainLayer* L, const Con
     const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
     const int res_n = tc.img + tc.batch * p.res_n_off;
     const int nchunks = min(BN / CW, (p.cout - tc.n0 + CW - 1) / CW);
-    // ---- scale / bias of this tile's columns in shared memory (skipped when the previous tile had the same columns)
-    const int key = tc.n0 | (tc.batch << 20);
-    const bool sb_changed = key != sb_key;
-    if (sb_changed) {
-      epi_bar_sync_all();   // every warp is done with the previous tile's scale / bias
-      if (epi_tid < BN) {
-        if (pref_key != key) {
-          const int n = tc.n0 + epi_tid;
-          const int zoff = tc.batch * p.bias_z_off;
-          nsc = (p.scale && n < p.cout) ? __ldg(p.scale + zoff + n) : 1.f;
-          nbi = (p.bias && n < p.cout) ? __ldg(p.bias + zoff + n) : 0.f;
-        }
-        sb_s[epi_tid] = nsc;
-        sb_s[128 + epi_tid] = nbi;
-      }
-      sb_key = key;
+    // ---- while the MMAs of this tile run: stage its scale / bias slice in shared memory and start this warp's first
+    //      residual load
+    epi_bar_sync_all();   // every warp is done with the previous tile's scale / bias
+    if (epi_tid < BN) {
+      const int n = tc.n0 + epi_tid;
+      const int zoff = tc.batch * p.bias_z_off;
+      sb_s[epi_tid] = (p.scale && n < p.cout) ? __ldg(p.scale + zoff + n) : 1.f;
+      sb_s[128 + epi_tid] = (p.bias && n < p.cout) ? __ldg(p.bias + zoff + n) : 0.f;
     }
-    if (complete && has_res && !res_inflight && lane == 0 && half < nchunks) {
+    if (complete && has_res && lane == 0 && half < nchunks) {
       mbar_arrive_expect_tx(rbar, 4096);
       tma_load_4d(reinterpret_cast<void*>(smem + kChainStages * kChainStageBytes + ew * 8192 + 4096), tmRes, rbar,
                   tc.n0 + half * CW + tc.batch * p.res_c_off, st_w, st_h, res_n);
     }
-    res_inflight = false;
-    // ---- the next tile of this CTA: start fetching its scale / bias into registers
-    TileCoord tcn = tc;
-    bool next_complete = false;
-    if (have_next) {
-      tcn = decode_tile(p, tn, BN);
-      next_complete = (kbn0 == 0 && kbn1 == KB);
-      const int keyn = tcn.n0 | (tcn.batch << 20);
-      if (keyn != key && epi_tid < BN) {
-        const int n = tcn.n0 + epi_tid;
-        const int zoff = tcn.batch * p.bias_z_off;
-        nsc = (p.scale && n < p.cout) ? __ldg(p.scale + zoff + n) : 1.f;
-        nbi = (p.bias && n < p.cout) ? __ldg(p.bias + zoff + n) : 0.f;
-      }
-      pref_key = keyn != key ? keyn : pref_key;
-    }
-    if (sb_changed) epi_bar_sync_all();
+    epi_bar_sync_all();
     mbar_wait(&tmem_full_bar[buf], use & 1);
     tc_fence_after();
     tr.put(TR_TAG(layer, tile_item, 4));
@@ -400,25 +372,7 @@ __device__ __noinline__ void chain_epilogue_layer(const ChainLayer* L, const Con
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-    // ---- this warp's residual staging is free: fetch the first residual chunk of the next tile now, so that it lands
-    //      while the store, the work-list bookkeeping and the next accumulator wait go by
-    if (have_next && next_complete && has_res) {
-      const int nchunks_n = min(BN / CW, (p.cout - tcn.n0 + CW - 1) / CW);
-      if (half < nchunks_n) {
-        if (lane == 0) {
-          mbar_arrive_expect_tx(rbar, 4096);
-          tma_load_4d(reinterpret_cast<void*>(smem + kChainStages * kChainStageBytes + ew * 8192 + 4096), tmRes, rbar,
-                      tcn.n0 + half * CW + tcn.batch * p.res_c_off, tcn.w0 + bw0, tcn.h0 + bh0,
-                      tcn.img + tcn.batch * p.res_n_off);
-        }
-        res_inflight = true;
-      }
-    }
     tr.put(TR_TAG(layer, tile_item, 6));
-    have = have_next;
-    t = tn;
-    kb0 = kbn0;
-    kb1 = kbn1;
   }
 }
 

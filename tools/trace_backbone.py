@@ -36,8 +36,10 @@ with torch.no_grad():
         eng.stepn_batched(batch, w, h)
     torch.cuda.synchronize()
     # trace the backbone chain of the next step only
-    chains = [c for c in eng.backbone._chains.values() if c.n >= 90 and c.info["layers"][0]["m"] == 2 * n * 150 * 250]
-    assert len(chains) == 1, [(c.n, c.info["layers"][0]["m"]) for c in eng.backbone._chains.values()]
+    # the chain that ran the batch of 2n images: one lane (95 layers) or two interleaved lanes of n images (190 layers)
+    chains = [c for c in eng.backbone._chains.values()
+              if c.n >= 90 and c.info["layers"][0]["m"] * (2 if c.depth == 2 and c.n >= 180 else 1) == 2 * n * 150 * 250]
+    assert len(chains) == 1, [(c.n, c.depth, c.info["layers"][0]["m"]) for c in eng.backbone._chains.values()]
     ch = chains[0]
     trace = torch.zeros(3 * 4096 * 2, dtype=torch.int64, device=dev)
     lib.mega_conv_chain_set_trace2(ctypes.c_void_p(trace.data_ptr()), args.cta, 1 if args.layer < 0 else 2 + args.layer)
