@@ -501,25 +501,27 @@ def roofline_pass(eng, step, reps=3):
             "dominant": dom}
 
 
-def traffic_bytes():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (null when absent)"""
-    for name in ("r02_traffic.json", "r01_traffic.json"):
-        try:
-            d = json.load(open(os.path.join(ROOT, "profiles", name)))
-            return d["traffic_bytes_per_launch"], name
-        except Exception:
-            continue
+def traffic_bytes(precision):
+    """DRAM bytes per launch of the dominant kernel of `precision` from the committed ncu capture (null when that mode's
+    dominant kernel has no capture): profiles/r02_traffic.json = {"<precision>": {"traffic_bytes_per_launch": ..,
+    "kernel": .., "capture": ..}}"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(precision)
+        if d:
+            return d["traffic_bytes_per_launch"], "profiles/r02_traffic.json: %s, %s" % (d.get("kernel"), d.get("capture"))
+    except Exception:
+        pass
     return None, None
 
 
 def roofline_block(args, roof, step_ms, key_frames_per_step, precision):
     pk = peaks()
     algo_tflops = ALGO_GFLOP[args.arch] * key_frames_per_step * 1e9 / (roof["kernel_ms"] * 1e-3) / 1e12
-    traffic, tname = traffic_bytes()
+    traffic, tname = traffic_bytes(precision)
     return {"bound": "tensor", "achieved": algo_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
             "frac": algo_tflops / pk["tflops"], "traffic": traffic, "peak_source": pk["src"],
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, one ncu --set full capture "
-                            "(profiles/%s)" % tname,
+            "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum per launch, one ncu --set full capture (%s)" % tname)
+                            if tname else "no ncu --set full capture of this mode's dominant kernel is committed",
             "dominant_kernel": roof["dominant"], "kernel": KERNEL_NOTE.get(precision),
             "algorithmic_gflop_per_key_frame": ALGO_GFLOP[args.arch],
             "executed_gflop_per_step": roof["exec_gflop"], "kernel_ms_per_step": roof["kernel_ms"],

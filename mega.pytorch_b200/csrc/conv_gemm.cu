@@ -290,8 +290,8 @@ extern "C" int mega_conv_gemm(const mega_conv_gemm_desc* d, void* stream_v) {
   const int pdl = d->pdl ? 1 : 0;
   if (f16) return launch_conv_gemm_f16(d->block_n, out16 ? 1 : 0, tmA, tmB, tmOut, tmRes, p, grid, stream, pdl);
   if (strict) {
-    return d->block_n == 64 ? launch_cfg<64, 3, kModeSplit3, false>(tmA, tmB, tmOut, tmRes, p, grid, stream, pdl)
-                            : launch_cfg<128, 2, kModeSplit3, false>(tmA, tmB, tmOut, tmRes, p, grid, stream, pdl);
+    return d->block_n == 64 ? launch_cfg<64, 4, kModeSplit3, false>(tmA, tmB, tmOut, tmRes, p, grid, stream, pdl)
+                            : launch_cfg<128, 3, kModeSplit3, false>(tmA, tmB, tmOut, tmRes, p, grid, stream, pdl);
   }
   switch (d->block_n) {
     case 32: return launch_cfg<32, 6, kModeTf32, false>(tmA, tmB, tmOut, tmRes, p, grid, stream, pdl);

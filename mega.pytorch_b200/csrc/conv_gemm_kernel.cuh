@@ -65,8 +65,9 @@ struct SmemLayout {
   static constexpr bool SPLIT3 = MODE == kModeSplit3;
   static constexpr int kABytes = kBM * 128;
   static constexpr int kBBytes = BN * 128;
-  static constexpr int kHalf = kABytes + kBBytes;                 // 3xTF32: the low-part tiles follow at +kHalf
-  static constexpr int kStageBytes = SPLIT3 ? 2 * kHalf : kHalf;
+  static constexpr int kHalf = kABytes + kBBytes;                 // bytes the two TMA loads of a k-block deliver
+  // 3xTF32: [A raw | B raw (= the hi operand: the MMA ignores the low 13 bits) | B lo]; A's hi / lo parts live in TENSOR memory
+  static constexpr int kStageBytes = SPLIT3 ? kHalf + kBBytes : kHalf;
   static constexpr int kEpiOffset = STAGES * kStageBytes;       // 4 warps x (2 out + 2 residual) x 4 KB
   static constexpr int kEpiBytes = 4 * 4 * 4096;
   static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
@@ -145,9 +146,14 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // arrive, which sums the partial accumulators (in CTA order -> deterministic) and runs the
 // epilogue. Accumulators are double-buffered in TMEM so the epilogue of item i overlaps the
 // MMAs of item i+1.
-// SPLIT3 ("3xTF32"): operands stay full fp32 in shared memory; four extra warps split every staged tile into
-// hi = fp32 truncated to TF32 and lo = x - hi (exact), and each k-step issues hi*hi + hi*lo + lo*hi into the same
-// accumulator: ~2^-19 relative error instead of 2^-11, for the strict-parity mode.
+// SPLIT3 ("3xTF32"): operands arrive as full fp32; four extra warps split every staged tile into hi = fp32 truncated to
+// TF32 and lo = x - hi (exact), and each k-step issues hi*hi + hi*lo + lo*hi into the same accumulator: ~2^-19 relative
+// error instead of 2^-11, for the strict-parity mode. Round 1 kept all four split tiles in shared memory (224 KB of smem
+// traffic per 128 x 128 x 32 k-block: TMA 32 + split 96 + twelve MMAs reading both operands 96), which bound the mode at
+// ~100 TFLOP/s. Now the A operand is a TENSOR-MEMORY operand (tcgen05.mma "TS" form): a splitter thread reads its row of
+// the raw A tile once (8 x LDS.128) and writes hi / lo straight into two 32-column TMEM slabs with tcgen05.st; the MMAs
+// read A from TMEM and only B (the raw tile as hi, lo beside it) from shared memory: 128 KB per k-block, and the stage shrinks
+// from 64 to 48 KB (3 stages instead of 2 at block_n 128).
 // OUT16: output (and residual) tensors are fp16; the epilogue then works in chunks of 64 columns (= one 128-byte
 // swizzle row of halves) instead of 32.
 // Programmatic dependent launch: the prologue (barrier init, TMEM allocation, descriptor prefetch) runs before
@@ -166,8 +172,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using L = SmemLayout<BN, STAGES, MODE>;
   // accumulators: two ping-pong buffers (+ a master accumulator in 3xTF32 mode, see kSegLen)
   constexpr uint32_t kAccBufs = SPLIT3 ? 3 : 2;
-  constexpr uint32_t kTmemCols = (kAccBufs * BN <= 64) ? 64 : (kAccBufs * BN <= 128) ? 128 : (kAccBufs * BN <= 256) ? 256 : 512;
+  // 3xTF32: three accumulators + two A slabs of 64 columns (hi: 32 columns of K, lo: the next 32)
+  constexpr uint32_t kNeedCols = kAccBufs * BN + (SPLIT3 ? 128 : 0);
+  static_assert(kNeedCols <= 512, "accumulators + A slabs exceed the 512 TMEM columns");
+  constexpr uint32_t kTmemCols = (kNeedCols <= 64) ? 64 : (kNeedCols <= 128) ? 128 : (kNeedCols <= 256) ? 256 : 512;
   constexpr uint32_t kAccStride = SPLIT3 ? BN : kTmemCols / 2;
+  constexpr uint32_t kASlab = 3 * BN;        // first column of A slab 0 (3xTF32); slab s at + 64 s
   // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
   // accumulation chain (measured ~1e-3 relative after 3000 k-blocks; ~2e-5 after 32, which the chaotic position
   // embedding of the relation module amplifies to 5e-3 on the final logits). The strict mode therefore restarts the
@@ -184,7 +194,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full_bar = split_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint64_t* res_bar = tmem_empty_bar + 2;         // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 8);
+  uint64_t* aslab_empty_bar = res_bar + 8;        // [2] (3xTF32: the MMAs that read A slab s have completed)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aslab_empty_bar + 2);
   int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -211,6 +222,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tmem_empty_bar[b], 4);
     }
     for (int b = 0; b < 8; ++b) mbar_init(&res_bar[b], 1);
+    for (int b = 0; b < 2; ++b) mbar_init(&aslab_empty_bar[b], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -277,6 +289,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int t;
       int kb0, kb1;
       int item = 0;
+      uint32_t kbn = 0;            // k-blocks issued by this CTA (3xTF32: A slab = kbn & 1)
       while (it.next(t, kb0, kb1)) {
         for (int s0 = kb0, s1 = 0; s0 < kb1; s0 = s1, ++item) {
           s1 = (kb1 - s0 > kSegLen) ? s0 + kSegLen : kb1;
@@ -285,25 +298,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);   // epilogue drained this accumulator
           tc_fence_after();
           const uint32_t tmem_d = tmem_base + buf * kAccStride;
-          for (int kb = s0; kb < s1; ++kb) {
+          for (int kb = s0; kb < s1; ++kb, ++kbn) {
             mbar_wait(SPLIT3 ? &split_bar[stage] : &full_bar[stage], phase);
             tc_fence_after();
             const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
             const uint32_t b_addr = a_addr + L::kABytes;
             const uint64_t adesc = umma_desc_sw128(a_addr);
             const uint64_t bdesc = umma_desc_sw128(b_addr);
+            if (SPLIT3) {
+              // A from tensor memory: slab (kbn & 1), hi in its columns [0, 32), lo in [32, 64); 8 columns of K per MMA
+              const uint32_t a_hi = tmem_base + kASlab + (kbn & 1u) * 64u, a_lo = a_hi + 32u;
+              const uint64_t blo = umma_desc_sw128(b_addr + L::kBBytes);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              // advance 32 B (8 floats / 16 halves) inside the swizzle row: +2 in 16-byte units
-              if (MODE == kModeF16) {
-                umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
-              } else {
-                umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                umma_tf32_ts(tmem_d, a_hi + 8 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+                umma_tf32_ts(tmem_d, a_hi + 8 * k, blo + 2 * k, idesc, 1u);
+                umma_tf32_ts(tmem_d, a_lo + 8 * k, bdesc + 2 * k, idesc, 1u);
               }
-              if (SPLIT3) {
-                const uint64_t alo = umma_desc_sw128(a_addr + L::kHalf), blo = umma_desc_sw128(b_addr + L::kHalf);
-                umma_tf32(tmem_d, adesc + 2 * k, blo + 2 * k, idesc, 1u);
-                umma_tf32(tmem_d, alo + 2 * k, bdesc + 2 * k, idesc, 1u);
+              umma_commit(&aslab_empty_bar[kbn & 1u]);   // the splitter may overwrite this A slab
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                // advance 32 B (8 floats / 16 halves) inside the swizzle row: +2 in 16-byte units
+                if (MODE == kModeF16) {
+                  umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+                } else {
+                  umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+                }
               }
             }
             umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
@@ -319,28 +340,63 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 6) {
     // ===================== operand splitter (3xTF32 only, warps 6..9) =====================
     if (SPLIT3) {
-      const int stid = threadIdx.x - kThreads;
+      const int stid = threadIdx.x - kThreads;            // 0..127
+      const int arow = (warp & 3) * 32 + lane;            // the A-tile row = TMEM lane this thread may write
+      const uint32_t lane_bits = static_cast<uint32_t>((warp & 3) * 32) << 16;
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t kbn = 0;
       WorkIter it(p, cta, grid);
       int t;
       int kb0, kb1;
       while (it.next(t, kb0, kb1)) {
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb, ++kbn) {
           mbar_wait(&full_bar[stage], phase);
           uint8_t* base = smem + stage * L::kStageBytes;
-          constexpr int kVecs = L::kHalf / 16;
-#pragma unroll 4
-          for (int v = stid; v < kVecs; v += 128) {
-            const float4 x = *reinterpret_cast<const float4*>(base + v * 16);
-            float4 hi, lo;
-            hi.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); lo.x = x.x - hi.x;
-            hi.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u); lo.y = x.y - hi.y;
-            hi.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); lo.z = x.z - hi.z;
-            hi.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u); lo.w = x.w - hi.w;
-            *reinterpret_cast<float4*>(base + v * 16) = hi;
-            *reinterpret_cast<float4*>(base + L::kHalf + v * 16) = lo;
+          // ---- A: this thread's row (32 floats = 128 bytes, 16-byte chunks swizzled by row & 7) -> hi / lo -> TMEM
+          {
+            const uint8_t* rowp = base + arow * 128;
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = *reinterpret_cast<const float4*>(rowp + ((j ^ (arow & 7)) << 4));
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t h = __float_as_uint(xs[e]) & 0xffffe000u;
+                hi[4 * j + e] = h;
+                lo[4 * j + e] = __float_as_uint(xs[e] - __uint_as_float(h));
+              }
+            }
+            const uint32_t slab = kbn & 1u;
+            // the MMAs of k-block kbn - 2 (the previous user of this slab) have completed
+            if (kbn >= 2) mbar_wait(&aslab_empty_bar[slab], ((kbn >> 1) - 1) & 1u);
+            tc_fence_after();
+            const uint32_t ta = tmem_base + kASlab + slab * 64u + lane_bits;
+            __syncwarp();
+            tmem_st_32x32(ta, hi);
+            tmem_st_32x32(ta + 32u, lo);
           }
+          // ---- B: lo = x - trunc_tf32(x) into the region behind the raw tile. The raw tile itself serves as the hi
+          //      operand: kind::tf32 reads the upper 19 bits of a 32-bit container and IGNORES the low 13 mantissa bits
+          //      (truncation, not rounding -- measured with tools/tf32_trunc_probe.py: (1 + 0.75 * 2^-10) * 1 = 1.0 on
+          //      both operand sides), so writing the masked copy back would only cost shared-memory bandwidth
+          {
+            uint8_t* bb = base + L::kABytes;
+            constexpr int kVecs = L::kBBytes / 16;
+#pragma unroll 4
+            for (int v = stid; v < kVecs; v += 128) {
+              const float4 x = *reinterpret_cast<const float4*>(bb + v * 16);
+              float4 l;
+              l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+              l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+              l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+              l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+              *reinterpret_cast<float4*>(bb + L::kBBytes + v * 16) = l;
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(&split_bar[stage]);

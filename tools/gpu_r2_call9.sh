@@ -30,12 +30,14 @@ except Exception as e:
     print("$a: no line", e); print(open("gpurun_out/r2_c9_bench_$a.err").read()[-1500:])
 PY
 done
-# launch list of one steady step at 4 key frames per step (graphs off so every kernel is a launch): shares, not absolutes
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_c9_launches_f16_fps4.csv \
-  python bench.py --steps 1 --warmup 1 --precision f16 --no-parity --skip-cpu-baseline --skip-roofline --no-graph --prime 0 > gpurun_out/r2_c9_ncu_list.log 2>&1
+# launch list of one steady step at 4 key frames per step (profiler on for that step only): shares, not absolutes
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_c9_launches_f16_fps4.csv \
+  python tools/ncu_chain.py --fps 4 --step > gpurun_out/r2_c9_ncu_list.log 2>&1
 tail -1 gpurun_out/r2_c9_ncu_list.log | cut -c1-200
-# full capture (source-level) of the 190-layer backbone chain of a step (the 13th+ conv_chain launch: after start_video's 2-image chains)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_chain_kernel -s 120 -c 3 -o gpurun_out/r2_c9_chain_fps4 \
-  python bench.py --steps 1 --warmup 1 --precision f16 --no-parity --skip-cpu-baseline --skip-roofline --no-graph --prime 0 > gpurun_out/r2_c9_ncu_full.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r2_c9_launches_fp32x3_fps4.csv \
+  python tools/ncu_chain.py --fps 4 --step --precision fp32x3 > gpurun_out/r2_c9_ncu_list_strict.log 2>&1
+# full capture (source-level) of the 190-layer backbone chain of a step
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r2_c9_chain_fps4 \
+  python tools/ncu_chain.py --fps 4 > gpurun_out/r2_c9_ncu_full.log 2>&1
 tail -2 gpurun_out/r2_c9_ncu_full.log | cut -c1-200
 ls -la gpurun_out/*.ncu-rep; du -sh gpurun_out
