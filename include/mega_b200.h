@@ -92,6 +92,12 @@ typedef struct mega_conv_gemm_desc {
                                            out_ld * out_w * out_h) -- lets a conv write every other pixel of a larger
                                            map (the four parity classes of a stride-2 transposed convolution) */
   long long res_stride_h, res_stride_n; /* same for the residual */
+  /* ABI v5 (zero = previous behaviour): precision 1 only. b_lo_tap_off = taps_r * taps_s says that the low parts of the
+   * 3xTF32 split of B, lo = b - trunc_tf32(b), are stored BEHIND b as taps more [rows][k] slices (b then holds 2 * taps
+   * slices): the kernel fetches them by TMA instead of splitting the staged B tile on every k-block -- for weights, which
+   * never change (mega_core.b200.ops.presplit builds the pair once). */
+  int b_lo_tap_off;
+  int reserved_v5;
 } mega_conv_gemm_desc;
 
 int mega_conv_gemm(const mega_conv_gemm_desc* desc, void* stream);

@@ -147,10 +147,14 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   }
   {
     const int taps = d->taps_r * d->taps_s;
+    MEGA_ARG_CHECK(d->b_lo_tap_off == 0 || (strict && d->b_lo_tap_off == taps && d->batch == 1),
+                   "conv_gemm: b_lo_tap_off (%d) needs precision 1, batch 1 and must equal taps_r * taps_s (%d)",
+                   d->b_lo_tap_off, taps);
     cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d->b_k), static_cast<cuuint64_t>(d->b_n),
-                          static_cast<cuuint64_t>(taps)};
+                          static_cast<cuuint64_t>(taps + d->b_lo_tap_off)};
     cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d->b_stride_n) * esz,
-                          static_cast<cuuint64_t>(taps > 1 ? d->b_stride_tap : d->b_stride_n * d->b_n) * esz};
+                          static_cast<cuuint64_t>((taps > 1 || d->b_lo_tap_off) && d->b_stride_tap > 0
+                                                      ? d->b_stride_tap : d->b_stride_n * d->b_n) * esz};
     cuuint32_t box[3] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(d->block_n), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tmB, dt, 3, const_cast<void*>(d->b), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -245,6 +249,7 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   p.total_tiles = tiles;
   p.stream_k = d->stream_k ? 1 : 0;
   p.seg_len = g_seg_len;
+  p.b_lo_tap_off = d->b_lo_tap_off;
   MEGA_ARG_CHECK(tiles <= kCounterSlots, "conv_gemm: %lld output tiles exceed the %d counter slots", tiles, kCounterSlots);
   MEGA_ARG_CHECK(p.total_units > 0, "conv_gemm: empty problem");
   MEGA_ARG_CHECK(p.total_units * kMaxCtas < (1LL << 31), "conv_gemm: %lld work units exceed the 32-bit work-list range",

@@ -58,6 +58,7 @@ struct ConvGemmParams {
   float* part_ws;            // [grid][2][128][BN] partial accumulators
   int* counters;             // [tiles], zero between launches
   int seg_len;               // 3xTF32 only: k-blocks accumulated in TMEM before the RN fold into the master accumulator
+  int b_lo_tap_off;          // 3xTF32 only: > 0: B's low parts are stored as taps [b_lo_tap_off, 2 * b_lo_tap_off) of the B tensor
 };
 
 template <int BN, int STAGES, int MODE = kModeTf32>
@@ -257,12 +258,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * L::kStageBytes;
+          const bool b_lo_ready = SPLIT3 && p.b_lo_tap_off > 0;    // pre-split weights: the low parts come by TMA too
           if (lane == 0) {
-            mbar_arrive_expect_tx(&full_bar[stage], L::kHalf);   // bytes delivered by the two TMA loads
+            mbar_arrive_expect_tx(&full_bar[stage], L::kHalf + (b_lo_ready ? L::kBBytes : 0));   // bytes the TMA loads deliver
             tma_load_4d(a_dst, &tmA, &full_bar[stage], kc * kBK + a_c0, tc.w0 * p.stride_w + sx * p.dil - p.pad_w,
                         tc.h0 * p.stride_h + r * p.dil - p.pad, a_n);
           } else {
             tma_load_3d(a_dst + L::kABytes, &tmB, &full_bar[stage], kc * kBK + b_k0, b_n, tap);
+            if (b_lo_ready)
+              tma_load_3d(a_dst + L::kABytes + L::kBBytes, &tmB, &full_bar[stage], kc * kBK + b_k0, b_n, tap + p.b_lo_tap_off);
           }
           if (++kc == k_chunks) {
             kc = 0;
@@ -381,7 +385,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           //      operand: kind::tf32 reads the upper 19 bits of a 32-bit container and IGNORES the low 13 mantissa bits
           //      (truncation, not rounding -- measured with tools/tf32_trunc_probe.py: (1 + 0.75 * 2^-10) * 1 = 1.0 on
           //      both operand sides), so writing the masked copy back would only cost shared-memory bandwidth
-          {
+          if (p.b_lo_tap_off == 0) {      // (pre-split weights: the producer fetched lo by TMA, nothing to do for B)
             uint8_t* bb = base + L::kABytes;
             constexpr int kVecs = L::kBBytes / 16;
 #pragma unroll 4

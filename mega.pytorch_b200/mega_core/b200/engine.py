@@ -604,6 +604,24 @@ class WindowedEngine(HeadCommon):
         self._fc0(pooled, x)
         return x, boxes, cnt, spans
 
+    def _presplit_weights(self):
+        """strict mode: every weight that serves as a B operand gets its 3xTF32 low part stored behind it once
+        (ops.presplit), so the kernels stop re-splitting the same weight tile on every k-block of every launch"""
+        if self.cfg.precision != "fp32x3" or self.dev.type != "cuda":
+            return
+        for stages in (self.backbone.stages, self.res5):
+            for blocks in stages.stages:
+                for blk in blocks:
+                    for name in ("w1", "w2", "w3", "wd"):
+                        if getattr(blk, name, None) is not None:
+                            setattr(blk, name, ops.presplit(getattr(blk, name)))
+        self.backbone.stem_wr = ops.presplit(self.backbone.stem_wr)
+        self.rpn_w, self.rpn_hw, self.pred_w = ops.presplit(self.rpn_w), ops.presplit(self.rpn_hw), ops.presplit(self.pred_w)
+        self.fc0_w = ops.presplit(self.fc0_w)
+        self.fc_w = [None if w is None else ops.presplit(w) for w in self.fc_w]
+        for att in list(getattr(self, "att_l", [])) + list(getattr(self, "att_g", [])) + list(getattr(self, "att", [])):
+            att.wq, att.wk = ops.presplit(att.wq), ops.presplit(att.wk)      # (wv is an A operand: V'^T = Wv . refs^T)
+
     # ---- the reference's sub-module calls (model.backbone / model.rpn / feature_extractor(pre_calculate=True),
     #      generalized_rcnn_mega.py:145-158) served piecewise, for callers that drive the parts themselves
     def to_nhwc(self, feats_nchw):
@@ -785,6 +803,7 @@ class MegaEngine(WindowedEngine, WavefrontMixin):
         self.idx_qin0 = torch.tensor(q_idx, dtype=torch.int32, device=dev)
         self._aranges = {"KP": np.arange(KP, dtype=np.int32), "R": np.arange(R, dtype=np.int32),
                          "A": np.arange(A, dtype=np.int32)}
+        self._presplit_weights()
         self._init_window_state()
         self.reset()
 
@@ -1198,6 +1217,7 @@ class RdnEngine(WindowedEngine):
         self.tab_h = self._tab_ring[0]
         self.tab_d = z(off, dtype=torch.int32)
         self.payload = z(KP * (D * (2 if act == torch.float16 else 4) // 4) + KP * 4 + 4)
+        self._presplit_weights()
         self._init_window_state()
         self.reset()
 

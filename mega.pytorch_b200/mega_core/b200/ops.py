@@ -1,5 +1,6 @@
 """Python wrappers (pointer plumbing only) around the C-ABI kernels."""
 import ctypes
+import weakref
 
 import torch
 
@@ -215,6 +216,28 @@ class precision(object):
         return False
 
 
+# ---- strict mode (3xTF32): weights split ONCE. presplit(w) returns a tensor equal to w whose storage continues with the
+#      low parts lo = w - trunc_tf32(w) (as `taps` more [rows, K] slices); conv_gemm recognises it by its address and lets
+#      the kernel fetch lo by TMA instead of splitting the staged weight tile on every k-block of every launch.
+_PRESPLIT = {}
+
+
+def presplit(w):
+    """w: contiguous fp32 CUDA weight [rows, K] or [taps, rows, K] -> the same values as a view of a [2 * taps, rows, K]
+    tensor whose second half holds the low parts of the 3xTF32 split"""
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() in (2, 3)
+    w3 = w if w.dim() == 3 else w.view(1, *w.shape)
+    taps = w3.shape[0]
+    combo = torch.empty(2 * taps, w3.shape[1], w3.shape[2], device=w.device, dtype=torch.float32)
+    combo[:taps].copy_(w3)
+    hi = (w3.view(torch.int32) & -8192).view(torch.float32)            # truncation to TF32: clear the low 13 mantissa bits
+    combo[taps:].copy_(w3 - hi)
+    out = combo[:taps] if w.dim() == 3 else combo[0]
+    # keyed by address, valid while the returned tensor lives (a freed weight's address may be handed to an activation)
+    _PRESPLIT[out.data_ptr()] = (weakref.ref(out), taps, tuple(w3.shape[1:]))
+    return out
+
+
 # ---- per-shape kernel configuration (block_n, stream_k, max_ctas), filled by autotune()
 TUNED = {}
 AUTOTUNE = [False]
@@ -421,6 +444,14 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.out_c_off, d.out_n_off, d.res_c_off, d.res_n_off = out_c_off, out_n_off, res_c_off, res_n_off
     d.bias_z_off = bias_z_off
     d.max_ctas = max_ctas
+    if d.precision == 1 and batch == 1:
+        ps = _PRESPLIT.get(w.data_ptr())
+        if ps is not None and ps[0]() is None:
+            del _PRESPLIT[w.data_ptr()]
+            ps = None
+        if ps is not None and ps[1] == t and ps[2] == (rows, kk) and w.stride(1) == kk:
+            d.b_lo_tap_off = t
+            d.b_stride_tap = rows * kk
     ws = gemm_workspace(a.device)
     d.workspace = ptr(ws)
     d.workspace_bytes = ws.numel()

@@ -307,6 +307,39 @@ def test_f16_layer_chain_matches_per_layer_launches(cuda_dev):
     assert _rel_err(y_ch.float(), x.float()) < 1e-2      # fp16 storage of 9 chained layers
 
 
+def test_fp32x3_presplit_weights_are_bit_identical(cuda_dev):
+    """strict mode with the weights' low parts stored behind them once (ops.presplit: the kernel fetches lo by TMA,
+    mega_conv_gemm_desc.b_lo_tap_off) against the same launches splitting the staged weight tile on the fly: identical bits,
+    for a 3x3 convolution (9 taps), a Linear (1 tap, rows not a multiple of the tile) and a stream-K deep reduction"""
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 19, 31, 96, generator=g).to(cuda_dev)
+    w = (torch.randn(9, 160, 96, generator=g) / 30).to(cuda_dev)
+    xl = torch.randn(300, 1024, generator=g).to(cuda_dev)
+    wl = (torch.randn(155, 1024, generator=g) / 32).to(cuda_dev)
+    bias = torch.randn(160, generator=g).to(cuda_dev)
+    with ops.precision("fp32x3"):
+        for bn, sk in ((64, 0), (128, 1)):
+            ref = torch.zeros(2, 19, 31, 160, device=cuda_dev)
+            ops.conv_gemm(x, w, ref, taps=(3, 3), pad=1, bias=bias, relu=True, block_n=bn, stream_k=sk)
+            wp = ops.presplit(w)
+            assert torch.equal(wp, w) and wp.data_ptr() != w.data_ptr()
+            got = torch.zeros_like(ref)
+            ops.conv_gemm(x, wp, got, taps=(3, 3), pad=1, bias=bias, relu=True, block_n=bn, stream_k=sk)
+            torch.cuda.synchronize()
+            assert torch.equal(got, ref), (bn, sk, (got - ref).abs().max())
+            refl = torch.zeros(300, 156, device=cuda_dev)
+            ops.linear(xl, wl, refl[:, :155], block_n=bn, stream_k=sk)
+            wlp = ops.presplit(wl)
+            gotl = torch.zeros_like(refl)
+            ops.linear(xl, wlp, gotl[:, :155], block_n=bn, stream_k=sk)
+            torch.cuda.synchronize()
+            assert torch.equal(gotl, refl), (bn, sk)
+    ref64 = F.conv2d(x.double().cpu().permute(0, 3, 1, 2), w.double().cpu().reshape(3, 3, 160, 96).permute(2, 3, 0, 1), padding=1)
+    ref64 = (ref64 + bias.double().cpu().view(1, -1, 1, 1)).relu().permute(0, 2, 3, 1)
+    assert _rel_err(got.cpu(), ref64.float()) < 1e-5
+
+
 def test_f16_interleaved_chain_matches_per_layer_launches(cuda_dev):
     """barrier depth 2 (ops.chain(interleave=True)): the res4 pattern on the two halves of a batch of four 38 x 63 maps as
     two interleaved lanes A0 B0 A1 B1 ... of ONE chain kernel, every layer waiting only for the layer two positions back.

@@ -1,0 +1,16 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --no-header -rf -x > gpurun_out/r2_c12_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2_c12_pytest.log; tail -4 gpurun_out/r2_c12_pytest.log
+timeout 200 python tools/strict_gemm_probe.py > gpurun_out/r2_c12_strict_gemm.log 2>&1; cat gpurun_out/r2_c12_strict_gemm.log
+timeout 300 python tools/strict_probe.py 2 > gpurun_out/r2_c12_strict.log 2>&1; grep seg_len gpurun_out/r2_c12_strict.log
+timeout 300 python bench.py --steps 10 --warmup 3 --precision fp32x3 --no-parity --skip-cpu-baseline > gpurun_out/r2_c12_bench_strict.json 2> gpurun_out/r2_c12_bench_strict.err
+python - <<PY
+import json
+try:
+    l = [x for x in open("gpurun_out/r2_c12_bench_strict.json").read().splitlines() if x.startswith("{")][-1]
+    d = json.loads(l); print("strict fps4:", "value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1), "roof", round(d["roofline"]["frac"], 3))
+except Exception as e:
+    print("no line", e); print(open("gpurun_out/r2_c12_bench_strict.err").read()[-1500:])
+PY
+cp gpurun_out/launch_times_fp32x3.json gpurun_out/r2_c12_launch_times_fp32x3.json 2>/dev/null

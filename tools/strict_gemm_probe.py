@@ -1,0 +1,49 @@
+"""Three representative contractions of the strict (3xTF32, A operand in TMEM) mode at the sizes of a 4-key-frame step
+(8 images of 600x1000), timed with CUDA events and -- under `ncu --profile-from-start off` -- profiled one launch each:
+res4 3x3 (K = 2304 -> 256), RPN head 3x3 (K = 9216 -> 1024), res4 1x1 expand (K = 256 -> 1024, residual).
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/strict python tools/strict_gemm_probe.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "mega.pytorch_b200"))
+import torch  # noqa: E402
+
+from mega_core.b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(0)
+n, h, w = 8, 38, 63
+ops.load_tuned(os.path.join(ROOT, "mega.pytorch_b200", "mega_core", "b200", "tuned_b200.json"))
+ops.AUTOTUNE[0] = True
+
+
+def mk(*s):
+    return (torch.randn(*s, generator=g) * 0.5).to(dev)
+
+
+x256, x1024 = mk(n, h, w, 256), mk(n, h, w, 1024)
+w33, wrpn, wexp = mk(9, 256, 256) * 0.05, mk(9, 1024, 1024) * 0.02, mk(1, 1024, 256) * 0.1
+o256, o1024, o1024b = torch.zeros(n, h, w, 256, device=dev), torch.zeros(n, h, w, 1024, device=dev), torch.zeros(n, h, w, 1024, device=dev)
+sc, bi = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
+cases = [("res4 3x3 256->256", lambda: ops.conv_gemm(x256, w33, o256, taps=(3, 3), pad=1, scale=sc[:256], bias=bi[:256], relu=True), 2 * n * h * w * 256 * 2304),
+         ("rpn 3x3 1024->1024", lambda: ops.conv_gemm(x1024, wrpn, o1024, taps=(3, 3), pad=1, bias=bi, relu=True), 2 * n * h * w * 1024 * 9216),
+         ("res4 1x1 256->1024 + residual", lambda: ops.conv_gemm(x256, wexp, o1024b, scale=sc, bias=bi, residual=x1024, relu=True), 2 * n * h * w * 1024 * 256)]
+with ops.precision("fp32x3"):
+    for name, fn, flops in cases:
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(10):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        print("%-32s %8.1f us  %7.1f GFLOP  %6.1f TFLOP/s (x3 MMAs: %6.1f executed)" % (name, ms * 1e3, flops / 1e9, flops / ms / 1e9, 3 * flops / ms / 1e9))
+    torch.cuda.profiler.start()
+    for name, fn, flops in cases:
+        fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
