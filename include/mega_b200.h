@@ -32,8 +32,14 @@ int mega_device_ok(void);
 /* ------------------------------------------------- dense contractions (tcgen05)
  * Implicit-GEMM convolution / GEMM on the tensor cores, FP32 accumulation in TMEM. Operand arithmetic is selected
  * by `precision`: 0 = fp32 tensors rounded to TF32 on load, 1 = fp32 tensors, 3xTF32 split (near-fp32), 2 = fp16
- * tensors (same 10-bit mantissa as TF32, half the bytes, twice the tensor-pipe rate); the output / residual are
- * fp32, or fp16 when out_f16 != 0 (precision 2 only).
+ * tensors (same 10-bit mantissa as TF32, half the bytes, twice the tensor-pipe rate), 3 = "3xFP16": operands in the
+ * SPLIT-FP16 format (below; near-fp32 like 1, kind::f16 MMAs, no split work in the kernel); the output / residual are
+ * fp32, or fp16 when out_f16 != 0 (precision 2), or split-fp16 (precision 3: out_f16 != 0 for the output, res_split != 0
+ * for the residual).
+ * SPLIT-FP16 format: a tensor with the shape, strides and byte size of an fp32 tensor whose innermost dimension is a
+ * multiple of 32; every aligned group of 32 consecutive values x[0..32) occupies its 128 bytes as 32 halves
+ * hi[i] = fp16_rn(x[i]) (saturating) followed by 32 halves lo[i] = fp16_rn(x[i] - hi[i]): |x - (hi + lo)| <= 2^-23 |x| for
+ * |x| >= 2^-3, <= 2^-25 below. mega_split16_pack / mega_split16_unpack convert from / to fp32.
  *   out[n,h,w,co] = act( scale[co] * sum_{r,s,ci} a[n, h + r*dil - pad, w + s*dil - pad, ci]
  *                                          * b[r*S+s, co, ci]  + bias[co] + residual[n,h,w,co] )
  * Replaces: ATen/cuDNN conv2d + FrozenBatchNorm2d + add + relu_ of
@@ -75,7 +81,8 @@ typedef struct mega_conv_gemm_desc {
    * its counter region zero) holds the tile counters and the partial accumulators of tiles whose
    * K range is shared by several CTAs. Launches that may run concurrently need distinct workspaces. */
   int precision; /* 0: TF32 operands (round-to-nearest on load); 1: "3xTF32" split (hi*hi + hi*lo + lo*hi),
-                    ~2^-19 relative error, block_n 64 or 128; 2: fp16 operands (A and B are __half arrays) */
+                    ~2^-19 relative error, block_n 64 or 128; 2: fp16 operands (A and B are __half arrays);
+                    3: "3xFP16": A and B in the split-fp16 format, hi*hi + hi*lo + lo*hi with kind::f16 MMAs */
   int max_ctas;
   int stream_k; /* 1: split tiles across CTAs at k-block granularity (balances any tile count over the
                    SMs; partial tiles are reduced by the last CTA to arrive, in CTA order); 0: whole tiles */
@@ -97,9 +104,20 @@ typedef struct mega_conv_gemm_desc {
    * slices): the kernel fetches them by TMA instead of splitting the staged B tile on every k-block -- for weights, which
    * never change (mega_core.b200.ops.presplit builds the pair once). */
   int b_lo_tap_off;
-  int reserved_v5;
+  /* ABI v6 (zero = previous behaviour): precision 3 only. a, b: split-fp16 tensors (a_c, b_k, k_per_tap, a_c_off, b_k_off
+   * multiples of 32; block_n 64 or 128). out_f16 != 0: split-fp16 output (cout, out_c_off multiples of 32), else fp32.
+   * res_split != 0: the residual is split-fp16, else fp32. acc_scale: 0 = 1; otherwise the accumulator is multiplied by it
+   * before scale / bias -- weights are stored multiplied by a power of two 1 / acc_scale so that their low halves stay
+   * normal fp16 numbers (mega_core.b200.ops.pack_weights_split16). */
+  int res_split;
+  float acc_scale;
+  int reserved_v6;
 } mega_conv_gemm_desc;
 
+/* fp32 <-> split-fp16 (format above) over n_values contiguous values (multiple of 32, 128-byte aligned); pack may run in
+ * place (dst == src). New in this build (no reference counterpart: the reference computes in fp32 throughout). */
+int mega_split16_pack(const float* src, void* dst, long long n_values, void* stream);
+int mega_split16_unpack(const void* src, float* dst, long long n_values, void* stream);
 int mega_conv_gemm(const mega_conv_gemm_desc* desc, void* stream);
 /* ABI v1 name of mega_conv_gemm (kept for existing callers) */
 int mega_conv_gemm_tf32(const mega_conv_gemm_desc* desc, void* stream);
@@ -193,6 +211,13 @@ int mega_roi_align_forward_nhwc_f16(const void* input, int channels, int height,
                                     const float* rois, int roi_ld, int roi_box_off, const int* roi_batch,
                                     int num_rois, float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
                                     void* output, long long out_roi_stride, void* stream);
+/* ROIAlign over a split-fp16 NHWC map into split-fp16 rows (the strict engine's storage format, see mega_conv_gemm_desc):
+ * separable kernel, channels % 128 == 0, bins <= 7 x 7, map <= 64 x 64 cells (MEGA_ERR_ARG otherwise). fp32 blends with
+ * fused multiply-adds: equal to layers/roi_align.py:13-36 / ROIAlign_cuda.cu:62-115 to ~1e-6 relative, not bit for bit. */
+int mega_roi_align_forward_nhwc_split16(const void* input, int channels, int height, int width, long long in_img_stride,
+                                        const float* rois, int roi_ld, int roi_box_off, const int* roi_batch,
+                                        int num_rois, float spatial_scale, int pooled_h, int pooled_w, int sampling_ratio,
+                                        void* output, long long out_roi_stride, void* stream);
 
 /* --------------------------------------------------------- backbone helpers
  * stem_im2col: NCHW image [N,3,H,W] -> [N, Ho*Wo, kpad] rows (k = c*49 + r*7 + s, zero padded) for

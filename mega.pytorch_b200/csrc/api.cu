@@ -13,7 +13,7 @@ void mega_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* mega_last_error(void) { return g_err; }
-extern "C" int mega_abi_version(void) { return 5; }
+extern "C" int mega_abi_version(void) { return 6; }
 extern "C" int mega_device_ok(void) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;

@@ -283,6 +283,12 @@ __device__ __forceinline__ uint32_t f2_to_h2(float lo, float hi) {
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// same, saturating to the largest finite half instead of inf
+__device__ __forceinline__ uint32_t f2_to_h2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ float2 h2_to_f2(uint32_t h) {
   float2 f;
   asm("{\n.reg .b16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}" : "=f"(f.x), "=f"(f.y) : "r"(h));

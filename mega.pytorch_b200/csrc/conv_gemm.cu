@@ -41,7 +41,7 @@ static EncodeTiledFn get_encode_fn() {
 static int g_tf32_round = 1;  // TMA converts fp32 -> tf32 (round to nearest) while loading
 
 static int g_num_sms = 0;
-static int g_seg_len = 2;      // 3xTF32: k-blocks per accumulator segment
+static int g_seg_len = 4;      // 3xTF32 / 3xFP16: k-blocks per accumulator segment (tools/strict_probe.py: 2 / 4 / 8 -> logits p99 1.8e-4 / 2.3e-4 / 5.3e-4)
 constexpr int kCounterSlots = 65536;   // ints at the head of the workspace
 constexpr int kMinUnits = 4;
 
@@ -73,11 +73,12 @@ namespace mega {
 int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, CUtensorMap* tmB_p, CUtensorMap* tmOut_p,
                              CUtensorMap* tmRes_p, ConvGemmParams* p_out, int* ctas_out) {
   MEGA_ARG_CHECK(d != nullptr, "conv_gemm: null descriptor");
-  MEGA_ARG_CHECK(d->precision >= 0 && d->precision <= 2,
-                 "conv_gemm: precision must be 0 (tf32), 1 (3xtf32) or 2 (fp16 operands)");
+  MEGA_ARG_CHECK(d->precision >= 0 && d->precision <= 3,
+                 "conv_gemm: precision must be 0 (tf32), 1 (3xtf32), 2 (fp16 operands) or 3 (3xfp16, split-fp16 operands)");
   const bool strict = d->precision == kModeSplit3;
   const bool f16 = d->precision == kModeF16;
-  const bool out16 = d->out_f16 != 0;
+  const bool pk = d->precision == kModeF16x3;  // split-fp16 tensors are addressed like fp32 tensors (4 bytes per value)
+  const bool out16 = d->out_f16 != 0 && !pk;
   const int esz = f16 ? 2 : 4;                 // operand element size
   const int osz = out16 ? 2 : 4;               // output / residual element size
   const int ealign = 16 / esz, oalign = 16 / osz;
@@ -117,9 +118,28 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
     mega_set_error("conv_gemm: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     return MEGA_ERR_CUDA;
   }
-  MEGA_ARG_CHECK(!strict || d->block_n == 64 || d->block_n == 128, "conv_gemm: 3xtf32 supports block_n 64 / 128");
+  MEGA_ARG_CHECK(!(strict || pk) || d->block_n == 64 || d->block_n == 128, "conv_gemm: 3xtf32 / 3xfp16 support block_n 64 / 128");
+  if (pk) {
+    MEGA_ARG_CHECK((d->a_c & 31) == 0 && (d->b_k & 31) == 0 && (d->k_per_tap & 31) == 0 && (d->a_c_off & 31) == 0 &&
+                       (d->b_k_off & 31) == 0,
+                   "conv_gemm: split-fp16 operands need channel counts / offsets in multiples of 32 (a_c %d, b_k %d, k %d)",
+                   d->a_c, d->b_k, d->k_per_tap);
+    // a ragged cout is rounded up to whole 32-value groups (the extra columns are computed from zero-filled B rows and must
+    // fit inside the row pitch); batched launches address whole groups only
+    const int cout_r = (d->cout + 31) & ~31;
+    MEGA_ARG_CHECK(d->out_f16 == 0 || ((d->out_c_off & 31) == 0 && (d->cout == cout_r || (d->batch == 1 && d->out_ld >= cout_r))),
+                   "conv_gemm: split-fp16 output needs cout (%d) in multiples of 32 (or batch 1 and a row pitch >= the rounded cout)", d->cout);
+    MEGA_ARG_CHECK(d->res_split == 0 || d->residual == nullptr ||
+                       ((d->res_c_off & 31) == 0 && (d->cout == cout_r || (d->batch == 1 && d->res_ld >= cout_r))),
+                   "conv_gemm: split-fp16 residual needs cout (%d) in multiples of 32", d->cout);
+    MEGA_ARG_CHECK((d->a_stride_w & 31) == 0 && (d->b_stride_n & 31) == 0 && (reinterpret_cast<uintptr_t>(d->a) & 127) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d->b) & 127) == 0,
+                   "conv_gemm: split-fp16 operands need 128-byte aligned rows");
+  } else {
+    MEGA_ARG_CHECK(d->res_split == 0, "conv_gemm: res_split needs precision 3");
+  }
   const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
-                                     : (g_tf32_round && !strict) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
+                                     : (g_tf32_round && !strict && !pk) ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32
                                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const CUtensorMapDataType odt = out16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
 
@@ -185,7 +205,9 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
       const long long ld = which == 0 ? d->out_ld : d->res_ld;
       const int c_off = which == 0 ? d->out_c_off : d->res_c_off;
       const int n_off = which == 0 ? d->out_n_off : d->res_n_off;
-      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->cout + (d->batch - 1) * c_off), static_cast<cuuint64_t>(d->out_w),
+      const bool split_fmt = pk && (which == 0 ? d->out_f16 != 0 : d->res_split != 0);
+      const int c_extent = split_fmt ? ((d->cout + 31) & ~31) : d->cout;
+      cuuint64_t gdim[4] = {static_cast<cuuint64_t>(c_extent + (d->batch - 1) * c_off), static_cast<cuuint64_t>(d->out_w),
                             static_cast<cuuint64_t>(d->out_h),
                             static_cast<cuuint64_t>(d->n_img + (d->batch - 1) * n_off)};
       const long long sh = which == 0 ? d->out_stride_h : d->res_stride_h;
@@ -250,6 +272,8 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   p.stream_k = d->stream_k ? 1 : 0;
   p.seg_len = g_seg_len;
   p.b_lo_tap_off = d->b_lo_tap_off;
+  p.res_split = d->res_split ? 1 : 0;
+  p.acc_scale = (pk && d->acc_scale != 0.f) ? d->acc_scale : 1.f;
   MEGA_ARG_CHECK(tiles <= kCounterSlots, "conv_gemm: %lld output tiles exceed the %d counter slots", tiles, kCounterSlots);
   MEGA_ARG_CHECK(p.total_units > 0, "conv_gemm: empty problem");
   MEGA_ARG_CHECK(p.total_units * kMaxCtas < (1LL << 31), "conv_gemm: %lld work units exceed the 32-bit work-list range",
@@ -293,6 +317,8 @@ extern "C" int mega_conv_gemm(const mega_conv_gemm_desc* d, void* stream_v) {
   const bool out16 = d->out_f16 != 0;
   dim3 grid(static_cast<unsigned>(ctas), 1, 1);
   const int pdl = d->pdl ? 1 : 0;
+  if (d->precision == kModeF16x3)
+    return launch_conv_gemm_f16x3(d->block_n, out16 ? 1 : 0, tmA, tmB, tmOut, tmRes, p, grid, stream, pdl);
   if (f16) return launch_conv_gemm_f16(d->block_n, out16 ? 1 : 0, tmA, tmB, tmOut, tmRes, p, grid, stream, pdl);
   if (strict) {
     return d->block_n == 64 ? launch_cfg<64, 4, kModeSplit3, false>(tmA, tmB, tmOut, tmRes, p, grid, stream, pdl)

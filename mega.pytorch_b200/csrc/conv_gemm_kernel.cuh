@@ -27,7 +27,12 @@ constexpr int kModeTf32 = 0;    // fp32 operands in HBM, rounded to TF32 by the 
 constexpr int kModeSplit3 = 1;  // "3xTF32": fp32 operands split hi/lo in shared memory
 constexpr int kModeF16 = 2;     // fp16 operands in HBM (10-bit mantissa like TF32, half the bytes, twice the
                                 // tensor-pipe rate); K slab = 64 halves
+constexpr int kModeF16x3 = 3;   // "3xFP16": operands stored SPLIT in HBM -- every group of 32 K-values is one 128-byte row
+                                // [32 hi halves | 32 lo halves] with hi = fp16(x), lo = fp16(x - hi): the same 4 bytes per
+                                // value as fp32 and 22 mantissa bits like 3xTF32, but NO split work in the kernel (the
+                                // producing epilogue / the weight packer did it) and kind::f16 MMAs; K slab = 32 values
 // every mode stages K slabs of 128 bytes per row (one swizzle row) and issues 4 MMAs of 32 bytes of K each
+// (3xFP16: 2 k-steps x 3 products over the hi / lo halves of the row)
 __host__ __device__ constexpr int mode_bk(int mode) { return mode == kModeF16 ? 64 : 32; }
 constexpr int kThreads = 192;   // 6 warps
 constexpr int kMaxCtas = 148;   // persistent grid: one CTA per SM
@@ -59,6 +64,9 @@ struct ConvGemmParams {
   int* counters;             // [tiles], zero between launches
   int seg_len;               // 3xTF32 only: k-blocks accumulated in TMEM before the RN fold into the master accumulator
   int b_lo_tap_off;          // 3xTF32 only: > 0: B's low parts are stored as taps [b_lo_tap_off, 2 * b_lo_tap_off) of the B tensor
+  int res_split;             // 3xFP16 only: the residual tensor is in the split-fp16 format (else fp32)
+  float acc_scale;           // 3xFP16 only: the accumulator is multiplied by this power of two first (weights are stored
+                             // scaled by its inverse so that their low halves stay normal fp16 numbers)
 };
 
 template <int BN, int STAGES, int MODE = kModeTf32>
@@ -166,25 +174,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                       const ConvGemmParams p) {
   constexpr bool SPLIT3 = MODE == kModeSplit3;
+  constexpr bool PK = MODE == kModeF16x3;       // split-fp16 operands; OUT16 then means "split-fp16 output" (else fp32)
+  constexpr bool SEG = SPLIT3 || PK;            // segmented accumulation with a round-to-nearest master accumulator
+  constexpr bool OUTH = OUT16 && !PK;           // plain fp16 output
   constexpr int kBK = mode_bk(MODE);
-  constexpr int CW = OUT16 ? 64 : 32;   // epilogue chunk: columns per 128-byte output row segment
-  static_assert(!OUT16 || BN % 64 == 0, "fp16 output needs block_n % 64 == 0");
+  constexpr int CW = OUTH ? 64 : 32;   // epilogue chunk: columns per 128-byte output row segment
+  static_assert(!OUTH || BN % 64 == 0, "fp16 output needs block_n % 64 == 0");
   static_assert(SmemLayout<BN, STAGES, MODE>::kTotal <= 227 * 1024, "pipeline + staging exceed the 227 KB of a CTA");
   using L = SmemLayout<BN, STAGES, MODE>;
   // accumulators: two ping-pong buffers (+ a master accumulator in 3xTF32 mode, see kSegLen)
-  constexpr uint32_t kAccBufs = SPLIT3 ? 3 : 2;
+  // 3xFP16 keeps the master accumulator in REGISTERS of the epilogue threads (one row x BN columns each; the mode has no
+  // splitter warps, so 192 threads share the register file): a fold then reads the segment from tensor memory once
+  // (64 B/cycle per SM: 0.54 us per 128 x 128 segment) instead of segment + master and writes nothing back
+  constexpr bool REGM = false;   // (measured with 4 epilogue warps: 6-10 % SLOWER than the TMEM master -- 255 registers, spills in the chunk loop)
+  constexpr uint32_t kAccBufs = (SEG && !REGM) ? 3 : 2;
   // 3xTF32: three accumulators + two A slabs of 64 columns (hi: 32 columns of K, lo: the next 32)
   constexpr uint32_t kNeedCols = kAccBufs * BN + (SPLIT3 ? 128 : 0);
   static_assert(kNeedCols <= 512, "accumulators + A slabs exceed the 512 TMEM columns");
   constexpr uint32_t kTmemCols = (kNeedCols <= 64) ? 64 : (kNeedCols <= 128) ? 128 : (kNeedCols <= 256) ? 256 : 512;
-  constexpr uint32_t kAccStride = SPLIT3 ? BN : kTmemCols / 2;
+  constexpr uint32_t kAccStride = (SEG && !REGM) ? BN : kTmemCols / 2;
   constexpr uint32_t kASlab = 3 * BN;        // first column of A slab 0 (3xTF32); slab s at + 64 s
   // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
   // accumulation chain (measured ~1e-3 relative after 3000 k-blocks; ~2e-5 after 32, which the chaotic position
   // embedding of the relation module amplifies to 5e-3 on the final logits). The strict mode therefore restarts the
   // TMEM accumulator every kSegLen k-blocks (4 k-blocks = 48 truncating adds, <= 3e-6 relative) and folds the segments into a master accumulator (also in TMEM)
   // with round-to-nearest fp32 adds done by the epilogue warps.
-  const int kSegLen = SPLIT3 ? p.seg_len : 0x7fffffff;   // k-blocks per accumulator segment (mega_set_split3_seg_len, default 4)
+  const int kSegLen = SEG ? p.seg_len : 0x7fffffff;   // k-blocks per accumulator segment (mega_set_split3_seg_len, default 4)
   extern __shared__ uint8_t smem_raw[];
   // the 128B swizzle pattern is a function of the absolute smem address: align to 1024 B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -286,7 +301,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = MODE == kModeF16 ? umma_idesc<0>(kBM, BN) : umma_idesc<2>(kBM, BN);
+      const uint32_t idesc = (MODE == kModeF16 || PK) ? umma_idesc<0>(kBM, BN) : umma_idesc<2>(kBM, BN);
       int stage = 0;
       uint32_t phase = 0;
       WorkIter it(p, cta, grid);
@@ -320,6 +335,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_tf32_ts(tmem_d, a_lo + 8 * k, bdesc + 2 * k, idesc, 1u);
               }
               umma_commit(&aslab_empty_bar[kbn & 1u]);   // the splitter may overwrite this A slab
+            } else if (PK) {
+              // a staged row = [32 hi halves | 32 lo halves] of 32 K-values: k-step j (16 values) reads hi at byte 32 j and
+              // lo at byte 64 + 32 j of the swizzle row (descriptor units of 16 bytes); hi.hi + hi.lo + lo.hi
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+                umma_f16(tmem_d, adesc + 2 * k, bdesc + 4 + 2 * k, idesc, 1u);
+                umma_f16(tmem_d, adesc + 4 + 2 * k, bdesc + 2 * k, idesc, 1u);
+              }
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -427,18 +451,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int item = 0;   // accumulator-segment counter (ping-pong bookkeeping shared with the MMA warp)
     const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t master_row = tmem_base + 2 * kAccStride + lane_bits;
+    float master[REGM ? BN : 1];      // (statically indexed everywhere: the loops over its chunks are fully unrolled)
     for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
       const TileCoord tc = decode_tile(p, t, BN);
       // ---- 3xTF32 only: fold every segment but the last into the master accumulator (RN fp32 adds)
       bool has_master = false;
       int s0 = kb0;
-      for (; SPLIT3 && s0 + kSegLen < kb1; s0 += kSegLen, ++item) {
+      for (; SEG && s0 + kSegLen < kb1; s0 += kSegLen, ++item) {
         const int fb = item & 1;
         mbar_wait(&tmem_full_bar[fb], static_cast<uint32_t>(item >> 1) & 1);
         tc_fence_after();
         const uint32_t seg_row = tmem_base + fb * kAccStride + lane_bits;
+        if (REGM) {
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            uint32_t a[32];
+            __syncwarp();
+            tmem_ld_32x32(seg_row + c * 32, a);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(a[j]);
+              master[REGM ? c * 32 + j : 0] = has_master ? __fadd_rn(v, master[REGM ? c * 32 + j : 0]) : v;
+            }
+          }
+        }
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = 0; !REGM && c < BN / 32; ++c) {
           uint32_t a[32];
           __syncwarp();
           tmem_ld_32x32(seg_row + c * 32, a);
@@ -452,7 +491,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           tmem_st_32x32(master_row + c * 32, a);
         }
-        tmem_st_wait();
+        if (!REGM) tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[fb]);
@@ -489,7 +528,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();  // tcgen05.ld is .sync.aligned
         tmem_ld_32x32(tmem_row + c * 32, acc);
         tmem_ld_wait();
-        if (SPLIT3 && has_master) {
+        if (REGM) {
+          if (has_master) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              acc[j] = __float_as_uint(__fadd_rn(__uint_as_float(acc[j]), master[REGM ? c * 32 + j : 0]));
+          }
+        } else if (SEG && has_master) {
           uint32_t m[32];
           tmem_ld_32x32(master_row + c * 32, m);
           tmem_ld_wait();
@@ -502,8 +547,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!complete) {
         // ---- publish this CTA's partial accumulator, then find out whether it arrived last
         float* my_ws = p.part_ws + ((static_cast<long long>(cta) * 2 + (tile_item == 0 ? 0 : 1)) * kBM + row) * BN;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        auto publish = [&](const int c) {
           uint32_t acc[32];
           load_acc(c, acc);
 #pragma unroll
@@ -512,6 +556,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                    __uint_as_float(acc[j + 2]), __uint_as_float(acc[j + 3]));
             __stcg(reinterpret_cast<float4*>(my_ws + c * 32 + j), v);
           }
+        };
+        if constexpr (REGM) {     // (register master: the chunk index must be a compile-time constant)
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) publish(c);
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) publish(c);
         }
         __threadfence();
         epi_bar_sync();
@@ -539,8 +590,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&rbar[0], 4096);
           tma_load_4d(epi_res, &tmRes, &rbar[0], tc.n0 + tc.batch * p.res_c_off, st_w, st_h, res_n);
         }
-#pragma unroll 1
-        for (int c = 0; c < nchunks; ++c) {
+        auto finish_chunk = [&](const int c) {
           const int nb = tc.n0 + c * CW;
           const uint8_t* rsrc = nullptr;
           if (p.has_residual) {
@@ -589,6 +639,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         #pragma unroll
               for (int j = 0; j < 32; ++j) acc[j] = sum[j];
             }
+            if (PK && p.acc_scale != 1.f) {
+        #pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] *= p.acc_scale;
+            }
             if (has_sb) {
               const float4* scv = reinterpret_cast<const float4*>(sb_s + col0);
               const float4* biv = reinterpret_cast<const float4*>(sb_s + L::kSbCols + col0);
@@ -600,7 +654,56 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             const float slope = p.relu == 2 ? 0.1f : 0.f;
-            if (OUT16) {
+            if (PK) {
+              // the residual and / or the output as split fp16: 16-byte chunk g (8 values) of the 32 columns holds the hi
+              // halves, chunk 4 + g their lo halves (same swizzle as the TMA box)
+              const bool res_split = p.res_split != 0;
+        #pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint32_t ch_hi = (static_cast<uint32_t>(j >> 3) ^ sw) << 4;
+                const uint32_t ch_lo = (static_cast<uint32_t>(4 + (j >> 3)) ^ sw) << 4;
+                float v[8];
+        #pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = acc[j + e];
+                if (rsrc) {
+                  if (res_split) {
+                    const uint4 rh = *reinterpret_cast<const uint4*>(rsrc + ch_hi);
+                    const uint4 rl = *reinterpret_cast<const uint4*>(rsrc + ch_lo);
+                    const uint32_t hs[4] = {rh.x, rh.y, rh.z, rh.w}, ls[4] = {rl.x, rl.y, rl.z, rl.w};
+        #pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 a2 = h2_to_f2(hs[e]), b2 = h2_to_f2(ls[e]);
+                      v[2 * e] += a2.x + b2.x;
+                      v[2 * e + 1] += a2.y + b2.y;
+                    }
+                  } else {
+                    // fp32 residual: values j .. j+7 are the 16-byte chunks j/4 and j/4 + 1 of the row
+                    const float4 r0v = *reinterpret_cast<const float4*>(rsrc + ((static_cast<uint32_t>(j >> 2) ^ sw) << 4));
+                    const float4 r1v = *reinterpret_cast<const float4*>(rsrc + ((static_cast<uint32_t>((j >> 2) + 1) ^ sw) << 4));
+                    v[0] += r0v.x; v[1] += r0v.y; v[2] += r0v.z; v[3] += r0v.w;
+                    v[4] += r1v.x; v[5] += r1v.y; v[6] += r1v.z; v[7] += r1v.w;
+                  }
+                }
+                if (p.relu) {
+        #pragma unroll
+                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], slope * v[e]);
+                }
+                if (OUT16) {
+                  uint32_t hh[4], ll[4];
+        #pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    hh[e] = f2_to_h2_sat(v[2 * e], v[2 * e + 1]);
+                    const float2 back = h2_to_f2(hh[e]);
+                    ll[e] = f2_to_h2_sat(v[2 * e] - back.x, v[2 * e + 1] - back.y);
+                  }
+                  *reinterpret_cast<uint4*>(dst + ch_hi) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                  *reinterpret_cast<uint4*>(dst + ch_lo) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                } else {
+                  *reinterpret_cast<float4*>(dst + ((static_cast<uint32_t>(j >> 2) ^ sw) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+                  *reinterpret_cast<float4*>(dst + ((static_cast<uint32_t>((j >> 2) + 1) ^ sw) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+              }
+            } else if (OUTH) {
               // 64 halves per staging row: 16-byte groups of 8 halves, swizzled like the TMA box
         #pragma unroll
               for (int j = 0; j < 32; j += 8) {
@@ -646,6 +749,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_4d(&tmOut, epi_out + (c & 1) * 4096, nb + tc.batch * p.out_c_off, st_w, st_h, out_n);
             tma_store_commit();
           }
+        };
+        if constexpr (REGM) {
+#pragma unroll
+          for (int c = 0; c < BN / CW; ++c) {
+            if (c < nchunks) finish_chunk(c);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < nchunks; ++c) finish_chunk(c);
         }
       }
       // release the accumulator buffer to the MMA warp
@@ -695,5 +807,10 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 int launch_conv_gemm_f16(int block_n, int out_f16, const CUtensorMap& tmA, const CUtensorMap& tmB,
                          const CUtensorMap& tmOut, const CUtensorMap& tmRes, const ConvGemmParams& p, dim3 grid,
                          cudaStream_t stream, int pdl);
+
+// split-fp16 ("3xFP16") instantiations: conv_gemm_f16x3.cu
+int launch_conv_gemm_f16x3(int block_n, int out_split, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                           const CUtensorMap& tmOut, const CUtensorMap& tmRes, const ConvGemmParams& p, dim3 grid,
+                           cudaStream_t stream, int pdl);
 
 }  // namespace mega

@@ -253,6 +253,54 @@ static int grid_for(long long total, int block) {
   return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// ---- split-fp16 format (include/mega_b200.h): every aligned group of 32 fp32 values <-> 128 bytes [32 hi halves | 32 lo
+// halves]. A team of 8 lanes owns a group: lane l holds values 4l .. 4l+3 (one 16-byte access); the 16-byte chunks of the
+// packed row pair the halves of two neighbouring lanes, exchanged by shuffle. In-place conversion is safe: every load of
+// a group precedes its stores (same warp instruction order).
+__global__ void split16_pack_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long n_groups) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; w * 4 < n_groups; w += warps) {
+    const long long g = w * 4 + (lane >> 3);
+    const bool ok = g < n_groups;
+    const int l = lane & 7;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) x = *reinterpret_cast<const float4*>(src + g * 32 + l * 4);
+    const uint32_t h0 = f2_to_h2_sat(x.x, x.y), h1 = f2_to_h2_sat(x.z, x.w);
+    const float2 b0 = h2_to_f2(h0), b1 = h2_to_f2(h1);
+    const uint32_t l0 = f2_to_h2_sat(x.x - b0.x, x.y - b0.y), l1 = f2_to_h2_sat(x.z - b1.x, x.w - b1.y);
+    // even lane: writes the hi chunk l/2 = (own hi, partner hi); odd lane: the lo chunk 4 + l/2 = (partner lo, own lo)
+    const bool odd = l & 1;
+    const uint32_t s0 = odd ? h0 : l0, s1 = odd ? h1 : l1;          // what the partner needs from this lane
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (ok) {
+      const uint4 o = odd ? make_uint4(r0, r1, l0, l1) : make_uint4(h0, h1, r0, r1);
+      dst[g * 8 + (odd ? 4 : 0) + (l >> 1)] = o;
+    }
+  }
+}
+
+__global__ void split16_unpack_kernel(const uint4* __restrict__ src, float* __restrict__ dst, long long n_groups) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; w * 4 < n_groups; w += warps) {
+    const long long g = w * 4 + (lane >> 3);
+    const bool ok = g < n_groups;
+    const int l = lane & 7;
+    const bool odd = l & 1;
+    uint4 c = make_uint4(0u, 0u, 0u, 0u);
+    if (ok) c = src[g * 8 + (odd ? 4 : 0) + (l >> 1)];     // even: hi of values 8q .. 8q+7, odd: their lo (q = l / 2)
+    // even lane keeps values 8q .. 8q+3 (needs the partner's lo first half), odd lane 8q+4 .. 8q+7 (partner's hi second half)
+    const uint32_t s0 = odd ? c.x : c.z, s1 = odd ? c.y : c.w;
+    const uint32_t r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    const uint32_t h0 = odd ? r0 : c.x, h1 = odd ? r1 : c.y, l0 = odd ? c.z : r0, l1 = odd ? c.w : r1;
+    if (ok) {
+      const float2 a0 = h2_to_f2(h0), a1 = h2_to_f2(h1), b0 = h2_to_f2(l0), b1 = h2_to_f2(l1);
+      *reinterpret_cast<float4*>(dst + g * 32 + l * 4) = make_float4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y);
+    }
+  }
+}
+
 }  // namespace mega
 
 using namespace mega;
@@ -375,6 +423,29 @@ extern "C" int mega_copy_rows_batch(const mega_copy_job* jobs_host, int n_jobs, 
   for (int i = n_jobs; i < kMaxCopyJobs; ++i) jobs.j[i] = jobs_host[0];
   dim3 grid(grid_for(most, 256) > 148 ? 148 : grid_for(most, 256), n_jobs);
   copy_rows_batch_kernel<<<grid, 256, 0, stream>>>(jobs);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+/* fp32 -> split-fp16 (include/mega_b200.h) over n_values contiguous values (a multiple of 32); dst == src converts in place */
+extern "C" int mega_split16_pack(const float* src, void* dst, long long n_values, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(n_values >= 0 && (n_values & 31) == 0, "split16_pack: n_values must be a multiple of 32 (got %lld)", n_values);
+  MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(src) & 127) == 0 && (reinterpret_cast<uintptr_t>(dst) & 127) == 0,
+                 "split16_pack: tensors must be 128-byte aligned");
+  if (n_values == 0) return MEGA_OK;
+  split16_pack_kernel<<<grid_for(n_values / 4, 256), 256, 0, stream>>>(src, static_cast<uint4*>(dst), n_values / 32);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
+}
+
+extern "C" int mega_split16_unpack(const void* src, float* dst, long long n_values, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(n_values >= 0 && (n_values & 31) == 0, "split16_unpack: n_values must be a multiple of 32 (got %lld)", n_values);
+  MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(src) & 127) == 0 && (reinterpret_cast<uintptr_t>(dst) & 127) == 0,
+                 "split16_unpack: tensors must be 128-byte aligned");
+  if (n_values == 0) return MEGA_OK;
+  split16_unpack_kernel<<<grid_for(n_values / 4, 256), 256, 0, stream>>>(static_cast<const uint4*>(src), dst, n_values / 32);
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
 }

@@ -405,12 +405,60 @@ static const bool g_roi_separable = [] {
   return e != nullptr ? e[0] != '0' : true;     // default ON: 181 -> 130 us (rois of 40-360 px), 583 -> 268 us (200-900 px), tools/roi_probe.py on a B200
 }();
 
+// SPLIT: the map and the result are split-fp16 tensors (include/mega_b200.h; the strict engine): a thread's 8 channels are
+// one 16-byte chunk of hi halves plus the 16-byte chunk of their lo halves 64 bytes further, in and out.
+template <bool SPLIT>
+struct SepIo {
+  static constexpr int kEB = SPLIT ? 4 : 2;      // bytes per value
+  // byte offset of thread q's 8 channels inside the 128-channel slice of a pixel
+  static __device__ __forceinline__ int chunk_off(int q) { return SPLIT ? (q >> 2) * 128 + (q & 3) * 16 : q * 16; }
+  static __device__ __forceinline__ void load8(const char* p, float (&v)[8]) {
+    const uint4 h = ldg_u4(p);
+    const uint32_t* ph_ = &h.x;
+    if (SPLIT) {
+      const uint4 l = ldg_u4(p + 64);
+      const uint32_t* pl = &l.x;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = h2_to_f2(ph_[e]), b = h2_to_f2(pl[e]);
+        v[2 * e] = a.x + b.x;
+        v[2 * e + 1] = a.y + b.y;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = h2_to_f2(ph_[e]);
+        v[2 * e] = a.x;
+        v[2 * e + 1] = a.y;
+      }
+    }
+  }
+  static __device__ __forceinline__ void store8(char* p, const float (&v)[8]) {
+    if (SPLIT) {
+      uint32_t hh[4], ll[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        hh[e] = f2_to_h2_sat(v[2 * e], v[2 * e + 1]);
+        const float2 back = h2_to_f2(hh[e]);
+        ll[e] = f2_to_h2_sat(v[2 * e] - back.x, v[2 * e + 1] - back.y);
+      }
+      *reinterpret_cast<uint4*>(p) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+      *reinterpret_cast<uint4*>(p + 64) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    } else {
+      *reinterpret_cast<uint4*>(p) = make_uint4(f2_to_h2(v[0], v[1]), f2_to_h2(v[2], v[3]), f2_to_h2(v[4], v[5]), f2_to_h2(v[6], v[7]));
+    }
+  }
+};
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
-roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int height, int width, long long in_img_stride,
-                              const float* __restrict__ rois, int roi_ld, int roi_box_off,
-                              const int* __restrict__ roi_batch, float scale, int ph, int pw, int sampling_ratio,
-                              __half* __restrict__ out, long long out_roi_stride) {
-  constexpr int kSlice = kRoiSliceBytes / 2;     // 128 channels per CTA
+roi_align_nhwc_sep_kernel(const void* __restrict__ in_v, int channels, int height, int width, long long in_img_stride,
+                          const float* __restrict__ rois, int roi_ld, int roi_box_off,
+                          const int* __restrict__ roi_batch, float scale, int ph, int pw, int sampling_ratio,
+                          void* __restrict__ out_v, long long out_roi_stride) {
+  using Io = SepIo<SPLIT>;
+  constexpr int kEB = Io::kEB;
+  constexpr int kSlice = 128;                    // channels per CTA
   __shared__ float Wy[7][kSepMaxDim], Wx[7][kSepMaxDim];
   __shared__ AxisSample ys[7 * kSepMaxGrid], xs[7 * kSepMaxGrid];
   __shared__ int ylo[7], yhi[7], xlo[7], xhi[7];
@@ -428,7 +476,7 @@ roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int h
   }
   roi5[1] = rb[0]; roi5[2] = rb[1]; roi5[3] = rb[2]; roi5[4] = rb[3];
   const RoiGeom g = roi_geom(roi5, scale, ph, pw, sampling_ratio);
-  const __half* img = in + static_cast<long long>(g.batch) * in_img_stride + slice * kSlice;
+  const char* img = static_cast<const char*>(in_v) + (static_cast<long long>(g.batch) * in_img_stride + slice * kSlice) * kEB;
   if (tid < 7) {
     ylo[tid] = kSepMaxDim; yhi[tid] = -1;
     xlo[tid] = kSepMaxDim; xhi[tid] = -1;
@@ -482,7 +530,7 @@ roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int h
   }
   const int q = tid & 15, worker = tid >> 4;
   const float inv_count = 1.0f / static_cast<float>(g.grid_h * g.grid_w);
-  __half* obase = out + static_cast<long long>(n) * out_roi_stride + slice * kSlice + q * 8;
+  char* obase = static_cast<char*>(out_v) + (static_cast<long long>(n) * out_roi_stride + slice * kSlice) * kEB + Io::chunk_off(q);
   for (int phi = 0; phi < ph; ++phi) {
     // 2. row pass: U[x] = sum_y Wy[phi][y] * f[y, x]   (thread = 8 channels of one column; 16 columns in flight)
     const int y0 = ylo[phi], y1 = yhi[phi];
@@ -490,26 +538,21 @@ roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int h
       float acc[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-      const __half* col = img + static_cast<long long>(x) * channels + q * 8;
-      const long long row_stride = static_cast<long long>(width) * channels;
+      const char* col = img + static_cast<long long>(x) * channels * kEB + Io::chunk_off(q);
+      const long long row_stride = static_cast<long long>(width) * channels * kEB;
       for (int y = y0; y <= y1; y += 4) {          // four rows in flight per thread (L2 latency)
-        uint4 v[4];
+        float v[4][8];
         float w[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const bool live = y + j <= y1;
           w[j] = live ? Wy[phi][y + j] : 0.f;
-          v[j] = ldg_u4(col + static_cast<long long>(live ? y + j : y1) * row_stride);
+          Io::load8(col + static_cast<long long>(live ? y + j : y1) * row_stride, v[j]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t* pv = &v[j].x;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 f = h2_to_f2(pv[e]);
-            acc[2 * e] = fmaf(w[j], f.x, acc[2 * e]);
-            acc[2 * e + 1] = fmaf(w[j], f.y, acc[2 * e + 1]);
-          }
+          for (int e = 0; e < 8; ++e) acc[e] = fmaf(w[j], v[j][e], acc[e]);
         }
       }
       U[x][q * 2] = make_float4(acc[0], acc[1], acc[2], acc[3]);
@@ -529,10 +572,9 @@ roi_align_nhwc_f16_sep_kernel(const __half* __restrict__ in, int channels, int h
         acc[4] = fmaf(w, u1.x, acc[4]); acc[5] = fmaf(w, u1.y, acc[5]);
         acc[6] = fmaf(w, u1.z, acc[6]); acc[7] = fmaf(w, u1.w, acc[7]);
       }
-      uint4 o;
-      o.x = f2_to_h2(acc[0] * inv_count, acc[1] * inv_count); o.y = f2_to_h2(acc[2] * inv_count, acc[3] * inv_count);
-      o.z = f2_to_h2(acc[4] * inv_count, acc[5] * inv_count); o.w = f2_to_h2(acc[6] * inv_count, acc[7] * inv_count);
-      *reinterpret_cast<uint4*>(obase + static_cast<long long>(phi * pw + worker) * channels) = o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] *= inv_count;
+      Io::store8(obase + static_cast<long long>(phi * pw + worker) * channels * kEB, acc);
     }
     __syncthreads();
   }
@@ -616,9 +658,9 @@ extern "C" int mega_roi_align_forward_nhwc_f16(const void* input, int channels, 
   if (fast && height <= kSepMaxDim && width <= kSepMaxDim && g_roi_separable) {
     if (num_rois == 0) return MEGA_OK;
     dim3 grid(channels / 128, num_rois);
-    roi_align_nhwc_f16_sep_kernel<<<grid, 256, 0, stream>>>(
-        static_cast<const __half*>(input), channels, height, width, in_img_stride, rois, roi_ld, roi_box_off, roi_batch,
-        spatial_scale, pooled_h, pooled_w, sampling_ratio, static_cast<__half*>(output), out_roi_stride);
+    roi_align_nhwc_sep_kernel<false><<<grid, 256, 0, stream>>>(
+        input, channels, height, width, in_img_stride, rois, roi_ld, roi_box_off, roi_batch,
+        spatial_scale, pooled_h, pooled_w, sampling_ratio, output, out_roi_stride);
     MEGA_CUDA_CHECK(cudaGetLastError());
     return MEGA_OK;
   }
@@ -640,4 +682,30 @@ extern "C" int mega_roi_align_forward_nhwc_f16(const void* input, int channels, 
   return roi_align_nhwc_launch<__half>(static_cast<const __half*>(input), channels, height, width, in_img_stride, rois,
                                        roi_ld, roi_box_off, roi_batch, num_rois, spatial_scale, pooled_h, pooled_w,
                                        sampling_ratio, static_cast<__half*>(output), out_roi_stride, stream);
+}
+
+/* ROIAlign over a split-fp16 NHWC map into split-fp16 rows (include/mega_b200.h; the strict engine's format): the separable
+ * kernel, maps up to 64 x 64 cells, channels a multiple of 128, bins up to 7 x 7 (MEGA_ERR_ARG otherwise: the caller then
+ * unpacks and uses mega_roi_align_forward_nhwc). Blends in fp32 with fused multiply-adds: results agree with the reference's
+ * association order to ~1e-6 relative, not bit for bit (layers/roi_align.py:13-36, ROIAlign_cuda.cu:62-115). */
+extern "C" int mega_roi_align_forward_nhwc_split16(const void* input, int channels, int height, int width,
+                                                   long long in_img_stride, const float* rois, int roi_ld, int roi_box_off,
+                                                   const int* roi_batch, int num_rois, float spatial_scale, int pooled_h,
+                                                   int pooled_w, int sampling_ratio, void* output,
+                                                   long long out_roi_stride, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK((channels % 128) == 0 && pooled_h <= 7 && pooled_w <= 7 && pooled_h > 0 && pooled_w > 0 &&
+                     height <= kSepMaxDim && width <= kSepMaxDim,
+                 "roi_align_split16: needs channels %% 128 == 0, bins <= 7x7, map <= 64x64 (got C %d, %dx%d bins, map %dx%d)",
+                 channels, pooled_h, pooled_w, height, width);
+  MEGA_ARG_CHECK((reinterpret_cast<uintptr_t>(input) & 127) == 0 && (reinterpret_cast<uintptr_t>(output) & 127) == 0 &&
+                     (out_roi_stride % 32) == 0 && (in_img_stride % 32) == 0,
+                 "roi_align_split16: 128-byte alignment required");
+  if (num_rois == 0) return MEGA_OK;
+  dim3 grid(channels / 128, num_rois);
+  roi_align_nhwc_sep_kernel<true><<<grid, 256, 0, stream>>>(input, channels, height, width, in_img_stride, rois, roi_ld,
+                                                             roi_box_off, roi_batch, spatial_scale, pooled_h, pooled_w,
+                                                             sampling_ratio, output, out_roi_stride);
+  MEGA_CUDA_CHECK(cudaGetLastError());
+  return MEGA_OK;
 }

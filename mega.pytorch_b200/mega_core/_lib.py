@@ -55,7 +55,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("pdl", c_int),
         ("stride_h", c_int), ("stride_w", c_int), ("pad_w_set", c_int), ("pad_w", c_int),
         ("out_stride_h", c_ll), ("out_stride_n", c_ll), ("res_stride_h", c_ll), ("res_stride_n", c_ll),
-        ("b_lo_tap_off", c_int), ("reserved_v5", c_int),
+        ("b_lo_tap_off", c_int), ("res_split", c_int), ("acc_scale", ctypes.c_float), ("reserved_v6", c_int),
     ]
 
 
@@ -136,6 +136,8 @@ lib.mega_roi_align_forward_nchw.restype = _i
 lib.mega_roi_align_forward_nhwc.argtypes = [_vp, _i, _i, _i, _ll, _vp, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _ll, _vp]
 lib.mega_roi_align_forward_nhwc.restype = _i
 lib.mega_roi_align_forward_nhwc_f16.argtypes = [_vp, _i, _i, _i, _ll, _vp, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _ll, _vp]
+lib.mega_roi_align_forward_nhwc_split16.argtypes = [_vp, _i, _i, _i, _ll, _vp, _i, _i, _vp, _i, _f, _i, _i, _i, _vp, _ll, _vp]
+lib.mega_roi_align_forward_nhwc_split16.restype = _i
 lib.mega_roi_align_forward_nhwc_f16.restype = _i
 lib.mega_stem_im2col_f16.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp]
 lib.mega_stem_im2col_f16.restype = _i
@@ -172,6 +174,10 @@ class CopyJob(ctypes.Structure):
 
 lib.mega_copy_rows_batch.argtypes = [ctypes.POINTER(CopyJob), _i, _vp]
 lib.mega_copy_rows_batch.restype = _i
+lib.mega_split16_pack.argtypes = [_vp, _vp, _ll, _vp]
+lib.mega_split16_pack.restype = _i
+lib.mega_split16_unpack.argtypes = [_vp, _vp, _ll, _vp]
+lib.mega_split16_unpack.restype = _i
 lib.mega_transpose_2d.argtypes = [_vp, _i, _i, _i, _vp, _vp]
 lib.mega_transpose_2d.restype = _i
 lib.mega_relation_softmax.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _f, _vp]
@@ -228,5 +234,5 @@ EXPORTS = [
     "mega_stem_prep", "mega_fgfa_pool_image", "mega_fgfa_build_pairs", "mega_avgpool2_nhwc", "mega_fgfa_aggregate",
     "mega_roi_align_backward_nchw", "mega_roi_pool_forward", "mega_roi_pool_backward", "mega_deform_im2col_kq",
     "mega_deform_col2im_fused", "mega_channel_sum_nchw", "mega_deform_psroi_pooling_backward",
-    "mega_image_transform_u8", "mega_dff_warp_scale", "mega_vid_match_host",
+    "mega_image_transform_u8", "mega_dff_warp_scale", "mega_vid_match_host", "mega_split16_pack", "mega_split16_unpack", "mega_roi_align_forward_nhwc_split16",
 ]

@@ -162,12 +162,26 @@ class ResNetStages:
             self.stages.append(blocks)
         self._bufs = {}
         self.lane = 0       # interleaved chains (ops.chain(interleave=True)): each lane owns its scratch buffers
+        self.split16 = False    # strict mode: weights and activations in the split-fp16 format (use_split16())
+
+    def use_split16(self):
+        """strict mode ("3xFP16", ops.pack_weights_split16): every weight is packed once, every scratch buffer holds
+        split-fp16 activations; forward() packs an fp32 input on entry and writes `out` in the format `out` is marked with"""
+        for blocks in self.stages:
+            for blk in blocks:
+                for name in ("w1", "w2", "w3", "wd"):
+                    if getattr(blk, name, None) is not None:
+                        setattr(blk, name, ops.pack_weights_split16(getattr(blk, name)))
+        self.split16 = True
+        self._bufs = {}
 
     def _buf(self, tag, shape):
         key = (tag, tuple(shape), self.lane)
         t = self._bufs.get(key)
         if t is None:
             t = torch.zeros(*shape, device=self.dev, dtype=self.dtype)
+            if self.split16:
+                ops.mark_split16(t)
             self._bufs[key] = t
         return t
 
@@ -200,6 +214,8 @@ class ResNetStages:
         """x [N,H,W,C] NHWC -> [N,H',W',C'] (max_ctas > 0: leave SMs free for a concurrent stream)"""
         n_blocks = sum(len(s) for s in self.stages)
         done = 0
+        if self.split16 and not ops.is_split16(x):
+            x = ops.pack_split16(x.contiguous(), out=self._buf("x_in", x.shape))
         for si, blocks in enumerate(self.stages):
             for bi, blk in enumerate(blocks):
                 n, h, w, _ = x.shape
@@ -280,6 +296,9 @@ class Backbone:
         hp, wp = (ho - 1) // 2 + 1, (wo - 1) // 2 + 1
         p = self._buf("pool", (n, hp, wp, 64))
         ops.maxpool3x3s2(s, p)
+        if self.stages.split16:
+            ops.unmark_split16(p)
+            ops.pack_split16(p)          # in place: res2 reads split-fp16
         chained = self.dtype == torch.float16
         dual = chained and ops.DUAL_CHAIN[0] and n >= ops.DUAL_MIN_IMAGES and n % 2 == 0
         with ops.chain(self._chains, ("body", tuple(p.shape), tail is not None, dual), self.dev, enabled=chained,
@@ -400,6 +419,10 @@ class HeadCommon:
             t = self._buf("rpn_t_lane%d" % lane, (n, h, w, feats.shape[3]), self.act)
             head = self._buf("rpn_head", (n_total, h, w, self.rpn_ld))
             out = head[lane * n:(lane + 1) * n]
+        if getattr(self, "split16", False):
+            ops.mark_split16(t)
+            if not ops.is_split16(feats):
+                feats = ops.pack_split16(feats.contiguous(), out=ops.mark_split16(self._buf("rpn_in", feats.shape)))
         ops.conv_gemm(feats, self.rpn_w, t, taps=(3, 3), dil=1, pad=1, bias=self.rpn_b, relu=True)
         ops.conv_gemm(t, self.rpn_hw, out, bias=self.rpn_hb, cout=5 * self.num_anchors, block_n=64)
         return head
@@ -426,6 +449,9 @@ class HeadCommon:
         D = self.feat_dim
         q, k, vt = self.Qb[:nq], self.Kb[:nref], self.Vt[ld]
         s = self.S[ld][:16 * nq * ld].view(16, nq, ld)
+        split = getattr(self, "split16_att", False)
+        if split:
+            ops.unmark_split16(s)      # the logits are plain fp32 (the soft-max kernels read and write them in place)
         key = (id(att), xq.data_ptr(), nq, refs.data_ptr(), nref, out.data_ptr(), tail is not None, reuse_kv)
         # [Q, K, V', Q.K^T]: the product reads Q (3 back) and K (2 back), so every layer may start once the layer TWO
         # positions back is complete (depth-2 barrier: V' and Q.K^T overlap the tails of K and V')
@@ -444,6 +470,8 @@ class HeadCommon:
                              host_w=att.host_w if boxes_q is not None else None)
         if pr is not None:
             s = pr
+        if split:
+            ops.pack_split16(s)        # probabilities -> split-fp16, in place: the A operand of P.V'
         with ops.chain(self._chains, ("pv",) + key, self.dev, enabled=self.chained):
             ops.conv_gemm(s.view(16, 1, nq, ld), vt.view(1, D, ld), out.view(1, 1, nq, D), tile=(1, 128), cout=64, k=ld,
                           batch=16, a_n_off=1, b_n_off=64, out_c_off=64, res_c_off=64, bias_z_off=64, bias=att.bv,
@@ -605,19 +633,45 @@ class WindowedEngine(HeadCommon):
         return x, boxes, cnt, spans
 
     def _presplit_weights(self):
-        """strict mode: every weight that serves as a B operand gets its 3xTF32 low part stored behind it once
-        (ops.presplit), so the kernels stop re-splitting the same weight tile on every k-block of every launch"""
+        """strict mode: the weights are split ONCE. Backbone body / res5 / RPN head / l_fcs[0] (>= 80 % of the
+        frame's arithmetic) run "3xFP16": weights and activations in the split-fp16 format, three kind::f16 MMAs per k-step and
+        no split work inside the kernels (ops.pack_weights_split16). The stem and the relation stages stay 3xTF32 on fp32
+        tensors, their weights' low parts stored behind them (ops.presplit)."""
         if self.cfg.precision != "fp32x3" or self.dev.type != "cuda":
             return
-        for stages in (self.backbone.stages, self.res5):
-            for blocks in stages.stages:
-                for blk in blocks:
-                    for name in ("w1", "w2", "w3", "wd"):
-                        if getattr(blk, name, None) is not None:
-                            setattr(blk, name, ops.presplit(getattr(blk, name)))
+        self.split16 = bool(ops.SPLIT16[0])
+        if self.split16:
+            self.backbone.stages.use_split16()
+            self.res5.use_split16()
+            self.rpn_w, self.rpn_hw = ops.pack_weights_split16(self.rpn_w), ops.pack_weights_split16(self.rpn_hw)
+            self.fc0_w = ops.pack_weights_split16(self.fc0_w)
+        else:
+            for stages in (self.backbone.stages, self.res5):
+                for blocks in stages.stages:
+                    for blk in blocks:
+                        for name in ("w1", "w2", "w3", "wd"):
+                            if getattr(blk, name, None) is not None:
+                                setattr(blk, name, ops.presplit(getattr(blk, name)))
+            self.rpn_w, self.rpn_hw = ops.presplit(self.rpn_w), ops.presplit(self.rpn_hw)
+            self.fc0_w = ops.presplit(self.fc0_w)
         self.backbone.stem_wr = ops.presplit(self.backbone.stem_wr)
-        self.rpn_w, self.rpn_hw, self.pred_w = ops.presplit(self.rpn_w), ops.presplit(self.rpn_hw), ops.presplit(self.pred_w)
-        self.fc0_w = ops.presplit(self.fc0_w)
+        atts = list(getattr(self, "att_l", [])) + list(getattr(self, "att_g", [])) + list(getattr(self, "att", []))
+        self.split16_att = self.split16 and bool(ops.SPLIT16_ATT[0])
+        if self.split16_att:
+            # the relation stages too: every [rows, 1024] feature buffer (rings, window, stage inputs / outputs, Q / K / V'
+            # scratch) holds split-fp16 rows -- gathers and copies move bytes, so only the GEMMs and the API edges care
+            for name, t in list(vars(self).items()):
+                if torch.is_tensor(t) and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] == self.feat_dim \
+                        and name not in ("pred_w",):
+                    ops.mark_split16(t)
+            for t in self.Vt.values():
+                ops.mark_split16(t)
+            self.fc_w = [None if w is None else ops.pack_weights_split16(w) for w in self.fc_w]
+            self.pred_w = ops.pack_weights_split16(self.pred_w)
+            for att in atts:
+                att.wq, att.wk, att.wv = (ops.pack_weights_split16(w) for w in (att.wq, att.wk, att.wv))
+            return
+        self.pred_w = ops.presplit(self.pred_w)
         self.fc_w = [None if w is None else ops.presplit(w) for w in self.fc_w]
         for att in list(getattr(self, "att_l", [])) + list(getattr(self, "att_g", [])) + list(getattr(self, "att", [])):
             att.wq, att.wk = ops.presplit(att.wq), ops.presplit(att.wk)      # (wv is an A operand: V'^T = Wv . refs^T)
@@ -631,7 +685,10 @@ class WindowedEngine(HeadCommon):
     @_with_precision
     def backbone_nchw(self, imgs):
         """ResNet.forward (resnet.py:145-152): [n,3,H,W] -> [n,1024,H/16,W/16] fp32 in the reference's layout"""
-        return self.backbone.forward(imgs).permute(0, 3, 1, 2).float().contiguous()
+        y = self.backbone.forward(imgs)
+        if ops.is_split16(y):
+            y = ops.unpack_split16(y, torch.empty_like(y))
+        return y.permute(0, 3, 1, 2).float().contiguous()
 
     @_with_precision
     def rpn_nchw(self, feats_nchw, im_w, im_h, post):
@@ -656,6 +713,8 @@ class WindowedEngine(HeadCommon):
                            pooled)
         x = self.fc0_out[:k]
         self._fc0(pooled, x)
+        if ops.is_split16(x):
+            return ops.unpack_split16(x, torch.empty_like(x))
         return x.float().clone()
 
     @staticmethod
@@ -672,6 +731,8 @@ class WindowedEngine(HeadCommon):
         convolution over a [rows, K/64] 'image' with 64 channels, whose weight layout is k-block-major (pack_fc0)."""
         rows, k = pooled.shape
         kb = k // 64
+        if getattr(self, "split16", False) and not ops.is_split16(pooled):
+            ops.pack_split16(pooled)     # in place (ops.roi_align_nhwc over a split-fp16 map already wrote the format)
         ops.conv_gemm(pooled.view(1, rows, kb, 64), self.fc0_w, x.view(1, rows, 1, x.shape[1]), taps=(1, kb), pad=0,
                       bias=self.fc0_b, relu=True, tile=(128, 1), out_hw=(rows, 1))
 
@@ -827,7 +888,10 @@ class MegaEngine(WindowedEngine, WavefrontMixin):
         R = self.R
         assert tuple(feats.shape) == (R, self.feat_dim), feats.shape
         g = self.glob_pushed % self.GF
-        self.glob_x[g * R:(g + 1) * R].copy_(feats.to(self.dev))
+        rows = feats.to(self.dev).float().contiguous()
+        if ops.is_split16(self.glob_x):
+            rows = ops.pack_split16(rows)
+        self.glob_x[g * R:(g + 1) * R].copy_(rows)
         self.glob_pushed += 1
 
     def _tab(self, name):

@@ -1,5 +1,6 @@
 """Python wrappers (pointer plumbing only) around the C-ABI kernels."""
 import ctypes
+import math
 import weakref
 
 import torch
@@ -238,6 +239,114 @@ def presplit(w):
     return out
 
 
+# ---- strict mode, "3xFP16" (precision 3): the SPLIT-FP16 storage format (include/mega_b200.h). A split-fp16 tensor is an
+#      fp32-typed torch tensor (same shape / strides / bytes) whose every aligned group of 32 values holds 32 hi halves then
+#      32 lo halves; which tensors are in that format is tracked by STORAGE (every view of a buffer shares it). conv_gemm runs
+#      precision 3 when its weights were packed by pack_weights_split16 (A must then be a split-fp16 tensor) and writes
+#      split-fp16 exactly when `out` is marked; the residual may be either.
+SPLIT16 = [_os.environ.get("MEGA_B200_SPLIT16", "1") != "0"]     # strict engines use the format (0: 3xTF32 everywhere)
+SPLIT16_ATT = [_os.environ.get("MEGA_B200_SPLIT16_ATT", "1") != "0"]   # ... also for the relation stages' feature rows
+_SPLIT16_BUFS = {}
+_SPLIT16_W = {}
+
+
+def mark_split16(t):
+    """declare the storage of `t` split-fp16 (the caller fills it through conv_gemm / pack_split16)"""
+    assert t.dtype == torch.float32
+    st = t.untyped_storage()
+    _SPLIT16_BUFS[st.data_ptr()] = weakref.ref(st)
+    return t
+
+
+def unmark_split16(t):
+    _SPLIT16_BUFS.pop(t.untyped_storage().data_ptr(), None)
+    return t
+
+
+def is_split16(t):
+    if t is None or t.dtype != torch.float32:
+        return False
+    st = t.untyped_storage()
+    r = _SPLIT16_BUFS.get(st.data_ptr())
+    if r is None:
+        return False
+    if r() is None:          # a freed buffer's address handed to a new tensor
+        del _SPLIT16_BUFS[st.data_ptr()]
+        return False
+    return True
+
+
+def pack_split16(x, out=None):
+    """fp32 values -> split-fp16; contiguous, numel % 32 == 0. out=None converts IN PLACE (and marks x)"""
+    require_cuda(x, out)
+    dst = x if out is None else out
+    assert x.dtype == torch.float32 and x.is_contiguous() and dst.is_contiguous() and dst.numel() == x.numel()
+    assert not is_split16(x) or out is not None, "already split-fp16"
+    check(lib.mega_split16_pack(ptr(x), ptr(dst), x.numel(), stream_ptr()), "mega_split16_pack")
+    return mark_split16(dst)
+
+
+def unpack_split16(x, out):
+    """split-fp16 -> fp32 values in `out` (contiguous, distinct storage)"""
+    require_cuda(x, out)
+    assert x.is_contiguous() and out.is_contiguous() and out.numel() == x.numel() and out.dtype == torch.float32
+    check(lib.mega_split16_unpack(ptr(x), ptr(out), x.numel(), stream_ptr()), "mega_split16_unpack")
+    return out
+
+
+def split16_encode(x):
+    """torch restatement of the format (any device): fp32 [..., K] (K % 32 == 0) -> fp32-typed tensor of the same shape
+    holding [32 hi halves | 32 lo halves] per group of 32 values"""
+    assert x.dtype == torch.float32 and x.shape[-1] % 32 == 0
+    xc = x.contiguous()
+    hi = xc.clamp(-65504.0, 65504.0).half()
+    lo = (xc - hi.float()).clamp(-65504.0, 65504.0).half()
+    g = xc.shape[:-1] + (xc.shape[-1] // 32, 1, 32)
+    both = torch.cat([hi.view(g), lo.view(g)], dim=-2)                  # [..., K/32, 2, 32] halves
+    return both.reshape(xc.shape[:-1] + (2 * xc.shape[-1],)).view(torch.float32)
+
+
+def split16_decode(p):
+    """inverse of split16_encode (fp32 sums hi + lo)"""
+    h = p.contiguous().view(torch.float16)
+    g = h.view(p.shape[:-1] + (p.shape[-1] // 32, 2, 32)).float()
+    return (g[..., 0, :] + g[..., 1, :]).reshape(p.shape)
+
+
+def pack_weights_split16(w):
+    """w: fp32 weight [rows, K] or [taps, rows, K] (K % 32 == 0) -> split-fp16 tensor of the same shape holding w * 2^e, e
+    chosen so that max |w| 2^e lies in [2^13, 2^14) (the low halves of all weights down to 2^-17 of the largest then stay
+    normal fp16 numbers); conv_gemm multiplies the accumulator by 2^-e (exact)."""
+    assert w.dtype == torch.float32 and w.dim() in (2, 3) and w.shape[-1] % 32 == 0
+    m = float(w.abs().max())
+    e = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
+    e = max(-24, min(e, 40))
+    out = split16_encode(w * (2.0 ** e))
+    _SPLIT16_W[out.data_ptr()] = (weakref.ref(out), 2.0 ** -e)
+    return out
+
+
+def _split16_weight(w):
+    r = _SPLIT16_W.get(w.data_ptr())
+    if r is None:
+        return None
+    if r[0]() is None:
+        del _SPLIT16_W[w.data_ptr()]
+        return None
+    return r[1]
+
+
+def _split16_fmt(t):
+    """None: plain tensor; else the power of two its split-fp16 values must be multiplied by (1.0 for activations, 2^-e for
+    tensors made by pack_weights_split16 -- either may serve as the A or the B operand)"""
+    if t is None or t.dtype != torch.float32:
+        return None
+    s = _split16_weight(t)
+    if s is not None:
+        return s
+    return 1.0 if is_split16(t) else None
+
+
 # ---- per-shape kernel configuration (block_n, stream_k, max_ctas), filled by autotune()
 TUNED = {}
 AUTOTUNE = [False]
@@ -275,7 +384,7 @@ def _shape_key(d):
 
 def _candidates(cout, prec=0, out_f16=0):
     cands = []
-    for bn in ((64, 128) if prec == 1 else BLOCK_NS):
+    for bn in ((64, 128) if prec in (1, 3) else BLOCK_NS):
         if out_f16 and bn % 64:
             continue
         if bn > MAX_BN[0]:
@@ -432,9 +541,21 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     kb_per_tile = taps[0] * taps[1] * (-(-d.k_per_tap // (64 if f16 else 32)))
     d.precision = 2 if f16 else PRECISION[0]
     d.out_f16 = 1 if out_f16 else 0
+    fa, fb = _split16_fmt(a), _split16_fmt(w)
+    if fa is not None or fb is not None:
+        assert fa is not None and fb is not None, \
+            "conv_gemm: both operands must be split-fp16 (ops.pack_split16 / pack_weights_split16) or neither (A %s, B %s)" % (
+                "split" if fa is not None else "plain", "split" if fb is not None else "plain")
+        d.precision = 3
+        d.out_f16 = 1 if is_split16(out) else 0
+        d.res_split = 1 if is_split16(residual) else 0
+        d.acc_scale = fa * fb
+    else:
+        assert not (is_split16(out) or is_split16(residual)), \
+            "conv_gemm: split-fp16 output / residual need split-fp16 operands"
     d.pdl = 1 if PDL[0] else 0
     auto_bn, auto_sk = pick_config(d.cout, m_tiles, batch, kb_per_tile, out_f16)
-    if d.precision == 1:
+    if d.precision in (1, 3):
         auto_bn = 64 if d.cout <= 64 else 128
         if block_n not in (None, 64, 128):
             block_n = auto_bn
@@ -564,6 +685,18 @@ def roi_align_nhwc(feat, boxes, roi_batch, scale, ph, pw, sampling_ratio, out):
     k = boxes.shape[0]
     assert out.dtype == feat.dtype
     fn = lib.mega_roi_align_forward_nhwc_f16 if feat.dtype == torch.float16 else lib.mega_roi_align_forward_nhwc
+    if is_split16(feat):
+        # split-fp16 map -> split-fp16 rows (marks `out`); maps beyond the separable kernel's 64 x 64 cells go through fp32
+        if h <= 64 and w <= 64 and c % 128 == 0 and ph <= 7 and pw <= 7:
+            fn = lib.mega_roi_align_forward_nhwc_split16
+            mark_split16(out)
+        else:
+            plain = unpack_split16(feat.contiguous(), torch.empty_like(feat))
+            unmark_split16(out)
+            roi_align_nhwc(plain, boxes, roi_batch, scale, ph, pw, sampling_ratio, out)
+            return pack_split16(out)
+    else:
+        unmark_split16(out)
     check(fn(ptr(feat), c, h, w, feat.stride(0), ptr(boxes), boxes.stride(0), 0,
                                           ptr(roi_batch), k, float(scale), ph, pw, sampling_ratio, ptr(out),
                                           out.stride(0), stream_ptr()), "mega_roi_align_forward_nhwc")

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(_lib.lib, s), "libmega_b200.so does not export %s" % s
     assert sorted(_lib.EXPORTS) == syms
-    assert _lib.lib.mega_abi_version() == 5
+    assert _lib.lib.mega_abi_version() == 6
 
 
 def test_no_cpu_fallback():
@@ -106,3 +106,23 @@ def test_C_nms_and_roi_align_accept_cpu_tensors_like_the_reference():
         _C.nms(torch.zeros(4, 4), torch.zeros(4).double(), 0.5)               # dets / scores of different types
     with pytest.raises(RuntimeError):
         _C.sigmoid_focalloss_forward(torch.zeros(4, 3), torch.zeros(4, dtype=torch.int32), 3, 2.0, 0.25)   # CUDA-only
+
+
+def test_split16_format_restatement_round_trips_on_the_cpu():
+    """ops.split16_encode / decode (the torch restatement the GPU pack kernels are checked against) and the weight packer's
+    power-of-two scaling"""
+    import torch
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(5, 64, generator=g) * 10
+    p = ops.split16_encode(x)
+    assert p.shape == x.shape and p.dtype == torch.float32
+    halves = p.view(torch.float16).view(5, 2, 2, 32)
+    assert torch.equal(halves[:, :, 0, :].reshape(5, 64), x.half())              # first the 32 hi halves of a group
+    assert (ops.split16_decode(p) - x).abs().max() <= x.abs().max() * 2.0 ** -22
+    w = torch.randn(3, 8, 32, generator=g) * 0.02
+    pw = ops.pack_weights_split16(w)
+    s = ops._split16_weight(pw)
+    assert s is not None and 2.0 ** 13 <= float(w.abs().max()) / s < 2.0 ** 14
+    assert ((ops.split16_decode(pw) * s).double() - w.double()).abs().max() <= float(w.abs().max()) * 2.0 ** -23
+    assert not ops.is_split16(x) and ops.is_split16(ops.mark_split16(torch.zeros(32)))

@@ -1,4 +1,4 @@
-"""Three representative contractions of the strict (3xTF32, A operand in TMEM) mode at the sizes of a 4-key-frame step
+"""Three representative contractions of the strict mode (3xTF32 with the A operand in TMEM; --split16: 3xFP16 on split-fp16 tensors) at the sizes of a 4-key-frame step
 (8 images of 600x1000), timed with CUDA events and -- under `ncu --profile-from-start off` -- profiled one launch each:
 res4 3x3 (K = 2304 -> 256), RPN head 3x3 (K = 9216 -> 1024), res4 1x1 expand (K = 256 -> 1024, residual).
     ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/strict python tools/strict_gemm_probe.py"""
@@ -31,6 +31,11 @@ sc, bi = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
 cases = [("res4 3x3 256->256", lambda: ops.conv_gemm(x256, w33, o256, taps=(3, 3), pad=1, scale=sc[:256], bias=bi[:256], relu=True), 2 * n * h * w * 256 * 2304),
          ("rpn 3x3 1024->1024", lambda: ops.conv_gemm(x1024, wrpn, o1024, taps=(3, 3), pad=1, bias=bi, relu=True), 2 * n * h * w * 1024 * 9216),
          ("res4 1x1 256->1024 + residual", lambda: ops.conv_gemm(x256, wexp, o1024b, scale=sc, bias=bi, residual=x1024, relu=True), 2 * n * h * w * 1024 * 256)]
+if "--split16" in sys.argv:      # the same three layers in the split-fp16 format ("3xFP16": no split work in the kernel)
+    ops.pack_split16(x256), ops.pack_split16(x1024)
+    ops.mark_split16(o256), ops.mark_split16(o1024b)
+    w33, wrpn, wexp = (ops.pack_weights_split16(t) for t in (w33, wrpn, wexp))
+    ops.mark_split16(o1024)
 with ops.precision("fp32x3"):
     for name, fn, flops in cases:
         for _ in range(3):
