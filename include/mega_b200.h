@@ -106,7 +106,8 @@ typedef struct mega_conv_gemm_desc {
   int b_lo_tap_off;
   /* ABI v6 (zero = previous behaviour): precision 3 only. a, b: split-fp16 tensors (a_c, b_k, k_per_tap, a_c_off, b_k_off
    * multiples of 32; block_n 64 or 128). out_f16 != 0: split-fp16 output (cout, out_c_off multiples of 32), else fp32.
-   * res_split != 0: the residual is split-fp16, else fp32. acc_scale: 0 = 1; otherwise the accumulator is multiplied by it
+   * `scale` must be NULL (fold per-channel factors into the weights before packing them). res_split != 0: the residual is
+   * split-fp16, else fp32. acc_scale: 0 = 1; otherwise the accumulator is multiplied by it
    * before scale / bias -- weights are stored multiplied by a power of two 1 / acc_scale so that their low halves stay
    * normal fp16 numbers (mega_core.b200.ops.pack_weights_split16). */
   int res_split;

@@ -135,6 +135,9 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
     MEGA_ARG_CHECK((d->a_stride_w & 31) == 0 && (d->b_stride_n & 31) == 0 && (reinterpret_cast<uintptr_t>(d->a) & 127) == 0 &&
                        (reinterpret_cast<uintptr_t>(d->b) & 127) == 0,
                    "conv_gemm: split-fp16 operands need 128-byte aligned rows");
+    MEGA_ARG_CHECK(d->scale == nullptr,
+                   "conv_gemm: precision 3 takes no per-channel scale: fold it into the weights before packing them "
+                   "(mega_core.b200.ops.pack_weights_split16(w, scale))");
   } else {
     MEGA_ARG_CHECK(d->res_split == 0, "conv_gemm: res_split needs precision 3");
   }

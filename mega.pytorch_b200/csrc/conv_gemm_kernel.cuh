@@ -148,6 +148,7 @@ struct WorkIter {
 };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // 8 epilogue warps
 
 // Persistent stream-K kernel. The work is the list of (tile, k-block) units, tiles ordered
 // (batch, n-tile, m-tile) with m fastest; CTA c owns the contiguous unit range
@@ -169,7 +170,7 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;"
 // griddepcontrol.wait, i.e. overlapped with the tail of the previous kernel on the stream; nothing before the wait
 // touches global memory.
 template <int BN, int STAGES, int MODE, bool OUT16>
-__global__ void __launch_bounds__(kThreads + (MODE == kModeSplit3 ? 128 : 0), 1)
+__global__ void __launch_bounds__(kThreads + ((MODE == kModeSplit3 || MODE == kModeF16x3) ? 128 : 0), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                       const ConvGemmParams p) {
@@ -183,10 +184,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   static_assert(SmemLayout<BN, STAGES, MODE>::kTotal <= 227 * 1024, "pipeline + staging exceed the 227 KB of a CTA");
   using L = SmemLayout<BN, STAGES, MODE>;
   // accumulators: two ping-pong buffers (+ a master accumulator in 3xTF32 mode, see kSegLen)
-  // 3xFP16 keeps the master accumulator in REGISTERS of the epilogue threads (one row x BN columns each; the mode has no
-  // splitter warps, so 192 threads share the register file): a fold then reads the segment from tensor memory once
-  // (64 B/cycle per SM: 0.54 us per 128 x 128 segment) instead of segment + master and writes nothing back
-  constexpr bool REGM = false;   // (measured with 4 epilogue warps: 6-10 % SLOWER than the TMEM master -- 255 registers, spills in the chunk loop)
+  // 3xFP16: eight epilogue warps, the master accumulator in their REGISTERS (64 columns per thread), see the epilogue below
+  constexpr bool REGM = PK;
   constexpr uint32_t kAccBufs = (SEG && !REGM) ? 3 : 2;
   // 3xTF32: three accumulators + two A slabs of 64 columns (hi: 32 columns of K, lo: the next 32)
   constexpr uint32_t kNeedCols = kAccBufs * BN + (SPLIT3 ? 128 : 0);
@@ -209,8 +208,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* split_bar = empty_bar + STAGES;       // [STAGES] (3xTF32 only)
   uint64_t* tmem_full_bar = split_bar + STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint64_t* res_bar = tmem_empty_bar + 2;         // [4 warps][2]
-  uint64_t* aslab_empty_bar = res_bar + 8;        // [2] (3xTF32: the MMAs that read A slab s have completed)
+  uint64_t* res_bar = tmem_empty_bar + 2;         // [4 warps][2] (3xFP16: [8 warps][2])
+  uint64_t* aslab_empty_bar = res_bar + 16;        // [2] (3xTF32: the MMAs that read A slab s have completed)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aslab_empty_bar + 2);
   int* epi_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
@@ -235,9 +234,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);
+      mbar_init(&tmem_empty_bar[b], PK ? 8 : 4);
     }
-    for (int b = 0; b < 8; ++b) mbar_init(&res_bar[b], 1);
+    for (int b = 0; b < 16; ++b) mbar_init(&res_bar[b], 1);
     for (int b = 0; b < 2; ++b) mbar_init(&aslab_empty_bar[b], 1);
     fence_barrier_init();
   }
@@ -365,7 +364,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp >= 6) {
+  } else if (warp >= 6 && !PK) {
     // ===================== operand splitter (3xTF32 only, warps 6..9) =====================
     if (SPLIT3) {
       const int stid = threadIdx.x - kThreads;            // 0..127
@@ -435,6 +434,261 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
+  } else if constexpr (PK) {
+    // ===================== epilogue, 3xFP16 (warps 2..9) =====================
+    // Two warps share a TMEM lane quarter (32 tile rows); each owns HALF of the tile's columns: kCPW chunks of 32. What
+    // the 4-warp epilogue above measured on this mode (10-13 us per 128 x 128 tile at K = 256 against 2.7 us of MMAs) came
+    // from (i) the RN folds -- segment + master read from tensor memory (64 B/cycle per SM) and written back, 0.85-1.2 us
+    // each: here the master lives in REGISTERS (64 columns per thread) and a fold reads the segment once; (ii) two
+    // CTA-wide barriers around L1-missing scale / bias loads per tile: here the BN scale is folded into the packed
+    // weights, the bias slice of the NEXT tile is fetched during the current one (double-buffered, one barrier per tile);
+    // (iii) separate residual staging: here the residual lands in the store staging buffer itself (every thread reads its
+    // 128-byte row into registers before it writes the same row), issued for both chunks at the start of the tile.
+    constexpr int kCPW = BN / 64;          // 32-column chunks per warp
+    const int q = warp & 3;                // TMEM lane quarter this warp may read
+    const int half = (warp - 2) >> 2;      // which half of the columns
+    const int row = q * 32 + lane;
+    const int epi_tid = (warp - 2) * 32 + lane;                              // 0 .. 255
+    uint8_t* stage_buf = smem + L::kEpiOffset + (warp - 2) * (kCPW * 4096);  // kCPW x 4 KB: residual in, result out
+    uint64_t* rbar = res_bar + (warp - 2) * 2;
+    float* bias_s = reinterpret_cast<float*>(smem + L::kSbOffset);           // [2][BN]
+    uint32_t rphase = 0;
+    WorkIter it(p, cta, grid);
+    int t;
+    int kb0, kb1;
+    int item = 0;
+    const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t col_base = static_cast<uint32_t>(half * kCPW * 32);
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    const bool res_split = p.res_split != 0;
+    const float slope = p.relu == 2 ? 0.1f : 0.f;
+    float master[kCPW * 32];
+    for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
+      const TileCoord tc = decode_tile(p, t, BN);
+      // ---- fold every segment but the last into the register master (round-to-nearest fp32 adds)
+      bool has_master = false;
+      int s0 = kb0;
+      for (; s0 + kSegLen < kb1; s0 += kSegLen, ++item) {
+        const int fb = item & 1;
+        mbar_wait(&tmem_full_bar[fb], static_cast<uint32_t>(item >> 1) & 1);
+        tc_fence_after();
+        const uint32_t seg_row = tmem_base + fb * kAccStride + lane_bits + col_base;
+#pragma unroll
+        for (int j = 0; j < kCPW; ++j) {
+          uint32_t a[32];
+          __syncwarp();
+          tmem_ld_32x32(seg_row + j * 32, a);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float v = __uint_as_float(a[i]);
+            master[j * 32 + i] = has_master ? __fadd_rn(v, master[j * 32 + i]) : v;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[fb]);
+        has_master = true;
+      }
+      const int buf = item & 1;
+      const uint32_t use = static_cast<uint32_t>(item >> 1);
+      ++item;
+      const bool complete = (kb0 == 0 && kb1 == KB);
+      const int r0 = q * 32;
+      const int bh0 = r0 / p.tile_w, bw0 = r0 - bh0 * p.tile_w;
+      const int st_w = tc.w0 + bw0, st_h = tc.h0 + bh0;
+      const int res_n = tc.img + tc.batch * p.res_n_off;
+      const int nchunks = min(BN / 32, (p.cout - tc.n0 + 31) / 32);
+      const int bsel = tile_item & 1;
+      // ---- bias slices: [bsel] holds this tile's (written at the end of the previous tile, or right here for the first)
+      epi_bar_sync8();     // every warp is done with the tile before: its bias buffer may be refilled, this one's is visible
+      if (tile_item == 0) {
+        if (epi_tid < BN) {
+          const int n = tc.n0 + epi_tid;
+          bias_s[epi_tid] = (p.bias && n < p.cout) ? __ldg(p.bias + tc.batch * p.bias_z_off + n) : 0.f;
+        }
+        epi_bar_sync8();
+      }
+      float next_bias = 0.f;
+      bool has_next = false;
+      {
+        WorkIter peek = it;
+        int t2, k0, k1;
+        has_next = peek.next(t2, k0, k1);
+        if (has_next && epi_tid < BN) {
+          const TileCoord tc2 = decode_tile(p, t2, BN);
+          const int n = tc2.n0 + epi_tid;
+          next_bias = (p.bias && n < p.cout) ? __ldg(p.bias + tc2.batch * p.bias_z_off + n) : 0.f;
+        }
+      }
+      // ---- the staging buffers are free once the previous tile's stores have read them; then the residual may land there
+      if (lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      auto issue_residual = [&]() {
+        if (p.has_residual && lane == 0) {
+#pragma unroll
+          for (int j = 0; j < kCPW; ++j) {
+            const int cj = half * kCPW + j;
+            if (cj < nchunks) {
+              mbar_arrive_expect_tx(&rbar[j], 4096);
+              tma_load_4d(stage_buf + j * 4096, &tmRes, &rbar[j], tc.n0 + cj * 32 + tc.batch * p.res_c_off, st_w, st_h, res_n);
+            }
+          }
+        }
+      };
+      if (complete) issue_residual();
+      mbar_wait(&tmem_full_bar[buf], use & 1);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + buf * kAccStride + lane_bits + col_base;
+      // chunk j of my columns: last segment (+ master). One chunk is live at a time (168 registers per thread at 320 threads)
+      auto load_chunk = [&](const int j, float (&acc)[32]) {
+        uint32_t raw[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_row + j * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = __uint_as_float(raw[i]);
+          acc[i] = has_master ? __fadd_rn(v, master[j * 32 + i]) : v;
+        }
+      };
+      const int my_chunks = max(0, min(kCPW, nchunks - half * kCPW));
+      auto release_acc = [&]() {      // hand the accumulator buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      };
+      bool finalize = complete;
+      int c_first = cta, c_last = cta;
+      if (!complete) {
+        // ---- publish this CTA's partial accumulator (my columns), then find out whether it arrived last
+        float* my_ws = p.part_ws + ((static_cast<long long>(cta) * 2 + (tile_item == 0 ? 0 : 1)) * kBM + row) * BN + col_base;
+#pragma unroll
+        for (int j = 0; j < kCPW; ++j) {
+          float acc[32];
+          load_chunk(j, acc);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            __stcg(reinterpret_cast<float4*>(my_ws + j * 32 + i), make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
+        }
+        __threadfence();
+        epi_bar_sync8();
+        c_first = unit_owner(U, grid, t * KB);
+        c_last = unit_owner(U, grid, t * KB + KB - 1);
+        if (epi_tid == 0) {
+          const int parts = c_last - c_first + 1;
+          const int old = atomicAdd(&p.counters[t], 1);
+          const int last = (old == parts - 1);
+          if (last) p.counters[t] = 0;   // every part has arrived: leave the counter clean for the next launch
+          *epi_flag = last;
+        }
+        epi_bar_sync8();
+        finalize = (*epi_flag != 0);
+        if (finalize) {
+          __threadfence();
+          issue_residual();
+        }
+      }
+      if (!finalize || my_chunks == 0) release_acc();
+      if (finalize) {
+        const int out_n = tc.img + tc.batch * p.out_n_off;
+#pragma unroll
+        for (int j = 0; j < kCPW; ++j) {
+          if (j < my_chunks) {
+            const int cj = half * kCPW + j;
+            float acc[32];
+            load_chunk(j, acc);
+            if (j + 1 == my_chunks) release_acc();
+            if (!complete) {
+              // deterministic reduction: parts summed in CTA order, own part from tensor memory
+              float sum[32];
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+              for (int oc = c_first; oc <= c_last; ++oc) {
+                if (oc == cta) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) sum[i] += acc[i];
+                } else {
+                  const int slot = (cta_first_unit(U, grid, oc) >= t * KB) ? 0 : 1;
+                  const float* ws = p.part_ws + ((static_cast<long long>(oc) * 2 + slot) * kBM + row) * BN + col_base + j * 32;
+#pragma unroll
+                  for (int i = 0; i < 32; i += 4) {
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(ws + i));
+                    sum[i] += v.x; sum[i + 1] += v.y; sum[i + 2] += v.z; sum[i + 3] += v.w;
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[i] = sum[i];
+            }
+            uint8_t* rowp = stage_buf + j * 4096 + lane * 128;
+            const float4* biv = reinterpret_cast<const float4*>(bias_s + bsel * BN + cj * 32);
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bi = biv[i >> 2];
+              acc[i] = fmaf(acc[i], p.acc_scale, bi.x); acc[i + 1] = fmaf(acc[i + 1], p.acc_scale, bi.y);
+              acc[i + 2] = fmaf(acc[i + 2], p.acc_scale, bi.z); acc[i + 3] = fmaf(acc[i + 3], p.acc_scale, bi.w);
+            }
+            if (p.has_residual) {
+              mbar_wait(&rbar[j], (rphase >> j) & 1u);
+              rphase ^= (1u << j);
+              if (res_split) {    // 16-byte chunks 0..3: hi halves of values 8c .. 8c+7, chunks 4..7: their lo halves
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const uint4 rh = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(c) ^ sw) << 4));
+                  const uint4 rl = *reinterpret_cast<const uint4*>(rowp + ((static_cast<uint32_t>(4 + c) ^ sw) << 4));
+                  const uint32_t hs[4] = {rh.x, rh.y, rh.z, rh.w}, ls[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 a2 = h2_to_f2(hs[e]), b2 = h2_to_f2(ls[e]);
+                    acc[8 * c + 2 * e] += a2.x + b2.x;
+                    acc[8 * c + 2 * e + 1] += a2.y + b2.y;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 rr = *reinterpret_cast<const float4*>(rowp + ((static_cast<uint32_t>(c) ^ sw) << 4));
+                  acc[4 * c] += rr.x; acc[4 * c + 1] += rr.y; acc[4 * c + 2] += rr.z; acc[4 * c + 3] += rr.w;
+                }
+              }
+            }
+            // (every read of the row precedes the first write below: the result goes back to the same bytes)
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) acc[i] = fmaxf(acc[i], slope * acc[i]);
+            }
+            if (OUT16) {      // split-fp16 result
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint32_t hh[4], ll[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  hh[e] = f2_to_h2_sat(acc[8 * c + 2 * e], acc[8 * c + 2 * e + 1]);
+                  const float2 back = h2_to_f2(hh[e]);
+                  ll[e] = f2_to_h2_sat(acc[8 * c + 2 * e] - back.x, acc[8 * c + 2 * e + 1] - back.y);
+                }
+                *reinterpret_cast<uint4*>(rowp + ((static_cast<uint32_t>(c) ^ sw) << 4)) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                *reinterpret_cast<uint4*>(rowp + ((static_cast<uint32_t>(4 + c) ^ sw) << 4)) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(rowp + ((static_cast<uint32_t>(c) ^ sw) << 4)) =
+                    make_float4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmOut, stage_buf + j * 4096, tc.n0 + cj * 32 + tc.batch * p.out_c_off, st_w, st_h, out_n);
+              tma_store_commit();
+            }
+          }
+        }
+      }
+      if (has_next && epi_tid < BN) bias_s[(bsel ^ 1) * BN + epi_tid] = next_bias;
+    }
+    if (lane == 0) tma_store_wait<0>();   // global writes complete before the CTA retires
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quarter this warp may read
@@ -451,7 +705,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int item = 0;   // accumulator-segment counter (ping-pong bookkeeping shared with the MMA warp)
     const uint32_t lane_bits = static_cast<uint32_t>(q * 32) << 16;
     const uint32_t master_row = tmem_base + 2 * kAccStride + lane_bits;
-    float master[REGM ? BN : 1];      // (statically indexed everywhere: the loops over its chunks are fully unrolled)
     for (int tile_item = 0; it.next(t, kb0, kb1); ++tile_item) {
       const TileCoord tc = decode_tile(p, t, BN);
       // ---- 3xTF32 only: fold every segment but the last into the master accumulator (RN fp32 adds)
@@ -462,22 +715,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_full_bar[fb], static_cast<uint32_t>(item >> 1) & 1);
         tc_fence_after();
         const uint32_t seg_row = tmem_base + fb * kAccStride + lane_bits;
-        if (REGM) {
-#pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
-            uint32_t a[32];
-            __syncwarp();
-            tmem_ld_32x32(seg_row + c * 32, a);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(a[j]);
-              master[REGM ? c * 32 + j : 0] = has_master ? __fadd_rn(v, master[REGM ? c * 32 + j : 0]) : v;
-            }
-          }
-        }
 #pragma unroll 1
-        for (int c = 0; !REGM && c < BN / 32; ++c) {
+        for (int c = 0; c < BN / 32; ++c) {
           uint32_t a[32];
           __syncwarp();
           tmem_ld_32x32(seg_row + c * 32, a);
@@ -491,7 +730,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           tmem_st_32x32(master_row + c * 32, a);
         }
-        if (!REGM) tmem_st_wait();
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[fb]);
@@ -528,13 +767,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();  // tcgen05.ld is .sync.aligned
         tmem_ld_32x32(tmem_row + c * 32, acc);
         tmem_ld_wait();
-        if (REGM) {
-          if (has_master) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              acc[j] = __float_as_uint(__fadd_rn(__uint_as_float(acc[j]), master[REGM ? c * 32 + j : 0]));
-          }
-        } else if (SEG && has_master) {
+        if (SEG && has_master) {
           uint32_t m[32];
           tmem_ld_32x32(master_row + c * 32, m);
           tmem_ld_wait();
@@ -557,13 +790,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __stcg(reinterpret_cast<float4*>(my_ws + c * 32 + j), v);
           }
         };
-        if constexpr (REGM) {     // (register master: the chunk index must be a compile-time constant)
-#pragma unroll
-          for (int c = 0; c < BN / 32; ++c) publish(c);
-        } else {
 #pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) publish(c);
-        }
+        for (int c = 0; c < BN / 32; ++c) publish(c);
         __threadfence();
         epi_bar_sync();
         c_first = unit_owner(U, grid, t * KB);
@@ -639,10 +867,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         #pragma unroll
               for (int j = 0; j < 32; ++j) acc[j] = sum[j];
             }
-            if (PK && p.acc_scale != 1.f) {
-        #pragma unroll
-              for (int j = 0; j < 32; ++j) acc[j] *= p.acc_scale;
-            }
             if (has_sb) {
               const float4* scv = reinterpret_cast<const float4*>(sb_s + col0);
               const float4* biv = reinterpret_cast<const float4*>(sb_s + L::kSbCols + col0);
@@ -654,56 +878,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             const float slope = p.relu == 2 ? 0.1f : 0.f;
-            if (PK) {
-              // the residual and / or the output as split fp16: 16-byte chunk g (8 values) of the 32 columns holds the hi
-              // halves, chunk 4 + g their lo halves (same swizzle as the TMA box)
-              const bool res_split = p.res_split != 0;
-        #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const uint32_t ch_hi = (static_cast<uint32_t>(j >> 3) ^ sw) << 4;
-                const uint32_t ch_lo = (static_cast<uint32_t>(4 + (j >> 3)) ^ sw) << 4;
-                float v[8];
-        #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = acc[j + e];
-                if (rsrc) {
-                  if (res_split) {
-                    const uint4 rh = *reinterpret_cast<const uint4*>(rsrc + ch_hi);
-                    const uint4 rl = *reinterpret_cast<const uint4*>(rsrc + ch_lo);
-                    const uint32_t hs[4] = {rh.x, rh.y, rh.z, rh.w}, ls[4] = {rl.x, rl.y, rl.z, rl.w};
-        #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float2 a2 = h2_to_f2(hs[e]), b2 = h2_to_f2(ls[e]);
-                      v[2 * e] += a2.x + b2.x;
-                      v[2 * e + 1] += a2.y + b2.y;
-                    }
-                  } else {
-                    // fp32 residual: values j .. j+7 are the 16-byte chunks j/4 and j/4 + 1 of the row
-                    const float4 r0v = *reinterpret_cast<const float4*>(rsrc + ((static_cast<uint32_t>(j >> 2) ^ sw) << 4));
-                    const float4 r1v = *reinterpret_cast<const float4*>(rsrc + ((static_cast<uint32_t>((j >> 2) + 1) ^ sw) << 4));
-                    v[0] += r0v.x; v[1] += r0v.y; v[2] += r0v.z; v[3] += r0v.w;
-                    v[4] += r1v.x; v[5] += r1v.y; v[6] += r1v.z; v[7] += r1v.w;
-                  }
-                }
-                if (p.relu) {
-        #pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], slope * v[e]);
-                }
-                if (OUT16) {
-                  uint32_t hh[4], ll[4];
-        #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    hh[e] = f2_to_h2_sat(v[2 * e], v[2 * e + 1]);
-                    const float2 back = h2_to_f2(hh[e]);
-                    ll[e] = f2_to_h2_sat(v[2 * e] - back.x, v[2 * e + 1] - back.y);
-                  }
-                  *reinterpret_cast<uint4*>(dst + ch_hi) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
-                  *reinterpret_cast<uint4*>(dst + ch_lo) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
-                } else {
-                  *reinterpret_cast<float4*>(dst + ((static_cast<uint32_t>(j >> 2) ^ sw) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
-                  *reinterpret_cast<float4*>(dst + ((static_cast<uint32_t>((j >> 2) + 1) ^ sw) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
-                }
-              }
-            } else if (OUTH) {
+            if (OUTH) {
               // 64 halves per staging row: 16-byte groups of 8 halves, swizzled like the TMA box
         #pragma unroll
               for (int j = 0; j < 32; j += 8) {
@@ -750,15 +925,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_commit();
           }
         };
-        if constexpr (REGM) {
-#pragma unroll
-          for (int c = 0; c < BN / CW; ++c) {
-            if (c < nchunks) finish_chunk(c);
-          }
-        } else {
 #pragma unroll 1
-          for (int c = 0; c < nchunks; ++c) finish_chunk(c);
-        }
+        for (int c = 0; c < nchunks; ++c) finish_chunk(c);
       }
       // release the accumulator buffer to the MMA warp
       tc_fence_before();
@@ -791,7 +959,7 @@ static int launch_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kThreads + (MODE == kModeSplit3 ? 128 : 0), 1, 1);
+  cfg.blockDim = dim3(kThreads + ((MODE == kModeSplit3 || MODE == kModeF16x3) ? 128 : 0), 1, 1);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -169,9 +169,10 @@ class ResNetStages:
         split-fp16 activations; forward() packs an fp32 input on entry and writes `out` in the format `out` is marked with"""
         for blocks in self.stages:
             for blk in blocks:
-                for name in ("w1", "w2", "w3", "wd"):
-                    if getattr(blk, name, None) is not None:
-                        setattr(blk, name, ops.pack_weights_split16(getattr(blk, name)))
+                for name, sname in (("w1", "s1"), ("w2", "s2"), ("w3", "s3"), ("wd", "sd")):
+                    if getattr(blk, name, None) is not None:     # the FrozenBatchNorm scale goes into the packed weights
+                        setattr(blk, name, ops.pack_weights_split16(getattr(blk, name), scale=getattr(blk, sname)))
+                        setattr(blk, sname, None)
         self.split16 = True
         self._bufs = {}
 

@@ -313,11 +313,14 @@ def split16_decode(p):
     return (g[..., 0, :] + g[..., 1, :]).reshape(p.shape)
 
 
-def pack_weights_split16(w):
+def pack_weights_split16(w, scale=None):
     """w: fp32 weight [rows, K] or [taps, rows, K] (K % 32 == 0) -> split-fp16 tensor of the same shape holding w * 2^e, e
     chosen so that max |w| 2^e lies in [2^13, 2^14) (the low halves of all weights down to 2^-17 of the largest then stay
-    normal fp16 numbers); conv_gemm multiplies the accumulator by 2^-e (exact)."""
+    normal fp16 numbers); conv_gemm multiplies the accumulator by 2^-e (exact). scale [rows]: a per-output-channel factor
+    (FrozenBatchNorm) folded into the weights first -- the precision-3 kernel adds a bias only."""
     assert w.dtype == torch.float32 and w.dim() in (2, 3) and w.shape[-1] % 32 == 0
+    if scale is not None:
+        w = w * scale.to(w.device).float().view(-1, 1)
     m = float(w.abs().max())
     e = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
     e = max(-24, min(e, 40))
@@ -546,6 +549,7 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
         assert fa is not None and fb is not None, \
             "conv_gemm: both operands must be split-fp16 (ops.pack_split16 / pack_weights_split16) or neither (A %s, B %s)" % (
                 "split" if fa is not None else "plain", "split" if fb is not None else "plain")
+        assert scale is None, "conv_gemm: split-fp16 contractions take no scale (fold it: pack_weights_split16(w, scale))"
         d.precision = 3
         d.out_f16 = 1 if is_split16(out) else 0
         d.res_split = 1 if is_split16(residual) else 0

@@ -55,7 +55,7 @@ def _conv_case(dev, n, h, w, cin, cout, ks, dil, relu, res_mode, out_split, seed
     if relu:
         ref = ref.relu()
     a = ops.pack_split16(x.permute(0, 2, 3, 1).contiguous().to(dev))
-    wp = ops.pack_weights_split16(wt.permute(2, 3, 0, 1).reshape(ks * ks, cout, cin).contiguous().to(dev))
+    wp = ops.pack_weights_split16(wt.permute(2, 3, 0, 1).reshape(ks * ks, cout, cin).contiguous().to(dev), scale=scale.to(dev))
     out = torch.full((n, h, w, cout), float("nan"), device=dev)
     if out_split:
         ops.mark_split16(out)
@@ -65,7 +65,7 @@ def _conv_case(dev, n, h, w, cin, cout, ks, dil, relu, res_mode, out_split, seed
         if res_mode == "split":
             ops.pack_split16(r)
     with ops.precision("fp32x3"):
-        ops.conv_gemm(a, wp, out, taps=(ks, ks), dil=dil, pad=pad, scale=scale.to(dev), bias=bias.to(dev),
+        ops.conv_gemm(a, wp, out, taps=(ks, ks), dil=dil, pad=pad, bias=bias.to(dev),      # (the scale is in the packed weights)
                       residual=r, relu=relu, block_n=block_n, stream_k=stream_k)
     torch.cuda.synchronize()
     if out_split:

@@ -28,13 +28,15 @@ x256, x1024 = mk(n, h, w, 256), mk(n, h, w, 1024)
 w33, wrpn, wexp = mk(9, 256, 256) * 0.05, mk(9, 1024, 1024) * 0.02, mk(1, 1024, 256) * 0.1
 o256, o1024, o1024b = torch.zeros(n, h, w, 256, device=dev), torch.zeros(n, h, w, 1024, device=dev), torch.zeros(n, h, w, 1024, device=dev)
 sc, bi = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
-cases = [("res4 3x3 256->256", lambda: ops.conv_gemm(x256, w33, o256, taps=(3, 3), pad=1, scale=sc[:256], bias=bi[:256], relu=True), 2 * n * h * w * 256 * 2304),
+S256, S1024 = sc[:256], sc
+cases = [("res4 3x3 256->256", lambda: ops.conv_gemm(x256, w33, o256, taps=(3, 3), pad=1, scale=S256, bias=bi[:256], relu=True), 2 * n * h * w * 256 * 2304),
          ("rpn 3x3 1024->1024", lambda: ops.conv_gemm(x1024, wrpn, o1024, taps=(3, 3), pad=1, bias=bi, relu=True), 2 * n * h * w * 1024 * 9216),
-         ("res4 1x1 256->1024 + residual", lambda: ops.conv_gemm(x256, wexp, o1024b, scale=sc, bias=bi, residual=x1024, relu=True), 2 * n * h * w * 1024 * 256)]
+         ("res4 1x1 256->1024 + residual", lambda: ops.conv_gemm(x256, wexp, o1024b, scale=S1024, bias=bi, residual=x1024, relu=True), 2 * n * h * w * 1024 * 256)]
 if "--split16" in sys.argv:      # the same three layers in the split-fp16 format ("3xFP16": no split work in the kernel)
     ops.pack_split16(x256), ops.pack_split16(x1024)
     ops.mark_split16(o256), ops.mark_split16(o1024b)
-    w33, wrpn, wexp = (ops.pack_weights_split16(t) for t in (w33, wrpn, wexp))
+    w33, wrpn, wexp = ops.pack_weights_split16(w33, scale=S256), ops.pack_weights_split16(wrpn), ops.pack_weights_split16(wexp, scale=S1024)
+    S256 = S1024 = None      # (folded into the packed weights)
     ops.mark_split16(o1024)
 with ops.precision("fp32x3"):
     for name, fn, flops in cases:
