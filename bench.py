@@ -12,7 +12,8 @@ many key frames a step carries (--frames-per-step: the per-frame branch of n con
 initialisation of mega_core.b200.synth (no checkpoints offline); frames are synthetic.
 
 Arithmetic modes and the headline. The engine has a throughput mode ("f16": fp16 operands / fp32 accumulate) and a
-strict mode ("fp32x3": 3xTF32 split, near-fp32). Both are timed in full at N = 1 and both are replayed over the
+strict mode ("fp32x3": every product as three tensor-core products on operands split hi + lo -- 22 mantissa bits -- with
+round-to-nearest accumulator folds: near-fp32. Since round 2 the split operands are stored as fp16 pairs). Both are timed in full at N = 1 and both are replayed over the
 committed 600x1000 / 42-key-frame fixture of the UNMODIFIED reference (tests/golden/mega_r101_600x1000.pt) inside this
 run: the `parity` block reports, per mode, the distance of the class logits from the reference's and whether the mode
 meets the bar (PARITY_BAR below; the floor it sits on -- the reference's own fp32 vs fp64 vs other-thread-count
@@ -62,12 +63,13 @@ FIXTURE = os.path.join(ROOT, "tests", "golden", "mega_r101_600x1000.pt")
 PARITY_BAR = {"min_matched_frac": 1.0, "logits_p99": 1e-3, "frames_with_equal_det_count": "all"}
 MODES = ("f16", "fp32x3")            # fastest first
 PRECISION_DTYPE = {"f16": "f16 operands / f32 accumulate", "tf32": "tf32 operands / f32 accumulate",
-                   "fp32x3": "3xtf32 split (near-f32) / f32 accumulate"}
+                   "fp32x3": "f16 hi + f16 lo split operands, 3 products (near-f32) / f32 accumulate"}
 KERNEL_NOTE = {"f16": "conv_chain_kernel + conv_gemm_kernel<.., kModeF16> (tcgen05 kind::f16, fp16 operands; same dense peak as "
                       "bf16): all tensor-core launches of the step",
                "tf32": "conv_gemm_kernel<.., kModeTf32> (tcgen05 kind::tf32; TF32 dense peak is half the bf16 figure)",
-               "fp32x3": "conv_gemm_kernel<.., kModeSplit3> (3 tcgen05 kind::tf32 MMAs per product; the bf16 dense peak is the "
-                         "denominator, so frac <= 1/6 by construction)"}
+               "fp32x3": "conv_gemm_kernel<.., kModeF16x3> (3 tcgen05 kind::f16 MMAs per product on split-fp16 operands; the stem "
+                         "runs kModeSplit3 = 3 kind::tf32 MMAs). The bf16 dense peak is the denominator of the ALGORITHMIC "
+                         "FLOP/s, so frac <= 1/3 by construction"}
 
 
 def parse():
@@ -89,7 +91,7 @@ def parse():
     ap.add_argument("--no-wave", action="store_true",
                     help="N > 1: keep the replicated-state schedule (dist_step). Default: every rank replays "
                          "parallel.wave_selfcheck on its own GPU and the run uses the wavefront schedule only if ALL pass")
-    ap.add_argument("--frames-per-step", type=int, default=0, choices=[0, 1, 2, 4],
+    ap.add_argument("--frames-per-step", type=int, default=0, choices=[0, 1, 2, 4, 8],
                     help="N = 1: key frames per step (MegaEngine.stepn_batched); 0 = the default of the build (DEFAULT_FPS)")
     ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
     ap.add_argument("--cpu-sample-frames", type=int, default=3)

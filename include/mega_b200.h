@@ -284,6 +284,17 @@ int mega_relation_softmax_pe(float* logits, void* probs_f16, int n_rows, int ldm
                              const float* boxes_k, const float* wg_host, const float* bg_host,
                              const float* dim_mat_host, const int* m_valid_ptr, int m_host, const int* n_valid_ptr,
                              int n_valid_off, float scale, void* stream);
+/* mega_relation_softmax_f16 / _pe with the probabilities written in the SPLIT-FP16 format (see mega_conv_gemm_desc): `probs`
+ * is a tensor of the logits' shape and byte size (ldm % 32 == 0, 128-byte aligned) -- the A operand of the precision-3
+ * P.V' product of the strict engine. */
+int mega_relation_softmax_split16(float* logits, void* probs, int n_rows, int ldm, const float* boxes_q,
+                                  const float* boxes_k, const float* wg, const float* bg, const float* dim_mat,
+                                  const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off, float scale,
+                                  void* stream);
+int mega_relation_softmax_pe_split16(float* logits, void* probs, int n_rows, int ldm, const float* boxes_q,
+                                     const float* boxes_k, const float* wg_host, const float* bg_host,
+                                     const float* dim_mat_host, const int* m_valid_ptr, int m_host, const int* n_valid_ptr,
+                                     int n_valid_off, float scale, void* stream);
 
 /* ------------------------------------------------------ box-head post-processing
  * softmax -> decode (weights wx..wh) -> clip -> per-class score threshold + NMS -> top max_det.

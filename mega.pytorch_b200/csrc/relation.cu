@@ -24,6 +24,9 @@ struct RelParams {
   float* s;                 // [G][N][ldm] logits in, probabilities out
   __half* p16;              // optional: probabilities are written here as fp16 [G][N][ldm] (A operand of the fp16
                             // P.V' GEMM) instead of in place
+  int p_split;              // p16 != NULL: 0 = plain fp16 probabilities, 1 = the split-fp16 format (include/mega_b200.h): p16 then
+                            // addresses a tensor of the logits' shape and byte size, value e of it = halves 2e - (e & 31) (hi)
+                            // and 2e - (e & 31) + 32 (lo)  (ldm % 32 == 0)
   long long head_stride;    // N * ldm
   int ldm;
   const float* boxes_q;     // [N,4] or NULL (no position term)
@@ -37,6 +40,17 @@ struct RelParams {
   int n_valid_off;          // rows in [n_valid, n_valid_off) are padding; rows >= n_valid_off are live
   float scale;
 };
+
+__device__ __forceinline__ void store_prob16(__half* p16, int p_split, long long e, float pr) {
+  if (p_split) {
+    const __half hi = __float2half_rn(pr);
+    __half* b = p16 + 2 * e - (e & 31);
+    b[0] = hi;
+    b[32] = __float2half_rn(pr - __half2float(hi));
+  } else {
+    p16[e] = __float2half_rn(pr);
+  }
+}
 
 // SMEM_STAGE: the row's [16, ldm] logits live in shared memory between the passes (ldm <= 1024), so the
 // global logits are read once and the probabilities written once.
@@ -183,7 +197,7 @@ relation_softmax_kernel(const RelParams p) {
       float* sp = srow + g * p.head_stride + m;
       const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
       const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
-      if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + g * p.head_stride + m] = __float2half_rn(pr);
+      if (p.p16) store_prob16(p.p16, p.p_split, static_cast<long long>(n) * p.ldm + g * p.head_stride + m, pr);
       else *sp = pr;
     }
   }
@@ -316,7 +330,7 @@ relation_softmax_pe_kernel(const __grid_constant__ RelParamsW pw) {
       float* sp = srow + g * p.head_stride + m;
       const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
       const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
-      if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + g * p.head_stride + m] = __float2half_rn(pr);
+      if (p.p16) store_prob16(p.p16, p.p_split, static_cast<long long>(n) * p.ldm + g * p.head_stride + m, pr);
       else *sp = pr;
     }
   }
@@ -513,7 +527,7 @@ relation_softmax_mma_kernel(const __grid_constant__ RelParamsW pw) {
       float* sp = srow + h * p.head_stride + m;
       const float l = SMEM_STAGE ? stage_s[h * p.ldm + (m < m_valid ? m : 0)] : *sp;
       const float pr = (m < m_valid) ? __expf(l - fin_max[h]) * fin_inv[h] : 0.f;
-      if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + h * p.head_stride + m] = __float2half_rn(pr);
+      if (p.p16) store_prob16(p.p16, p.p_split, static_cast<long long>(n) * p.ldm + h * p.head_stride + m, pr);
       else *sp = pr;
     }
   }
@@ -522,7 +536,7 @@ relation_softmax_mma_kernel(const __grid_constant__ RelParamsW pw) {
 // No position term: one warp per (head, query row); the row (<= 1024 keys) stays in registers, so the
 // logits are read once and the probabilities written once.
 __global__ void __launch_bounds__(256)
-plain_softmax_kernel(float* __restrict__ s, __half* __restrict__ p16, int n_rows, int ldm, long long head_stride,
+plain_softmax_kernel(float* __restrict__ s, __half* __restrict__ p16, int p_split, int n_rows, int ldm, long long head_stride,
                      const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off, float scale) {
   const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -557,7 +571,7 @@ plain_softmax_kernel(float* __restrict__ s, __half* __restrict__ p16, int n_rows
   for (int j = 0; j < 32; ++j) {
     const int m = j * 32 + lane;
     if (m < ldm) {
-      if (p16) p16[g * head_stride + static_cast<long long>(n) * ldm + m] = __float2half_rn(v[j] * inv);
+      if (p16) store_prob16(p16, p_split, g * head_stride + static_cast<long long>(n) * ldm + m, v[j] * inv);
       else row[m] = v[j] * inv;
     }
   }
@@ -567,7 +581,7 @@ plain_softmax_kernel(float* __restrict__ s, __half* __restrict__ p16, int n_rows
 
 using namespace mega;
 
-static int relation_softmax_impl(float* logits, void* probs_f16, int n_rows, int ldm, const float* boxes_q,
+static int relation_softmax_impl(float* logits, void* probs_f16, int p_split, int n_rows, int ldm, const float* boxes_q,
                                  const float* boxes_k, const float* wg, const float* bg, const float* dim_mat,
                                  const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off,
                                  float scale, void* stream_v) {
@@ -579,7 +593,10 @@ static int relation_softmax_impl(float* logits, void* probs_f16, int n_rows, int
   if (n_rows == 0) return MEGA_OK;
   RelParams p;
   p.s = logits;
+  MEGA_ARG_CHECK(!p_split || (ldm % 32 == 0 && (reinterpret_cast<uintptr_t>(probs_f16) & 127) == 0),
+                 "relation_softmax: split-fp16 probabilities need ldm %% 32 == 0 and a 128-byte aligned tensor");
   p.p16 = static_cast<__half*>(probs_f16);
+  p.p_split = p_split;
   p.head_stride = static_cast<long long>(n_rows) * ldm;
   p.ldm = ldm;
   p.boxes_q = boxes_q;
@@ -595,7 +612,7 @@ static int relation_softmax_impl(float* logits, void* probs_f16, int n_rows, int
   if (boxes_q == nullptr && ldm <= 1024) {
     const long long warps = static_cast<long long>(n_rows) * kGroups;
     plain_softmax_kernel<<<static_cast<int>((warps * 32 + 255) / 256), 256, 0, stream>>>(
-        logits, p.p16, n_rows, ldm, p.head_stride, m_valid_ptr, m_host, n_valid_ptr, n_valid_off, scale);
+        logits, p.p16, p_split, n_rows, ldm, p.head_stride, m_valid_ptr, m_host, n_valid_ptr, n_valid_off, scale);
   } else if (ldm <= 1024) {
     const int smem = kGroups * ldm * static_cast<int>(sizeof(float));
     static bool configured = false;
@@ -616,7 +633,7 @@ extern "C" int mega_relation_softmax(float* logits, int n_rows, int ldm, const f
                                      const float* wg, const float* bg, const float* dim_mat, const int* m_valid_ptr,
                                      int m_host, const int* n_valid_ptr, int n_valid_off, float scale,
                                      void* stream_v) {
-  return relation_softmax_impl(logits, nullptr, n_rows, ldm, boxes_q, boxes_k, wg, bg, dim_mat, m_valid_ptr, m_host,
+  return relation_softmax_impl(logits, nullptr, 0, n_rows, ldm, boxes_q, boxes_k, wg, bg, dim_mat, m_valid_ptr, m_host,
                                n_valid_ptr, n_valid_off, scale, stream_v);
 }
 
@@ -625,15 +642,27 @@ extern "C" int mega_relation_softmax_f16(float* logits, void* probs_f16, int n_r
                                          const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off,
                                          float scale, void* stream_v) {
   MEGA_ARG_CHECK(probs_f16 != nullptr, "relation_softmax_f16: probs_f16 is NULL");
-  return relation_softmax_impl(logits, probs_f16, n_rows, ldm, boxes_q, boxes_k, wg, bg, dim_mat, m_valid_ptr, m_host,
+  return relation_softmax_impl(logits, probs_f16, 0, n_rows, ldm, boxes_q, boxes_k, wg, bg, dim_mat, m_valid_ptr, m_host,
                                n_valid_ptr, n_valid_off, scale, stream_v);
 }
 
-extern "C" int mega_relation_softmax_pe(float* logits, void* probs_f16, int n_rows, int ldm, const float* boxes_q,
-                                        const float* boxes_k, const float* wg_host, const float* bg_host,
-                                        const float* dim_mat_host, const int* m_valid_ptr, int m_host,
-                                        const int* n_valid_ptr, int n_valid_off, float scale, void* stream_v) {
+/* same, the probabilities written in the split-fp16 format (a tensor of the logits' shape and byte size) */
+extern "C" int mega_relation_softmax_split16(float* logits, void* probs, int n_rows, int ldm, const float* boxes_q,
+                                             const float* boxes_k, const float* wg, const float* bg, const float* dim_mat,
+                                             const int* m_valid_ptr, int m_host, const int* n_valid_ptr, int n_valid_off,
+                                             float scale, void* stream_v) {
+  MEGA_ARG_CHECK(probs != nullptr, "relation_softmax_split16: probs is NULL");
+  return relation_softmax_impl(logits, probs, 1, n_rows, ldm, boxes_q, boxes_k, wg, bg, dim_mat, m_valid_ptr, m_host,
+                               n_valid_ptr, n_valid_off, scale, stream_v);
+}
+
+static int relation_softmax_pe_impl(float* logits, void* probs_f16, int p_split, int n_rows, int ldm, const float* boxes_q,
+                                    const float* boxes_k, const float* wg_host, const float* bg_host,
+                                    const float* dim_mat_host, const int* m_valid_ptr, int m_host,
+                                    const int* n_valid_ptr, int n_valid_off, float scale, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  MEGA_ARG_CHECK(!p_split || (probs_f16 != nullptr && ldm % 32 == 0 && (reinterpret_cast<uintptr_t>(probs_f16) & 127) == 0),
+                 "relation_softmax_pe: split-fp16 probabilities need ldm %% 32 == 0 and a 128-byte aligned tensor");
   MEGA_ARG_CHECK(logits != nullptr && n_rows >= 0 && ldm > 0 && boxes_q && boxes_k && wg_host && bg_host && dim_mat_host,
                  "relation_softmax_pe: bad arguments");
   MEGA_ARG_CHECK(m_valid_ptr != nullptr || (m_host >= 0 && m_host <= ldm), "relation_softmax_pe: m out of range");
@@ -642,6 +671,7 @@ extern "C" int mega_relation_softmax_pe(float* logits, void* probs_f16, int n_ro
   RelParams& p = pw.b;
   p.s = logits;
   p.p16 = static_cast<__half*>(probs_f16);
+  p.p_split = p_split;
   p.head_stride = static_cast<long long>(n_rows) * ldm;
   p.ldm = ldm;
   p.boxes_q = boxes_q;
@@ -688,4 +718,21 @@ extern "C" int mega_relation_softmax_pe(float* logits, void* probs_f16, int n_ro
   }
   MEGA_CUDA_CHECK(cudaGetLastError());
   return MEGA_OK;
+}
+
+extern "C" int mega_relation_softmax_pe(float* logits, void* probs_f16, int n_rows, int ldm, const float* boxes_q,
+                                        const float* boxes_k, const float* wg_host, const float* bg_host,
+                                        const float* dim_mat_host, const int* m_valid_ptr, int m_host,
+                                        const int* n_valid_ptr, int n_valid_off, float scale, void* stream_v) {
+  return relation_softmax_pe_impl(logits, probs_f16, 0, n_rows, ldm, boxes_q, boxes_k, wg_host, bg_host, dim_mat_host,
+                                  m_valid_ptr, m_host, n_valid_ptr, n_valid_off, scale, stream_v);
+}
+
+/* same, the probabilities written in the split-fp16 format (a tensor of the logits' shape and byte size) */
+extern "C" int mega_relation_softmax_pe_split16(float* logits, void* probs, int n_rows, int ldm, const float* boxes_q,
+                                                const float* boxes_k, const float* wg_host, const float* bg_host,
+                                                const float* dim_mat_host, const int* m_valid_ptr, int m_host,
+                                                const int* n_valid_ptr, int n_valid_off, float scale, void* stream_v) {
+  return relation_softmax_pe_impl(logits, probs, 1, n_rows, ldm, boxes_q, boxes_k, wg_host, bg_host, dim_mat_host,
+                                  m_valid_ptr, m_host, n_valid_ptr, n_valid_off, scale, stream_v);
 }

@@ -450,9 +450,7 @@ class HeadCommon:
         D = self.feat_dim
         q, k, vt = self.Qb[:nq], self.Kb[:nref], self.Vt[ld]
         s = self.S[ld][:16 * nq * ld].view(16, nq, ld)
-        split = getattr(self, "split16_att", False)
-        if split:
-            ops.unmark_split16(s)      # the logits are plain fp32 (the soft-max kernels read and write them in place)
+
         key = (id(att), xq.data_ptr(), nq, refs.data_ptr(), nref, out.data_ptr(), tail is not None, reuse_kv)
         # [Q, K, V', Q.K^T]: the product reads Q (3 back) and K (2 back), so every layer may start once the layer TWO
         # positions back is complete (depth-2 barrier: V' and Q.K^T overlap the tails of K and V')
@@ -470,9 +468,7 @@ class HeadCommon:
                              m_host=nref, n_valid=n_valid, n_valid_off=n_valid_off, probs_f16=pr,
                              host_w=att.host_w if boxes_q is not None else None)
         if pr is not None:
-            s = pr
-        if split:
-            ops.pack_split16(s)        # probabilities -> split-fp16, in place: the A operand of P.V'
+            s = pr                     # fp16 / split-fp16 probabilities: the A operand of P.V'
         with ops.chain(self._chains, ("pv",) + key, self.dev, enabled=self.chained):
             ops.conv_gemm(s.view(16, 1, nq, ld), vt.view(1, D, ld), out.view(1, 1, nq, D), tile=(1, 128), cout=64, k=ld,
                           batch=16, a_n_off=1, b_n_off=64, out_c_off=64, res_c_off=64, bias_z_off=64, bias=att.bv,
@@ -667,6 +663,8 @@ class WindowedEngine(HeadCommon):
                     ops.mark_split16(t)
             for t in self.Vt.values():
                 ops.mark_split16(t)
+            # the soft-max kernels write the probabilities (the A operand of P.V') in the format, beside the fp32 logits
+            self.P = {ld: ops.mark_split16(torch.zeros(t.numel(), device=self.dev)) for ld, t in self.S.items()}
             self.fc_w = [None if w is None else ops.pack_weights_split16(w) for w in self.fc_w]
             self.pred_w = ops.pack_weights_split16(self.pred_w)
             for att in atts:
@@ -788,7 +786,7 @@ class WindowedEngine(HeadCommon):
 class MegaEngine(WindowedEngine, WavefrontMixin):
     """GeneralizedRCNNMEGA._forward_test + MEGAFeatureExtractor test path
     (detector/generalized_rcnn_mega.py:137-225; extractors :657-699, :754-774, :806-829, :885-933)."""
-    MAX_FRAMES_PER_STEP = 4      # key frames whose per-frame branch stepn_batched may run as one batch
+    MAX_FRAMES_PER_STEP = 8      # key frames whose per-frame branch stepn_batched may run as one batch
 
     def __init__(self, sd, cfg=None, device="cuda"):
         cfg = cfg or EngineConfig()

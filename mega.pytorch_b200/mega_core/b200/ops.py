@@ -817,22 +817,28 @@ def transpose_2d(x, out, n_img, rows, cols):
 
 def relation_softmax(logits, n_rows, ldm, scale, boxes_q=None, boxes_k=None, wg=None, bg=None, dim_mat=None,
                      m_valid=None, m_host=0, n_valid=None, n_valid_off=0, probs_f16=None, host_w=None):
-    """in place over fp32 logits [16, n_rows, ldm]; with probs_f16 (fp16, same shape) the probabilities go there"""
+    """in place over fp32 logits [16, n_rows, ldm]; with probs_f16 (fp16, same shape) the probabilities go there -- or, when
+    probs_f16 is an fp32-typed tensor marked split-fp16, in the split-fp16 format"""
+    split = probs_f16 is not None and probs_f16.dtype == torch.float32
+    if split:
+        assert is_split16(probs_f16) and probs_f16.numel() == logits.numel() and ldm % 32 == 0
     if host_w is not None and boxes_q is not None:
         # (wg [16,64], bg [16], dim_mat [8]) as contiguous fp32 HOST tensors: they travel in the kernel parameters
         require_cuda(logits, boxes_q, boxes_k, m_valid, n_valid, probs_f16)
         wg_h, bg_h, dim_h = host_w
         assert not wg_h.is_cuda and wg_h.dtype == torch.float32 and wg_h.is_contiguous() and wg_h.numel() == 1024
-        assert probs_f16 is None or probs_f16.dtype == torch.float16
-        check(lib.mega_relation_softmax_pe(ptr(logits), ptr(probs_f16), n_rows, ldm, ptr(boxes_q), ptr(boxes_k),
+        assert probs_f16 is None or split or probs_f16.dtype == torch.float16
+        fn = lib.mega_relation_softmax_pe_split16 if split else lib.mega_relation_softmax_pe
+        check(fn(ptr(logits), ptr(probs_f16), n_rows, ldm, ptr(boxes_q), ptr(boxes_k),
                                            ptr(wg_h), ptr(bg_h), ptr(dim_h), ptr(m_valid), m_host, ptr(n_valid),
                                            n_valid_off, float(scale), stream_ptr()), "mega_relation_softmax_pe")
         LAUNCHES[0] += 1
         return logits
     require_cuda(logits, boxes_q, boxes_k, wg, bg, dim_mat, m_valid, n_valid, probs_f16)
     if probs_f16 is not None:
-        assert probs_f16.dtype == torch.float16
-        check(lib.mega_relation_softmax_f16(ptr(logits), ptr(probs_f16), n_rows, ldm, ptr(boxes_q), ptr(boxes_k),
+        assert split or probs_f16.dtype == torch.float16
+        fn = lib.mega_relation_softmax_split16 if split else lib.mega_relation_softmax_f16
+        check(fn(ptr(logits), ptr(probs_f16), n_rows, ldm, ptr(boxes_q), ptr(boxes_k),
                                             ptr(wg), ptr(bg), ptr(dim_mat), ptr(m_valid), m_host, ptr(n_valid),
                                             n_valid_off, float(scale), stream_ptr()), "mega_relation_softmax_f16")
     else:
