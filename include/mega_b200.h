@@ -156,6 +156,9 @@ int mega_conv_chain_set_trace2(void* trace_dev, int cta, int level);
  * the number of MMAs accumulated; the kernel restarts the accumulator every `k_blocks` k-blocks (12 MMAs each) and folds
  * the segments into a master accumulator with round-to-nearest adds. 1..64, default 2; returns the previous value. */
 int mega_set_split3_seg_len(int k_blocks);
+/* precision 3: 1 = the A operand goes through tensor memory (tcgen05.cp per staged tile, TS-form MMAs; same results), 0 = both
+ * operands from shared memory. Returns the previous setting. */
+int mega_set_split16_a_tmem(int enable);
 /* TMA fp32->tf32 conversion on load (round-to-nearest) on/off; returns the previous value. */
 int mega_set_tf32_rounding(int enable);
 

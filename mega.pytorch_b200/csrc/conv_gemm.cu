@@ -41,6 +41,7 @@ static EncodeTiledFn get_encode_fn() {
 static int g_tf32_round = 1;  // TMA converts fp32 -> tf32 (round to nearest) while loading
 
 static int g_num_sms = 0;
+static int g_pk_a_tmem = 0;    // 3xFP16: A operand through tensor memory (tcgen05.cp + TS-form MMAs); mega_set_split16_a_tmem
 static int g_seg_len = 4;      // 3xTF32 / 3xFP16: k-blocks per accumulator segment (tools/strict_probe.py: 2 / 4 / 8 -> logits p99 1.8e-4 / 2.3e-4 / 5.3e-4)
 constexpr int kCounterSlots = 65536;   // ints at the head of the workspace
 constexpr int kMinUnits = 4;
@@ -57,6 +58,12 @@ extern "C" long long mega_conv_gemm_workspace_bytes(void) {
 extern "C" int mega_set_split3_seg_len(int k_blocks) {
   int old = g_seg_len;
   if (k_blocks >= 1 && k_blocks <= 64) g_seg_len = k_blocks;
+  return old;
+}
+
+extern "C" int mega_set_split16_a_tmem(int enable) {
+  int old = g_pk_a_tmem;
+  g_pk_a_tmem = enable ? 1 : 0;
   return old;
 }
 
@@ -275,6 +282,7 @@ int encode_conv_gemm_problem(const mega_conv_gemm_desc* d, CUtensorMap* tmA_p, C
   p.stream_k = d->stream_k ? 1 : 0;
   p.seg_len = g_seg_len;
   p.b_lo_tap_off = d->b_lo_tap_off;
+  p.a_tmem = (pk && g_pk_a_tmem) ? 1 : 0;
   p.res_split = d->res_split ? 1 : 0;
   p.acc_scale = (pk && d->acc_scale != 0.f) ? d->acc_scale : 1.f;
   MEGA_ARG_CHECK(tiles <= kCounterSlots, "conv_gemm: %lld output tiles exceed the %d counter slots", tiles, kCounterSlots);

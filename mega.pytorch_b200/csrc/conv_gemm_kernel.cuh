@@ -64,6 +64,8 @@ struct ConvGemmParams {
   int* counters;             // [tiles], zero between launches
   int seg_len;               // 3xTF32 only: k-blocks accumulated in TMEM before the RN fold into the master accumulator
   int b_lo_tap_off;          // 3xTF32 only: > 0: B's low parts are stored as taps [b_lo_tap_off, 2 * b_lo_tap_off) of the B tensor
+  int a_tmem;                // 3xFP16 only: 1 = the MMA warp copies every staged A tile into tensor memory (tcgen05.cp) and issues
+                             // the MMAs in the TS form (A from TMEM, only B fetched from shared memory)
   int res_split;             // 3xFP16 only: the residual tensor is in the split-fp16 format (else fp32)
   float acc_scale;           // 3xFP16 only: the accumulator is multiplied by this power of two first (weights are stored
                              // scaled by its inverse so that their low halves stay normal fp16 numbers)
@@ -188,11 +190,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool REGM = PK;
   constexpr uint32_t kAccBufs = (SEG && !REGM) ? 3 : 2;
   // 3xTF32: three accumulators + two A slabs of 64 columns (hi: 32 columns of K, lo: the next 32)
-  constexpr uint32_t kNeedCols = kAccBufs * BN + (SPLIT3 ? 128 : 0);
+  constexpr uint32_t kNeedCols = kAccBufs * BN + (SPLIT3 ? 128 : 0) + (PK ? 64 : 0);   // 3xFP16: two 32-column A slabs
   static_assert(kNeedCols <= 512, "accumulators + A slabs exceed the 512 TMEM columns");
   constexpr uint32_t kTmemCols = (kNeedCols <= 64) ? 64 : (kNeedCols <= 128) ? 128 : (kNeedCols <= 256) ? 256 : 512;
   constexpr uint32_t kAccStride = (SEG && !REGM) ? BN : kTmemCols / 2;
   constexpr uint32_t kASlab = 3 * BN;        // first column of A slab 0 (3xTF32); slab s at + 64 s
+  constexpr uint32_t kASlabPk = kTmemCols - 64;   // 3xFP16 (a_tmem): slab s = 32 columns at + 32 s: [hi k0 | hi k1 | lo k0 | lo k1] x 8
   // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with the length of the
   // accumulation chain (measured ~1e-3 relative after 3000 k-blocks; ~2e-5 after 32, which the chaotic position
   // embedding of the relation module amplifies to 5e-3 on the final logits). The strict mode therefore restarts the
@@ -334,6 +337,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 umma_tf32_ts(tmem_d, a_lo + 8 * k, bdesc + 2 * k, idesc, 1u);
               }
               umma_commit(&aslab_empty_bar[kbn & 1u]);   // the splitter may overwrite this A slab
+            } else if (PK && p.a_tmem) {
+              // TS form: the four 128 x 32-byte slices of the A tile (hi / lo of the two k-steps) go to a tensor-memory slab by
+              // tcgen05.cp (same descriptors the SS-form MMAs would read them through; cp and mma issued by one thread
+              // execute in order), then the MMAs fetch only B from shared memory: 24 KB of operand reads per k-block
+              // instead of 48 KB (+ 16 KB read once by the copies)
+              const uint32_t a_tm = tmem_base + kASlabPk + (kbn & 1u) * 32u;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) tmem_cp_128x256b(a_tm + 8 * c, adesc + 2 * c);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_f16_ts(tmem_d, a_tm + 8 * k, bdesc + 2 * k, idesc, (kb > s0 || k > 0) ? 1u : 0u);
+                umma_f16_ts(tmem_d, a_tm + 8 * k, bdesc + 4 + 2 * k, idesc, 1u);
+                umma_f16_ts(tmem_d, a_tm + 16 + 8 * k, bdesc + 2 * k, idesc, 1u);
+              }
             } else if (PK) {
               // a staged row = [32 hi halves | 32 lo halves] of 32 K-values: k-step j (16 values) reads hi at byte 32 j and
               // lo at byte 64 + 32 j of the swizzle row (descriptor units of 16 bytes); hi.hi + hi.lo + lo.hi

@@ -40,7 +40,8 @@ def test_pack_unpack_kernels_match_the_torch_restatement_bit_for_bit(cuda_dev):
     assert (err[fin] <= bound[fin]).all()
 
 
-def _conv_case(dev, n, h, w, cin, cout, ks, dil, relu, res_mode, out_split, seed, block_n=None, stream_k=None, wscale=1.0):
+def _conv_case(dev, n, h, w, cin, cout, ks, dil, relu, res_mode, out_split, seed, block_n=None, stream_k=None, wscale=1.0,
+               want_output=False):
     from mega_core.b200 import ops
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(n, cin, h, w, generator=g).relu() * 3.0
@@ -72,6 +73,8 @@ def _conv_case(dev, n, h, w, cin, cout, ks, dil, relu, res_mode, out_split, seed
         out = ops.unpack_split16(out, torch.empty_like(out))
     got = out.permute(0, 3, 1, 2)
     assert torch.isfinite(got).all(), "kernel left unwritten / non-finite outputs"
+    if want_output:
+        return _rel_err(got, ref), got.clone()
     return _rel_err(got, ref)
 
 
@@ -91,6 +94,28 @@ def test_conv_3xfp16_matches_fp64(cuda_dev, case):
     err = _conv_case(cuda_dev, n, h, w, cin, cout, ks, dil, relu, res, osplit, seed=sum(map(hash, map(str, case))) % 1000,
                      block_n=bn, stream_k=sk, wscale=ws)
     assert err < TOL, err
+
+
+@pytest.mark.parametrize("case", [
+    (1, 38, 63, 256, 256, 3, 1, True, None, True, 128, 0, 1.0),
+    (1, 38, 63, 256, 1024, 1, 1, True, "split", True, 128, 0, 1.0),
+    (2, 38, 63, 1024, 256, 1, 1, True, None, True, 128, 1, 1.0),
+    (1, 19, 21, 96, 80, 3, 1, False, None, False, 64, 0, 1.0),
+])
+def test_a_operand_through_tensor_memory_is_bit_identical(cuda_dev, case):
+    """mega_set_split16_a_tmem(1): every staged A tile is copied to tensor memory (tcgen05.cp) and the MMAs run in the TS form --
+    the same products in the same order, so the outputs must not change by a bit"""
+    from mega_core._lib import lib
+    n, h, w, cin, cout, ks, dil, relu, res, osplit, bn, sk, ws = case
+    outs = []
+    for mode in (0, 1):
+        old = lib.mega_set_split16_a_tmem(mode)
+        try:
+            outs.append(_conv_case(cuda_dev, n, h, w, cin, cout, ks, dil, relu, res, osplit, seed=7, block_n=bn, stream_k=sk,
+                                   wscale=ws, want_output=True))
+        finally:
+            lib.mega_set_split16_a_tmem(old)
+    assert outs[0][0] < TOL and torch.equal(outs[0][1], outs[1][1])
 
 
 def test_deep_reduction_as_taps_matches_fp64(cuda_dev):

@@ -48,6 +48,10 @@ if "--split16" in sys.argv and "--more" in sys.argv:
               ("rpn head 1x1 1024->75, block_n 128", lambda: ops.conv_gemm(x1024, whead, ohead, bias=bi[:75], cout=75, block_n=128), 2 * n * h * w * 75 * 1024),
               ("res5 3x3 dil 2 512->512", lambda: ops.conv_gemm(x512, w5, o512, taps=(3, 3), dil=2, pad=2, bias=bi[:512], relu=True), 2 * n * h * w * 512 * 4608),
               ("res5 3x3 dil 2 512->512, 140 CTAs", lambda: ops.conv_gemm(x512, w5, o512, taps=(3, 3), dil=2, pad=2, bias=bi[:512], relu=True, max_ctas=140), 2 * n * h * w * 512 * 4608)]
+if "--a-tmem" in sys.argv:
+    from mega_core._lib import lib
+    lib.mega_set_split16_a_tmem(1)
+    print("A operand through tensor memory (tcgen05.cp + TS-form MMAs)")
 with ops.precision("fp32x3"):
     for name, fn, flops in cases:
         for _ in range(3):

@@ -2,7 +2,7 @@
 bench.py launch, so that tile choices -- hence summation orders, hence parity numbers -- are pinned:
     python tools/tune_all.py            -> gpurun_out/tuned_b200.json  (copy to mega.pytorch_b200/mega_core/b200/)
 Runs the GPU test-suite in-process (its engines autotune every new shape), then the benchmark configurations
-(MEGA R-101 at 600x1000 in f16 with 1 / 2 / 4 key frames per step, fp32x3, tf32; the frame-parallel row splits;
+(MEGA R-101 at 600x1000 in f16 and fp32x3 with 1 / 2 / 4 key frames per step, tf32; the frame-parallel row splits;
 RDN / FGFA), and dumps the union."""
 import os
 import sys
@@ -32,7 +32,7 @@ with torch.no_grad():
         eng.start_video(frames[0], frames[1:13], [frames[(3 * j + 1) % 16] for j in range(10)], w, h)
         for i in range(2):
             eng.step_batched(pairs[i], w, h)
-        if prec == "f16":
+        if prec in ("f16", "fp32x3"):
             for n in (2, 4):
                 eng.stepn_batched(torch.cat([pairs[j] for j in range(n)], 0), w, h)
             pl = torch.stack([eng.ref_payload(pairs[j], w, h) for j in range(2)])
