@@ -91,6 +91,9 @@ def parse():
     ap.add_argument("--no-wave", action="store_true",
                     help="N > 1: keep the replicated-state schedule (dist_step). Default: every rank replays "
                          "parallel.wave_selfcheck on its own GPU and the run uses the wavefront schedule only if ALL pass")
+    ap.add_argument("--pipeline", type=int, default=-1, choices=[-1, 0, 1],
+                    help="N = 1, frames-per-step > 1: overlap the aggregation of a batch of key frames with the per-frame branch of "
+                         "the next batch (MegaEngine.stepn_pipelined / model.forward_frames(prefetch=)); -1 = the build's default")
     ap.add_argument("--frames-per-step", type=int, default=0, choices=[0, 1, 2, 4, 8],
                     help="N = 1: key frames per step (MegaEngine.stepn_batched); 0 = the default of the build (DEFAULT_FPS)")
     ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
@@ -100,6 +103,7 @@ def parse():
     return ap.parse_args()
 
 
+DEFAULT_PIPELINE = 1   # N = 1: the aggregation of a batch overlaps the per-frame branch of the next one (stepn_pipelined)
 DEFAULT_FPS = 4      # key frames per step at N = 1 (the per-frame branch of 4 key frames = one batch of 8 images)
 
 
@@ -313,10 +317,16 @@ class MegaBench:
             batch = batch_dev(i)
             if world > 1:
                 return eng.dist_stepn_wave(batch, w, h)
+            if fps > 1 and pipelined:
+                return eng.stepn_pipelined(batch_dev(i + 1), w, h)      # aggregates batch i, starts the branch of batch i + 1
             if fps > 1:
                 return eng.stepn_batched(batch, w, h)
             return eng.step_batched(batch, w, h)
 
+        # (default: the strict mode only -- the fp16 mode's chain kernels must run on capped, disjoint SM budgets side by side,
+        #  which measured slower than the sequential step: 252 vs 383 key frames/s)
+        pipelined = world == 1 and fps > 1 and (args.pipeline == 1 or (args.pipeline < 0 and DEFAULT_PIPELINE and not eng.chained))
+        res["pipelined"] = bool(pipelined)
         static_in = eng.static_input((2 * fps, 3, h, w))
         state = {"t": t}
 
@@ -324,7 +334,8 @@ class MegaBench:
             """pinned host frames -> device, one step, detections of this rank's key frame(s) back on the host"""
             t0 = state["t"]
             if world == 1 and fps > 1:
-                outs = model.forward_frames([self.infos_next(t0 + j) for j in range(fps)])
+                nxt = [self.infos_next(t0 + fps + j) for j in range(fps)] if pipelined else None
+                outs = model.forward_frames([self.infos_next(t0 + j) for j in range(fps)], prefetch=nxt)
                 state["t"] = t0 + fps
                 return sum(len(o[0].to("cpu")) for o in outs)
             state["t"] = t0 + 1
@@ -600,6 +611,9 @@ def run_mega(args, rank, world):
                                    "of a key frame on its owner, NCCL all-gather of the ROI-feature payloads + one all-gather of "
                                    "the memory increments per relation stage" % world) if R["wave"] else "single GPU",
                    "key_frames_per_step": kf,
+                   "pipelined": ("aggregation of batch i concurrently with the per-frame branch of batch i + 1 (two streams, "
+                                 "MegaEngine.stepn_pipelined; SM caps branch / aggregation: %s)" % (list(R["eng"].PIPE_SMS),))
+                                if R.get("pipelined") else False,
                    "schedule": ("wavefront" if R["wave"] else "replicated-state") if world > 1 else None,
                    "wave_selfcheck": R["wave_note"], "cuda_graph": R["cuda_graph"], "precision": head,
                    "headline_rule": why,
@@ -608,7 +622,7 @@ def run_mega(args, rank, world):
         "e2e": {"value": R["e2e_value"], "unit": "frames/s", "h2d_bytes_per_step": R["h2d"], "d2h_bytes_per_step": R["d2h"],
                 "ms_per_step": R["e2e_ms"] / args.steps, "detections_per_frame": R["detections_per_frame"],
                 "api": "model(images) per key frame" if fps == 1 and world == 1 else
-                       ("model.forward_frames([images] * %d)" % fps if world == 1 else
+                       ("model.forward_frames([images] * %d%s)" % (fps, ", prefetch=next" if R.get("pipelined") else "") if world == 1 else
                         "MegaEngine.dist_step%s (one video stream)" % ("n_wave" if R["fps"] > 1 else "_wave" if R["wave"] else ""))},
         "gpu_launches": int(round(R["launches_per_step"] * args.steps)),
         "parity": {"fixture": "tests/golden/mega_r101_600x1000.pt (unmodified reference, %s key frames)" % (

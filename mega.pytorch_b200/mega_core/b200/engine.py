@@ -755,6 +755,8 @@ class WindowedEngine(HeadCommon):
     #      "ingest" payload -> ring buffers -> aggregation -> detections
     #      (frame-parallel multi-GPU runs all-gather the payloads between the two)
     def _graph_run(self, key, fn):
+        if ops.SM_LIMIT[0] > 0 or ops.WS_LANE[0] != 0:      # captured grids / stream-K workspace lanes are part of a graph
+            key = tuple(key) + ("sm", ops.SM_LIMIT[0], ops.WS_LANE[0])
         if self.use_graph and key not in self._graphs and self._eager_done.get(key, 0) >= 1:
             torch.cuda.synchronize(self.dev)
             graph = torch.cuda.CUDAGraph()
@@ -1090,6 +1092,67 @@ class MegaEngine(WindowedEngine, WavefrontMixin):
             if i < n - 1:
                 det = Detections(det.boxes.clone(), det.scores.clone(), det.labels.clone(), det.count.clone())
             dets.append(det)
+        return dets
+
+    # ---- two launch sequences side by side: the aggregation of a batch of key frames uses the GPU badly on its own (GEMMs of
+    #      300-675 rows = 24-48 tiles on 148 SMs, latency-bound soft-max and NMS kernels: ~25 % of the step at ~1/3 occupancy),
+    #      and the per-frame branch of the NEXT batch does not depend on it. stepn_pipelined issues the two on two streams: the
+    #      block scheduler fills the SMs a draining branch kernel frees with aggregation CTAs and vice versa. PIPE_SMS
+    #      (MEGA_B200_PIPE_SMS="branch,aggregation") optionally caps the persistent grids so that the two sequences own
+    #      disjoint SMs (ops.sm_limit) -- measured on a B200, strict mode, 4 key frames per step (sequential: 18.5 ms):
+    #      no caps 17.65 ms; aggregation capped at 32: 20.7; 132 + 16: 23.7; 140 + 8: 35.1 (a capped aggregation becomes the
+    #      critical path: its kernels are latency-bound, fewer SMs make each of them slower). Default: no caps.
+    PIPE_SMS = tuple(int(v) for v in os.environ.get("MEGA_B200_PIPE_SMS", "0,0").split(","))
+
+    @_with_precision
+    def stepn_pipelined(self, imgs_next, im_w, im_h):
+        """offline streams: start the per-frame branch of the NEXT batch of key frames (imgs_next [2n,3,H,W], or None at the
+        end of the stream) and, meanwhile, aggregate the batch handed in by the PREVIOUS call. Returns that batch's
+        detections like stepn_batched (None on the first call). Same arithmetic as stepn_batched except for the stream-K
+        split points of the capped grids."""
+        # chain kernels (fp16 mode) hold grid-wide barriers: two of them may only run side by side on DISJOINT SM budgets (a
+        # CTA that spins for peers which cannot become resident would deadlock), so that mode always runs capped
+        caps = self.PIPE_SMS
+        if self.chained and not (caps[0] > 0 and caps[1] > 0 and caps[0] + caps[1] + 8 <= 148):
+            caps = (124, 16)
+        main = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_pipe_stream", None) is None:
+            self._pipe_stream = torch.cuda.Stream(device=self.dev)
+            self.payload_q = None
+            self._pipe_n = 0
+        side = self._pipe_stream
+        n_cur = self._pipe_n
+        n_next = 0
+        if imgs_next is not None:
+            n_next = imgs_next.shape[0] // 2
+            assert imgs_next.shape[0] == 2 * n_next and 1 <= n_next <= self.MAX_FRAMES_PER_STEP, imgs_next.shape
+            if getattr(self, "payload_n", None) is None:
+                self.payload_n = torch.zeros(self.MAX_FRAMES_PER_STEP, self.payload_in.numel(), device=self.dev)
+            if self.payload_q is None:
+                self.payload_q = torch.zeros_like(self.payload_n)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.sm_limit(caps[0]):
+                static_in = self.static_input(tuple(imgs_next.shape))
+                if imgs_next.data_ptr() != static_in.data_ptr():
+                    static_in.copy_(imgs_next, non_blocking=True)
+                self._graph_run(("refn", tuple(imgs_next.shape), im_w, im_h),
+                                lambda: self._ref_to_payloads(static_in, im_w, im_h, [self.payload_n[i] for i in range(n_next)]))
+        dets = None
+        if n_cur:
+            dets = []
+            with ops.sm_limit(caps[1], lane=2):
+                for i in range(n_cur):
+                    self.payload_in.copy_(self.payload_q[i], non_blocking=True)
+                    det = self._ingest_next(im_w, im_h)
+                    if i < n_cur - 1:
+                        det = Detections(det.boxes.clone(), det.scores.clone(), det.labels.clone(), det.count.clone())
+                    dets.append(det)
+        if n_next:
+            with torch.cuda.stream(side):
+                side.wait_stream(main)          # the aggregations have read payload_q
+                self.payload_q[:n_next].copy_(self.payload_n[:n_next], non_blocking=True)
+        main.wait_stream(side)
+        self._pipe_n = n_next
         return dets
 
     def step2_batched(self, imgs4, im_w, im_h):

@@ -110,6 +110,10 @@ class chain(object):
     barrier. Results are those of the two sequences run one after the other."""
 
     def __init__(self, cache, key, device, enabled=True, max_ctas=0, interleave=False, depth=1):
+        if SM_LIMIT[0] > 0 or WS_LANE[0] != 0:   # a chain recorded under an SM limit / on another workspace lane is a different chain
+            key = tuple(key) + ("sm", SM_LIMIT[0], WS_LANE[0])
+        if SM_LIMIT[0] > 0:
+            max_ctas = min(max_ctas, SM_LIMIT[0]) if max_ctas > 0 else SM_LIMIT[0]
         self.cache, self.key, self.device, self.max_ctas = cache, key, device, max_ctas
         self.enabled = enabled and CHAINS_ENABLED[0] and _CHAIN_MODE[0] is None
         self.interleave = interleave and self.enabled
@@ -169,6 +173,26 @@ PDL = [True]
 
 _gemm_ws = {}
 WS_LANE = [0]   # launches that may overlap on different streams must use different lanes
+SM_LIMIT = [0]  # > 0: persistent kernels (conv_gemm / chains) launched inside `with sm_limit(n)` take at most n CTAs, so that two
+                # launch sequences on two streams share the GPU by SMs (MegaEngine.stepn_pipelined)
+
+
+class sm_limit(object):
+    """context manager: cap the persistent grids at `n` CTAs and select stream-K workspace lane `lane`"""
+
+    def __init__(self, n, lane=None):
+        self.n, self.lane = int(n), lane
+
+    def __enter__(self):
+        self.saved = (SM_LIMIT[0], WS_LANE[0])
+        SM_LIMIT[0] = self.n
+        if self.lane is not None:
+            WS_LANE[0] = self.lane
+        return self
+
+    def __exit__(self, *a):
+        SM_LIMIT[0], WS_LANE[0] = self.saved
+        return False
 
 
 def gemm_workspace(device):
@@ -569,6 +593,8 @@ def conv_gemm(a, w, out, *, taps=(1, 1), dil=1, pad=0, scale=None, bias=None, re
     d.out_c_off, d.out_n_off, d.res_c_off, d.res_n_off = out_c_off, out_n_off, res_c_off, res_n_off
     d.bias_z_off = bias_z_off
     d.max_ctas = max_ctas
+    if SM_LIMIT[0] > 0:
+        d.max_ctas = min(max_ctas, SM_LIMIT[0]) if max_ctas > 0 else SM_LIMIT[0]
     if d.precision == 1 and batch == 1:
         ps = _PRESPLIT.get(w.data_ptr())
         if ps is not None and ps[0]() is None:

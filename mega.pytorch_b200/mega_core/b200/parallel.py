@@ -129,16 +129,25 @@ def _rand_boxes(gen, n, im_w, im_h):
     return torch.stack([x1, y1, x1 + 10 + torch.rand(n, generator=gen) * 60, y1 + 10 + torch.rand(n, generator=gen) * 60], 1)
 
 
+def _rand_rows(eng, shape, gen, dtype):
+    """seeded feature rows in the engine's row format (the strict engine keeps them split-fp16: ops.split16_encode)"""
+    x = torch.randn(shape, generator=gen) * 0.5
+    if getattr(eng, "split16_att", False):
+        from . import ops
+        return ops.split16_encode(x)
+    return x.to(dtype)
+
+
 def random_state(eng, seed, im_w, im_h):
     """put a MegaEngine into the state of a video whose window and global pool are full (memory still empty)"""
     gen = torch.Generator().manual_seed(seed)
     eng.reset()
     for _ in range(eng.L):
         eng._claim_slot()
-    eng.win_x.copy_((torch.randn(eng.win_x.shape, generator=gen) * 0.5).to(eng.win_x.dtype))
+    eng.win_x.copy_(_rand_rows(eng, eng.win_x.shape, gen, eng.win_x.dtype))
     eng.win_boxes.copy_(_rand_boxes(gen, eng.win_boxes.shape[0], im_w, im_h))
     eng.win_cnt.fill_(eng.KP - 3)
-    eng.glob_x.copy_((torch.randn(eng.glob_x.shape, generator=gen) * 0.5).to(eng.glob_x.dtype))
+    eng.glob_x.copy_(_rand_rows(eng, eng.glob_x.shape, gen, eng.glob_x.dtype))
     eng.glob_pushed = eng.GF
 
 
@@ -147,10 +156,10 @@ def random_payload(eng, seed, im_w, im_h):
     gen = torch.Generator().manual_seed(seed)
     p = torch.zeros_like(eng.payload_in)
     px, pb, pc, pg = eng._payload_views(p)
-    px.copy_((torch.randn(px.shape, generator=gen) * 0.5).to(px.dtype))
+    px.copy_(_rand_rows(eng, px.shape, gen, px.dtype))
     pb.copy_(_rand_boxes(gen, pb.shape[0], im_w, im_h))
     pc.view(torch.int32)[0, 0] = eng.KP - 1 - seed % 4
-    pg.copy_((torch.randn(pg.shape, generator=gen) * 0.5).to(pg.dtype))
+    pg.copy_(_rand_rows(eng, pg.shape, gen, pg.dtype))
     return p
 
 

@@ -116,12 +116,15 @@ class GeneralizedRCNNMEGA(_EngineBacked):
                 det = eng.step_batched(pair, im_w, im_h)
         return [self._to_boxlist(det, im_w, im_h)]
 
-    def forward_frames(self, images_list):
+    def forward_frames(self, images_list, prefetch=None):
         """Offline streams (tools/test_net.py reads every frame from disk, so the frames after `cur` are at hand):
         n consecutive steady-state frames (each the dict forward() takes, frame_category 1) in ONE call. The per-frame
         branch -- backbone / RPN / res5 / ROIAlign / l_fcs[0], a pure function of each frame -- runs as one batch of
         2n images (MegaEngine.stepn_batched), the n aggregations in order. Returns n results, each what forward()
-        returns for that frame; n <= MegaEngine.MAX_FRAMES_PER_STEP."""
+        returns for that frame; n <= MegaEngine.MAX_FRAMES_PER_STEP.
+        prefetch: the images_list of the NEXT call (or None at the end of the stream). The per-frame branch of those frames
+        then runs WHILE this call's frames are aggregated (MegaEngine.stepn_pipelined: two streams sharing the GPU by SMs),
+        and the next call -- which must be given exactly that list -- finds it done."""
         if self.training:
             raise NotImplementedError("the B200 build covers inference (eval mode) only")
         eng = self.engine
@@ -130,13 +133,27 @@ class GeneralizedRCNNMEGA(_EngineBacked):
             "forward_frames takes steady-state frames (one look-ahead local frame and one global frame each)"
         cur = to_image_list(images_list[0]["cur"])
         im_h, im_w = cur.image_sizes[0]
-        with torch.no_grad():
-            buf = eng.static_input((2 * n,) + tuple(cur.tensors.shape[1:]))
-            for i, im in enumerate(images_list):
-                self.end_id = min(getattr(self, "end_id", 0) + 1, getattr(self, "seg_len", 1) - 1)
+
+        def stage(lst):
+            buf = eng.static_input((2 * len(lst),) + tuple(cur.tensors.shape[1:]))
+            for i, im in enumerate(lst):
                 buf[2 * i].copy_(self._host(im["ref_l"][0]), non_blocking=True)
                 buf[2 * i + 1].copy_(self._host(im["ref_g"][0]), non_blocking=True)
-            dets = eng.stepn_batched(buf, im_w, im_h)
+            return buf
+
+        with torch.no_grad():
+            for _ in images_list:
+                self.end_id = min(getattr(self, "end_id", 0) + 1, getattr(self, "seg_len", 1) - 1)
+            pending = getattr(self, "_prefetched", 0)
+            if prefetch is None and not pending:
+                dets = eng.stepn_batched(stage(images_list), im_w, im_h)
+            else:
+                if not pending:                                   # first call of a pipelined stream: its own branch now
+                    eng.stepn_pipelined(stage(images_list), im_w, im_h)
+                else:
+                    assert pending == n, "this call's frames are not the ones the previous call prefetched"
+                dets = eng.stepn_pipelined(stage(prefetch) if prefetch else None, im_w, im_h)
+                self._prefetched = len(prefetch) if prefetch else 0
         out, d2h = [], 0
         for det in dets:
             out.append([self._to_boxlist(det, im_w, im_h)])

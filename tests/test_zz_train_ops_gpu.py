@@ -123,7 +123,8 @@ def test_deform_psroi_pooling_backward(cuda_dev, no_trans):
         assert torch.allclose(gtr.cpu(), ref_tr, atol=2e-4, rtol=1e-3)
 
 
-def test_mega_wavefront_step_equals_replicated_state_step(cuda_dev):
+@pytest.mark.parametrize("precision", ["f16", "fp32x3"])
+def test_mega_wavefront_step_equals_replicated_state_step(cuda_dev, precision):
     """MegaEngine._wave (SURVEY.md section 8e option ii; schedule verified symbolically in
     tests/test_wave_schedule_cpu.py): both ranks of a 2-GPU group played on one device with parallel.play() must give
     the detections and predictor outputs of the sequential owner-mode step BIT for bit, and leave the same memory."""
@@ -137,7 +138,7 @@ def test_mega_wavefront_step_equals_replicated_state_step(cuda_dev):
     steps = 6
 
     def make():
-        e = engine.MegaEngine(sd, engine.EngineConfig(precision="f16"), device=cuda_dev)
+        e = engine.MegaEngine(sd, engine.EngineConfig(precision=precision), device=cuda_dev)
         e.start_video(frames[0], frames[1:13], glob0, w, h)
         return e
 
@@ -147,6 +148,11 @@ def test_mega_wavefront_step_equals_replicated_state_step(cuda_dev):
         k = int(e.cur_cnt.view(-1)[0].item())
         return e.last_pred[:k].clone().cpu(), b, s, l
 
+    # what bench.py runs on every rank before a multi-GPU run adopts the wavefront schedule (seeded rows in the engine's
+    # own row format: split-fp16 in the strict mode)
+    ok, msg = parallel.wave_selfcheck(lambda: engine.MegaEngine(sd, engine.EngineConfig(precision=precision), device=cuda_dev),
+                                      w, h, world=2, groups=2, use_graph=False)
+    assert ok, msg
     ranker = make()
     payloads = [ranker.ref_payload(pair(t), w, h) for t in range(1, steps + 1)]
     solo = make()
@@ -395,3 +401,44 @@ def test_two_key_frames_per_call_on_device(cuda_dev):
     assert ring_worst < 2e-2, ring_worst
     # global pool (75 rows per frame, no boxes kept): a swap inside the first 75 proposals shifts a few rows of one frame
     assert ((a.glob_x.float() - b.glob_x.float()).abs() > 0.05).float().mean().item() < 0.05
+
+
+@pytest.mark.parametrize("precision", ["fp32x3", "f16"])
+def test_pipelined_steps_match_batched_steps(cuda_dev, precision):
+    """MegaEngine.stepn_pipelined: the aggregation of a batch of key frames runs concurrently with the per-frame branch of the
+    next batch (two streams, persistent grids capped so that they share the GPU by SMs). The arithmetic is that of
+    stepn_batched up to the stream-K split points of the capped grids: strict mode -> every detection count equal and the
+    predictor outputs within 2e-3; fp16 mode -> the re-association bound of the tests above. Eager and CUDA-graph replays."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mega_core.b200 import engine, synth
+    from test_engine_gpu import _match_rows
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "mega_r101_192x320.pt"))
+    h, w = gold["h"], gold["w"]
+    sd = synth.make_state_dict(gold["arch"], seed=gold["seed"])
+    frames = [synth.synthetic_frame(i, h, w).to(cuda_dev) for i in range(24)]
+    glob0 = [frames[(3 * j + 1) % 24] for j in range(10)]
+    pair = lambda t: torch.cat([frames[(t + 12) % 24], frames[(5 * t + 3) % 24]], 0)
+    batch = lambda s: torch.cat([pair(1 + 2 * s), pair(2 + 2 * s)], 0)
+    a = engine.MegaEngine(sd, engine.EngineConfig(precision=precision), device=cuda_dev)
+    b = engine.MegaEngine(sd, engine.EngineConfig(precision=precision), device=cuda_dev)
+    for e in (a, b):
+        e.start_video(frames[0], frames[1:13], glob0, w, h)
+        e.use_graph = True
+    steps = 5                       # a graph key runs eagerly once, is captured on its second use, replays from the third
+
+    def snap(e, dets):
+        torch.cuda.synchronize()
+        k = int(e.cur_cnt.view(-1)[0].item())
+        return [int(d.count.item()) for d in dets], e.last_pred[:k].float().cpu(), e.Bq0[:k].cpu()
+
+    want = [snap(a, a.stepn_batched(batch(s), w, h)) for s in range(steps)]
+    assert b.stepn_pipelined(batch(0), w, h) is None
+    got = [snap(b, b.stepn_pipelined(batch(s + 1) if s + 1 < steps else None, w, h)) for s in range(steps)]
+    tol, cnt_tol = (2e-3, 0) if precision == "fp32x3" else (2e-2, 3)
+    for (ca, pa, ba), (cb, pb, bb) in zip(want, got):
+        assert all(abs(x - y) <= cnt_tol for x, y in zip(ca, cb)), (ca, cb)
+        idx = _match_rows(bb, ba)
+        m = idx >= 0
+        assert m.float().mean().item() >= (1.0 if precision == "fp32x3" else 0.95)
+        d = (pb[idx[m], :31] - pa[m, :31]).abs()
+        assert torch.quantile(d.flatten(), 0.99).item() < tol, torch.quantile(d.flatten(), 0.99).item()
