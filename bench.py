@@ -103,7 +103,10 @@ def parse():
     return ap.parse_args()
 
 
-DEFAULT_PIPELINE = 1   # N = 1: the aggregation of a batch overlaps the per-frame branch of the next one (stepn_pipelined)
+DEFAULT_PIPELINE = 0   # --pipeline 1 (N = 1, strict mode): the aggregation of a batch overlaps the per-frame branch of the next one
+                       # (stepn_pipelined): 214 -> 223 key frames/s. Off by default so that the N = 1 line runs the same schedule
+                       # per GPU as the N > 1 lines (whose wavefront step is not pipelined) and the scaling figures compare like
+                       # with like
 DEFAULT_FPS = 4      # key frames per step at N = 1 (the per-frame branch of 4 key frames = one batch of 8 images)
 
 
