@@ -94,7 +94,7 @@ def parse():
     ap.add_argument("--pipeline", type=int, default=-1, choices=[-1, 0, 1],
                     help="N = 1, frames-per-step > 1: overlap the aggregation of a batch of key frames with the per-frame branch of "
                          "the next batch (MegaEngine.stepn_pipelined / model.forward_frames(prefetch=)); -1 = the build's default")
-    ap.add_argument("--frames-per-step", type=int, default=0, choices=[0, 1, 2, 4, 8],
+    ap.add_argument("--frames-per-step", type=int, default=0, choices=[0, 1, 2, 3, 4, 5, 6, 7, 8],
                     help="N = 1: key frames per step (MegaEngine.stepn_batched); 0 = the default of the build (DEFAULT_FPS)")
     ap.add_argument("--prime", type=int, default=-1, help="untimed steady frames before timing (default: fill the memory)")
     ap.add_argument("--cpu-sample-frames", type=int, default=3)
