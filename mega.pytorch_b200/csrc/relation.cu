@@ -41,8 +41,11 @@ struct RelParams {
   float scale;
 };
 
-__device__ __forceinline__ void store_prob16(__half* p16, int p_split, long long e, float pr) {
-  if (p_split) {
+// (SPLIT is a compile-time tag: a run-time test inside the 16-fold unrolled loops of the callers cost the fp16 engine 17-28 %
+//  of its soft-max kernels)
+template <bool SPLIT>
+__device__ __forceinline__ void store_prob16(__half* p16, long long e, float pr) {
+  if (SPLIT) {
     const __half hi = __float2half_rn(pr);
     __half* b = p16 + 2 * e - (e & 31);
     b[0] = hi;
@@ -192,13 +195,22 @@ relation_softmax_kernel(const RelParams p) {
 
   // ---- pass 2: normalise in place; padded key columns get probability 0
   for (int m = tid; m < p.ldm; m += blockDim.x) {
+    if (p.p16 && p.p_split) {
 #pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-      float* sp = srow + g * p.head_stride + m;
-      const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
-      const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
-      if (p.p16) store_prob16(p.p16, p.p_split, static_cast<long long>(n) * p.ldm + g * p.head_stride + m, pr);
-      else *sp = pr;
+      for (int g = 0; g < kGroups; ++g) {
+        const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : srow[g * p.head_stride + m];
+        const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
+        store_prob16<true>(p.p16, static_cast<long long>(n) * p.ldm + g * p.head_stride + m, pr);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        float* sp = srow + g * p.head_stride + m;
+        const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
+        const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
+        if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + g * p.head_stride + m] = __float2half_rn(pr);
+        else *sp = pr;
+      }
     }
   }
 }
@@ -325,13 +337,22 @@ relation_softmax_pe_kernel(const __grid_constant__ RelParamsW pw) {
   }
   __syncthreads();
   for (int m = tid; m < p.ldm; m += kRelThreads) {
+    if (p.p16 && p.p_split) {
 #pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-      float* sp = srow + g * p.head_stride + m;
-      const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
-      const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
-      if (p.p16) store_prob16(p.p16, p.p_split, static_cast<long long>(n) * p.ldm + g * p.head_stride + m, pr);
-      else *sp = pr;
+      for (int g = 0; g < kGroups; ++g) {
+        const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : srow[g * p.head_stride + m];
+        const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
+        store_prob16<true>(p.p16, static_cast<long long>(n) * p.ldm + g * p.head_stride + m, pr);
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        float* sp = srow + g * p.head_stride + m;
+        const float l = SMEM_STAGE ? stage_s[g * p.ldm + (m < m_valid ? m : 0)] : *sp;
+        const float pr = (m < m_valid) ? __expf(l - fin_max[g]) * fin_inv[g] : 0.f;
+        if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + g * p.head_stride + m] = __float2half_rn(pr);
+        else *sp = pr;
+      }
     }
   }
 }
@@ -522,13 +543,22 @@ relation_softmax_mma_kernel(const __grid_constant__ RelParamsW pw) {
   }
   __syncthreads();
   for (int m = tid; m < p.ldm; m += kRelThreads) {
+    if (p.p16 && p.p_split) {
 #pragma unroll
-    for (int h = 0; h < kGroups; ++h) {
-      float* sp = srow + h * p.head_stride + m;
-      const float l = SMEM_STAGE ? stage_s[h * p.ldm + (m < m_valid ? m : 0)] : *sp;
-      const float pr = (m < m_valid) ? __expf(l - fin_max[h]) * fin_inv[h] : 0.f;
-      if (p.p16) store_prob16(p.p16, p.p_split, static_cast<long long>(n) * p.ldm + h * p.head_stride + m, pr);
-      else *sp = pr;
+      for (int h = 0; h < kGroups; ++h) {
+        const float l = SMEM_STAGE ? stage_s[h * p.ldm + (m < m_valid ? m : 0)] : srow[h * p.head_stride + m];
+        const float pr = (m < m_valid) ? __expf(l - fin_max[h]) * fin_inv[h] : 0.f;
+        store_prob16<true>(p.p16, static_cast<long long>(n) * p.ldm + h * p.head_stride + m, pr);
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < kGroups; ++h) {
+        float* sp = srow + h * p.head_stride + m;
+        const float l = SMEM_STAGE ? stage_s[h * p.ldm + (m < m_valid ? m : 0)] : *sp;
+        const float pr = (m < m_valid) ? __expf(l - fin_max[h]) * fin_inv[h] : 0.f;
+        if (p.p16) p.p16[static_cast<long long>(n) * p.ldm + h * p.head_stride + m] = __float2half_rn(pr);
+        else *sp = pr;
+      }
     }
   }
 }
@@ -567,12 +597,20 @@ plain_softmax_kernel(float* __restrict__ s, __half* __restrict__ p16, int p_spli
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
   const float inv = 1.0f / sum;
+  if (p16 && p_split) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const int m = j * 32 + lane;
-    if (m < ldm) {
-      if (p16) store_prob16(p16, p_split, g * head_stride + static_cast<long long>(n) * ldm + m, v[j] * inv);
-      else row[m] = v[j] * inv;
+    for (int j = 0; j < 32; ++j) {
+      const int m = j * 32 + lane;
+      if (m < ldm) store_prob16<true>(p16, g * head_stride + static_cast<long long>(n) * ldm + m, v[j] * inv);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int m = j * 32 + lane;
+      if (m < ldm) {
+        if (p16) p16[g * head_stride + static_cast<long long>(n) * ldm + m] = __float2half_rn(v[j] * inv);
+        else row[m] = v[j] * inv;
+      }
     }
   }
 }
