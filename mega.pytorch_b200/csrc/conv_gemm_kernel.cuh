@@ -14,7 +14,8 @@
 // tap (r,s) is the same rectangle shifted by (r,s)*dilation - pad: a plain 4-D tiled TMA load
 // with out-of-bounds zero fill supplies the padding. K is consumed in slabs of 32 floats
 // (= one 128 B swizzle row) per tap. Warp roles: warp 0 TMA producer, warp 1 MMA issuer,
-// warps 2-5 epilogue (TMEM -> registers -> global).
+// warps 2-5 epilogue (TMEM -> registers -> global); the strict modes add warps 6-9: operand splitters (3xTF32) or a second
+// set of epilogue warps (3xFP16 on split-fp16 tensors, the mode the strict engine runs; see kModeF16x3 below).
 #include "common.cuh"
 #pragma once
 #include "mega_b200.h"
