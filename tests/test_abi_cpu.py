@@ -126,3 +126,41 @@ def test_split16_format_restatement_round_trips_on_the_cpu():
     assert s is not None and 2.0 ** 13 <= float(w.abs().max()) / s < 2.0 ** 14
     assert ((ops.split16_decode(pw) * s).double() - w.double()).abs().max() <= float(w.abs().max()) * 2.0 ** -23
     assert not ops.is_split16(x) and ops.is_split16(ops.mark_split16(torch.zeros(32)))
+
+
+def test_three_product_fp16_split_arithmetic_model():
+    """the arithmetic the strict engine's contractions implement (csrc/conv_gemm_kernel.cuh, kModeF16x3), restated with
+    exact products on the CPU: operands stored as fp16 hi + lo (weights scaled by a power of two first), hi.hi + hi.lo + lo.hi
+    summed exactly -> the representation error alone. It must sit well below one TF32 / fp16 pass (1e-3) and below the
+    truncating 3xTF32 split it replaced; without the weight scaling the low halves of small weights go subnormal."""
+    import torch
+    from mega_core.b200 import ops
+    g = torch.Generator().manual_seed(0)
+    m, n, k = 64, 64, 2304
+    a = (torch.randn(m, k, generator=g).relu() * torch.tensor([0.01, 0.3, 1.0, 5.0])[torch.randint(0, 4, (m, k), generator=g)])
+    w = torch.randn(n, k, generator=g) * 0.02
+    ref = a.double() @ w.double().t()
+
+    def halves(x):                                   # the decoded hi and lo planes of the split-fp16 encoding
+        h = ops.split16_encode(x).view(torch.float16).view(x.shape[0], x.shape[1] // 32, 2, 32).double()
+        return h[:, :, 0, :].reshape(x.shape), h[:, :, 1, :].reshape(x.shape)
+
+    def product(ah, al, bh, bl):
+        return ah @ bh.t() + ah @ bl.t() + al @ bh.t()
+
+    scale = ref.abs().mean()
+    ah, al = halves(a)
+    pw = ops.pack_weights_split16(w)
+    s = ops._split16_weight(pw)
+    h = pw.view(torch.float16).view(n, k // 32, 2, 32).double()
+    bh, bl = h[:, :, 0, :].reshape(n, k), h[:, :, 1, :].reshape(n, k)
+    err_scaled = ((product(ah, al, bh, bl) * s - ref).pow(2).mean().sqrt() / scale).item()
+    bh0, bl0 = halves(w)
+    err_unscaled = ((product(ah, al, bh0, bl0) - ref).pow(2).mean().sqrt() / scale).item()
+    trunc = lambda x: (x.view(torch.int32) & -8192).view(torch.float32)          # what kind::tf32 does to an operand
+    ah3, bh3 = trunc(a), trunc(w)
+    al3, bl3 = trunc(a - ah3), trunc(w - bh3)
+    err_tf32x3 = ((product(ah3.double(), al3.double(), bh3.double(), bl3.double()) - ref).pow(2).mean().sqrt() / scale).item()
+    err_tf32 = ((ah3.double() @ bh3.double().t() - ref).pow(2).mean().sqrt() / scale).item()
+    assert err_scaled < 2e-7 and err_scaled < err_tf32x3 < 1e-6 < err_tf32
+    assert err_unscaled > 3 * err_scaled
