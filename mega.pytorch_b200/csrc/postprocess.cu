@@ -214,7 +214,9 @@ __global__ void __launch_bounds__(1024, 1) box_final_kernel(const FinalParams p)
     }
     thr_key = ~s_prefix;  // back to ascending-score order value
   }
-  // ordered compaction (class-major, proposal index ascending == cat_boxlist order)
+  // ordered compaction: class-major, proposal index ascending inside a class. The reference's filter_results concatenates each
+  // class's boxlist_nms output, i.e. score-descending inside a class (box_head/inference.py:111-136): the SAME detections in a
+  // different order within a class (evaluation sorts by score itself)
   for (int base = 0; base < total_slots; base += blockDim.x) {
     const int i = base + tid;
     const int f = (i < total_slots) && keep[i] && (pf2ord(scores[i]) >= thr_key);
