@@ -891,7 +891,7 @@ class MegaEngine(WindowedEngine, WavefrontMixin):
         g = self.glob_pushed % self.GF
         rows = feats.to(self.dev).float().contiguous()
         if ops.is_split16(self.glob_x):
-            rows = ops.pack_split16(rows)
+            rows = ops.pack_split16(rows, out=torch.empty_like(rows))     # (out of place: `rows` may BE the caller's tensor)
         self.glob_x[g * R:(g + 1) * R].copy_(rows)
         self.glob_pushed += 1
 
